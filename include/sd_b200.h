@@ -1,0 +1,180 @@
+/*
+ * sd_b200.h — C ABI of libsd_b200.so: the sm_100a kernels behind soccerdiffusion_b200.
+ *
+ * The reference (bit-bots/SoccerDiffusion) has NO native/FFI layer: its hot path is Python calling
+ * torch.nn and diffusers.  The drop-in boundary is therefore the Python surface of
+ * soccer_diffusion/ml (mirrored by soccerdiffusion_b200/), and THIS header is what that Python
+ * mirror binds with ctypes (soccerdiffusion_b200/_lib.py; INTEGRATION.md shows the stub).  Each entry
+ * point names the reference code it replaces (paths relative to /root/reference/soccer_diffusion/
+ * unless they start with torch/ or diffusers/).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a positive cudaError_t, or a negative SD_ERR_* code;
+ *     sd_error_string() translates either.  Nothing throws, nothing aborts.
+ *   - all pointers are DEVICE pointers to fp32 unless stated; sizes in elements; `ld*` = row stride
+ *     in elements; `stream` is a cudaStream_t passed as void*.
+ *   - no hidden allocation or global state, except inside an explicit sd_plan (sampler state).
+ *   - not thread-safe per plan; one plan per process/device (matches ml/inference/ros.py:155-163,
+ *     where Inference.step is in a MutuallyExclusiveCallbackGroup).
+ */
+#ifndef SD_B200_H
+#define SD_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SD_B200_ABI_VERSION 1
+
+/* error codes (negative; positive values are cudaError_t) */
+#define SD_E_BAD_ARG (-1)
+#define SD_E_UNSUPPORTED (-2)
+#define SD_E_NO_PLAN (-3)
+
+#define SD_PREC_FP32 0 /* true-fp32 FFMA: the 1e-4 mode */
+#define SD_PREC_BF16 1 /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM: the 2e-2 mode */
+
+#define SD_LAYOUT_MK 0 /* A stored (M x K) row-major */
+#define SD_LAYOUT_KM 1 /* A stored (K x M) row-major */
+#define SD_LAYOUT_NK 0 /* B stored (N x K) row-major (torch Linear weight) */
+#define SD_LAYOUT_KN 1 /* B stored (K x N) row-major */
+
+#define SD_ACT_NONE 0
+#define SD_ACT_GELU 1 /* exact erf GELU (activation="gelu" in base.py:36 / decoder.py:31) */
+
+int sd_abi_version(void);
+const char* sd_error_string(int code);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused GEMM:  C = epilogue( opA(A) * opB(B) ).
+ * Replaces nn.Linear / nn.Conv1d(k=stride=patch) / the packed in_proj of nn.MultiheadAttention and
+ * their autograd (encoder/base.py:28,49; decoder.py:23,36,48,54; torch/nn/functional.py:5849-5855),
+ * with nn.LayerNorm folded into the operand load (norm_first layers, torch/nn/modules/
+ * transformer.py:944-950, 1131-1143), and bias / erf-GELU / dropout / positional encoding
+ * (misc.py:57-65) / residual add folded into the store.
+ */
+typedef struct sd_gemm_desc {
+    const float* A; long long lda; int a_layout;
+    const float* B; long long ldb; int b_layout;
+    float* C; long long ldc;
+    int M, N, K;
+    int precision;               /* SD_PREC_* */
+    /* LayerNorm-on-load of the activation operand (A when MK; B when A is KM and B is KN): */
+    const float* ln_mean; const float* ln_rstd; const float* ln_gamma; const float* ln_beta;
+    /* epilogue, applied in this order: */
+    float alpha;                 /* 0 means 1 */
+    const float* bias;           /* [N] */
+    float* pre_out; long long ldp;             /* store value before activation (for backward) */
+    int act;                     /* SD_ACT_* */
+    const float* gelu_grad_src; long long ldg; /* multiply by gelu'(src[m][n]) (FFN backward) */
+    float dropout_p; unsigned long long dropout_seed; unsigned int dropout_stream; /* element idx = m*N+n */
+    const float* pe; int pe_period;            /* + pe[m % period][n]  (table is [period][N]) */
+    const float* residual; long long ldr;      /* + residual[m][n] */
+    int accumulate;              /* C += result instead of C = result */
+} sd_gemm_desc;
+
+int sd_gemm(const sd_gemm_desc* desc, void* stream);
+
+/* LayerNorm statistics / backward (eps as nn.LayerNorm: 1e-5). d in {32,64,128,256,512}. */
+int sd_ln_stats(const float* x, long long ld, long long M, int d, float* mean, float* rstd, float eps, void* stream);
+int sd_ln_bwd(const float* g, long long ldg, const float* x, long long ldx, const float* mean, const float* rstd,
+              const float* gamma, const float* dres, long long ldres, float* dx, long long lddx, float* dgamma,
+              float* dbeta, long long M, int d, void* stream);
+
+/* Attention core softmax(QK^T/sqrt(dh))V over packed head slices; rows are (b*T+t) / (b*M+m), head h
+ * occupies columns [h*dh,(h+1)*dh).  Replaces F.scaled_dot_product_attention inside
+ * nn.MultiheadAttention (torch/nn/functional.py:6623-6690). dh in {4,8,16,32,64,128}.
+ * lse: (B,H,T) log-sum-exp saved for the backward pass (may be NULL in inference). */
+int sd_attention_fwd(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv,
+                     float* O, long long ldo, float* lse, int B, int H, int T, int M, int dh, float dropout_p,
+                     unsigned long long seed, unsigned int stream_id, void* stream);
+int sd_attention_bwd(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv,
+                     const float* O, long long ldo, const float* dO, long long lddo, const float* lse, float* dQ,
+                     long long lddq, float* dK, long long lddk, float* dV, long long lddv, int B, int H, int T, int M,
+                     int dh, float dropout_p, unsigned long long seed, unsigned int stream_id, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Elementwise / scheduler kernels
+ */
+/* StepToken.forward (ml/model/misc.py:25-35): out[b] = [sin(t f) | cos(t f) | token]; t int64 or f32 */
+int sd_step_token(const void* t, int t_is_float, const float* freqs, const float* token, float* out, long long ld_out,
+                  int B, int d, void* stream);
+int sd_step_token_bwd(const float* dout, long long ld, int B, int d, float* dtoken, void* stream);
+/* Normalizer.normalize (dataset/pytorch.py:410-411) + DDIMScheduler.add_noise (train.py:204,218) */
+int sd_q_sample(const float* joint_command, const float* mean, const float* std, const float* noise, const long long* t,
+                const float* alphas_cumprod, int n_train, float* x0_out, float* xt_out, int B, int inner, int J,
+                void* stream);
+/* DDIMScheduler.step, eta=0 (ros.py:310, distill.py:189, plot.py:131) with host-side sqrt coefficients */
+int sd_ddim_step(const float* x, const float* eps, float* prev, float* x0_pred, long long n, float sqrt_beta_t,
+                 float sqrt_alpha_t, float sqrt_alpha_prev, float sqrt_beta_prev, void* stream);
+/* F.mse_loss (train.py:229, distill.py:198) forward/backward */
+int sd_mse_fwd(const float* pred, const float* target, long long n, float* loss_out, void* stream);
+int sd_mse_bwd(const float* pred, const float* target, long long n, const float* grad_loss, float* grad_pred,
+               void* stream);
+/* Normalizer.normalize (mode 0) / denormalize (mode 1) (dataset/pytorch.py:410-414; ros.py:313) */
+int sd_affine_joints(const float* x, const float* mean, const float* std, float* out, long long n, int J, int mode,
+                     void* stream);
+/* torch.optim.AdamW step over one flat buffer (train.py:162,239) */
+int sd_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step, float grad_scale, void* stream);
+/* GameStateEncoder (ml/model/encoder/game_state.py:27) gather + its gradient */
+int sd_gather_rows(const float* table, const long long* idx, int rows, float* out, long long ld_out, int B, int d,
+                   int* err_flag, void* stream);
+int sd_scatter_add_rows(const float* dout, long long ld, const long long* idx, int rows, float* dtable, int B, int d,
+                        void* stream);
+/* bias gradients: out[n] += sum_m x[m][n] */
+int sd_colsum_accum(const float* x, long long ld, long long M, int N, float* out, void* stream);
+/* torch.cat(context + [step_token], dim=1) (ml/model/model.py:176) as strided copies; and its gradient */
+int sd_copy_rows(const float* src, long long src_batch_stride, long long src_ld, float* dst, long long dst_batch_stride,
+                 long long dst_ld, int B, int rows, int cols, int accumulate, void* stream);
+int sd_add(const float* a, const float* b, float* y, long long n, void* stream);
+/* the exact keep/scale factors the fused kernels apply for dropout stream `stream_id` */
+int sd_dropout_mask(float* out, long long n, float p, unsigned long long seed, unsigned int stream_id, void* stream);
+/* y = x * (that factor): re-applies a forward dropout mask in the backward pass */
+int sd_dropout_apply(const float* x, float* y, long long n, float p, unsigned long long seed, unsigned int stream_id,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Persistent DDIM sampler (ros.py:301-310, distill.py:179-189): one launch = all steps.
+ */
+typedef struct sd_plan sd_plan;
+
+typedef struct sd_plan_config {
+    int d;          /* hidden_dim */
+    int heads;      /* 4 (model.py:115) */
+    int layers;     /* num_decoder_layers */
+    int T;          /* trajectory_prediction_length (<= 32) */
+    int J;          /* num_joints */
+    int ctx_tokens; /* context tokens WITHOUT the step token (311 at default.yaml) */
+} sd_plan_config;
+
+/* reference-format (state_dict) tensors of one nn.TransformerDecoderLayer */
+typedef struct sd_decoder_layer_weights {
+    const float *sa_in_w, *sa_in_b, *sa_out_w, *sa_out_b;   /* self_attn.{in_proj_weight (3d,d), in_proj_bias, out_proj.*} */
+    const float *ca_in_w, *ca_in_b, *ca_out_w, *ca_out_b;   /* multihead_attn.* */
+    const float *lin1_w, *lin1_b, *lin2_w, *lin2_b;
+    const float *norm1_w, *norm1_b, *norm2_w, *norm2_b, *norm3_w, *norm3_b;
+} sd_decoder_layer_weights;
+
+int sd_plan_create(const sd_plan_config* cfg, sd_plan** out);
+int sd_plan_destroy(sd_plan* plan);
+/* (re)pack weights after load_state_dict / optimizer steps */
+int sd_plan_set_layer(sd_plan* plan, int layer, const sd_decoder_layer_weights* w, void* stream);
+int sd_plan_set_io(sd_plan* plan, const float* emb_w, const float* emb_b, const float* fc_w, const float* fc_b,
+                   const float* pe, const float* step_freqs, const float* step_token, const float* mean,
+                   const float* std, void* stream);
+/* DDIMScheduler.set_timesteps: HOST arrays timesteps[num_steps], coef[num_steps][4] =
+ * {sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev)}; tabulates the step-token K/V rows */
+int sd_plan_set_schedule(sd_plan* plan, int num_steps, const long long* timesteps_host, const float* coef_host,
+                         void* stream);
+/* model.encode_input_data output, concatenated (B, ctx_tokens, d): projects K/V for all layers once */
+int sd_plan_set_context(sd_plan* plan, const float* ctx, int B, void* stream);
+/* x_T (B,T,J) -> x_0 (B,T,J); eps_trace optional (steps,B,T,J); denormalize: x*std+mean (ros.py:313) */
+int sd_plan_sample(sd_plan* plan, const float* x_T, float* x_out, float* eps_trace, int denormalize, void* stream);
+/* one forward_with_context (model.py:159-179) against the cached context, per-sample t */
+int sd_plan_denoise(sd_plan* plan, const float* x, const void* t, int t_is_float, float* eps_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SD_B200_H */

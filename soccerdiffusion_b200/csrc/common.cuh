@@ -1,0 +1,91 @@
+// Shared device helpers for the sm_100a kernels of soccerdiffusion_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <math.h>
+
+#define SD_OK 0
+#define SD_ERR_BAD_ARG (-1)
+#define SD_ERR_UNSUPPORTED (-2)
+#define SD_ERR_NO_PLAN (-3)
+
+#define SD_LAUNCH_CHECK()                         \
+    do {                                          \
+        cudaError_t e__ = cudaGetLastError();     \
+        if (e__ != cudaSuccess) return (int)e__;  \
+    } while (0)
+
+#define SD_CUDA(x)                                \
+    do {                                          \
+        cudaError_t e__ = (x);                    \
+        if (e__ != cudaSuccess) return (int)e__;  \
+    } while (0)
+
+namespace sd {
+
+constexpr int kWarp = 32;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// exact (erf) GELU — torch.nn.functional.gelu(approximate="none")
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// d/dx gelu(x) = Phi(x) + x * phi(x)
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+
+// Stateless counter-based RNG for dropout: one 32-bit draw per (seed, stream, element).
+// (splitmix64 finaliser; the same function is exported through sd_dropout_mask so a test can
+// hand the oracle exactly the masks the fused kernels used.)
+__host__ __device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint32_t stream, uint64_t idx) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1) + ((uint64_t)stream << 40);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (uint32_t)(z >> 32);
+}
+// returns 0 (dropped) or 1/(1-p) (kept)
+__host__ __device__ __forceinline__ float dropout_scale(uint64_t seed, uint32_t stream, uint64_t idx, uint32_t thresh,
+                                                        float inv_keep) {
+    return hash_u32(seed, stream, idx) >= thresh ? inv_keep : 0.0f;
+}
+__host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
+    double t = (double)p * 4294967296.0;
+    if (t < 0) t = 0;
+    if (t > 4294967295.0) t = 4294967295.0;
+    return (uint32_t)t;
+}
+
+struct Dropout {
+    uint64_t seed;
+    uint32_t stream;
+    uint32_t thresh;   // 0 => disabled
+    float inv_keep;
+    __host__ __device__ __forceinline__ float operator()(uint64_t idx) const {
+        return thresh == 0 ? 1.0f : dropout_scale(seed, stream, idx, thresh, inv_keep);
+    }
+};
+static inline Dropout make_dropout(float p, uint64_t seed, uint32_t stream) {
+    Dropout d;
+    d.seed = seed;
+    d.stream = stream;
+    d.thresh = (p > 0.f) ? dropout_threshold(p) : 0u;
+    d.inv_keep = (p > 0.f) ? 1.0f / (1.0f - p) : 1.0f;
+    return d;
+}
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace sd

@@ -1,0 +1,427 @@
+"""Autograd nodes of the hot path.  One ``torch.autograd.Function`` per transformer *stack* (an
+encoder with its embedding, the whole denoiser), so that residual joins, LayerNorm, bias and
+activation never appear as separate framework kernels: forward and backward are sequences of
+libsd_b200 launches.
+
+Reference semantics restated here (paths under /root/reference/soccer_diffusion/):
+  BaseEncoder.forward            ml/model/encoder/base.py:41-53
+  DiffusionActionGenerator       ml/model/decoder.py:38-54
+  pre-LN encoder / decoder layer torch/nn/modules/transformer.py:944-950, 1131-1143
+  packed in_proj of MHA          torch/nn/functional.py:5798-5856
+  context concat + StepToken     ml/model/model.py:173-176, ml/model/misc.py:25-35
+  mse_loss / add_noise           ml/training/train.py:218,229
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import ops
+from .ops import ACT_GELU, KM, KN, MK, NK
+
+ENC_PARAMS_PER_LAYER = 12   # in_w,in_b,out_w,out_b,l1_w,l1_b,l2_w,l2_b,n1_w,n1_b,n2_w,n2_b
+DEC_PARAMS_PER_LAYER = 18   # sa(4) ca(4) l1_w,l1_b,l2_w,l2_b n1(2) n2(2) n3(2)
+
+
+@dataclass
+class RunCfg:
+    precision: int = ops.PREC_FP32
+    p: float = 0.0          # dropout probability (0 in eval)
+    seed: int = 0
+    stream_base: int = 0    # dropout stream namespace of this stack
+
+    def drop(self, site: int):
+        return (self.p, self.seed, self.stream_base + site) if self.p > 0.0 else None
+
+
+def _empty(shape, like):
+    return torch.empty(shape, device=like.device, dtype=torch.float32)
+
+
+def _p(t, off=0):
+    return t.data_ptr() + 4 * off
+
+
+# --------------------------------------------------------------------------------------------------
+# blocks (forward returns (y, saved); backward returns dx and accumulates parameter grads)
+
+
+def _sa_fwd(x, B, T, H, in_w, in_b, out_w, out_b, n_w, n_b, cfg: RunCfg, site: int, save: bool):
+    d = x.shape[-1]
+    M = B * T
+    mean, rstd = ops.ln_stats(x, d)
+    qkv = _empty((M, 3 * d), x)
+    ops.gemm(x, d, MK, in_w, d, NK, qkv, 3 * d, M, 3 * d, d, precision=cfg.precision, ln=(mean, rstd, n_w, n_b), bias=in_b)
+    attn = _empty((M, d), x)
+    lse = _empty((B, H, T), x) if save else None
+    ops.attention_fwd(_p(qkv), 3 * d, _p(qkv, d), 3 * d, _p(qkv, 2 * d), 3 * d, _p(attn), d,
+                      None if lse is None else _p(lse), B, H, T, T, d // H, cfg.drop(site))
+    y = _empty((M, d), x)
+    ops.gemm(attn, d, MK, out_w, d, NK, y, d, M, d, d, precision=cfg.precision, bias=out_b, dropout=cfg.drop(site + 1),
+             residual=x, ldr=d)
+    return y, ((x, mean, rstd, qkv, attn, lse) if save else None)
+
+
+def _sa_bwd(dy, saved, B, T, H, in_w, out_w, n_w, n_b, g_in_w, g_in_b, g_out_w, g_out_b, g_n_w, g_n_b, cfg: RunCfg,
+            site: int):
+    x, mean, rstd, qkv, attn, lse = saved
+    d = x.shape[-1]
+    M = B * T
+    g1 = dy if cfg.p == 0.0 else ops.dropout_apply(dy, cfg.p, cfg.seed, cfg.stream_base + site + 1)
+    ops.colsum_accum(g1, d, M, d, g_out_b)
+    ops.gemm(g1, d, KM, attn, d, KN, g_out_w, d, d, d, M, precision=cfg.precision, accumulate=True)
+    dattn = _empty((M, d), x)
+    ops.gemm(g1, d, MK, out_w, d, KN, dattn, d, M, d, d, precision=cfg.precision)
+    dqkv = _empty((M, 3 * d), x)
+    ops.attention_bwd(_p(qkv), 3 * d, _p(qkv, d), 3 * d, _p(qkv, 2 * d), 3 * d, _p(attn), d, _p(dattn), d, _p(lse),
+                      _p(dqkv), 3 * d, _p(dqkv, d), 3 * d, _p(dqkv, 2 * d), 3 * d, B, H, T, T, d // H, cfg.drop(site))
+    ops.colsum_accum(dqkv, 3 * d, M, 3 * d, g_in_b)
+    ops.gemm(dqkv, 3 * d, KM, x, d, KN, g_in_w, d, 3 * d, d, M, precision=cfg.precision, ln=(mean, rstd, n_w, n_b),
+             accumulate=True)
+    dxn = _empty((M, d), x)
+    ops.gemm(dqkv, 3 * d, MK, in_w, d, KN, dxn, d, M, d, 3 * d, precision=cfg.precision)
+    dx = _empty((M, d), x)
+    ops.ln_bwd(dxn, x, mean, rstd, n_w, dy, dx, g_n_w, g_n_b, M, d)
+    return dx
+
+
+def _ffn_fwd(x, l1_w, l1_b, l2_w, l2_b, n_w, n_b, cfg: RunCfg, site: int, save: bool):
+    d = x.shape[-1]
+    ff = l1_w.shape[0]
+    M = x.shape[0]
+    mean, rstd = ops.ln_stats(x, d)
+    hpre = _empty((M, ff), x) if save else None
+    hact = _empty((M, ff), x)
+    ops.gemm(x, d, MK, l1_w, d, NK, hact, ff, M, ff, d, precision=cfg.precision, ln=(mean, rstd, n_w, n_b), bias=l1_b,
+             pre_out=hpre, ldp=ff, act=ACT_GELU, dropout=cfg.drop(site))
+    y = _empty((M, d), x)
+    ops.gemm(hact, ff, MK, l2_w, ff, NK, y, d, M, d, ff, precision=cfg.precision, bias=l2_b, dropout=cfg.drop(site + 1),
+             residual=x, ldr=d)
+    return y, ((x, mean, rstd, hpre, hact) if save else None)
+
+
+def _ffn_bwd(dy, saved, l1_w, l2_w, n_w, n_b, g_l1_w, g_l1_b, g_l2_w, g_l2_b, g_n_w, g_n_b, cfg: RunCfg, site: int):
+    x, mean, rstd, hpre, hact = saved
+    d = x.shape[-1]
+    ff = l1_w.shape[0]
+    M = x.shape[0]
+    g = dy if cfg.p == 0.0 else ops.dropout_apply(dy, cfg.p, cfg.seed, cfg.stream_base + site + 1)
+    ops.colsum_accum(g, d, M, d, g_l2_b)
+    ops.gemm(g, d, KM, hact, ff, KN, g_l2_w, ff, d, ff, M, precision=cfg.precision, accumulate=True)
+    dhpre = _empty((M, ff), x)
+    ops.gemm(g, d, MK, l2_w, ff, KN, dhpre, ff, M, ff, d, precision=cfg.precision, gelu_grad_src=hpre, ldg=ff,
+             dropout=cfg.drop(site))
+    ops.colsum_accum(dhpre, ff, M, ff, g_l1_b)
+    ops.gemm(dhpre, ff, KM, x, d, KN, g_l1_w, d, ff, d, M, precision=cfg.precision, ln=(mean, rstd, n_w, n_b),
+             accumulate=True)
+    dxn = _empty((M, d), x)
+    ops.gemm(dhpre, ff, MK, l1_w, d, KN, dxn, d, M, d, ff, precision=cfg.precision)
+    dx = _empty((M, d), x)
+    ops.ln_bwd(dxn, x, mean, rstd, n_w, dy, dx, g_n_w, g_n_b, M, d)
+    return dx
+
+
+def _ca_fwd(x, mem, B, T, Mm, H, in_w, in_b, out_w, out_b, n_w, n_b, cfg: RunCfg, site: int, save: bool):
+    """x (B*T,d) queries (pre-LN), mem (B*Mm,d) keys/values (NOT layer-normed; transformer.py:1137)."""
+    d = x.shape[-1]
+    Mq = B * T
+    mean, rstd = ops.ln_stats(x, d)
+    q = _empty((Mq, d), x)
+    ops.gemm(x, d, MK, in_w, d, NK, q, d, Mq, d, d, precision=cfg.precision, ln=(mean, rstd, n_w, n_b), bias=in_b)
+    kv = _empty((B * Mm, 2 * d), x)
+    ops.gemm(mem, d, MK, _p(in_w, d * d), d, NK, kv, 2 * d, B * Mm, 2 * d, d, precision=cfg.precision, bias=_p(in_b, d))
+    attn = _empty((Mq, d), x)
+    lse = _empty((B, H, T), x) if save else None
+    ops.attention_fwd(_p(q), d, _p(kv), 2 * d, _p(kv, d), 2 * d, _p(attn), d, None if lse is None else _p(lse), B, H, T,
+                      Mm, d // H, cfg.drop(site))
+    y = _empty((Mq, d), x)
+    ops.gemm(attn, d, MK, out_w, d, NK, y, d, Mq, d, d, precision=cfg.precision, bias=out_b, dropout=cfg.drop(site + 1),
+             residual=x, ldr=d)
+    return y, ((x, mean, rstd, q, kv, attn, lse) if save else None)
+
+
+def _ca_bwd(dy, saved, mem, dmem, B, T, Mm, H, in_w, out_w, n_w, n_b, g_in_w, g_in_b, g_out_w, g_out_b, g_n_w, g_n_b,
+            cfg: RunCfg, site: int):
+    x, mean, rstd, q, kv, attn, lse = saved
+    d = x.shape[-1]
+    Mq = B * T
+    g1 = dy if cfg.p == 0.0 else ops.dropout_apply(dy, cfg.p, cfg.seed, cfg.stream_base + site + 1)
+    ops.colsum_accum(g1, d, Mq, d, g_out_b)
+    ops.gemm(g1, d, KM, attn, d, KN, g_out_w, d, d, d, Mq, precision=cfg.precision, accumulate=True)
+    dattn = _empty((Mq, d), x)
+    ops.gemm(g1, d, MK, out_w, d, KN, dattn, d, Mq, d, d, precision=cfg.precision)
+    dq = _empty((Mq, d), x)
+    dkv = _empty((B * Mm, 2 * d), x)
+    ops.attention_bwd(_p(q), d, _p(kv), 2 * d, _p(kv, d), 2 * d, _p(attn), d, _p(dattn), d, _p(lse), _p(dq), d, _p(dkv),
+                      2 * d, _p(dkv, d), 2 * d, B, H, T, Mm, d // H, cfg.drop(site))
+    # q projection (rows 0:d of in_proj) and k/v projection (rows d:3d)
+    ops.colsum_accum(dq, d, Mq, d, g_in_b)
+    ops.colsum_accum(dkv, 2 * d, B * Mm, 2 * d, _p(g_in_b, d))
+    ops.gemm(dq, d, KM, x, d, KN, g_in_w, d, d, d, Mq, precision=cfg.precision, ln=(mean, rstd, n_w, n_b), accumulate=True)
+    ops.gemm(dkv, 2 * d, KM, mem, d, KN, _p(g_in_w, d * d), d, 2 * d, d, B * Mm, precision=cfg.precision, accumulate=True)
+    if dmem is not None:
+        ops.gemm(dkv, 2 * d, MK, _p(in_w, d * d), d, KN, dmem, d, B * Mm, d, 2 * d, precision=cfg.precision,
+                 accumulate=True)
+    dxn = _empty((Mq, d), x)
+    ops.gemm(dq, d, MK, in_w, d, KN, dxn, d, Mq, d, d, precision=cfg.precision)
+    dx = _empty((Mq, d), x)
+    ops.ln_bwd(dxn, x, mean, rstd, n_w, dy, dx, g_n_w, g_n_b, Mq, d)
+    return dx
+
+
+def _zero_grads(params):
+    """One flat zeroed buffer viewed as per-parameter gradients."""
+    total = sum(p.numel() for p in params)
+    flat = torch.zeros(total, device=params[0].device, dtype=torch.float32)
+    views, off = [], 0
+    for p in params:
+        # keep every view 16-byte aligned for the vectorised paths
+        views.append(flat[off: off + p.numel()].view_as(p))
+        off += p.numel()
+    return views
+
+
+# --------------------------------------------------------------------------------------------------
+class EncoderStackFn(torch.autograd.Function):
+    """Conv1d patch embedding (as a GEMM) + PE + L pre-LN encoder layers (base.py:49-53)."""
+
+    @staticmethod
+    def forward(ctx, cfg: RunCfg, B: int, S: int, H: int, pe, x_in, emb_w, emb_b, *layer_params):
+        d = emb_w.shape[0]
+        Kin = emb_w.shape[1]
+        M = B * S
+        L = len(layer_params) // ENC_PARAMS_PER_LAYER
+        save = any(ctx.needs_input_grad)  # grad mode is always off inside forward(); this reflects the caller's
+        h = _empty((M, d), x_in)
+        ops.gemm(x_in, Kin, MK, emb_w, Kin, NK, h, d, M, d, Kin, precision=cfg.precision, bias=emb_b, pe=pe, pe_period=S)
+        acts = []
+        for l in range(L):
+            in_w, in_b, out_w, out_b, l1_w, l1_b, l2_w, l2_b, n1_w, n1_b, n2_w, n2_b = layer_params[
+                l * ENC_PARAMS_PER_LAYER: (l + 1) * ENC_PARAMS_PER_LAYER]
+            h, s1 = _sa_fwd(h, B, S, H, in_w, in_b, out_w, out_b, n1_w, n1_b, cfg, 8 * l, save)
+            h, s2 = _ffn_fwd(h, l1_w, l1_b, l2_w, l2_b, n2_w, n2_b, cfg, 8 * l + 2, save)
+            acts.append((s1, s2))
+        if save:
+            ctx.cfg, ctx.dims, ctx.acts = cfg, (B, S, H, d, Kin, L), acts
+            ctx.save_for_backward(x_in, emb_w, emb_b, *layer_params)
+        return h.view(B, S, d)
+
+    @staticmethod
+    def backward(ctx, dy):
+        cfg = ctx.cfg
+        B, S, H, d, Kin, L = ctx.dims
+        x_in, emb_w, emb_b, *layer_params = ctx.saved_tensors
+        M = B * S
+        grads = _zero_grads([emb_w, emb_b, *layer_params])
+        g_emb_w, g_emb_b, g_layers = grads[0], grads[1], grads[2:]
+        dh = dy.contiguous().view(M, d)
+        for l in reversed(range(L)):
+            in_w, in_b, out_w, out_b, l1_w, l1_b, l2_w, l2_b, n1_w, n1_b, n2_w, n2_b = layer_params[
+                l * ENC_PARAMS_PER_LAYER: (l + 1) * ENC_PARAMS_PER_LAYER]
+            (g_in_w, g_in_b, g_out_w, g_out_b, g_l1_w, g_l1_b, g_l2_w, g_l2_b, g_n1_w, g_n1_b, g_n2_w,
+             g_n2_b) = g_layers[l * ENC_PARAMS_PER_LAYER: (l + 1) * ENC_PARAMS_PER_LAYER]
+            s1, s2 = ctx.acts[l]
+            dh = _ffn_bwd(dh, s2, l1_w, l2_w, n2_w, n2_b, g_l1_w, g_l1_b, g_l2_w, g_l2_b, g_n2_w, g_n2_b, cfg, 8 * l + 2)
+            dh = _sa_bwd(dh, s1, B, S, H, in_w, out_w, n1_w, n1_b, g_in_w, g_in_b, g_out_w, g_out_b, g_n1_w, g_n1_b,
+                         cfg, 8 * l)
+        ops.colsum_accum(dh, d, M, d, g_emb_b)
+        ops.gemm(dh, d, KM, x_in, Kin, KN, g_emb_w, Kin, d, Kin, M, precision=cfg.precision, accumulate=True)
+        dx_in = None
+        if ctx.needs_input_grad[5]:
+            dx_in = _empty((M, Kin), dh)
+            ops.gemm(dh, d, MK, emb_w, Kin, KN, dx_in, Kin, M, Kin, d, precision=cfg.precision)
+            dx_in = dx_in.view_as(x_in)
+        ctx.acts = None
+        return (None, None, None, None, None, dx_in, g_emb_w, g_emb_b, *g_layers)
+
+
+class DenoiserFn(torch.autograd.Function):
+    """Linear(J->d)+PE, L pre-LN decoder layers over memory, Linear(d->J) (decoder.py:47-54)."""
+
+    @staticmethod
+    def forward(ctx, cfg: RunCfg, B: int, T: int, Mm: int, H: int, pe, x, mem, emb_w, emb_b, fc_w, fc_b, *layer_params):
+        d = emb_w.shape[0]
+        J = emb_w.shape[1]
+        Mq = B * T
+        L = len(layer_params) // DEC_PARAMS_PER_LAYER
+        save = any(ctx.needs_input_grad)
+        mem2 = mem.contiguous().view(B * Mm, d)
+        x2 = x.contiguous().view(Mq, J)
+        h = _empty((Mq, d), mem2)
+        ops.gemm(x2, J, MK, emb_w, J, NK, h, d, Mq, d, J, precision=cfg.precision, bias=emb_b, pe=pe, pe_period=T)
+        acts = []
+        for l in range(L):
+            (sa_in_w, sa_in_b, sa_out_w, sa_out_b, ca_in_w, ca_in_b, ca_out_w, ca_out_b, l1_w, l1_b, l2_w, l2_b, n1_w,
+             n1_b, n2_w, n2_b, n3_w, n3_b) = layer_params[l * DEC_PARAMS_PER_LAYER: (l + 1) * DEC_PARAMS_PER_LAYER]
+            h, s1 = _sa_fwd(h, B, T, H, sa_in_w, sa_in_b, sa_out_w, sa_out_b, n1_w, n1_b, cfg, 8 * l, save)
+            h, s2 = _ca_fwd(h, mem2, B, T, Mm, H, ca_in_w, ca_in_b, ca_out_w, ca_out_b, n2_w, n2_b, cfg, 8 * l + 2, save)
+            h, s3 = _ffn_fwd(h, l1_w, l1_b, l2_w, l2_b, n3_w, n3_b, cfg, 8 * l + 4, save)
+            acts.append((s1, s2, s3))
+        out = _empty((Mq, J), mem2)
+        ops.gemm(h, d, MK, fc_w, d, NK, out, J, Mq, J, d, precision=cfg.precision, bias=fc_b)
+        if save:
+            ctx.cfg, ctx.dims, ctx.acts, ctx.h_last = cfg, (B, T, Mm, H, d, J, L), acts, h
+            ctx.save_for_backward(x2, mem2, emb_w, emb_b, fc_w, fc_b, *layer_params)
+        return out.view(B, T, J)
+
+    @staticmethod
+    def backward(ctx, dout):
+        cfg = ctx.cfg
+        B, T, Mm, H, d, J, L = ctx.dims
+        x2, mem2, emb_w, emb_b, fc_w, fc_b, *layer_params = ctx.saved_tensors
+        Mq = B * T
+        grads = _zero_grads([emb_w, emb_b, fc_w, fc_b, *layer_params])
+        g_emb_w, g_emb_b, g_fc_w, g_fc_b, g_layers = grads[0], grads[1], grads[2], grads[3], grads[4:]
+        do = dout.contiguous().view(Mq, J)
+        ops.colsum_accum(do, J, Mq, J, g_fc_b)
+        ops.gemm(do, J, KM, ctx.h_last, d, KN, g_fc_w, d, J, d, Mq, precision=cfg.precision, accumulate=True)
+        dh = _empty((Mq, d), mem2)
+        ops.gemm(do, J, MK, fc_w, d, KN, dh, d, Mq, d, J, precision=cfg.precision)
+        need_dmem = ctx.needs_input_grad[7]
+        dmem = torch.zeros((B * Mm, d), device=mem2.device, dtype=torch.float32) if need_dmem else None
+        for l in reversed(range(L)):
+            (sa_in_w, sa_in_b, sa_out_w, sa_out_b, ca_in_w, ca_in_b, ca_out_w, ca_out_b, l1_w, l1_b, l2_w, l2_b, n1_w,
+             n1_b, n2_w, n2_b, n3_w, n3_b) = layer_params[l * DEC_PARAMS_PER_LAYER: (l + 1) * DEC_PARAMS_PER_LAYER]
+            (g_sa_in_w, g_sa_in_b, g_sa_out_w, g_sa_out_b, g_ca_in_w, g_ca_in_b, g_ca_out_w, g_ca_out_b, g_l1_w, g_l1_b,
+             g_l2_w, g_l2_b, g_n1_w, g_n1_b, g_n2_w, g_n2_b, g_n3_w,
+             g_n3_b) = g_layers[l * DEC_PARAMS_PER_LAYER: (l + 1) * DEC_PARAMS_PER_LAYER]
+            s1, s2, s3 = ctx.acts[l]
+            dh = _ffn_bwd(dh, s3, l1_w, l2_w, n3_w, n3_b, g_l1_w, g_l1_b, g_l2_w, g_l2_b, g_n3_w, g_n3_b, cfg, 8 * l + 4)
+            dh = _ca_bwd(dh, s2, mem2, dmem, B, T, Mm, H, ca_in_w, ca_out_w, n2_w, n2_b, g_ca_in_w, g_ca_in_b,
+                         g_ca_out_w, g_ca_out_b, g_n2_w, g_n2_b, cfg, 8 * l + 2)
+            dh = _sa_bwd(dh, s1, B, T, H, sa_in_w, sa_out_w, n1_w, n1_b, g_sa_in_w, g_sa_in_b, g_sa_out_w, g_sa_out_b,
+                         g_n1_w, g_n1_b, cfg, 8 * l)
+        ops.colsum_accum(dh, d, Mq, d, g_emb_b)
+        ops.gemm(dh, d, KM, x2, J, KN, g_emb_w, J, d, J, Mq, precision=cfg.precision, accumulate=True)
+        dx = None
+        if ctx.needs_input_grad[6]:
+            dx = _empty((Mq, J), dh)
+            ops.gemm(dh, d, MK, emb_w, J, KN, dx, J, Mq, J, d, precision=cfg.precision)
+            dx = dx.view(B, T, J)
+        ctx.acts = None
+        ctx.h_last = None
+        return (None, None, None, None, None, None, dx, None if dmem is None else dmem.view(B, Mm, d), g_emb_w,
+                g_emb_b, g_fc_w, g_fc_b, *g_layers)
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b for 2-D x (image-token head: Conv2d 1x1 and fc; image.py:69-73)."""
+
+    @staticmethod
+    def forward(ctx, precision: int, x, w, b):
+        M, K = x.shape
+        N = w.shape[0]
+        y = _empty((M, N), x)
+        ops.gemm(x, K, MK, w, K, NK, y, N, M, N, K, precision=precision, bias=b)
+        ctx.precision = precision
+        ctx.save_for_backward(x, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        M, K = x.shape
+        N = w.shape[0]
+        dy = dy.contiguous()
+        gw = torch.zeros_like(w)
+        gb = torch.zeros(N, device=w.device, dtype=torch.float32)
+        ops.colsum_accum(dy, N, M, N, gb)
+        ops.gemm(dy, N, KM, x, K, KN, gw, K, N, K, M, precision=ctx.precision, accumulate=True)
+        dx = None
+        if ctx.needs_input_grad[1]:
+            dx = _empty((M, K), x)
+            ops.gemm(dy, N, MK, w, K, KN, dx, K, M, K, N, precision=ctx.precision)
+        return None, dx, gw, gb
+
+
+class AssembleContextFn(torch.autograd.Function):
+    """torch.cat(context + [StepToken(t)], dim=1) (model.py:173-176) written by strided-copy kernels."""
+
+    @staticmethod
+    def forward(ctx, step, freqs, token, d: int, *parts):
+        B = step.shape[0]
+        lens = [p.shape[1] for p in parts]
+        Mm = sum(lens) + 1
+        mem = torch.empty((B, Mm, d), device=token.device, dtype=torch.float32)
+        off = 0
+        for p_, n in zip(parts, lens):
+            pc = p_.contiguous()
+            ops.copy_rows(pc.data_ptr(), n * d, d, mem.data_ptr() + 4 * off * d, Mm * d, d, B, n, d)
+            off += n
+        ops.step_token(step, freqs, token, mem.data_ptr() + 4 * off * d, Mm * d, B, d)
+        ctx.lens, ctx.d, ctx.B = lens, d, B
+        ctx.save_for_backward(token)
+        return mem
+
+    @staticmethod
+    def backward(ctx, dmem):
+        (token,) = ctx.saved_tensors
+        d, B, lens = ctx.d, ctx.B, ctx.lens
+        Mm = sum(lens) + 1
+        dmem = dmem.contiguous()
+        outs = []
+        off = 0
+        for i, n in enumerate(lens):
+            if ctx.needs_input_grad[4 + i]:
+                g = torch.empty((B, n, d), device=dmem.device, dtype=torch.float32)
+                ops.copy_rows(dmem.data_ptr() + 4 * off * d, Mm * d, d, g.data_ptr(), n * d, d, B, n, d)
+                outs.append(g)
+            else:
+                outs.append(None)
+            off += n
+        dtoken = None
+        if ctx.needs_input_grad[2]:
+            dtoken = torch.zeros_like(token)
+            ops.step_token_bwd(dmem.data_ptr() + 4 * off * d, Mm * d, B, d, dtoken)
+        return (None, None, dtoken, None, *outs)
+
+
+class GatherRowsFn(torch.autograd.Function):
+    """nn.Embedding lookup (game_state.py:27)."""
+
+    @staticmethod
+    def forward(ctx, table, idx):
+        B, d = idx.numel(), table.shape[1]
+        out = torch.empty((B, 1, d), device=table.device, dtype=torch.float32)
+        err = torch.zeros(1, device=table.device, dtype=torch.int32)
+        ops.gather_rows(table, idx, out, d, err)
+        ctx.save_for_backward(idx)
+        ctx.shape = table.shape
+        ctx.err = err
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (idx,) = ctx.saved_tensors
+        dtable = torch.zeros(ctx.shape, device=dout.device, dtype=torch.float32)
+        dout = dout.contiguous()
+        ops.scatter_add_rows(dout.data_ptr(), dout.shape[-1], idx, dtable)
+        return dtable, None
+
+
+class MseLossFn(torch.autograd.Function):
+    """F.mse_loss(pred, target) with mean reduction (train.py:229)."""
+
+    @staticmethod
+    def forward(ctx, pred, target):
+        pred = pred.contiguous()
+        target = target.contiguous()
+        out = torch.empty((), device=pred.device, dtype=torch.float32)
+        ops.mse_fwd(pred, target, out)
+        ctx.save_for_backward(pred, target)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, target = ctx.saved_tensors
+        gp = torch.empty_like(pred)
+        ops.mse_bwd(pred, target, g.contiguous(), gp)
+        gt = None
+        if ctx.needs_input_grad[1]:
+            gt = -gp
+        return gp, gt
+
+
+def mse_loss(pred, target):
+    return MseLossFn.apply(pred, target)

@@ -1,0 +1,207 @@
+"""Thin typed wrappers over the C ABI (one Python function per entry point of include/sd_b200.h).
+
+Device memory comes from torch's caching allocator and kernels are launched on torch's current
+stream — PyTorch is plumbing here; all arithmetic happens in libsd_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import GemmDesc, check, stream_ptr
+
+MK, KM, NK, KN = 0, 1, 0, 1
+ACT_NONE, ACT_GELU = 0, 1
+PREC_FP32, PREC_BF16 = 0, 1
+LN_EPS = 1e-5
+
+# number of kernels of this library launched since the last reset (bench.py's gpu_launches)
+_launches = 0
+
+
+def launches() -> int:
+    return _launches
+
+
+def reset_launches():
+    global _launches
+    _launches = 0
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
+def _f32(t: torch.Tensor, name="tensor"):
+    if t.dtype != torch.float32:
+        raise _lib.SdError(f"{name} must be float32, got {t.dtype}")
+    if not t.is_cuda:
+        raise _lib.SdError(f"{name} must live on a CUDA device (no CPU fallback)")
+    return t
+
+
+def gemm(A, lda, a_layout, B, ldb, b_layout, C_, ldc, M, N, K, *, precision=PREC_FP32, ln=None, bias=None,
+         pre_out=None, ldp=0, act=ACT_NONE, gelu_grad_src=None, ldg=0, dropout=None, pe=None, pe_period=0,
+         residual=None, ldr=0, accumulate=False, alpha=1.0):
+    """A, B, C_, ... are tensors or raw int pointers (for sliced views use ``t.data_ptr() + off*4``)."""
+    d = GemmDesc()
+    P = lambda t: (t if isinstance(t, int) or t is None else t.data_ptr())
+    d.A, d.lda, d.a_layout = P(A), lda, a_layout
+    d.B, d.ldb, d.b_layout = P(B), ldb, b_layout
+    d.C, d.ldc = P(C_), ldc
+    d.M, d.N, d.K = M, N, K
+    d.precision = precision
+    if ln is not None:
+        d.ln_mean, d.ln_rstd, d.ln_gamma, d.ln_beta = (P(t) for t in ln)
+    d.alpha = alpha
+    d.bias = P(bias)
+    d.pre_out, d.ldp = P(pre_out), ldp
+    d.act = act
+    d.gelu_grad_src, d.ldg = P(gelu_grad_src), ldg
+    if dropout is not None and dropout[0] > 0.0:
+        d.dropout_p, d.dropout_seed, d.dropout_stream = dropout
+    d.pe, d.pe_period = P(pe), pe_period
+    d.residual, d.ldr = P(residual), ldr
+    d.accumulate = 1 if accumulate else 0
+    check(_lib.lib().sd_gemm(C.byref(d), stream_ptr()), "sd_gemm")
+    _count()
+
+
+def ln_stats(x2d: torch.Tensor, d: int):
+    M = x2d.numel() // d
+    mean = torch.empty(M, device=x2d.device, dtype=torch.float32)
+    rstd = torch.empty(M, device=x2d.device, dtype=torch.float32)
+    check(_lib.lib().sd_ln_stats(x2d.data_ptr(), d, M, d, mean.data_ptr(), rstd.data_ptr(), LN_EPS, stream_ptr()),
+          "sd_ln_stats")
+    _count()
+    return mean, rstd
+
+
+def ln_bwd(g, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, M, d):
+    check(_lib.lib().sd_ln_bwd(g.data_ptr(), d, x.data_ptr(), d, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                               None if dres is None else dres.data_ptr(), d, dx.data_ptr(), d, dgamma.data_ptr(),
+                               dbeta.data_ptr(), M, d, stream_ptr()), "sd_ln_bwd")
+    _count()
+
+
+def attention_fwd(Q, ldq, K, ldk, V, ldv, O, ldo, lse, B, H, T, M, dh, dropout=None):
+    p, seed, sid = dropout if dropout is not None else (0.0, 0, 0)
+    check(_lib.lib().sd_attention_fwd(Q, ldq, K, ldk, V, ldv, O, ldo, lse, B, H, T, M, dh, p, seed, sid, stream_ptr()),
+          "sd_attention_fwd")
+    _count()
+
+
+def attention_bwd(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, dQ, lddq, dK, lddk, dV, lddv, B, H, T, M, dh,
+                  dropout=None):
+    p, seed, sid = dropout if dropout is not None else (0.0, 0, 0)
+    check(_lib.lib().sd_attention_bwd(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, dQ, lddq, dK, lddk, dV, lddv,
+                                      B, H, T, M, dh, p, seed, sid, stream_ptr()), "sd_attention_bwd")
+    _count()
+
+
+def step_token(t: torch.Tensor, freqs, token, out, ld_out, B, d):
+    if t.dtype == torch.int64:
+        is_float = 0
+    elif t.dtype == torch.float32:
+        is_float = 1
+    else:
+        raise _lib.SdError(f"step must be int64 or float32, got {t.dtype}")
+    check(_lib.lib().sd_step_token(t.data_ptr(), is_float, freqs.data_ptr(), token.data_ptr(),
+                                   out if isinstance(out, int) else out.data_ptr(), ld_out, B, d, stream_ptr()),
+          "sd_step_token")
+    _count()
+
+
+def step_token_bwd(dout_ptr, ld, B, d, dtoken):
+    check(_lib.lib().sd_step_token_bwd(dout_ptr, ld, B, d, dtoken.data_ptr(), stream_ptr()), "sd_step_token_bwd")
+    _count()
+
+
+def q_sample(joint_command, mean, std, noise, t, acp, x0_out, xt_out):
+    B = joint_command.shape[0]
+    inner = joint_command.numel() // max(B, 1)
+    J = joint_command.shape[-1]
+    check(_lib.lib().sd_q_sample(joint_command.data_ptr(), _lib.ptr(mean), _lib.ptr(std), noise.data_ptr(),
+                                 t.data_ptr(), acp.data_ptr(), acp.numel(), _lib.ptr(x0_out), xt_out.data_ptr(), B,
+                                 inner, J, stream_ptr()), "sd_q_sample")
+    _count()
+
+
+def ddim_step(x, eps, prev, x0_pred, coef):
+    sb, sa, sap, sbp = coef
+    check(_lib.lib().sd_ddim_step(x.data_ptr(), eps.data_ptr(), prev.data_ptr(), _lib.ptr(x0_pred), x.numel(), sb, sa,
+                                  sap, sbp, stream_ptr()), "sd_ddim_step")
+    _count()
+
+
+def mse_fwd(pred, target, out):
+    check(_lib.lib().sd_mse_fwd(pred.data_ptr(), target.data_ptr(), pred.numel(), out.data_ptr(), stream_ptr()),
+          "sd_mse_fwd")
+    _count()
+
+
+def mse_bwd(pred, target, grad_loss, grad_pred):
+    check(_lib.lib().sd_mse_bwd(pred.data_ptr(), target.data_ptr(), pred.numel(), _lib.ptr(grad_loss),
+                                grad_pred.data_ptr(), stream_ptr()), "sd_mse_bwd")
+    _count()
+
+
+def affine_joints(x, mean, std, out, mode):
+    check(_lib.lib().sd_affine_joints(x.data_ptr(), mean.data_ptr(), std.data_ptr(), out.data_ptr(), x.numel(),
+                                      x.shape[-1], mode, stream_ptr()), "sd_affine_joints")
+    _count()
+
+
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale=1.0):
+    check(_lib.lib().sd_adamw_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2,
+                                   eps, wd, step, grad_scale, stream_ptr()), "sd_adamw_step")
+    _count()
+
+
+def gather_rows(table, idx, out, ld_out, err_flag=None):
+    B, d = idx.numel(), table.shape[1]
+    check(_lib.lib().sd_gather_rows(table.data_ptr(), idx.data_ptr(), table.shape[0],
+                                    out if isinstance(out, int) else out.data_ptr(), ld_out, B, d,
+                                    _lib.ptr(err_flag), stream_ptr()), "sd_gather_rows")
+    _count()
+
+
+def scatter_add_rows(dout_ptr, ld, idx, dtable):
+    check(_lib.lib().sd_scatter_add_rows(dout_ptr, ld, idx.data_ptr(), dtable.shape[0], dtable.data_ptr(), idx.numel(),
+                                         dtable.shape[1], stream_ptr()), "sd_scatter_add_rows")
+    _count()
+
+
+def colsum_accum(x, ld, M, N, out):
+    check(_lib.lib().sd_colsum_accum(x if isinstance(x, int) else x.data_ptr(), ld, M, N,
+                                     out if isinstance(out, int) else out.data_ptr(), stream_ptr()), "sd_colsum_accum")
+    _count()
+
+
+def copy_rows(src, sbs, sld, dst, dbs, dld, B, rows, cols, accumulate=False):
+    check(_lib.lib().sd_copy_rows(src, sbs, sld, dst, dbs, dld, B, rows, cols, 1 if accumulate else 0, stream_ptr()),
+          "sd_copy_rows")
+    _count()
+
+
+def add(a, b, y):
+    check(_lib.lib().sd_add(a.data_ptr(), b.data_ptr(), y.data_ptr(), y.numel(), stream_ptr()), "sd_add")
+    _count()
+
+
+def dropout_mask(n, p, seed, stream_id, device):
+    out = torch.empty(n, device=device, dtype=torch.float32)
+    check(_lib.lib().sd_dropout_mask(out.data_ptr(), n, p, seed, stream_id, stream_ptr()), "sd_dropout_mask")
+    _count()
+    return out
+
+
+def dropout_apply(x, p, seed, stream_id):
+    y = torch.empty_like(x)
+    check(_lib.lib().sd_dropout_apply(x.data_ptr(), y.data_ptr(), x.numel(), p, seed, stream_id, stream_ptr()),
+          "sd_dropout_apply")
+    _count()
+    return y

@@ -1,0 +1,56 @@
+"""Process-wide run-time switches of the hot path: arithmetic mode and dropout RNG state."""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import ops
+
+_PRECISIONS = {"fp32": ops.PREC_FP32, "bf16": ops.PREC_BF16}
+_precision = _PRECISIONS[os.environ.get("SD_B200_PRECISION", "fp32")]
+_seed_base = None
+_calls = 0
+
+# torch default of nn.Transformer{En,De}coderLayer, never overridden by the reference
+# (encoder/base.py:30-37, decoder.py:26-33)
+DROPOUT_P = 0.1
+
+
+def set_precision(name: str):
+    """"fp32": true-fp32 FFMA kernels (<=1e-4 of the reference); "bf16": bf16 tcgen05 GEMMs with fp32
+    accumulation, fp32 LayerNorm/softmax/residual stream (<=2e-2)."""
+    global _precision
+    if name not in _PRECISIONS:
+        raise ValueError(f"Invalid precision: {name}")
+    _precision = _PRECISIONS[name]
+
+
+def get_precision() -> int:
+    return _precision
+
+
+def precision_name() -> str:
+    return "bf16" if _precision == ops.PREC_BF16 else "fp32"
+
+
+def manual_seed(seed: int):
+    """Seeds the counter-based dropout RNG of the fused kernels."""
+    global _seed_base, _calls
+    _seed_base = int(seed) & 0xFFFFFFFFFFFF
+    _calls = 0
+
+
+def next_seed() -> int:
+    global _seed_base, _calls
+    if _seed_base is None:
+        _seed_base = torch.initial_seed() & 0xFFFFFFFFFFFF
+    _calls += 1
+    return (_seed_base * 1000003 + _calls) & 0x7FFFFFFFFFFFFFFF
+
+
+def make_cfg(training: bool, dropout_p: float = DROPOUT_P):
+    from .functional import RunCfg
+
+    p = dropout_p if training else 0.0
+    return RunCfg(precision=_precision, p=p, seed=next_seed() if p > 0.0 else 0, stream_base=0)
