@@ -24,6 +24,7 @@ class DiffusionActionGenerator(nn.Module):
         self.num_heads = num_heads
         self.hidden_dim = hidden_dim
         self.num_joints = num_joints
+        self.max_seq_len = max_seq_len
 
     def forward(self, x, context):
         """x (B,T,J) noisy actions; context (B,M,d) memory -> (B,T,J) predicted noise."""

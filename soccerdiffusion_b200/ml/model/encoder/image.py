@@ -37,8 +37,19 @@ class SequenceEncoderType(Enum):
     NONE = "none"
 
 
+import contextlib
+
+
+@contextlib.contextmanager
 def _trunk_autocast():
-    return torch.autocast("cuda", dtype=torch.bfloat16, enabled=runtime.get_precision() == ops.PREC_BF16)
+    """Arithmetic mode of the library trunk: bf16 autocast in bf16 mode; true fp32 (TF32 convolutions off —
+    they cost ~1e-3) in the 1e-4 fp32 mode."""
+    if runtime.get_precision() == ops.PREC_BF16:
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            yield
+    else:
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            yield
 
 
 class AbstractImageEncoder(nn.Module):

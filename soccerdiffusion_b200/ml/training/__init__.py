@@ -1,0 +1,7 @@
+from soccerdiffusion_b200.ml.training.optim import FusedAdamW  # noqa: F401
+from soccerdiffusion_b200.ml.training.step import (  # noqa: F401
+    allreduce_gradients,
+    broadcast_parameters,
+    distill_step,
+    train_step,
+)

@@ -49,8 +49,16 @@ def next_seed() -> int:
     return (_seed_base * 1000003 + _calls) & 0x7FFFFFFFFFFFFFFF
 
 
-def make_cfg(training: bool, dropout_p: float = DROPOUT_P):
+def set_dropout(p: float):
+    """Overrides the train-mode dropout probability (parity tests run with 0.0; the reference's value is 0.1)."""
+    global DROPOUT_P
+    if not 0.0 <= p < 1.0:
+        raise ValueError(f"dropout probability has to be in [0, 1), but got {p}")
+    DROPOUT_P = float(p)
+
+
+def make_cfg(training: bool, dropout_p: float | None = None):
     from .functional import RunCfg
 
-    p = dropout_p if training else 0.0
+    p = (DROPOUT_P if dropout_p is None else dropout_p) if training else 0.0
     return RunCfg(precision=_precision, p=p, seed=next_seed() if p > 0.0 else 0, stream_base=0)
