@@ -1,0 +1,440 @@
+#!/usr/bin/env python
+"""bench.py — the hot path's headline metric (BASELINE.json): train samples/s, plus p50 DDIM latency at bs=1.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|bf16]
+                    [--batch B] [--workload full|inscope|denoiser]
+
+A "step" is one pass of the reference's training loop body (ml/training/train.py:193-240) over one synthetic
+batch of default.yaml shapes: normalise -> t, eps -> add_noise -> model fwd -> mse -> bwd -> AdamW -> OneCycleLR,
+dropout p=0.1 live as in the reference.  N>1: one rank per GPU (torchrun), each rank its own bs=256 slice
+(weak scaling), one NCCL all-reduce of the flat gradient per step.
+
+Prints ONE JSON line (rank 0).  `value`: samples/s with inputs resident in HBM; `e2e`: the same step fed from
+pinned HOST buffers (H2D inside the timed region) with the loss read back; `roofline`: the dominant kernel
+class of libsd_b200 timed with CUDA events; `cpu_baseline`: the oracle port of the reference's CPU path on a
+bounded sample; `ddim`: bs=1 30-step trajectory latency (persistent-kernel sampler).
+
+--impl reference: the reference's own CPU PyTorch path (restated in oracle/, the live reference cannot travel to
+the GPU box) timed on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "train samples/s (default.yaml denoiser training step, bs=256/GPU)"
+UNIT = "samples/s"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sust=p["bf16_tflops_sustained"], source="measured")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="sd_clocks_", suffix=".csv")
+            os.close(fd)
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU arm: the reference's training-loop body in the oracle restatement (torch CPU fp32, all host threads)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    from oracle import model_ref, synth
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    hp = synth.DEFAULT_HP
+    bs = args.cpu_batch
+    tmpl = _state_template(hp)
+    sd = synth.synth_state_dict(tmpl, 0)
+    names = [n for n in tmpl if tmpl[n].is_floating_point() and "running_" not in n and n not in ("mean", "std")]
+    sd = {k: (v.clone().requires_grad_(True) if k in names else v) for k, v in sd.items()}
+    opt = torch.optim.AdamW([sd[n] for n in names], lr=hp["lr"])
+    batch = synth.synth_batch(hp, bs, 0)
+    times = []
+    for it in range(args.warmup + args.steps):
+        noise = torch.randn(bs, hp["trajectory_prediction_length"], hp["num_joints"])
+        t = torch.randint(0, 1000, (bs,))
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        # dropout p=0.1 is live in the reference's loop; the oracle applies supplied masks only, so the CPU arm
+        # runs without dropout (slightly LESS work than the reference: the baseline is not under-reported)
+        loss, _ = model_ref.training_loss(batch, noise, t, sd, hp, masks=None, train_bn=True)
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    val = bs * len(times) / total
+    line = dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * total / len(times), higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload=f"default.yaml full training step on host CPU, bounded sample bs={bs}",
+                            global_batch=bs),
+                cpu_baseline=dict(value=val, unit=UNIT, cores=cores, kind="port",
+                                  sample=f"{len(times)} full training steps at bs={bs} (oracle/model_ref.py + torch AdamW)"),
+                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def _state_template(hp):
+    """name -> empty tensor with the shape the REAL reference's state_dict has for default.yaml (recorded from the
+    live reference by oracle/gen_golden.py into tests/golden/manifest.json) — no product code on the CPU arm."""
+    import torch
+
+    with open(os.path.join(ROOT, "tests", "golden", "manifest.json")) as fh:
+        c = json.load(fh)["cases"]["default"]
+    out = {}
+    for n, s in zip(c["state_dict_names"], c["state_dict_shapes"]):
+        out[n] = torch.empty(s, dtype=torch.int64 if n.endswith("num_batches_tracked") else torch.float32)
+    return out
+
+
+def cpu_baseline_sample(hp, bs, max_seconds=25.0):
+    import torch
+
+    from oracle import model_ref, synth
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    tmpl = _state_template(hp)
+    sd = synth.synth_state_dict(tmpl, 0)
+    names = [n for n in tmpl if tmpl[n].is_floating_point() and "running_" not in n and n not in ("mean", "std")]
+    sd = {k: (v.clone().requires_grad_(True) if k in names else v) for k, v in sd.items()}
+    opt = torch.optim.AdamW([sd[n] for n in names], lr=1e-4)
+    batch = synth.synth_batch(hp, bs, 0)
+    noise = synth.synth_noise("eps", hp, bs, 0)
+    t = synth.synth_timesteps(bs, 0)
+    n, t_total = 0, 0.0
+    for it in range(4):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss, _ = model_ref.training_loss(batch, noise, t, sd, hp, masks=None, train_bn=True)
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if it >= 1:
+            n += 1
+            t_total += dt
+        if t_total > max_seconds:
+            break
+    return dict(value=bs * n / t_total, unit=UNIT, cores=cores, kind="port",
+                sample=f"{n} full training steps at bs={bs} after 1 warm-up (oracle/model_ref.py, torch CPU fp32 + AdamW)")
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import soccerdiffusion_b200 as sd
+    from soccerdiffusion_b200 import config, ops
+    from soccerdiffusion_b200.dataset.pytorch import Normalizer
+    from soccerdiffusion_b200.ml.training import FusedAdamW, broadcast_parameters, train_step
+    from soccerdiffusion_b200.schedulers import DDIMScheduler
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    sd.set_precision(args.precision)
+    peaks = load_peaks()
+
+    hp = dict(config.DEFAULT)
+    bs = args.batch
+    torch.manual_seed(0)
+    model = config.build_model(hp).to(dev)
+    model.mean.fill_(3.14159)
+    model.std.fill_(1.8138)
+    if world > 1:
+        broadcast_parameters(model)
+    model.train()
+    sd.manual_seed(1234 + rank)
+    opt = FusedAdamW(model.parameters(), lr=hp["lr"])
+    total_steps = 4 * (args.steps + args.warmup) + 64
+    lrs = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=hp["lr"], total_steps=total_steps)
+    sch = DDIMScheduler(beta_schedule="squaredcos_cap_v2", clip_sample=False)
+    sch.config["num_train_timesteps"] = hp["train_denoising_timesteps"]
+    norm = Normalizer(model.mean, model.std)
+
+    host = config.synthetic_batch(hp, bs, None, seed=rank, pin=True)
+    if args.workload != "full":
+        host.pop("image_data")
+    batch = {k: v.to(dev) for k, v in host.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+    img_tokens = None
+    if args.workload == "inscope":
+        # image tokens precomputed: the trunk (library cuDNN, SURVEY.md §8 a8') is outside the timed step
+        img_tokens = torch.randn(bs, hp["image_context_length"], hp["hidden_dim"], device=dev)
+
+    def step(b):
+        if args.workload == "full":
+            return train_step(model, opt, sch, norm, b, lr_scheduler=lrs, data_parallel=world > 1)
+        if args.workload == "denoiser":
+            return train_step(model, opt, sch, norm, b, lr_scheduler=lrs, data_parallel=world > 1,
+                              decoder_pretraining=True)
+        return _inscope_step(model, opt, sch, b, img_tokens, lrs, world > 1)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(batch)
+    sync()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ops.reset_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(batch)
+    e1.record()
+    sync()
+    ms = e0.elapsed_time(e1)
+    launches = ops.launches()
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- e2e: pinned host buffers -> device every step, loss read back every step ------------------
+    for _ in range(1):
+        step({k: v.to(dev, non_blocking=True) for k, v in host.items()}).item()
+    sync()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        step(b).item()
+    e3.record()
+    sync()
+    ms_e2e = e2.elapsed_time(e3)
+
+    if world > 1:
+        tt = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = tt.tolist()
+
+    # ---- per-kernel-class device time (CUDA events around every libsd_b200 GEMM/attention launch) ----
+    roofline = None
+    kernel_classes = None
+    if rank == 0:
+        ops.profile_begin()
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record()
+        nprof = 2
+        for _ in range(nprof):
+            step(batch)
+        pe1.record()
+        prof = ops.profile_end()
+        step_ms = pe0.elapsed_time(pe1) / nprof
+        kernel_classes = {k: dict(launches_per_step=v["launches"] // nprof, ms_per_step=v["ms"] / nprof,
+                                  tflops=(v["flops"] / v["ms"] / 1e9 if v["ms"] > 0 else 0.0),
+                                  share_of_step=v["ms"] / nprof / step_ms) for k, v in prof.items()}
+        gemm = {k: v for k, v in prof.items() if "gemm" in k}
+        if gemm:
+            top = max(gemm, key=lambda k: gemm[k]["ms"])
+            v = gemm[top]
+            ach = v["flops"] / v["ms"] / 1e9
+            roofline = dict(kernel=top, bound="tensor", achieved=ach, peak=peaks["tf_sust"], unit="TFLOP/s",
+                            frac=ach / peaks["tf_sust"], traffic=None, peak_source=peaks["source"] + " (sustained bf16)",
+                            launches_per_step=v["launches"] // nprof, avg_launch_ms=v["ms"] / v["launches"],
+                            algorithmic_flops_per_launch=v["flops"] / v["launches"])
+    if world > 1:
+        dist.barrier()
+
+    # ---- bs=1 DDIM trajectory latency (BASELINE.json configs[2]) ------------------------------------
+    ddim = None
+    if rank == 0 and not args.no_ddim:
+        ddim = ddim_latency(model, hp, dev, args.precision)
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import synth
+
+            cpu = cpu_baseline_sample(synth.DEFAULT_HP if args.workload == "full" else synth.DEFAULT_HP, args.cpu_batch)
+        gb = bs * world
+        line = dict(
+            metric=METRIC, value=gb * args.steps / (ms / 1e3), unit=UNIT, n_gpus=world, steps=args.steps,
+            warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+            dtype="f32" if args.precision == "fp32" else "bf16", data="synthetic", impl="ours",
+            config=dict(workload={"full": "default.yaml full training step incl. ResNet18 trunk (trunk = cuDNN library call)",
+                                  "inscope": "default.yaml training step, image tokens precomputed (trunk outside the step)",
+                                  "denoiser": "denoiser-only training step (train.py:221-224)"}[args.workload],
+                        global_batch=gb, per_gpu_batch=bs, parallelism=f"dp{world}", dropout_p=0.1,
+                        l2="inputs %.2f GB/step per GPU > 126 MB L2; no explicit flush" % (h2d / 1e9),
+                        precision_mode=args.precision),
+            e2e=dict(value=gb * args.steps / (ms_e2e / 1e3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4),
+            gpu_launches=launches, clocks=clk, roofline=roofline, kernel_classes=kernel_classes, cpu_baseline=cpu, ddim=ddim)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _inscope_step(model, opt, sch, batch, img_tokens, lrs, dp):
+    """train.py:193-240 with the image tokens given (trunk outside): every kernel in the step is libsd_b200's."""
+    import torch
+
+    from soccerdiffusion_b200.functional import mse_loss
+    from soccerdiffusion_b200.ml.training.step import allreduce_gradients, q_sample
+
+    jt = batch["joint_command"]
+    bsz = jt.size(0)
+    opt.zero_grad()
+    t = torch.randint(0, 1000, (bsz,), device=jt.device)
+    noise = torch.randn(jt.shape, device=jt.device)
+    noisy = q_sample(sch, model, jt, noise, t)
+    ctx = [model.action_history_encoder(batch["joint_command_history"]), model.imu_encoder(batch["rotation"]),
+           model.joint_states_encoder(batch["joint_state"]),
+           model.image_sequence_encoder.transformer_encoder(img_tokens), model.game_state_encoder(batch["game_state"])]
+    pred = model.forward_with_context(ctx, noisy, t)
+    loss = mse_loss(pred, noise)
+    loss.backward()
+    if dp:
+        allreduce_gradients(opt)
+    opt.step()
+    lrs.step()
+    return loss.detach()
+
+
+def ddim_latency(model, hp, dev, precision, reps=200):
+    import torch
+
+    import soccerdiffusion_b200 as sd
+    from soccerdiffusion_b200 import config
+    from soccerdiffusion_b200.schedulers import DDIMScheduler
+
+    sd.set_precision("fp32")  # the persistent sampler is the true-fp32 path (1e-4 mode)
+    model.eval()
+    sch = DDIMScheduler(beta_schedule="squaredcos_cap_v2", clip_sample=False)
+    sch.set_timesteps(30)
+    batch = config.synthetic_batch(hp, 1, dev, seed=7)
+    x_T = torch.randn(1, hp["trajectory_prediction_length"], hp["num_joints"], device=dev)
+    out = {}
+    with torch.no_grad():
+        ctx = model.encode_input_data(batch)
+        for name, fn in (("sampler", lambda: model.sample(ctx, x_T, sch, denormalize=True)),
+                         ("tick", lambda: model.sample(model.encode_input_data(batch), x_T, sch, denormalize=True))):
+            for _ in range(5):
+                fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(reps if name == "sampler" else 30):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                b.synchronize()
+                ts.append(a.elapsed_time(b))
+            ts.sort()
+            out[name + "_p50_ms"] = ts[len(ts) // 2]
+            out[name + "_p99_ms"] = ts[min(len(ts) - 1, int(len(ts) * 0.99))]
+    out["steps"] = 30
+    out["algorithmic_gflop_per_trajectory"] = 2.97
+    out["note"] = "sampler = x_T -> x_0 with the context given (one persistent-kernel launch); tick = encode_input_data (10x224^2 frames) + sampler"
+    model.train()
+    sd.set_precision(precision)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("SD_B200_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
+    ap.add_argument("--cpu-batch", type=int, default=8, help="bounded CPU sample batch")
+    ap.add_argument("--workload", default="full", choices=["full", "inscope", "denoiser"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ddim", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

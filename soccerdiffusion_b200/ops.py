@@ -35,6 +35,49 @@ def _count(n=1):
     _launches += n
 
 
+# optional per-entry-point device timing (CUDA events on the launching stream) for bench.py's roofline block;
+# off by default: the events are only recorded while a profile is open
+_profile = None
+
+
+def profile_begin():
+    global _profile
+    _profile = []
+
+
+def profile_end():
+    """-> {kernel class: {"launches", "ms", "flops", "bytes"}} ; synchronises the device."""
+    global _profile
+    rec, _profile = _profile, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1, flops, nbytes in rec or []:
+        d = out.setdefault(name, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+        d["launches"] += 1
+        d["ms"] += e0.elapsed_time(e1)
+        d["flops"] += flops
+        d["bytes"] += nbytes
+    return out
+
+
+class _Timed:
+    def __init__(self, name, flops=0.0, nbytes=0.0):
+        self.name, self.flops, self.nbytes = name, flops, nbytes
+
+    def __enter__(self):
+        if _profile is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _profile is not None and exc[0] is None:
+            self.e1.record()
+            _profile.append((self.name, self.e0, self.e1, self.flops, self.nbytes))
+        return False
+
+
 def _f32(t: torch.Tensor, name="tensor"):
     if t.dtype != torch.float32:
         raise _lib.SdError(f"{name} must be float32, got {t.dtype}")
@@ -66,7 +109,9 @@ def gemm(A, lda, a_layout, B, ldb, b_layout, C_, ldc, M, N, K, *, precision=PREC
     d.pe, d.pe_period = P(pe), pe_period
     d.residual, d.ldr = P(residual), ldr
     d.accumulate = 1 if accumulate else 0
-    check(_lib.lib().sd_gemm(C.byref(d), stream_ptr()), "sd_gemm")
+    kind = "gemm_wgrad" if a_layout == KM else ("gemm_dgrad" if b_layout == KN else "gemm_fwd")
+    with _Timed(("tc_" if precision == PREC_BF16 else "f32_") + kind, 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N)):
+        check(_lib.lib().sd_gemm(C.byref(d), stream_ptr()), "sd_gemm")
     _count()
 
 
@@ -89,16 +134,18 @@ def ln_bwd(g, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, M, d):
 
 def attention_fwd(Q, ldq, K, ldk, V, ldv, O, ldo, lse, B, H, T, M, dh, dropout=None):
     p, seed, sid = dropout if dropout is not None else (0.0, 0, 0)
-    check(_lib.lib().sd_attention_fwd(Q, ldq, K, ldk, V, ldv, O, ldo, lse, B, H, T, M, dh, p, seed, sid, stream_ptr()),
-          "sd_attention_fwd")
+    with _Timed("attention_fwd", 4.0 * B * H * T * M * dh, 4.0 * B * H * dh * (2 * T + 2 * M)):
+        check(_lib.lib().sd_attention_fwd(Q, ldq, K, ldk, V, ldv, O, ldo, lse, B, H, T, M, dh, p, seed, sid,
+                                          stream_ptr()), "sd_attention_fwd")
     _count()
 
 
 def attention_bwd(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, dQ, lddq, dK, lddk, dV, lddv, B, H, T, M, dh,
                   dropout=None):
     p, seed, sid = dropout if dropout is not None else (0.0, 0, 0)
-    check(_lib.lib().sd_attention_bwd(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, dQ, lddq, dK, lddk, dV, lddv,
-                                      B, H, T, M, dh, p, seed, sid, stream_ptr()), "sd_attention_bwd")
+    with _Timed("attention_bwd", 10.0 * B * H * T * M * dh, 4.0 * B * H * dh * (4 * T + 4 * M)):
+        check(_lib.lib().sd_attention_bwd(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, dQ, lddq, dK, lddk, dV, lddv,
+                                          B, H, T, M, dh, p, seed, sid, stream_ptr()), "sd_attention_bwd")
     _count()
 
 
@@ -156,8 +203,9 @@ def affine_joints(x, mean, std, out, mode):
 
 
 def adamw_step(p, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale=1.0):
-    check(_lib.lib().sd_adamw_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2,
-                                   eps, wd, step, grad_scale, stream_ptr()), "sd_adamw_step")
+    with _Timed("adamw", 0.0, 28.0 * p.numel()):
+        check(_lib.lib().sd_adamw_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1,
+                                       beta2, eps, wd, step, grad_scale, stream_ptr()), "sd_adamw_step")
     _count()
 
 
