@@ -415,6 +415,11 @@ extern "C" int sd_attention_fwd(const float* Q, long long ldq, const float* K, l
         attn_fwd_kernel<NVv><<<grid, kThreads, bytes, st>>>(p);                                               \
     }
     switch (dh) {
+        case 4: {
+            const size_t bytes = sizeof(float) * kWarps * (size_t)M;
+            if ((rc = set_smem(attn_fwd_small_kernel<4>, bytes)) != SD_OK) return rc;
+            attn_fwd_small_kernel<4><<<grid, kThreads, bytes, st>>>(p);
+        } break;
         case 8: {
             const size_t bytes = sizeof(float) * kWarps * (size_t)M;
             if ((rc = set_smem(attn_fwd_small_kernel<8>, bytes)) != SD_OK) return rc;
@@ -454,6 +459,11 @@ extern "C" int sd_attention_bwd(const float* Q, long long ldq, const float* K, l
         attn_bwd_kernel<NVv><<<grid, kThreads, bytes, st>>>(p);                                                \
     }
     switch (dh) {
+        case 4: {
+            const size_t bytes = sizeof(float) * 2 * (size_t)T * M;
+            if ((rc = set_smem(attn_bwd_small_kernel<4>, bytes)) != SD_OK) return rc;
+            attn_bwd_small_kernel<4><<<grid, kThreads, bytes, st>>>(p);
+        } break;
         case 8: {
             const size_t bytes = sizeof(float) * 2 * (size_t)T * M;
             if ((rc = set_smem(attn_bwd_small_kernel<8>, bytes)) != SD_OK) return rc;
