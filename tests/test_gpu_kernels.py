@@ -87,7 +87,8 @@ def test_mse_affine_gather(ops):
     assert torch.equal(o.cpu()[:, 0], table[idx]) and err.item() == 0
     dt = torch.zeros(4, 128, device="cuda")
     do = torch.randn(5, 128)
-    ops.scatter_add_rows(do.cuda().data_ptr(), 128, idx.cuda(), dt)
+    dod = do.cuda()
+    ops.scatter_add_rows(dod.data_ptr(), 128, idx.cuda(), dt)
     want = torch.zeros(4, 128).index_add_(0, idx, do)
     assert rel(dt, want) < 1e-6
 
@@ -224,3 +225,61 @@ def test_bad_arguments_are_reported_not_crashes(ops):
         ops.attention_fwd(x.data_ptr(), 100, x.data_ptr(), 100, x.data_ptr(), 100, x.data_ptr(), 100, None, 1, 4, 1, 4, 25)
     with pytest.raises(_lib.SdError):
         ops.gemm(x, 100, ops.MK, x, 100, ops.NK, x, 4, 4, 4, 100, precision=7)
+
+
+# ---------------------------------------------------------------------------------------------------
+# bf16 tensor-core (tcgen05) GEMM: exact-arithmetic check against a float64 product of the bf16-ROUNDED
+# operands (fp32 accumulation in TMEM => ~1e-6), plus the loose 2e-2 check against the unrounded product.
+def _bf(x):
+    return x.to(torch.bfloat16).double()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (1, 128, 128), (37, 20, 20), (130, 384, 128), (1000, 128, 20),
+                                   (257, 144, 65), (300, 256, 256), (513, 32, 1568), (25600, 384, 128)])
+def test_tc_gemm_forward_epilogues(ops, M, N, K):
+    torch.manual_seed(M + N + K)
+    A, W, bias = torch.randn(M, K), torch.randn(N, K) / math.sqrt(K), torch.randn(N)
+    res, pe = torch.randn(M, N), torch.randn(7, N)
+    Ad, Wd = A.cuda(), W.cuda()
+    C = torch.empty(M, N, device="cuda")
+    ops.gemm(Ad, K, ops.MK, Wd, K, ops.NK, C, N, M, N, K, precision=ops.PREC_BF16, bias=bias.cuda())
+    exact = _bf(A) @ _bf(W).T + bias.double()
+    assert rel(C, exact) < 5e-6
+    assert rel(C, A.double() @ W.double().T + bias.double()) < 2e-2
+    if K in (128, 256):
+        gamma, beta = torch.rand(K) + 0.5, torch.randn(K) * 0.1
+        mean, rstd = ops.ln_stats(Ad, K)
+        pre = torch.empty(M, N, device="cuda")
+        ops.gemm(Ad, K, ops.MK, Wd, K, ops.NK, C, N, M, N, K, precision=ops.PREC_BF16,
+                 ln=(mean, rstd, gamma.cuda(), beta.cuda()), bias=bias.cuda(), pre_out=pre, ldp=N, act=ops.ACT_GELU,
+                 residual=res.cuda(), ldr=N)
+        xn = torch.nn.functional.layer_norm(A, (K,), gamma, beta, 1e-5)
+        z = _bf(xn) @ _bf(W).T + bias.double()
+        assert rel(pre, z) < 2e-3          # LN rounding differs by fp32 ulps before the bf16 rounding
+        assert rel(C, torch.nn.functional.gelu(z) + res.double()) < 2e-3
+    ops.gemm(Ad, K, ops.MK, Wd, K, ops.NK, C, N, M, N, K, precision=ops.PREC_BF16, bias=bias.cuda(), pe=pe.cuda(),
+             pe_period=7)
+    assert rel(C, exact + pe.double()[torch.arange(M) % 7]) < 5e-6
+
+
+@pytest.mark.parametrize("M,N,K", [(37, 20, 128), (1000, 128, 384), (25600, 128, 128), (3120, 256, 128)])
+def test_tc_gemm_dgrad_wgrad(ops, M, N, K):
+    torch.manual_seed(1)
+    dY, W, X = torch.randn(M, N), torch.randn(N, K), torch.randn(M, K)
+    dX = torch.empty(M, K, device="cuda")
+    ops.gemm(dY.cuda(), N, ops.MK, W.cuda(), K, ops.KN, dX, K, M, K, N, precision=ops.PREC_BF16)
+    assert rel(dX, _bf(dY) @ _bf(W)) < 5e-6
+    dW = torch.ones(N, K, device="cuda")
+    ops.gemm(dY.cuda(), N, ops.KM, X.cuda(), K, ops.KN, dW, K, N, K, M, precision=ops.PREC_BF16, accumulate=True)
+    assert rel(dW, 1.0 + _bf(dY).T @ _bf(X)) < 2e-5
+    dW2 = torch.empty(N, K, device="cuda")
+    ops.gemm(dY.cuda(), N, ops.KM, X.cuda(), K, ops.KN, dW2, K, N, K, M, precision=ops.PREC_BF16)
+    assert rel(dW2, _bf(dY).T @ _bf(X)) < 2e-5
+    if K == 128:
+        gamma, beta = torch.rand(K) + 0.5, torch.randn(K) * 0.1
+        mean, rstd = ops.ln_stats(X.cuda(), K)
+        dW.zero_()
+        ops.gemm(dY.cuda(), N, ops.KM, X.cuda(), K, ops.KN, dW, K, N, K, M, precision=ops.PREC_BF16,
+                 ln=(mean, rstd, gamma.cuda(), beta.cuda()), accumulate=True)
+        xn = torch.nn.functional.layer_norm(X, (K,), gamma, beta, 1e-5)
+        assert rel(dW, _bf(dY).T @ _bf(xn)) < 2e-3

@@ -317,3 +317,48 @@ def test_empty_batch_and_ragged_sizes():
             with torch.no_grad():
                 want = model_ref.forward(synth.synth_batch(hp, B, 3), x.cpu(), t.cpu(), sd, hp)
             assert rel(out, want) < TOL
+
+
+# ---------------------------------------------------------------------------------------------------
+# bf16 mode (tcgen05 GEMMs, fp32 accumulate / LayerNorm / softmax / residual stream): 2e-2 (north_star)
+@pytest.mark.parametrize("case", ["patch", "default"])
+def test_bf16_mode_inference_and_training_within_2e_2(manifest, case):
+    import soccerdiffusion_b200 as sdb
+    from soccerdiffusion_b200 import runtime
+    from soccerdiffusion_b200.functional import mse_loss
+
+    c = manifest["cases"][case]
+    hp, B, seed = CASES[case], c["batch_size"], c["seed"]
+    g = load_golden(case)
+    model, _ = synth_model(hp, seed)
+    batch = to_dev(synth.synth_batch(hp, B, seed))
+    x_T = synth.synth_noise("x_T", hp, B, seed).cuda()
+    t = synth.synth_timesteps(B, seed).cuda()
+    sdb.set_precision("bf16")
+    try:
+        model.eval()
+        with torch.no_grad():
+            ctx = model.encode_input_data(batch)
+            for i, cx in enumerate(ctx):
+                assert rel(cx, g[f"ctx{i}"]) < 2e-2, f"ctx{i}"
+            assert rel(model.forward_with_context(ctx, x_T, t), g["eps_eval"]) < 2e-2
+        runtime.set_dropout(0.0)
+        model.train()
+        noise = synth.synth_noise("eps", hp, B, seed).cuda()
+        x_t = torch.from_numpy(g["train_x_t"]).cuda()
+        pred = model(batch, x_t, t)
+        loss = mse_loss(pred, noise)
+        loss.backward()
+        assert rel(pred, g["train_pred"]) < 2e-2
+        assert abs(loss.item() - float(g["train_loss"])) < 2e-2 * abs(float(g["train_loss"]))
+        params = dict(model.named_parameters())
+        checked = 0
+        for key in g.files:
+            if key.startswith("grad/") and "image_encoder.encoder" not in key:
+                e = rel(params[key[5:]].grad, g[key])
+                assert e < 6e-2, (key, e)   # gradients: several bf16 GEMMs chained
+                checked += 1
+        assert checked > 10
+    finally:
+        sdb.set_precision("fp32")
+        runtime.set_dropout(0.1)
