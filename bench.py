@@ -266,14 +266,23 @@ def run_ours(args):
         clocks.start()
     ops.reset_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.ncu_range:
+        torch.cuda.profiler.start()   # ncu --profile-from-start off: only the timed region is captured
     e0.record()
     for _ in range(args.steps):
         step(batch)
     e1.record()
     sync()
+    if args.ncu_range:
+        torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     launches = ops.launches()
     clk = clocks.stop() if rank == 0 else None
+    if args.ncu_range:
+        if rank == 0:
+            print(json.dumps(dict(note="ncu range run: numbers under a profiler are not bench values", steps=args.steps,
+                                  ms_per_step=ms / args.steps, gpu_launches=launches)), flush=True)
+        return
 
     # ---- e2e: pinned host buffers -> device every step, loss read back every step ------------------
     for _ in range(1):
@@ -306,10 +315,14 @@ def run_ours(args):
         pe1.record()
         prof = ops.profile_end()
         step_ms = pe0.elapsed_time(pe1) / nprof
-        kernel_classes = {k: dict(launches_per_step=v["launches"] // nprof, ms_per_step=v["ms"] / nprof,
-                                  tflops=(v["flops"] / v["ms"] / 1e9 if v["ms"] > 0 else 0.0),
-                                  share_of_step=v["ms"] / nprof / step_ms) for k, v in prof.items()}
-        gemm = {k: v for k, v in prof.items() if "gemm" in k}
+        fmt = lambda v: dict(launches_per_step=v["launches"] // nprof, ms_per_step=round(v["ms"] / nprof, 4),
+                             tflops=round(v["flops"] / v["ms"] / 1e9, 2) if v["ms"] > 0 else 0.0,
+                             gbs=round(v["bytes"] / v["ms"] / 1e6, 1) if v["ms"] > 0 else 0.0,
+                             share_of_step=round(v["ms"] / nprof / step_ms, 4))
+        kernel_classes = {k: fmt(v) for k, v in prof.items() if " " not in k}
+        shapes = sorted(((k, v) for k, v in prof.items() if " " in k), key=lambda kv: -kv[1]["ms"])[:14]
+        kernel_classes["top_shapes"] = {k: fmt(v) for k, v in shapes}
+        gemm = {k: v for k, v in prof.items() if "gemm" in k and " " not in k}
         if gemm:
             top = max(gemm, key=lambda k: gemm[k]["ms"])
             v = gemm[top]
@@ -422,12 +435,14 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("SD_B200_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("SD_B200_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
     ap.add_argument("--cpu-batch", type=int, default=8, help="bounded CPU sample batch")
     ap.add_argument("--workload", default="full", choices=["full", "inscope", "denoiser"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ddim", action="store_true")
+    ap.add_argument("--ncu-range", action="store_true",
+                    help="bracket the timed region with cudaProfilerStart/Stop and stop after it (for ncu --profile-from-start off)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

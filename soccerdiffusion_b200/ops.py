@@ -51,18 +51,20 @@ def profile_end():
     rec, _profile = _profile, None
     torch.cuda.synchronize()
     out = {}
-    for name, e0, e1, flops, nbytes in rec or []:
-        d = out.setdefault(name, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
-        d["launches"] += 1
-        d["ms"] += e0.elapsed_time(e1)
-        d["flops"] += flops
-        d["bytes"] += nbytes
+    for name, e0, e1, flops, nbytes, detail in rec or []:
+        ms = e0.elapsed_time(e1)
+        for key in (name, name + " " + detail) if detail else (name,):
+            d = out.setdefault(key, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+            d["launches"] += 1
+            d["ms"] += ms
+            d["flops"] += flops
+            d["bytes"] += nbytes
     return out
 
 
 class _Timed:
-    def __init__(self, name, flops=0.0, nbytes=0.0):
-        self.name, self.flops, self.nbytes = name, flops, nbytes
+    def __init__(self, name, flops=0.0, nbytes=0.0, detail=""):
+        self.name, self.flops, self.nbytes, self.detail = name, flops, nbytes, detail
 
     def __enter__(self):
         if _profile is not None:
@@ -74,7 +76,7 @@ class _Timed:
     def __exit__(self, *exc):
         if _profile is not None and exc[0] is None:
             self.e1.record()
-            _profile.append((self.name, self.e0, self.e1, self.flops, self.nbytes))
+            _profile.append((self.name, self.e0, self.e1, self.flops, self.nbytes, self.detail))
         return False
 
 
@@ -110,7 +112,8 @@ def gemm(A, lda, a_layout, B, ldb, b_layout, C_, ldc, M, N, K, *, precision=PREC
     d.residual, d.ldr = P(residual), ldr
     d.accumulate = 1 if accumulate else 0
     kind = "gemm_wgrad" if a_layout == KM else ("gemm_dgrad" if b_layout == KN else "gemm_fwd")
-    with _Timed(("tc_" if precision == PREC_BF16 else "f32_") + kind, 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N)):
+    with _Timed(("tc_" if precision == PREC_BF16 else "f32_") + kind, 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N),
+                f"[{M}x{N}x{K}]"):
         check(_lib.lib().sd_gemm(C.byref(d), stream_ptr()), "sd_gemm")
     _count()
 
@@ -134,7 +137,7 @@ def ln_bwd(g, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, M, d):
 
 def attention_fwd(Q, ldq, K, ldk, V, ldv, O, ldo, lse, B, H, T, M, dh, dropout=None):
     p, seed, sid = dropout if dropout is not None else (0.0, 0, 0)
-    with _Timed("attention_fwd", 4.0 * B * H * T * M * dh, 4.0 * B * H * dh * (2 * T + 2 * M)):
+    with _Timed("attention_fwd", 4.0 * B * H * T * M * dh, 4.0 * B * H * dh * (2 * T + 2 * M), f"[B{B} H{H} T{T} M{M} dh{dh}]"):
         check(_lib.lib().sd_attention_fwd(Q, ldq, K, ldk, V, ldv, O, ldo, lse, B, H, T, M, dh, p, seed, sid,
                                           stream_ptr()), "sd_attention_fwd")
     _count()
@@ -143,7 +146,7 @@ def attention_fwd(Q, ldq, K, ldk, V, ldv, O, ldo, lse, B, H, T, M, dh, dropout=N
 def attention_bwd(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, dQ, lddq, dK, lddk, dV, lddv, B, H, T, M, dh,
                   dropout=None):
     p, seed, sid = dropout if dropout is not None else (0.0, 0, 0)
-    with _Timed("attention_bwd", 10.0 * B * H * T * M * dh, 4.0 * B * H * dh * (4 * T + 4 * M)):
+    with _Timed("attention_bwd", 10.0 * B * H * T * M * dh, 4.0 * B * H * dh * (4 * T + 4 * M), f"[B{B} H{H} T{T} M{M} dh{dh}]"):
         check(_lib.lib().sd_attention_bwd(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, dQ, lddq, dK, lddk, dV, lddv,
                                           B, H, T, M, dh, p, seed, sid, stream_ptr()), "sd_attention_bwd")
     _count()
