@@ -91,6 +91,8 @@ SIGNATURES = {
     "sd_plan_set_context": [C.c_void_p, c_f, c_i, c_f],
     "sd_plan_sample": [C.c_void_p, c_f, c_f, c_f, c_i, c_f],
     "sd_plan_denoise": [C.c_void_p, c_f, c_f, c_i, c_f, c_f],
+    "sd_plan_set_sampler": [C.c_void_p, c_i],
+    "sd_plan_last_sampler": [C.c_void_p],
 }
 
 _lib = None

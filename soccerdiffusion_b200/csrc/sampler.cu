@@ -25,8 +25,13 @@
 #include "common.cuh"
 #include "../../include/sd_b200.h"
 
+#include <cooperative_groups.h>
+#include <cstdlib>
+#include <cstring>
 #include <new>
 #include <vector>
+
+namespace cg = cooperative_groups;
 
 using namespace sd;
 
@@ -333,6 +338,430 @@ size_t sampler_smem_bytes(int d, int J, int H, int Mpad) {
     return f * sizeof(float);
 }
 
+
+// ==========================================================================================
+// Cluster sampler: ONE THREAD-BLOCK CLUSTER (16 CTAs = 16 SMs) per trajectory.
+//
+// bs=1 robot control is latency-bound: a single CTA leaves 147 SMs idle and streams the
+// decoder weights (2 MB fp32) from L2 every step.  Here every CTA of the cluster owns 1/16 of the OUTPUT
+// COLUMNS of every projection and keeps that weight slice resident in its shared memory for all steps;
+// per projection each CTA computes its (T x N/16) slice and pushes it into the activation buffer of all
+// 16 peers through distributed shared memory, one cluster barrier per projection (7 per layer).
+// Cross-attention is split (head, key quarter) over the 16 CTAs flash-decoding style: each CTA produces
+// (max, sum, partial PV) for its keys, every CTA combines the partials.  Self-attention (T x T),
+// LayerNorm, residual adds, the embedding / output projections and the DDIM update are tiny and are
+// computed redundantly by every CTA so that no further exchange is needed.
+constexpr int kClusterSize = 16;
+constexpr int kClThreads = 256;
+
+struct ClusterLayout {   // offsets in floats inside dynamic shared memory
+    int w, act0, act1, h, xT, xs, eps, cab, sc, red, total;
+};
+
+__host__ __device__ inline int align4(int x) { return (x + 3) & ~3; }
+
+__host__ __device__ inline ClusterLayout cluster_layout(int d, int L_res, int TR, int J, int H, int M) {
+    const int C = kClusterSize;
+    const int dh = d / H;
+    const int parts = C / H;
+    const int Mq = (M + parts - 1) / parts;
+    const int Jp = (J + 3) & ~3;
+    int G = kClThreads / (Mq > 0 ? Mq : 1);
+    if (G > dh) G = dh;
+    if (G < 1) G = 1;
+    const int groups2 = kClThreads / dh > 0 ? kClThreads / dh : 1;
+    ClusterLayout o;
+    int cur = 0;
+    o.w = cur;    cur += align4(L_res * 8 * (d / C) * d);        // (3 + 5) slices of d/C columns each
+    o.act0 = cur; cur += align4(3 * d * TR);
+    o.act1 = cur; cur += align4(3 * d * TR);
+    o.h = cur;    cur += align4(TR * d);
+    o.xT = cur;   cur += align4(d * TR);
+    o.xs = cur;   cur += align4(TR * Jp);
+    o.eps = cur;  cur += align4(TR * Jp);
+    o.cab = cur;  cur += align4(C * (2 * TR + TR * dh));
+    o.sc = cur;   cur += align4(TR * (Mq + 1));
+    const int red1 = G * TR * Mq, red2 = groups2 * TR * dh;
+    o.red = cur;  cur += align4(red1 > red2 ? red1 : red2);
+    o.total = cur;
+    return o;
+}
+
+// out[t][j] for the CTA's column slice: W(j,k) = Wb[j*sj + k*sk]; xT [K][TR].  Warp per column, lanes over k,
+// butterfly reduction; afterwards lane (t + 16*half) holds out[t][j] and pushes it to half of the peers.
+template <int TR, class Epi>
+__device__ __forceinline__ void slice_gemm(const float* Wb, int sj, int sk, int ncols, int K, const float* xT, Epi epi) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int j = warp; j < ncols; j += nw) {
+        float acc[TR];
+#pragma unroll
+        for (int t = 0; t < TR; ++t) acc[t] = 0.f;
+        const float* wj = Wb + (long long)j * sj;
+        for (int k = lane; k < K; k += 32) {
+            const float w = wj[(long long)k * sk];
+            const float4* xp = reinterpret_cast<const float4*>(xT + k * TR);
+#pragma unroll
+            for (int q = 0; q < TR / 4; ++q) {
+                const float4 x4 = xp[q];
+                acc[4 * q + 0] = fmaf(w, x4.x, acc[4 * q + 0]);
+                acc[4 * q + 1] = fmaf(w, x4.y, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(w, x4.z, acc[4 * q + 2]);
+                acc[4 * q + 3] = fmaf(w, x4.w, acc[4 * q + 3]);
+            }
+        }
+        float v = 0.f;
+#pragma unroll
+        for (int t = 0; t < TR; ++t) {
+            const float sum = warp_sum(acc[t]);
+            if ((lane & 15) == t) v = sum;
+        }
+        epi(j, lane & 15, lane >> 4, v);
+    }
+}
+
+template <int TR>
+__global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const SamplerArgs a, const int L_res) {
+    extern __shared__ __align__(16) float smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    constexpr int C = kClusterSize;
+    const int rank = (int)cluster.block_rank();
+    const int b = blockIdx.x / C;
+    const int d = a.d, T = a.T, J = a.J, H = a.heads, dh = a.dh, M = a.M, Mpad = a.Mpad, L = a.L;
+    const int nd = d / C, nq = 3 * nd;
+    const int Jp = (J + 3) & ~3;
+    const ClusterLayout lo = cluster_layout(d, L_res, TR, J, H, M);
+    float* Wres = smem + lo.w;
+    float* act[2] = {smem + lo.act0, smem + lo.act1};
+    float* h = smem + lo.h;
+    float* xT = smem + lo.xT;
+    float* xs = smem + lo.xs;
+    float* eps = smem + lo.eps;
+    float* cab = smem + lo.cab;
+    float* sc = smem + lo.sc;
+    float* red = smem + lo.red;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const float scale = rsqrtf((float)dh);
+    const int parts = C / H;
+    const int Mq = (M + parts - 1) / parts;
+    const int hc = rank % H, kp = rank / H;
+    const int m_lo = min(M, kp * Mq), m_hi = min(M, (kp + 1) * Mq), nk = m_hi - m_lo;
+    const int RS = 2 * TR + TR * dh;   // cross-attention partial record: max[TR] | sum[TR] | O[T][dh]
+    const int per_layer = 8 * nd * d;
+
+    // ---- one-time: weight slices -> shared memory (k contiguous per output column) -----------------
+    for (int l = 0; l < L_res; ++l) {
+        const LayerPtrs& P = a.layers[l];
+        float* wl = Wres + l * per_layer;
+        const float* srcs[6] = {P.sa_wqkv_t, P.sa_wo_t, P.ca_wq_t, P.ca_wo_t, P.w1_t, P.w2_t};
+        const int ncs[6] = {nq, nd, nd, nd, nd, nd};
+        const int Ns[6] = {3 * d, d, d, d, d, d};
+        int off = 0;
+        for (int g = 0; g < 6; ++g) {
+            const int nc = ncs[g], N = Ns[g];
+            if (g == 0) {
+                // q, k, v column blocks: slice j covers columns {part*d + rank*nd + jj}
+                for (int i = tid; i < nc * d; i += blockDim.x) {
+                    const int k = i / nc, j = i % nc;
+                    const int col = (j / nd) * d + rank * nd + (j % nd);
+                    wl[off + j * d + k] = __ldg(srcs[g] + (long long)k * N + col);
+                }
+            } else {
+                for (int i = tid; i < nc * d; i += blockDim.x) {
+                    const int k = i / nc, j = i % nc;
+                    wl[off + j * d + k] = __ldg(srcs[g] + (long long)k * N + rank * nd + j);
+                }
+            }
+            off += nc * d;
+        }
+    }
+    for (int i = tid; i < T * J; i += blockDim.x) xs[(i / J) * Jp + (i % J)] = a.x_in[(long long)b * T * J + i];
+    for (int i = tid; i < d * TR; i += blockDim.x) xT[i] = 0.f;
+    for (int i = tid; i < 3 * d * TR; i += blockDim.x) { act[0][i] = 0.f; act[1][i] = 0.f; }
+    __syncthreads();
+    cluster.sync();
+
+    int ph = 0;   // activation ping-pong phase
+    // weight slice accessor: resident layers read smem [j][k]; others read the K-major blob in global memory
+    auto wslice = [&](int l, int g, const float* gsrc, int N, const float*& base, int& sj, int& sk) {
+        if (l < L_res) {
+            base = Wres + l * per_layer + (g == 0 ? 0 : nq * d + (g - 1) * nd * d);
+            sj = d; sk = 1;
+        } else {
+            base = gsrc + rank * nd;   // g==0 handled by the caller (three column blocks)
+            sj = 1; sk = N;
+        }
+    };
+    // push one value to half of the peers' buffer `buf` at offset `o`
+    auto push = [&](float* buf, int o, int half, float v) {
+#pragma unroll
+        for (int p = 0; p < C / 2; ++p) cluster.map_shared_rank(buf, half * (C / 2) + p)[o] = v;
+    };
+
+    for (int s = 0; s < a.num_steps; ++s) {
+        // ---- embedding + positional encoding (redundant in every CTA) ------------------------------
+        for (int i = tid; i < T * d; i += blockDim.x) {
+            const int t = i / d, n = i % d;
+            float acc = __ldg(a.io.emb_b + n) + __ldg(a.io.pe + t * d + n);
+            for (int j = 0; j < J; ++j) acc = fmaf(xs[t * Jp + j], __ldg(a.io.emb_wt + j * d + n), acc);
+            h[i] = acc;
+        }
+        __syncthreads();
+
+        for (int l = 0; l < L; ++l) {
+            const LayerPtrs& P = a.layers[l];
+            const float* wb; int sj, sk;
+            // ---- self-attention ---------------------------------------------------------------------
+            cta_layernorm_T<TR>(h, d, T, P.ln1_g, P.ln1_b, xT);
+            {
+                float* dst = act[ph & 1];
+                if (l < L_res) {
+                    wslice(l, 0, nullptr, 0, wb, sj, sk);
+                    slice_gemm<TR>(wb, sj, sk, nq, d, xT, [&](int j, int t, int half, float v) {
+                        const int col = (j / nd) * d + rank * nd + (j % nd);
+                        if (t < T) push(dst, col * TR + t, half, v + __ldg(P.sa_bqkv + col));
+                    });
+                } else {
+                    for (int part = 0; part < 3; ++part)
+                        slice_gemm<TR>(P.sa_wqkv_t + part * d + rank * nd, 1, 3 * d, nd, d, xT,
+                                       [&](int j, int t, int half, float v) {
+                                           const int col = part * d + rank * nd + j;
+                                           if (t < T) push(dst, col * TR + t, half, v + __ldg(P.sa_bqkv + col));
+                                       });
+                }
+            }
+            cluster.sync();
+            {
+                const float* qkv = act[ph & 1];   // [3d][TR]
+                ++ph;
+                for (int pair = warp; pair < H * T; pair += nwarps) {
+                    const int hh = pair / T, t = pair % T;
+                    float scv = -INFINITY;
+                    if (lane < T) {
+                        float acc = 0.f;
+                        for (int c = 0; c < dh; ++c)
+                            acc = fmaf(qkv[(hh * dh + c) * TR + t], qkv[(d + hh * dh + c) * TR + lane], acc);
+                        scv = acc * scale;
+                    }
+                    const float mx = warp_max(scv);
+                    const float e = lane < T ? expf(scv - mx) : 0.f;
+                    const float p = e / warp_sum(e);
+                    for (int c0 = 0; c0 < dh; c0 += 32) {
+                        const int c = c0 + lane;
+                        float o = 0.f;
+                        for (int m = 0; m < T; ++m) {
+                            const float pm = __shfl_sync(0xffffffffu, p, m);
+                            if (c < dh) o = fmaf(pm, qkv[(2 * d + hh * dh + c) * TR + m], o);
+                        }
+                        if (c < dh) xT[(hh * dh + c) * TR + t] = o;
+                    }
+                }
+                __syncthreads();
+            }
+            {
+                float* dst = act[ph & 1];
+                wslice(l, 1, P.sa_wo_t, d, wb, sj, sk);
+                slice_gemm<TR>(wb, sj, sk, nd, d, xT, [&](int j, int t, int half, float v) {
+                    const int col = rank * nd + j;
+                    if (t < T) push(dst, col * TR + t, half, v + __ldg(P.sa_bo + col));
+                });
+            }
+            cluster.sync();
+            {
+                const float* dl = act[ph & 1];
+                ++ph;
+                for (int i = tid; i < T * d; i += blockDim.x) h[i] += dl[(i % d) * TR + (i / d)];
+                __syncthreads();
+            }
+            // ---- cross-attention --------------------------------------------------------------------
+            cta_layernorm_T<TR>(h, d, T, P.ln2_g, P.ln2_b, xT);
+            {
+                float* dst = act[ph & 1];
+                wslice(l, 2, P.ca_wq_t, d, wb, sj, sk);
+                slice_gemm<TR>(wb, sj, sk, nd, d, xT, [&](int j, int t, int half, float v) {
+                    const int col = rank * nd + j;
+                    if (t < T) push(dst, col * TR + t, half, (v + __ldg(P.ca_bq + col)) * scale);
+                });
+            }
+            cluster.sync();
+            {
+                const float* q = act[ph & 1];   // [d][TR], pre-scaled
+                ++ph;
+                const float* Kt = a.Kt + ((long long)l * a.B + b) * (long long)H * dh * Mpad + (long long)hc * dh * Mpad;
+                const float* Vc = a.Vc + ((long long)l * a.B + b) * (long long)Mpad * d + hc * dh;
+                const float* tk = a.tok_kv + ((long long)s * L + l) * 2 * d;
+                // scores for this CTA's keys: thread = (key, c-group)
+                int G = min(dh, kClThreads / max(Mq, 1));   // same formula as cluster_layout()
+                if (G < 1) G = 1;
+                const int cpg = (dh + G - 1) / G;
+                for (int idx = tid; idx < nk * G; idx += blockDim.x) {
+                    const int mi = idx % nk, g = idx / nk;
+                    const int m = m_lo + mi;
+                    float acc[TR];
+#pragma unroll
+                    for (int t = 0; t < TR; ++t) acc[t] = 0.f;
+                    const int c1 = min(dh, (g + 1) * cpg);
+                    for (int c = g * cpg; c < c1; ++c) {
+                        const float kv = (m == M - 1) ? __ldg(tk + hc * dh + c) : __ldcg(Kt + (long long)c * Mpad + m);
+                        const float4* qp = reinterpret_cast<const float4*>(q + (hc * dh + c) * TR);
+#pragma unroll
+                        for (int qq = 0; qq < TR / 4; ++qq) {
+                            const float4 x4 = qp[qq];
+                            acc[4 * qq + 0] = fmaf(kv, x4.x, acc[4 * qq + 0]);
+                            acc[4 * qq + 1] = fmaf(kv, x4.y, acc[4 * qq + 1]);
+                            acc[4 * qq + 2] = fmaf(kv, x4.z, acc[4 * qq + 2]);
+                            acc[4 * qq + 3] = fmaf(kv, x4.w, acc[4 * qq + 3]);
+                        }
+                    }
+#pragma unroll
+                    for (int t = 0; t < TR; ++t) red[(g * TR + t) * Mq + mi] = acc[t];
+                }
+                __syncthreads();
+                for (int idx = tid; idx < T * nk; idx += blockDim.x) {
+                    const int t = idx / nk, mi = idx % nk;
+                    float v = 0.f;
+                    for (int g = 0; g < G; ++g) v += red[(g * TR + t) * Mq + mi];
+                    sc[t * (Mq + 1) + mi] = v;
+                }
+                __syncthreads();
+                // partial softmax (unnormalised) per query row; record header pushed to every peer
+                for (int t = warp; t < T; t += nwarps) {
+                    float mx = -INFINITY;
+                    for (int mi = lane; mi < nk; mi += 32) mx = fmaxf(mx, sc[t * (Mq + 1) + mi]);
+                    mx = warp_max(mx);
+                    float sum = 0.f;
+                    for (int mi = lane; mi < nk; mi += 32) {
+                        const float e = expf(sc[t * (Mq + 1) + mi] - mx);
+                        sc[t * (Mq + 1) + mi] = e;
+                        sum += e;
+                    }
+                    sum = warp_sum(sum);
+                    if (lane < C) {
+                        float* rc = cluster.map_shared_rank(cab, lane) + rank * RS;
+                        rc[t] = mx;
+                        rc[TR + t] = sum;
+                    }
+                }
+                __syncthreads();
+                // partial P.V : thread = (c, key group)
+                const int groups2 = max(1, kClThreads / dh);
+                {
+                    const int c = tid % dh, g = tid / dh;
+                    if (g < groups2) {
+                        float acc[TR];
+#pragma unroll
+                        for (int t = 0; t < TR; ++t) acc[t] = 0.f;
+                        for (int mi = g; mi < nk; mi += groups2) {
+                            const int m = m_lo + mi;
+                            const float vv = (m == M - 1) ? __ldg(tk + d + hc * dh + c) : __ldcg(Vc + (long long)m * d + c);
+#pragma unroll
+                            for (int t = 0; t < TR; ++t)
+                                if (t < T) acc[t] = fmaf(sc[t * (Mq + 1) + mi], vv, acc[t]);
+                        }
+#pragma unroll
+                        for (int t = 0; t < TR; ++t) red[(g * TR + t) * dh + c] = acc[t];
+                    }
+                }
+                __syncthreads();
+                for (int idx = tid; idx < T * dh; idx += blockDim.x) {
+                    const int t = idx / dh, c = idx % dh;
+                    float v = 0.f;
+                    for (int g = 0; g < groups2; ++g) v += red[(g * TR + t) * dh + c];
+#pragma unroll
+                    for (int p = 0; p < C; ++p) cluster.map_shared_rank(cab, p)[rank * RS + 2 * TR + t * dh + c] = v;
+                }
+            }
+            cluster.sync();
+            // combine the partials of all key parts -> O (every CTA, redundantly), transposed into xT
+            for (int i = tid; i < T * d; i += blockDim.x) {
+                const int t = i / d, n = i % d;
+                const int hh = n / dh, c = n % dh;
+                float mx = -INFINITY;
+                for (int p2 = 0; p2 < parts; ++p2) mx = fmaxf(mx, cab[(p2 * H + hh) * RS + t]);
+                float num = 0.f, den = 0.f;
+                for (int p2 = 0; p2 < parts; ++p2) {
+                    const float* rc = cab + (p2 * H + hh) * RS;
+                    const float mk = rc[t];
+                    const float wgt = (mk == -INFINITY) ? 0.f : expf(mk - mx);
+                    num = fmaf(wgt, rc[2 * TR + t * dh + c], num);
+                    den = fmaf(wgt, rc[TR + t], den);
+                }
+                xT[n * TR + t] = num / den;
+            }
+            __syncthreads();
+            {
+                float* dst = act[ph & 1];
+                wslice(l, 3, P.ca_wo_t, d, wb, sj, sk);
+                slice_gemm<TR>(wb, sj, sk, nd, d, xT, [&](int j, int t, int half, float v) {
+                    const int col = rank * nd + j;
+                    if (t < T) push(dst, col * TR + t, half, v + __ldg(P.ca_bo + col));
+                });
+            }
+            cluster.sync();
+            {
+                const float* dl = act[ph & 1];
+                ++ph;
+                for (int i = tid; i < T * d; i += blockDim.x) h[i] += dl[(i % d) * TR + (i / d)];
+                __syncthreads();
+            }
+            // ---- feed-forward -----------------------------------------------------------------------
+            cta_layernorm_T<TR>(h, d, T, P.ln3_g, P.ln3_b, xT);
+            {
+                float* dst = act[ph & 1];
+                wslice(l, 4, P.w1_t, d, wb, sj, sk);
+                slice_gemm<TR>(wb, sj, sk, nd, d, xT, [&](int j, int t, int half, float v) {
+                    const int col = rank * nd + j;
+                    if (t < T) push(dst, col * TR + t, half, gelu_erf(v + __ldg(P.b1 + col)));
+                });
+            }
+            cluster.sync();
+            {
+                const float* ff = act[ph & 1];   // [d][TR] = GEMM input layout already
+                ++ph;
+                float* dst = act[ph & 1];
+                wslice(l, 5, P.w2_t, d, wb, sj, sk);
+                slice_gemm<TR>(wb, sj, sk, nd, d, ff, [&](int j, int t, int half, float v) {
+                    const int col = rank * nd + j;
+                    if (t < T) push(dst, col * TR + t, half, v + __ldg(P.b2 + col));
+                });
+            }
+            cluster.sync();
+            {
+                const float* dl = act[ph & 1];
+                ++ph;
+                for (int i = tid; i < T * d; i += blockDim.x) h[i] += dl[(i % d) * TR + (i / d)];
+                __syncthreads();
+            }
+        }
+
+        // ---- output projection + DDIM update (redundant) --------------------------------------------
+        for (int i = tid; i < T * J; i += blockDim.x) {
+            const int t = i / J, j = i % J;
+            float acc = __ldg(a.io.fc_b + j);
+            for (int k = 0; k < d; ++k) acc = fmaf(h[t * d + k], __ldg(a.io.fc_wt + k * J + j), acc);
+            eps[t * Jp + j] = acc;
+        }
+        __syncthreads();
+        const float sb = __ldg(a.coef + 4 * s + 0), sa = __ldg(a.coef + 4 * s + 1);
+        const float sap = __ldg(a.coef + 4 * s + 2), sbp = __ldg(a.coef + 4 * s + 3);
+        for (int i = tid; i < T * J; i += blockDim.x) {
+            const int o = (i / J) * Jp + (i % J);
+            const float e = eps[o];
+            if (a.eps_out && rank == 0) a.eps_out[((long long)s * a.B + b) * T * J + i] = e;
+            const float x0 = (xs[o] - sb * e) / sa;
+            xs[o] = sap * x0 + sbp * e;
+        }
+        __syncthreads();
+    }
+    if (rank == 0) {
+        for (int i = tid; i < T * J; i += blockDim.x) {
+            float v = xs[(i / J) * Jp + (i % J)];
+            if (a.denorm) v = v * __ldg(a.io.stdv + i % J) + __ldg(a.io.mean + i % J);
+            a.x_out[(long long)b * T * J + i] = v;
+        }
+    }
+    cluster.sync();   // no CTA may exit while peers can still address its shared memory
+}
+
 // dst[c][r] = src[r][c]
 __global__ void transpose_kernel(const float* __restrict__ src, long long ld_src, float* __restrict__ dst, int rows,
                                  int cols) {
@@ -387,6 +816,8 @@ struct sd_plan {
     int num_steps = 0, sched_cap = 0;
     int ctx_B = 0;
     bool layers_dirty = true;
+    int sampler_mode = 0;   // 0 auto, 1 one CTA per trajectory, 2 one 16-CTA cluster per trajectory
+    int last_sampler = 0;   // which kernel the last sd_plan_sample launched (1 / 2)
 };
 
 namespace {
@@ -594,7 +1025,88 @@ int launch_sampler(sd_plan* p, SamplerArgs& a, cudaStream_t st) {
     SD_LAUNCH_CHECK();
     return SD_OK;
 }
+// 0: auto, 1: one CTA per trajectory, 2: one 16-CTA cluster per trajectory   (SD_B200_SAMPLER=auto|cta|cluster)
+int sampler_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("SD_B200_SAMPLER");
+        mode = (!e || !strcmp(e, "auto")) ? 0 : (!strcmp(e, "cta") ? 1 : (!strcmp(e, "cluster") ? 2 : 0));
+    }
+    return mode;
+}
+
+template <int TR>
+int launch_cluster(sd_plan* p, SamplerArgs& a, cudaStream_t st, bool* launched) {
+    *launched = false;
+    const int C = kClusterSize;
+    if (a.d % C != 0 || C % a.heads != 0 || a.T > 16 || a.T > TR || a.dh > kClThreads) return SD_OK;
+    // resident layers: as many as fit beside the working buffers
+    int L_res = a.L;
+    size_t bytes = 0;
+    for (; L_res >= 0; --L_res) {
+        bytes = (size_t)cluster_layout(a.d, L_res, TR, a.J, a.heads, a.M).total * sizeof(float);
+        if (bytes <= 227 * 1024) break;
+    }
+    if (L_res < 0) return SD_OK;
+    auto kernel = sampler_cluster_kernel<TR>;
+    static bool configured = false;
+    static bool usable = true;
+    if (!usable) return SD_OK;
+    if (!configured) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+            cudaGetLastError();
+            usable = false;
+            return SD_OK;
+        }
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(a.B * C));
+    cfg.blockDim = dim3(kClThreads);
+    cfg.dynamicSmemBytes = bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static size_t checked_bytes = 0;
+    if (checked_bytes != bytes) {
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, kernel, &cfg) != cudaSuccess || nclusters < 1) {
+            cudaGetLastError();
+            usable = false;   // this device cannot co-schedule 16 CTAs of this size: use the single-CTA sampler
+            return SD_OK;
+        }
+        checked_bytes = bytes;
+    }
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, a, L_res);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        usable = false;
+        return SD_OK;
+    }
+    *launched = true;
+    return SD_OK;
+}
+
 int run_sampler(sd_plan* p, SamplerArgs& a, cudaStream_t st) {
+    const int mode = p->sampler_mode != 0 ? p->sampler_mode : sampler_mode();
+    p->last_sampler = 1;
+    if (a.tok_mode == 0 && mode != 1 && (mode == 2 || a.B <= 64)) {
+        bool launched = false;
+        int rc = SD_OK;
+        if (a.T <= 12) rc = launch_cluster<12>(p, a, st, &launched);
+        else if (a.T <= 16) rc = launch_cluster<16>(p, a, st, &launched);
+        if (rc != SD_OK) return rc;
+        if (launched) {
+            p->last_sampler = 2;
+            return SD_OK;
+        }
+    }
     if (a.T <= 12) return launch_sampler<12>(p, a, st);
     if (a.T <= 20) return launch_sampler<20>(p, a, st);
     if (a.T <= 32) return launch_sampler<32>(p, a, st);
@@ -618,6 +1130,15 @@ extern "C" int sd_plan_sample(sd_plan* p, const float* x_T, float* x_out, float*
     a.x_in = x_T; a.x_out = x_out; a.eps_out = eps_trace; a.denorm = denormalize;
     return run_sampler(p, a, (cudaStream_t)stream);
 }
+
+extern "C" int sd_plan_set_sampler(sd_plan* p, int mode) {
+    if (!p) return SD_ERR_NO_PLAN;
+    if (mode < 0 || mode > 2) return SD_ERR_BAD_ARG;
+    p->sampler_mode = mode;
+    return SD_OK;
+}
+
+extern "C" int sd_plan_last_sampler(const sd_plan* p) { return p ? p->last_sampler : SD_ERR_NO_PLAN; }
 
 extern "C" int sd_plan_denoise(sd_plan* p, const float* x, const void* t, int t_is_float, float* eps_out,
                                void* stream) {

@@ -282,7 +282,7 @@ class End2EndDiffusionTransformer(nn.Module):
 
     @torch.no_grad()
     def sample(self, context: list[torch.Tensor], x_T: torch.Tensor, scheduler, num_inference_steps: int | None = None,
-               denormalize: bool = False, return_trace: bool = False):
+               denormalize: bool = False, return_trace: bool = False, sampler: str = "auto"):
         """Runs the complete DDIM loop of ros.py:301-310 / distill.py:179-189 in one persistent kernel.
 
         ``scheduler`` is a ``soccerdiffusion_b200.schedulers.DDIMScheduler`` whose ``set_timesteps`` has
@@ -295,6 +295,8 @@ class End2EndDiffusionTransformer(nn.Module):
             scheduler.set_timesteps(num_inference_steps)
         B, T, J = x_T.shape
         plan = self._plan_for(sum(c.shape[1] for c in context), T)
+        _lib.check(_lib.lib().sd_plan_set_sampler(plan.handle, {"auto": 0, "cta": 1, "cluster": 2}[sampler]),
+                   "sd_plan_set_sampler")
         self._set_context(plan, context)
         ts, coef = scheduler.schedule_tables()
         ssig = (tuple(ts), coef.tobytes())
@@ -312,4 +314,5 @@ class End2EndDiffusionTransformer(nn.Module):
         _lib.check(_lib.lib().sd_plan_sample(plan.handle, xin.data_ptr(), out.data_ptr(), _lib.ptr(trace),
                                              1 if denormalize else 0, _lib.stream_ptr()), "sd_plan_sample")
         ops._count()
+        self.last_sampler = {1: "cta", 2: "cluster"}.get(_lib.lib().sd_plan_last_sampler(plan.handle), "?")
         return (out, trace) if return_trace else out
