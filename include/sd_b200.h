@@ -135,6 +135,24 @@ int sd_dropout_apply(const float* x, float* y, long long n, float p, unsigned lo
                      void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Image-trunk non-convolution layers, bf16 NHWC (x[R][C], R = N*H*W, C a multiple of 8 dividing 2048).
+ * Replace nn.BatchNorm2d (train: batch statistics + running-stat update; eval: pass running stats as
+ * mean/invstd) fused with ReLU and the residual add of torchvision's BasicBlock/Bottleneck, and the stem's
+ * MaxPool2d(3, 2, 1) — ml/model/encoder/image.py:46-52 (convolutions remain cuDNN calls).
+ * `sums` is a caller-provided scratch of 2*C doubles. */
+int sd_bn_stats_nhwc_bf16(const void* x, long long R, int C, double* sums, float eps, float momentum, float* mean,
+                          float* invstd, float* running_mean, float* running_var, void* stream);
+int sd_bn_apply_nhwc_bf16(const void* x, const void* residual, const float* mean, const float* invstd, const float* gamma,
+                          const float* beta, int relu, void* y, long long R, int C, void* stream);
+/* dy -> (dx, dresidual = dy*relu_mask, dgamma, dbeta); y_relu = forward output when ReLU was fused, else NULL */
+int sd_bn_bwd_nhwc_bf16(const void* dy, const void* y_relu, const void* x, const float* mean, const float* invstd,
+                        const float* gamma, double* sums, void* dx, void* dres, float* dgamma, float* dbeta, long long R,
+                        int C, void* stream);
+/* idx: one byte per output element (arg-max tap 0..8) */
+int sd_maxpool3x3s2_nhwc_bf16_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, void* stream);
+int sd_maxpool3x3s2_nhwc_bf16_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Persistent DDIM sampler (ros.py:301-310, distill.py:179-189): one launch = all steps.
  */
 typedef struct sd_plan sd_plan;

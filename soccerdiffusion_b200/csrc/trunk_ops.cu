@@ -1,0 +1,349 @@
+// HBM-bound kernels of the image trunk's non-convolution layers, bf16 NHWC ("channels_last"):
+// training/eval BatchNorm fused with ReLU and the residual add, and the 3x3/stride-2 max-pool — forward and
+// backward.  The convolutions themselves stay cuDNN library calls (SURVEY.md §8 a8', row (f)-1); these kernels
+// replace torch's batch_norm_*_channels_last / max_pool_*_nhwc / elementwise kernels, which the round-1 launch
+// list showed to be 52 % of the full training step at ~10 % of HBM bandwidth.
+//
+// Reference semantics: torchvision resnet BasicBlock/Bottleneck (bn -> relu, bn -> (+identity) -> relu,
+// downsample bn), nn.BatchNorm2d training mode (batch statistics, biased variance for normalisation, unbiased
+// for running_var, momentum 0.1, eps 1e-5) as run by ml/model/encoder/image.py:46-52 under train().
+//
+// Layout: x[R][C] bf16, R = N*H*W, C in {64,...,2048} multiple of 8.  Every thread owns 8 consecutive channels
+// (one 16-byte vector) and walks rows with a stride that keeps its channel group fixed, so per-channel
+// parameters / accumulators live in registers and all accesses are 16-byte, fully coalesced.
+#include "common.cuh"
+#include "../../include/sd_b200.h"
+
+using namespace sd;
+
+namespace {
+
+constexpr int kT = 256;
+
+struct bf8 { uint4 u; };
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 v = __bfloat1622float2(p[i]);
+        f[2 * i] = v.x;
+        f[2 * i + 1] = v.y;
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+    uint4 u;
+    __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return u;
+}
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// ---- per-channel sums over rows: out[0][c] += sum f0, out[1][c] += sum f1 (double atomics) -------------
+// MODE 0: f0 = x, f1 = x^2                         (forward statistics)
+// MODE 1: g = dy * (y > 0 if y); f0 = g, f1 = g * xhat  (backward reductions)
+template <int MODE>
+__global__ void __launch_bounds__(kT) bn_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
+                                                       const uint4* __restrict__ y, const float* __restrict__ mean,
+                                                       const float* __restrict__ invstd, long long nvec, int CV,
+                                                       double* __restrict__ out, int C) {
+    __shared__ float red[2][kT][8 + 1];
+    const int tid = threadIdx.x;
+    const int cv = tid % CV;   // kT % CV == 0: a thread keeps its channel group for every vector it visits
+    float mu[8], is[8];
+    if (MODE == 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { mu[i] = mean[cv * 8 + i]; is[i] = invstd[cv * 8 + i]; }
+    }
+    float a0[8], a1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.f;
+    const long long per_cta = ((nvec + gridDim.x - 1) / gridDim.x + kT - 1) / kT * kT;
+    const long long v0 = blockIdx.x * per_cta, v1 = min(nvec, v0 + per_cta);
+    for (long long v = v0 + tid; v < v1; v += kT) {
+        float fx[8];
+        unpack8(ld_stream(x + v), fx);
+        if (MODE == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { a0[i] += fx[i]; a1[i] = fmaf(fx[i], fx[i], a1[i]); }
+        } else {
+            float g[8];
+            unpack8(ld_stream(dy + v), g);
+            if (y) {
+                float fy[8];
+                unpack8(ld_stream(y + v), fy);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) g[i] = fy[i] > 0.f ? g[i] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { a0[i] += g[i]; a1[i] = fmaf(g[i], (fx[i] - mu[i]) * is[i], a1[i]); }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { red[0][tid][i] = a0[i]; red[1][tid][i] = a1[i]; }
+    __syncthreads();
+    // threads tid < CV*8*2 each finish one (which, channel) over the kT/CV row lanes
+    for (int o = tid; o < 2 * CV * 8; o += kT) {
+        const int which = o / (CV * 8), c = o % (CV * 8);
+        const int ccv = c / 8, ci = c % 8;
+        float s = 0.f;
+        for (int r = ccv; r < kT; r += CV) s += red[which][r][ci];
+        atomicAdd(&out[which * C + c], (double)s);
+    }
+}
+
+// mean / invstd from the sums; running statistics update like nn.BatchNorm2d (momentum, unbiased running_var)
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, long long R, int C, float eps, float momentum,
+                                   float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double m = sums[c] / (double)R;
+    double var = sums[C + c] / (double)R - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[c] = (float)m;
+    invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+        const double unbiased = R > 1 ? var * (double)R / (double)(R - 1) : var;
+        running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * m);
+        running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+    }
+}
+
+// y = act((x - mean) * invstd * gamma + beta (+ residual))
+__global__ void __launch_bounds__(kT) bn_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ res,
+                                                      const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      int relu, uint4* __restrict__ y, long long nvec, int CV) {
+    const long long stride = (long long)gridDim.x * kT;
+    const long long v0 = (long long)blockIdx.x * kT + threadIdx.x;
+    const int cv = threadIdx.x % CV;   // stride % CV == 0
+    float sc[8], sh[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = cv * 8 + i;
+        sc[i] = invstd[c] * gamma[c];
+        sh[i] = beta[c] - mean[c] * sc[i];
+    }
+    for (long long v = v0; v < nvec; v += stride) {
+        float f[8];
+        unpack8(ld_stream(x + v), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], sc[i], sh[i]);
+        if (res) {
+            float r[8];
+            unpack8(ld_stream(res + v), r);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] += r[i];
+        }
+        if (relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+        }
+        y[v] = pack8(f);
+    }
+}
+
+// g = dy * (y > 0);  dx = gamma * invstd * (g - sum_g/R - xhat * sum_gx/R);  dres = g
+__global__ void __launch_bounds__(kT) bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y,
+                                                          const uint4* __restrict__ x, const float* __restrict__ mean,
+                                                          const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                          const double* __restrict__ sums, long long R,
+                                                          uint4* __restrict__ dx, uint4* __restrict__ dres, long long nvec,
+                                                          int CV, int C) {
+    const long long stride = (long long)gridDim.x * kT;
+    const long long v0 = (long long)blockIdx.x * kT + threadIdx.x;
+    const int cv = threadIdx.x % CV;
+    float mu[8], is[8], k0[8], k1[8], k2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = cv * 8 + i;
+        mu[i] = mean[c];
+        is[i] = invstd[c];
+        k0[i] = gamma[c] * is[i];
+        k1[i] = (float)(sums[c] / (double)R);
+        k2[i] = (float)(sums[C + c] / (double)R);
+    }
+    for (long long v = v0; v < nvec; v += stride) {
+        float g[8], fx[8];
+        unpack8(ld_stream(dy + v), g);
+        unpack8(ld_stream(x + v), fx);
+        if (y) {
+            float fy[8];
+            unpack8(ld_stream(y + v), fy);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i] = fy[i] > 0.f ? g[i] : 0.f;
+        }
+        if (dres) dres[v] = pack8(g);
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = k0[i] * (g[i] - k1[i] - (fx[i] - mu[i]) * is[i] * k2[i]);
+        dx[v] = pack8(o);
+    }
+}
+
+__global__ void bn_param_grads_kernel(const double* __restrict__ sums, int C, float* __restrict__ dgamma,
+                                      float* __restrict__ dbeta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    dbeta[c] = (float)sums[c];
+    dgamma[c] = (float)sums[C + c];
+}
+
+// ---- max-pool 3x3, stride 2, padding 1 (torchvision resnet stem), NHWC bf16 ------------------------------
+// forward stores the arg-max tap (0..8) per output element; backward gathers: every input pixel looks at the
+// <= 4 windows that contain it (no atomics).
+__global__ void __launch_bounds__(kT) maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
+                                                         uint2* __restrict__ idx, int N, int H, int W, int CV, int HO,
+                                                         int WO) {
+    const long long total = (long long)N * HO * WO * CV;
+    for (long long o = (long long)blockIdx.x * kT + threadIdx.x; o < total; o += (long long)gridDim.x * kT) {
+        const int cv = (int)(o % CV);
+        long long r = o / CV;
+        const int wo = (int)(r % WO); r /= WO;
+        const int ho = (int)(r % HO);
+        const int n = (int)(r / HO);
+        float best[8];
+        unsigned char bi[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; bi[i] = 0; }
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int h = 2 * ho - 1 + dy;
+            if (h < 0 || h >= H) continue;
+#pragma unroll
+            for (int dxx = 0; dxx < 3; ++dxx) {
+                const int w = 2 * wo - 1 + dxx;
+                if (w < 0 || w >= W) continue;
+                float f[8];
+                unpack8(x[(((long long)n * H + h) * W + w) * CV + cv], f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (f[i] > best[i] || f[i] != f[i]) { best[i] = f[i]; bi[i] = (unsigned char)(dy * 3 + dxx); }
+            }
+        }
+        y[o] = pack8(best);
+        uint2 pk;
+        pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+        pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+        idx[o] = pk;
+    }
+}
+
+__global__ void __launch_bounds__(kT) maxpool_bwd_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx,
+                                                         uint4* __restrict__ dx, int N, int H, int W, int CV, int HO,
+                                                         int WO) {
+    const long long total = (long long)N * H * W * CV;
+    for (long long o = (long long)blockIdx.x * kT + threadIdx.x; o < total; o += (long long)gridDim.x * kT) {
+        const int cv = (int)(o % CV);
+        long long r = o / CV;
+        const int w = (int)(r % W); r /= W;
+        const int h = (int)(r % H);
+        const int n = (int)(r / H);
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        // windows (ho, wo) with 2*ho-1 <= h <= 2*ho+1
+        const int ho0 = max(0, (h) / 2), ho1 = min(HO - 1, (h + 1) / 2);
+        const int wo0 = max(0, (w) / 2), wo1 = min(WO - 1, (w + 1) / 2);
+        for (int ho = ho0; ho <= ho1; ++ho) {
+            const int tdy = h - (2 * ho - 1);
+            if (tdy < 0 || tdy > 2) continue;
+            for (int wo = wo0; wo <= wo1; ++wo) {
+                const int tdx = w - (2 * wo - 1);
+                if (tdx < 0 || tdx > 2) continue;
+                const long long q = (((long long)n * HO + ho) * WO + wo) * CV + cv;
+                const uint2 pk = idx[q];
+                float g[8];
+                unpack8(dy[q], g);
+                const unsigned tap = (unsigned)(tdy * 3 + tdx);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const unsigned b = ((i < 4 ? pk.x : pk.y) >> (8 * (i & 3))) & 0xFFu;
+                    if (b == tap) acc[i] += g[i];
+                }
+            }
+        }
+        dx[o] = pack8(acc);
+    }
+}
+
+inline int stream_grid(long long nvec) { return (int)min((long long)148 * 16, (nvec + kT - 1) / kT); }
+inline bool ok_c(int C) { return C >= 8 && C % 8 == 0 && (kT % (C / 8) == 0); }
+
+}  // namespace
+
+extern "C" int sd_bn_stats_nhwc_bf16(const void* x, long long R, int C, double* sums /*[2][C], zeroed here*/, float eps,
+                                     float momentum, float* mean, float* invstd, float* running_mean, float* running_var,
+                                     void* stream) {
+    if (R <= 0) return SD_OK;
+    if (!x || !sums || !mean || !invstd || !ok_c(C)) return SD_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    SD_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+    const long long nvec = R * (C / 8);
+    const int grid = (int)min((long long)148 * 8, (nvec + kT - 1) / kT);
+    bn_reduce_kernel<0><<<grid, kT, 0, st>>>((const uint4*)x, nullptr, nullptr, nullptr, nullptr, nvec, C / 8, sums, C);
+    SD_LAUNCH_CHECK();
+    bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, R, C, eps, momentum, mean, invstd, running_mean, running_var);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+}
+
+extern "C" int sd_bn_apply_nhwc_bf16(const void* x, const void* residual, const float* mean, const float* invstd,
+                                     const float* gamma, const float* beta, int relu, void* y, long long R, int C,
+                                     void* stream) {
+    if (R <= 0) return SD_OK;
+    if (!x || !y || !mean || !invstd || !gamma || !beta || !ok_c(C)) return SD_ERR_BAD_ARG;
+    const long long nvec = R * (C / 8);
+    bn_apply_kernel<<<stream_grid(nvec), kT, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)residual, mean, invstd,
+                                                                       gamma, beta, relu, (uint4*)y, nvec, C / 8);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+}
+
+extern "C" int sd_bn_bwd_nhwc_bf16(const void* dy, const void* y_relu, const void* x, const float* mean,
+                                   const float* invstd, const float* gamma, double* sums, void* dx, void* dres,
+                                   float* dgamma, float* dbeta, long long R, int C, void* stream) {
+    if (R <= 0) return SD_OK;
+    if (!dy || !x || !mean || !invstd || !gamma || !sums || !dx || !dgamma || !dbeta || !ok_c(C)) return SD_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    SD_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+    const long long nvec = R * (C / 8);
+    const int grid = (int)min((long long)148 * 8, (nvec + kT - 1) / kT);
+    bn_reduce_kernel<1><<<grid, kT, 0, st>>>((const uint4*)x, (const uint4*)dy, (const uint4*)y_relu, mean, invstd, nvec,
+                                             C / 8, sums, C);
+    SD_LAUNCH_CHECK();
+    bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, C, dgamma, dbeta);
+    SD_LAUNCH_CHECK();
+    bn_bwd_apply_kernel<<<stream_grid(nvec), kT, 0, st>>>((const uint4*)dy, (const uint4*)y_relu, (const uint4*)x, mean,
+                                                          invstd, gamma, sums, R, (uint4*)dx, (uint4*)dres, nvec, C / 8, C);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+}
+
+extern "C" int sd_maxpool3x3s2_nhwc_bf16_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, void* stream) {
+    if (N <= 0) return SD_OK;
+    if (!x || !y || !idx || C % 8 != 0) return SD_ERR_BAD_ARG;
+    const int HO = (H + 2 - 3) / 2 + 1, WO = (W + 2 - 3) / 2 + 1;
+    const long long total = (long long)N * HO * WO * (C / 8);
+    maxpool_fwd_kernel<<<stream_grid(total), kT, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, (uint2*)idx, N, H, W,
+                                                                           C / 8, HO, WO);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+}
+
+extern "C" int sd_maxpool3x3s2_nhwc_bf16_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C,
+                                             void* stream) {
+    if (N <= 0) return SD_OK;
+    if (!dy || !idx || !dx || C % 8 != 0) return SD_ERR_BAD_ARG;
+    const int HO = (H + 2 - 3) / 2 + 1, WO = (W + 2 - 3) / 2 + 1;
+    const long long total = (long long)N * H * W * (C / 8);
+    maxpool_bwd_kernel<<<stream_grid(total), kT, 0, (cudaStream_t)stream>>>((const uint4*)dy, (const uint2*)idx, (uint4*)dx, N,
+                                                                           H, W, C / 8, HO, WO);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+}

@@ -93,6 +93,11 @@ class ResNetImageEncoder(AbstractImageEncoder):
     def trunk(self, images: torch.Tensor) -> torch.Tensor:
         """torchvision/cuDNN conv stack -> (n, C, h, w), channels_last."""
         e = self.encoder
+        if runtime.get_precision() == ops.PREC_BF16 and runtime.fused_trunk() and (self.training or not torch.is_grad_enabled()):
+            from soccerdiffusion_b200.ml.model.encoder import trunk as _trunk
+
+            if _trunk.supported(e):
+                return _trunk.resnet_trunk_bf16(e, images)
         images = images.contiguous(memory_format=torch.channels_last)
         with _trunk_autocast():
             x = e.maxpool(e.relu(e.bn1(e.conv1(images))))

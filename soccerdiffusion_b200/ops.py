@@ -256,3 +256,44 @@ def dropout_apply(x, p, seed, stream_id):
           "sd_dropout_apply")
     _count()
     return y
+
+
+# ---- image-trunk layers (bf16 NHWC) --------------------------------------------------------------------
+def bn_stats(x, R, C, sums, eps, momentum, mean, invstd, running_mean, running_var):
+    with _Timed("bn_stats", 0.0, 2.0 * R * C, f"[R{R} C{C}]"):
+        check(_lib.lib().sd_bn_stats_nhwc_bf16(x.data_ptr(), R, C, sums.data_ptr(), eps, momentum, mean.data_ptr(),
+                                               invstd.data_ptr(), _lib.ptr(running_mean), _lib.ptr(running_var),
+                                               stream_ptr()), "sd_bn_stats_nhwc_bf16")
+    _count(2)
+
+
+def bn_apply(x, residual, mean, invstd, gamma, beta, relu, y, R, C):
+    with _Timed("bn_apply", 0.0, 2.0 * R * C * (3 if residual is not None else 2), f"[R{R} C{C}]"):
+        check(_lib.lib().sd_bn_apply_nhwc_bf16(x.data_ptr(), _lib.ptr(residual), mean.data_ptr(), invstd.data_ptr(),
+                                               gamma.data_ptr(), beta.data_ptr(), 1 if relu else 0, y.data_ptr(), R, C,
+                                               stream_ptr()), "sd_bn_apply_nhwc_bf16")
+    _count()
+
+
+def bn_bwd(dy, y_relu, x, mean, invstd, gamma, sums, dx, dres, dgamma, dbeta, R, C):
+    nb = 2.0 * R * C * ((3 if y_relu is not None else 2) * 2 + 1 + (1 if dres is not None else 0))
+    with _Timed("bn_bwd", 0.0, nb, f"[R{R} C{C}]"):
+        check(_lib.lib().sd_bn_bwd_nhwc_bf16(dy.data_ptr(), _lib.ptr(y_relu), x.data_ptr(), mean.data_ptr(),
+                                             invstd.data_ptr(), gamma.data_ptr(), sums.data_ptr(), dx.data_ptr(),
+                                             _lib.ptr(dres), dgamma.data_ptr(), dbeta.data_ptr(), R, C, stream_ptr()),
+              "sd_bn_bwd_nhwc_bf16")
+    _count(3)
+
+
+def maxpool_fwd(x, y, idx, N, H, W, C):
+    with _Timed("maxpool_fwd", 0.0, 2.0 * N * H * W * C * 1.25 + N * H * W * C / 4, f"[N{N} H{H} C{C}]"):
+        check(_lib.lib().sd_maxpool3x3s2_nhwc_bf16_fwd(x.data_ptr(), y.data_ptr(), idx.data_ptr(), N, H, W, C, stream_ptr()),
+              "sd_maxpool3x3s2_nhwc_bf16_fwd")
+    _count()
+
+
+def maxpool_bwd(dy, idx, dx, N, H, W, C):
+    with _Timed("maxpool_bwd", 0.0, 2.0 * N * H * W * C * 1.25 + N * H * W * C / 4, f"[N{N} H{H} C{C}]"):
+        check(_lib.lib().sd_maxpool3x3s2_nhwc_bf16_bwd(dy.data_ptr(), idx.data_ptr(), dx.data_ptr(), N, H, W, C, stream_ptr()),
+              "sd_maxpool3x3s2_nhwc_bf16_bwd")
+    _count()

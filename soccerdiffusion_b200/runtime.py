@@ -49,6 +49,20 @@ def next_seed() -> int:
     return (_seed_base * 1000003 + _calls) & 0x7FFFFFFFFFFFFFFF
 
 
+_fused_trunk = os.environ.get("SD_B200_FUSED_TRUNK", "1") == "1"
+
+
+def set_fused_trunk(on: bool):
+    """bf16 mode: run the trunk's BatchNorm/ReLU/residual/max-pool layers on libsd_b200 kernels (default) or
+    through torch's own kernels."""
+    global _fused_trunk
+    _fused_trunk = bool(on)
+
+
+def fused_trunk() -> bool:
+    return _fused_trunk
+
+
 def set_dropout(p: float):
     """Overrides the train-mode dropout probability (parity tests run with 0.0; the reference's value is 0.1)."""
     global DROPOUT_P

@@ -1,0 +1,106 @@
+"""GPU parity of the bf16 NHWC trunk kernels (fused BatchNorm(+residual)(+ReLU), max-pool) against torch's own ops
+evaluated in fp32 on the same bf16 inputs, and of the whole fused trunk against the torchvision/cuDNN path."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util_gpu import rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _cl_bf16(*shape):
+    return torch.randn(*shape, device="cuda").to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+
+
+@pytest.mark.parametrize("N,C,H,W,res,relu", [(4, 64, 56, 56, False, True), (3, 128, 28, 28, True, True),
+                                               (2, 512, 7, 7, False, False), (5, 256, 14, 14, True, True),
+                                               (1, 64, 112, 112, False, True)])
+def test_fused_bn_act_forward_backward(N, C, H, W, res, relu):
+    from soccerdiffusion_b200.ml.model.encoder.trunk import FusedBNAct
+
+    torch.manual_seed(C + H)
+    x = (_cl_bf16(N, C, H, W) * 1.7 + 0.3).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    r = _cl_bf16(N, C, H, W) if res else None
+    gamma = (torch.rand(C, device="cuda") + 0.5).requires_grad_(True)
+    beta = (torch.randn(C, device="cuda") * 0.1).requires_grad_(True)
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    rm2, rv2 = rm.clone(), rv.clone()
+    go = _cl_bf16(N, C, H, W)
+    xg = x.clone().requires_grad_(True)
+    rg = r.clone().requires_grad_(True) if res else None
+    y = FusedBNAct.apply(xg, gamma, beta, rm, rv, rg, relu, True, 0.1, 1e-5)
+    y.backward(go)
+    # reference: torch ops in fp32 on the same (bf16-valued) inputs
+    xf = x.float().requires_grad_(True)
+    rf = r.float().requires_grad_(True) if res else None
+    g2, b2 = gamma.detach().clone().requires_grad_(True), beta.detach().clone().requires_grad_(True)
+    yf = F.batch_norm(xf, rm2, rv2, g2, b2, True, 0.1, 1e-5)
+    if res:
+        yf = yf + rf
+    if relu:
+        yf = F.relu(yf)
+    yf.backward(go.float())
+    assert rel(y.float(), yf) < 6e-3                       # bf16 output rounding
+    assert rel(rm, rm2) < 1e-4 and rel(rv, rv2) < 1e-4      # running statistics (fp32)
+    assert rel(xg.grad.float(), xf.grad) < 1.5e-2
+    assert rel(gamma.grad, g2.grad) < 1.5e-2 and rel(beta.grad, b2.grad) < 1.5e-2
+    if res:
+        assert rel(rg.grad.float(), rf.grad) < 1e-2
+    # eval mode uses the running statistics
+    ye = FusedBNAct.apply(x, gamma.detach(), beta.detach(), rm, rv, r, relu, False, 0.1, 1e-5)
+    yef = F.batch_norm(x.float(), rm2, rv2, g2.detach(), b2.detach(), False, 0.1, 1e-5)
+    if res:
+        yef = yef + r.float()
+    if relu:
+        yef = F.relu(yef)
+    assert rel(ye.float(), yef) < 6e-3
+
+
+@pytest.mark.parametrize("N,C,H,W", [(3, 64, 112, 112), (2, 64, 32, 32), (1, 16, 7, 9)])
+def test_maxpool_forward_backward(N, C, H, W):
+    from soccerdiffusion_b200.ml.model.encoder.trunk import MaxPool3x3s2
+
+    x = _cl_bf16(N, C, H, W)
+    xg = x.clone().requires_grad_(True)
+    y = MaxPool3x3s2.apply(xg)
+    xf = x.float().requires_grad_(True)
+    yf = F.max_pool2d(xf, 3, 2, 1)
+    assert torch.equal(y.float(), yf)
+    go = _cl_bf16(*y.shape)
+    y.backward(go)
+    yf.backward(go.float())
+    assert rel(xg.grad.float(), xf.grad) < 5e-3   # sums of <= 4 bf16 gradients, rounded once to bf16
+
+
+def test_fused_trunk_matches_library_trunk_bf16():
+    import soccerdiffusion_b200 as sdb
+    from oracle import synth
+    from soccerdiffusion_b200 import runtime
+    from util_gpu import synth_model
+
+    hp = dict(synth.TINY_HP, image_resolution=96, image_context_length=3)
+    outs = {}
+    sdb.set_precision("bf16")
+    try:
+        for fused in (True, False):
+            runtime.set_fused_trunk(fused)
+            model, _ = synth_model(hp, 3)
+            model.train()
+            enc = model.image_sequence_encoder.image_encoder
+            imgs = torch.from_numpy(synth.normal("img", (2 * 3, 3, 96, 96), 3)).cuda()
+            feat = enc.trunk(imgs)
+            feat.float().square().mean().backward()
+            e = enc.encoder
+            outs[fused] = dict(feat=feat.float().detach(), rm=e.bn1.running_mean.clone(), rv=e.layer2[0].bn2.running_var.clone(),
+                               nbt=int(e.bn1.num_batches_tracked), g_conv1=e.conv1.weight.grad.clone(),
+                               g_bn=e.layer3[1].bn2.weight.grad.clone(), g_ds=e.layer4[0].downsample[0].weight.grad.clone())
+    finally:
+        runtime.set_fused_trunk(True)
+        sdb.set_precision("fp32")
+    a, b = outs[True], outs[False]
+    assert a["nbt"] == b["nbt"] == 1
+    assert rel(a["feat"], b["feat"]) < 3e-2
+    assert rel(a["rm"], b["rm"]) < 1e-2 and rel(a["rv"], b["rv"]) < 1e-2
+    for k in ("g_conv1", "g_bn", "g_ds"):
+        assert rel(a[k], b[k]) < 8e-2, k   # two bf16 pipelines, 20 layers deep
