@@ -107,7 +107,8 @@ def resnet_trunk_bf16(encoder, images: torch.Tensor) -> torch.Tensor:
     """(n,3,R,R) -> (n,C,h,w) bf16 channels_last: conv1..layer4 of a torchvision ResNet."""
     from torchvision.models.resnet import BasicBlock
 
-    with torch.autocast("cuda", dtype=torch.bfloat16):
+    # cuDNN autotuning for the (fixed) convolution shapes of the trunk; restored on exit
+    with torch.backends.cudnn.flags(enabled=True, benchmark=True), torch.autocast("cuda", dtype=torch.bfloat16):
         x = _conv(encoder.conv1, images.to(dtype=torch.bfloat16, memory_format=torch.channels_last))
         x = _bn(encoder.bn1, x, None, True)
         x = MaxPool3x3s2.apply(x)
