@@ -142,12 +142,20 @@ int sd_dropout_apply(const float* x, float* y, long long n, float p, unsigned lo
  * `sums` is a caller-provided scratch of 2*C doubles. */
 int sd_bn_stats_nhwc_bf16(const void* x, long long R, int C, double* sums, float eps, float momentum, float* mean,
                           float* invstd, float* running_mean, float* running_var, void* stream);
+/* relu_mask (optional, R*C/8 bytes): bit i of byte v = ReLU passed channel 8*(v % (C/8)) + i of row v / (C/8) */
 int sd_bn_apply_nhwc_bf16(const void* x, const void* residual, const float* mean, const float* invstd, const float* gamma,
-                          const float* beta, int relu, void* y, long long R, int C, void* stream);
-/* dy -> (dx, dresidual = dy*relu_mask, dgamma, dbeta); y_relu = forward output when ReLU was fused, else NULL */
-int sd_bn_bwd_nhwc_bf16(const void* dy, const void* y_relu, const void* x, const float* mean, const float* invstd,
+                          const float* beta, int relu, void* y, void* relu_mask, long long R, int C, void* stream);
+/* dy -> (dx, dresidual = dy*relu_mask, dgamma, dbeta); relu_mask = the bytes written by the forward, or NULL */
+int sd_bn_bwd_nhwc_bf16(const void* dy, const void* relu_mask, const void* x, const float* mean, const float* invstd,
                         const float* gamma, double* sums, void* dx, void* dres, float* dgamma, float* dbeta, long long R,
                         int C, void* stream);
+/* Fused stem: maxpool3x3s2(relu(bn(x))) without materialising the activated 112x112 map; backward recomputes the
+ * ReLU mask from x (torchvision ResNet stem bn1 -> relu -> maxpool). mean/invstd from sd_bn_stats_nhwc_bf16. */
+int sd_stem_bn_relu_pool_nhwc_bf16_fwd(const void* x, const float* mean, const float* invstd, const float* gamma,
+                                       const float* beta, void* y, void* idx, int N, int H, int W, int C, void* stream);
+int sd_stem_bn_relu_pool_nhwc_bf16_bwd(const void* dpool, const void* idx, const void* x, const float* mean,
+                                       const float* invstd, const float* gamma, const float* beta, double* sums, void* dx,
+                                       float* dgamma, float* dbeta, int N, int H, int W, int C, void* stream);
 /* idx: one byte per output element (arg-max tap 0..8) */
 int sd_maxpool3x3s2_nhwc_bf16_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, void* stream);
 int sd_maxpool3x3s2_nhwc_bf16_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C, void* stream);

@@ -57,6 +57,15 @@ __device__ __forceinline__ void stage_k_contig(uint8_t* tile, const float* __res
                                                int rows_total, int R, int k0, int ke, bool vec, const TcParams& p) {
     const int c = threadIdx.x & 7;
     const int k = k0 + 8 * c;
+    float ga[8], be[8];
+    if (LN) {   // the thread's 8 k positions are the same for every row it stages
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            ga[j] = (k + j < ke) ? __ldg(p.ln_gamma + k + j) : 0.f;
+            be[j] = (k + j < ke) ? __ldg(p.ln_beta + k + j) : 0.f;
+        }
+    }
+    const bool full = vec && (k + 7 < ke);
     for (int r = threadIdx.x >> 3; r < R; r += NT / 8) {
         const int row = row0 + r;
         float f[8];
@@ -64,7 +73,7 @@ __device__ __forceinline__ void stage_k_contig(uint8_t* tile, const float* __res
         for (int j = 0; j < 8; ++j) f[j] = 0.f;
         if (row < rows_total && k < ke) {
             const float* g = src + (long long)row * ld + k;
-            if (vec && k + 7 < ke) {
+            if (full) {
                 const float4 a = *reinterpret_cast<const float4*>(g);
                 const float4 b = *reinterpret_cast<const float4*>(g + 4);
                 f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
@@ -74,10 +83,10 @@ __device__ __forceinline__ void stage_k_contig(uint8_t* tile, const float* __res
                     if (k + j < ke) f[j] = g[j];
             }
             if (LN) {
-                const float mu = p.ln_mean[row], rs = p.ln_rstd[row];
+                const float rs = p.ln_rstd[row];
+                const float nm = -p.ln_mean[row] * rs;
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (k + j < ke) f[j] = (f[j] - mu) * rs * __ldg(p.ln_gamma + k + j) + __ldg(p.ln_beta + k + j);
+                for (int j = 0; j < 8; ++j) f[j] = fmaf(fmaf(f[j], rs, nm), ga[j], be[j]);   // 0 beyond ke: ga = be = 0
             }
         }
         *reinterpret_cast<uint4*>(tile + sw128_chunk_off(r, c)) = pack8_bf16(f);
@@ -113,7 +122,12 @@ __device__ __forceinline__ void stage_row_contig(uint8_t* tile, const float* __r
     }
 }
 
-template <bool A_KM, bool B_KN>
+// epilogue feature mask (compile-time specialisations of the combinations the layer code uses; EPI_GENERIC keeps
+// every feature a run-time flag)
+constexpr int EPI_PRE = 1, EPI_GELU = 2, EPI_GG = 4, EPI_DROP = 8, EPI_PE = 16, EPI_RES = 32, EPI_ACC = 64;
+constexpr int EPI_GENERIC = -1;
+
+template <bool A_KM, bool B_KN, int EPI>
 __global__ void __launch_bounds__(NT) gemm_tc_kernel(const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_stage[STAGES];
@@ -178,11 +192,21 @@ __global__ void __launch_bounds__(NT) gemm_tc_kernel(const TcParams p) {
     tc_fence_after_sync();
 
     // ---- epilogue: TMEM -> registers -> (transpose in smem) -> coalesced global ----------------------
+    constexpr bool G = EPI == EPI_GENERIC;
+    const bool f_pre = G ? p.pre_out != nullptr : (EPI & EPI_PRE) != 0;
+    const bool f_gelu = G ? p.act == SD_ACT_GELU : (EPI & EPI_GELU) != 0;
+    const bool f_gg = G ? p.gelu_grad_src != nullptr : (EPI & EPI_GG) != 0;
+    const bool f_drop = G ? p.drop.thresh != 0 : (EPI & EPI_DROP) != 0;
+    const bool f_pe = G ? p.pe != nullptr : (EPI & EPI_PE) != 0;
+    const bool f_res = G ? p.residual != nullptr : (EPI & EPI_RES) != 0;
+    const bool f_acc = G ? p.accumulate != 0 : (EPI & EPI_ACC) != 0;
     float* bounce = reinterpret_cast<float*>(smem) + warp * (32 * 33);
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const bool split = gridDim.z > 1;
     const bool first_slice = blockIdx.z == 0;
     const int nblocks = (BN + 31) / 32;
+    const int m_first = m0 + q * 32;
+    const int rows = min(32, p.M - m_first);
     for (int cb = warp >> 2; cb < nblocks; cb += 2) {
         if (n0 + cb * 32 >= p.N) break;
         float v[32];
@@ -192,25 +216,35 @@ __global__ void __launch_bounds__(NT) gemm_tc_kernel(const TcParams p) {
         __syncwarp();
         const int n = n0 + cb * 32 + lane;
         const bool n_ok = n < p.N && (cb * 32 + lane) < BN;
-        const float bias = (n_ok && p.bias) ? __ldg(p.bias + n) : 0.f;
-        for (int rr = 0; rr < 32; ++rr) {
-            const int m = m0 + q * 32 + rr;
-            if (m >= p.M) break;
-            if (!n_ok) continue;
-            float x = bounce[rr * 33 + lane] * p.alpha;
-            if (!split) {
-                x += bias;
-                if (p.pre_out) p.pre_out[(long long)m * p.ldp + n] = x;
-                if (p.act == SD_ACT_GELU) x = gelu_erf(x);
-                if (p.gelu_grad_src) x *= gelu_erf_grad(p.gelu_grad_src[(long long)m * p.ldg + n]);
-                x *= p.drop((uint64_t)m * (uint64_t)p.N + (uint64_t)n);
-                if (p.pe) x += __ldg(p.pe + (long long)(m % p.pe_period) * p.N + n);
-                if (p.residual) x += p.residual[(long long)m * p.ldr + n];
-                float* c = &p.C[(long long)m * p.ldc + n];
-                *c = p.accumulate ? *c + x : x;
+        if (n_ok && rows > 0) {
+            const float bias = p.bias ? __ldg(p.bias + n) : 0.f;
+            float* cp = p.C + (long long)m_first * p.ldc + n;
+            if (split) {
+                const float b2 = first_slice ? bias : 0.f;
+                for (int rr = 0; rr < rows; ++rr, cp += p.ldc) atomicAdd(cp, fmaf(bounce[rr * 33 + lane], p.alpha, b2));
             } else {
-                if (first_slice) x += bias;
-                atomicAdd(&p.C[(long long)m * p.ldc + n], x);
+                float* prep = f_pre ? p.pre_out + (long long)m_first * p.ldp + n : nullptr;
+                const float* ggp = f_gg ? p.gelu_grad_src + (long long)m_first * p.ldg + n : nullptr;
+                const float* resp = f_res ? p.residual + (long long)m_first * p.ldr + n : nullptr;
+                int pe_row = f_pe ? m_first % p.pe_period : 0;
+                const float* pep = f_pe ? p.pe + (long long)pe_row * p.N + n : nullptr;
+                uint64_t didx = (uint64_t)m_first * (uint64_t)p.N + (uint64_t)n;
+#pragma unroll 4
+                for (int rr = 0; rr < rows; ++rr) {
+                    float x = fmaf(bounce[rr * 33 + lane], p.alpha, bias);
+                    if (f_pre) { *prep = x; prep += p.ldp; }
+                    if (f_gelu) x = gelu_erf(x);
+                    if (f_gg) { x *= gelu_erf_grad(*ggp); ggp += p.ldg; }
+                    if (f_drop) { x *= p.drop(didx); didx += (uint64_t)p.N; }
+                    if (f_pe) {
+                        x += __ldg(pep);
+                        if (++pe_row == p.pe_period) { pe_row = 0; pep = p.pe + n; } else pep += p.N;
+                    }
+                    if (f_res) { x += *resp; resp += p.ldr; }
+                    if (f_acc) x += *cp;
+                    *cp = x;
+                    cp += p.ldc;
+                }
             }
         }
         __syncwarp();
@@ -223,10 +257,10 @@ __global__ void __launch_bounds__(NT) gemm_tc_kernel(const TcParams p) {
 
 inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
-template <bool A_KM, bool B_KN>
+template <bool A_KM, bool B_KN, int EPI>
 int launch(dim3 grid, size_t smem, cudaStream_t st, const TcParams& p) {
-    auto kernel = gemm_tc_kernel<A_KM, B_KN>;
-    static bool configured = false;   // one flag per <A_KM, B_KN> instantiation
+    auto kernel = gemm_tc_kernel<A_KM, B_KN, EPI>;
+    static bool configured = false;   // one flag per instantiation
     if (!configured) {
         SD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      STAGES * (A_STAGE_BYTES + 256 * TK * 2) + 1024));
@@ -235,6 +269,12 @@ int launch(dim3 grid, size_t smem, cudaStream_t st, const TcParams& p) {
     kernel<<<grid, NT, smem, st>>>(p);
     SD_LAUNCH_CHECK();
     return SD_OK;
+}
+
+int epilogue_mask(const TcParams& p) {
+    return (p.pre_out ? EPI_PRE : 0) | (p.act == SD_ACT_GELU ? EPI_GELU : 0) | (p.gelu_grad_src ? EPI_GG : 0) |
+           (p.drop.thresh != 0 ? EPI_DROP : 0) | (p.pe ? EPI_PE : 0) | (p.residual ? EPI_RES : 0) |
+           (p.accumulate ? EPI_ACC : 0);
 }
 
 }  // namespace
@@ -281,9 +321,28 @@ int sd_gemm_tc_dispatch(const sd_gemm_desc* d, void* stream) {
         SD_CUDA(cudaMemset2DAsync(d->C, d->ldc * sizeof(float), 0, (size_t)d->N * sizeof(float), d->M, st));
     dim3 grid(ntn, ntm, slices);
     const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + p.BN * TK * 2) + 1024;
-    if (d->a_layout == SD_LAYOUT_MK && d->b_layout == SD_LAYOUT_NK) return launch<false, false>(grid, smem, st, p);
-    if (d->a_layout == SD_LAYOUT_MK && d->b_layout == SD_LAYOUT_KN) return launch<false, true>(grid, smem, st, p);
-    if (d->a_layout == SD_LAYOUT_KM && d->b_layout == SD_LAYOUT_KN) return launch<true, true>(grid, smem, st, p);
-    if (d->a_layout == SD_LAYOUT_KM && d->b_layout == SD_LAYOUT_NK) return launch<true, false>(grid, smem, st, p);
+    const int em = slices > 1 ? 0 : epilogue_mask(p);
+    if (d->a_layout == SD_LAYOUT_MK && d->b_layout == SD_LAYOUT_NK) {
+        switch (em) {
+            case 0: return launch<false, false, 0>(grid, smem, st, p);
+            case EPI_PE: return launch<false, false, EPI_PE>(grid, smem, st, p);
+            case EPI_RES: return launch<false, false, EPI_RES>(grid, smem, st, p);
+            case EPI_RES | EPI_DROP: return launch<false, false, EPI_RES | EPI_DROP>(grid, smem, st, p);
+            case EPI_PRE | EPI_GELU: return launch<false, false, EPI_PRE | EPI_GELU>(grid, smem, st, p);
+            case EPI_PRE | EPI_GELU | EPI_DROP: return launch<false, false, EPI_PRE | EPI_GELU | EPI_DROP>(grid, smem, st, p);
+            default: return launch<false, false, EPI_GENERIC>(grid, smem, st, p);
+        }
+    }
+    if (d->a_layout == SD_LAYOUT_MK && d->b_layout == SD_LAYOUT_KN) {
+        switch (em) {
+            case 0: return launch<false, true, 0>(grid, smem, st, p);
+            case EPI_GG: return launch<false, true, EPI_GG>(grid, smem, st, p);
+            case EPI_GG | EPI_DROP: return launch<false, true, EPI_GG | EPI_DROP>(grid, smem, st, p);
+            case EPI_ACC: return launch<false, true, EPI_ACC>(grid, smem, st, p);
+            default: return launch<false, true, EPI_GENERIC>(grid, smem, st, p);
+        }
+    }
+    if (d->a_layout == SD_LAYOUT_KM && d->b_layout == SD_LAYOUT_KN) return launch<true, true, EPI_GENERIC>(grid, smem, st, p);
+    if (d->a_layout == SD_LAYOUT_KM && d->b_layout == SD_LAYOUT_NK) return launch<true, false, EPI_GENERIC>(grid, smem, st, p);
     return SD_ERR_BAD_ARG;
 }

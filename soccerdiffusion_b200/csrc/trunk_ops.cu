@@ -48,7 +48,7 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
 // MODE 1: g = dy * (y > 0 if y); f0 = g, f1 = g * xhat  (backward reductions)
 template <int MODE>
 __global__ void __launch_bounds__(kT) bn_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
-                                                       const uint4* __restrict__ y, const float* __restrict__ mean,
+                                                       const unsigned char* __restrict__ y, const float* __restrict__ mean,
                                                        const float* __restrict__ invstd, long long nvec, int CV,
                                                        double* __restrict__ out, int C) {
     __shared__ float red[2][kT][8 + 1];
@@ -74,10 +74,9 @@ __global__ void __launch_bounds__(kT) bn_reduce_kernel(const uint4* __restrict__
             float g[8];
             unpack8(ld_stream(dy + v), g);
             if (y) {
-                float fy[8];
-                unpack8(ld_stream(y + v), fy);
+                const unsigned mk = y[v];   // bit i: ReLU passed channel i of this vector in the forward pass
 #pragma unroll
-                for (int i = 0; i < 8; ++i) g[i] = fy[i] > 0.f ? g[i] : 0.f;
+                for (int i = 0; i < 8; ++i) g[i] = (mk >> i) & 1u ? g[i] : 0.f;
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) { a0[i] += g[i]; a1[i] = fmaf(g[i], (fx[i] - mu[i]) * is[i], a1[i]); }
@@ -118,7 +117,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, long long R,
 __global__ void __launch_bounds__(kT) bn_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ res,
                                                       const float* __restrict__ mean, const float* __restrict__ invstd,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                      int relu, uint4* __restrict__ y, long long nvec, int CV) {
+                                                      int relu, uint4* __restrict__ y, unsigned char* __restrict__ mask,
+                                                      long long nvec, int CV) {
     const long long stride = (long long)gridDim.x * kT;
     const long long v0 = (long long)blockIdx.x * kT + threadIdx.x;
     const int cv = threadIdx.x % CV;   // stride % CV == 0
@@ -141,15 +141,20 @@ __global__ void __launch_bounds__(kT) bn_apply_kernel(const uint4* __restrict__ 
             for (int i = 0; i < 8; ++i) f[i] += r[i];
         }
         if (relu) {
+            unsigned mk = 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+            for (int i = 0; i < 8; ++i) {
+                mk |= (f[i] > 0.f ? 1u : 0u) << i;
+                f[i] = fmaxf(f[i], 0.f);
+            }
+            if (mask) mask[v] = (unsigned char)mk;
         }
         y[v] = pack8(f);
     }
 }
 
 // g = dy * (y > 0);  dx = gamma * invstd * (g - sum_g/R - xhat * sum_gx/R);  dres = g
-__global__ void __launch_bounds__(kT) bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y,
+__global__ void __launch_bounds__(kT) bn_bwd_apply_kernel(const uint4* __restrict__ dy, const unsigned char* __restrict__ y,
                                                           const uint4* __restrict__ x, const float* __restrict__ mean,
                                                           const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                           const double* __restrict__ sums, long long R,
@@ -173,10 +178,9 @@ __global__ void __launch_bounds__(kT) bn_bwd_apply_kernel(const uint4* __restric
         unpack8(ld_stream(dy + v), g);
         unpack8(ld_stream(x + v), fx);
         if (y) {
-            float fy[8];
-            unpack8(ld_stream(y + v), fy);
+            const unsigned mk = y[v];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) g[i] = fy[i] > 0.f ? g[i] : 0.f;
+            for (int i = 0; i < 8; ++i) g[i] = (mk >> i) & 1u ? g[i] : 0.f;
         }
         if (dres) dres[v] = pack8(g);
         float o[8];
@@ -272,6 +276,150 @@ __global__ void __launch_bounds__(kT) maxpool_bwd_kernel(const uint4* __restrict
     }
 }
 
+// ---- fused stem: y = maxpool3x3s2(relu(bn(x))) --------------------------------------------------------
+// The normalised/activated 112x112 map (the largest tensor of the network) is never written: the forward reads
+// the convolution output once and writes the pooled map + arg-max taps; the backward recomputes the ReLU mask from
+// x and gathers the pooled gradient, once for the per-channel reductions and once to write dx.
+__global__ void __launch_bounds__(kT) stem_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ mean,
+                                                      const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, uint4* __restrict__ y,
+                                                      uint2* __restrict__ idx, int N, int H, int W, int CV, int HO, int WO) {
+    const long long total = (long long)N * HO * WO * CV;
+    const int cv = threadIdx.x % CV;   // (gridDim.x * kT) % CV == 0
+    float sc[8], sh[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = cv * 8 + i;
+        sc[i] = invstd[c] * gamma[c];
+        sh[i] = beta[c] - mean[c] * sc[i];
+    }
+    for (long long o = (long long)blockIdx.x * kT + threadIdx.x; o < total; o += (long long)gridDim.x * kT) {
+        long long r = o / CV;
+        const int wo = (int)(r % WO); r /= WO;
+        const int ho = (int)(r % HO);
+        const int n = (int)(r / HO);
+        float best[8];
+        unsigned char bi[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; bi[i] = 0; }
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int h = 2 * ho - 1 + dy;
+            if (h < 0 || h >= H) continue;
+#pragma unroll
+            for (int dxx = 0; dxx < 3; ++dxx) {
+                const int w = 2 * wo - 1 + dxx;
+                if (w < 0 || w >= W) continue;
+                float f[8];
+                unpack8(x[(((long long)n * H + h) * W + w) * CV + cv], f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float a = fmaxf(fmaf(f[i], sc[i], sh[i]), 0.f);
+                    if (a > best[i]) { best[i] = a; bi[i] = (unsigned char)(dy * 3 + dxx); }
+                }
+            }
+        }
+        y[o] = pack8(best);
+        uint2 pk;
+        pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+        pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+        idx[o] = pk;
+    }
+}
+
+// gradient reaching the ReLU output at input pixel (n,h,w), channel vector cv: sum over the <= 4 pooling windows
+// whose arg-max is this pixel
+__device__ __forceinline__ void stem_gather(const uint4* __restrict__ dp, const uint2* __restrict__ idx, int n, int h,
+                                            int w, int cv, int CV, int HO, int WO, float* g) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = 0.f;
+    const int ho0 = h / 2, ho1 = min(HO - 1, (h + 1) / 2);
+    const int wo0 = w / 2, wo1 = min(WO - 1, (w + 1) / 2);
+    for (int ho = ho0; ho <= ho1; ++ho) {
+        const int tdy = h - (2 * ho - 1);
+        for (int wo = wo0; wo <= wo1; ++wo) {
+            const int tdx = w - (2 * wo - 1);
+            const long long q = (((long long)n * HO + ho) * WO + wo) * CV + cv;
+            const uint2 pk = idx[q];
+            float d[8];
+            unpack8(dp[q], d);
+            const unsigned tap = (unsigned)(tdy * 3 + tdx);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const unsigned b = ((i < 4 ? pk.x : pk.y) >> (8 * (i & 3))) & 0xFFu;
+                if (b == tap) g[i] += d[i];
+            }
+        }
+    }
+}
+
+template <int PASS>   // 0: per-channel sums (sum g, sum g*xhat) ; 1: dx
+__global__ void __launch_bounds__(kT) stem_bwd_kernel(const uint4* __restrict__ dp, const uint2* __restrict__ idx,
+                                                      const uint4* __restrict__ x, const float* __restrict__ mean,
+                                                      const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, double* __restrict__ sums,
+                                                      uint4* __restrict__ dx, int N, int H, int W, int CV, int HO, int WO,
+                                                      int C) {
+    __shared__ float red[2][kT][8 + 1];
+    const int tid = threadIdx.x;
+    const int cv = tid % CV;
+    const long long nvec = (long long)N * H * W * CV;
+    const long long R = (long long)N * H * W;
+    float mu[8], is[8], sc[8], sh[8], k0[8], k1[8], k2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = cv * 8 + i;
+        mu[i] = mean[c];
+        is[i] = invstd[c];
+        sc[i] = is[i] * gamma[c];
+        sh[i] = beta[c] - mu[i] * sc[i];
+        if (PASS == 1) {
+            k0[i] = sc[i];
+            k1[i] = (float)(sums[c] / (double)R);
+            k2[i] = (float)(sums[C + c] / (double)R);
+        }
+    }
+    float a0[8], a1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.f;
+    const long long per_cta = ((nvec + gridDim.x - 1) / gridDim.x + kT - 1) / kT * kT;
+    const long long v0 = blockIdx.x * per_cta, v1 = min(nvec, v0 + per_cta);
+    for (long long v = v0 + tid; v < v1; v += kT) {
+        long long r = v / CV;
+        const int w = (int)(r % W); r /= W;
+        const int h = (int)(r % H);
+        const int n = (int)(r / H);
+        float fx[8], g[8];
+        unpack8(ld_stream(x + v), fx);
+        stem_gather(dp, idx, n, h, w, cv, CV, HO, WO, g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (!(fmaf(fx[i], sc[i], sh[i]) > 0.f)) g[i] = 0.f;   // ReLU mask, recomputed
+        }
+        if (PASS == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { a0[i] += g[i]; a1[i] = fmaf(g[i], (fx[i] - mu[i]) * is[i], a1[i]); }
+        } else {
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = k0[i] * (g[i] - k1[i] - (fx[i] - mu[i]) * is[i] * k2[i]);
+            dx[v] = pack8(o);
+        }
+    }
+    if (PASS == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { red[0][tid][i] = a0[i]; red[1][tid][i] = a1[i]; }
+        __syncthreads();
+        for (int o = tid; o < 2 * CV * 8; o += kT) {
+            const int which = o / (CV * 8), c = o % (CV * 8);
+            const int ccv = c / 8, ci = c % 8;
+            float s2 = 0.f;
+            for (int r = ccv; r < kT; r += CV) s2 += red[which][r][ci];
+            atomicAdd(&sums[which * C + c], (double)s2);
+        }
+    }
+}
+
 inline int stream_grid(long long nvec) { return (int)min((long long)148 * 16, (nvec + kT - 1) / kT); }
 inline bool ok_c(int C) { return C >= 8 && C % 8 == 0 && (kT % (C / 8) == 0); }
 
@@ -294,18 +442,18 @@ extern "C" int sd_bn_stats_nhwc_bf16(const void* x, long long R, int C, double* 
 }
 
 extern "C" int sd_bn_apply_nhwc_bf16(const void* x, const void* residual, const float* mean, const float* invstd,
-                                     const float* gamma, const float* beta, int relu, void* y, long long R, int C,
-                                     void* stream) {
+                                     const float* gamma, const float* beta, int relu, void* y, void* relu_mask,
+                                     long long R, int C, void* stream) {
     if (R <= 0) return SD_OK;
     if (!x || !y || !mean || !invstd || !gamma || !beta || !ok_c(C)) return SD_ERR_BAD_ARG;
     const long long nvec = R * (C / 8);
     bn_apply_kernel<<<stream_grid(nvec), kT, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)residual, mean, invstd,
-                                                                       gamma, beta, relu, (uint4*)y, nvec, C / 8);
+                                                                       gamma, beta, relu, (uint4*)y, (unsigned char*)relu_mask, nvec, C / 8);
     SD_LAUNCH_CHECK();
     return SD_OK;
 }
 
-extern "C" int sd_bn_bwd_nhwc_bf16(const void* dy, const void* y_relu, const void* x, const float* mean,
+extern "C" int sd_bn_bwd_nhwc_bf16(const void* dy, const void* relu_mask, const void* x, const float* mean,
                                    const float* invstd, const float* gamma, double* sums, void* dx, void* dres,
                                    float* dgamma, float* dbeta, long long R, int C, void* stream) {
     if (R <= 0) return SD_OK;
@@ -314,12 +462,12 @@ extern "C" int sd_bn_bwd_nhwc_bf16(const void* dy, const void* y_relu, const voi
     SD_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
     const long long nvec = R * (C / 8);
     const int grid = (int)min((long long)148 * 8, (nvec + kT - 1) / kT);
-    bn_reduce_kernel<1><<<grid, kT, 0, st>>>((const uint4*)x, (const uint4*)dy, (const uint4*)y_relu, mean, invstd, nvec,
+    bn_reduce_kernel<1><<<grid, kT, 0, st>>>((const uint4*)x, (const uint4*)dy, (const unsigned char*)relu_mask, mean, invstd, nvec,
                                              C / 8, sums, C);
     SD_LAUNCH_CHECK();
     bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, C, dgamma, dbeta);
     SD_LAUNCH_CHECK();
-    bn_bwd_apply_kernel<<<stream_grid(nvec), kT, 0, st>>>((const uint4*)dy, (const uint4*)y_relu, (const uint4*)x, mean,
+    bn_bwd_apply_kernel<<<stream_grid(nvec), kT, 0, st>>>((const uint4*)dy, (const unsigned char*)relu_mask, (const uint4*)x, mean,
                                                           invstd, gamma, sums, R, (uint4*)dx, (uint4*)dres, nvec, C / 8, C);
     SD_LAUNCH_CHECK();
     return SD_OK;
@@ -344,6 +492,42 @@ extern "C" int sd_maxpool3x3s2_nhwc_bf16_bwd(const void* dy, const void* idx, vo
     const long long total = (long long)N * H * W * (C / 8);
     maxpool_bwd_kernel<<<stream_grid(total), kT, 0, (cudaStream_t)stream>>>((const uint4*)dy, (const uint2*)idx, (uint4*)dx, N,
                                                                            H, W, C / 8, HO, WO);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+}
+
+extern "C" int sd_stem_bn_relu_pool_nhwc_bf16_fwd(const void* x, const float* mean, const float* invstd, const float* gamma,
+                                                  const float* beta, void* y, void* idx, int N, int H, int W, int C,
+                                                  void* stream) {
+    if (N <= 0) return SD_OK;
+    if (!x || !mean || !invstd || !gamma || !beta || !y || !idx || !ok_c(C)) return SD_ERR_BAD_ARG;
+    const int HO = (H + 2 - 3) / 2 + 1, WO = (W + 2 - 3) / 2 + 1;
+    const long long total = (long long)N * HO * WO * (C / 8);
+    stem_fwd_kernel<<<stream_grid(total), kT, 0, (cudaStream_t)stream>>>((const uint4*)x, mean, invstd, gamma, beta, (uint4*)y,
+                                                                        (uint2*)idx, N, H, W, C / 8, HO, WO);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+}
+
+extern "C" int sd_stem_bn_relu_pool_nhwc_bf16_bwd(const void* dpool, const void* idx, const void* x, const float* mean,
+                                                  const float* invstd, const float* gamma, const float* beta, double* sums,
+                                                  void* dx, float* dgamma, float* dbeta, int N, int H, int W, int C,
+                                                  void* stream) {
+    if (N <= 0) return SD_OK;
+    if (!dpool || !idx || !x || !mean || !invstd || !gamma || !beta || !sums || !dx || !dgamma || !dbeta || !ok_c(C))
+        return SD_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int HO = (H + 2 - 3) / 2 + 1, WO = (W + 2 - 3) / 2 + 1;
+    SD_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+    const long long nvec = (long long)N * H * W * (C / 8);
+    const int grid = (int)min((long long)148 * 8, (nvec + kT - 1) / kT);
+    stem_bwd_kernel<0><<<grid, kT, 0, st>>>((const uint4*)dpool, (const uint2*)idx, (const uint4*)x, mean, invstd, gamma, beta,
+                                            sums, nullptr, N, H, W, C / 8, HO, WO, C);
+    SD_LAUNCH_CHECK();
+    bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, C, dgamma, dbeta);
+    SD_LAUNCH_CHECK();
+    stem_bwd_kernel<1><<<grid, kT, 0, st>>>((const uint4*)dpool, (const uint2*)idx, (const uint4*)x, mean, invstd, gamma, beta,
+                                            sums, (uint4*)dx, N, H, W, C / 8, HO, WO, C);
     SD_LAUNCH_CHECK();
     return SD_OK;
 }

@@ -38,15 +38,17 @@ class FusedBNAct(torch.autograd.Function):
             torch.rsqrt(running_var + eps, out=invstd)
         res = _cl(residual) if residual is not None else None
         y = torch.empty_like(x)
-        ops.bn_apply(x, res, mean, invstd, gamma, beta, relu, y, R, C)
-        ctx.save_for_backward(x, y if relu else None, mean, invstd, gamma)
+        # 1 bit per element records where the ReLU passed: the backward reads R*C/8 bytes instead of y (2 B/element)
+        mask = torch.empty(R * C // 8, device=dev, dtype=torch.uint8) if (relu and training) else None
+        ops.bn_apply(x, res, mean, invstd, gamma, beta, relu, y, mask, R, C)
+        ctx.save_for_backward(x, mask, mean, invstd, gamma)
         ctx.meta = (R, C, residual is not None, training)
         ctx.sums = sums
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y, mean, invstd, gamma = ctx.saved_tensors
+        x, mask, mean, invstd, gamma = ctx.saved_tensors
         R, C, has_res, training = ctx.meta
         if not training:
             raise RuntimeError("FusedBNAct backward implements train-mode BatchNorm only")
@@ -55,7 +57,7 @@ class FusedBNAct(torch.autograd.Function):
         dres = torch.empty_like(x) if has_res else None
         dgamma = torch.empty(C, device=x.device, dtype=torch.float32)
         dbeta = torch.empty(C, device=x.device, dtype=torch.float32)
-        ops.bn_bwd(dy, y, x, mean, invstd, gamma, ctx.sums, dx, dres, dgamma, dbeta, R, C)
+        ops.bn_bwd(dy, mask, x, mean, invstd, gamma, ctx.sums, dx, dres, dgamma, dbeta, R, C)
         return dx, dgamma, dbeta, None, None, dres, None, None, None, None
 
 
@@ -82,6 +84,45 @@ class MaxPool3x3s2(torch.autograd.Function):
         return dx
 
 
+class StemBNReLUPool(torch.autograd.Function):
+    """maxpool3x3s2(relu(BN(x))) in one pass (torchvision ResNet stem after conv1)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, training: bool, momentum: float, eps: float):
+        x = _cl(x)
+        N, C, H, W = x.shape
+        dev = x.device
+        mean = torch.empty(C, device=dev, dtype=torch.float32)
+        invstd = torch.empty(C, device=dev, dtype=torch.float32)
+        sums = torch.empty(2 * C, device=dev, dtype=torch.float64)
+        if training:
+            ops.bn_stats(x, N * H * W, C, sums, eps, momentum, mean, invstd, running_mean, running_var)
+        else:
+            mean.copy_(running_mean)
+            torch.rsqrt(running_var + eps, out=invstd)
+        HO, WO = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        y = torch.empty((N, C, HO, WO), device=dev, dtype=x.dtype, memory_format=torch.channels_last)
+        idx = torch.empty((N, HO, WO, C), device=dev, dtype=torch.uint8)
+        ops.stem_fwd(x, mean, invstd, gamma, beta, y, idx, N, H, W, C)
+        ctx.save_for_backward(x, idx, mean, invstd, gamma, beta)
+        ctx.sums = sums
+        ctx.training = training
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, idx, mean, invstd, gamma, beta = ctx.saved_tensors
+        if not ctx.training:
+            raise RuntimeError("StemBNReLUPool backward implements train-mode BatchNorm only")
+        N, C, H, W = x.shape
+        dy = _cl(dy)
+        dx = torch.empty_like(x)
+        dgamma = torch.empty(C, device=x.device, dtype=torch.float32)
+        dbeta = torch.empty(C, device=x.device, dtype=torch.float32)
+        ops.stem_bwd(dy, idx, x, mean, invstd, gamma, beta, ctx.sums, dx, dgamma, dbeta, N, H, W, C)
+        return dx, dgamma, dbeta, None, None, None, None, None
+
+
 def _bn(bn, x, residual=None, relu=True):
     if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
@@ -92,6 +133,28 @@ def _bn(bn, x, residual=None, relu=True):
 
 def _conv(conv, x):
     return F.conv2d(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
+
+
+def _stem_conv_s2d(conv, images: torch.Tensor) -> torch.Tensor:
+    """conv1 (7x7, stride 2, pad 3, Cin=3) evaluated as a 4x4 stride-1 convolution over the 2x2 space-to-depth
+    image (Cin = 3*2*2 = 12, zero-padded to 16): the same products and sums (the extra taps/channels are exact
+    zeros), but a tensor-core friendly shape instead of cuDNN's Cin=3 -> 8 padding path.  The weight transform is
+    ordinary differentiable torch code, so the gradient lands on the original (64,3,7,7) parameter."""
+    N, Cin, H, W = images.shape
+    Cout = conv.weight.shape[0]
+    x = F.pad(images.to(torch.bfloat16), (3, 3, 3, 3))                                  # (N,3,H+6,W+6)
+    Hp, Wp = (H + 6) // 2, (W + 6) // 2
+    x = x.view(N, Cin, Hp, 2, Wp, 2).permute(0, 1, 3, 5, 2, 4).reshape(N, Cin * 4, Hp, Wp)  # channel = (c, dy, dx)
+    x = F.pad(x, (0, 0, 0, 0, 0, 16 - Cin * 4)).contiguous(memory_format=torch.channels_last)
+    w = F.pad(conv.weight, (0, 1, 0, 1))                                                # (Cout,3,8,8): zero last tap
+    w = w.view(Cout, Cin, 4, 2, 4, 2).permute(0, 1, 3, 5, 2, 4).reshape(Cout, Cin * 4, 4, 4)
+    w = F.pad(w, (0, 0, 0, 0, 0, 16 - Cin * 4))
+    return F.conv2d(x, w, conv.bias, 1, 0)
+
+
+def _stem_is_s2d_compatible(conv, images) -> bool:
+    return (conv.kernel_size == (7, 7) and conv.stride == (2, 2) and conv.padding == (3, 3) and conv.dilation == (1, 1)
+            and conv.groups == 1 and conv.in_channels == 3 and images.shape[-1] % 2 == 0 and images.shape[-2] % 2 == 0)
 
 
 def supported(encoder) -> bool:
@@ -109,9 +172,15 @@ def resnet_trunk_bf16(encoder, images: torch.Tensor) -> torch.Tensor:
 
     # cuDNN autotuning for the (fixed) convolution shapes of the trunk; restored on exit
     with torch.backends.cudnn.flags(enabled=True, benchmark=True), torch.autocast("cuda", dtype=torch.bfloat16):
-        x = _conv(encoder.conv1, images.to(dtype=torch.bfloat16, memory_format=torch.channels_last))
-        x = _bn(encoder.bn1, x, None, True)
-        x = MaxPool3x3s2.apply(x)
+        if _stem_is_s2d_compatible(encoder.conv1, images):
+            x = _stem_conv_s2d(encoder.conv1, images)
+        else:
+            x = _conv(encoder.conv1, images.to(dtype=torch.bfloat16, memory_format=torch.channels_last))
+        bn1 = encoder.bn1
+        if bn1.training and bn1.track_running_stats and bn1.num_batches_tracked is not None:
+            bn1.num_batches_tracked.add_(1)
+        x = StemBNReLUPool.apply(x, bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var, bn1.training,
+                                 float(0.1 if bn1.momentum is None else bn1.momentum), float(bn1.eps))
         for layer in (encoder.layer1, encoder.layer2, encoder.layer3, encoder.layer4):
             for blk in layer:
                 identity = x

@@ -267,16 +267,17 @@ def bn_stats(x, R, C, sums, eps, momentum, mean, invstd, running_mean, running_v
     _count(2)
 
 
-def bn_apply(x, residual, mean, invstd, gamma, beta, relu, y, R, C):
-    with _Timed("bn_apply", 0.0, 2.0 * R * C * (3 if residual is not None else 2), f"[R{R} C{C}]"):
+def bn_apply(x, residual, mean, invstd, gamma, beta, relu, y, mask, R, C):
+    with _Timed("bn_apply", 0.0, 2.0 * R * C * (3 if residual is not None else 2) + (R * C / 8 if mask is not None else 0),
+                f"[R{R} C{C}]"):
         check(_lib.lib().sd_bn_apply_nhwc_bf16(x.data_ptr(), _lib.ptr(residual), mean.data_ptr(), invstd.data_ptr(),
-                                               gamma.data_ptr(), beta.data_ptr(), 1 if relu else 0, y.data_ptr(), R, C,
-                                               stream_ptr()), "sd_bn_apply_nhwc_bf16")
+                                               gamma.data_ptr(), beta.data_ptr(), 1 if relu else 0, y.data_ptr(),
+                                               _lib.ptr(mask), R, C, stream_ptr()), "sd_bn_apply_nhwc_bf16")
     _count()
 
 
 def bn_bwd(dy, y_relu, x, mean, invstd, gamma, sums, dx, dres, dgamma, dbeta, R, C):
-    nb = 2.0 * R * C * ((3 if y_relu is not None else 2) * 2 + 1 + (1 if dres is not None else 0))
+    nb = 2.0 * R * C * (2 * 2 + 1 + (1 if dres is not None else 0)) + (2.0 * R * C / 8 if y_relu is not None else 0)
     with _Timed("bn_bwd", 0.0, nb, f"[R{R} C{C}]"):
         check(_lib.lib().sd_bn_bwd_nhwc_bf16(dy.data_ptr(), _lib.ptr(y_relu), x.data_ptr(), mean.data_ptr(),
                                              invstd.data_ptr(), gamma.data_ptr(), sums.data_ptr(), dx.data_ptr(),
@@ -297,3 +298,23 @@ def maxpool_bwd(dy, idx, dx, N, H, W, C):
         check(_lib.lib().sd_maxpool3x3s2_nhwc_bf16_bwd(dy.data_ptr(), idx.data_ptr(), dx.data_ptr(), N, H, W, C, stream_ptr()),
               "sd_maxpool3x3s2_nhwc_bf16_bwd")
     _count()
+
+
+def stem_fwd(x, mean, invstd, gamma, beta, y, idx, N, H, W, C):
+    with _Timed("stem_bn_relu_pool_fwd", 0.0, 2.0 * N * H * W * C * 1.25 + N * H * W * C / 4, f"[N{N} H{H} C{C}]"):
+        check(_lib.lib().sd_stem_bn_relu_pool_nhwc_bf16_fwd(x.data_ptr(), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+                                                            beta.data_ptr(), y.data_ptr(), idx.data_ptr(), N, H, W, C,
+                                                            stream_ptr()), "sd_stem_bn_relu_pool_nhwc_bf16_fwd")
+    _count()
+
+
+def stem_bwd(dpool, idx, x, mean, invstd, gamma, beta, sums, dx, dgamma, dbeta, N, H, W, C):
+    # two passes, each reads x once and the pooled gradient + taps; the second writes dx
+    nb = 2.0 * N * H * W * C * 3 + 2 * (2.0 * N * H * W * C / 4 + N * H * W * C / 4)
+    with _Timed("stem_bn_relu_pool_bwd", 0.0, nb, f"[N{N} H{H} C{C}]"):
+        check(_lib.lib().sd_stem_bn_relu_pool_nhwc_bf16_bwd(dpool.data_ptr(), idx.data_ptr(), x.data_ptr(), mean.data_ptr(),
+                                                            invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                                            sums.data_ptr(), dx.data_ptr(), dgamma.data_ptr(),
+                                                            dbeta.data_ptr(), N, H, W, C, stream_ptr()),
+              "sd_stem_bn_relu_pool_nhwc_bf16_bwd")
+    _count(3)

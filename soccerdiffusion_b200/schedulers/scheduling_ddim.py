@@ -92,6 +92,7 @@ class DDIMScheduler:
         self._n_train = num_train_timesteps
         self._steps_offset = steps_offset
         self._acp_dev: dict = {}
+        self._tables: dict = {}
 
     # ------------------------------------------------------------------------------------------
     def _acp_on(self, device) -> torch.Tensor:
@@ -130,9 +131,13 @@ class DDIMScheduler:
 
     def schedule_tables(self):
         """(timesteps list, (n,4) float32 coefficient table) for the persistent sampler (sd_plan_set_schedule)."""
-        ts = [int(t) for t in self.timesteps]
-        coef = np.asarray([self.coefficients(t) for t in ts], dtype=np.float32)
-        return ts, coef
+        key = (self.num_inference_steps, self._steps_offset)
+        hit = self._tables.get(key)
+        if hit is None:
+            ts = [int(t) for t in self.timesteps]
+            coef = np.asarray([self.coefficients(t) for t in ts], dtype=np.float32)
+            hit = self._tables[key] = (ts, coef)
+        return hit
 
     # ------------------------------------------------------------------------------------------
     def scale_model_input(self, sample, timestep=None):

@@ -299,6 +299,17 @@ def test_trajectory_sampler_control_tick_and_distilled():
         ctx = model_ref.encode_input_data(synth.synth_batch(hp, 1, 4), sd, hp)
         want, _ = model_ref.sample_ddim(ctx, x_T, sd, hp, 30)
     assert rel(out, want * sd["std"] + sd["mean"]) < TOL
+    # the same tick replayed from a captured CUDA graph (twice: replays must not depend on capture-time state)
+    gs = TrajectorySampler(model, sch, 30, use_cuda_graph=True)
+    for seed2 in (4, 6):
+        b2 = synth.synth_batch(hp, 1, seed2)
+        x2 = synth.synth_noise("x_T", hp, 1, seed2)
+        got = gs(to_dev(b2), x2.cuda())
+        with torch.no_grad():
+            c2 = model_ref.encode_input_data(b2, sd, hp)
+            w2, _ = model_ref.sample_ddim(c2, x2, sd, hp, 30)
+        assert rel(got, w2 * sd["std"] + sd["mean"]) < TOL, seed2
+    assert len(gs._graphs) == 1
     d1 = TrajectorySampler(model, sch, 30, distilled=True)(batch, x_T.cuda(), denormalize=False)
     with torch.no_grad():
         w1 = model_ref.forward_with_context(ctx, x_T, torch.zeros(1, dtype=torch.int64), sd, hp)

@@ -73,6 +73,30 @@ def test_maxpool_forward_backward(N, C, H, W):
     assert rel(xg.grad.float(), xf.grad) < 5e-3   # sums of <= 4 bf16 gradients, rounded once to bf16
 
 
+@pytest.mark.parametrize("N,C,H,W", [(3, 64, 112, 112), (2, 64, 30, 34), (1, 16, 7, 9)])
+def test_fused_stem_bn_relu_pool(N, C, H, W):
+    from soccerdiffusion_b200.ml.model.encoder.trunk import StemBNReLUPool
+
+    torch.manual_seed(H)
+    x = (_cl_bf16(N, C, H, W) * 1.3 - 0.2).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    gamma = (torch.rand(C, device="cuda") + 0.5).requires_grad_(True)
+    beta = (torch.randn(C, device="cuda") * 0.2).requires_grad_(True)
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    rm2, rv2 = rm.clone(), rv.clone()
+    xg = x.clone().requires_grad_(True)
+    y = StemBNReLUPool.apply(xg, gamma, beta, rm, rv, True, 0.1, 1e-5)
+    go = _cl_bf16(*y.shape)
+    y.backward(go)
+    xf = x.float().requires_grad_(True)
+    g2, b2 = gamma.detach().clone().requires_grad_(True), beta.detach().clone().requires_grad_(True)
+    yf = F.max_pool2d(F.relu(F.batch_norm(xf, rm2, rv2, g2, b2, True, 0.1, 1e-5)), 3, 2, 1)
+    yf.backward(go.float())
+    assert rel(y.float(), yf) < 6e-3
+    assert rel(rm, rm2) < 1e-4 and rel(rv, rv2) < 1e-4
+    assert rel(xg.grad.float(), xf.grad) < 1.5e-2
+    assert rel(gamma.grad, g2.grad) < 1.5e-2 and rel(beta.grad, b2.grad) < 1.5e-2
+
+
 def test_fused_trunk_matches_library_trunk_bf16():
     import soccerdiffusion_b200 as sdb
     from oracle import synth
