@@ -145,10 +145,16 @@ int sd_bn_stats_nhwc_bf16(const void* x, long long R, int C, double* sums, float
 /* relu_mask (optional, R*C/8 bytes): bit i of byte v = ReLU passed channel 8*(v % (C/8)) + i of row v / (C/8) */
 int sd_bn_apply_nhwc_bf16(const void* x, const void* residual, const float* mean, const float* invstd, const float* gamma,
                           const float* beta, int relu, void* y, void* relu_mask, long long R, int C, void* stream);
-/* dy -> (dx, dresidual = dy*relu_mask, dgamma, dbeta); relu_mask = the bytes written by the forward, or NULL */
+/* dy -> (dx, dresidual = dy*relu_mask, dgamma, dbeta); relu_mask = the bytes written by the forward, or NULL;
+ * beta_recompute (used when relu_mask is NULL): non-NULL = a ReLU followed the BatchNorm (no residual) and its mask
+ * is recomputed as (x - mean) * invstd * gamma + beta > 0 */
 int sd_bn_bwd_nhwc_bf16(const void* dy, const void* relu_mask, const void* x, const float* mean, const float* invstd,
-                        const float* gamma, double* sums, void* dx, void* dres, float* dgamma, float* dbeta, long long R,
+                        const float* gamma, const float* beta_recompute, double* sums, void* dx, void* dres, float* dgamma, float* dbeta, long long R,
                         int C, void* stream);
+/* fp32 NCHW images (N,3,H,W), H and W even -> bf16 NHWC (N,(H+6)/2,(W+6)/2,16): 3-pixel zero padding + 2x2
+ * space-to-depth (channel = c*4 + dy*2 + dx, 12 used), the layout in which the 7x7/s2/p3 stem convolution
+ * (torchvision resnet conv1; ml/model/encoder/image.py:55-73) is a 4x4/s1 convolution with Cin=16 */
+int sd_stem_pack_s2d_bf16(const float* images, void* out, int N, int H, int W, void* stream);
 /* Fused stem: maxpool3x3s2(relu(bn(x))) without materialising the activated 112x112 map; backward recomputes the
  * ReLU mask from x (torchvision ResNet stem bn1 -> relu -> maxpool). mean/invstd from sd_bn_stats_nhwc_bf16. */
 int sd_stem_bn_relu_pool_nhwc_bf16_fwd(const void* x, const float* mean, const float* invstd, const float* gamma,

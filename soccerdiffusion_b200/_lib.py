@@ -85,7 +85,8 @@ SIGNATURES = {
     "sd_dropout_apply": [c_f, c_f, c_ll, c_fl, c_ull, c_u, c_f],
     "sd_bn_stats_nhwc_bf16": [c_f, c_ll, c_i, c_f, c_fl, c_fl, c_f, c_f, c_f, c_f, c_f],
     "sd_bn_apply_nhwc_bf16": [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_ll, c_i, c_f],
-    "sd_bn_bwd_nhwc_bf16": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_ll, c_i, c_f],
+    "sd_bn_bwd_nhwc_bf16": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_ll, c_i, c_f],
+    "sd_stem_pack_s2d_bf16": [c_f, c_f, c_i, c_i, c_i, c_f],
     "sd_stem_bn_relu_pool_nhwc_bf16_fwd": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f],
     "sd_stem_bn_relu_pool_nhwc_bf16_bwd": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f],
     "sd_maxpool3x3s2_nhwc_bf16_fwd": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f],

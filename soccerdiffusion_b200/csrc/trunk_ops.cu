@@ -50,14 +50,22 @@ template <int MODE>
 __global__ void __launch_bounds__(kT) bn_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
                                                        const unsigned char* __restrict__ y, const float* __restrict__ mean,
                                                        const float* __restrict__ invstd, long long nvec, int CV,
-                                                       double* __restrict__ out, int C) {
+                                                       double* __restrict__ out, int C,
+                                                       const float* __restrict__ gamma_rc, const float* __restrict__ beta_rc) {
     __shared__ float red[2][kT][8 + 1];
     const int tid = threadIdx.x;
     const int cv = tid % CV;   // kT % CV == 0: a thread keeps its channel group for every vector it visits
-    float mu[8], is[8];
+    float mu[8], is[8], sc[8], sh[8];
     if (MODE == 1) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { mu[i] = mean[cv * 8 + i]; is[i] = invstd[cv * 8 + i]; }
+        for (int i = 0; i < 8; ++i) {
+            mu[i] = mean[cv * 8 + i];
+            is[i] = invstd[cv * 8 + i];
+            if (beta_rc) {   // ReLU mask recomputed from x: relu(x*sc + sh) > 0
+                sc[i] = is[i] * gamma_rc[cv * 8 + i];
+                sh[i] = beta_rc[cv * 8 + i] - mu[i] * sc[i];
+            }
+        }
     }
     float a0[8], a1[8];
 #pragma unroll
@@ -77,6 +85,9 @@ __global__ void __launch_bounds__(kT) bn_reduce_kernel(const uint4* __restrict__
                 const unsigned mk = y[v];   // bit i: ReLU passed channel i of this vector in the forward pass
 #pragma unroll
                 for (int i = 0; i < 8; ++i) g[i] = (mk >> i) & 1u ? g[i] : 0.f;
+            } else if (beta_rc) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) g[i] = fmaf(fx[i], sc[i], sh[i]) > 0.f ? g[i] : 0.f;
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) { a0[i] += g[i]; a1[i] = fmaf(g[i], (fx[i] - mu[i]) * is[i], a1[i]); }
@@ -159,11 +170,11 @@ __global__ void __launch_bounds__(kT) bn_bwd_apply_kernel(const uint4* __restric
                                                           const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                           const double* __restrict__ sums, long long R,
                                                           uint4* __restrict__ dx, uint4* __restrict__ dres, long long nvec,
-                                                          int CV, int C) {
+                                                          int CV, int C, const float* __restrict__ beta_rc) {
     const long long stride = (long long)gridDim.x * kT;
     const long long v0 = (long long)blockIdx.x * kT + threadIdx.x;
     const int cv = threadIdx.x % CV;
-    float mu[8], is[8], k0[8], k1[8], k2[8];
+    float mu[8], is[8], k0[8], k1[8], k2[8], sh[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int c = cv * 8 + i;
@@ -172,6 +183,7 @@ __global__ void __launch_bounds__(kT) bn_bwd_apply_kernel(const uint4* __restric
         k0[i] = gamma[c] * is[i];
         k1[i] = (float)(sums[c] / (double)R);
         k2[i] = (float)(sums[C + c] / (double)R);
+        sh[i] = beta_rc ? beta_rc[c] - mu[i] * k0[i] : 0.f;
     }
     for (long long v = v0; v < nvec; v += stride) {
         float g[8], fx[8];
@@ -181,6 +193,9 @@ __global__ void __launch_bounds__(kT) bn_bwd_apply_kernel(const uint4* __restric
             const unsigned mk = y[v];
 #pragma unroll
             for (int i = 0; i < 8; ++i) g[i] = (mk >> i) & 1u ? g[i] : 0.f;
+        } else if (beta_rc) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i] = fmaf(fx[i], k0[i], sh[i]) > 0.f ? g[i] : 0.f;
         }
         if (dres) dres[v] = pack8(g);
         float o[8];
@@ -420,6 +435,39 @@ __global__ void __launch_bounds__(kT) stem_bwd_kernel(const uint4* __restrict__ 
     }
 }
 
+// ---- stem input packing: fp32 NCHW image -> bf16 NHWC, 2x2 space-to-depth of the 3-pixel zero-padded image -------
+// out[n][hp][wp][c*4 + dy*2 + dx] = in[n][c][2*hp + dy - 3][2*wp + dx - 3]  (12 channels, zero-padded to 16):
+// the operand layout under which conv1 (7x7/s2/p3, Cin=3) becomes a 4x4/s1 convolution with Cin=16.
+__global__ void __launch_bounds__(kT) stem_pack_kernel(const float* __restrict__ in, uint4* __restrict__ out, int N, int H,
+                                                       int W, int Hp, int Wp) {
+    const long long total = (long long)N * Hp * Wp;
+    for (long long o = (long long)blockIdx.x * kT + threadIdx.x; o < total; o += (long long)gridDim.x * kT) {
+        const int wp = (int)(o % Wp);
+        long long r = o / Wp;
+        const int hp = (int)(r % Hp);
+        const int n = (int)(r / Hp);
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float* plane = in + ((long long)n * 3 + c) * H * W;
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+                const int h = 2 * hp + dy - 3;
+                if (h < 0 || h >= H) continue;
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const int w = 2 * wp + dx - 3;
+                    if (w >= 0 && w < W) f[c * 4 + dy * 2 + dx] = __ldg(plane + (long long)h * W + w);
+                }
+            }
+        }
+        out[2 * o] = pack8(f);
+        out[2 * o + 1] = pack8(f + 8);
+    }
+}
+
 inline int stream_grid(long long nvec) { return (int)min((long long)148 * 16, (nvec + kT - 1) / kT); }
 inline bool ok_c(int C) { return C >= 8 && C % 8 == 0 && (kT % (C / 8) == 0); }
 
@@ -434,7 +482,8 @@ extern "C" int sd_bn_stats_nhwc_bf16(const void* x, long long R, int C, double* 
     SD_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
     const long long nvec = R * (C / 8);
     const int grid = (int)min((long long)148 * 8, (nvec + kT - 1) / kT);
-    bn_reduce_kernel<0><<<grid, kT, 0, st>>>((const uint4*)x, nullptr, nullptr, nullptr, nullptr, nvec, C / 8, sums, C);
+    bn_reduce_kernel<0><<<grid, kT, 0, st>>>((const uint4*)x, nullptr, nullptr, nullptr, nullptr, nvec, C / 8, sums, C, nullptr,
+                                             nullptr);
     SD_LAUNCH_CHECK();
     bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, R, C, eps, momentum, mean, invstd, running_mean, running_var);
     SD_LAUNCH_CHECK();
@@ -454,8 +503,8 @@ extern "C" int sd_bn_apply_nhwc_bf16(const void* x, const void* residual, const 
 }
 
 extern "C" int sd_bn_bwd_nhwc_bf16(const void* dy, const void* relu_mask, const void* x, const float* mean,
-                                   const float* invstd, const float* gamma, double* sums, void* dx, void* dres,
-                                   float* dgamma, float* dbeta, long long R, int C, void* stream) {
+                                   const float* invstd, const float* gamma, const float* beta_recompute, double* sums,
+                                   void* dx, void* dres, float* dgamma, float* dbeta, long long R, int C, void* stream) {
     if (R <= 0) return SD_OK;
     if (!dy || !x || !mean || !invstd || !gamma || !sums || !dx || !dgamma || !dbeta || !ok_c(C)) return SD_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
@@ -463,12 +512,13 @@ extern "C" int sd_bn_bwd_nhwc_bf16(const void* dy, const void* relu_mask, const 
     const long long nvec = R * (C / 8);
     const int grid = (int)min((long long)148 * 8, (nvec + kT - 1) / kT);
     bn_reduce_kernel<1><<<grid, kT, 0, st>>>((const uint4*)x, (const uint4*)dy, (const unsigned char*)relu_mask, mean, invstd, nvec,
-                                             C / 8, sums, C);
+                                             C / 8, sums, C, gamma, relu_mask ? nullptr : beta_recompute);
     SD_LAUNCH_CHECK();
     bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, C, dgamma, dbeta);
     SD_LAUNCH_CHECK();
     bn_bwd_apply_kernel<<<stream_grid(nvec), kT, 0, st>>>((const uint4*)dy, (const unsigned char*)relu_mask, (const uint4*)x, mean,
-                                                          invstd, gamma, sums, R, (uint4*)dx, (uint4*)dres, nvec, C / 8, C);
+                                                          invstd, gamma, sums, R, (uint4*)dx, (uint4*)dres, nvec, C / 8, C,
+                                                          relu_mask ? nullptr : beta_recompute);
     SD_LAUNCH_CHECK();
     return SD_OK;
 }
@@ -528,6 +578,16 @@ extern "C" int sd_stem_bn_relu_pool_nhwc_bf16_bwd(const void* dpool, const void*
     SD_LAUNCH_CHECK();
     stem_bwd_kernel<1><<<grid, kT, 0, st>>>((const uint4*)dpool, (const uint2*)idx, (const uint4*)x, mean, invstd, gamma, beta,
                                             sums, (uint4*)dx, N, H, W, C / 8, HO, WO, C);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+}
+
+extern "C" int sd_stem_pack_s2d_bf16(const float* images, void* out, int N, int H, int W, void* stream) {
+    if (N <= 0) return SD_OK;
+    if (!images || !out || (H & 1) || (W & 1)) return SD_ERR_BAD_ARG;
+    const int Hp = (H + 6) / 2, Wp = (W + 6) / 2;
+    const long long total = (long long)N * Hp * Wp;
+    stem_pack_kernel<<<stream_grid(total), kT, 0, (cudaStream_t)stream>>>(images, (uint4*)out, N, H, W, Hp, Wp);
     SD_LAUNCH_CHECK();
     return SD_OK;
 }

@@ -116,10 +116,15 @@ class StemBNReLUPool(torch.autograd.Function):
             raise RuntimeError("StemBNReLUPool backward implements train-mode BatchNorm only")
         N, C, H, W = x.shape
         dy = _cl(dy)
-        dx = torch.empty_like(x)
         dgamma = torch.empty(C, device=x.device, dtype=torch.float32)
         dbeta = torch.empty(C, device=x.device, dtype=torch.float32)
-        ops.stem_bwd(dy, idx, x, mean, invstd, gamma, beta, ctx.sums, dx, dgamma, dbeta, N, H, W, C)
+        # gradient w.r.t. the (never materialised) activated map, then BatchNorm backward with the ReLU mask
+        # recomputed from x.  (A single gather-fused kernel, sd_stem_bn_relu_pool_nhwc_bf16_bwd, exists but measured
+        # slower: it is instruction-bound on the arg-max tap matching.)
+        dact = torch.empty_like(x)
+        ops.maxpool_bwd(dy, idx, dact, N, H, W, C)
+        dx = torch.empty_like(x)
+        ops.bn_bwd(dact, None, x, mean, invstd, gamma, ctx.sums, dx, None, dgamma, dbeta, N * H * W, C, beta_recompute=beta)
         return dx, dgamma, dbeta, None, None, None, None, None
 
 
@@ -142,14 +147,52 @@ def _stem_conv_s2d(conv, images: torch.Tensor) -> torch.Tensor:
     ordinary differentiable torch code, so the gradient lands on the original (64,3,7,7) parameter."""
     N, Cin, H, W = images.shape
     Cout = conv.weight.shape[0]
-    x = F.pad(images.to(torch.bfloat16), (3, 3, 3, 3))                                  # (N,3,H+6,W+6)
     Hp, Wp = (H + 6) // 2, (W + 6) // 2
-    x = x.view(N, Cin, Hp, 2, Wp, 2).permute(0, 1, 3, 5, 2, 4).reshape(N, Cin * 4, Hp, Wp)  # channel = (c, dy, dx)
-    x = F.pad(x, (0, 0, 0, 0, 0, 16 - Cin * 4)).contiguous(memory_format=torch.channels_last)
+    if images.dtype == torch.float32 and not images.requires_grad:
+        # one pass: pad + space-to-depth + bf16 + NHWC (channel = (c, dy, dx), 12 -> 16)
+        xp = torch.empty((N, Hp, Wp, 16), device=images.device, dtype=torch.bfloat16)
+        ops.stem_pack(images.contiguous(), xp, N, H, W)
+        x = xp.permute(0, 3, 1, 2)                                                       # NCHW view of NHWC storage
+    else:
+        x = F.pad(images.to(torch.bfloat16), (3, 3, 3, 3))                               # (N,3,H+6,W+6)
+        x = x.view(N, Cin, Hp, 2, Wp, 2).permute(0, 1, 3, 5, 2, 4).reshape(N, Cin * 4, Hp, Wp)
+        x = F.pad(x, (0, 0, 0, 0, 0, 16 - Cin * 4)).contiguous(memory_format=torch.channels_last)
     w = F.pad(conv.weight, (0, 1, 0, 1))                                                # (Cout,3,8,8): zero last tap
     w = w.view(Cout, Cin, 4, 2, 4, 2).permute(0, 1, 3, 5, 2, 4).reshape(Cout, Cin * 4, 4, 4)
     w = F.pad(w, (0, 0, 0, 0, 0, 16 - Cin * 4))
     return F.conv2d(x, w, conv.bias, 1, 0)
+
+
+class StemConvS2D(torch.autograd.Function):
+    """conv1 forward in the space-to-depth formulation (fast cuDNN fprop), weight gradient in the original 7x7
+    formulation (cuDNN's wgrad kernel for the 4x4/Cin=16 problem measured 2.3x slower than for 7x7/Cin=3)."""
+
+    @staticmethod
+    def forward(ctx, images, weight):
+        with torch.no_grad():
+            y = _stem_conv_s2d_raw(images, weight)
+        ctx.save_for_backward(images, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        images, weight = ctx.saved_tensors
+        x = images.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+        gw = torch.ops.aten.convolution_backward(_cl(dy), x, weight.to(torch.bfloat16), None, (2, 2), (3, 3), (1, 1), False,
+                                                 (0, 0), 1, (False, True, False))[1]
+        return None, gw.to(weight.dtype)
+
+
+def _stem_conv_s2d_raw(images, weight):
+    N, Cin, H, W = images.shape
+    Cout = weight.shape[0]
+    Hp, Wp = (H + 6) // 2, (W + 6) // 2
+    xp = torch.empty((N, Hp, Wp, 16), device=images.device, dtype=torch.bfloat16)
+    ops.stem_pack(images.contiguous(), xp, N, H, W)
+    w = F.pad(weight.to(torch.bfloat16), (0, 1, 0, 1))
+    w = w.view(Cout, Cin, 4, 2, 4, 2).permute(0, 1, 3, 5, 2, 4).reshape(Cout, Cin * 4, 4, 4)
+    w = F.pad(w, (0, 0, 0, 0, 0, 16 - Cin * 4)).contiguous(memory_format=torch.channels_last)
+    return F.conv2d(xp.permute(0, 3, 1, 2), w, None, 1, 0)
 
 
 def _stem_is_s2d_compatible(conv, images) -> bool:
@@ -173,7 +216,10 @@ def resnet_trunk_bf16(encoder, images: torch.Tensor) -> torch.Tensor:
     # cuDNN autotuning for the (fixed) convolution shapes of the trunk; restored on exit
     with torch.backends.cudnn.flags(enabled=True, benchmark=True), torch.autocast("cuda", dtype=torch.bfloat16):
         if _stem_is_s2d_compatible(encoder.conv1, images):
-            x = _stem_conv_s2d(encoder.conv1, images)
+            if images.dtype == torch.float32 and not images.requires_grad and encoder.conv1.bias is None:
+                x = StemConvS2D.apply(images, encoder.conv1.weight)
+            else:
+                x = _stem_conv_s2d(encoder.conv1, images)
         else:
             x = _conv(encoder.conv1, images.to(dtype=torch.bfloat16, memory_format=torch.channels_last))
         bn1 = encoder.bn1

@@ -276,12 +276,13 @@ def bn_apply(x, residual, mean, invstd, gamma, beta, relu, y, mask, R, C):
     _count()
 
 
-def bn_bwd(dy, y_relu, x, mean, invstd, gamma, sums, dx, dres, dgamma, dbeta, R, C):
+def bn_bwd(dy, y_relu, x, mean, invstd, gamma, sums, dx, dres, dgamma, dbeta, R, C, beta_recompute=None):
     nb = 2.0 * R * C * (2 * 2 + 1 + (1 if dres is not None else 0)) + (2.0 * R * C / 8 if y_relu is not None else 0)
     with _Timed("bn_bwd", 0.0, nb, f"[R{R} C{C}]"):
         check(_lib.lib().sd_bn_bwd_nhwc_bf16(dy.data_ptr(), _lib.ptr(y_relu), x.data_ptr(), mean.data_ptr(),
-                                             invstd.data_ptr(), gamma.data_ptr(), sums.data_ptr(), dx.data_ptr(),
-                                             _lib.ptr(dres), dgamma.data_ptr(), dbeta.data_ptr(), R, C, stream_ptr()),
+                                             invstd.data_ptr(), gamma.data_ptr(), _lib.ptr(beta_recompute), sums.data_ptr(),
+                                             dx.data_ptr(), _lib.ptr(dres), dgamma.data_ptr(), dbeta.data_ptr(), R, C,
+                                             stream_ptr()),
               "sd_bn_bwd_nhwc_bf16")
     _count(3)
 
@@ -318,3 +319,10 @@ def stem_bwd(dpool, idx, x, mean, invstd, gamma, beta, sums, dx, dgamma, dbeta, 
                                                             dbeta.data_ptr(), N, H, W, C, stream_ptr()),
               "sd_stem_bn_relu_pool_nhwc_bf16_bwd")
     _count(3)
+
+
+def stem_pack(images, out, N, H, W):
+    with _Timed("stem_pack_s2d", 0.0, 12.0 * N * H * W + 32.0 * N * ((H + 6) // 2) * ((W + 6) // 2), f"[N{N} H{H}]"):
+        check(_lib.lib().sd_stem_pack_s2d_bf16(images.data_ptr(), out.data_ptr(), N, H, W, stream_ptr()),
+              "sd_stem_pack_s2d_bf16")
+    _count()

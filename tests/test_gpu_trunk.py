@@ -97,7 +97,31 @@ def test_fused_stem_bn_relu_pool(N, C, H, W):
     assert rel(gamma.grad, g2.grad) < 1.5e-2 and rel(beta.grad, b2.grad) < 1.5e-2
 
 
+def test_stem_pack_and_space_to_depth_conv_equal_conv1():
+    from soccerdiffusion_b200.ml.model.encoder.trunk import _stem_conv_s2d
+
+    torch.manual_seed(0)
+    conv = torch.nn.Conv2d(3, 64, 7, 2, 3, bias=False).cuda()
+    img = torch.randn(3, 3, 64, 96, device="cuda")
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        got = _stem_conv_s2d(conv, img)                        # packed by sd_stem_pack_s2d_bf16
+        got2 = _stem_conv_s2d(conv, img.double().float().requires_grad_(True))   # torch-op packing path
+        want = conv(img.to(memory_format=torch.channels_last))
+    assert got.shape == want.shape
+    assert rel(got.float(), want.float()) < 4e-3 and rel(got2.float(), want.float()) < 4e-3
+    assert torch.equal(got, got2)                              # the two packings feed cuDNN identical operands
+    got.float().square().mean().backward()
+    g1 = conv.weight.grad.clone()
+    conv.weight.grad = None
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        conv(img.to(memory_format=torch.channels_last)).float().square().mean().backward()
+    assert rel(g1, conv.weight.grad) < 1e-2
+
+
 def test_fused_trunk_matches_library_trunk_bf16():
+    """Whole trunk, train mode: libsd_b200 path (space-to-depth stem, fused BN/ReLU/pool kernels) and torch's bf16
+    autocast path are both compared with the fp32 trunk; the fused path must be as close to fp32 as the library
+    bf16 path is (a layout/indexing bug would show as a much larger error, bf16 noise does not)."""
     import soccerdiffusion_b200 as sdb
     from oracle import synth
     from soccerdiffusion_b200 import runtime
@@ -105,26 +129,28 @@ def test_fused_trunk_matches_library_trunk_bf16():
 
     hp = dict(synth.TINY_HP, image_resolution=96, image_context_length=3)
     outs = {}
-    sdb.set_precision("bf16")
     try:
-        for fused in (True, False):
+        for name, prec, fused in (("fp32", "fp32", False), ("fused", "bf16", True), ("lib", "bf16", False)):
+            sdb.set_precision(prec)
             runtime.set_fused_trunk(fused)
             model, _ = synth_model(hp, 3)
             model.train()
             enc = model.image_sequence_encoder.image_encoder
             imgs = torch.from_numpy(synth.normal("img", (2 * 3, 3, 96, 96), 3)).cuda()
             feat = enc.trunk(imgs)
-            feat.float().square().mean().backward()
+            tgt = torch.from_numpy(synth.normal("tgt", tuple(feat.shape), 3)).cuda()
+            (feat.float() * tgt).mean().backward()   # linear functional of the features: no amplification by the loss
             e = enc.encoder
-            outs[fused] = dict(feat=feat.float().detach(), rm=e.bn1.running_mean.clone(), rv=e.layer2[0].bn2.running_var.clone(),
-                               nbt=int(e.bn1.num_batches_tracked), g_conv1=e.conv1.weight.grad.clone(),
-                               g_bn=e.layer3[1].bn2.weight.grad.clone(), g_ds=e.layer4[0].downsample[0].weight.grad.clone())
+            outs[name] = dict(feat=feat.float().detach(), rm=e.bn1.running_mean.clone(), rv=e.layer2[0].bn2.running_var.clone(),
+                              nbt=int(e.bn1.num_batches_tracked), g_conv1=e.conv1.weight.grad.clone(),
+                              g_bn1=e.bn1.weight.grad.clone(), g_l1=e.layer1[0].conv1.weight.grad.clone(),
+                              g_bn=e.layer3[1].bn2.weight.grad.clone(), g_ds=e.layer4[0].downsample[0].weight.grad.clone())
     finally:
         runtime.set_fused_trunk(True)
         sdb.set_precision("fp32")
-    a, b = outs[True], outs[False]
-    assert a["nbt"] == b["nbt"] == 1
-    assert rel(a["feat"], b["feat"]) < 5e-2   # two independent bf16 pipelines, 20 layers deep
-    assert rel(a["rm"], b["rm"]) < 1e-2 and rel(a["rv"], b["rv"]) < 1e-2
-    for k in ("g_conv1", "g_bn", "g_ds"):
-        assert rel(a[k], b[k]) < 8e-2, k   # two bf16 pipelines, 20 layers deep
+    ref, a, b = outs["fp32"], outs["fused"], outs["lib"]
+    assert a["nbt"] == b["nbt"] == ref["nbt"] == 1
+    for k in ("feat", "rm", "rv", "g_ds", "g_bn", "g_l1", "g_bn1", "g_conv1"):
+        ea, eb = rel(a[k], ref[k]), rel(b[k], ref[k])
+        print(f"{k}: fused-vs-fp32 {ea:.3e}  torch-bf16-vs-fp32 {eb:.3e}")
+        assert ea < max(2.0 * eb, 2e-2), (k, ea, eb)
