@@ -72,25 +72,43 @@ __global__ void __launch_bounds__(kT) bn_reduce_kernel(const uint4* __restrict__
     for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.f;
     const long long per_cta = ((nvec + gridDim.x - 1) / gridDim.x + kT - 1) / kT * kT;
     const long long v0 = blockIdx.x * per_cta, v1 = min(nvec, v0 + per_cta);
-    for (long long v = v0 + tid; v < v1; v += kT) {
-        float fx[8];
-        unpack8(ld_stream(x + v), fx);
-        if (MODE == 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { a0[i] += fx[i]; a1[i] = fmaf(fx[i], fx[i], a1[i]); }
-        } else {
-            float g[8];
-            unpack8(ld_stream(dy + v), g);
+    // two vectors per iteration: all loads of both are issued before any use (memory-level parallelism)
+    for (long long v = v0 + tid; v < v1; v += 2 * kT) {
+        const long long w = v + kT;
+        const bool two = w < v1;
+        uint4 ux[2], ud[2];
+        unsigned mk[2] = {0xFFu, 0xFFu};
+        ux[0] = ld_stream(x + v);
+        if (two) ux[1] = ld_stream(x + w);
+        if (MODE == 1) {
+            ud[0] = ld_stream(dy + v);
+            if (two) ud[1] = ld_stream(dy + w);
             if (y) {
-                const unsigned mk = y[v];   // bit i: ReLU passed channel i of this vector in the forward pass
-#pragma unroll
-                for (int i = 0; i < 8; ++i) g[i] = (mk >> i) & 1u ? g[i] : 0.f;
-            } else if (beta_rc) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) g[i] = fmaf(fx[i], sc[i], sh[i]) > 0.f ? g[i] : 0.f;
+                mk[0] = y[v];
+                if (two) mk[1] = y[w];
             }
+        }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { a0[i] += g[i]; a1[i] = fmaf(g[i], (fx[i] - mu[i]) * is[i], a1[i]); }
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) break;
+            float fx[8];
+            unpack8(ux[u], fx);
+            if (MODE == 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { a0[i] += fx[i]; a1[i] = fmaf(fx[i], fx[i], a1[i]); }
+            } else {
+                float g[8];
+                unpack8(ud[u], g);
+                if (y) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) g[i] = (mk[u] >> i) & 1u ? g[i] : 0.f;
+                } else if (beta_rc) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) g[i] = fmaf(fx[i], sc[i], sh[i]) > 0.f ? g[i] : 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { a0[i] += g[i]; a1[i] = fmaf(g[i], (fx[i] - mu[i]) * is[i], a1[i]); }
+            }
         }
     }
 #pragma unroll
@@ -140,27 +158,41 @@ __global__ void __launch_bounds__(kT) bn_apply_kernel(const uint4* __restrict__ 
         sc[i] = invstd[c] * gamma[c];
         sh[i] = beta[c] - mean[c] * sc[i];
     }
-    for (long long v = v0; v < nvec; v += stride) {
-        float f[8];
-        unpack8(ld_stream(x + v), f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], sc[i], sh[i]);
+    for (long long v = v0; v < nvec; v += 2 * stride) {
+        const long long w = v + stride;
+        const bool two = w < nvec;
+        uint4 ux[2], ur[2];
+        ux[0] = ld_stream(x + v);
+        if (two) ux[1] = ld_stream(x + w);
         if (res) {
-            float r[8];
-            unpack8(ld_stream(res + v), r);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] += r[i];
+            ur[0] = ld_stream(res + v);
+            if (two) ur[1] = ld_stream(res + w);
         }
-        if (relu) {
-            unsigned mk = 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                mk |= (f[i] > 0.f ? 1u : 0u) << i;
-                f[i] = fmaxf(f[i], 0.f);
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) break;
+            const long long vv = u ? w : v;
+            float f[8];
+            unpack8(ux[u], f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], sc[i], sh[i]);
+            if (res) {
+                float r[8];
+                unpack8(ur[u], r);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] += r[i];
             }
-            if (mask) mask[v] = (unsigned char)mk;
+            if (relu) {
+                unsigned mk = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    mk |= (f[i] > 0.f ? 1u : 0u) << i;
+                    f[i] = fmaxf(f[i], 0.f);
+                }
+                if (mask) mask[vv] = (unsigned char)mk;
+            }
+            y[vv] = pack8(f);
         }
-        y[v] = pack8(f);
     }
 }
 
@@ -185,23 +217,41 @@ __global__ void __launch_bounds__(kT) bn_bwd_apply_kernel(const uint4* __restric
         k2[i] = (float)(sums[C + c] / (double)R);
         sh[i] = beta_rc ? beta_rc[c] - mu[i] * k0[i] : 0.f;
     }
-    for (long long v = v0; v < nvec; v += stride) {
-        float g[8], fx[8];
-        unpack8(ld_stream(dy + v), g);
-        unpack8(ld_stream(x + v), fx);
-        if (y) {
-            const unsigned mk = y[v];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) g[i] = (mk >> i) & 1u ? g[i] : 0.f;
-        } else if (beta_rc) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) g[i] = fmaf(fx[i], k0[i], sh[i]) > 0.f ? g[i] : 0.f;
+    for (long long v = v0; v < nvec; v += 2 * stride) {
+        const long long w = v + stride;
+        const bool two = w < nvec;
+        uint4 ud[2], ux[2];
+        unsigned mk[2] = {0xFFu, 0xFFu};
+        ud[0] = ld_stream(dy + v);
+        ux[0] = ld_stream(x + v);
+        if (two) {
+            ud[1] = ld_stream(dy + w);
+            ux[1] = ld_stream(x + w);
         }
-        if (dres) dres[v] = pack8(g);
-        float o[8];
+        if (y) {
+            mk[0] = y[v];
+            if (two) mk[1] = y[w];
+        }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = k0[i] * (g[i] - k1[i] - (fx[i] - mu[i]) * is[i] * k2[i]);
-        dx[v] = pack8(o);
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) break;
+            const long long vv = u ? w : v;
+            float g[8], fx[8];
+            unpack8(ud[u], g);
+            unpack8(ux[u], fx);
+            if (y) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) g[i] = (mk[u] >> i) & 1u ? g[i] : 0.f;
+            } else if (beta_rc) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) g[i] = fmaf(fx[i], k0[i], sh[i]) > 0.f ? g[i] : 0.f;
+            }
+            if (dres) dres[vv] = pack8(g);
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = k0[i] * (g[i] - k1[i] - (fx[i] - mu[i]) * is[i] * k2[i]);
+            dx[vv] = pack8(o);
+        }
     }
 }
 

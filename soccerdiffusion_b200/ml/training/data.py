@@ -1,10 +1,11 @@
 """Host->device input pipeline of the training loop (reference: ml/training/train.py:193,
 ``batch = {k: v.to(device, non_blocking=True) ...}``).
 
-``DevicePrefetcher`` issues the pinned-host -> HBM copies of batch i+1 on a dedicated copy stream while the kernels of
-step i run on the compute stream (the reference's copy is on the compute stream and serialises with it: 1.5 GB of fp32
-images per step at bs=256).  Double-buffered; the compute stream waits on the copy's event before using a batch, and a
-buffer is recycled only after the step that consumed it has been enqueued.
+``DevicePrefetcher`` copies batch i+1 from pinned host memory into one of ``depth`` preallocated device buffer sets
+on a dedicated copy stream while the kernels of step i run on the compute stream (the reference's copy is on the
+compute stream and serialises with it: 1.5 GB of fp32 images per step at bs=256).  No allocation per batch; a
+buffer set is overwritten only after the step that consumed it has finished (event recorded on the compute stream
+when the next batch is requested).
 """
 from __future__ import annotations
 
@@ -13,12 +14,15 @@ import torch
 
 class DevicePrefetcher:
     def __init__(self, batches, device, depth: int = 2):
-        """``batches``: iterable of dicts of (ideally pinned) host tensors."""
+        """``batches``: iterable of dicts of (ideally pinned) host tensors, all of the same shapes."""
         self.it = iter(batches)
         self.device = device
         self.copy_stream = torch.cuda.Stream(device=device)
         self.depth = depth
-        self.queue = []
+        self.slots = []        # [dict of device tensors, ready_event, free_event]
+        self.queue = []        # indices of slots holding a copied batch, in order
+        self.next_slot = 0
+        self.in_use = None     # slot handed out by the previous __next__
         for _ in range(depth):
             self._enqueue()
 
@@ -27,22 +31,37 @@ class DevicePrefetcher:
             host = next(self.it)
         except StopIteration:
             return
+        if len(self.slots) < self.depth:
+            dev = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in host.items()}
+            self.slots.append([dev, torch.cuda.Event(), None])
+            i = len(self.slots) - 1
+        else:
+            i = self.next_slot
+        self.next_slot = (i + 1) % self.depth
+        dev, ready, free = self.slots[i]
         with torch.cuda.stream(self.copy_stream):
-            dev = {k: v.to(self.device, non_blocking=True) for k, v in host.items()}
-            ev = torch.cuda.Event()
-            ev.record(self.copy_stream)
-        self.queue.append((dev, ev))
+            if free is not None:
+                self.copy_stream.wait_event(free)      # the step that read this buffer set has finished
+            for k, v in host.items():
+                dev[k].copy_(v, non_blocking=True)
+            ready.record(self.copy_stream)
+        self.queue.append(i)
 
     def __iter__(self):
         return self
 
     def __next__(self):
+        cur = torch.cuda.current_stream(self.device)
+        if self.in_use is not None:
+            ev = torch.cuda.Event()
+            ev.record(cur)                              # everything enqueued so far (the previous step) reads in_use
+            self.slots[self.in_use][2] = ev
+            self.in_use = None
+            self._enqueue()
         if not self.queue:
             raise StopIteration
-        dev, ev = self.queue.pop(0)
-        cur = torch.cuda.current_stream(self.device)
-        cur.wait_event(ev)
-        for t in dev.values():
-            t.record_stream(cur)   # the caching allocator must not recycle these while the step uses them
-        self._enqueue()
+        i = self.queue.pop(0)
+        dev, ready, _ = self.slots[i]
+        cur.wait_event(ready)
+        self.in_use = i
         return dev

@@ -34,7 +34,7 @@ for _ in range(3):
 torch.cuda.synchronize()
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
 
-with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=True) as prof:
     train_step(model, opt, sch, norm, batch)
     torch.cuda.synchronize()
 ev = [e for e in prof.key_averages() if e.device_time_total > 0 and e.device_type.name == "CUDA"] if hasattr(prof.key_averages()[0], "device_type") else prof.key_averages()
@@ -46,3 +46,9 @@ for e in rows[: args.rows]:
     if t <= 0:
         break
     print(f"{t/1e3:9.3f} ms {100*t/tot:5.1f}% x{e.count:<5d} {e.key[:110]}")
+
+print("\n--- aten::copy_ / add_ / contiguous by input shape ---")
+rows2 = [e for e in prof.key_averages(group_by_input_shape=True) if e.key in ("aten::copy_", "aten::add_", "aten::contiguous", "aten::to", "aten::_to_copy", "aten::fill_", "aten::zero_", "aten::mul", "aten::clone")]
+rows2.sort(key=lambda e: -getattr(e, "self_device_time_total", 0))
+for e in rows2[:18]:
+    print(f"{getattr(e, 'self_device_time_total', 0)/1e3:9.3f} ms x{e.count:<4d} {e.key:18s} {str(e.input_shapes)[:110]}")
