@@ -145,7 +145,7 @@ def run_reference(args):
                 cpu_baseline=dict(value=val, unit=UNIT, cores=cores, kind="port",
                                   sample=f"{len(times)} full training steps at bs={bs} (oracle/model_ref.py + torch AdamW)"),
                 e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def _state_template(hp):
@@ -280,8 +280,8 @@ def run_ours(args):
     clk = clocks.stop() if rank == 0 else None
     if args.ncu_range:
         if rank == 0:
-            print(json.dumps(dict(note="ncu range run: numbers under a profiler are not bench values", steps=args.steps,
-                                  ms_per_step=ms / args.steps, gpu_launches=launches)), flush=True)
+            emit(dict(note="ncu range run: numbers under a profiler are not bench values", steps=args.steps,
+                      ms_per_step=ms / args.steps, gpu_launches=launches))
         return
 
     # ---- e2e: pinned host buffers -> device EVERY step (copy stream, overlapped with the previous step's kernels),
@@ -370,7 +370,7 @@ def run_ours(args):
                         precision_mode=args.precision),
             e2e=dict(value=gb * args.steps / (ms_e2e / 1e3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4),
             gpu_launches=launches, clocks=clk, roofline=roofline, kernel_classes=kernel_classes, cpu_baseline=cpu, ddim=ddim)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -450,7 +450,29 @@ def ddim_latency(model, hp, dev, precision, reps=200):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def _capture_stdout():
+    """Everything libraries print to fd 1 (e.g. NCCL's version banner) goes to stderr; the ONE JSON line is written
+    to the real stdout by emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    _capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

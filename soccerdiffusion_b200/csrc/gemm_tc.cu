@@ -18,6 +18,8 @@
 #include "tc_common.cuh"
 #include "../../include/sd_b200.h"
 
+#include <cstdlib>
+
 using namespace sd;
 using namespace sdtc;
 
@@ -122,12 +124,50 @@ __device__ __forceinline__ void stage_row_contig(uint8_t* tile, const float* __r
     }
 }
 
+// Stage a tile from a matrix whose MN index is contiguous in memory (src[k][mn]) WITHOUT transposing: MN-major
+// operand layout (64 MN elements = one 128-byte row per k, 128-byte swizzle).  16-byte global loads, 16-byte
+// conflict-free shared stores.  R = MN extent of the tile (multiple of 8), rows of k = TK.
+template <bool LN>
+__device__ __forceinline__ void stage_mn_major(uint8_t* tile, const float* __restrict__ src, long long ld, int mn0,
+                                               int mn_total, int R, int k0, int ke, bool vec, const TcParams& p) {
+    const int chunks = R >> 3;                     // 16-byte chunks per k row
+    for (int item = threadIdx.x; item < chunks * TK; item += NT) {
+        const int c = item % chunks, kr = item / chunks;
+        const int mn = mn0 + 8 * c, k = k0 + kr;
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = 0.f;
+        if (k < ke && mn < mn_total) {
+            const float* g = src + (long long)k * ld + mn;
+            if (vec && mn + 7 < mn_total) {
+                const float4 a = *reinterpret_cast<const float4*>(g);
+                const float4 b = *reinterpret_cast<const float4*>(g + 4);
+                f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (mn + j < mn_total) f[j] = g[j];
+            }
+            if (LN) {   // the k index is the normalised row, the MN index the feature
+                const float rs = p.ln_rstd[k];
+                const float nm = -p.ln_mean[k] * rs;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (mn + j < mn_total) f[j] = fmaf(fmaf(f[j], rs, nm), __ldg(p.ln_gamma + mn + j), __ldg(p.ln_beta + mn + j));
+            }
+        }
+        *reinterpret_cast<uint4*>(tile + sw128_mn_chunk_off(8 * c, kr, TK)) = pack8_bf16(f);
+    }
+}
+
 // epilogue feature mask (compile-time specialisations of the combinations the layer code uses; EPI_GENERIC keeps
 // every feature a run-time flag)
 constexpr int EPI_PRE = 1, EPI_GELU = 2, EPI_GG = 4, EPI_DROP = 8, EPI_PE = 16, EPI_RES = 32, EPI_ACC = 64;
 constexpr int EPI_GENERIC = -1;
 
-template <bool A_KM, bool B_KN, int EPI>
+// MNMAJ: operands whose MN index is contiguous in memory (A_KM / B_KN) are staged untransposed and described to
+// tcgen05 as MN-major; otherwise they are transposed by the staging threads into K-major tiles.
+template <bool A_KM, bool B_KN, int EPI, bool MNMAJ>
 __global__ void __launch_bounds__(NT) gemm_tc_kernel(const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_stage[STAGES];
@@ -136,7 +176,7 @@ __global__ void __launch_bounds__(NT) gemm_tc_kernel(const TcParams p) {
 
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int BN = p.BN;
-    const int stage_bytes = A_STAGE_BYTES + BN * TK * 2;
+    const int stage_bytes = A_STAGE_BYTES + ((BN + 63) & ~63) * TK * 2;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -155,7 +195,9 @@ __global__ void __launch_bounds__(NT) gemm_tc_kernel(const TcParams p) {
     const int kb = blockIdx.z * p.k_per_slice;
     const int ke = min(p.K, kb + p.k_per_slice);
     const int nchunks = (ke - kb + TK - 1) / TK;
-    const uint32_t idesc = instr_desc_bf16(TM, BN);
+    constexpr bool A_MN = A_KM && MNMAJ, B_MN = B_KN && MNMAJ;
+    const uint32_t idesc = instr_desc_bf16(TM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    const int BNr = (BN + 63) & ~63;   // MN-major B tiles are laid out in 64-wide blocks
 
     for (int ci = 0; ci < nchunks; ++ci) {
         const int s = ci % STAGES;
@@ -163,13 +205,18 @@ __global__ void __launch_bounds__(NT) gemm_tc_kernel(const TcParams p) {
         const int k0 = kb + ci * TK;
         uint8_t* As = smem + s * stage_bytes;
         uint8_t* Bs = As + A_STAGE_BYTES;
-        if (A_KM) {
+        if (A_MN) {
+            stage_mn_major<false>(As, p.A, p.lda, m0, p.M, TM, k0, ke, p.vecA, p);
+        } else if (A_KM) {
             stage_row_contig<false>(As, p.A, p.lda, m0, p.M, TM, k0, ke, p);
         } else {
             if (p.ln_on_a) stage_k_contig<true>(As, p.A, p.lda, m0, p.M, TM, k0, ke, p.vecA, p);
             else stage_k_contig<false>(As, p.A, p.lda, m0, p.M, TM, k0, ke, p.vecA, p);
         }
-        if (B_KN) {
+        if (B_MN) {
+            if (p.ln_on_b) stage_mn_major<true>(Bs, p.B, p.ldb, n0, p.N, BNr, k0, ke, p.vecB, p);
+            else stage_mn_major<false>(Bs, p.B, p.ldb, n0, p.N, BNr, k0, ke, p.vecB, p);
+        } else if (B_KN) {
             if (p.ln_on_b) stage_row_contig<true>(Bs, p.B, p.ldb, n0, p.N, BN, k0, ke, p);
             else stage_row_contig<false>(Bs, p.B, p.ldb, n0, p.N, BN, k0, ke, p);
         } else {
@@ -179,11 +226,13 @@ __global__ void __launch_bounds__(NT) gemm_tc_kernel(const TcParams p) {
         __syncthreads();
         if (tid == 0) {
             tc_fence_after_sync();
-            const uint64_t da = smem_desc_k_sw128(smem_u32(As));
-            const uint64_t db = smem_desc_k_sw128(smem_u32(Bs));
+            // K-major: +32 bytes of K per step inside the swizzle atom; MN-major: +2 atoms of 8 k-rows (2048 bytes)
+            const uint64_t da = A_MN ? smem_desc_mn_sw128(smem_u32(As), TK * 128, 1024) : smem_desc_k_sw128(smem_u32(As));
+            const uint64_t db = B_MN ? smem_desc_mn_sw128(smem_u32(Bs), TK * 128, 1024) : smem_desc_k_sw128(smem_u32(Bs));
+            const uint64_t sa = A_MN ? 128 : 2, sb = B_MN ? 128 : 2;
             const int ksteps = (min(TK, ke - k0) + 15) / 16;
-            for (int j = 0; j < ksteps; ++j)   // +32 bytes (2 x 16 B) of K per step inside the swizzle atom
-                mma_bf16_ss(tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, (ci > 0 || j > 0) ? 1u : 0u);
+            for (int j = 0; j < ksteps; ++j)
+                mma_bf16_ss(tmem, da + sa * (uint64_t)j, db + sb * (uint64_t)j, idesc, (ci > 0 || j > 0) ? 1u : 0u);
             mma_commit(&bar_stage[s]);
             if (ci == nchunks - 1) mma_commit(&bar_done);
         }
@@ -257,9 +306,9 @@ __global__ void __launch_bounds__(NT) gemm_tc_kernel(const TcParams p) {
 
 inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
-template <bool A_KM, bool B_KN, int EPI>
-int launch(dim3 grid, size_t smem, cudaStream_t st, const TcParams& p) {
-    auto kernel = gemm_tc_kernel<A_KM, B_KN, EPI>;
+template <bool A_KM, bool B_KN, int EPI, bool MNMAJ>
+int launch_impl(dim3 grid, size_t smem, cudaStream_t st, const TcParams& p) {
+    auto kernel = gemm_tc_kernel<A_KM, B_KN, EPI, MNMAJ>;
     static bool configured = false;   // one flag per instantiation
     if (!configured) {
         SD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -269,6 +318,21 @@ int launch(dim3 grid, size_t smem, cudaStream_t st, const TcParams& p) {
     kernel<<<grid, NT, smem, st>>>(p);
     SD_LAUNCH_CHECK();
     return SD_OK;
+}
+
+bool use_mn_major() {   // SD_B200_TC_MNMAJOR=0 selects the transposing K-major staging for A_KM / B_KN operands
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SD_B200_TC_MNMAJOR");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+template <bool A_KM, bool B_KN, int EPI>
+int launch(dim3 grid, size_t smem, cudaStream_t st, const TcParams& p) {
+    if ((A_KM || B_KN) && use_mn_major()) return launch_impl<A_KM, B_KN, EPI, true>(grid, smem, st, p);
+    return launch_impl<A_KM, B_KN, EPI, false>(grid, smem, st, p);
 }
 
 int epilogue_mask(const TcParams& p) {
@@ -320,7 +384,7 @@ int sd_gemm_tc_dispatch(const sd_gemm_desc* d, void* stream) {
     if (slices > 1 && !d->accumulate)
         SD_CUDA(cudaMemset2DAsync(d->C, d->ldc * sizeof(float), 0, (size_t)d->N * sizeof(float), d->M, st));
     dim3 grid(ntn, ntm, slices);
-    const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + p.BN * TK * 2) + 1024;
+    const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + ((p.BN + 63) & ~63) * TK * 2) + 1024;
     const int em = slices > 1 ? 0 : epilogue_mask(p);
     if (d->a_layout == SD_LAYOUT_MK && d->b_layout == SD_LAYOUT_NK) {
         switch (em) {

@@ -91,12 +91,30 @@ __device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                            // layout type: SWIZZLE_128B
     return d;
 }
-// instruction descriptor, kind::f16: bf16 x bf16 -> fp32, both operands K-major, M x N tile
-__host__ __device__ __forceinline__ constexpr uint32_t instr_desc_bf16(int M, int N) {
+// shared-memory matrix descriptor: MN-major, SWIZZLE_128B.  Canonical layout (bf16):
+//   element (mn, k) at  (mn / 64) * LBO + (k / 8) * SBO + (k % 8) * 128 + (mn % 64) * 2   bytes, then Swizzle<3,4,3>
+// i.e. 64 consecutive MN elements are contiguous (one 128-byte row per k), 8 k-rows form a 1024-byte atom.
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;  // between 64-wide MN blocks
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;  // between 8-row k groups
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor, kind::f16: bf16 x bf16 -> fp32, M x N tile; operand majorness: 0 = K-major, 1 = MN-major
+__host__ __device__ __forceinline__ constexpr uint32_t instr_desc_bf16(int M, int N, int a_mn = 0, int b_mn = 0) {
     return (1u << 4)                       // D format: F32
            | (1u << 7) | (1u << 10)        // A, B format: BF16
+           | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16)
            | ((uint32_t)(N >> 3) << 17)    // N / 8
            | ((uint32_t)(M >> 4) << 24);   // M / 16
+}
+// byte offset of the 16-byte chunk holding mn..mn+7 (mn % 8 == 0) of k-row k inside an MN-major SW128 tile of
+// `krows` k rows per 64-wide MN block
+__device__ __forceinline__ uint32_t sw128_mn_chunk_off(int mn, int k, int krows) {
+    return (uint32_t)((mn >> 6) * (krows * 128) + (k >> 3) * 1024 + (k & 7) * 128 + ((((mn & 63) >> 3) ^ (k & 7)) << 4));
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
