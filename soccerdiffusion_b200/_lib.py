@@ -101,6 +101,7 @@ SIGNATURES = {
     "sd_plan_denoise": [C.c_void_p, c_f, c_f, c_i, c_f, c_f],
     "sd_plan_set_sampler": [C.c_void_p, c_i],
     "sd_plan_last_sampler": [C.c_void_p],
+    "sd_plan_set_debug_stamps": [C.c_void_p, c_f],
 }
 
 _lib = None

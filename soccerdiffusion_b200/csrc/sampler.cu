@@ -71,6 +71,7 @@ struct SamplerArgs {
     float* x_out;         // (B,T,J) final sample (tok_mode 0)
     float* eps_out;       // tok_mode 1: (B,T,J);  tok_mode 0: optional trace (S,B,T,J)
     int denorm;
+    long long* dbg;       // optional: clock64() stamps of the cluster kernel's phases (CTA 0, thread 0), 64 per step
 };
 
 // ------------------------------------------------------------------------------------------
@@ -481,6 +482,12 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
     cluster.sync();
 
     int ph = 0;   // activation ping-pong phase
+    int dbg_i = 0;
+#define SD_STAMP()                                                                     \
+    do {                                                                               \
+        if (a.dbg && blockIdx.x == 0 && tid == 0 && dbg_i < 64) a.dbg[s * 64 + dbg_i] = clock64(); \
+        ++dbg_i;                                                                       \
+    } while (0)
     // weight slice accessor: resident layers read smem [j][k]; others read the K-major blob in global memory
     auto wslice = [&](int l, int g, const float* gsrc, int N, const float*& base, int& sj, int& sk) {
         if (l < L_res) {
@@ -498,6 +505,8 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
     };
 
     for (int s = 0; s < a.num_steps; ++s) {
+        dbg_i = 0;
+        SD_STAMP();   // 0: step start
         // ---- embedding + positional encoding (redundant in every CTA) ------------------------------
         for (int i = tid; i < T * d; i += blockDim.x) {
             const int t = i / d, n = i % d;
@@ -511,7 +520,9 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
             const LayerPtrs& P = a.layers[l];
             const float* wb; int sj, sk;
             // ---- self-attention ---------------------------------------------------------------------
+            SD_STAMP();   // layer start
             cta_layernorm_T<TR>(h, d, T, P.ln1_g, P.ln1_b, xT);
+            SD_STAMP();   // after LN1
             {
                 float* dst = act[ph & 1];
                 if (l < L_res) {
@@ -529,7 +540,9 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
                                        });
                 }
             }
+            SD_STAMP();   // after qkv gemm+push
             cluster.sync();
+            SD_STAMP();   // after sync
             {
                 const float* qkv = act[ph & 1];   // [3d][TR]
                 ++ph;
@@ -557,6 +570,7 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
                 }
                 __syncthreads();
             }
+            SD_STAMP();   // after self-attention core
             {
                 float* dst = act[ph & 1];
                 wslice(l, 1, P.sa_wo_t, d, wb, sj, sk);
@@ -573,6 +587,7 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
                 __syncthreads();
             }
             // ---- cross-attention --------------------------------------------------------------------
+            SD_STAMP();   // after sa out-proj + sync + residual
             cta_layernorm_T<TR>(h, d, T, P.ln2_g, P.ln2_b, xT);
             {
                 float* dst = act[ph & 1];
@@ -583,6 +598,7 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
                 });
             }
             cluster.sync();
+            SD_STAMP();   // after LN2 + q gemm + sync
             {
                 const float* q = act[ph & 1];   // [d][TR], pre-scaled
                 ++ph;
@@ -616,6 +632,7 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
                     for (int t = 0; t < TR; ++t) red[(g * TR + t) * Mq + mi] = acc[t];
                 }
                 __syncthreads();
+                SD_STAMP();   // after score partials
                 for (int idx = tid; idx < T * nk; idx += blockDim.x) {
                     const int t = idx / nk, mi = idx % nk;
                     float v = 0.f;
@@ -642,6 +659,7 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
                     }
                 }
                 __syncthreads();
+                SD_STAMP();   // after softmax partial
                 // partial P.V : thread = (c, key group)
                 const int groups2 = max(1, kClThreads / dh);
                 {
@@ -670,7 +688,9 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
                     for (int p = 0; p < C; ++p) cluster.map_shared_rank(cab, p)[rank * RS + 2 * TR + t * dh + c] = v;
                 }
             }
+            SD_STAMP();   // after PV + push
             cluster.sync();
+            SD_STAMP();   // after sync
             // combine the partials of all key parts -> O (every CTA, redundantly), transposed into xT
             for (int i = tid; i < T * d; i += blockDim.x) {
                 const int t = i / d, n = i % d;
@@ -704,6 +724,7 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
                 __syncthreads();
             }
             // ---- feed-forward -----------------------------------------------------------------------
+            SD_STAMP();   // after combine + ca out-proj + sync + residual
             cta_layernorm_T<TR>(h, d, T, P.ln3_g, P.ln3_b, xT);
             {
                 float* dst = act[ph & 1];
@@ -733,6 +754,7 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
             }
         }
 
+        SD_STAMP();   // after all layers
         // ---- output projection + DDIM update (redundant) --------------------------------------------
         for (int i = tid; i < T * J; i += blockDim.x) {
             const int t = i / J, j = i % J;
@@ -751,7 +773,9 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
             xs[o] = sap * x0 + sbp * e;
         }
         __syncthreads();
+        SD_STAMP();   // step end
     }
+#undef SD_STAMP
     if (rank == 0) {
         for (int i = tid; i < T * J; i += blockDim.x) {
             float v = xs[(i / J) * Jp + (i % J)];
@@ -818,6 +842,7 @@ struct sd_plan {
     bool layers_dirty = true;
     int sampler_mode = 0;   // 0 auto, 1 one CTA per trajectory, 2 one 16-CTA cluster per trajectory
     int last_sampler = 0;   // which kernel the last sd_plan_sample launched (1 / 2)
+    long long* dbg = nullptr;   // optional phase-timestamp buffer (device), num_steps * 64 entries
 };
 
 namespace {
@@ -1128,6 +1153,7 @@ extern "C" int sd_plan_sample(sd_plan* p, const float* x_T, float* x_out, float*
     fill_args(p, a);
     a.tok_mode = 0; a.t_ptr = nullptr; a.t_is_float = 0;
     a.x_in = x_T; a.x_out = x_out; a.eps_out = eps_trace; a.denorm = denormalize;
+    a.dbg = p->dbg;
     return run_sampler(p, a, (cudaStream_t)stream);
 }
 
@@ -1135,6 +1161,12 @@ extern "C" int sd_plan_set_sampler(sd_plan* p, int mode) {
     if (!p) return SD_ERR_NO_PLAN;
     if (mode < 0 || mode > 2) return SD_ERR_BAD_ARG;
     p->sampler_mode = mode;
+    return SD_OK;
+}
+
+extern "C" int sd_plan_set_debug_stamps(sd_plan* p, long long* device_buffer) {
+    if (!p) return SD_ERR_NO_PLAN;
+    p->dbg = device_buffer;
     return SD_OK;
 }
 
