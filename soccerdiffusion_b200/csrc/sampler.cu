@@ -356,12 +356,16 @@ constexpr int kClusterSize = 16;
 constexpr int kClThreads = 256;
 
 struct ClusterLayout {   // offsets in floats inside dynamic shared memory
-    int w, act0, act1, h, xT, xs, eps, cab, sc, red, total;
+    int w, prm, act0, act1, h, xT, xs, eps, cab, sc, red, total;
 };
 
 __host__ __device__ inline int align4(int x) { return (x + 3) & ~3; }
+__host__ __device__ inline int imax(int a, int b) { return a > b ? a : b; }
 
-__host__ __device__ inline ClusterLayout cluster_layout(int d, int L_res, int TR, int J, int H, int M) {
+// per layer: LayerNorm gamma/beta (6 d) + this CTA's bias slices (qkv 3*d/C, five projections d/C each)
+__host__ __device__ inline int cluster_param_floats(int d) { return 6 * d + 8 * (d / kClusterSize); }
+
+__host__ __device__ inline ClusterLayout cluster_layout(int d, int L, int L_res, int TR, int J, int H, int M, int T) {
     const int C = kClusterSize;
     const int dh = d / H;
     const int parts = C / H;
@@ -374,14 +378,15 @@ __host__ __device__ inline ClusterLayout cluster_layout(int d, int L_res, int TR
     ClusterLayout o;
     int cur = 0;
     o.w = cur;    cur += align4(L_res * 8 * (d / C) * d);        // (3 + 5) slices of d/C columns each
-    o.act0 = cur; cur += align4(3 * d * TR);
-    o.act1 = cur; cur += align4(3 * d * TR);
+    o.prm = cur;  cur += align4(L * cluster_param_floats(d));
+    o.act0 = cur; cur += align4(3 * d * TR);                     // gathered q|k|v, q (cross), ffn hidden
+    o.act1 = cur; cur += align4(d * TR);                         // gathered residual deltas
     o.h = cur;    cur += align4(TR * d);
     o.xT = cur;   cur += align4(d * TR);
     o.xs = cur;   cur += align4(TR * Jp);
     o.eps = cur;  cur += align4(TR * Jp);
     o.cab = cur;  cur += align4(C * (2 * TR + TR * dh));
-    o.sc = cur;   cur += align4(TR * (Mq + 1));
+    o.sc = cur;   cur += align4(imax(TR * (Mq + 1), H * T * T));
     const int red1 = G * TR * Mq, red2 = groups2 * TR * dh;
     o.red = cur;  cur += align4(red1 > red2 ? red1 : red2);
     o.total = cur;
@@ -389,7 +394,8 @@ __host__ __device__ inline ClusterLayout cluster_layout(int d, int L_res, int TR
 }
 
 // out[t][j] for the CTA's column slice: W(j,k) = Wb[j*sj + k*sk]; xT [K][TR].  Warp per column, lanes over k,
-// butterfly reduction; afterwards lane (t + 16*half) holds out[t][j] and pushes it to half of the peers.
+// butterfly reduction: afterwards EVERY lane holds the whole column out[0..TR)[j]; epi(j, column) runs on all lanes
+// (lane p pushes the column to peer p with 16-byte distributed-shared-memory stores).
 template <int TR, class Epi>
 __device__ __forceinline__ void slice_gemm(const float* Wb, int sj, int sk, int ncols, int K, const float* xT, Epi epi) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -410,14 +416,31 @@ __device__ __forceinline__ void slice_gemm(const float* Wb, int sj, int sk, int 
                 acc[4 * q + 3] = fmaf(w, x4.w, acc[4 * q + 3]);
             }
         }
-        float v = 0.f;
 #pragma unroll
-        for (int t = 0; t < TR; ++t) {
-            const float sum = warp_sum(acc[t]);
-            if ((lane & 15) == t) v = sum;
-        }
-        epi(j, lane & 15, lane >> 4, v);
+        for (int t = 0; t < TR; ++t) acc[t] = warp_sum(acc[t]);
+        epi(j, acc);
     }
+}
+
+// LayerNorm of the T rows of h -> xT[c][t]; gamma/beta in SHARED memory (plain loads)
+template <int TR>
+__device__ __forceinline__ void cta_layernorm_T_sm(const float* h, int d, int T, const float* gamma, const float* beta,
+                                                   float* xT) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int t = w; t < T; t += nw) {
+        const float* r = h + t * d;
+        float s = 0.f;
+        for (int c = lane; c < d; c += 32) s += r[c];
+        const float mu = warp_sum(s) / (float)d;
+        float q = 0.f;
+        for (int c = lane; c < d; c += 32) {
+            const float dl = r[c] - mu;
+            q = fmaf(dl, dl, q);
+        }
+        const float rs = rsqrtf(warp_sum(q) / (float)d + 1e-5f);
+        for (int c = lane; c < d; c += 32) xT[c * TR + t] = (r[c] - mu) * rs * gamma[c] + beta[c];
+    }
+    __syncthreads();
 }
 
 template <int TR>
@@ -430,8 +453,9 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
     const int d = a.d, T = a.T, J = a.J, H = a.heads, dh = a.dh, M = a.M, Mpad = a.Mpad, L = a.L;
     const int nd = d / C, nq = 3 * nd;
     const int Jp = (J + 3) & ~3;
-    const ClusterLayout lo = cluster_layout(d, L_res, TR, J, H, M);
+    const ClusterLayout lo = cluster_layout(d, L, L_res, TR, J, H, M, T);
     float* Wres = smem + lo.w;
+    float* prm = smem + lo.prm;
     float* act[2] = {smem + lo.act0, smem + lo.act1};
     float* h = smem + lo.h;
     float* xT = smem + lo.xT;
@@ -448,65 +472,69 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
     const int m_lo = min(M, kp * Mq), m_hi = min(M, (kp + 1) * Mq), nk = m_hi - m_lo;
     const int RS = 2 * TR + TR * dh;   // cross-attention partial record: max[TR] | sum[TR] | O[T][dh]
     const int per_layer = 8 * nd * d;
+    const int PS = cluster_param_floats(d);
 
-    // ---- one-time: weight slices -> shared memory (k contiguous per output column) -----------------
+    // ---- one-time: weight slices (k contiguous per output column) and small parameters -> shared memory ----
     for (int l = 0; l < L_res; ++l) {
         const LayerPtrs& P = a.layers[l];
         float* wl = Wres + l * per_layer;
         const float* srcs[6] = {P.sa_wqkv_t, P.sa_wo_t, P.ca_wq_t, P.ca_wo_t, P.w1_t, P.w2_t};
-        const int ncs[6] = {nq, nd, nd, nd, nd, nd};
-        const int Ns[6] = {3 * d, d, d, d, d, d};
         int off = 0;
         for (int g = 0; g < 6; ++g) {
-            const int nc = ncs[g], N = Ns[g];
-            if (g == 0) {
-                // q, k, v column blocks: slice j covers columns {part*d + rank*nd + jj}
-                for (int i = tid; i < nc * d; i += blockDim.x) {
-                    const int k = i / nc, j = i % nc;
-                    const int col = (j / nd) * d + rank * nd + (j % nd);
-                    wl[off + j * d + k] = __ldg(srcs[g] + (long long)k * N + col);
-                }
-            } else {
-                for (int i = tid; i < nc * d; i += blockDim.x) {
-                    const int k = i / nc, j = i % nc;
-                    wl[off + j * d + k] = __ldg(srcs[g] + (long long)k * N + rank * nd + j);
-                }
+            const int nc = g == 0 ? nq : nd, N = g == 0 ? 3 * d : d;
+            for (int i = tid; i < nc * d; i += blockDim.x) {
+                const int k = i / nc, j = i % nc;
+                const int col = g == 0 ? (j / nd) * d + rank * nd + (j % nd) : rank * nd + j;
+                wl[off + j * d + k] = __ldg(srcs[g] + (long long)k * N + col);
             }
             off += nc * d;
         }
     }
+    for (int l = 0; l < L; ++l) {
+        const LayerPtrs& P = a.layers[l];
+        float* pl = prm + l * PS;
+        const float* lnp[6] = {P.ln1_g, P.ln1_b, P.ln2_g, P.ln2_b, P.ln3_g, P.ln3_b};
+        for (int i = tid; i < 6 * d; i += blockDim.x) pl[i] = __ldg(lnp[i / d] + (i % d));
+        float* bl = pl + 6 * d;
+        for (int j = tid; j < nq; j += blockDim.x) bl[j] = __ldg(P.sa_bqkv + (j / nd) * d + rank * nd + (j % nd));
+        const float* bs[5] = {P.sa_bo, P.ca_bq, P.ca_bo, P.b1, P.b2};
+        for (int i = tid; i < 5 * nd; i += blockDim.x) bl[nq + i] = __ldg(bs[i / nd] + rank * nd + (i % nd));
+    }
     for (int i = tid; i < T * J; i += blockDim.x) xs[(i / J) * Jp + (i % J)] = a.x_in[(long long)b * T * J + i];
-    for (int i = tid; i < d * TR; i += blockDim.x) xT[i] = 0.f;
-    for (int i = tid; i < 3 * d * TR; i += blockDim.x) { act[0][i] = 0.f; act[1][i] = 0.f; }
+    for (int i = tid; i < d * TR; i += blockDim.x) { xT[i] = 0.f; act[1][i] = 0.f; }
+    for (int i = tid; i < 3 * d * TR; i += blockDim.x) act[0][i] = 0.f;
     __syncthreads();
     cluster.sync();
 
-    int ph = 0;   // activation ping-pong phase
     int dbg_i = 0;
 #define SD_STAMP()                                                                     \
     do {                                                                               \
         if (a.dbg && blockIdx.x == 0 && tid == 0 && dbg_i < 64) a.dbg[s * 64 + dbg_i] = clock64(); \
         ++dbg_i;                                                                       \
     } while (0)
+
     // weight slice accessor: resident layers read smem [j][k]; others read the K-major blob in global memory
     auto wslice = [&](int l, int g, const float* gsrc, int N, const float*& base, int& sj, int& sk) {
         if (l < L_res) {
             base = Wres + l * per_layer + (g == 0 ? 0 : nq * d + (g - 1) * nd * d);
             sj = d; sk = 1;
         } else {
-            base = gsrc + rank * nd;   // g==0 handled by the caller (three column blocks)
+            base = gsrc + rank * nd;
             sj = 1; sk = N;
         }
     };
-    // push one value to half of the peers' buffer `buf` at offset `o`
-    auto push = [&](float* buf, int o, int half, float v) {
+    // lane p (< C) writes one whole column (TR floats, 16-byte stores) into peer p's buffer
+    auto push_col = [&](float* buf, int col, const float* v) {
+        if (lane < C) {
+            float4* dst = reinterpret_cast<float4*>(cluster.map_shared_rank(buf, lane) + col * TR);
 #pragma unroll
-        for (int p = 0; p < C / 2; ++p) cluster.map_shared_rank(buf, half * (C / 2) + p)[o] = v;
+            for (int q = 0; q < TR / 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
     };
 
     for (int s = 0; s < a.num_steps; ++s) {
         dbg_i = 0;
-        SD_STAMP();   // 0: step start
+        SD_STAMP();   // step start
         // ---- embedding + positional encoding (redundant in every CTA) ------------------------------
         for (int i = tid; i < T * d; i += blockDim.x) {
             const int t = i / d, n = i % d;
@@ -518,90 +546,95 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
 
         for (int l = 0; l < L; ++l) {
             const LayerPtrs& P = a.layers[l];
+            const float* pl = prm + l * PS;            // ln1_g ln1_b ln2_g ln2_b ln3_g ln3_b | bias slices
+            const float* bl = pl + 6 * d;              // bqkv[nq] bo_sa bq_ca bo_ca b1 b2 (nd each)
             const float* wb; int sj, sk;
-            // ---- self-attention ---------------------------------------------------------------------
             SD_STAMP();   // layer start
-            cta_layernorm_T<TR>(h, d, T, P.ln1_g, P.ln1_b, xT);
+            // ---- self-attention ---------------------------------------------------------------------
+            cta_layernorm_T_sm<TR>(h, d, T, pl, pl + d, xT);
             SD_STAMP();   // after LN1
-            {
-                float* dst = act[ph & 1];
-                if (l < L_res) {
-                    wslice(l, 0, nullptr, 0, wb, sj, sk);
-                    slice_gemm<TR>(wb, sj, sk, nq, d, xT, [&](int j, int t, int half, float v) {
-                        const int col = (j / nd) * d + rank * nd + (j % nd);
-                        if (t < T) push(dst, col * TR + t, half, v + __ldg(P.sa_bqkv + col));
+            if (l < L_res) {
+                wslice(l, 0, nullptr, 0, wb, sj, sk);
+                slice_gemm<TR>(wb, sj, sk, nq, d, xT, [&](int j, float* v) {
+                    const float bias = bl[j];
+#pragma unroll
+                    for (int t = 0; t < TR; ++t) v[t] += bias;
+                    push_col(act[0], (j / nd) * d + rank * nd + (j % nd), v);
+                });
+            } else {
+                for (int part = 0; part < 3; ++part)
+                    slice_gemm<TR>(P.sa_wqkv_t + part * d + rank * nd, 1, 3 * d, nd, d, xT, [&](int j, float* v) {
+                        const float bias = bl[part * nd + j];
+#pragma unroll
+                        for (int t = 0; t < TR; ++t) v[t] += bias;
+                        push_col(act[0], part * d + rank * nd + j, v);
                     });
-                } else {
-                    for (int part = 0; part < 3; ++part)
-                        slice_gemm<TR>(P.sa_wqkv_t + part * d + rank * nd, 1, 3 * d, nd, d, xT,
-                                       [&](int j, int t, int half, float v) {
-                                           const int col = part * d + rank * nd + j;
-                                           if (t < T) push(dst, col * TR + t, half, v + __ldg(P.sa_bqkv + col));
-                                       });
-                }
             }
             SD_STAMP();   // after qkv gemm+push
             cluster.sync();
             SD_STAMP();   // after sync
             {
-                const float* qkv = act[ph & 1];   // [3d][TR]
-                ++ph;
-                for (int pair = warp; pair < H * T; pair += nwarps) {
-                    const int hh = pair / T, t = pair % T;
-                    float scv = -INFINITY;
-                    if (lane < T) {
-                        float acc = 0.f;
-                        for (int c = 0; c < dh; ++c)
-                            acc = fmaf(qkv[(hh * dh + c) * TR + t], qkv[(d + hh * dh + c) * TR + lane], acc);
-                        scv = acc * scale;
+                const float* qkv = act[0];   // [3d][TR]
+                // scores: one thread per (head, query, key)
+                for (int idx = tid; idx < H * T * T; idx += blockDim.x) {
+                    const int m = idx % T, t = (idx / T) % T, hh = idx / (T * T);
+                    const float* qp = qkv + (hh * dh) * TR + t;
+                    const float* kq = qkv + (d + hh * dh) * TR + m;
+                    float acc = 0.f;
+#pragma unroll 8
+                    for (int c = 0; c < dh; ++c) acc = fmaf(qp[c * TR], kq[c * TR], acc);
+                    sc[idx] = acc * scale;
+                }
+                __syncthreads();
+                for (int row = tid; row < H * T; row += blockDim.x) {
+                    float* pr = sc + row * T;
+                    float mx = -INFINITY;
+                    for (int m = 0; m < T; ++m) mx = fmaxf(mx, pr[m]);
+                    float sum = 0.f;
+                    for (int m = 0; m < T; ++m) {
+                        const float e = expf(pr[m] - mx);
+                        pr[m] = e;
+                        sum += e;
                     }
-                    const float mx = warp_max(scv);
-                    const float e = lane < T ? expf(scv - mx) : 0.f;
-                    const float p = e / warp_sum(e);
-                    for (int c0 = 0; c0 < dh; c0 += 32) {
-                        const int c = c0 + lane;
-                        float o = 0.f;
-                        for (int m = 0; m < T; ++m) {
-                            const float pm = __shfl_sync(0xffffffffu, p, m);
-                            if (c < dh) o = fmaf(pm, qkv[(2 * d + hh * dh + c) * TR + m], o);
-                        }
-                        if (c < dh) xT[(hh * dh + c) * TR + t] = o;
-                    }
+                    const float inv = 1.0f / sum;
+                    for (int m = 0; m < T; ++m) pr[m] *= inv;
+                }
+                __syncthreads();
+                for (int idx = tid; idx < T * d; idx += blockDim.x) {
+                    const int t = idx % T, n = idx / T;
+                    const float* pr = sc + ((n / dh) * T + t) * T;
+                    const float* vp = qkv + (2 * d + n) * TR;
+                    float o = 0.f;
+                    for (int m = 0; m < T; ++m) o = fmaf(pr[m], vp[m], o);
+                    xT[n * TR + t] = o;
                 }
                 __syncthreads();
             }
             SD_STAMP();   // after self-attention core
-            {
-                float* dst = act[ph & 1];
-                wslice(l, 1, P.sa_wo_t, d, wb, sj, sk);
-                slice_gemm<TR>(wb, sj, sk, nd, d, xT, [&](int j, int t, int half, float v) {
-                    const int col = rank * nd + j;
-                    if (t < T) push(dst, col * TR + t, half, v + __ldg(P.sa_bo + col));
-                });
-            }
+            wslice(l, 1, P.sa_wo_t, d, wb, sj, sk);
+            slice_gemm<TR>(wb, sj, sk, nd, d, xT, [&](int j, float* v) {
+                const float bias = bl[nq + j];
+#pragma unroll
+                for (int t = 0; t < TR; ++t) v[t] += bias;
+                push_col(act[1], rank * nd + j, v);
+            });
             cluster.sync();
-            {
-                const float* dl = act[ph & 1];
-                ++ph;
-                for (int i = tid; i < T * d; i += blockDim.x) h[i] += dl[(i % d) * TR + (i / d)];
-                __syncthreads();
-            }
+            for (int i = tid; i < T * d; i += blockDim.x) h[i] += act[1][(i % d) * TR + (i / d)];
+            __syncthreads();
             // ---- cross-attention --------------------------------------------------------------------
             SD_STAMP();   // after sa out-proj + sync + residual
-            cta_layernorm_T<TR>(h, d, T, P.ln2_g, P.ln2_b, xT);
-            {
-                float* dst = act[ph & 1];
-                wslice(l, 2, P.ca_wq_t, d, wb, sj, sk);
-                slice_gemm<TR>(wb, sj, sk, nd, d, xT, [&](int j, int t, int half, float v) {
-                    const int col = rank * nd + j;
-                    if (t < T) push(dst, col * TR + t, half, (v + __ldg(P.ca_bq + col)) * scale);
-                });
-            }
+            cta_layernorm_T_sm<TR>(h, d, T, pl + 2 * d, pl + 3 * d, xT);
+            wslice(l, 2, P.ca_wq_t, d, wb, sj, sk);
+            slice_gemm<TR>(wb, sj, sk, nd, d, xT, [&](int j, float* v) {
+                const float bias = bl[nq + nd + j];
+#pragma unroll
+                for (int t = 0; t < TR; ++t) v[t] = (v[t] + bias) * scale;
+                push_col(act[0], rank * nd + j, v);
+            });
             cluster.sync();
             SD_STAMP();   // after LN2 + q gemm + sync
             {
-                const float* q = act[ph & 1];   // [d][TR], pre-scaled
-                ++ph;
+                const float* q = act[0];   // [d][TR], pre-scaled
                 const float* Kt = a.Kt + ((long long)l * a.B + b) * (long long)H * dh * Mpad + (long long)hc * dh * Mpad;
                 const float* Vc = a.Vc + ((long long)l * a.B + b) * (long long)Mpad * d + hc * dh;
                 const float* tk = a.tok_kv + ((long long)s * L + l) * 2 * d;
@@ -680,12 +713,20 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
                     }
                 }
                 __syncthreads();
-                for (int idx = tid; idx < T * dh; idx += blockDim.x) {
-                    const int t = idx / dh, c = idx % dh;
-                    float v = 0.f;
-                    for (int g = 0; g < groups2; ++g) v += red[(g * TR + t) * dh + c];
+                // reduce over key groups, 4 channels per item, 16-byte pushes; item = (t, c4, peer quarter)
+                const int dh4 = dh >> 2;
+                for (int it = tid; it < T * dh4 * 4; it += blockDim.x) {
+                    const int pq = it & 3, idx = it >> 2;
+                    const int t = idx / dh4, c4 = idx % dh4;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int g = 0; g < groups2; ++g) {
+                        const float4 r4 = *reinterpret_cast<const float4*>(red + (g * TR + t) * dh + 4 * c4);
+                        v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+                    }
 #pragma unroll
-                    for (int p = 0; p < C; ++p) cluster.map_shared_rank(cab, p)[rank * RS + 2 * TR + t * dh + c] = v;
+                    for (int p = 0; p < C / 4; ++p)
+                        *reinterpret_cast<float4*>(cluster.map_shared_rank(cab, pq * (C / 4) + p) + rank * RS + 2 * TR + t * dh +
+                                                   4 * c4) = v;
                 }
             }
             SD_STAMP();   // after PV + push
@@ -693,7 +734,7 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
             SD_STAMP();   // after sync
             // combine the partials of all key parts -> O (every CTA, redundantly), transposed into xT
             for (int i = tid; i < T * d; i += blockDim.x) {
-                const int t = i / d, n = i % d;
+                const int t = i % T, n = i / T;
                 const int hh = n / dh, c = n % dh;
                 float mx = -INFINITY;
                 for (int p2 = 0; p2 < parts; ++p2) mx = fmaxf(mx, cab[(p2 * H + hh) * RS + t]);
@@ -708,50 +749,37 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
                 xT[n * TR + t] = num / den;
             }
             __syncthreads();
-            {
-                float* dst = act[ph & 1];
-                wslice(l, 3, P.ca_wo_t, d, wb, sj, sk);
-                slice_gemm<TR>(wb, sj, sk, nd, d, xT, [&](int j, int t, int half, float v) {
-                    const int col = rank * nd + j;
-                    if (t < T) push(dst, col * TR + t, half, v + __ldg(P.ca_bo + col));
-                });
-            }
+            wslice(l, 3, P.ca_wo_t, d, wb, sj, sk);
+            slice_gemm<TR>(wb, sj, sk, nd, d, xT, [&](int j, float* v) {
+                const float bias = bl[nq + 2 * nd + j];
+#pragma unroll
+                for (int t = 0; t < TR; ++t) v[t] += bias;
+                push_col(act[1], rank * nd + j, v);
+            });
             cluster.sync();
-            {
-                const float* dl = act[ph & 1];
-                ++ph;
-                for (int i = tid; i < T * d; i += blockDim.x) h[i] += dl[(i % d) * TR + (i / d)];
-                __syncthreads();
-            }
+            for (int i = tid; i < T * d; i += blockDim.x) h[i] += act[1][(i % d) * TR + (i / d)];
+            __syncthreads();
             // ---- feed-forward -----------------------------------------------------------------------
             SD_STAMP();   // after combine + ca out-proj + sync + residual
-            cta_layernorm_T<TR>(h, d, T, P.ln3_g, P.ln3_b, xT);
-            {
-                float* dst = act[ph & 1];
-                wslice(l, 4, P.w1_t, d, wb, sj, sk);
-                slice_gemm<TR>(wb, sj, sk, nd, d, xT, [&](int j, int t, int half, float v) {
-                    const int col = rank * nd + j;
-                    if (t < T) push(dst, col * TR + t, half, gelu_erf(v + __ldg(P.b1 + col)));
-                });
-            }
+            cta_layernorm_T_sm<TR>(h, d, T, pl + 4 * d, pl + 5 * d, xT);
+            wslice(l, 4, P.w1_t, d, wb, sj, sk);
+            slice_gemm<TR>(wb, sj, sk, nd, d, xT, [&](int j, float* v) {
+                const float bias = bl[nq + 3 * nd + j];
+#pragma unroll
+                for (int t = 0; t < TR; ++t) v[t] = gelu_erf(v[t] + bias);
+                push_col(act[0], rank * nd + j, v);
+            });
             cluster.sync();
-            {
-                const float* ff = act[ph & 1];   // [d][TR] = GEMM input layout already
-                ++ph;
-                float* dst = act[ph & 1];
-                wslice(l, 5, P.w2_t, d, wb, sj, sk);
-                slice_gemm<TR>(wb, sj, sk, nd, d, ff, [&](int j, int t, int half, float v) {
-                    const int col = rank * nd + j;
-                    if (t < T) push(dst, col * TR + t, half, v + __ldg(P.b2 + col));
-                });
-            }
+            wslice(l, 5, P.w2_t, d, wb, sj, sk);
+            slice_gemm<TR>(wb, sj, sk, nd, d, act[0], [&](int j, float* v) {   // gathered hidden = GEMM input layout
+                const float bias = bl[nq + 4 * nd + j];
+#pragma unroll
+                for (int t = 0; t < TR; ++t) v[t] += bias;
+                push_col(act[1], rank * nd + j, v);
+            });
             cluster.sync();
-            {
-                const float* dl = act[ph & 1];
-                ++ph;
-                for (int i = tid; i < T * d; i += blockDim.x) h[i] += dl[(i % d) * TR + (i / d)];
-                __syncthreads();
-            }
+            for (int i = tid; i < T * d; i += blockDim.x) h[i] += act[1][(i % d) * TR + (i / d)];
+            __syncthreads();
         }
 
         SD_STAMP();   // after all layers
@@ -1064,12 +1092,12 @@ template <int TR>
 int launch_cluster(sd_plan* p, SamplerArgs& a, cudaStream_t st, bool* launched) {
     *launched = false;
     const int C = kClusterSize;
-    if (a.d % C != 0 || C % a.heads != 0 || a.T > 16 || a.T > TR || a.dh > kClThreads) return SD_OK;
+    if (a.d % C != 0 || C % a.heads != 0 || a.T > 16 || a.T > TR || a.dh > kClThreads || a.dh % 4 != 0) return SD_OK;
     // resident layers: as many as fit beside the working buffers
     int L_res = a.L;
     size_t bytes = 0;
     for (; L_res >= 0; --L_res) {
-        bytes = (size_t)cluster_layout(a.d, L_res, TR, a.J, a.heads, a.M).total * sizeof(float);
+        bytes = (size_t)cluster_layout(a.d, a.L, L_res, TR, a.J, a.heads, a.M, a.T).total * sizeof(float);
         if (bytes <= 227 * 1024) break;
     }
     if (L_res < 0) return SD_OK;
