@@ -422,23 +422,32 @@ __device__ __forceinline__ void slice_gemm(const float* Wb, int sj, int sk, int 
     }
 }
 
-// LayerNorm of the T rows of h -> xT[c][t]; gamma/beta in SHARED memory (plain loads)
+// LayerNorm of the T rows of h -> xT[c][t]; gamma/beta in SHARED memory (plain loads).  Half a warp per row
+// (two rows per warp): with T <= 16 rows and 8 warps every row is normalised in one round.
 template <int TR>
 __device__ __forceinline__ void cta_layernorm_T_sm(const float* h, int d, int T, const float* gamma, const float* beta,
                                                    float* xT) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int t = w; t < T; t += nw) {
-        const float* r = h + t * d;
+    const int hl = lane & 15, half = lane >> 4;
+    for (int t0 = 2 * w; t0 < T; t0 += 2 * nw) {
+        const int t = t0 + half;
+        const bool ok = t < T;
+        const float* r = h + (ok ? t : 0) * d;
         float s = 0.f;
-        for (int c = lane; c < d; c += 32) s += r[c];
-        const float mu = warp_sum(s) / (float)d;
+        for (int c = hl; c < d; c += 16) s += r[c];
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);   // stays inside the half-warp
+        const float mu = s / (float)d;
         float q = 0.f;
-        for (int c = lane; c < d; c += 32) {
+        for (int c = hl; c < d; c += 16) {
             const float dl = r[c] - mu;
             q = fmaf(dl, dl, q);
         }
-        const float rs = rsqrtf(warp_sum(q) / (float)d + 1e-5f);
-        for (int c = lane; c < d; c += 32) xT[c * TR + t] = (r[c] - mu) * rs * gamma[c] + beta[c];
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rs = rsqrtf(q / (float)d + 1e-5f);
+        if (ok)
+            for (int c = hl; c < d; c += 16) xT[c * TR + t] = (r[c] - mu) * rs * gamma[c] + beta[c];
     }
     __syncthreads();
 }
@@ -500,11 +509,24 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
         const float* bs[5] = {P.sa_bo, P.ca_bq, P.ca_bo, P.b1, P.b2};
         for (int i = tid; i < 5 * nd; i += blockDim.x) bl[nq + i] = __ldg(bs[i / nd] + rank * nd + (i % nd));
     }
+    for (int i = tid; i < TR * Jp; i += blockDim.x) { xs[i] = 0.f; eps[i] = 0.f; }
+    __syncthreads();
     for (int i = tid; i < T * J; i += blockDim.x) xs[(i / J) * Jp + (i % J)] = a.x_in[(long long)b * T * J + i];
     for (int i = tid; i < d * TR; i += blockDim.x) { xT[i] = 0.f; act[1][i] = 0.f; }
     for (int i = tid; i < 3 * d * TR; i += blockDim.x) act[0][i] = 0.f;
     __syncthreads();
     cluster.sync();
+
+    // embedding weights of this thread's column stay in registers for all steps (column n = tid % d, rows tg, tg+ng, ..)
+    constexpr int kMaxJ = 24;
+    const bool emb_regs = d <= kClThreads && kClThreads % d == 0 && J <= kMaxJ;
+    float embw[kMaxJ];
+    float embb = 0.f;
+    if (emb_regs) {
+#pragma unroll
+        for (int j = 0; j < kMaxJ; ++j) embw[j] = j < J ? __ldg(a.io.emb_wt + j * d + (tid % d)) : 0.f;
+        embb = __ldg(a.io.emb_b + (tid % d));
+    }
 
     int dbg_i = 0;
 #define SD_STAMP()                                                                     \
@@ -536,11 +558,21 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
         dbg_i = 0;
         SD_STAMP();   // step start
         // ---- embedding + positional encoding (redundant in every CTA) ------------------------------
-        for (int i = tid; i < T * d; i += blockDim.x) {
-            const int t = i / d, n = i % d;
-            float acc = __ldg(a.io.emb_b + n) + __ldg(a.io.pe + t * d + n);
-            for (int j = 0; j < J; ++j) acc = fmaf(xs[t * Jp + j], __ldg(a.io.emb_wt + j * d + n), acc);
-            h[i] = acc;
+        if (emb_regs) {
+            const int n = tid % d, ng = kClThreads / d;
+            for (int t = tid / d; t < T; t += ng) {
+                float acc = embb + __ldg(a.io.pe + t * d + n);
+#pragma unroll
+                for (int j = 0; j < kMaxJ; ++j) acc = fmaf(xs[t * Jp + min(j, Jp - 1)], embw[j], acc);   // embw = 0 for j >= J
+                h[t * d + n] = acc;
+            }
+        } else {
+            for (int i = tid; i < T * d; i += blockDim.x) {
+                const int t = i / d, n = i % d;
+                float acc = __ldg(a.io.emb_b + n) + __ldg(a.io.pe + t * d + n);
+                for (int j = 0; j < J; ++j) acc = fmaf(xs[t * Jp + j], __ldg(a.io.emb_wt + j * d + n), acc);
+                h[i] = acc;
+            }
         }
         __syncthreads();
 
@@ -649,16 +681,25 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
 #pragma unroll
                     for (int t = 0; t < TR; ++t) acc[t] = 0.f;
                     const int c1 = min(dh, (g + 1) * cpg);
-                    for (int c = g * cpg; c < c1; ++c) {
-                        const float kv = (m == M - 1) ? __ldg(tk + hc * dh + c) : __ldcg(Kt + (long long)c * Mpad + m);
-                        const float4* qp = reinterpret_cast<const float4*>(q + (hc * dh + c) * TR);
+                    for (int cb = g * cpg; cb < c1; cb += 8) {   // 8 independent L2 loads in flight, then the FMAs
+                        float kv[8];
 #pragma unroll
-                        for (int qq = 0; qq < TR / 4; ++qq) {
-                            const float4 x4 = qp[qq];
-                            acc[4 * qq + 0] = fmaf(kv, x4.x, acc[4 * qq + 0]);
-                            acc[4 * qq + 1] = fmaf(kv, x4.y, acc[4 * qq + 1]);
-                            acc[4 * qq + 2] = fmaf(kv, x4.z, acc[4 * qq + 2]);
-                            acc[4 * qq + 3] = fmaf(kv, x4.w, acc[4 * qq + 3]);
+                        for (int u = 0; u < 8; ++u) {
+                            const int c = cb + u;
+                            kv[u] = c < c1 ? ((m == M - 1) ? __ldg(tk + hc * dh + c) : __ldcg(Kt + (long long)c * Mpad + m)) : 0.f;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int c = min(cb + u, c1 - 1);   // kv[u] = 0 beyond c1
+                            const float4* qp = reinterpret_cast<const float4*>(q + (hc * dh + c) * TR);
+#pragma unroll
+                            for (int qq = 0; qq < TR / 4; ++qq) {
+                                const float4 x4 = qp[qq];
+                                acc[4 * qq + 0] = fmaf(kv[u], x4.x, acc[4 * qq + 0]);
+                                acc[4 * qq + 1] = fmaf(kv[u], x4.y, acc[4 * qq + 1]);
+                                acc[4 * qq + 2] = fmaf(kv[u], x4.z, acc[4 * qq + 2]);
+                                acc[4 * qq + 3] = fmaf(kv[u], x4.w, acc[4 * qq + 3]);
+                            }
                         }
                     }
 #pragma unroll
@@ -701,12 +742,21 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
                         float acc[TR];
 #pragma unroll
                         for (int t = 0; t < TR; ++t) acc[t] = 0.f;
-                        for (int mi = g; mi < nk; mi += groups2) {
-                            const int m = m_lo + mi;
-                            const float vv = (m == M - 1) ? __ldg(tk + d + hc * dh + c) : __ldcg(Vc + (long long)m * d + c);
+                        for (int mb = g; mb < nk; mb += 8 * groups2) {   // 8 independent L2 loads in flight per thread
+                            float vv[8];
 #pragma unroll
-                            for (int t = 0; t < TR; ++t)
-                                if (t < T) acc[t] = fmaf(sc[t * (Mq + 1) + mi], vv, acc[t]);
+                            for (int u = 0; u < 8; ++u) {
+                                const int mi = mb + u * groups2;
+                                const int m = m_lo + mi;
+                                vv[u] = mi < nk ? ((m == M - 1) ? __ldg(tk + d + hc * dh + c) : __ldcg(Vc + (long long)m * d + c)) : 0.f;
+                            }
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                const int mi = min(mb + u * groups2, nk - 1);   // vv[u] = 0 beyond nk
+#pragma unroll
+                                for (int t = 0; t < TR; ++t)
+                                    if (t < T) acc[t] = fmaf(sc[t * (Mq + 1) + mi], vv[u], acc[t]);
+                            }
                         }
 #pragma unroll
                         for (int t = 0; t < TR; ++t) red[(g * TR + t) * dh + c] = acc[t];
@@ -784,12 +834,18 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
 
         SD_STAMP();   // after all layers
         // ---- output projection + DDIM update (redundant) --------------------------------------------
-        for (int i = tid; i < T * J; i += blockDim.x) {
-            const int t = i / J, j = i % J;
-            float acc = __ldg(a.io.fc_b + j);
-            for (int k = 0; k < d; ++k) acc = fmaf(h[t * d + k], __ldg(a.io.fc_wt + k * J + j), acc);
-            eps[t * Jp + j] = acc;
-        }
+        for (int i = tid; i < T * d; i += blockDim.x) xT[(i % d) * TR + (i / d)] = h[i];
+        __syncthreads();
+        slice_gemm<TR>(a.io.fc_wt, 1, J, J, d, xT, [&](int j, float* v) {   // weights [d][J] in global memory
+            const float bias = __ldg(a.io.fc_b + j);
+            if (lane < T) {
+                float e = 0.f;
+#pragma unroll
+                for (int t = 0; t < TR; ++t)
+                    if (lane == t) e = v[t];
+                eps[lane * Jp + j] = e + bias;
+            }
+        });
         __syncthreads();
         const float sb = __ldg(a.coef + 4 * s + 0), sa = __ldg(a.coef + 4 * s + 1);
         const float sap = __ldg(a.coef + 4 * s + 2), sbp = __ldg(a.coef + 4 * s + 3);
