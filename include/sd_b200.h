@@ -209,7 +209,7 @@ int sd_plan_sample(sd_plan* plan, const float* x_T, float* x_out, float* eps_tra
  * auto|cta|cluster sets the process default.  sd_plan_last_sampler: which one the last sd_plan_sample ran (1/2). */
 int sd_plan_set_sampler(sd_plan* plan, int mode);
 int sd_plan_last_sampler(const sd_plan* plan);
-/* profiling aid: device buffer of num_steps*64 int64 that the cluster sampler fills with clock64() stamps of its
+/* profiling aid: device buffer of num_steps*96 int64 that the cluster sampler fills with clock64() stamps of its
  * phases (CTA 0); NULL disables */
 int sd_plan_set_debug_stamps(sd_plan* plan, long long* device_buffer);
 /* one forward_with_context (model.py:159-179) against the cached context, per-sample t */

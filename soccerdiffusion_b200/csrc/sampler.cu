@@ -71,7 +71,7 @@ struct SamplerArgs {
     float* x_out;         // (B,T,J) final sample (tok_mode 0)
     float* eps_out;       // tok_mode 1: (B,T,J);  tok_mode 0: optional trace (S,B,T,J)
     int denorm;
-    long long* dbg;       // optional: clock64() stamps of the cluster kernel's phases (CTA 0, thread 0), 64 per step
+    long long* dbg;       // optional: clock64() stamps of the cluster kernel's phases (CTA 0, thread 0), 96 per step
 };
 
 // ------------------------------------------------------------------------------------------
@@ -379,7 +379,7 @@ __host__ __device__ inline ClusterLayout cluster_layout(int d, int L, int L_res,
     int cur = 0;
     o.w = cur;    cur += align4(L_res * 8 * (d / C) * d);        // (3 + 5) slices of d/C columns each
     o.prm = cur;  cur += align4(L * cluster_param_floats(d));
-    o.act0 = cur; cur += align4(3 * d * TR);                     // gathered q|k|v, q (cross), ffn hidden
+    o.act0 = cur; cur += align4(imax(3 * d * TR, d * TR + dh * Mq));   // gathered q|k|v; q (cross) + staged K/V slice; ffn hidden
     o.act1 = cur; cur += align4(d * TR);                         // gathered residual deltas
     o.h = cur;    cur += align4(TR * d);
     o.xT = cur;   cur += align4(d * TR);
@@ -452,14 +452,19 @@ __device__ __forceinline__ void cta_layernorm_T_sm(const float* h, int d, int T,
     __syncthreads();
 }
 
-template <int TR>
+// D / DH / TT: compile-time hidden size, head size and trajectory length (0 = run-time values).  The default
+// architecture (d=128, 4 heads, T=10) is instantiated with constants so that the index arithmetic of the many short
+// loops folds to shifts/multiplies; every other shape runs the generic instantiation.
+template <int TR, int D, int DH, int TT>
 __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const SamplerArgs a, const int L_res) {
     extern __shared__ __align__(16) float smem[];
     cg::cluster_group cluster = cg::this_cluster();
     constexpr int C = kClusterSize;
     const int rank = (int)cluster.block_rank();
     const int b = blockIdx.x / C;
-    const int d = a.d, T = a.T, J = a.J, H = a.heads, dh = a.dh, M = a.M, Mpad = a.Mpad, L = a.L;
+    const int d = D ? D : a.d, T = TT ? TT : a.T, dh = DH ? DH : a.dh;
+    const int H = (D && DH) ? D / DH : a.heads;
+    const int J = a.J, M = a.M, Mpad = a.Mpad, L = a.L;
     const int nd = d / C, nq = 3 * nd;
     const int Jp = (J + 3) & ~3;
     const ClusterLayout lo = cluster_layout(d, L, L_res, TR, J, H, M, T);
@@ -531,7 +536,7 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
     int dbg_i = 0;
 #define SD_STAMP()                                                                     \
     do {                                                                               \
-        if (a.dbg && blockIdx.x == 0 && tid == 0 && dbg_i < 64) a.dbg[s * 64 + dbg_i] = clock64(); \
+        if (a.dbg && blockIdx.x == 0 && tid == 0 && dbg_i < 96) a.dbg[s * 96 + dbg_i] = clock64(); \
         ++dbg_i;                                                                       \
     } while (0)
 
@@ -670,36 +675,46 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
                 const float* Kt = a.Kt + ((long long)l * a.B + b) * (long long)H * dh * Mpad + (long long)hc * dh * Mpad;
                 const float* Vc = a.Vc + ((long long)l * a.B + b) * (long long)Mpad * d + hc * dh;
                 const float* tk = a.tok_kv + ((long long)s * L + l) * 2 * d;
+                // this CTA's K slice [dh][nk] -> shared memory (free upper part of act[0]): one coalesced, fully parallel
+                // round trip to L2 instead of dependent loads inside the dot products
+                float* kvs = act[0] + d * TR;
+                for (int i0 = tid; i0 < dh * nk; i0 += 8 * kClThreads) {   // 8 loads in flight per thread, then the stores
+                    float v8[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = i0 + u * kClThreads;
+                        const int c = i / nk, mi = i - c * nk;
+                        const int m = m_lo + mi;
+                        v8[u] = i < dh * nk ? ((m == M - 1) ? __ldg(tk + hc * dh + c) : __ldcg(Kt + (long long)c * Mpad + m)) : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = i0 + u * kClThreads;
+                        const int c = i / nk, mi = i - c * nk;
+                        if (i < dh * nk) kvs[c * Mq + mi] = v8[u];
+                    }
+                }
+                __syncthreads();
                 // scores for this CTA's keys: thread = (key, c-group)
                 int G = min(dh, kClThreads / max(Mq, 1));   // same formula as cluster_layout()
                 if (G < 1) G = 1;
                 const int cpg = (dh + G - 1) / G;
                 for (int idx = tid; idx < nk * G; idx += blockDim.x) {
                     const int mi = idx % nk, g = idx / nk;
-                    const int m = m_lo + mi;
                     float acc[TR];
 #pragma unroll
                     for (int t = 0; t < TR; ++t) acc[t] = 0.f;
                     const int c1 = min(dh, (g + 1) * cpg);
-                    for (int cb = g * cpg; cb < c1; cb += 8) {   // 8 independent L2 loads in flight, then the FMAs
-                        float kv[8];
+                    for (int c = g * cpg; c < c1; ++c) {
+                        const float kv = kvs[c * Mq + mi];
+                        const float4* qp = reinterpret_cast<const float4*>(q + (hc * dh + c) * TR);
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int c = cb + u;
-                            kv[u] = c < c1 ? ((m == M - 1) ? __ldg(tk + hc * dh + c) : __ldcg(Kt + (long long)c * Mpad + m)) : 0.f;
-                        }
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int c = min(cb + u, c1 - 1);   // kv[u] = 0 beyond c1
-                            const float4* qp = reinterpret_cast<const float4*>(q + (hc * dh + c) * TR);
-#pragma unroll
-                            for (int qq = 0; qq < TR / 4; ++qq) {
-                                const float4 x4 = qp[qq];
-                                acc[4 * qq + 0] = fmaf(kv[u], x4.x, acc[4 * qq + 0]);
-                                acc[4 * qq + 1] = fmaf(kv[u], x4.y, acc[4 * qq + 1]);
-                                acc[4 * qq + 2] = fmaf(kv[u], x4.z, acc[4 * qq + 2]);
-                                acc[4 * qq + 3] = fmaf(kv[u], x4.w, acc[4 * qq + 3]);
-                            }
+                        for (int qq = 0; qq < TR / 4; ++qq) {
+                            const float4 x4 = qp[qq];
+                            acc[4 * qq + 0] = fmaf(kv, x4.x, acc[4 * qq + 0]);
+                            acc[4 * qq + 1] = fmaf(kv, x4.y, acc[4 * qq + 1]);
+                            acc[4 * qq + 2] = fmaf(kv, x4.z, acc[4 * qq + 2]);
+                            acc[4 * qq + 3] = fmaf(kv, x4.w, acc[4 * qq + 3]);
                         }
                     }
 #pragma unroll
@@ -734,6 +749,23 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
                 }
                 __syncthreads();
                 SD_STAMP();   // after softmax partial
+                // V slice [nk][dh] -> the same shared region (the K slice is no longer needed)
+                for (int i0 = tid; i0 < nk * dh; i0 += 8 * kClThreads) {
+                    float v8[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = i0 + u * kClThreads;
+                        const int mi = i / dh, c = i - mi * dh;
+                        const int m = m_lo + mi;
+                        v8[u] = i < nk * dh ? ((m == M - 1) ? __ldg(tk + d + hc * dh + c) : __ldcg(Vc + (long long)m * d + c)) : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = i0 + u * kClThreads;
+                        if (i < nk * dh) kvs[i] = v8[u];
+                    }
+                }
+                __syncthreads();
                 // partial P.V : thread = (c, key group)
                 const int groups2 = max(1, kClThreads / dh);
                 {
@@ -742,27 +774,19 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
                         float acc[TR];
 #pragma unroll
                         for (int t = 0; t < TR; ++t) acc[t] = 0.f;
-                        for (int mb = g; mb < nk; mb += 8 * groups2) {   // 8 independent L2 loads in flight per thread
-                            float vv[8];
+                        for (int mi = g; mi < nk; mi += groups2) {
+                            const float vv = kvs[mi * dh + c];
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) {
-                                const int mi = mb + u * groups2;
-                                const int m = m_lo + mi;
-                                vv[u] = mi < nk ? ((m == M - 1) ? __ldg(tk + d + hc * dh + c) : __ldcg(Vc + (long long)m * d + c)) : 0.f;
-                            }
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) {
-                                const int mi = min(mb + u * groups2, nk - 1);   // vv[u] = 0 beyond nk
-#pragma unroll
-                                for (int t = 0; t < TR; ++t)
-                                    if (t < T) acc[t] = fmaf(sc[t * (Mq + 1) + mi], vv[u], acc[t]);
-                            }
+                            for (int t = 0; t < TR; ++t)
+                                if (t < T) acc[t] = fmaf(sc[t * (Mq + 1) + mi], vv, acc[t]);
                         }
 #pragma unroll
                         for (int t = 0; t < TR; ++t) red[(g * TR + t) * dh + c] = acc[t];
                     }
                 }
+                SD_STAMP();   // after PV partial (thread 0's own work)
                 __syncthreads();
+                SD_STAMP();   // after PV barrier
                 // reduce over key groups, 4 channels per item, 16-byte pushes; item = (t, c4, peer quarter)
                 const int dh4 = dh >> 2;
                 for (int it = tid; it < T * dh4 * 4; it += blockDim.x) {
@@ -799,6 +823,7 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
                 xT[n * TR + t] = num / den;
             }
             __syncthreads();
+            SD_STAMP();   // after combine
             wslice(l, 3, P.ca_wo_t, d, wb, sj, sk);
             slice_gemm<TR>(wb, sj, sk, nd, d, xT, [&](int j, float* v) {
                 const float bias = bl[nq + 2 * nd + j];
@@ -806,7 +831,9 @@ __global__ void __launch_bounds__(kClThreads, 1) sampler_cluster_kernel(const Sa
                 for (int t = 0; t < TR; ++t) v[t] += bias;
                 push_col(act[1], rank * nd + j, v);
             });
+            SD_STAMP();   // after ca out gemm+push
             cluster.sync();
+            SD_STAMP();   // after sync
             for (int i = tid; i < T * d; i += blockDim.x) h[i] += act[1][(i % d) * TR + (i / d)];
             __syncthreads();
             // ---- feed-forward -----------------------------------------------------------------------
@@ -1144,7 +1171,7 @@ int sampler_mode() {
     return mode;
 }
 
-template <int TR>
+template <int TR, int D, int DH, int TT>
 int launch_cluster(sd_plan* p, SamplerArgs& a, cudaStream_t st, bool* launched) {
     *launched = false;
     const int C = kClusterSize;
@@ -1157,7 +1184,7 @@ int launch_cluster(sd_plan* p, SamplerArgs& a, cudaStream_t st, bool* launched) 
         if (bytes <= 227 * 1024) break;
     }
     if (L_res < 0) return SD_OK;
-    auto kernel = sampler_cluster_kernel<TR>;
+    auto kernel = sampler_cluster_kernel<TR, D, DH, TT>;
     static bool configured = false;
     static bool usable = true;
     if (!usable) return SD_OK;
@@ -1208,8 +1235,9 @@ int run_sampler(sd_plan* p, SamplerArgs& a, cudaStream_t st) {
     if (a.tok_mode == 0 && mode != 1 && (mode == 2 || a.B <= 64)) {
         bool launched = false;
         int rc = SD_OK;
-        if (a.T <= 12) rc = launch_cluster<12>(p, a, st, &launched);
-        else if (a.T <= 16) rc = launch_cluster<16>(p, a, st, &launched);
+        if (a.d == 128 && a.dh == 32 && a.T == 10) rc = launch_cluster<12, 128, 32, 10>(p, a, st, &launched);
+        else if (a.T <= 12) rc = launch_cluster<12, 0, 0, 0>(p, a, st, &launched);
+        else if (a.T <= 16) rc = launch_cluster<16, 0, 0, 0>(p, a, st, &launched);
         if (rc != SD_OK) return rc;
         if (launched) {
             p->last_sampler = 2;

@@ -21,16 +21,17 @@ x_T = torch.randn(1, 10, 20, device=dev)
 with torch.no_grad():
     model.sample(ctx, x_T, sch)
     plan = next(iter(model._plans.values()))
-    buf = torch.zeros(30 * 64, dtype=torch.int64, device=dev)
+    buf = torch.zeros(30 * 96, dtype=torch.int64, device=dev)
     _lib.check(_lib.lib().sd_plan_set_debug_stamps(plan.handle, buf.data_ptr()), "dbg")
     model.sample(ctx, x_T, sch)
     torch.cuda.synchronize()
     _lib.lib().sd_plan_set_debug_stamps(plan.handle, None)
-st = buf.view(30, 64).cpu().numpy()
+st = buf.view(30, 96).cpu().numpy()
 names = ["step start"]
 for l in range(4):
     names += [f"L{l} start", "LN1", "qkv gemm+push", "sync", "self-attn core", "sa out+sync+res", "LN2+q gemm+sync",
-              "scores", "softmax", "PV+push", "sync", "combine+ca out+sync+res"]
+              "scores", "softmax", "PV partial", "PV barrier", "PV reduce+push", "sync", "combine", "ca out gemm+push",
+              "sync", "residual"]
 names += ["all layers (LN3+ffn1+sync+ffn2+sync+res of last layer)", "fc_out+ddim (step end)"]
 n = len(names)
 d = np.diff(st[5:25, :n].astype(np.float64), axis=1).mean(axis=0)
