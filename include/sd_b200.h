@@ -155,6 +155,10 @@ int sd_bn_bwd_nhwc_bf16(const void* dy, const void* relu_mask, const void* x, co
  * space-to-depth (channel = c*4 + dy*2 + dx, 12 used), the layout in which the 7x7/s2/p3 stem convolution
  * (torchvision resnet conv1; ml/model/encoder/image.py:55-73) is a 4x4/s1 convolution with Cin=16 */
 int sd_stem_pack_s2d_bf16(const float* images, void* out, int N, int H, int W, void* stream);
+/* Weight gradient of the stem convolution in its space-to-depth form: dw_s2d[256][64] fp32 (row = kh*64 + kw*16 + ci,
+ * column = output channel) from the packed image (sd_stem_pack_s2d_bf16) and dy bf16 NHWC (N,H/2,W/2,64); tcgen05,
+ * both operands MN-major.  Replaces cuDNN's conv1 wgrad (ml/model/encoder/image.py:55-73 under autograd). */
+int sd_stem_wgrad_s2d_bf16(const void* xs2d, const void* dy, float* dw_s2d, int N, int H, int W, void* stream);
 /* Fused stem: maxpool3x3s2(relu(bn(x))) without materialising the activated 112x112 map; backward recomputes the
  * ReLU mask from x (torchvision ResNet stem bn1 -> relu -> maxpool). mean/invstd from sd_bn_stats_nhwc_bf16. */
 int sd_stem_bn_relu_pool_nhwc_bf16_fwd(const void* x, const float* mean, const float* invstd, const float* gamma,

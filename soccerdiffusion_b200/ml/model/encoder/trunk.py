@@ -14,6 +14,11 @@ import torch.nn.functional as F
 from soccerdiffusion_b200 import ops
 
 
+import os
+
+_USE_TC_STEM_WGRAD = os.environ.get("SD_B200_STEM_WGRAD", "tc") == "tc"
+
+
 def _cl(t: torch.Tensor) -> torch.Tensor:
     return t if t.is_contiguous(memory_format=torch.channels_last) else t.contiguous(memory_format=torch.channels_last)
 
@@ -177,6 +182,19 @@ class StemConvS2D(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         images, weight = ctx.saved_tensors
+        N, Cin, H, W = images.shape
+        Cout = weight.shape[0]
+        if Cout == 64 and _USE_TC_STEM_WGRAD:
+            # tcgen05 kernel on the (re-packed) space-to-depth image; then undo the weight transform
+            Hp, Wp = (H + 6) // 2, (W + 6) // 2
+            xp = torch.empty((N, Hp, Wp, 16), device=images.device, dtype=torch.bfloat16)
+            ops.stem_pack(images.contiguous(), xp, N, H, W)
+            dws = torch.empty((256, 64), device=images.device, dtype=torch.float32)
+            ops.stem_wgrad(xp, _cl(dy), dws, N, H, W)
+            g = dws.view(4, 4, 16, Cout)[:, :, : Cin * 4]                  # (kh, kw, ci=(c,dy,dx), cout)
+            g = g.reshape(4, 4, Cin, 2, 2, Cout).permute(5, 2, 0, 3, 1, 4)  # (cout, c, kh, dy, kw, dx)
+            gw = g.reshape(Cout, Cin, 8, 8)[:, :, :7, :7]
+            return None, gw.to(weight.dtype).contiguous()
         x = images.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
         gw = torch.ops.aten.convolution_backward(_cl(dy), x, weight.to(torch.bfloat16), None, (2, 2), (3, 3), (1, 1), False,
                                                  (0, 0), 1, (False, True, False))[1]

@@ -326,3 +326,11 @@ def stem_pack(images, out, N, H, W):
         check(_lib.lib().sd_stem_pack_s2d_bf16(images.data_ptr(), out.data_ptr(), N, H, W, stream_ptr()),
               "sd_stem_pack_s2d_bf16")
     _count()
+
+
+def stem_wgrad(xs2d, dy, dw, N, H, W):
+    P = N * (H // 2) * (W // 2)
+    with _Timed("stem_wgrad_s2d", 2.0 * 256 * 64 * P, 32.0 * N * ((H + 6) // 2) * ((W + 6) // 2) + 128.0 * P, f"[N{N} H{H}]"):
+        check(_lib.lib().sd_stem_wgrad_s2d_bf16(xs2d.data_ptr(), dy.data_ptr(), dw.data_ptr(), N, H, W, stream_ptr()),
+              "sd_stem_wgrad_s2d_bf16")
+    _count(2)

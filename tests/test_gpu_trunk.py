@@ -118,6 +118,31 @@ def test_stem_pack_and_space_to_depth_conv_equal_conv1():
     assert rel(g1, conv.weight.grad) < 1e-2
 
 
+@pytest.mark.parametrize("N,H,W", [(4, 224, 224), (3, 20, 36), (2, 64, 96), (1, 6, 6)])
+def test_stem_wgrad_tcgen05_matches_cudnn(N, H, W):
+    """conv1 weight gradient: tcgen05 kernel on the space-to-depth image vs aten.convolution_backward (7x7 form)."""
+    from soccerdiffusion_b200.ml.model.encoder import trunk as T
+
+    torch.manual_seed(N * H)
+    w = torch.randn(64, 3, 7, 7, device="cuda") * 0.05
+    img = torch.randn(N, 3, H, W, device="cuda")
+    dy = _cl_bf16(N, 64, H // 2, W // 2)
+    got = {}
+    for mode in (True, False):
+        T._USE_TC_STEM_WGRAD = mode
+        try:
+            wg = w.clone().requires_grad_(True)
+            y = T.StemConvS2D.apply(img, wg)
+            y.backward(dy)
+            got[mode] = wg.grad.clone()
+        finally:
+            T._USE_TC_STEM_WGRAD = True
+    # exact reference in float64 on the bf16-rounded operands
+    ref = torch.nn.grad.conv2d_weight(img.to(torch.bfloat16).double(), (64, 3, 7, 7), dy.double(), stride=2, padding=3)
+    assert rel(got[True], ref) < 2e-5, rel(got[True], ref)        # fp32 accumulation of exact bf16 products
+    assert rel(got[False], ref) < 1e-2                            # cuDNN result is rounded to bf16
+
+
 def test_fused_trunk_matches_library_trunk_bf16():
     """Whole trunk, train mode: libsd_b200 path (space-to-depth stem, fused BN/ReLU/pool kernels) and torch's bf16
     autocast path are both compared with the fp32 trunk; the fused path must be as close to fp32 as the library
