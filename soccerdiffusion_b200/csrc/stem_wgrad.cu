@@ -78,9 +78,8 @@ __global__ void __launch_bounds__(NT, 1) stem_wgrad_kernel(const uint4* __restri
         for (int i = 0; i < 8; ++i) {
             const int px = a_px0 + 8 * i;
             int wo = wo0 + px, ho = ho0, n = n0;
-            if (wo >= WO) { wo -= WO; ++ho; }
-            if (wo >= WO) { wo -= WO; ++ho; }   // KC may exceed WO for small images
-            if (ho >= HO) { ho -= HO; ++n; }
+            while (wo >= WO) { wo -= WO; ++ho; }   // one iteration at most when WO >= KC (224x224 images: WO = 112)
+            while (ho >= HO) { ho -= HO; ++n; }
             const uint32_t dst = smem_u32(As) + (uint32_t)((a_kh >> 1) * (2 * KC * 128)) +
                                  sw128_mn_chunk_off((a_kh & 1) * 64 + a_c16 * 8, px, KC);
             if (p0 + px < P) {
