@@ -15,6 +15,9 @@
 #include "tc_common.cuh"
 #include "../../include/sd_b200.h"
 
+#include <cuda.h>
+#include <cstdlib>
+
 using namespace sd;
 using namespace sdtc;
 
@@ -151,6 +154,177 @@ __global__ void __launch_bounds__(NT, 1) stem_wgrad_kernel(const uint4* __restri
     if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
+// ---- TMA-fed variant: one image row of output pixels (KC = WO, a multiple of 16, <= 128) per pipeline stage --------
+// Operand tiles are fetched by the TMA engine from two tensor maps with the 128-byte swizzle the MN-major tcgen05
+// descriptors expect:
+//   tmA: the packed image viewed as [pixel-start q][64 elements] with a 32-byte row pitch (consecutive patch rows
+//        overlap by 3 pixels): box {64, KC} at (0, (n*Hp + ho + kh)*Wp) = the kh-th filter row of KC patches;
+//   tmB: dy viewed as [pixel][64]: box {64, KC} at (0, row*WO).
+// Warp 0 = producer (one lane issues 5 TMA loads per stage), warp 1 = MMA issuer (one lane), full/empty mbarrier
+// ring; everybody joins for the TMEM epilogue.
+constexpr int TMA_STAGES = 3;
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__global__ void __launch_bounds__(NT, 1) stem_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB, float* __restrict__ dw,
+                                                               int HO, int WO, int Hp, int Wp, long long rows_total,
+                                                               int rows_per_cta) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[TMA_STAGES];
+    __shared__ __align__(8) uint64_t bar_empty[TMA_STAGES];
+    __shared__ __align__(8) uint64_t bar_done;
+    __shared__ uint32_t tmem_slot;
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int KCr = WO;                       // pixels (k rows) per stage
+    const int blk = KCr * 128;                // bytes of one 64-wide MN block (one filter row / dy)
+    const int stage_bytes = 5 * blk;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < TMA_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+        mbar_init(&bar_done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, 128);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+
+    const long long r_begin = (long long)blockIdx.x * rows_per_cta;
+    const long long r_end = min(rows_total, r_begin + rows_per_cta);
+    const int nrows = (int)max(0LL, r_end - r_begin);
+
+    if (warp == 0 && lane == 0) {
+        for (int ci = 0; ci < nrows; ++ci) {
+            const int s = ci % TMA_STAGES;
+            mbar_wait(&bar_empty[s], (uint32_t)(((ci / TMA_STAGES) & 1) ^ 1));
+            const long long r = r_begin + ci;
+            const int n = (int)(r / HO), ho = (int)(r - (long long)n * HO);
+            const uint32_t base = smem_u32(smem + s * stage_bytes);
+            mbar_arrive_expect_tx(&bar_full[s], (uint32_t)stage_bytes);
+#pragma unroll
+            for (int kh = 0; kh < 4; ++kh)
+                tma_load_2d(base + kh * blk, &tmA, 0, (n * Hp + ho + kh) * Wp, &bar_full[s]);
+            tma_load_2d(base + 4 * blk, &tmB, 0, (int)(r * WO), &bar_full[s]);
+        }
+    } else if (warp == 1 && lane == 0) {
+        const uint32_t idesc = instr_desc_bf16(128, 64, 1, 1);
+        const int ksteps = KCr / 16;
+        for (int ci = 0; ci < nrows; ++ci) {
+            const int s = ci % TMA_STAGES;
+            mbar_wait(&bar_full[s], (uint32_t)((ci / TMA_STAGES) & 1));
+            tc_fence_after_sync();
+            const uint32_t base = smem_u32(smem + s * stage_bytes);
+            const uint64_t db = smem_desc_mn_sw128(base + 4 * blk, (uint32_t)blk, 1024);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const uint64_t da = smem_desc_mn_sw128(base + mt * 2 * blk, (uint32_t)blk, 1024);
+                for (int ks = 0; ks < ksteps; ++ks)
+                    mma_bf16_ss(tmem + mt * 64, da + (uint64_t)(128 * ks), db + (uint64_t)(128 * ks), idesc,
+                                (ci > 0 || ks > 0) ? 1u : 0u);
+            }
+            mma_commit(&bar_empty[s]);
+            if (ci == nrows - 1) mma_commit(&bar_done);
+        }
+    }
+    __syncwarp();
+    if (nrows > 0) {
+        mbar_wait(&bar_done, 0);
+        tc_fence_after_sync();
+        const int q = warp & 3, mt = warp >> 2;
+        const int j = mt * 128 + q * 32 + lane;
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) {
+            float v[32];
+            tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 64 + cb * 32), v);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) atomicAdd(dw + j * 64 + cb * 32 + c, v[c]);
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+bool use_tma() {   // SD_B200_STEM_WGRAD_TMA=0 selects the cp.async-fed kernel
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SD_B200_STEM_WGRAD_TMA");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+// returns SD_OK and sets *done when the TMA kernel was launched; leaves *done false when this shape / driver cannot
+int launch_tma(const void* xs2d, const void* dy, float* dw, int N, int HO, int WO, int Hp, int Wp, cudaStream_t st, bool* done) {
+    *done = false;
+    if (!use_tma() || WO % 16 != 0 || WO > 128 || WO < 16) return SD_OK;
+    const size_t smem = (size_t)TMA_STAGES * 5 * WO * 128 + 1024;
+    if (smem > 227 * 1024) return SD_OK;
+    static bool usable = true;
+    if (!usable) return SD_OK;
+    // the driver entry point is resolved at run time (the library must load on machines without libcuda.so.1)
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+            qres != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            usable = false;
+            return SD_OK;
+        }
+        encode = (EncodeFn)fn;
+    }
+    CUtensorMap tmA, tmB;
+    {
+        const cuuint64_t gdim[2] = {64, (cuuint64_t)N * Hp * Wp - 3};
+        const cuuint64_t gstr[1] = {32};   // bytes between consecutive patch rows (they overlap by 3 pixels)
+        const cuuint32_t box[2] = {64, (cuuint32_t)WO};
+        const cuuint32_t estr[2] = {1, 1};
+        if (encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(xs2d), gdim, gstr, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+            usable = false;
+            return SD_OK;
+        }
+    }
+    {
+        const cuuint64_t gdim[2] = {64, (cuuint64_t)N * HO * WO};
+        const cuuint64_t gstr[1] = {128};
+        const cuuint32_t box[2] = {64, (cuuint32_t)WO};
+        const cuuint32_t estr[2] = {1, 1};
+        if (encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(dy), gdim, gstr, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+            usable = false;
+            return SD_OK;
+        }
+    }
+    static bool configured = false;
+    if (!configured) {
+        SD_CUDA(cudaFuncSetAttribute(stem_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    const long long rows = (long long)N * HO;
+    const int grid = (int)min((long long)148, rows);
+    const int per = (int)((rows + grid - 1) / grid);
+    stem_wgrad_tma_kernel<<<grid, NT, smem, st>>>(tmA, tmB, dw, HO, WO, Hp, Wp, rows, per);
+    SD_LAUNCH_CHECK();
+    *done = true;
+    return SD_OK;
+}
+
 }  // namespace
 
 extern "C" int sd_stem_wgrad_s2d_bf16(const void* xs2d, const void* dy, float* dw_s2d, int N, int H, int W, void* stream) {
@@ -161,6 +335,12 @@ extern "C" int sd_stem_wgrad_s2d_bf16(const void* xs2d, const void* dy, float* d
     const long long P = (long long)N * HO * WO;
     cudaStream_t st = (cudaStream_t)stream;
     SD_CUDA(cudaMemsetAsync(dw_s2d, 0, sizeof(float) * 256 * 64, st));
+    {
+        bool done = false;
+        const int rc = launch_tma(xs2d, dy, dw_s2d, N, HO, WO, Hp, Wp, st, &done);
+        if (rc != SD_OK) return rc;
+        if (done) return SD_OK;
+    }
     const long long nchunks = (P + KC - 1) / KC;
     const int grid = (int)min((long long)148, nchunks);
     const int per = (int)((nchunks + grid - 1) / grid);
