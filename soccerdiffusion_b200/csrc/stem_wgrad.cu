@@ -267,7 +267,7 @@ int launch_tma(const void* xs2d, const void* dy, float* dw, int N, int HO, int W
     *done = false;
     if (!use_tma() || WO % 16 != 0 || WO > 128 || WO < 16) return SD_OK;
     const size_t smem = (size_t)TMA_STAGES * 5 * WO * 128 + 1024;
-    if (smem > 227 * 1024) return SD_OK;
+    if (smem > 227 * 1024 - 256) return SD_OK;
     static bool usable = true;
     if (!usable) return SD_OK;
     // the driver entry point is resolved at run time (the library must load on machines without libcuda.so.1)
@@ -311,10 +311,14 @@ int launch_tma(const void* xs2d, const void* dy, float* dw, int N, int HO, int W
             return SD_OK;
         }
     }
-    static bool configured = false;
-    if (!configured) {
-        SD_CUDA(cudaFuncSetAttribute(stem_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
+    static size_t configured = 0;   // dynamic + static shared memory must stay within the 227 KB opt-in limit
+    if (configured < smem) {
+        if (cudaFuncSetAttribute(stem_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            usable = false;
+            return SD_OK;
+        }
+        configured = smem;
     }
     const long long rows = (long long)N * HO;
     const int grid = (int)min((long long)148, rows);
