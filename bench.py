@@ -245,7 +245,21 @@ def run_ours(args):
         # image tokens precomputed: the trunk (library cuDNN, SURVEY.md §8 a8') is outside the timed step
         img_tokens = torch.randn(bs, hp["image_context_length"], hp["hidden_dim"], device=dev)
 
+    graphed = None
+    if args.graph and args.workload in ("full", "denoiser") and not args.ncu_range:
+        from soccerdiffusion_b200.ml.training import GraphedTrainStep
+
+        try:
+            graphed = GraphedTrainStep(model, opt, sch, batch, lr_scheduler=lrs, data_parallel=world > 1,
+                                       decoder_pretraining=args.workload == "denoiser", warmup_steps=3)
+        except Exception as e:   # capture not possible on this stack: run the step kernel by kernel
+            sys.stderr.write(f"[bench] CUDA-graph capture of the training step failed ({type(e).__name__}: {e}); eager launches\n")
+            graphed = None
+            torch.cuda.synchronize()
+
     def step(b):
+        if graphed is not None:
+            return graphed(b)
         if args.workload == "full":
             return train_step(model, opt, sch, norm, b, lr_scheduler=lrs, data_parallel=world > 1)
         if args.workload == "denoiser":
@@ -313,8 +327,16 @@ def run_ours(args):
         ops.profile_begin()
     pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pe0.record()
+    def eager_step(b):
+        if args.workload == "full":
+            return train_step(model, opt, sch, norm, b, lr_scheduler=lrs, data_parallel=world > 1)
+        if args.workload == "denoiser":
+            return train_step(model, opt, sch, norm, b, lr_scheduler=lrs, data_parallel=world > 1,
+                              decoder_pretraining=True)
+        return _inscope_step(model, opt, sch, b, img_tokens, lrs, world > 1)
+
     for _ in range(nprof):
-        step(batch)
+        eager_step(batch)
     pe1.record()
     torch.cuda.synchronize()
     if rank == 0:
@@ -367,7 +389,8 @@ def run_ours(args):
                                   "denoiser": "denoiser-only training step (train.py:221-224)"}[args.workload],
                         global_batch=gb, per_gpu_batch=bs, parallelism=f"dp{world}", dropout_p=0.1,
                         l2="inputs %.2f GB/step per GPU > 126 MB L2; no explicit flush" % (h2d / 1e9),
-                        precision_mode=args.precision),
+                        precision_mode=args.precision,
+                        launch="one CUDA graph replay per step" if graphed is not None else "kernel by kernel"),
             e2e=dict(value=gb * args.steps / (ms_e2e / 1e3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4),
             gpu_launches=launches, clocks=clk, roofline=roofline, kernel_classes=kernel_classes, cpu_baseline=cpu, ddim=ddim)
         emit(line)
@@ -484,6 +507,8 @@ def main():
     ap.add_argument("--workload", default="full", choices=["full", "inscope", "denoiser"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ddim", action="store_true")
+    ap.add_argument("--no-graph", dest="graph", action="store_false",
+                    help="launch the training step kernel by kernel instead of replaying one captured CUDA graph")
     ap.add_argument("--ncu-range", action="store_true",
                     help="bracket the timed region with cudaProfilerStart/Stop and stop after it (for ncu --profile-from-start off)")
     args = ap.parse_args()

@@ -117,6 +117,12 @@ int sd_affine_joints(const float* x, const float* mean, const float* std, float*
 /* torch.optim.AdamW step over one flat buffer (train.py:162,239) */
 int sd_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int step, float grad_scale, void* stream);
+/* the same update with the hyper-parameters in device memory: hyper_dev = {lr, beta1, beta2, eps, weight_decay,
+ * lr/(1-beta1^t), 1/sqrt(1-beta2^t), grad_scale} — capturable in a CUDA graph while OneCycleLR advances on the host */
+int sd_adamw_step_dev(float* p, const float* g, float* m, float* v, long long n, const float* hyper_dev, void* stream);
+/* device-resident counter added to every dropout seed (NULL = off): advancing it between CUDA-graph replays gives
+ * each replay fresh masks although the host-side seeds are frozen in the graph */
+int sd_set_dropout_seed_offset(const unsigned long long* device_counter);
 /* GameStateEncoder (ml/model/encoder/game_state.py:27) gather + its gradient */
 int sd_gather_rows(const float* table, const long long* idx, int rows, float* out, long long ld_out, int B, int d,
                    int* err_flag, void* stream);

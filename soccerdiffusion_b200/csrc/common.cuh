@@ -70,16 +70,27 @@ __host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
 
 struct Dropout {
     uint64_t seed;
+    const unsigned long long* seed_dev;   // optional device-resident offset added to `seed` (CUDA-graph replays: the
+                                          // host-side seed is frozen in the graph, the device counter advances)
     uint32_t stream;
     uint32_t thresh;   // 0 => disabled
     float inv_keep;
     __host__ __device__ __forceinline__ float operator()(uint64_t idx) const {
-        return thresh == 0 ? 1.0f : dropout_scale(seed, stream, idx, thresh, inv_keep);
+        if (thresh == 0) return 1.0f;
+#ifdef __CUDA_ARCH__
+        const uint64_t s = seed_dev ? seed + __ldg(seed_dev) : seed;
+#else
+        const uint64_t s = seed;
+#endif
+        return dropout_scale(s, stream, idx, thresh, inv_keep);
     }
 };
+// process-wide device seed offset (sd_set_dropout_seed_offset); defined in elementwise.cu
+extern const unsigned long long* g_dropout_seed_dev;
 static inline Dropout make_dropout(float p, uint64_t seed, uint32_t stream) {
     Dropout d;
     d.seed = seed;
+    d.seed_dev = g_dropout_seed_dev;
     d.stream = stream;
     d.thresh = (p > 0.f) ? dropout_threshold(p) : 0u;
     d.inv_keep = (p > 0.f) ? 1.0f / (1.0f - p) : 1.0f;

@@ -386,6 +386,65 @@ extern "C" int sd_dropout_mask(float* out, long long n, float p, unsigned long l
 }
 
 // ------------------------------------------------------------------------------------------
+namespace sd { const unsigned long long* g_dropout_seed_dev = nullptr; }
+
+extern "C" int sd_set_dropout_seed_offset(const unsigned long long* device_counter) {
+    sd::g_dropout_seed_dev = device_counter;
+    return SD_OK;
+}
+
+// AdamW with every hyper-parameter read from device memory: hp = {lr, beta1, beta2, eps, weight_decay, step_size,
+// inv_sqrt_bc2, grad_scale} (step_size = lr / (1 - beta1^t), inv_sqrt_bc2 = 1/sqrt(1 - beta2^t)).  Lets the
+// optimizer launch live inside a captured CUDA graph while the learning-rate schedule advances on the host.
+__global__ void adamw_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, long long n, const float* __restrict__ hp) {
+    const float lr = hp[0], b1 = hp[1], b2 = hp[2], eps = hp[3], wd = hp[4], step_size = hp[5], inv_sqrt_bc2 = hp[6],
+                gscale = hp[7];
+    const long long n4 = n >> 2;
+    const float decay = 1.0f - lr * wd;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 P = reinterpret_cast<float4*>(p)[i];
+        const float4 G = reinterpret_cast<const float4*>(g)[i];
+        float4 M = reinterpret_cast<float4*>(m)[i];
+        float4 V = reinterpret_cast<float4*>(v)[i];
+#define SD_ADAM2(c)                                                      \
+    {                                                                    \
+        const float gg = G.c * gscale;                                   \
+        P.c *= decay;                                                    \
+        M.c = b1 * M.c + (1.0f - b1) * gg;                               \
+        V.c = b2 * V.c + (1.0f - b2) * gg * gg;                          \
+        P.c -= step_size * (M.c / (sqrtf(V.c) * inv_sqrt_bc2 + eps));    \
+    }
+        SD_ADAM2(x) SD_ADAM2(y) SD_ADAM2(z) SD_ADAM2(w)
+        reinterpret_cast<float4*>(p)[i] = P;
+        reinterpret_cast<float4*>(m)[i] = M;
+        reinterpret_cast<float4*>(v)[i] = V;
+    }
+    const long long base = n4 << 2;
+    for (long long i = base + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float gg = g[i] * gscale;
+        float P = p[i] * decay;
+        const float M = b1 * m[i] + (1.0f - b1) * gg;
+        const float V = b2 * v[i] + (1.0f - b2) * gg * gg;
+        P -= step_size * (M / (sqrtf(V) * inv_sqrt_bc2 + eps));
+        p[i] = P;
+        m[i] = M;
+        v[i] = V;
+    }
+}
+extern "C" int sd_adamw_step_dev(float* p, const float* g, float* m, float* v, long long n, const float* hyper_dev,
+                                 void* stream) {
+    if (n <= 0) return SD_OK;
+    if (!p || !g || !m || !v || !hyper_dev) return SD_ERR_BAD_ARG;
+    if ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) != 0) return SD_ERR_BAD_ARG;
+    const int threads = 256;
+    const int blocks = min(ceil_div((n + 3) / 4, threads), 148 * 8);
+    adamw_dev_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(p, g, m, v, n, hyper_dev);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+}
+
 extern "C" int sd_abi_version(void) { return SD_B200_ABI_VERSION; }
 
 extern "C" const char* sd_error_string(int code) {

@@ -1,0 +1,77 @@
+"""The training-loop body (ml/training/train.py:193-240) captured ONCE as a CUDA graph and replayed.
+
+Per iteration the host copies the batch into static device buffers, uploads eight optimizer scalars, launches ONE graph
+(≈ 1000 kernels: context encoders, trunk, denoiser, loss, backward, gradient all-reduce, AdamW) and steps the
+learning-rate schedule.  What changes between replays lives in device memory: the batch, torch's Philox state
+(timesteps, noise), the dropout seed counter (``runtime.device_seed_counter``) and the optimizer hyper-parameters
+(``FusedAdamW.prepare_captured_step``).
+"""
+from __future__ import annotations
+
+import torch
+
+from soccerdiffusion_b200 import ops, runtime
+from soccerdiffusion_b200.functional import mse_loss
+from soccerdiffusion_b200.ml.training.step import allreduce_gradients, q_sample
+
+
+class GraphedTrainStep:
+    def __init__(self, model, optimizer, scheduler, example_batch: dict, *, lr_scheduler=None, data_parallel: bool = False,
+                 group=None, decoder_pretraining: bool = False, warmup_steps: int = 3, noise=None, timesteps=None):
+        self.model, self.opt, self.sch, self.lrs = model, optimizer, scheduler, lr_scheduler
+        self.dp, self.group, self.pretrain = data_parallel, group, decoder_pretraining
+        self.static = {k: v.clone() for k, v in example_batch.items()}
+        self.fixed_noise, self.fixed_t = noise, timesteps   # parity tests pin the RNG inputs
+        self.seed_counter = runtime.device_seed_counter(next(model.parameters()).device)
+        self.launches_per_replay = 0
+        # warm-up on a side stream: allocations, cuDNN autotuning, lazy kernel attributes, NCCL communicators
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup_steps):
+                self.opt.prepare_captured_step()
+                self._body()
+                if self.lrs is not None:
+                    self.lrs.step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.opt.prepare_captured_step()
+        n0 = ops.launches()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._body()
+        self.launches_per_replay = ops.launches() - n0
+        self.opt.rollback_captured_step()      # the capture executed nothing: undo its step-counter increment
+        self.warmup_steps = warmup_steps       # optimizer steps already taken on ``example_batch``
+
+    def _body(self):
+        b = self.static
+        jt = b["joint_command"]
+        bs, dev = jt.size(0), jt.device
+        self.seed_counter.add_(1)
+        self.opt.zero_grad()
+        t = self.fixed_t if self.fixed_t is not None else torch.randint(0, self.sch.config["num_train_timesteps"], (bs,), device=dev)
+        noise = self.fixed_noise if self.fixed_noise is not None else torch.randn(jt.shape, device=dev, dtype=torch.float32)
+        noisy = q_sample(self.sch, self.model, jt, noise, t)
+        if self.pretrain:
+            ctx = torch.randn((bs, 10, self.model.hidden_dim), device=dev)
+            pred = self.model.forward_with_context([ctx], noisy, t)
+        else:
+            pred = self.model(b, noisy, t)
+        loss = mse_loss(pred, noise)
+        loss.backward()
+        if self.dp:
+            allreduce_gradients(self.opt, self.group)
+        self.opt.step_captured()
+        return loss.detach()
+
+    def __call__(self, batch: dict) -> torch.Tensor:
+        """One training iteration on ``batch`` (device tensors); returns the (static) loss tensor."""
+        for k, v in self.static.items():
+            v.copy_(batch[k], non_blocking=True)
+        self.opt.prepare_captured_step()
+        self.graph.replay()
+        ops._count(self.launches_per_replay)
+        if self.lrs is not None:
+            self.lrs.step()
+        return self.loss

@@ -103,6 +103,42 @@ class FusedAdamW(torch.optim.Optimizer):
                 self.state[p]["step"] = torch.tensor(float(f["step"]))
         return loss
 
+    # ---- CUDA-graph friendly stepping: hyper-parameters travel through device memory ------------------------
+    def prepare_captured_step(self):
+        """Host side of one step (call BEFORE replaying a graph that contains ``step_captured``): advances the step
+        counters and uploads {lr, betas, eps, wd, bias corrections} of every group (async, current stream)."""
+        for group, f in zip(self.param_groups, self._flat):
+            if f is None:
+                continue
+            if "hp_host" not in f:
+                f["hp_host"] = torch.empty(8, dtype=torch.float32).pin_memory()
+                f["hp_dev"] = torch.empty(8, dtype=torch.float32, device=f["p"].device)
+            f["step"] += 1
+            b1, b2 = group["betas"]
+            t = f["step"]
+            bc1 = 1.0 - float(b1) ** t
+            bc2 = 1.0 - float(b2) ** t
+            hp = f["hp_host"]
+            hp[0], hp[1], hp[2], hp[3], hp[4] = float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"])
+            hp[5], hp[6], hp[7] = float(group["lr"]) / bc1, 1.0 / (bc2 ** 0.5), 1.0
+            f["hp_dev"].copy_(hp, non_blocking=True)
+
+    def rollback_captured_step(self):
+        for f in self._flat:
+            if f is not None:
+                f["step"] -= 1
+
+    @torch.no_grad()
+    def step_captured(self):
+        """Device side: one sd_adamw_step_dev launch per group (this is what a CUDA graph captures)."""
+        for f in self._flat:
+            if f is None:
+                continue
+            if "hp_dev" not in f:
+                raise RuntimeError("call prepare_captured_step() once before capturing step_captured()")
+            self._gather_stray_grads(f)
+            ops.adamw_step_dev(f["p"], f["g"], f["m"], f["v"], f["hp_dev"])
+
     # torch's loader would replace the state tensors by copies; keep the flat views instead
     def load_state_dict(self, state_dict):
         groups = state_dict["param_groups"]

@@ -212,6 +212,19 @@ def adamw_step(p, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale=1.0):
     _count()
 
 
+def adamw_step_dev(p, g, m, v, hyper_dev):
+    with _Timed("adamw", 0.0, 28.0 * p.numel()):
+        check(_lib.lib().sd_adamw_step_dev(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(),
+                                           hyper_dev.data_ptr(), stream_ptr()), "sd_adamw_step_dev")
+    _count()
+
+
+def set_dropout_seed_offset(counter):
+    """counter: 1-element int64/uint64 CUDA tensor (kept alive by the caller) or None."""
+    check(_lib.lib().sd_set_dropout_seed_offset(None if counter is None else counter.data_ptr()),
+          "sd_set_dropout_seed_offset")
+
+
 def gather_rows(table, idx, out, ld_out, err_flag=None):
     B, d = idx.numel(), table.shape[1]
     check(_lib.lib().sd_gather_rows(table.data_ptr(), idx.data_ptr(), table.shape[0],

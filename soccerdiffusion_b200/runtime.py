@@ -71,6 +71,19 @@ def set_dropout(p: float):
     DROPOUT_P = float(p)
 
 
+_seed_counter = None
+
+
+def device_seed_counter(device=None):
+    """Creates (once) and registers the device-resident dropout seed offset; ``counter.add_(1)`` inside a captured
+    training step gives every graph replay fresh dropout masks."""
+    global _seed_counter
+    if _seed_counter is None:
+        _seed_counter = torch.zeros(1, dtype=torch.int64, device=device or "cuda")
+        ops.set_dropout_seed_offset(_seed_counter)
+    return _seed_counter
+
+
 def make_cfg(training: bool, dropout_p: float | None = None):
     from .functional import RunCfg
 

@@ -376,3 +376,51 @@ def test_bf16_mode_inference_and_training_within_2e_2(manifest, case):
     finally:
         sdb.set_precision("fp32")
         runtime.set_dropout(0.1)
+
+
+def test_graphed_train_step_matches_eager_steps():
+    """The CUDA-graph replayed training step (device-side optimizer hyper-parameters, static buffers) follows the
+    eager train_step exactly when RNG inputs are pinned and dropout is off; with dropout on, replays draw new masks."""
+    from soccerdiffusion_b200 import runtime
+    from soccerdiffusion_b200.dataset.pytorch import Normalizer
+    from soccerdiffusion_b200.ml.training import FusedAdamW, GraphedTrainStep, train_step
+    from soccerdiffusion_b200.schedulers import DDIMScheduler
+
+    hp = synth.PATCH_HP
+    B, seed = 4, 21
+    noise = synth.synth_noise("eps", hp, B, seed).cuda()
+    t = synth.synth_timesteps(B, seed).cuda()
+    batches = [to_dev(synth.synth_batch(hp, B, seed + i)) for i in range(4)]
+    sch = DDIMScheduler(beta_schedule="squaredcos_cap_v2", clip_sample=False)
+    sch.config["num_train_timesteps"] = 1000
+    runtime.set_dropout(0.0)
+    # eager
+    m1, _ = synth_model(hp, seed)
+    m1.train()
+    o1 = FusedAdamW(m1.parameters(), lr=1e-3)
+    l1 = torch.optim.lr_scheduler.OneCycleLR(o1, max_lr=1e-3, total_steps=20)
+    n1 = Normalizer(m1.mean, m1.std)
+    eager = []
+    for b in [batches[0]] * 3 + batches[1:]:
+        eager.append(train_step(m1, o1, sch, n1, b, lr_scheduler=l1, noise=noise, timesteps=t).item())
+    # graphed: 3 warm-up steps on batches[0] inside the constructor, then replays
+    m2, _ = synth_model(hp, seed)
+    m2.train()
+    o2 = FusedAdamW(m2.parameters(), lr=1e-3)
+    l2 = torch.optim.lr_scheduler.OneCycleLR(o2, max_lr=1e-3, total_steps=20)
+    g = GraphedTrainStep(m2, o2, sch, batches[0], lr_scheduler=l2, warmup_steps=3, noise=noise, timesteps=t)
+    got = [g(b).item() for b in batches[1:]]
+    for a, b_ in zip(got, eager[3:]):
+        assert abs(a - b_) < 1e-5 * abs(b_), (got, eager)
+    for (n, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert rel(p2, p1) < 1e-5, n
+    assert o2.param_groups[0]["lr"] == pytest.approx(o1.param_groups[0]["lr"], rel=1e-12)
+    assert g.launches_per_replay > 50
+    # dropout on: two replays on the same batch give different losses (fresh masks from the device seed counter)
+    runtime.set_dropout(0.1)
+    m3, _ = synth_model(hp, seed)
+    m3.train()
+    o3 = FusedAdamW(m3.parameters(), lr=0.0)
+    g3 = GraphedTrainStep(m3, o3, sch, batches[0], warmup_steps=1, noise=noise, timesteps=t)
+    la, lb = g3(batches[0]).item(), g3(batches[0]).item()
+    assert la != lb
