@@ -327,14 +327,15 @@ __global__ void __launch_bounds__(kT) maxpool_bwd_kernel(const uint4* __restrict
                 if (tdx < 0 || tdx > 2) continue;
                 const long long q = (((long long)n * HO + ho) * WO + wo) * CV + cv;
                 const uint2 pk = idx[q];
+                // packed byte compare: 0xFF in every byte (channel) whose arg-max tap is this pixel
+                const unsigned tap4 = (unsigned)(tdy * 3 + tdx) * 0x01010101u;
+                const unsigned mlo = __vcmpeq4(pk.x, tap4), mhi = __vcmpeq4(pk.y, tap4);
+                if ((mlo | mhi) == 0u) continue;
                 float g[8];
                 unpack8(dy[q], g);
-                const unsigned tap = (unsigned)(tdy * 3 + tdx);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const unsigned b = ((i < 4 ? pk.x : pk.y) >> (8 * (i & 3))) & 0xFFu;
-                    if (b == tap) acc[i] += g[i];
-                }
+                for (int i = 0; i < 8; ++i)
+                    if (((i < 4 ? mlo : mhi) >> (8 * (i & 3))) & 1u) acc[i] += g[i];
             }
         }
         dx[o] = pack8(acc);

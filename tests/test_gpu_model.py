@@ -413,7 +413,9 @@ def test_graphed_train_step_matches_eager_steps():
     for a, b_ in zip(got, eager[3:]):
         assert abs(a - b_) < 1e-5 * abs(b_), (got, eager)
     for (n, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
-        assert rel(p2, p1) < 1e-4, n   # bias corrections: float32 on the host vs double in sd_adamw_step
+        # bias corrections are float32 on the host vs double inside sd_adamw_step, and Adam's m/sqrt(v) amplifies
+        # rounding on near-zero gradients: compare absolutely (the updates themselves are ~lr = 1e-3 per step)
+        assert (p2 - p1).abs().max().item() < 5e-5, n
     assert o2.param_groups[0]["lr"] == pytest.approx(o1.param_groups[0]["lr"], rel=1e-12)
     assert g.launches_per_replay > 50
     # dropout on: two replays on the same batch give different losses (fresh masks from the device seed counter)
@@ -424,3 +426,56 @@ def test_graphed_train_step_matches_eager_steps():
     g3 = GraphedTrainStep(m3, o3, sch, batches[0], warmup_steps=1, noise=noise, timesteps=t)
     la, lb = g3(batches[0]).item(), g3(batches[0]).item()
     assert la != lb
+
+
+def test_distill_step_matches_oracle():
+    """distill.py:160-205: teacher 30-step DDIM under no_grad (persistent sampler), student one step at float t=0."""
+    from soccerdiffusion_b200 import runtime
+    from soccerdiffusion_b200.ml.training import FusedAdamW, distill_step
+    from soccerdiffusion_b200.schedulers import DDIMScheduler
+
+    runtime.set_dropout(0.0)
+    hp = synth.PATCH_HP
+    B = 3
+    teacher, sd_t = synth_model(hp, 31)
+    student, sd_s = synth_model(hp, 32)
+    student.train()
+    batch = synth.synth_batch(hp, B, 33)
+    noise = synth.synth_noise("x_T", hp, B, 33)
+    sch = DDIMScheduler(beta_schedule="squaredcos_cap_v2", clip_sample=False)
+    opt = FusedAdamW(student.parameters(), lr=0.0)   # lr 0: parameters unchanged, loss comparable
+    loss = distill_step(teacher, student, opt, sch, to_dev(batch), 30, noise=noise.cuda())
+    with torch.no_grad():
+        ctx = model_ref.encode_input_data(batch, sd_t, hp)
+        traj, _ = model_ref.sample_ddim(ctx, noise, sd_t, hp, 30)
+        pred = model_ref.forward_with_context(ctx, noise, torch.zeros(B), sd_s, hp)
+        want = torch.nn.functional.mse_loss(pred, traj)
+    assert abs(loss.item() - want.item()) < 2e-4 * abs(want.item())
+
+
+def test_scaled_up_config_forward_and_batched_sampler():
+    """BASELINE.json configs[4]: 2x depth, 20 image frames, T=20 -> M=322 memory tokens.  Checked
+    without the image branch's trunk (image tokens given as a foreign context would change M), at small batch."""
+    from soccerdiffusion_b200.schedulers import DDIMScheduler
+
+    hp = dict(synth.SCALED_HP, use_images=False)
+    B, seed = 3, 41
+    model, sd = synth_model(hp, seed)
+    model.eval()
+    batch = synth.synth_batch(hp, B, seed)
+    x_T = synth.synth_noise("x_T", hp, B, seed)
+    t = synth.synth_timesteps(B, seed)
+    with torch.no_grad():
+        ctx = model.encode_input_data(to_dev(batch))
+        eps = model.forward_with_context(ctx, x_T.cuda(), t.cuda())
+        want_ctx = model_ref.encode_input_data(batch, sd, hp)
+        want = model_ref.forward_with_context(want_ctx, x_T, t, sd, hp)
+    assert eps.shape == (B, 20, 20)
+    assert rel(eps, want) < TOL
+    sch = DDIMScheduler(beta_schedule="squaredcos_cap_v2", clip_sample=False)
+    sch.set_timesteps(10)
+    x0 = model.sample(ctx, x_T.cuda(), sch)          # T=20: single-CTA persistent kernel
+    with torch.no_grad():
+        w0, _ = model_ref.sample_ddim(want_ctx, x_T, sd, hp, 10)
+    assert rel(x0, w0) < TOL
+    assert model.last_sampler == "cta"
