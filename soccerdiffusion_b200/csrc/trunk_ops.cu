@@ -303,42 +303,51 @@ __global__ void __launch_bounds__(kT) maxpool_fwd_kernel(const uint4* __restrict
     }
 }
 
+// one CTA per input row (n, h): the two candidate window rows are uniform for the CTA, the per-thread index math is
+// shifts (CVT = compile-time channel-vector count; 0 = run time)
+template <int CVT>
 __global__ void __launch_bounds__(kT) maxpool_bwd_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx,
-                                                         uint4* __restrict__ dx, int N, int H, int W, int CV, int HO,
+                                                         uint4* __restrict__ dx, int N, int H, int W, int CVr, int HO,
                                                          int WO) {
-    const long long total = (long long)N * H * W * CV;
-    for (long long o = (long long)blockIdx.x * kT + threadIdx.x; o < total; o += (long long)gridDim.x * kT) {
-        const int cv = (int)(o % CV);
-        long long r = o / CV;
-        const int w = (int)(r % W); r /= W;
-        const int h = (int)(r % H);
-        const int n = (int)(r / H);
-        float acc[8];
+    const int CV = CVT ? CVT : CVr;
+    const long long nrows = (long long)N * H;
+    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int n = (int)(row / H), h = (int)(row - (long long)n * H);
+        // window rows containing h: ho = h/2 (tap row h - (2ho-1) in {1,2}) and ho = (h+1)/2 when different (tap row 0)
+        const int hoA = h >> 1, hoB = (h + 1) >> 1;
+        const bool useA = hoA < HO, useB = hoB != hoA && hoB < HO;
+        const int tdyA = h - (2 * hoA - 1), tdyB = h - (2 * hoB - 1);
+        for (int i = threadIdx.x; i < W * CV; i += kT) {
+            const int cv = CVT ? (i % CVT) : (i % CV);
+            const int w = CVT ? (i / CVT) : (i / CV);
+            const int woA = w >> 1, woB = (w + 1) >> 1;
+            const bool wA = woA < WO, wB = woB != woA && woB < WO;
+            const int tdxA = w - (2 * woA - 1), tdxB = w - (2 * woB - 1);
+            float acc[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        // windows (ho, wo) with 2*ho-1 <= h <= 2*ho+1
-        const int ho0 = max(0, (h) / 2), ho1 = min(HO - 1, (h + 1) / 2);
-        const int wo0 = max(0, (w) / 2), wo1 = min(WO - 1, (w + 1) / 2);
-        for (int ho = ho0; ho <= ho1; ++ho) {
-            const int tdy = h - (2 * ho - 1);
-            if (tdy < 0 || tdy > 2) continue;
-            for (int wo = wo0; wo <= wo1; ++wo) {
-                const int tdx = w - (2 * wo - 1);
-                if (tdx < 0 || tdx > 2) continue;
-                const long long q = (((long long)n * HO + ho) * WO + wo) * CV + cv;
-                const uint2 pk = idx[q];
-                // packed byte compare: 0xFF in every byte (channel) whose arg-max tap is this pixel
-                const unsigned tap4 = (unsigned)(tdy * 3 + tdx) * 0x01010101u;
-                const unsigned mlo = __vcmpeq4(pk.x, tap4), mhi = __vcmpeq4(pk.y, tap4);
-                if ((mlo | mhi) == 0u) continue;
-                float g[8];
-                unpack8(dy[q], g);
+            for (int k = 0; k < 8; ++k) acc[k] = 0.f;
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (((i < 4 ? mlo : mhi) >> (8 * (i & 3))) & 1u) acc[i] += g[i];
+            for (int a = 0; a < 2; ++a) {
+                if (!(a ? useB : useA)) continue;
+                const int ho = a ? hoB : hoA, tdy = a ? tdyB : tdyA;
+#pragma unroll
+                for (int b2 = 0; b2 < 2; ++b2) {
+                    if (!(b2 ? wB : wA)) continue;
+                    const int wo = b2 ? woB : woA, tdx = b2 ? tdxB : tdxA;
+                    const long long q = (((long long)n * HO + ho) * WO + wo) * CV + cv;
+                    const uint2 pk = idx[q];
+                    float g[8];
+                    unpack8(dy[q], g);
+                    const unsigned tap = (unsigned)(tdy * 3 + tdx);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const unsigned bsel = ((k < 4 ? pk.x : pk.y) >> (8 * (k & 3))) & 0xFFu;
+                        if (bsel == tap) acc[k] += g[k];
+                    }
+                }
             }
+            dx[(row * W + w) * CV + cv] = pack8(acc);
         }
-        dx[o] = pack8(acc);
     }
 }
 
@@ -346,12 +355,14 @@ __global__ void __launch_bounds__(kT) maxpool_bwd_kernel(const uint4* __restrict
 // The normalised/activated 112x112 map (the largest tensor of the network) is never written: the forward reads
 // the convolution output once and writes the pooled map + arg-max taps; the backward recomputes the ReLU mask from
 // x and gathers the pooled gradient, once for the per-channel reductions and once to write dx.
+template <int CVT>
 __global__ void __launch_bounds__(kT) stem_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ mean,
                                                       const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                       const float* __restrict__ beta, uint4* __restrict__ y,
-                                                      uint2* __restrict__ idx, int N, int H, int W, int CV, int HO, int WO) {
-    const long long total = (long long)N * HO * WO * CV;
-    const int cv = threadIdx.x % CV;   // (gridDim.x * kT) % CV == 0
+                                                      uint2* __restrict__ idx, int N, int H, int W, int CVr, int HO, int WO) {
+    // one CTA per output row (n, ho); requires kT % CV == 0 so that a thread keeps its channel group
+    const int CV = CVT ? CVT : CVr;
+    const int cv = threadIdx.x % CV;
     float sc[8], sh[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -359,37 +370,39 @@ __global__ void __launch_bounds__(kT) stem_fwd_kernel(const uint4* __restrict__ 
         sc[i] = invstd[c] * gamma[c];
         sh[i] = beta[c] - mean[c] * sc[i];
     }
-    for (long long o = (long long)blockIdx.x * kT + threadIdx.x; o < total; o += (long long)gridDim.x * kT) {
-        long long r = o / CV;
-        const int wo = (int)(r % WO); r /= WO;
-        const int ho = (int)(r % HO);
-        const int n = (int)(r / HO);
-        float best[8];
-        unsigned char bi[8];
+    const long long nrows = (long long)N * HO;
+    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int n = (int)(row / HO), ho = (int)(row - (long long)n * HO);
+        for (int i = threadIdx.x; i < WO * CV; i += kT) {
+            const int wo = CVT ? (i / CVT) : (i / CV);
+            float best[8];
+            unsigned char bi[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; bi[i] = 0; }
+            for (int k = 0; k < 8; ++k) { best[k] = -INFINITY; bi[k] = 0; }
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-            const int h = 2 * ho - 1 + dy;
-            if (h < 0 || h >= H) continue;
+            for (int dy = 0; dy < 3; ++dy) {
+                const int h = 2 * ho - 1 + dy;
+                if (h < 0 || h >= H) continue;
 #pragma unroll
-            for (int dxx = 0; dxx < 3; ++dxx) {
-                const int w = 2 * wo - 1 + dxx;
-                if (w < 0 || w >= W) continue;
-                float f[8];
-                unpack8(x[(((long long)n * H + h) * W + w) * CV + cv], f);
+                for (int dxx = 0; dxx < 3; ++dxx) {
+                    const int w = 2 * wo - 1 + dxx;
+                    if (w < 0 || w >= W) continue;
+                    float f[8];
+                    unpack8(x[(((long long)n * H + h) * W + w) * CV + cv], f);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float a = fmaxf(fmaf(f[i], sc[i], sh[i]), 0.f);
-                    if (a > best[i]) { best[i] = a; bi[i] = (unsigned char)(dy * 3 + dxx); }
+                    for (int k = 0; k < 8; ++k) {
+                        const float a = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f);
+                        if (a > best[k]) { best[k] = a; bi[k] = (unsigned char)(dy * 3 + dxx); }
+                    }
                 }
             }
+            const long long o = (row * WO + wo) * CV + cv;
+            y[o] = pack8(best);
+            uint2 pk;
+            pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+            pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+            idx[o] = pk;
         }
-        y[o] = pack8(best);
-        uint2 pk;
-        pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
-        pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
-        idx[o] = pk;
     }
 }
 
@@ -591,8 +604,14 @@ extern "C" int sd_maxpool3x3s2_nhwc_bf16_bwd(const void* dy, const void* idx, vo
     if (!dy || !idx || !dx || C % 8 != 0) return SD_ERR_BAD_ARG;
     const int HO = (H + 2 - 3) / 2 + 1, WO = (W + 2 - 3) / 2 + 1;
     const long long total = (long long)N * H * W * (C / 8);
-    maxpool_bwd_kernel<<<stream_grid(total), kT, 0, (cudaStream_t)stream>>>((const uint4*)dy, (const uint2*)idx, (uint4*)dx, N,
-                                                                           H, W, C / 8, HO, WO);
+    (void)total;
+    const int grid = (int)min((long long)148 * 16, (long long)N * H);
+    if (C == 64)
+        maxpool_bwd_kernel<8><<<grid, kT, 0, (cudaStream_t)stream>>>((const uint4*)dy, (const uint2*)idx, (uint4*)dx, N, H, W,
+                                                                     C / 8, HO, WO);
+    else
+        maxpool_bwd_kernel<0><<<grid, kT, 0, (cudaStream_t)stream>>>((const uint4*)dy, (const uint2*)idx, (uint4*)dx, N, H, W,
+                                                                     C / 8, HO, WO);
     SD_LAUNCH_CHECK();
     return SD_OK;
 }
@@ -604,8 +623,14 @@ extern "C" int sd_stem_bn_relu_pool_nhwc_bf16_fwd(const void* x, const float* me
     if (!x || !mean || !invstd || !gamma || !beta || !y || !idx || !ok_c(C)) return SD_ERR_BAD_ARG;
     const int HO = (H + 2 - 3) / 2 + 1, WO = (W + 2 - 3) / 2 + 1;
     const long long total = (long long)N * HO * WO * (C / 8);
-    stem_fwd_kernel<<<stream_grid(total), kT, 0, (cudaStream_t)stream>>>((const uint4*)x, mean, invstd, gamma, beta, (uint4*)y,
-                                                                        (uint2*)idx, N, H, W, C / 8, HO, WO);
+    (void)total;
+    const int grid = (int)min((long long)148 * 16, (long long)N * HO);
+    if (C == 64)
+        stem_fwd_kernel<8><<<grid, kT, 0, (cudaStream_t)stream>>>((const uint4*)x, mean, invstd, gamma, beta, (uint4*)y,
+                                                                  (uint2*)idx, N, H, W, C / 8, HO, WO);
+    else
+        stem_fwd_kernel<0><<<grid, kT, 0, (cudaStream_t)stream>>>((const uint4*)x, mean, invstd, gamma, beta, (uint4*)y,
+                                                                  (uint2*)idx, N, H, W, C / 8, HO, WO);
     SD_LAUNCH_CHECK();
     return SD_OK;
 }
