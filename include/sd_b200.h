@@ -93,6 +93,18 @@ int sd_attention_bwd(const float* Q, long long ldq, const float* K, long long ld
                      long long lddq, float* dK, long long lddk, float* dV, long long lddv, int B, int H, int T, int M,
                      int dh, float dropout_p, unsigned long long seed, unsigned int stream_id, void* stream);
 
+/* The same attention core on tcgen05 tensor cores (bf16 operands, fp32 accumulation in TMEM, fp32 softmax) for
+ * T <= 128, M <= 128, dh in {16,32,64}, 16-byte aligned pointers and strides that are multiples of 4: the bf16
+ * (2e-2) mode of the encoders' and the denoiser's self-attention.  sd_attention_tc_supported -> 1/0. */
+int sd_attention_tc_supported(int T, int M, int dh);
+int sd_attention_tc_fwd(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv,
+                        float* O, long long ldo, float* lse, int B, int H, int T, int M, int dh, float dropout_p,
+                        unsigned long long seed, unsigned int stream_id, void* stream);
+int sd_attention_tc_bwd(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv,
+                        const float* O, long long ldo, const float* dO, long long lddo, const float* lse, float* dQ,
+                        long long lddq, float* dK, long long lddk, float* dV, long long lddv, int B, int H, int T, int M,
+                        int dh, float dropout_p, unsigned long long seed, unsigned int stream_id, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Elementwise / scheduler kernels
  */

@@ -68,6 +68,10 @@ SIGNATURES = {
     "sd_attention_fwd": [c_f, c_ll, c_f, c_ll, c_f, c_ll, c_f, c_ll, c_f, c_i, c_i, c_i, c_i, c_i, c_fl, c_ull, c_u, c_f],
     "sd_attention_bwd": [c_f, c_ll, c_f, c_ll, c_f, c_ll, c_f, c_ll, c_f, c_ll, c_f, c_f, c_ll, c_f, c_ll, c_f, c_ll,
                          c_i, c_i, c_i, c_i, c_i, c_fl, c_ull, c_u, c_f],
+    "sd_attention_tc_supported": [c_i, c_i, c_i],
+    "sd_attention_tc_fwd": [c_f, c_ll, c_f, c_ll, c_f, c_ll, c_f, c_ll, c_f, c_i, c_i, c_i, c_i, c_i, c_fl, c_ull, c_u, c_f],
+    "sd_attention_tc_bwd": [c_f, c_ll, c_f, c_ll, c_f, c_ll, c_f, c_ll, c_f, c_ll, c_f, c_f, c_ll, c_f, c_ll, c_f, c_ll,
+                            c_i, c_i, c_i, c_i, c_i, c_fl, c_ull, c_u, c_f],
     "sd_step_token": [c_f, c_i, c_f, c_f, c_f, c_ll, c_i, c_i, c_f],
     "sd_step_token_bwd": [c_f, c_ll, c_i, c_i, c_f, c_f],
     "sd_q_sample": [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_i, c_i, c_i, c_f],

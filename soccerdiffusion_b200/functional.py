@@ -56,7 +56,7 @@ def _sa_fwd(x, B, T, H, in_w, in_b, out_w, out_b, n_w, n_b, cfg: RunCfg, site: i
     attn = _empty((M, d), x)
     lse = _empty((B, H, T), x) if save else None
     ops.attention_fwd(_p(qkv), 3 * d, _p(qkv, d), 3 * d, _p(qkv, 2 * d), 3 * d, _p(attn), d,
-                      None if lse is None else _p(lse), B, H, T, T, d // H, cfg.drop(site))
+                      None if lse is None else _p(lse), B, H, T, T, d // H, cfg.drop(site), cfg.precision)
     y = _empty((M, d), x)
     ops.gemm(attn, d, MK, out_w, d, NK, y, d, M, d, d, precision=cfg.precision, bias=out_b, dropout=cfg.drop(site + 1),
              residual=x, ldr=d)
@@ -75,7 +75,7 @@ def _sa_bwd(dy, saved, B, T, H, in_w, out_w, n_w, n_b, g_in_w, g_in_b, g_out_w, 
     ops.gemm(g1, d, MK, out_w, d, KN, dattn, d, M, d, d, precision=cfg.precision)
     dqkv = _empty((M, 3 * d), x)
     ops.attention_bwd(_p(qkv), 3 * d, _p(qkv, d), 3 * d, _p(qkv, 2 * d), 3 * d, _p(attn), d, _p(dattn), d, _p(lse),
-                      _p(dqkv), 3 * d, _p(dqkv, d), 3 * d, _p(dqkv, 2 * d), 3 * d, B, H, T, T, d // H, cfg.drop(site))
+                      _p(dqkv), 3 * d, _p(dqkv, d), 3 * d, _p(dqkv, 2 * d), 3 * d, B, H, T, T, d // H, cfg.drop(site), cfg.precision)
     ops.colsum_accum(dqkv, 3 * d, M, 3 * d, g_in_b)
     ops.gemm(dqkv, 3 * d, KM, x, d, KN, g_in_w, d, 3 * d, d, M, precision=cfg.precision, ln=(mean, rstd, n_w, n_b),
              accumulate=True)
@@ -134,7 +134,7 @@ def _ca_fwd(x, mem, B, T, Mm, H, in_w, in_b, out_w, out_b, n_w, n_b, cfg: RunCfg
     attn = _empty((Mq, d), x)
     lse = _empty((B, H, T), x) if save else None
     ops.attention_fwd(_p(q), d, _p(kv), 2 * d, _p(kv, d), 2 * d, _p(attn), d, None if lse is None else _p(lse), B, H, T,
-                      Mm, d // H, cfg.drop(site))
+                      Mm, d // H, cfg.drop(site), cfg.precision)
     y = _empty((Mq, d), x)
     ops.gemm(attn, d, MK, out_w, d, NK, y, d, Mq, d, d, precision=cfg.precision, bias=out_b, dropout=cfg.drop(site + 1),
              residual=x, ldr=d)
@@ -154,7 +154,7 @@ def _ca_bwd(dy, saved, mem, dmem, B, T, Mm, H, in_w, out_w, n_w, n_b, g_in_w, g_
     dq = _empty((Mq, d), x)
     dkv = _empty((B * Mm, 2 * d), x)
     ops.attention_bwd(_p(q), d, _p(kv), 2 * d, _p(kv, d), 2 * d, _p(attn), d, _p(dattn), d, _p(lse), _p(dq), d, _p(dkv),
-                      2 * d, _p(dkv, d), 2 * d, B, H, T, Mm, d // H, cfg.drop(site))
+                      2 * d, _p(dkv, d), 2 * d, B, H, T, Mm, d // H, cfg.drop(site), cfg.precision)
     # q projection (rows 0:d of in_proj) and k/v projection (rows d:3d)
     ops.colsum_accum(dq, d, Mq, d, g_in_b)
     ops.colsum_accum(dkv, 2 * d, B * Mm, 2 * d, _p(g_in_b, d))

@@ -135,20 +135,31 @@ def ln_bwd(g, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, M, d):
     _count()
 
 
-def attention_fwd(Q, ldq, K, ldk, V, ldv, O, ldo, lse, B, H, T, M, dh, dropout=None):
+def _attn_tc_ok(ptrs, lds, T, M, dh):
+    return (_lib.lib().sd_attention_tc_supported(T, M, dh) == 1 and all(p_ % 16 == 0 for p_ in ptrs)
+            and all(l % 4 == 0 for l in lds))
+
+
+def attention_fwd(Q, ldq, K, ldk, V, ldv, O, ldo, lse, B, H, T, M, dh, dropout=None, precision=PREC_FP32):
     p, seed, sid = dropout if dropout is not None else (0.0, 0, 0)
-    with _Timed("attention_fwd", 4.0 * B * H * T * M * dh, 4.0 * B * H * dh * (2 * T + 2 * M), f"[B{B} H{H} T{T} M{M} dh{dh}]"):
-        check(_lib.lib().sd_attention_fwd(Q, ldq, K, ldk, V, ldv, O, ldo, lse, B, H, T, M, dh, p, seed, sid,
-                                          stream_ptr()), "sd_attention_fwd")
+    tc = precision == PREC_BF16 and _attn_tc_ok((Q, K, V, O), (ldq, ldk, ldv, ldo), T, M, dh)
+    fn = _lib.lib().sd_attention_tc_fwd if tc else _lib.lib().sd_attention_fwd
+    with _Timed("tc_attention_fwd" if tc else "attention_fwd", 4.0 * B * H * T * M * dh, 4.0 * B * H * dh * (2 * T + 2 * M),
+                f"[B{B} H{H} T{T} M{M} dh{dh}]"):
+        check(fn(Q, ldq, K, ldk, V, ldv, O, ldo, lse, B, H, T, M, dh, p, seed, sid, stream_ptr()), "sd_attention_fwd")
     _count()
 
 
 def attention_bwd(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, dQ, lddq, dK, lddk, dV, lddv, B, H, T, M, dh,
-                  dropout=None):
+                  dropout=None, precision=PREC_FP32):
     p, seed, sid = dropout if dropout is not None else (0.0, 0, 0)
-    with _Timed("attention_bwd", 10.0 * B * H * T * M * dh, 4.0 * B * H * dh * (4 * T + 4 * M), f"[B{B} H{H} T{T} M{M} dh{dh}]"):
-        check(_lib.lib().sd_attention_bwd(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, dQ, lddq, dK, lddk, dV, lddv,
-                                          B, H, T, M, dh, p, seed, sid, stream_ptr()), "sd_attention_bwd")
+    tc = precision == PREC_BF16 and _attn_tc_ok((Q, K, V, O, dO, dQ, dK, dV), (ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv),
+                                                T, M, dh)
+    fn = _lib.lib().sd_attention_tc_bwd if tc else _lib.lib().sd_attention_bwd
+    with _Timed("tc_attention_bwd" if tc else "attention_bwd", 10.0 * B * H * T * M * dh, 4.0 * B * H * dh * (4 * T + 4 * M),
+                f"[B{B} H{H} T{T} M{M} dh{dh}]"):
+        check(fn(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, dQ, lddq, dK, lddk, dV, lddv, B, H, T, M, dh, p, seed, sid,
+                 stream_ptr()), "sd_attention_bwd")
     _count()
 
 

@@ -283,3 +283,34 @@ def test_tc_gemm_dgrad_wgrad(ops, M, N, K):
                  ln=(mean, rstd, gamma.cuda(), beta.cuda()), accumulate=True)
         xn = torch.nn.functional.layer_norm(X, (K,), gamma, beta, 1e-5)
         assert rel(dW, _bf(dY).T @ _bf(xn)) < 2e-3
+
+
+@pytest.mark.parametrize("B,H,T,M,dh", [(3, 4, 100, 100, 32), (2, 8, 10, 10, 16), (2, 4, 10, 10, 32), (1, 2, 128, 128, 64),
+                                         (2, 4, 7, 33, 32), (1, 4, 1, 1, 32)])
+def test_tc_attention_fwd_bwd(ops, B, H, T, M, dh):
+    """tcgen05 attention (bf16 operands): forward within bf16 rounding of the fp64 result, backward likewise; the
+    dropout masks are the exported ones."""
+    torch.manual_seed(B * 100 + T + M)
+    d = H * dh
+    p, seed, sid = 0.1, 4242, 3
+    q = torch.randn(B, T, d, dtype=torch.double, requires_grad=True)
+    k = torch.randn(B, M, d, dtype=torch.double, requires_grad=True)
+    v = torch.randn(B, M, d, dtype=torch.double, requires_grad=True)
+    go = torch.randn(B, T, d, dtype=torch.double)
+    mask = ops.dropout_mask(B * H * T * M, p, seed, sid, "cuda").view(B, H, T, M).cpu().double()
+    qh = q.view(B, T, H, dh).transpose(1, 2); kh = k.view(B, M, H, dh).transpose(1, 2); vh = v.view(B, M, H, dh).transpose(1, 2)
+    pr = torch.softmax(qh @ kh.transpose(-1, -2) / math.sqrt(dh), -1) * mask
+    o = (pr @ vh).transpose(1, 2).reshape(B, T, d)
+    (o * go).sum().backward()
+    qd, kd, vd = (t_.detach().float().cuda().contiguous() for t_ in (q, k, v))
+    od = torch.empty(B, T, d, device="cuda")
+    lse = torch.empty(B, H, T, device="cuda")
+    ops.attention_fwd(qd.data_ptr(), d, kd.data_ptr(), d, vd.data_ptr(), d, od.data_ptr(), d, lse.data_ptr(), B, H, T, M, dh,
+                      (p, seed, sid), precision=ops.PREC_BF16)
+    assert rel(od, o) < 1.5e-2
+    dq, dk, dv = torch.empty_like(qd), torch.empty_like(kd), torch.empty_like(vd)
+    god = go.float().cuda().contiguous()
+    ops.attention_bwd(qd.data_ptr(), d, kd.data_ptr(), d, vd.data_ptr(), d, od.data_ptr(), d, god.data_ptr(), d,
+                      lse.data_ptr(), dq.data_ptr(), d, dk.data_ptr(), d, dv.data_ptr(), d, B, H, T, M, dh, (p, seed, sid),
+                      precision=ops.PREC_BF16)
+    assert rel(dq, q.grad) < 2.5e-2 and rel(dk, k.grad) < 2.5e-2 and rel(dv, v.grad) < 2.5e-2
