@@ -118,6 +118,32 @@ def test_stem_pack_and_space_to_depth_conv_equal_conv1():
     assert rel(g1, conv.weight.grad) < 1e-2
 
 
+def test_fused_stem_backward_kernel_matches_two_kernel_path():
+    """sd_stem_bn_relu_pool_nhwc_bf16_bwd (single gather-fused backward, kept as an alternative) against the default
+    path (max-pool backward + BatchNorm backward with the recomputed ReLU mask)."""
+    from soccerdiffusion_b200 import ops
+    from soccerdiffusion_b200.ml.model.encoder.trunk import StemBNReLUPool
+
+    torch.manual_seed(3)
+    N, C, H, W = 2, 64, 40, 48
+    x = (_cl_bf16(N, C, H, W) * 1.2 + 0.1).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    gamma = (torch.rand(C, device="cuda") + 0.5).requires_grad_(True)
+    beta = (torch.randn(C, device="cuda") * 0.2).requires_grad_(True)
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    xg = x.clone().requires_grad_(True)
+    y = StemBNReLUPool.apply(xg, gamma, beta, rm, rv, True, 0.1, 1e-5)
+    go = _cl_bf16(*y.shape)
+    y.backward(go)
+    # the same backward through the fused kernel, from the tensors the forward saved
+    xs, idx, mean, invstd, g_, b_ = y.grad_fn.saved_tensors
+    sums = torch.empty(2 * C, device="cuda", dtype=torch.float64)
+    dx = torch.empty_like(xs)
+    dg, db = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    ops.stem_bwd(go, idx, xs, mean, invstd, g_, b_, sums, dx, dg, db, N, H, W, C)
+    assert rel(dx.float(), xg.grad.float()) < 1e-2
+    assert rel(dg, gamma.grad) < 1e-4 and rel(db, beta.grad) < 1e-4
+
+
 @pytest.mark.parametrize("N,H,W", [(4, 224, 224), (3, 20, 36), (2, 64, 96), (1, 6, 6)])
 def test_stem_wgrad_tcgen05_matches_cudnn(N, H, W):
     """conv1 weight gradient: tcgen05 kernel on the space-to-depth image vs aten.convolution_backward (7x7 form)."""
