@@ -225,7 +225,7 @@ int sd_plan_set_schedule(sd_plan* plan, int num_steps, const long long* timestep
 int sd_plan_set_context(sd_plan* plan, const float* ctx, int B, void* stream);
 /* x_T (B,T,J) -> x_0 (B,T,J); eps_trace optional (steps,B,T,J); denormalize: x*std+mean (ros.py:313) */
 int sd_plan_sample(sd_plan* plan, const float* x_T, float* x_out, float* eps_trace, int denormalize, void* stream);
-/* Sampler kernel selection: 0 = auto (cluster kernel for small batches when the device can co-schedule it),
+/* Sampler kernel selection: 0 = auto (cluster kernel for batches of <= 18 trajectories when the device can co-schedule it),
  * 1 = one CTA per trajectory, 2 = one 16-CTA thread-block cluster per trajectory (weights resident in the
  * cluster's shared memory, activations exchanged through distributed shared memory).  Env SD_B200_SAMPLER=
  * auto|cta|cluster sets the process default.  sd_plan_last_sampler: which one the last sd_plan_sample ran (1/2). */

@@ -1232,7 +1232,9 @@ int launch_cluster(sd_plan* p, SamplerArgs& a, cudaStream_t st, bool* launched) 
 int run_sampler(sd_plan* p, SamplerArgs& a, cudaStream_t st) {
     const int mode = p->sampler_mode != 0 ? p->sampler_mode : sampler_mode();
     p->last_sampler = 1;
-    if (a.tok_mode == 0 && mode != 1 && (mode == 2 || a.B <= 64)) {
+    // auto: ~9 clusters of 16 SMs run concurrently (3.3 ms per trajectory) vs 148 single-CTA trajectories (7.5 ms):
+    // the cluster kernel wins up to two waves of clusters
+    if (a.tok_mode == 0 && mode != 1 && (mode == 2 || a.B <= 18)) {
         bool launched = false;
         int rc = SD_OK;
         if (a.d == 128 && a.dh == 32 && a.T == 10) rc = launch_cluster<12, 128, 32, 10>(p, a, st, &launched);
