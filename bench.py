@@ -462,6 +462,25 @@ def ddim_latency(model, hp, dev, precision, reps=200):
             ts.sort()
             out[name + "_p50_ms"] = ts[len(ts) // 2]
             out[name + "_p99_ms"] = ts[min(len(ts) - 1, int(len(ts) * 0.99))]
+    # batched inference (BASELINE.json configs[4]: 512 independent trajectories on 8 GPUs = 64 per GPU, no collective)
+    with torch.no_grad():
+        ctx64 = [torch.randn(64, sum(c.shape[1] for c in ctx), hp["hidden_dim"], device=dev)]
+        x64 = torch.randn(64, hp["trajectory_prediction_length"], hp["num_joints"], device=dev)
+        for _ in range(3):
+            model.sample(ctx64, x64, sch, denormalize=True)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(20):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            model.sample(ctx64, x64, sch, denormalize=True)
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts.sort()
+        out["batched_bs64_p50_ms"] = ts[len(ts) // 2]
+        out["batched_bs64_trajectories_per_s"] = 64e3 / ts[len(ts) // 2]
+        out["batched_bs64_kernel"] = getattr(model, "last_sampler", "?")
     out["steps"] = 30
     out["algorithmic_gflop_per_trajectory"] = 2.97
     out["sampler_kernel"] = getattr(model, "last_sampler", "?")
