@@ -395,7 +395,13 @@ def run_ours(args):
             gpu_launches=launches, clocks=clk, roofline=roofline, kernel_classes=kernel_classes, cpu_baseline=cpu, ddim=ddim)
         emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        # all ranks leave together; a hard exit avoids tearing down NCCL communicators that captured CUDA graphs still
+        # reference (observed to hang in destroy_process_group)
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def _inscope_step(model, opt, sch, batch, img_tokens, lrs, dp):
