@@ -217,7 +217,7 @@ def run_ours(args):
     sd.set_precision(args.precision)
     peaks = load_peaks()
 
-    hp = dict(config.DEFAULT)
+    hp = dict(config.SCALED if args.config == "scaled" else config.DEFAULT)
     bs = args.batch
     torch.manual_seed(0)
     model = config.build_model(hp).to(dev)
@@ -384,7 +384,7 @@ def run_ours(args):
             metric=METRIC, value=gb * args.steps / (ms / 1e3), unit=UNIT, n_gpus=world, steps=args.steps,
             warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
             dtype="f32" if args.precision == "fp32" else "bf16", data="synthetic", impl="ours",
-            config=dict(workload={"full": "default.yaml full training step incl. ResNet18 trunk (trunk = cuDNN library call)",
+            config=dict(architecture=args.config, workload={"full": "default.yaml full training step incl. ResNet18 trunk (trunk = cuDNN library call)",
                                   "inscope": "default.yaml training step, image tokens precomputed (trunk outside the step)",
                                   "denoiser": "denoiser-only training step (train.py:221-224)"}[args.workload],
                         global_batch=gb, per_gpu_batch=bs, parallelism=f"dp{world}", dropout_p=0.1,
@@ -530,6 +530,8 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
     ap.add_argument("--cpu-batch", type=int, default=8, help="bounded CPU sample batch")
     ap.add_argument("--workload", default="full", choices=["full", "inscope", "denoiser"])
+    ap.add_argument("--config", default="default", choices=["default", "scaled"],
+                    help="default.yaml, or BASELINE.json configs[4]: 2x depth, 20 frames, T=20 (use a smaller --batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ddim", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
