@@ -1175,7 +1175,7 @@ template <int TR, int D, int DH, int TT>
 int launch_cluster(sd_plan* p, SamplerArgs& a, cudaStream_t st, bool* launched) {
     *launched = false;
     const int C = kClusterSize;
-    if (a.d % C != 0 || C % a.heads != 0 || a.T > 16 || a.T > TR || a.dh > kClThreads || a.dh % 4 != 0) return SD_OK;
+    if (a.d % C != 0 || C % a.heads != 0 || a.T > TR || a.T > 32 || a.dh > kClThreads || a.dh % 4 != 0) return SD_OK;
     // resident layers: as many as fit beside the working buffers
     int L_res = a.L;
     size_t bytes = 0;
@@ -1240,6 +1240,7 @@ int run_sampler(sd_plan* p, SamplerArgs& a, cudaStream_t st) {
         if (a.d == 128 && a.dh == 32 && a.T == 10) rc = launch_cluster<12, 128, 32, 10>(p, a, st, &launched);
         else if (a.T <= 12) rc = launch_cluster<12, 0, 0, 0>(p, a, st, &launched);
         else if (a.T <= 16) rc = launch_cluster<16, 0, 0, 0>(p, a, st, &launched);
+        else if (a.T <= 20) rc = launch_cluster<20, 0, 0, 0>(p, a, st, &launched);
         if (rc != SD_OK) return rc;
         if (launched) {
             p->last_sampler = 2;

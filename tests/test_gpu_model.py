@@ -477,8 +477,9 @@ def test_scaled_up_config_forward_and_batched_sampler():
     assert rel(eps, want) < TOL
     sch = DDIMScheduler(beta_schedule="squaredcos_cap_v2", clip_sample=False)
     sch.set_timesteps(10)
-    x0 = model.sample(ctx, x_T.cuda(), sch)          # T=20: single-CTA persistent kernel
     with torch.no_grad():
         w0, _ = model_ref.sample_ddim(want_ctx, x_T, sd, hp, 10)
-    assert rel(x0, w0) < TOL
-    assert model.last_sampler == "cta"
+    for kind in ("cta", "cluster"):                  # T=20, 8 layers: the cluster kernel keeps only some layers resident
+        x0 = model.sample(ctx, x_T.cuda(), sch, sampler=kind)
+        assert rel(x0, w0) < TOL, kind
+        assert model.last_sampler == kind
