@@ -171,15 +171,31 @@ def _ca_bwd(dy, saved, mem, dmem, B, T, Mm, H, in_w, out_w, n_w, n_b, g_in_w, g_
 
 
 def _zero_grads(params):
-    """One flat zeroed buffer viewed as per-parameter gradients."""
-    total = sum(p.numel() for p in params)
-    flat = torch.zeros(total, device=params[0].device, dtype=torch.float32)
-    views, off = [], 0
-    for p in params:
-        # keep every view 16-byte aligned for the vectorised paths
-        views.append(flat[off: off + p.numel()].view_as(p))
-        off += p.numel()
-    return views
+    """Gradient buffers of ``params``: (buffers the kernels accumulate into, what backward() hands to autograd).
+
+    Default: one flat zeroed buffer viewed per parameter, returned to autograd (which adds it into ``p.grad``).
+    With ``runtime.set_direct_grads(True)`` a leaf parameter whose ``.grad`` already exists (``FusedAdamW`` keeps them as
+    views of its flat, zeroed gradient buffer) is accumulated into IN PLACE and ``None`` is returned for it: the ~260
+    per-parameter ``add_`` launches of autograd's accumulation disappear.  (Gradient hooks on such parameters do not
+    fire in that mode — it is opt-in, used by the captured training step.)"""
+    from . import runtime
+
+    direct = runtime.direct_grads()
+    in_place = [direct and p.is_leaf and p.grad is not None and p.grad.dtype == torch.float32 and p.grad.is_contiguous()
+                and p.grad.shape == p.shape for p in params]
+    total = sum(p.numel() for p, ip in zip(params, in_place) if not ip)
+    flat = torch.zeros(max(total, 1), device=params[0].device, dtype=torch.float32)
+    bufs, rets, off = [], [], 0
+    for p, ip in zip(params, in_place):
+        if ip:
+            bufs.append(p.grad)
+            rets.append(None)
+        else:
+            v = flat[off: off + p.numel()].view_as(p)
+            off += p.numel()
+            bufs.append(v)
+            rets.append(v)
+    return bufs, rets
 
 
 # --------------------------------------------------------------------------------------------------
@@ -213,7 +229,7 @@ class EncoderStackFn(torch.autograd.Function):
         B, S, H, d, Kin, L = ctx.dims
         x_in, emb_w, emb_b, *layer_params = ctx.saved_tensors
         M = B * S
-        grads = _zero_grads([emb_w, emb_b, *layer_params])
+        grads, rets = _zero_grads([emb_w, emb_b, *layer_params])
         g_emb_w, g_emb_b, g_layers = grads[0], grads[1], grads[2:]
         dh = dy.contiguous().view(M, d)
         for l in reversed(range(L)):
@@ -233,7 +249,7 @@ class EncoderStackFn(torch.autograd.Function):
             ops.gemm(dh, d, MK, emb_w, Kin, KN, dx_in, Kin, M, Kin, d, precision=cfg.precision)
             dx_in = dx_in.view_as(x_in)
         ctx.acts = None
-        return (None, None, None, None, None, dx_in, g_emb_w, g_emb_b, *g_layers)
+        return (None, None, None, None, None, dx_in, *rets)
 
 
 class DenoiserFn(torch.autograd.Function):
@@ -271,7 +287,7 @@ class DenoiserFn(torch.autograd.Function):
         B, T, Mm, H, d, J, L = ctx.dims
         x2, mem2, emb_w, emb_b, fc_w, fc_b, *layer_params = ctx.saved_tensors
         Mq = B * T
-        grads = _zero_grads([emb_w, emb_b, fc_w, fc_b, *layer_params])
+        grads, rets = _zero_grads([emb_w, emb_b, fc_w, fc_b, *layer_params])
         g_emb_w, g_emb_b, g_fc_w, g_fc_b, g_layers = grads[0], grads[1], grads[2], grads[3], grads[4:]
         do = dout.contiguous().view(Mq, J)
         ops.colsum_accum(do, J, Mq, J, g_fc_b)
@@ -301,8 +317,7 @@ class DenoiserFn(torch.autograd.Function):
             dx = dx.view(B, T, J)
         ctx.acts = None
         ctx.h_last = None
-        return (None, None, None, None, None, None, dx, None if dmem is None else dmem.view(B, Mm, d), g_emb_w,
-                g_emb_b, g_fc_w, g_fc_b, *g_layers)
+        return (None, None, None, None, None, None, dx, None if dmem is None else dmem.view(B, Mm, d), *rets)
 
 
 class LinearFn(torch.autograd.Function):
@@ -315,24 +330,23 @@ class LinearFn(torch.autograd.Function):
         y = _empty((M, N), x)
         ops.gemm(x, K, MK, w, K, NK, y, N, M, N, K, precision=precision, bias=b)
         ctx.precision = precision
-        ctx.save_for_backward(x, w)
+        ctx.save_for_backward(x, w, b)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w = ctx.saved_tensors
+        x, w, b = ctx.saved_tensors
         M, K = x.shape
         N = w.shape[0]
         dy = dy.contiguous()
-        gw = torch.zeros_like(w)
-        gb = torch.zeros(N, device=w.device, dtype=torch.float32)
+        (gw, gb), (rw, rb) = _zero_grads([w, b])
         ops.colsum_accum(dy, N, M, N, gb)
         ops.gemm(dy, N, KM, x, K, KN, gw, K, N, K, M, precision=ctx.precision, accumulate=True)
         dx = None
         if ctx.needs_input_grad[1]:
             dx = _empty((M, K), x)
             ops.gemm(dy, N, MK, w, K, KN, dx, K, M, K, N, precision=ctx.precision)
-        return None, dx, gw, gb
+        return None, dx, rw, rb
 
 
 class AssembleContextFn(torch.autograd.Function):

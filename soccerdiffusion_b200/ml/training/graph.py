@@ -17,12 +17,14 @@ from soccerdiffusion_b200.ml.training.step import allreduce_gradients, q_sample
 
 class GraphedTrainStep:
     def __init__(self, model, optimizer, scheduler, example_batch: dict, *, lr_scheduler=None, data_parallel: bool = False,
-                 group=None, decoder_pretraining: bool = False, warmup_steps: int = 3, noise=None, timesteps=None):
+                 group=None, decoder_pretraining: bool = False, warmup_steps: int = 3, noise=None, timesteps=None,
+                 direct_grads: bool = True):
         self.model, self.opt, self.sch, self.lrs = model, optimizer, scheduler, lr_scheduler
         self.dp, self.group, self.pretrain = data_parallel, group, decoder_pretraining
         self.static = {k: v.clone() for k, v in example_batch.items()}
         self.fixed_noise, self.fixed_t = noise, timesteps   # parity tests pin the RNG inputs
         self.seed_counter = runtime.device_seed_counter(next(model.parameters()).device)
+        self.direct_grads = direct_grads
         self.launches_per_replay = 0
         # warm-up on a side stream: allocations, cuDNN autotuning, lazy kernel attributes, NCCL communicators
         side = torch.cuda.Stream()
@@ -59,7 +61,12 @@ class GraphedTrainStep:
         else:
             pred = self.model(b, noisy, t)
         loss = mse_loss(pred, noise)
-        loss.backward()
+        prev = runtime.direct_grads()
+        runtime.set_direct_grads(self.direct_grads)   # gradients land in FusedAdamW's flat buffer without autograd adds
+        try:
+            loss.backward()
+        finally:
+            runtime.set_direct_grads(prev)
         if self.dp:
             allreduce_gradients(self.opt, self.group)
         self.opt.step_captured()

@@ -71,6 +71,20 @@ def set_dropout(p: float):
     DROPOUT_P = float(p)
 
 
+_direct_grads = False
+
+
+def set_direct_grads(on: bool):
+    """Opt-in: backward passes accumulate parameter gradients straight into existing ``p.grad`` buffers (the flat views
+    of ``FusedAdamW``) instead of returning them to autograd; see functional._zero_grads."""
+    global _direct_grads
+    _direct_grads = bool(on)
+
+
+def direct_grads() -> bool:
+    return _direct_grads
+
+
 _seed_counter = None
 
 

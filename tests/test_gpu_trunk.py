@@ -133,9 +133,9 @@ def test_fused_stem_backward_kernel_matches_two_kernel_path():
     xg = x.clone().requires_grad_(True)
     y = StemBNReLUPool.apply(xg, gamma, beta, rm, rv, True, 0.1, 1e-5)
     go = _cl_bf16(*y.shape)
+    xs, idx, mean, invstd, g_, b_ = y.grad_fn.saved_tensors   # read before backward() frees them
     y.backward(go)
     # the same backward through the fused kernel, from the tensors the forward saved
-    xs, idx, mean, invstd, g_, b_ = y.grad_fn.saved_tensors
     sums = torch.empty(2 * C, device="cuda", dtype=torch.float64)
     dx = torch.empty_like(xs)
     dg, db = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
