@@ -177,6 +177,11 @@ int sd_stem_pack_s2d_bf16(const float* images, void* out, int N, int H, int W, v
  * column = output channel) from the packed image (sd_stem_pack_s2d_bf16) and dy bf16 NHWC (N,H/2,W/2,64); tcgen05,
  * both operands MN-major.  Replaces cuDNN's conv1 wgrad (ml/model/encoder/image.py:55-73 under autograd). */
 int sd_stem_wgrad_s2d_bf16(const void* xs2d, const void* dy, float* dw_s2d, int N, int H, int W, void* stream);
+/* Forward of the stem convolution on the packed image: y (N,H/2,W/2,64) bf16 NHWC; w_s2d[64][256] bf16 (row = output
+ * channel, column = kh*64 + kw*16 + ci).  TMA tensor map -> tcgen05, weights resident in shared memory, double-buffered
+ * TMEM accumulators.  Returns SD_E_UNSUPPORTED when W/2 is not a multiple of 8 in [8,128] or the driver has no tensor-map
+ * encoder (callers then use the library convolution). */
+int sd_stem_fprop_s2d_bf16(const void* xs2d, const void* w_s2d, void* y, int N, int H, int W, void* stream);
 /* Fused stem: maxpool3x3s2(relu(bn(x))) without materialising the activated 112x112 map; backward recomputes the
  * ReLU mask from x (torchvision ResNet stem bn1 -> relu -> maxpool). mean/invstd from sd_bn_stats_nhwc_bf16. */
 int sd_stem_bn_relu_pool_nhwc_bf16_fwd(const void* x, const float* mean, const float* invstd, const float* gamma,

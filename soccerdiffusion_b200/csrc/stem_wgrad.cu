@@ -253,6 +253,110 @@ __global__ void __launch_bounds__(NT, 1) stem_wgrad_tma_kernel(const __grid_cons
     if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
+// ---- conv1 forward (space-to-depth form) on the same TMA tensor map: y[p][c] = sum_j patch[p][j] * W[c][j] ------------
+// One image row of output pixels per tile (M = 128 >= WO rows of the accumulator, rows >= WO are ignored), N = 64 output
+// channels, K = 256 = 4 filter rows x 64.  The four patch segments of a pixel are the K-major rows of four [WO][64]
+// operand tiles (the very boxes the weight-gradient kernel loads, read here with K-major descriptors); the weights
+// [64][256] stay resident in shared memory.  Warp 0: TMA producer, warp 1: MMA issuer, warps 4-7: epilogue
+// (TMEM -> bf16 -> one 128-byte NHWC row per thread) with two TMEM accumulators so that the epilogue of tile i overlaps
+// the loads and MMAs of tile i+1.
+__global__ void __launch_bounds__(NT, 1) stem_fprop_tma_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                               const uint4* __restrict__ w_s2d, uint4* __restrict__ y,
+                                                               int HO, int WO, int Hp, int Wp, long long rows_total,
+                                                               int rows_per_cta) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[TMA_STAGES];
+    __shared__ __align__(8) uint64_t bar_empty[TMA_STAGES];
+    __shared__ __align__(8) uint64_t acc_full[2];
+    __shared__ __align__(8) uint64_t acc_empty[2];
+    __shared__ uint32_t tmem_slot;
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int blk = WO * 128;                 // one filter row of WO patches
+    const int stage_bytes = 4 * blk;
+    uint8_t* Ws = smem + TMA_STAGES * stage_bytes;   // 4 tiles [64 channels][64 k] K-major, 8 KB each (+ slack for M=128 reads)
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < TMA_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 1); }
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, 128);
+    // weights: w_s2d[c][j] bf16 (j = kh*64 + kw*16 + ci) -> tile kh, row c, 16-byte chunk (j % 64) / 8
+    for (int i = tid; i < 64 * 32; i += NT) {
+        const int c = i >> 5, ch = i & 31;    // 32 chunks of 8 bf16 per output channel
+        *reinterpret_cast<uint4*>(Ws + (ch >> 3) * 8192 + sw128_chunk_off(c, ch & 7)) = w_s2d[i];
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+
+    const long long r_begin = (long long)blockIdx.x * rows_per_cta;
+    const long long r_end = min(rows_total, r_begin + rows_per_cta);
+    const int nrows = (int)max(0LL, r_end - r_begin);
+
+    if (warp == 0 && lane == 0) {
+        for (int ci = 0; ci < nrows; ++ci) {
+            const int s = ci % TMA_STAGES;
+            mbar_wait(&bar_empty[s], (uint32_t)(((ci / TMA_STAGES) & 1) ^ 1));
+            const long long r = r_begin + ci;
+            const int n = (int)(r / HO), ho = (int)(r - (long long)n * HO);
+            const uint32_t base = smem_u32(smem + s * stage_bytes);
+            mbar_arrive_expect_tx(&bar_full[s], (uint32_t)stage_bytes);
+#pragma unroll
+            for (int kh = 0; kh < 4; ++kh)
+                tma_load_2d(base + kh * blk, &tmA, 0, (n * Hp + ho + kh) * Wp, &bar_full[s]);
+        }
+    } else if (warp == 1 && lane == 0) {
+        const uint32_t idesc = instr_desc_bf16(128, 64, 0, 0);
+        for (int ci = 0; ci < nrows; ++ci) {
+            const int s = ci % TMA_STAGES, a = ci & 1;
+            mbar_wait(&acc_empty[a], (uint32_t)(((ci >> 1) & 1) ^ 1));   // epilogue drained this accumulator
+            mbar_wait(&bar_full[s], (uint32_t)((ci / TMA_STAGES) & 1));
+            tc_fence_after_sync();
+            const uint32_t base = smem_u32(smem + s * stage_bytes);
+#pragma unroll
+            for (int kh = 0; kh < 4; ++kh) {
+                const uint64_t da = smem_desc_k_sw128(base + kh * blk);
+                const uint64_t db = smem_desc_k_sw128(smem_u32(Ws) + kh * 8192);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    mma_bf16_ss(tmem + a * 64, da + 2 * ks, db + 2 * ks, idesc, (kh | ks) ? 1u : 0u);
+            }
+            mma_commit(&bar_empty[s]);
+            mma_commit(&acc_full[a]);
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;        // pixel within the image row
+        for (int ci = 0; ci < nrows; ++ci) {
+            const int a = ci & 1;
+            mbar_wait(&acc_full[a], (uint32_t)((ci >> 1) & 1));
+            tc_fence_after_sync();
+            float v0[32], v1[32];
+            tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 64), v0);
+            tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 64 + 32), v1);
+            tc_fence_before_sync();
+            // all four epilogue warps have read the accumulator -> hand it back to the MMA warp
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (tid == 128) mbar_arrive(&acc_empty[a]);
+            if (row < WO) {
+                uint4* dst = y + ((r_begin + ci) * WO + row) * 8;
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) dst[c8] = pack8_bf16(v0 + 8 * c8);
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) dst[4 + c8] = pack8_bf16(v1 + 8 * c8);
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
 bool use_tma() {   // SD_B200_STEM_WGRAD_TMA=0 selects the cp.async-fed kernel
     static int v = -1;
     if (v < 0) {
@@ -260,6 +364,38 @@ bool use_tma() {   // SD_B200_STEM_WGRAD_TMA=0 selects the cp.async-fed kernel
         v = (e && e[0] == '0') ? 0 : 1;
     }
     return v == 1;
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// cuTensorMapEncodeTiled resolved at run time (the library must load on machines without libcuda.so.1); nullptr = no
+EncodeFn tensor_map_encoder() {
+    static EncodeFn encode = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
+            qres == cudaDriverEntryPointSuccess)
+            encode = (EncodeFn)fn;
+        else
+            cudaGetLastError();
+    }
+    return encode;
+}
+// the packed image as [patch-row start q][64 elements], 32-byte pitch (overlapping rows), box {64, WO}
+bool encode_patch_map(CUtensorMap* tm, const void* xs2d, int N, int Hp, int Wp, int WO) {
+    EncodeFn encode = tensor_map_encoder();
+    if (!encode) return false;
+    const cuuint64_t gdim[2] = {64, (cuuint64_t)N * Hp * Wp - 3};
+    const cuuint64_t gstr[1] = {32};
+    const cuuint32_t box[2] = {64, (cuuint32_t)WO};
+    const cuuint32_t estr[2] = {1, 1};
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(xs2d), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // returns SD_OK and sets *done when the TMA kernel was launched; leaves *done false when this shape / driver cannot
@@ -355,6 +491,34 @@ extern "C" int sd_stem_wgrad_s2d_bf16(const void* xs2d, const void* dy, float* d
         configured = true;
     }
     stem_wgrad_kernel<<<grid, NT, smem, st>>>((const uint4*)xs2d, (const uint4*)dy, dw_s2d, N, HO, WO, Hp, Wp, P, per);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+}
+
+// y (N, H/2, W/2, 64) bf16 NHWC = conv1 of the packed image with w_s2d[64][256] bf16 (row = output channel,
+// column = kh*64 + kw*16 + ci).  Returns SD_E_UNSUPPORTED when the shape / driver cannot use the TMA kernel (the
+// caller then runs cuDNN).
+extern "C" int sd_stem_fprop_s2d_bf16(const void* xs2d, const void* w_s2d, void* y, int N, int H, int W, void* stream) {
+    if (N <= 0) return SD_OK;
+    if (!xs2d || !w_s2d || !y || (H & 1) || (W & 1)) return SD_ERR_BAD_ARG;
+    const int Hp = (H + 6) / 2, Wp = (W + 6) / 2, HO = H / 2, WO = W / 2;
+    if (!use_tma() || WO % 8 != 0 || WO > 128 || WO < 8) return SD_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)TMA_STAGES * 4 * WO * 128 + 4 * 8192 + 4096 + 1024;   // stages + weights + M=128 over-read slack
+    if (smem > 227 * 1024 - 256) return SD_ERR_UNSUPPORTED;
+    CUtensorMap tmA;
+    if (!encode_patch_map(&tmA, xs2d, N, Hp, Wp, WO)) return SD_ERR_UNSUPPORTED;
+    static size_t configured = 0;
+    if (configured < smem) {
+        if (cudaFuncSetAttribute(stem_fprop_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return SD_ERR_UNSUPPORTED;
+        }
+        configured = smem;
+    }
+    const long long rows = (long long)N * HO;
+    const int grid = (int)min((long long)148, rows);
+    const int per = (int)((rows + grid - 1) / grid);
+    stem_fprop_tma_kernel<<<grid, NT, smem, (cudaStream_t)stream>>>(tmA, (const uint4*)w_s2d, (uint4*)y, HO, WO, Hp, Wp, rows, per);
     SD_LAUNCH_CHECK();
     return SD_OK;
 }

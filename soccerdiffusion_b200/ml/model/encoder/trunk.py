@@ -17,6 +17,7 @@ from soccerdiffusion_b200 import ops
 import os
 
 _USE_TC_STEM_WGRAD = os.environ.get("SD_B200_STEM_WGRAD", "tc") == "tc"
+_USE_TC_STEM_FPROP = os.environ.get("SD_B200_STEM_FPROP", "tc") == "tc"
 
 
 def _cl(t: torch.Tensor) -> torch.Tensor:
@@ -209,8 +210,14 @@ def _stem_conv_s2d_raw(images, weight):
     ops.stem_pack(images.contiguous(), xp, N, H, W)
     w = F.pad(weight.to(torch.bfloat16), (0, 1, 0, 1))
     w = w.view(Cout, Cin, 4, 2, 4, 2).permute(0, 1, 3, 5, 2, 4).reshape(Cout, Cin * 4, 4, 4)
-    w = F.pad(w, (0, 0, 0, 0, 0, 16 - Cin * 4)).contiguous(memory_format=torch.channels_last)
-    return F.conv2d(xp.permute(0, 3, 1, 2), w, None, 1, 0)
+    w = F.pad(w, (0, 0, 0, 0, 0, 16 - Cin * 4))                      # (Cout, 16, 4, 4)
+    if Cout == 64 and _USE_TC_STEM_FPROP:
+        # TMA + tcgen05 kernel: weights as [cout][kh][kw][ci] = [64][256]
+        w2 = w.permute(0, 2, 3, 1).reshape(Cout, 256).contiguous()
+        y = torch.empty((N, Cout, H // 2, W // 2), device=images.device, dtype=torch.bfloat16, memory_format=torch.channels_last)
+        if ops.stem_fprop(xp, w2, y, N, H, W):
+            return y
+    return F.conv2d(xp.permute(0, 3, 1, 2), w.contiguous(memory_format=torch.channels_last), None, 1, 0)
 
 
 def _stem_is_s2d_compatible(conv, images) -> bool:

@@ -358,3 +358,15 @@ def stem_wgrad(xs2d, dy, dw, N, H, W):
         check(_lib.lib().sd_stem_wgrad_s2d_bf16(xs2d.data_ptr(), dy.data_ptr(), dw.data_ptr(), N, H, W, stream_ptr()),
               "sd_stem_wgrad_s2d_bf16")
     _count(2)
+
+
+def stem_fprop(xs2d, w_s2d, y, N, H, W) -> bool:
+    """conv1 forward on the packed image; False when the TMA/tcgen05 kernel does not support this shape."""
+    P = N * (H // 2) * (W // 2)
+    with _Timed("stem_fprop_s2d", 2.0 * 256 * 64 * P, 32.0 * N * ((H + 6) // 2) * ((W + 6) // 2) + 128.0 * P, f"[N{N} H{H}]"):
+        rc = _lib.lib().sd_stem_fprop_s2d_bf16(xs2d.data_ptr(), w_s2d.data_ptr(), y.data_ptr(), N, H, W, stream_ptr())
+    if rc == -2:
+        return False
+    check(rc, "sd_stem_fprop_s2d_bf16")
+    _count()
+    return True

@@ -169,6 +169,27 @@ def test_stem_wgrad_tcgen05_matches_cudnn(N, H, W):
     assert rel(got[False], ref) < 1e-2                            # cuDNN result is rounded to bf16
 
 
+@pytest.mark.parametrize("N,H,W", [(4, 224, 224), (2, 64, 96), (3, 16, 16)])
+def test_stem_fprop_tcgen05_matches_cudnn(N, H, W):
+    """conv1 forward: TMA + tcgen05 kernel on the space-to-depth image vs the library convolution, and vs float64."""
+    from soccerdiffusion_b200.ml.model.encoder import trunk as T
+
+    torch.manual_seed(N + H)
+    w = torch.randn(64, 3, 7, 7, device="cuda") * 0.05
+    img = torch.randn(N, 3, H, W, device="cuda")
+    outs = {}
+    for mode in (True, False):
+        T._USE_TC_STEM_FPROP = mode
+        try:
+            outs[mode] = T._stem_conv_s2d_raw(img, w).float()
+        finally:
+            T._USE_TC_STEM_FPROP = True
+    ref = torch.nn.functional.conv2d(img.to(torch.bfloat16).double(), w.to(torch.bfloat16).double(), None, 2, 3)
+    assert outs[True].shape == ref.shape
+    assert rel(outs[True], ref) < 4e-3 and rel(outs[False], ref) < 4e-3     # bf16 output rounding
+    assert rel(outs[True], outs[False]) < 4e-3
+
+
 def test_fused_trunk_matches_library_trunk_bf16():
     """Whole trunk, train mode: libsd_b200 path (space-to-depth stem, fused BN/ReLU/pool kernels) and torch's bf16
     autocast path are both compared with the fp32 trunk; the fused path must be as close to fp32 as the library
