@@ -170,26 +170,23 @@ def _stem_conv_s2d(conv, images: torch.Tensor) -> torch.Tensor:
 
 
 class StemConvS2D(torch.autograd.Function):
-    """conv1 forward in the space-to-depth formulation (fast cuDNN fprop), weight gradient in the original 7x7
-    formulation (cuDNN's wgrad kernel for the 4x4/Cin=16 problem measured 2.3x slower than for 7x7/Cin=3)."""
+    """conv1 in the space-to-depth formulation: forward and weight gradient on libsd_b200's TMA + tcgen05 kernels
+    (sd_stem_fprop_s2d_bf16 / sd_stem_wgrad_s2d_bf16; cuDNN when the shape is not supported).  The packed image is kept
+    for the backward pass (1.1 GB at bs=256) instead of being re-packed."""
 
     @staticmethod
     def forward(ctx, images, weight):
         with torch.no_grad():
-            y = _stem_conv_s2d_raw(images, weight)
-        ctx.save_for_backward(images, weight)
+            y, xp = _stem_conv_s2d_raw(images, weight, return_packed=True)
+        ctx.save_for_backward(images, weight, xp)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        images, weight = ctx.saved_tensors
+        images, weight, xp = ctx.saved_tensors
         N, Cin, H, W = images.shape
         Cout = weight.shape[0]
         if Cout == 64 and _USE_TC_STEM_WGRAD:
-            # tcgen05 kernel on the (re-packed) space-to-depth image; then undo the weight transform
-            Hp, Wp = (H + 6) // 2, (W + 6) // 2
-            xp = torch.empty((N, Hp, Wp, 16), device=images.device, dtype=torch.bfloat16)
-            ops.stem_pack(images.contiguous(), xp, N, H, W)
             dws = torch.empty((256, 64), device=images.device, dtype=torch.float32)
             ops.stem_wgrad(xp, _cl(dy), dws, N, H, W)
             g = dws.view(4, 4, 16, Cout)[:, :, : Cin * 4]                  # (kh, kw, ci=(c,dy,dx), cout)
@@ -202,7 +199,7 @@ class StemConvS2D(torch.autograd.Function):
         return None, gw.to(weight.dtype)
 
 
-def _stem_conv_s2d_raw(images, weight):
+def _stem_conv_s2d_raw(images, weight, return_packed: bool = False):
     N, Cin, H, W = images.shape
     Cout = weight.shape[0]
     Hp, Wp = (H + 6) // 2, (W + 6) // 2
@@ -216,8 +213,9 @@ def _stem_conv_s2d_raw(images, weight):
         w2 = w.permute(0, 2, 3, 1).reshape(Cout, 256).contiguous()
         y = torch.empty((N, Cout, H // 2, W // 2), device=images.device, dtype=torch.bfloat16, memory_format=torch.channels_last)
         if ops.stem_fprop(xp, w2, y, N, H, W):
-            return y
-    return F.conv2d(xp.permute(0, 3, 1, 2), w.contiguous(memory_format=torch.channels_last), None, 1, 0)
+            return (y, xp) if return_packed else y
+    y = F.conv2d(xp.permute(0, 3, 1, 2), w.contiguous(memory_format=torch.channels_last), None, 1, 0)
+    return (y, xp) if return_packed else y
 
 
 def _stem_is_s2d_compatible(conv, images) -> bool:
