@@ -41,20 +41,44 @@ struct AttnTcParams {
     Dropout drop;
 };
 
-// rows [0,R) of src (row stride ld floats, `dh` floats per row) -> bf16 [128][64] swizzled tile; rows >= R zero
-__device__ __forceinline__ void stage_rows(uint8_t* tile, const float* __restrict__ src, long long ld, int R, int dh) {
+// Operand staging: rows [0,R) of each source (row stride ld floats, `dh` floats per row) -> bf16 [128][64] swizzled
+// tile, rows >= R zero.  The global loads of NOPS operands x IB passes are all issued before the first conversion /
+// shared store, so a CTA pays one DRAM round trip per batch instead of one per pass.
+struct StageSrc {
+    const float* src; long long ld; int R;
+};
+template <int NOPS, int IB>
+__device__ __forceinline__ void stage_multi(uint8_t* tile0, const StageSrc* ops, int dh) {
     const int cpr = dh >> 3;   // 16-byte chunks per row
-    for (int item = threadIdx.x; item < 128 * cpr; item += NT) {
-        const int r = item / cpr, c = item % cpr;
-        float f[8];
+    const int iters = (128 * cpr) / NT;
+    for (int it0 = 0; it0 < iters; it0 += IB) {
+        float4 lo[NOPS][IB], hi[NOPS][IB];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = 0.f;
-        if (r < R) {
-            const float4 a = *reinterpret_cast<const float4*>(src + (long long)r * ld + 8 * c);
-            const float4 b = *reinterpret_cast<const float4*>(src + (long long)r * ld + 8 * c + 4);
-            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-        }
-        *reinterpret_cast<uint4*>(tile + sw128_chunk_off(r, c)) = pack8_bf16(f);
+        for (int o = 0; o < NOPS; ++o)
+#pragma unroll
+            for (int i = 0; i < IB; ++i) {
+                const int item = threadIdx.x + NT * (it0 + i);
+                const int r = item / cpr, c = item % cpr;
+                lo[o][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                hi[o][i] = lo[o][i];
+                if (it0 + i < iters && r < ops[o].R) {
+                    const float* g = ops[o].src + (long long)r * ops[o].ld + 8 * c;
+                    lo[o][i] = *reinterpret_cast<const float4*>(g);
+                    hi[o][i] = *reinterpret_cast<const float4*>(g + 4);
+                }
+            }
+#pragma unroll
+        for (int o = 0; o < NOPS; ++o)
+#pragma unroll
+            for (int i = 0; i < IB; ++i) {
+                const int item = threadIdx.x + NT * (it0 + i);
+                const int r = item / cpr, c = item % cpr;
+                if (it0 + i < iters) {
+                    const float f[8] = {lo[o][i].x, lo[o][i].y, lo[o][i].z, lo[o][i].w,
+                                        hi[o][i].x, hi[o][i].y, hi[o][i].z, hi[o][i].w};
+                    *reinterpret_cast<uint4*>(tile0 + o * TILE + sw128_chunk_off(r, c)) = pack8_bf16(f);
+                }
+            }
     }
 }
 
@@ -87,9 +111,13 @@ __global__ void __launch_bounds__(NT) attn_tc_fwd_kernel(const AttnTcParams p) {
     const int Mp = (M + 15) & ~15;
     if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
     if (warp == 0) tmem_alloc(&tmem_slot, 256);
-    stage_rows(Qs, p.Q + (long long)b * T * p.ldq + h * dh, p.ldq, T, dh);
-    stage_rows(Ks, p.K + (long long)b * M * p.ldk + h * dh, p.ldk, M, dh);
-    stage_rows(Vs, p.V + (long long)b * M * p.ldv + h * dh, p.ldv, M, dh);
+    {   // Qs, Ks, Vs are consecutive tiles
+        const StageSrc ops[3] = {{p.Q + (long long)b * T * p.ldq + h * dh, p.ldq, T},
+                                 {p.K + (long long)b * M * p.ldk + h * dh, p.ldk, M},
+                                 {p.V + (long long)b * M * p.ldv + h * dh, p.ldv, M}};
+        stage_multi<3, 4>(Qs, ops, dh);
+    }
+    const uint64_t dseed = p.drop.resolve();
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
@@ -125,7 +153,7 @@ __global__ void __launch_bounds__(NT) attn_tc_fwd_kernel(const AttnTcParams p) {
             if (m < M) {
                 e = expf(v[j] * p.scale - mx);
                 sum += e;
-                if (t < T) e *= p.drop(row_idx + m);
+                if (t < T) e *= p.drop.at(dseed, row_idx + m);
             }
             v[j] = e;   // columns >= M are exactly zero: V rows >= M never contribute
         }
@@ -184,21 +212,29 @@ __global__ void __launch_bounds__(NT) attn_tc_bwd_kernel(const AttnTcParams p) {
     if (warp == 0) tmem_alloc(&tmem_slot, 256);
     const float* Og = p.O + (long long)b * T * p.ldo + h * dh;
     const float* dOg = p.dO + (long long)b * T * p.lddo + h * dh;
-    stage_rows(Qs, p.Q + (long long)b * T * p.ldq + h * dh, p.ldq, T, dh);
-    stage_rows(Ks, p.K + (long long)b * M * p.ldk + h * dh, p.ldk, M, dh);
-    stage_rows(Vs, p.V + (long long)b * M * p.ldv + h * dh, p.ldv, M, dh);
-    stage_rows(dOs, dOg, p.lddo, T, dh);
-    // delta[t] = dO[t] . O[t] and the saved log-sum-exp of this thread's row
+    // delta[t] = dO[t] . O[t] and the saved log-sum-exp of this thread's row (loads issued ahead of the staging)
     const int t = tid;
     float delta = 0.f, lse = 0.f;
     if (t < T) {
+        float d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
         for (int c = 0; c < dh; c += 4) {
             const float4 a = *reinterpret_cast<const float4*>(dOg + (long long)t * p.lddo + c);
             const float4 o = *reinterpret_cast<const float4*>(Og + (long long)t * p.ldo + c);
-            delta = fmaf(a.x, o.x, fmaf(a.y, o.y, fmaf(a.z, o.z, fmaf(a.w, o.w, delta))));
+            d4[0] = fmaf(a.x, o.x, d4[0]); d4[1] = fmaf(a.y, o.y, d4[1]);
+            d4[2] = fmaf(a.z, o.z, d4[2]); d4[3] = fmaf(a.w, o.w, d4[3]);
         }
+        delta = (d4[0] + d4[1]) + (d4[2] + d4[3]);
         lse = p.lse[((long long)b * p.H + h) * T + t];
     }
+    {   // Qs, Ks, Vs, dOs are consecutive tiles
+        const StageSrc ops[4] = {{p.Q + (long long)b * T * p.ldq + h * dh, p.ldq, T},
+                                 {p.K + (long long)b * M * p.ldk + h * dh, p.ldk, M},
+                                 {p.V + (long long)b * M * p.ldv + h * dh, p.ldv, M},
+                                 {dOg, p.lddo, T}};
+        stage_multi<4, 2>(Qs, ops, dh);
+    }
+    const uint64_t dseed = p.drop.resolve();
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
@@ -225,7 +261,7 @@ __global__ void __launch_bounds__(NT) attn_tc_bwd_kernel(const AttnTcParams p) {
             float pd = 0.f, ds = 0.f;
             if (m < M && t < T) {
                 const float pr = expf(s[j] * p.scale - lse);
-                const float dm = p.drop(row_idx + m);
+                const float dm = p.drop.at(dseed, row_idx + m);
                 pd = pr * dm;
                 ds = pr * (dp[j] * dm - delta) * p.scale;
             }

@@ -84,6 +84,15 @@ struct Dropout {
 #endif
         return dropout_scale(s, stream, idx, thresh, inv_keep);
     }
+#ifdef __CUDACC__
+    // hot loops: read the device seed offset once per thread, then draw with at()
+    __device__ __forceinline__ uint64_t resolve() const {
+        return (thresh != 0 && seed_dev) ? seed + __ldg(seed_dev) : seed;
+    }
+    __device__ __forceinline__ float at(uint64_t resolved_seed, uint64_t idx) const {
+        return thresh == 0 ? 1.0f : dropout_scale(resolved_seed, stream, idx, thresh, inv_keep);
+    }
+#endif
 };
 // process-wide device seed offset (sd_set_dropout_seed_offset); defined in elementwise.cu
 extern const unsigned long long* g_dropout_seed_dev;

@@ -37,6 +37,7 @@ struct TcParams {
     float* C; long long ldc;
     int M, N, K;
     int vecA, vecB;
+    int vecC;        // every epilogue pointer 16-byte aligned, every row pitch and N a multiple of 4
     const float* ln_mean; const float* ln_rstd; const float* ln_gamma; const float* ln_beta;
     int ln_on_a, ln_on_b;
     const float* bias;
@@ -53,10 +54,53 @@ struct TcParams {
     int tmem_cols;   // power of two >= max(32, BN)
 };
 
-// Stage a [R rows][64 k] bf16 tile from a matrix whose k index is contiguous in memory (src[row][k]).
+// Operand staging is split into a LOAD phase (global -> registers: every load of a batch of 4 row passes is in
+// flight before the first use, and the A and B batches are issued back to back) and a STORE phase (LayerNorm-on-load,
+// fp32 -> bf16, swizzled 16-byte shared stores).  One DRAM round trip per k chunk instead of one per row pass.
+struct Frag {
+    float4 lo[4], hi[4];   // 8 consecutive source elements per pass
+    float rs[4], nm[4];    // LayerNorm rstd and -mean*rstd of the pass's row (K-contiguous sources only)
+};
+
+__device__ __forceinline__ void load8(float4& lo, float4& hi, const float* __restrict__ g, bool full, int nvalid) {
+    if (full) {
+        lo = *reinterpret_cast<const float4*>(g);
+        hi = *reinterpret_cast<const float4*>(g + 4);
+    } else {
+        float t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = (j < nvalid) ? g[j] : 0.f;
+        lo = make_float4(t[0], t[1], t[2], t[3]);
+        hi = make_float4(t[4], t[5], t[6], t[7]);
+    }
+}
+
+// K-contiguous source (src[row][k]): thread -> 16-byte chunk c = tid & 7 of rows (tid >> 3) + 32 * (it0 + i).
 template <bool LN>
-__device__ __forceinline__ void stage_k_contig(uint8_t* tile, const float* __restrict__ src, long long ld, int row0,
-                                               int rows_total, int R, int k0, int ke, bool vec, const TcParams& p) {
+__device__ __forceinline__ void load_k_contig(Frag& f, const float* __restrict__ src, long long ld, int row0,
+                                              int rows_total, int R, int it0, int k0, int ke, bool vec,
+                                              const TcParams& p) {
+    const int c = threadIdx.x & 7;
+    const int k = k0 + 8 * c;
+    const bool full = vec && (k + 7 < ke);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = (threadIdx.x >> 3) + 32 * (it0 + i);
+        const int row = row0 + r;
+        f.lo[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        f.hi[i] = f.lo[i];
+        if (r < R && row < rows_total && k < ke) {
+            load8(f.lo[i], f.hi[i], src + (long long)row * ld + k, full, ke - k);
+            if (LN) {
+                f.rs[i] = p.ln_rstd[row];
+                f.nm[i] = -p.ln_mean[row] * f.rs[i];
+            }
+        }
+    }
+}
+template <bool LN>
+__device__ __forceinline__ void store_k_contig(uint8_t* tile, const Frag& f, int row0, int rows_total, int R, int it0,
+                                               int k0, int ke, const TcParams& p) {
     const int c = threadIdx.x & 7;
     const int k = k0 + 8 * c;
     float ga[8], be[8];
@@ -67,31 +111,54 @@ __device__ __forceinline__ void stage_k_contig(uint8_t* tile, const float* __res
             be[j] = (k + j < ke) ? __ldg(p.ln_beta + k + j) : 0.f;
         }
     }
-    const bool full = vec && (k + 7 < ke);
-    for (int r = threadIdx.x >> 3; r < R; r += NT / 8) {
-        const int row = row0 + r;
-        float f[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = 0.f;
-        if (row < rows_total && k < ke) {
-            const float* g = src + (long long)row * ld + k;
-            if (full) {
-                const float4 a = *reinterpret_cast<const float4*>(g);
-                const float4 b = *reinterpret_cast<const float4*>(g + 4);
-                f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-            } else {
+    for (int i = 0; i < 4; ++i) {
+        const int r = (threadIdx.x >> 3) + 32 * (it0 + i);
+        if (r >= R) break;
+        float v[8] = {f.lo[i].x, f.lo[i].y, f.lo[i].z, f.lo[i].w, f.hi[i].x, f.hi[i].y, f.hi[i].z, f.hi[i].w};
+        if (LN && row0 + r < rows_total && k < ke) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (k + j < ke) f[j] = g[j];
-            }
-            if (LN) {
-                const float rs = p.ln_rstd[row];
-                const float nm = -p.ln_mean[row] * rs;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = fmaf(fmaf(f[j], rs, nm), ga[j], be[j]);   // 0 beyond ke: ga = be = 0
-            }
+            for (int j = 0; j < 8; ++j) v[j] = fmaf(fmaf(v[j], f.rs[i], f.nm[i]), ga[j], be[j]);   // 0 beyond ke: ga = be = 0
         }
-        *reinterpret_cast<uint4*>(tile + sw128_chunk_off(r, c)) = pack8_bf16(f);
+        *reinterpret_cast<uint4*>(tile + sw128_chunk_off(r, c)) = pack8_bf16(v);
+    }
+}
+
+// MN-contiguous source (src[k][mn]) staged WITHOUT transposing: MN-major operand layout (64 MN elements = one
+// 128-byte row per k, 128-byte swizzle).  R = MN extent of the tile (multiple of 8), TK k rows; item = (k row, chunk).
+__device__ __forceinline__ void load_mn_major(Frag& f, const float* __restrict__ src, long long ld, int mn0,
+                                              int mn_total, int R, int it0, int k0, int ke, bool vec) {
+    const int chunks = R >> 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int item = threadIdx.x + NT * (it0 + i);
+        const int c = item % chunks, kr = item / chunks;
+        const int mn = mn0 + 8 * c, k = k0 + kr;
+        f.lo[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        f.hi[i] = f.lo[i];
+        if (kr < TK && k < ke && mn < mn_total)
+            load8(f.lo[i], f.hi[i], src + (long long)k * ld + mn, vec && mn + 7 < mn_total, mn_total - mn);
+    }
+}
+template <bool LN>
+__device__ __forceinline__ void store_mn_major(uint8_t* tile, const Frag& f, int mn0, int mn_total, int R, int it0, int k0,
+                                               int ke, const TcParams& p) {
+    const int chunks = R >> 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int item = threadIdx.x + NT * (it0 + i);
+        const int c = item % chunks, kr = item / chunks;
+        if (kr >= TK) break;
+        const int mn = mn0 + 8 * c, k = k0 + kr;
+        float v[8] = {f.lo[i].x, f.lo[i].y, f.lo[i].z, f.lo[i].w, f.hi[i].x, f.hi[i].y, f.hi[i].z, f.hi[i].w};
+        if (LN && k < ke && mn < mn_total) {   // the k index is the normalised row, the MN index the feature
+            const float rs = p.ln_rstd[k];
+            const float nm = -p.ln_mean[k] * rs;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (mn + j < mn_total) v[j] = fmaf(fmaf(v[j], rs, nm), __ldg(p.ln_gamma + mn + j), __ldg(p.ln_beta + mn + j));
+        }
+        *reinterpret_cast<uint4*>(tile + sw128_mn_chunk_off(8 * c, kr, TK)) = pack8_bf16(v);
     }
 }
 
@@ -121,42 +188,6 @@ __device__ __forceinline__ void stage_row_contig(uint8_t* tile, const float* __r
             }
         }
         *reinterpret_cast<uint4*>(tile + sw128_chunk_off(r, c)) = pack8_bf16(f);
-    }
-}
-
-// Stage a tile from a matrix whose MN index is contiguous in memory (src[k][mn]) WITHOUT transposing: MN-major
-// operand layout (64 MN elements = one 128-byte row per k, 128-byte swizzle).  16-byte global loads, 16-byte
-// conflict-free shared stores.  R = MN extent of the tile (multiple of 8), rows of k = TK.
-template <bool LN>
-__device__ __forceinline__ void stage_mn_major(uint8_t* tile, const float* __restrict__ src, long long ld, int mn0,
-                                               int mn_total, int R, int k0, int ke, bool vec, const TcParams& p) {
-    const int chunks = R >> 3;                     // 16-byte chunks per k row
-    for (int item = threadIdx.x; item < chunks * TK; item += NT) {
-        const int c = item % chunks, kr = item / chunks;
-        const int mn = mn0 + 8 * c, k = k0 + kr;
-        float f[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = 0.f;
-        if (k < ke && mn < mn_total) {
-            const float* g = src + (long long)k * ld + mn;
-            if (vec && mn + 7 < mn_total) {
-                const float4 a = *reinterpret_cast<const float4*>(g);
-                const float4 b = *reinterpret_cast<const float4*>(g + 4);
-                f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (mn + j < mn_total) f[j] = g[j];
-            }
-            if (LN) {   // the k index is the normalised row, the MN index the feature
-                const float rs = p.ln_rstd[k];
-                const float nm = -p.ln_mean[k] * rs;
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (mn + j < mn_total) f[j] = fmaf(fmaf(f[j], rs, nm), __ldg(p.ln_gamma + mn + j), __ldg(p.ln_beta + mn + j));
-            }
-        }
-        *reinterpret_cast<uint4*>(tile + sw128_mn_chunk_off(8 * c, kr, TK)) = pack8_bf16(f);
     }
 }
 
@@ -201,26 +232,44 @@ __global__ void __launch_bounds__(NT) gemm_tc_kernel(const TcParams p) {
 
     for (int ci = 0; ci < nchunks; ++ci) {
         const int s = ci % STAGES;
-        if (ci >= STAGES) mbar_wait(&bar_stage[s], (uint32_t)((ci / STAGES - 1) & 1));
         const int k0 = kb + ci * TK;
         uint8_t* As = smem + s * stage_bytes;
         uint8_t* Bs = As + A_STAGE_BYTES;
-        if (A_MN) {
-            stage_mn_major<false>(As, p.A, p.lda, m0, p.M, TM, k0, ke, p.vecA, p);
-        } else if (A_KM) {
-            stage_row_contig<false>(As, p.A, p.lda, m0, p.M, TM, k0, ke, p);
-        } else {
-            if (p.ln_on_a) stage_k_contig<true>(As, p.A, p.lda, m0, p.M, TM, k0, ke, p.vecA, p);
-            else stage_k_contig<false>(As, p.A, p.lda, m0, p.M, TM, k0, ke, p.vecA, p);
+        constexpr bool A_ROWC = A_KM && !MNMAJ, B_ROWC = B_KN && !MNMAJ;   // transposing staging (SD_B200_TC_MNMAJOR=0)
+        const int itersB = B_MN ? (BNr >> 5) : ((BN + 31) >> 5);         // 32-row (or 256-item) passes of the B tile
+        Frag fa, fb;
+        // load phase: A and the first B batch in flight together
+        if (A_MN) load_mn_major(fa, p.A, p.lda, m0, p.M, TM, 0, k0, ke, p.vecA);
+        else if (!A_ROWC) {
+            if (p.ln_on_a) load_k_contig<true>(fa, p.A, p.lda, m0, p.M, TM, 0, k0, ke, p.vecA, p);
+            else load_k_contig<false>(fa, p.A, p.lda, m0, p.M, TM, 0, k0, ke, p.vecA, p);
         }
-        if (B_MN) {
-            if (p.ln_on_b) stage_mn_major<true>(Bs, p.B, p.ldb, n0, p.N, BNr, k0, ke, p.vecB, p);
-            else stage_mn_major<false>(Bs, p.B, p.ldb, n0, p.N, BNr, k0, ke, p.vecB, p);
-        } else if (B_KN) {
+        if (B_MN) load_mn_major(fb, p.B, p.ldb, n0, p.N, BNr, 0, k0, ke, p.vecB);
+        else if (!B_ROWC) load_k_contig<false>(fb, p.B, p.ldb, n0, p.N, BN, 0, k0, ke, p.vecB, p);
+        // store phase (the stage must have been drained by the MMAs that last read it)
+        if (ci >= STAGES) mbar_wait(&bar_stage[s], (uint32_t)((ci / STAGES - 1) & 1));
+        if (A_MN) store_mn_major<false>(As, fa, m0, p.M, TM, 0, k0, ke, p);
+        else if (A_ROWC) stage_row_contig<false>(As, p.A, p.lda, m0, p.M, TM, k0, ke, p);
+        else {
+            if (p.ln_on_a) store_k_contig<true>(As, fa, m0, p.M, TM, 0, k0, ke, p);
+            else store_k_contig<false>(As, fa, m0, p.M, TM, 0, k0, ke, p);
+        }
+        if (B_ROWC) {
             if (p.ln_on_b) stage_row_contig<true>(Bs, p.B, p.ldb, n0, p.N, BN, k0, ke, p);
             else stage_row_contig<false>(Bs, p.B, p.ldb, n0, p.N, BN, k0, ke, p);
         } else {
-            stage_k_contig<false>(Bs, p.B, p.ldb, n0, p.N, BN, k0, ke, p.vecB, p);
+            for (int it0 = 0; it0 < itersB; it0 += 4) {
+                if (it0 > 0) {
+                    if (B_MN) load_mn_major(fb, p.B, p.ldb, n0, p.N, BNr, it0, k0, ke, p.vecB);
+                    else load_k_contig<false>(fb, p.B, p.ldb, n0, p.N, BN, it0, k0, ke, p.vecB, p);
+                }
+                if (B_MN) {
+                    if (p.ln_on_b) store_mn_major<true>(Bs, fb, n0, p.N, BNr, it0, k0, ke, p);
+                    else store_mn_major<false>(Bs, fb, n0, p.N, BNr, it0, k0, ke, p);
+                } else {
+                    store_k_contig<false>(Bs, fb, n0, p.N, BN, it0, k0, ke, p);
+                }
+            }
         }
         fence_proxy_async_smem();
         __syncthreads();
@@ -249,20 +298,90 @@ __global__ void __launch_bounds__(NT) gemm_tc_kernel(const TcParams p) {
     const bool f_pe = G ? p.pe != nullptr : (EPI & EPI_PE) != 0;
     const bool f_res = G ? p.residual != nullptr : (EPI & EPI_RES) != 0;
     const bool f_acc = G ? p.accumulate != 0 : (EPI & EPI_ACC) != 0;
-    float* bounce = reinterpret_cast<float*>(smem) + warp * (32 * 33);
+    constexpr int BP = 36;                        // bounce row pitch in floats: 16-byte rows, conflict-free both ways
+    float* bounce = reinterpret_cast<float*>(smem) + warp * (32 * BP);
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const bool split = gridDim.z > 1;
     const bool first_slice = blockIdx.z == 0;
     const int nblocks = (BN + 31) / 32;
     const int m_first = m0 + q * 32;
     const int rows = min(32, p.M - m_first);
+    const uint64_t dseed = f_drop ? p.drop.seed + (p.drop.seed_dev ? __ldg(p.drop.seed_dev) : 0ull) : 0ull;
     for (int cb = warp >> 2; cb < nblocks; cb += 2) {
         if (n0 + cb * 32 >= p.N) break;
         float v[32];
         tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32), v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) bounce[lane * 33 + j] = v[j];
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(bounce + lane * BP + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
+        if (p.vecC) {
+            // 8 lanes cover the 32 columns of one row with 16-byte accesses, 4 rows per pass, 8 passes; every global
+            // load of a batch of passes is issued before the first dependent store (one DRAM round trip per batch)
+            const int c4 = lane & 7, rsub = lane >> 3;
+            const int n = n0 + cb * 32 + 4 * c4;
+            if (n < p.N && cb * 32 + 4 * c4 < BN && rows > 0) {
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n)) : z4;
+                if (split && !first_slice) b4 = z4;
+                constexpr int IB = G ? 4 : 8;     // passes per batch
+#pragma unroll
+                for (int h = 0; h < 8; h += IB) {
+                    float4 r_res[IB], r_gg[IB], r_acc[IB], r_pe[IB];
+                    if (!split) {
+#pragma unroll
+                        for (int i = 0; i < IB; ++i) {
+                            const int rr = (h + i) * 4 + rsub;
+                            if (rr < rows) {
+                                const long long m = m_first + rr;
+                                if (f_res) r_res[i] = *reinterpret_cast<const float4*>(p.residual + m * p.ldr + n);
+                                if (f_gg) r_gg[i] = *reinterpret_cast<const float4*>(p.gelu_grad_src + m * p.ldg + n);
+                                if (f_acc) r_acc[i] = *reinterpret_cast<const float4*>(p.C + m * p.ldc + n);
+                                if (f_pe) r_pe[i] = __ldg(reinterpret_cast<const float4*>(p.pe + (long long)(m % p.pe_period) * p.N + n));
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < IB; ++i) {
+                        const int rr = (h + i) * 4 + rsub;
+                        if (rr >= rows) continue;
+                        const long long m = m_first + rr;
+                        const float4 a4 = *reinterpret_cast<const float4*>(bounce + rr * BP + 4 * c4);
+                        float x[4] = {fmaf(a4.x, p.alpha, b4.x), fmaf(a4.y, p.alpha, b4.y), fmaf(a4.z, p.alpha, b4.z),
+                                      fmaf(a4.w, p.alpha, b4.w)};
+                        float* cp = p.C + m * p.ldc + n;
+                        if (split) {
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp), "f"(x[0]), "f"(x[1]),
+                                         "f"(x[2]), "f"(x[3])
+                                         : "memory");
+                            continue;
+                        }
+                        if (f_pre) *reinterpret_cast<float4*>(p.pre_out + m * p.ldp + n) = make_float4(x[0], x[1], x[2], x[3]);
+                        if (f_gelu) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) x[e] = gelu_erf(x[e]);
+                        }
+                        if (f_gg) {
+                            x[0] *= gelu_erf_grad(r_gg[i].x); x[1] *= gelu_erf_grad(r_gg[i].y);
+                            x[2] *= gelu_erf_grad(r_gg[i].z); x[3] *= gelu_erf_grad(r_gg[i].w);
+                        }
+                        if (f_drop) {
+                            const uint64_t didx = (uint64_t)m * (uint64_t)p.N + (uint64_t)n;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                x[e] *= dropout_scale(dseed, p.drop.stream, didx + e, p.drop.thresh, p.drop.inv_keep);
+                        }
+                        if (f_pe) { x[0] += r_pe[i].x; x[1] += r_pe[i].y; x[2] += r_pe[i].z; x[3] += r_pe[i].w; }
+                        if (f_res) { x[0] += r_res[i].x; x[1] += r_res[i].y; x[2] += r_res[i].z; x[3] += r_res[i].w; }
+                        if (f_acc) { x[0] += r_acc[i].x; x[1] += r_acc[i].y; x[2] += r_acc[i].z; x[3] += r_acc[i].w; }
+                        *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
+                    }
+                }
+            }
+            __syncwarp();
+            continue;
+        }
+        // scalar path (unaligned pointers / pitches, N not a multiple of 4): one column per lane, row by row
         const int n = n0 + cb * 32 + lane;
         const bool n_ok = n < p.N && (cb * 32 + lane) < BN;
         if (n_ok && rows > 0) {
@@ -270,7 +389,7 @@ __global__ void __launch_bounds__(NT) gemm_tc_kernel(const TcParams p) {
             float* cp = p.C + (long long)m_first * p.ldc + n;
             if (split) {
                 const float b2 = first_slice ? bias : 0.f;
-                for (int rr = 0; rr < rows; ++rr, cp += p.ldc) atomicAdd(cp, fmaf(bounce[rr * 33 + lane], p.alpha, b2));
+                for (int rr = 0; rr < rows; ++rr, cp += p.ldc) atomicAdd(cp, fmaf(bounce[rr * BP + lane], p.alpha, b2));
             } else {
                 float* prep = f_pre ? p.pre_out + (long long)m_first * p.ldp + n : nullptr;
                 const float* ggp = f_gg ? p.gelu_grad_src + (long long)m_first * p.ldg + n : nullptr;
@@ -280,11 +399,11 @@ __global__ void __launch_bounds__(NT) gemm_tc_kernel(const TcParams p) {
                 uint64_t didx = (uint64_t)m_first * (uint64_t)p.N + (uint64_t)n;
 #pragma unroll 4
                 for (int rr = 0; rr < rows; ++rr) {
-                    float x = fmaf(bounce[rr * 33 + lane], p.alpha, bias);
+                    float x = fmaf(bounce[rr * BP + lane], p.alpha, bias);
                     if (f_pre) { *prep = x; prep += p.ldp; }
                     if (f_gelu) x = gelu_erf(x);
                     if (f_gg) { x *= gelu_erf_grad(*ggp); ggp += p.ldg; }
-                    if (f_drop) { x *= p.drop(didx); didx += (uint64_t)p.N; }
+                    if (f_drop) { x *= dropout_scale(dseed, p.drop.stream, didx, p.drop.thresh, p.drop.inv_keep); didx += (uint64_t)p.N; }
                     if (f_pe) {
                         x += __ldg(pep);
                         if (++pe_row == p.pe_period) { pe_row = 0; pep = p.pe + n; } else pep += p.N;
@@ -360,6 +479,9 @@ int sd_gemm_tc_dispatch(const sd_gemm_desc* d, void* stream) {
     p.pre_out = d->pre_out; p.ldp = d->ldp; p.gelu_grad_src = d->gelu_grad_src; p.ldg = d->ldg;
     p.act = d->act; p.accumulate = d->accumulate; p.alpha = d->alpha == 0.f ? 1.f : d->alpha;
     p.drop = make_dropout(d->dropout_p, d->dropout_seed, d->dropout_stream);
+    auto vec_ok = [](const void* ptr, long long ld) { return ptr == nullptr || (aligned16(ptr) && ld % 4 == 0); };
+    p.vecC = d->N % 4 == 0 && vec_ok(d->C, d->ldc) && vec_ok(d->bias, 0) && vec_ok(d->residual, d->ldr) &&
+             vec_ok(d->pe, 0) && vec_ok(d->pre_out, d->ldp) && vec_ok(d->gelu_grad_src, d->ldg);
 
     // tile columns: one tile when N <= 256, otherwise 128-wide tiles (multiple of 16 for UMMA M=128)
     const int n16 = ((d->N + 15) / 16) * 16;
