@@ -183,7 +183,11 @@ int sd_stem_wgrad_s2d_bf16(const void* xs2d, const void* dy, float* dw_s2d, int 
  * encoder (callers then use the library convolution). */
 int sd_stem_fprop_s2d_bf16(const void* xs2d, const void* w_s2d, void* y, int N, int H, int W, void* stream);
 /* Fused stem: maxpool3x3s2(relu(bn(x))) without materialising the activated 112x112 map; backward recomputes the
- * ReLU mask from x (torchvision ResNet stem bn1 -> relu -> maxpool). mean/invstd from sd_bn_stats_nhwc_bf16. */
+ * ReLU mask from x (torchvision ResNet stem bn1 -> relu -> maxpool). mean/invstd from sd_bn_stats_nhwc_bf16.
+ * With C = 64 and W <= 112 (sd_stem_band_supported) both directions run as row-band kernels: the forward stages its
+ * input rows with one TMA bulk copy per CTA, the backward scatters the pooled gradient into a shared-memory
+ * accumulator (csrc/stem_band.cu); other shapes use generic gather kernels. */
+int sd_stem_band_supported(int H, int W, int C);
 int sd_stem_bn_relu_pool_nhwc_bf16_fwd(const void* x, const float* mean, const float* invstd, const float* gamma,
                                        const float* beta, void* y, void* idx, int N, int H, int W, int C, void* stream);
 int sd_stem_bn_relu_pool_nhwc_bf16_bwd(const void* dpool, const void* idx, const void* x, const float* mean,

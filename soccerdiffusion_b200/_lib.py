@@ -95,6 +95,7 @@ SIGNATURES = {
     "sd_stem_pack_s2d_bf16": [c_f, c_f, c_i, c_i, c_i, c_f],
     "sd_stem_fprop_s2d_bf16": [c_f, c_f, c_f, c_i, c_i, c_i, c_f],
     "sd_stem_wgrad_s2d_bf16": [c_f, c_f, c_f, c_i, c_i, c_i, c_f],
+    "sd_stem_band_supported": [c_i, c_i, c_i],
     "sd_stem_bn_relu_pool_nhwc_bf16_fwd": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f],
     "sd_stem_bn_relu_pool_nhwc_bf16_bwd": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f],
     "sd_maxpool3x3s2_nhwc_bf16_fwd": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f],

@@ -108,4 +108,12 @@ static inline Dropout make_dropout(float p, uint64_t seed, uint32_t stream) {
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// stem_band.cu: row-band kernels for maxpool3x3s2(relu(bn(x))) with 64 channels (used by trunk_ops.cu's entry points)
+bool stem_band_supported(int H, int W, int C);
+int stem_band_fwd(const void* x, const float* mean, const float* invstd, const float* gamma, const float* beta, void* y,
+                  void* idx, int N, int H, int W, cudaStream_t st);
+int stem_band_bwd(const void* dpool, const void* idx, const void* x, const float* mean, const float* invstd,
+                  const float* gamma, const float* beta, double* sums, void* dx, int N, int H, int W, int pass,
+                  cudaStream_t st);
+
 }  // namespace sd

@@ -47,50 +47,47 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
 // MODE 0: f0 = x, f1 = x^2                         (forward statistics)
 // MODE 1: g = dy * (y > 0 if y); f0 = g, f1 = g * xhat  (backward reductions)
 template <int MODE>
-__global__ void __launch_bounds__(kT) bn_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
-                                                       const unsigned char* __restrict__ y, const float* __restrict__ mean,
-                                                       const float* __restrict__ invstd, long long nvec, int CV,
-                                                       double* __restrict__ out, int C,
-                                                       const float* __restrict__ gamma_rc, const float* __restrict__ beta_rc) {
+__global__ void __launch_bounds__(kT, MODE == 0 ? 6 : 3) bn_reduce_kernel(
+    const uint4* __restrict__ x, const uint4* __restrict__ dy, const unsigned char* __restrict__ y,
+    const float* __restrict__ mean, const float* __restrict__ invstd, long long nvec, int CV, double* __restrict__ out, int C,
+    const float* __restrict__ gamma_rc, const float* __restrict__ beta_rc) {
     __shared__ float red[2][kT][8 + 1];
     const int tid = threadIdx.x;
     const int cv = tid % CV;   // kT % CV == 0: a thread keeps its channel group for every vector it visits
-    float mu[8], is[8], sc[8], sh[8];
-    if (MODE == 1) {
+    float sc[8], sh[8];
+    if (MODE == 1 && beta_rc) {   // ReLU mask recomputed from x: relu(x*sc + sh) > 0
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            mu[i] = mean[cv * 8 + i];
-            is[i] = invstd[cv * 8 + i];
-            if (beta_rc) {   // ReLU mask recomputed from x: relu(x*sc + sh) > 0
-                sc[i] = is[i] * gamma_rc[cv * 8 + i];
-                sh[i] = beta_rc[cv * 8 + i] - mu[i] * sc[i];
-            }
+            sc[i] = invstd[cv * 8 + i] * gamma_rc[cv * 8 + i];
+            sh[i] = beta_rc[cv * 8 + i] - mean[cv * 8 + i] * sc[i];
         }
     }
+    // MODE 1 accumulates sum g and the RAW sum g*x; sum g*xhat = invstd * (sum g*x - mean * sum g) is formed once per
+    // thread after the loop, which keeps the per-channel statistics out of the loop's live registers
     float a0[8], a1[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.f;
     const long long per_cta = ((nvec + gridDim.x - 1) / gridDim.x + kT - 1) / kT * kT;
     const long long v0 = blockIdx.x * per_cta, v1 = min(nvec, v0 + per_cta);
-    // two vectors per iteration: all loads of both are issued before any use (memory-level parallelism)
-    for (long long v = v0 + tid; v < v1; v += 2 * kT) {
-        const long long w = v + kT;
-        const bool two = w < v1;
-        uint4 ux[2], ud[2];
-        unsigned mk[2] = {0xFFu, 0xFFu};
-        ux[0] = ld_stream(x + v);
-        if (two) ux[1] = ld_stream(x + w);
-        if (MODE == 1) {
-            ud[0] = ld_stream(dy + v);
-            if (two) ud[1] = ld_stream(dy + w);
-            if (y) {
-                mk[0] = y[v];
-                if (two) mk[1] = y[w];
+    constexpr int U = MODE == 0 ? 4 : 2;   // vectors per iteration: all their loads are issued before any use
+    for (long long v = v0 + tid; v < v1; v += U * kT) {
+        uint4 ux[U], ud[U];
+        unsigned mk[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long w = v + (long long)u * kT;
+            mk[u] = 0xFFu;
+            if (w < v1) {
+                ux[u] = ld_stream(x + w);
+                if (MODE == 1) {
+                    ud[u] = ld_stream(dy + w);
+                    if (y) mk[u] = y[w];
+                }
             }
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (u == 1 && !two) break;
+        for (int u = 0; u < U; ++u) {
+            if (v + (long long)u * kT >= v1) break;
             float fx[8];
             unpack8(ux[u], fx);
             if (MODE == 0) {
@@ -107,9 +104,13 @@ __global__ void __launch_bounds__(kT) bn_reduce_kernel(const uint4* __restrict__
                     for (int i = 0; i < 8; ++i) g[i] = fmaf(fx[i], sc[i], sh[i]) > 0.f ? g[i] : 0.f;
                 }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { a0[i] += g[i]; a1[i] = fmaf(g[i], (fx[i] - mu[i]) * is[i], a1[i]); }
+                for (int i = 0; i < 8; ++i) { a0[i] += g[i]; a1[i] = fmaf(g[i], fx[i], a1[i]); }
             }
         }
+    }
+    if (MODE == 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a1[i] = invstd[cv * 8 + i] * fmaf(-mean[cv * 8 + i], a0[i], a1[i]);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) { red[0][tid][i] = a0[i]; red[1][tid][i] = a1[i]; }
@@ -197,25 +198,27 @@ __global__ void __launch_bounds__(kT) bn_apply_kernel(const uint4* __restrict__ 
 }
 
 // g = dy * (y > 0);  dx = gamma * invstd * (g - sum_g/R - xhat * sum_gx/R);  dres = g
-__global__ void __launch_bounds__(kT) bn_bwd_apply_kernel(const uint4* __restrict__ dy, const unsigned char* __restrict__ y,
-                                                          const uint4* __restrict__ x, const float* __restrict__ mean,
-                                                          const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                                          const double* __restrict__ sums, long long R,
-                                                          uint4* __restrict__ dx, uint4* __restrict__ dres, long long nvec,
-                                                          int CV, int C, const float* __restrict__ beta_rc) {
+// evaluated as dx = kg * g + kx * x + kc with three per-channel constants (kg = gamma*invstd, kx = -kg*invstd*sum_gx/R,
+// kc = -kg*sum_g/R - kx*mean): 24 live registers of constants instead of 48, three CTAs per SM instead of two.
+__global__ void __launch_bounds__(kT, 3) bn_bwd_apply_kernel(const uint4* __restrict__ dy, const unsigned char* __restrict__ y,
+                                                             const uint4* __restrict__ x, const float* __restrict__ mean,
+                                                             const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                             const double* __restrict__ sums, long long R,
+                                                             uint4* __restrict__ dx, uint4* __restrict__ dres, long long nvec,
+                                                             int CV, int C, const float* __restrict__ beta_rc) {
     const long long stride = (long long)gridDim.x * kT;
     const long long v0 = (long long)blockIdx.x * kT + threadIdx.x;
     const int cv = threadIdx.x % CV;
-    float mu[8], is[8], k0[8], k1[8], k2[8], sh[8];
+    float kg[8], kx[8], kc[8], sh[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int c = cv * 8 + i;
-        mu[i] = mean[c];
-        is[i] = invstd[c];
-        k0[i] = gamma[c] * is[i];
-        k1[i] = (float)(sums[c] / (double)R);
-        k2[i] = (float)(sums[C + c] / (double)R);
-        sh[i] = beta_rc ? beta_rc[c] - mu[i] * k0[i] : 0.f;
+        const float mu = mean[c], is = invstd[c];
+        kg[i] = gamma[c] * is;
+        const float k1 = (float)(sums[c] / (double)R), k2 = (float)(sums[C + c] / (double)R);
+        kx[i] = -kg[i] * is * k2;
+        kc[i] = -kg[i] * k1 - kx[i] * mu;
+        sh[i] = beta_rc ? beta_rc[c] - mu * kg[i] : 0.f;
     }
     for (long long v = v0; v < nvec; v += 2 * stride) {
         const long long w = v + stride;
@@ -244,13 +247,12 @@ __global__ void __launch_bounds__(kT) bn_bwd_apply_kernel(const uint4* __restric
                 for (int i = 0; i < 8; ++i) g[i] = (mk[u] >> i) & 1u ? g[i] : 0.f;
             } else if (beta_rc) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) g[i] = fmaf(fx[i], k0[i], sh[i]) > 0.f ? g[i] : 0.f;
+                for (int i = 0; i < 8; ++i) g[i] = fmaf(fx[i], kg[i], sh[i]) > 0.f ? g[i] : 0.f;
             }
             if (dres) dres[vv] = pack8(g);
-            float o[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = k0[i] * (g[i] - k1[i] - (fx[i] - mu[i]) * is[i] * k2[i]);
-            dx[vv] = pack8(o);
+            for (int i = 0; i < 8; ++i) fx[i] = fmaf(kg[i], g[i], fmaf(kx[i], fx[i], kc[i]));
+            dx[vv] = pack8(fx);
         }
     }
 }
@@ -533,6 +535,15 @@ __global__ void __launch_bounds__(kT) stem_pack_kernel(const float* __restrict__
 }
 
 inline int stream_grid(long long nvec) { return (int)min((long long)148 * 16, (nvec + kT - 1) / kT); }
+// grid = (CTAs resident per SM) x (SM count) x waves: grid-stride / contiguous-chunk kernels finish in whole waves
+template <typename K>
+inline int wave_grid(K kernel, long long nvec, int waves) {
+    int occ = 0, sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kT, 0) != cudaSuccess || occ < 1) occ = 2;
+    return (int)min((long long)sms * occ * waves, (nvec + kT - 1) / kT);
+}
 inline bool ok_c(int C) { return C >= 8 && C % 8 == 0 && (kT % (C / 8) == 0); }
 
 }  // namespace
@@ -545,7 +556,9 @@ extern "C" int sd_bn_stats_nhwc_bf16(const void* x, long long R, int C, double* 
     cudaStream_t st = (cudaStream_t)stream;
     SD_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
     const long long nvec = R * (C / 8);
-    const int grid = (int)min((long long)148 * 8, (nvec + kT - 1) / kT);
+    static int occ_grid = 0;
+    if (!occ_grid) occ_grid = wave_grid(bn_reduce_kernel<0>, 1ll << 40, 1);
+    const int grid = (int)min((long long)occ_grid, (nvec + kT - 1) / kT);
     bn_reduce_kernel<0><<<grid, kT, 0, st>>>((const uint4*)x, nullptr, nullptr, nullptr, nullptr, nvec, C / 8, sums, C, nullptr,
                                              nullptr);
     SD_LAUNCH_CHECK();
@@ -574,13 +587,18 @@ extern "C" int sd_bn_bwd_nhwc_bf16(const void* dy, const void* relu_mask, const 
     cudaStream_t st = (cudaStream_t)stream;
     SD_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
     const long long nvec = R * (C / 8);
-    const int grid = (int)min((long long)148 * 8, (nvec + kT - 1) / kT);
+    static int occ_grid = 0, occ_grid_apply = 0;
+    if (!occ_grid) {
+        occ_grid = wave_grid(bn_reduce_kernel<1>, 1ll << 40, 1);
+        occ_grid_apply = wave_grid(bn_bwd_apply_kernel, 1ll << 40, 4);
+    }
+    const int grid = (int)min((long long)occ_grid, (nvec + kT - 1) / kT);
     bn_reduce_kernel<1><<<grid, kT, 0, st>>>((const uint4*)x, (const uint4*)dy, (const unsigned char*)relu_mask, mean, invstd, nvec,
                                              C / 8, sums, C, gamma, relu_mask ? nullptr : beta_recompute);
     SD_LAUNCH_CHECK();
     bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, C, dgamma, dbeta);
     SD_LAUNCH_CHECK();
-    bn_bwd_apply_kernel<<<stream_grid(nvec), kT, 0, st>>>((const uint4*)dy, (const unsigned char*)relu_mask, (const uint4*)x, mean,
+    bn_bwd_apply_kernel<<<(int)min((long long)occ_grid_apply, (nvec + kT - 1) / kT), kT, 0, st>>>((const uint4*)dy, (const unsigned char*)relu_mask, (const uint4*)x, mean,
                                                           invstd, gamma, sums, R, (uint4*)dx, (uint4*)dres, nvec, C / 8, C,
                                                           relu_mask ? nullptr : beta_recompute);
     SD_LAUNCH_CHECK();
@@ -616,11 +634,15 @@ extern "C" int sd_maxpool3x3s2_nhwc_bf16_bwd(const void* dy, const void* idx, vo
     return SD_OK;
 }
 
+extern "C" int sd_stem_band_supported(int H, int W, int C) { return stem_band_supported(H, W, C) ? 1 : 0; }
+
 extern "C" int sd_stem_bn_relu_pool_nhwc_bf16_fwd(const void* x, const float* mean, const float* invstd, const float* gamma,
                                                   const float* beta, void* y, void* idx, int N, int H, int W, int C,
                                                   void* stream) {
     if (N <= 0) return SD_OK;
     if (!x || !mean || !invstd || !gamma || !beta || !y || !idx || !ok_c(C)) return SD_ERR_BAD_ARG;
+    if (stem_band_supported(H, W, C))   // TMA-staged row bands (stem_band.cu)
+        return stem_band_fwd(x, mean, invstd, gamma, beta, y, idx, N, H, W, (cudaStream_t)stream);
     const int HO = (H + 2 - 3) / 2 + 1, WO = (W + 2 - 3) / 2 + 1;
     const long long total = (long long)N * HO * WO * (C / 8);
     (void)total;
@@ -645,6 +667,13 @@ extern "C" int sd_stem_bn_relu_pool_nhwc_bf16_bwd(const void* dpool, const void*
     cudaStream_t st = (cudaStream_t)stream;
     const int HO = (H + 2 - 3) / 2 + 1, WO = (W + 2 - 3) / 2 + 1;
     SD_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+    if (stem_band_supported(H, W, C)) {   // scatter-in-shared-memory row bands (stem_band.cu)
+        int rc = stem_band_bwd(dpool, idx, x, mean, invstd, gamma, beta, sums, nullptr, N, H, W, 0, st);
+        if (rc != SD_OK) return rc;
+        bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, C, dgamma, dbeta);
+        SD_LAUNCH_CHECK();
+        return stem_band_bwd(dpool, idx, x, mean, invstd, gamma, beta, sums, dx, N, H, W, 1, st);
+    }
     const long long nvec = (long long)N * H * W * (C / 8);
     const int grid = (int)min((long long)148 * 8, (nvec + kT - 1) / kT);
     stem_bwd_kernel<0><<<grid, kT, 0, st>>>((const uint4*)dpool, (const uint2*)idx, (const uint4*)x, mean, invstd, gamma, beta,

@@ -124,13 +124,16 @@ class StemBNReLUPool(torch.autograd.Function):
         dy = _cl(dy)
         dgamma = torch.empty(C, device=x.device, dtype=torch.float32)
         dbeta = torch.empty(C, device=x.device, dtype=torch.float32)
-        # gradient w.r.t. the (never materialised) activated map, then BatchNorm backward with the ReLU mask
-        # recomputed from x.  (A single gather-fused kernel, sd_stem_bn_relu_pool_nhwc_bf16_bwd, exists but measured
-        # slower: it is instruction-bound on the arg-max tap matching.)
-        dact = torch.empty_like(x)
-        ops.maxpool_bwd(dy, idx, dact, N, H, W, C)
         dx = torch.empty_like(x)
-        ops.bn_bwd(dact, None, x, mean, invstd, gamma, ctx.sums, dx, None, dgamma, dbeta, N * H * W, C, beta_recompute=beta)
+        if ops.stem_band_supported(H, W, C):
+            # row-band kernels: the pooled gradient is scattered into shared memory, the ReLU mask recomputed from x;
+            # pass 0 = per-channel reductions, pass 1 = dx.  The activated map's gradient is never materialised.
+            ops.stem_bwd(dy, idx, x, mean, invstd, gamma, beta, ctx.sums, dx, dgamma, dbeta, N, H, W, C)
+        else:
+            # generic shapes: gradient w.r.t. the activated map, then BatchNorm backward with the recomputed ReLU mask
+            dact = torch.empty_like(x)
+            ops.maxpool_bwd(dy, idx, dact, N, H, W, C)
+            ops.bn_bwd(dact, None, x, mean, invstd, gamma, ctx.sums, dx, None, dgamma, dbeta, N * H * W, C, beta_recompute=beta)
         return dx, dgamma, dbeta, None, None, None, None, None
 
 

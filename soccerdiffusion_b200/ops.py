@@ -333,9 +333,13 @@ def stem_fwd(x, mean, invstd, gamma, beta, y, idx, N, H, W, C):
     _count()
 
 
+def stem_band_supported(H, W, C) -> bool:
+    return _lib.lib().sd_stem_band_supported(H, W, C) == 1
+
+
 def stem_bwd(dpool, idx, x, mean, invstd, gamma, beta, sums, dx, dgamma, dbeta, N, H, W, C):
-    # two passes, each reads x once and the pooled gradient + taps; the second writes dx
-    nb = 2.0 * N * H * W * C * 3 + 2 * (2.0 * N * H * W * C / 4 + N * H * W * C / 4)
+    # two passes, each reads x once (2 B/elem) and the pooled gradient + taps (3 B per pooled elem); the second writes dx
+    nb = 2.0 * N * H * W * C * 3 + 2 * (3.0 * N * H * W * C / 4)
     with _Timed("stem_bn_relu_pool_bwd", 0.0, nb, f"[N{N} H{H} C{C}]"):
         check(_lib.lib().sd_stem_bn_relu_pool_nhwc_bf16_bwd(dpool.data_ptr(), idx.data_ptr(), x.data_ptr(), mean.data_ptr(),
                                                             invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),

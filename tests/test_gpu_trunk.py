@@ -73,7 +73,8 @@ def test_maxpool_forward_backward(N, C, H, W):
     assert rel(xg.grad.float(), xf.grad) < 5e-3   # sums of <= 4 bf16 gradients, rounded once to bf16
 
 
-@pytest.mark.parametrize("N,C,H,W", [(3, 64, 112, 112), (2, 64, 30, 34), (1, 16, 7, 9)])
+@pytest.mark.parametrize("N,C,H,W", [(3, 64, 112, 112), (2, 64, 30, 34), (1, 16, 7, 9), (2, 64, 33, 47), (5, 64, 2, 2),
+                                     (1, 64, 9, 112), (2, 64, 20, 120)])
 def test_fused_stem_bn_relu_pool(N, C, H, W):
     from soccerdiffusion_b200.ml.model.encoder.trunk import StemBNReLUPool
 
@@ -118,14 +119,17 @@ def test_stem_pack_and_space_to_depth_conv_equal_conv1():
     assert rel(g1, conv.weight.grad) < 1e-2
 
 
-def test_fused_stem_backward_kernel_matches_two_kernel_path():
-    """sd_stem_bn_relu_pool_nhwc_bf16_bwd (single gather-fused backward, kept as an alternative) against the default
-    path (max-pool backward + BatchNorm backward with the recomputed ReLU mask)."""
+@pytest.mark.parametrize("N,H,W", [(2, 40, 48), (3, 112, 112), (2, 31, 45)])
+def test_stem_band_backward_matches_two_kernel_path(N, H, W):
+    """sd_stem_bn_relu_pool_nhwc_bf16_bwd (row-band kernels: shared-memory scatter of the pooled gradient, ReLU mask
+    recomputed) against the generic path (max-pool backward + BatchNorm backward with the recomputed ReLU mask), both
+    fed with the tensors the band forward saved (same arg-max tap encoding)."""
     from soccerdiffusion_b200 import ops
     from soccerdiffusion_b200.ml.model.encoder.trunk import StemBNReLUPool
 
     torch.manual_seed(3)
-    N, C, H, W = 2, 64, 40, 48
+    C = 64
+    assert ops.stem_band_supported(H, W, C)
     x = (_cl_bf16(N, C, H, W) * 1.2 + 0.1).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     gamma = (torch.rand(C, device="cuda") + 0.5).requires_grad_(True)
     beta = (torch.randn(C, device="cuda") * 0.2).requires_grad_(True)
@@ -134,14 +138,15 @@ def test_fused_stem_backward_kernel_matches_two_kernel_path():
     y = StemBNReLUPool.apply(xg, gamma, beta, rm, rv, True, 0.1, 1e-5)
     go = _cl_bf16(*y.shape)
     xs, idx, mean, invstd, g_, b_ = y.grad_fn.saved_tensors   # read before backward() frees them
-    y.backward(go)
-    # the same backward through the fused kernel, from the tensors the forward saved
+    y.backward(go)                                            # band kernels
+    # generic two-kernel path from the same saved tensors
     sums = torch.empty(2 * C, device="cuda", dtype=torch.float64)
-    dx = torch.empty_like(xs)
+    dact, dx = torch.empty_like(xs), torch.empty_like(xs)
     dg, db = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
-    ops.stem_bwd(go, idx, xs, mean, invstd, g_, b_, sums, dx, dg, db, N, H, W, C)
-    assert rel(dx.float(), xg.grad.float()) < 1e-2
-    assert rel(dg, gamma.grad) < 1e-2 and rel(db, beta.grad) < 1e-2   # the two-kernel path rounds the pooled gradient to bf16
+    ops.maxpool_bwd(go, idx, dact, N, H, W, C)
+    ops.bn_bwd(dact, None, xs, mean, invstd, g_, sums, dx, None, dg, db, N * H * W, C, beta_recompute=b_)
+    assert rel(xg.grad.float(), dx.float()) < 1e-2
+    assert rel(gamma.grad, dg) < 1e-2 and rel(beta.grad, db) < 1e-2   # the two-kernel path rounds the pooled gradient to bf16
 
 
 @pytest.mark.parametrize("N,H,W", [(4, 224, 224), (3, 20, 36), (2, 64, 96), (1, 6, 6)])
