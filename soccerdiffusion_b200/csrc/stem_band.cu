@@ -114,6 +114,21 @@ __global__ void __launch_bounds__(kT, 3) stem_fwd_band_kernel(const uint4* __res
     }
 }
 
+// predicated accumulate (ISETP + @p FADD: one ALU-pipe instruction per routed tap instead of compare + select + add;
+// written in PTX because the C form is compiled into a divergent jump tree)
+__device__ __forceinline__ void add_if_eq(float& acc, unsigned tap, unsigned code, float g) {
+    asm("{\n\t.reg .pred q;\n\tsetp.eq.u32 q, %1, %2;\n\t@q add.f32 %0, %0, %3;\n\t}" : "+f"(acc) : "r"(tap), "r"(code), "f"(g));
+}
+// ReLU-masked accumulation of the two BatchNorm-backward reductions: if (act > 0) { a0 += g; a1 += g * x; }
+__device__ __forceinline__ void acc_if_pos(float& a0, float& a1, float act, float g, float x) {
+    asm("{\n\t.reg .pred q;\n\tsetp.gt.f32 q, %2, 0f00000000;\n\t@q add.f32 %0, %0, %3;\n\t@q fma.rn.f32 %1, %3, %4, %1;\n\t}"
+        : "+f"(a0), "+f"(a1) : "f"(act), "f"(g), "f"(x));
+}
+// v += (act > 0) ? s * g : 0
+__device__ __forceinline__ void fma_if_pos(float& v, float act, float s, float g) {
+    asm("{\n\t.reg .pred q;\n\tsetp.gt.f32 q, %1, 0f00000000;\n\t@q fma.rn.f32 %0, %2, %3, %0;\n\t}" : "+f"(v) : "f"(act), "f"(s), "f"(g));
+}
+
 // ---- backward --------------------------------------------------------------------------------------------------
 // Thread = (2x2 block of input pixels, 8-channel vector).  The block is reached by exactly four pooling windows
 // (ho in {j, j+1}, wo in {a, a+1} for block rows 2j,2j+1 and columns 2a,2a+1) and by nine (window, tap) pairs in
@@ -128,7 +143,7 @@ __global__ void __launch_bounds__(kT, 2) stem_bwd_block_kernel(const uint4* __re
                                                                uint4* __restrict__ dx, int N, int H, int W, int HO, int WO) {
     __shared__ float red[PASS == 0 ? 2 * kT * 9 : 1];
     const int tid = threadIdx.x, cv = tid & 7;
-    const long long R = (long long)N * H * W;
+    const double invR = 1.0 / (double)((long long)N * H * W);
     float sc[8], sh[8], kx[8], kc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -137,7 +152,7 @@ __global__ void __launch_bounds__(kT, 2) stem_bwd_block_kernel(const uint4* __re
         sc[i] = is * gamma[c];
         sh[i] = beta[c] - mu * sc[i];
         if (PASS == 1) {   // dx = sc*g + kx*x + kc  (see bn_bwd_apply_kernel)
-            const float k1 = (float)(sums[c] / (double)R), k2 = (float)(sums[64 + c] / (double)R);
+            const float k1 = (float)(sums[c] * invR), k2 = (float)(sums[64 + c] * invR);
             kx[i] = -sc[i] * is * k2;
             kc[i] = -sc[i] * k1 - kx[i] * mu;
         }
@@ -191,18 +206,18 @@ __global__ void __launch_bounds__(kT, 2) stem_bwd_block_kernel(const uint4* __re
                 for (int k = 0; k < 8; ++k) {
                     const unsigned tap = ((k < 4 ? ui[pr][pc].x : ui[pr][pc].y) >> (8 * (k & 3))) & 0xFFu;
                     if (pr == 0 && pc == 0) {          // rows tdy-1, columns tdx-1
-                        if (tap == 4u) acc[0][0][k] += g[k];
-                        if (tap == 5u) acc[0][1][k] += g[k];
-                        if (tap == 7u) acc[1][0][k] += g[k];
-                        if (tap == 8u) acc[1][1][k] += g[k];
+                        add_if_eq(acc[0][0][k], tap, 4u, g[k]);
+                        add_if_eq(acc[0][1][k], tap, 5u, g[k]);
+                        add_if_eq(acc[1][0][k], tap, 7u, g[k]);
+                        add_if_eq(acc[1][1][k], tap, 8u, g[k]);
                     } else if (pr == 0 && pc == 1) {   // tdx = 0 -> column 1
-                        if (tap == 3u) acc[0][1][k] += g[k];
-                        if (tap == 6u) acc[1][1][k] += g[k];
+                        add_if_eq(acc[0][1][k], tap, 3u, g[k]);
+                        add_if_eq(acc[1][1][k], tap, 6u, g[k]);
                     } else if (pr == 1 && pc == 0) {   // tdy = 0 -> row 1
-                        if (tap == 1u) acc[1][0][k] += g[k];
-                        if (tap == 2u) acc[1][1][k] += g[k];
+                        add_if_eq(acc[1][0][k], tap, 1u, g[k]);
+                        add_if_eq(acc[1][1][k], tap, 2u, g[k]);
                     } else {
-                        if (tap == 0u) acc[1][1][k] += g[k];
+                        add_if_eq(acc[1][1][k], tap, 0u, g[k]);
                     }
                 }
             }
@@ -213,16 +228,18 @@ __global__ void __launch_bounds__(kT, 2) stem_bwd_block_kernel(const uint4* __re
                 if (!vx[r][c]) continue;
                 float fx[8];
                 unpack8(ux[r][c], fx);
-                float* g = acc[r][c];
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (!(fmaf(fx[k], sc[k], sh[k]) > 0.f)) g[k] = 0.f;   // ReLU mask, recomputed
+                const float* g = acc[r][c];
+                // ReLU mask recomputed from x: act = x*sc + sh > 0
                 if (PASS == 0) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) { a0[k] += g[k]; a1[k] = fmaf(g[k], fx[k], a1[k]); }
+                    for (int k = 0; k < 8; ++k) acc_if_pos(a0[k], a1[k], fmaf(fx[k], sc[k], sh[k]), g[k], fx[k]);
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) fx[k] = fmaf(sc[k], g[k], fmaf(kx[k], fx[k], kc[k]));
+                    for (int k = 0; k < 8; ++k) {
+                        const float act = fmaf(fx[k], sc[k], sh[k]);
+                        fx[k] = fmaf(kx[k], fx[k], kc[k]);
+                        fma_if_pos(fx[k], act, sc[k], g[k]);
+                    }
                     dx[(((long long)n * H + h0 + r) * W + w0 + c) * 8 + cv] = pack8(fx);
                 }
             }

@@ -209,13 +209,14 @@ __global__ void __launch_bounds__(kT, 3) bn_bwd_apply_kernel(const uint4* __rest
     const long long stride = (long long)gridDim.x * kT;
     const long long v0 = (long long)blockIdx.x * kT + threadIdx.x;
     const int cv = threadIdx.x % CV;
+    const double invR = 1.0 / (double)R;
     float kg[8], kx[8], kc[8], sh[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int c = cv * 8 + i;
         const float mu = mean[c], is = invstd[c];
         kg[i] = gamma[c] * is;
-        const float k1 = (float)(sums[c] / (double)R), k2 = (float)(sums[C + c] / (double)R);
+        const float k1 = (float)(sums[c] * invR), k2 = (float)(sums[C + c] * invR);
         kx[i] = -kg[i] * is * k2;
         kc[i] = -kg[i] * k1 - kx[i] * mu;
         sh[i] = beta_rc ? beta_rc[c] - mu * kg[i] : 0.f;

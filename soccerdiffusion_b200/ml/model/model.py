@@ -156,18 +156,49 @@ class End2EndDiffusionTransformer(nn.Module):
 
     # ----------------------------------------------------------------------------------------
     def encode_input_data(self, input_data: dict[str, torch.Tensor]) -> list[torch.Tensor]:
-        context = []
+        """Runs the enabled encoders; returns their token tensors in the reference's fixed order (model.py:123-148).
+
+        The encoders share no data, so on a CUDA device the sequence encoders are launched on side streams beside the
+        image path (which stays on the caller's stream) and joined before returning; autograd replays every node on
+        the stream of its forward, so the backward passes overlap the same way.  Works inside CUDA-graph capture
+        (the side streams fork from / join into the capturing stream)."""
+        from soccerdiffusion_b200 import runtime
+
+        jobs = []   # (encoder, input, stays on the caller's stream)
         if self.action_history_encoder is not None:
-            context.append(self.action_history_encoder(input_data["joint_command_history"]))
+            jobs.append((self.action_history_encoder, input_data["joint_command_history"], False))
         if self.imu_encoder is not None:
-            context.append(self.imu_encoder(input_data["rotation"]))
+            jobs.append((self.imu_encoder, input_data["rotation"], False))
         if self.joint_states_encoder is not None:
-            context.append(self.joint_states_encoder(input_data["joint_state"]))
+            jobs.append((self.joint_states_encoder, input_data["joint_state"], False))
         if self.image_sequence_encoder is not None:
-            context.append(self.image_sequence_encoder(input_data["image_data"]))
+            jobs.append((self.image_sequence_encoder, input_data["image_data"], True))
         if self.game_state_encoder is not None:
-            context.append(self.game_state_encoder(input_data["game_state"]))
-        return context
+            jobs.append((self.game_state_encoder, input_data["game_state"], True))
+        n_side = sum(1 for _, x, main in jobs if not main)
+        if not (runtime.concurrent_encoders() and n_side >= 1 and len(jobs) >= 2 and all(x.is_cuda for _, x, _ in jobs)):
+            return [enc(x) for enc, x, _ in jobs]
+        cur = torch.cuda.current_stream()
+        side = runtime.side_streams(cur.device, n_side)
+        out: list = [None] * len(jobs)
+        k = 0
+        for i, (enc, x, main) in enumerate(jobs):
+            if main:
+                continue
+            s = side[k]
+            k += 1
+            s.wait_stream(cur)
+            with torch.cuda.stream(s):
+                out[i] = enc(x)
+        for i, (enc, x, main) in enumerate(jobs):
+            if main:
+                out[i] = enc(x)
+        for s in side[:n_side]:
+            cur.wait_stream(s)
+        for i, (_, _, main) in enumerate(jobs):
+            if not main:
+                out[i].record_stream(cur)   # allocated on a side stream, consumed on the caller's
+        return out
 
     def forward(
         self, input_data: dict[str, torch.Tensor], noisy_action_predictions: torch.Tensor, step: torch.Tensor

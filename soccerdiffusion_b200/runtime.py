@@ -71,6 +71,32 @@ def set_dropout(p: float):
     DROPOUT_P = float(p)
 
 
+_concurrent_encoders = os.environ.get("SD_B200_CONCURRENT_ENCODERS", "1") == "1"
+
+
+def set_concurrent_encoders(on: bool):
+    """The context encoders are independent until the denoiser: by default the sequence encoders run on side CUDA
+    streams beside the image trunk (forward, and — because autograd replays each node on its forward stream —
+    backward), joined before the denoiser.  Off = one stream, the reference's call order."""
+    global _concurrent_encoders
+    _concurrent_encoders = bool(on)
+
+
+def concurrent_encoders() -> bool:
+    return _concurrent_encoders
+
+
+_side_streams: dict = {}
+
+
+def side_streams(device, n: int):
+    """Process-wide pool of side CUDA streams per device (created lazily, reused by every model instance)."""
+    lst = _side_streams.setdefault((device.type, device.index), [])
+    while len(lst) < n:
+        lst.append(torch.cuda.Stream(device=device))
+    return lst[:n]
+
+
 _direct_grads = False
 
 
