@@ -303,20 +303,54 @@ def run_ours(args):
     from soccerdiffusion_b200.ml.training import DevicePrefetcher
 
     step({k: v.to(dev, non_blocking=True) for k, v in host.items()}).item()
+    _run_e2e(step, DevicePrefetcher((host for _ in range(2)), dev), dev)   # untimed: allocations of the feeder path
     sync()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     feeder = DevicePrefetcher((host for _ in range(args.steps)), dev)   # first copies are issued inside the timed region
-    for b in feeder:
-        step(b).item()
+    losses = _run_e2e(step, feeder, dev)
     e3.record()
     sync()
     ms_e2e = e2.elapsed_time(e3)
 
+    # ---- e2e with RAW uint8 frames: the reference's host preprocessing (ToDtype + Normalize) runs on
+    #      the device inside the stem's packing kernel; the per-step host->device copy is 4x smaller ---------------------
+    ms_e2e_u8, h2d_u8 = None, None
+    used_graph = graphed is not None
+    if args.workload == "full" and args.uint8_leg:
+        host8 = config.synthetic_batch(hp, bs, None, seed=rank, pin=True, uint8_images=True)
+        h2d_u8 = sum(v.numel() * v.element_size() for v in host8.values())
+        step8 = None
+        if used_graph:
+            graphed = None          # the fp32-frame graph (and its private memory pool) is no longer needed
+            import gc
+
+            gc.collect()
+            torch.cuda.empty_cache()
+            try:
+                step8 = GraphedTrainStep(model, opt, sch, {k: v.to(dev) for k, v in host8.items()}, lr_scheduler=lrs,
+                                         data_parallel=world > 1, warmup_steps=2)
+            except Exception as e:
+                sys.stderr.write(f"[bench] uint8 leg: graph capture failed ({type(e).__name__}: {e}); eager launches\n")
+                torch.cuda.synchronize()
+        if step8 is None:
+            step8 = lambda b: train_step(model, opt, sch, norm, b, lr_scheduler=lrs, data_parallel=world > 1)
+        step8({k: v.to(dev, non_blocking=True) for k, v in host8.items()}).item()
+        _run_e2e(step8, DevicePrefetcher((host8 for _ in range(2)), dev), dev)   # untimed: allocations of the feeder path
+        sync()
+        e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e4.record()
+        _run_e2e(step8, DevicePrefetcher((host8 for _ in range(args.steps)), dev), dev)
+        e5.record()
+        sync()
+        ms_e2e_u8 = e4.elapsed_time(e5)
+        del step8
+
     if world > 1:
-        tt = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        tt = torch.tensor([ms, ms_e2e, ms_e2e_u8 or 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = tt.tolist()
+        ms, ms_e2e, mu8 = tt.tolist()
+        ms_e2e_u8 = mu8 if ms_e2e_u8 is not None else None
 
     # ---- per-kernel-class device time (CUDA events around every libsd_b200 GEMM/attention launch) ----
     roofline = None
@@ -390,8 +424,13 @@ def run_ours(args):
                         global_batch=gb, per_gpu_batch=bs, parallelism=f"dp{world}", dropout_p=0.1,
                         l2="inputs %.2f GB/step per GPU > 126 MB L2; no explicit flush" % (h2d / 1e9),
                         precision_mode=args.precision,
-                        launch="one CUDA graph replay per step" if graphed is not None else "kernel by kernel"),
-            e2e=dict(value=gb * args.steps / (ms_e2e / 1e3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4),
+                        launch="one CUDA graph replay per step" if used_graph else "kernel by kernel"),
+            e2e=dict(value=gb * args.steps / (ms_e2e / 1e3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
+                     loss_readback="every step, pinned async copy, read on the host one step behind the launch front",
+                     input="float32 frames preprocessed on the host (the reference's dataset output)"),
+            e2e_uint8=(dict(value=gb * args.steps / (ms_e2e_u8 / 1e3), unit=UNIT, h2d_bytes_per_step=h2d_u8, d2h_bytes_per_step=4,
+                            input="raw uint8 frames; ToDtype(scale)+Normalize fused into the stem packing kernel on the device")
+                       if ms_e2e_u8 else None),
             gpu_launches=launches, clocks=clk, roofline=roofline, kernel_classes=kernel_classes, cpu_baseline=cpu, ddim=ddim)
         emit(line)
     if world > 1:
@@ -402,6 +441,31 @@ def run_ours(args):
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
+
+
+def _run_e2e(step, feeder, dev):
+    """End-to-end loop: every step's loss is copied device->host (pinned, asynchronous) and READ on the host inside the
+    timed region, one step behind the launch front — the host blocks on step i-1's loss while step i runs, so the
+    device never idles waiting for the next launch (a training loop that logs its loss does exactly this)."""
+    import torch
+
+    bufs = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    pending, losses, i = None, [], 0
+    for b in feeder:
+        loss = step(b)
+        buf = bufs[i % 2]
+        buf.copy_(loss.reshape(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        if pending is not None:
+            pending[0].synchronize()
+            losses.append(float(pending[1][0]))
+        pending = (ev, buf)
+        i += 1
+    if pending is not None:
+        pending[0].synchronize()
+        losses.append(float(pending[1][0]))
+    return losses
 
 
 def _inscope_step(model, opt, sch, batch, img_tokens, lrs, dp):
@@ -534,6 +598,8 @@ def main():
                     help="default.yaml, or BASELINE.json configs[4]: 2x depth, 20 frames, T=20 (use a smaller --batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ddim", action="store_true")
+    ap.add_argument("--no-uint8-leg", dest="uint8_leg", action="store_false",
+                    help="skip the extra end-to-end leg fed with raw uint8 frames")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="launch the training step kernel by kernel instead of replaying one captured CUDA graph")
     ap.add_argument("--ncu-range", action="store_true",

@@ -173,6 +173,12 @@ int sd_bn_bwd_nhwc_bf16(const void* dy, const void* relu_mask, const void* x, co
  * space-to-depth (channel = c*4 + dy*2 + dx, 12 used), the layout in which the 7x7/s2/p3 stem convolution
  * (torchvision resnet conv1; ml/model/encoder/image.py:55-73) is a 4x4/s1 convolution with Cin=16 */
 int sd_stem_pack_s2d_bf16(const float* images, void* out, int N, int H, int W, void* stream);
+/* Same packing from the RAW uint8 image (N,3,H,W): the reference's host-side torchvision preprocessing
+ * v2.ToDtype(float32, scale=True) -> v2.Normalize(mean, std) (dataset/pytorch.py:198-204, ml/inference/ros.py:190-196) is
+ * applied on the device in the same fp32 operations, (u * fp32(1/255) - mean[c]) / std[c], so the result is bit-identical to
+ * packing the host-normalised float image; the host->device copy is 4x smaller. */
+int sd_stem_pack_s2d_u8(const void* images_u8, void* out, int N, int H, int W, float mean0, float mean1, float mean2,
+                        float std0, float std1, float std2, void* stream);
 /* Weight gradient of the stem convolution in its space-to-depth form: dw_s2d[256][64] fp32 (row = kh*64 + kw*16 + ci,
  * column = output channel) from the packed image (sd_stem_pack_s2d_bf16) and dy bf16 NHWC (N,H/2,W/2,64); tcgen05,
  * both operands MN-major.  Replaces cuDNN's conv1 wgrad (ml/model/encoder/image.py:55-73 under autograd). */

@@ -93,6 +93,7 @@ SIGNATURES = {
     "sd_bn_apply_nhwc_bf16": [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_ll, c_i, c_f],
     "sd_bn_bwd_nhwc_bf16": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_ll, c_i, c_f],
     "sd_stem_pack_s2d_bf16": [c_f, c_f, c_i, c_i, c_i, c_f],
+    "sd_stem_pack_s2d_u8": [c_f, c_f, c_i, c_i, c_i, c_fl, c_fl, c_fl, c_fl, c_fl, c_fl, c_f],
     "sd_stem_fprop_s2d_bf16": [c_f, c_f, c_f, c_i, c_i, c_i, c_f],
     "sd_stem_wgrad_s2d_bf16": [c_f, c_f, c_f, c_i, c_i, c_i, c_f],
     "sd_stem_band_supported": [c_i, c_i, c_i],

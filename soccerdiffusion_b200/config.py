@@ -54,8 +54,9 @@ def build_model(params: dict):
     )
 
 
-def synthetic_batch(params: dict, batch: int, device, seed: int = 0, pin: bool = False) -> dict:
-    """Synthetic inputs of the named shapes: joints U[0,2pi), unit quaternions, N(0,1) images."""
+def synthetic_batch(params: dict, batch: int, device, seed: int = 0, pin: bool = False, uint8_images: bool = False) -> dict:
+    """Synthetic inputs of the named shapes: joints U[0,2pi), unit quaternions, N(0,1) images
+    (``uint8_images``: raw U{0..255} frames instead — the model then runs the reference's preprocessing on the device)."""
     import math
 
     import torch
@@ -70,7 +71,10 @@ def synthetic_batch(params: dict, batch: int, device, seed: int = 0, pin: bool =
     b["rotation"] = q / q.norm(dim=-1, keepdim=True)
     if params.get("use_images", True):
         R = params.get("image_resolution", 480)
-        b["image_data"] = torch.randn(batch, params["image_context_length"], 3, R, R, generator=g)
+        if uint8_images:
+            b["image_data"] = torch.randint(0, 256, (batch, params["image_context_length"], 3, R, R), generator=g, dtype=torch.uint8)
+        else:
+            b["image_data"] = torch.randn(batch, params["image_context_length"], 3, R, R, generator=g)
     b["game_state"] = torch.randint(0, 4, (batch,), generator=g)
     b["joint_command"] = torch.rand(batch, params["trajectory_prediction_length"], J, generator=g) * (2 * math.pi)
     if pin:

@@ -505,8 +505,14 @@ __global__ void __launch_bounds__(kT) stem_bwd_kernel(const uint4* __restrict__ 
 // ---- stem input packing: fp32 NCHW image -> bf16 NHWC, 2x2 space-to-depth of the 3-pixel zero-padded image -------
 // out[n][hp][wp][c*4 + dy*2 + dx] = in[n][c][2*hp + dy - 3][2*wp + dx - 3]  (12 channels, zero-padded to 16):
 // the operand layout under which conv1 (7x7/s2/p3, Cin=3) becomes a 4x4/s1 convolution with Cin=16.
-__global__ void __launch_bounds__(kT) stem_pack_kernel(const float* __restrict__ in, uint4* __restrict__ out, int N, int H,
-                                                       int W, int Hp, int Wp) {
+// U8 = true: the input is the raw uint8 image (N,3,H,W); the reference's torchvision preprocessing (v2.ToDtype(float32,
+// scale=True) -> v2.Normalize(mean, std); dataset/pytorch.py:198-204, ml/inference/ros.py:190-196) is applied here in the
+// same fp32 operations (u * fp32(1/255), - mean, / std: torchvision's to_dtype_image / normalize_image), so the packed bf16 image is bit-identical to packing the host-normalised one
+// while the host->device copy and this kernel's read shrink 4x.
+struct PackNorm { float mean[3], std[3]; };
+template <bool U8>
+__global__ void __launch_bounds__(kT) stem_pack_kernel(const void* __restrict__ in_, uint4* __restrict__ out, int N, int H,
+                                                       int W, int Hp, int Wp, PackNorm nm) {
     const long long total = (long long)N * Hp * Wp;
     for (long long o = (long long)blockIdx.x * kT + threadIdx.x; o < total; o += (long long)gridDim.x * kT) {
         const int wp = (int)(o % Wp);
@@ -518,7 +524,7 @@ __global__ void __launch_bounds__(kT) stem_pack_kernel(const float* __restrict__
         for (int i = 0; i < 16; ++i) f[i] = 0.f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const float* plane = in + ((long long)n * 3 + c) * H * W;
+            const long long plane = ((long long)n * 3 + c) * H * W;
 #pragma unroll
             for (int dy = 0; dy < 2; ++dy) {
                 const int h = 2 * hp + dy - 3;
@@ -526,7 +532,14 @@ __global__ void __launch_bounds__(kT) stem_pack_kernel(const float* __restrict__
 #pragma unroll
                 for (int dx = 0; dx < 2; ++dx) {
                     const int w = 2 * wp + dx - 3;
-                    if (w >= 0 && w < W) f[c * 4 + dy * 2 + dx] = __ldg(plane + (long long)h * W + w);
+                    if (w < 0 || w >= W) continue;
+                    const long long i = plane + (long long)h * W + w;
+                    if (U8) {
+                        const float u = (float)__ldg(reinterpret_cast<const unsigned char*>(in_) + i);
+                        f[c * 4 + dy * 2 + dx] = __fdiv_rn(__fsub_rn(__fmul_rn(u, (float)(1.0 / 255.0)), nm.mean[c]), nm.std[c]);
+                    } else {
+                        f[c * 4 + dy * 2 + dx] = __ldg(reinterpret_cast<const float*>(in_) + i);
+                    }
                 }
             }
         }
@@ -693,7 +706,19 @@ extern "C" int sd_stem_pack_s2d_bf16(const float* images, void* out, int N, int 
     if (!images || !out || (H & 1) || (W & 1)) return SD_ERR_BAD_ARG;
     const int Hp = (H + 6) / 2, Wp = (W + 6) / 2;
     const long long total = (long long)N * Hp * Wp;
-    stem_pack_kernel<<<stream_grid(total), kT, 0, (cudaStream_t)stream>>>(images, (uint4*)out, N, H, W, Hp, Wp);
+    stem_pack_kernel<false><<<stream_grid(total), kT, 0, (cudaStream_t)stream>>>(images, (uint4*)out, N, H, W, Hp, Wp, PackNorm{});
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+}
+
+extern "C" int sd_stem_pack_s2d_u8(const void* images_u8, void* out, int N, int H, int W, float mean0, float mean1, float mean2,
+                                   float std0, float std1, float std2, void* stream) {
+    if (N <= 0) return SD_OK;
+    if (!images_u8 || !out || (H & 1) || (W & 1) || std0 == 0.f || std1 == 0.f || std2 == 0.f) return SD_ERR_BAD_ARG;
+    const int Hp = (H + 6) / 2, Wp = (W + 6) / 2;
+    const long long total = (long long)N * Hp * Wp;
+    PackNorm nm{{mean0, mean1, mean2}, {std0, std1, std2}};
+    stem_pack_kernel<true><<<stream_grid(total), kT, 0, (cudaStream_t)stream>>>(images_u8, (uint4*)out, N, H, W, Hp, Wp, nm);
     SD_LAUNCH_CHECK();
     return SD_OK;
 }

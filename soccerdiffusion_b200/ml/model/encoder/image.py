@@ -59,7 +59,9 @@ class AbstractImageEncoder(nn.Module):
         raise NotImplementedError
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """(B, F, 3, R, R) -> (B, F, d)"""
+        """(B, F, 3, R, R) -> (B, F, d).  Besides the reference's normalised float32 frames, raw uint8 frames are accepted:
+        the host preprocessing (ToDtype(scale) + Normalize, dataset/pytorch.py:198-204) then runs on the device, fused
+        into the stem's packing kernel in bf16 mode."""
         _lib.require_cuda(x)
         images = x.reshape(-1, *x.shape[2:])
         tokens = self.tokens(images)
@@ -98,7 +100,9 @@ class ResNetImageEncoder(AbstractImageEncoder):
 
             if _trunk.supported(e):
                 return _trunk.resnet_trunk_bf16(e, images)
-        images = images.contiguous(memory_format=torch.channels_last)
+        from soccerdiffusion_b200.ml.model.encoder.trunk import normalize_u8
+
+        images = normalize_u8(images).contiguous(memory_format=torch.channels_last)   # raw uint8 frames: preprocess on device
         with _trunk_autocast():
             x = e.maxpool(e.relu(e.bn1(e.conv1(images))))
             x = e.layer4(e.layer3(e.layer2(e.layer1(x))))
@@ -138,7 +142,10 @@ class SwinTransformerImageEncoder(AbstractImageEncoder):
         self.encoder.head = nn.Linear(self.encoder.head.in_features, hidden_dim)
 
     def tokens(self, images: torch.Tensor) -> torch.Tensor:
+        from soccerdiffusion_b200.ml.model.encoder.trunk import normalize_u8
+
         e = self.encoder
+        images = normalize_u8(images)
         with _trunk_autocast():
             x = e.flatten(e.avgpool(e.permute(e.norm(e.features(images)))))
         return LinearFn.apply(runtime.get_precision(), x.float().contiguous(), e.head.weight, e.head.bias)

@@ -196,10 +196,20 @@ class StemConvS2D(torch.autograd.Function):
             g = g.reshape(4, 4, Cin, 2, 2, Cout).permute(5, 2, 0, 3, 1, 4)  # (cout, c, kh, dy, kw, dx)
             gw = g.reshape(Cout, Cin, 8, 8)[:, :, :7, :7]
             return None, gw.to(weight.dtype).contiguous()
-        x = images.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+        x = normalize_u8(images).to(dtype=torch.bfloat16, memory_format=torch.channels_last)
         gw = torch.ops.aten.convolution_backward(_cl(dy), x, weight.to(torch.bfloat16), None, (2, 2), (3, 3), (1, 1), False,
                                                  (0, 0), 1, (False, True, False))[1]
         return None, gw.to(weight.dtype)
+
+
+def normalize_u8(images: torch.Tensor) -> torch.Tensor:
+    """Device-side replica of the reference's host preprocessing for raw uint8 frames (v2.ToDtype(float32, scale=True)
+    -> v2.Normalize(ImageNet mean/std); dataset/pytorch.py:198-204): same fp32 operations, identity for float input."""
+    if images.dtype != torch.uint8:
+        return images
+    mean = torch.tensor(ops.IMAGENET_MEAN, device=images.device, dtype=torch.float32).view(-1, 1, 1)
+    std = torch.tensor(ops.IMAGENET_STD, device=images.device, dtype=torch.float32).view(-1, 1, 1)
+    return images.to(torch.float32).mul_(1.0 / 255).sub_(mean).div_(std)
 
 
 def _stem_conv_s2d_raw(images, weight, return_packed: bool = False):
@@ -207,7 +217,10 @@ def _stem_conv_s2d_raw(images, weight, return_packed: bool = False):
     Cout = weight.shape[0]
     Hp, Wp = (H + 6) // 2, (W + 6) // 2
     xp = torch.empty((N, Hp, Wp, 16), device=images.device, dtype=torch.bfloat16)
-    ops.stem_pack(images.contiguous(), xp, N, H, W)
+    if images.dtype == torch.uint8:
+        ops.stem_pack_u8(images.contiguous(), xp, N, H, W)   # ToDtype(scale) + Normalize fused into the packing pass
+    else:
+        ops.stem_pack(images.contiguous(), xp, N, H, W)
     w = F.pad(weight.to(torch.bfloat16), (0, 1, 0, 1))
     w = w.view(Cout, Cin, 4, 2, 4, 2).permute(0, 1, 3, 5, 2, 4).reshape(Cout, Cin * 4, 4, 4)
     w = F.pad(w, (0, 0, 0, 0, 0, 16 - Cin * 4))                      # (Cout, 16, 4, 4)
@@ -242,12 +255,12 @@ def resnet_trunk_bf16(encoder, images: torch.Tensor) -> torch.Tensor:
     # cuDNN autotuning for the (fixed) convolution shapes of the trunk; restored on exit
     with torch.backends.cudnn.flags(enabled=True, benchmark=True), torch.autocast("cuda", dtype=torch.bfloat16):
         if _stem_is_s2d_compatible(encoder.conv1, images):
-            if images.dtype == torch.float32 and not images.requires_grad and encoder.conv1.bias is None:
+            if images.dtype in (torch.float32, torch.uint8) and not images.requires_grad and encoder.conv1.bias is None:
                 x = StemConvS2D.apply(images, encoder.conv1.weight)
             else:
-                x = _stem_conv_s2d(encoder.conv1, images)
+                x = _stem_conv_s2d(encoder.conv1, normalize_u8(images))
         else:
-            x = _conv(encoder.conv1, images.to(dtype=torch.bfloat16, memory_format=torch.channels_last))
+            x = _conv(encoder.conv1, normalize_u8(images).to(dtype=torch.bfloat16, memory_format=torch.channels_last))
         bn1 = encoder.bn1
         if bn1.training and bn1.track_running_stats and bn1.num_batches_tracked is not None:
             bn1.num_batches_tracked.add_(1)

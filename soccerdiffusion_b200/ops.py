@@ -356,6 +356,18 @@ def stem_pack(images, out, N, H, W):
     _count()
 
 
+IMAGENET_MEAN = (0.485, 0.456, 0.406)   # v2.Normalize constants of the reference (dataset/pytorch.py:202, ros.py:194)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def stem_pack_u8(images_u8, out, N, H, W, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    """uint8 (N,3,H,W) -> normalised, space-to-depth packed bf16 image (the host preprocessing moved onto the device)."""
+    with _Timed("stem_pack_s2d", 0.0, 3.0 * N * H * W + 32.0 * N * ((H + 6) // 2) * ((W + 6) // 2), f"[u8 N{N} H{H}]"):
+        check(_lib.lib().sd_stem_pack_s2d_u8(images_u8.data_ptr(), out.data_ptr(), N, H, W, *[float(m) for m in mean],
+                                             *[float(v) for v in std], stream_ptr()), "sd_stem_pack_s2d_u8")
+    _count()
+
+
 def stem_wgrad(xs2d, dy, dw, N, H, W):
     P = N * (H // 2) * (W // 2)
     with _Timed("stem_wgrad_s2d", 2.0 * 256 * 64 * P, 32.0 * N * ((H + 6) // 2) * ((W + 6) // 2) + 128.0 * P, f"[N{N} H{H}]"):

@@ -231,3 +231,66 @@ def test_fused_trunk_matches_library_trunk_bf16():
         ea, eb = rel(a[k], ref[k]), rel(b[k], ref[k])
         print(f"{k}: fused-vs-fp32 {ea:.3e}  torch-bf16-vs-fp32 {eb:.3e}")
         assert ea < max(2.0 * eb, 2e-2), (k, ea, eb)
+
+
+@pytest.mark.parametrize("N,H,W", [(3, 224, 224), (2, 20, 36)])
+def test_uint8_stem_pack_equals_reference_preprocessing(N, H, W):
+    """Raw uint8 frames packed by sd_stem_pack_s2d_u8 == the reference's host preprocessing (torchvision v2.ToDtype(float32,
+    scale=True) -> v2.Normalize(ImageNet), dataset/pytorch.py:198-204) followed by sd_stem_pack_s2d_bf16: bit for bit."""
+    from torchvision.transforms import v2
+
+    from soccerdiffusion_b200 import ops
+    from soccerdiffusion_b200.ml.model.encoder.trunk import normalize_u8
+
+    g = torch.Generator().manual_seed(5)
+    u8 = torch.randint(0, 256, (N, 3, H, W), generator=g, dtype=torch.uint8)
+    u8[0, :, 0, :4] = torch.tensor([0, 1, 254, 255], dtype=torch.uint8)
+    pre = v2.Compose([v2.ToDtype(torch.float32, scale=True), v2.Normalize((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))])
+    ref = torch.stack([pre(img) for img in u8])                      # host, as the reference does per frame
+    Hp, Wp = (H + 6) // 2, (W + 6) // 2
+    a = torch.empty((N, Hp, Wp, 16), device="cuda", dtype=torch.bfloat16)
+    b = torch.empty_like(a)
+    ops.stem_pack_u8(u8.cuda(), a, N, H, W)
+    ops.stem_pack(ref.cuda(), b, N, H, W)
+    assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+    assert torch.equal(normalize_u8(u8.cuda()).cpu(), ref)            # generic (non-fused) device path: same fp32 values
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_model_accepts_raw_uint8_frames(precision):
+    """End2EndDiffusionTransformer.forward with uint8 image_data == the same call with host-preprocessed float frames."""
+    from torchvision.transforms import v2
+
+    import soccerdiffusion_b200 as sd
+    from soccerdiffusion_b200 import config, runtime
+
+    hp = dict(config.DEFAULT)
+    hp.update(image_context_length=2, image_resolution=64, image_use_final_avgpool=False, action_context_length=10,
+              imu_context_length=10, joint_state_context_length=10)
+    prev = sd.precision_name()
+    sd.set_precision(precision)
+    try:
+        torch.manual_seed(0)
+        model = config.build_model(hp).cuda().eval()
+        batch = config.synthetic_batch(hp, 3, "cuda", seed=1, uint8_images=True)
+        u8 = batch["image_data"]
+        pre = v2.Compose([v2.ToDtype(torch.float32, scale=True), v2.Normalize((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))])
+        flt = torch.stack([pre(img) for img in u8.cpu().flatten(0, 1)]).view(*u8.shape).cuda()
+        x = torch.randn(3, hp["trajectory_prediction_length"], hp["num_joints"], device="cuda")
+        t = torch.tensor([5, 500, 900], device="cuda")
+        with torch.no_grad():
+            a = model(batch, x, t)
+            b = model({**batch, "image_data": flt}, x, t)
+        assert torch.equal(a, b)
+        # training mode (train-mode BatchNorm, fused stem with the uint8 packing): gradients identical too
+        model.train()
+        runtime.set_dropout(0.0)
+        grads = []
+        for imgs in (u8, flt):
+            model.zero_grad()
+            model({**batch, "image_data": imgs}, x, t).square().mean().backward()
+            grads.append(model.image_sequence_encoder.image_encoder.encoder.conv1.weight.grad.clone())
+        assert rel(grads[0], grads[1]) < 1e-5   # split-K atomics: summation order differs run to run
+    finally:
+        runtime.set_dropout(0.1)
+        sd.set_precision(prev)

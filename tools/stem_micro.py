@@ -46,3 +46,17 @@ t = timed(lambda: ops.stem_fwd(x, mean, invstd, gamma, beta, y, idx, N, H, W, C)
 print(f"stem_fwd       {t:7.3f} ms  {(2 * elems + 3 * pooled) / t / 1e6:7.0f} GB/s")
 t = timed(lambda: ops.stem_bwd(dp, idx, x, mean, invstd, gamma, beta, sums, dx, dg, db, N, H, W, C))
 print(f"stem_bwd (2p)  {t:7.3f} ms  {(6 * elems + 6 * pooled) / t / 1e6:7.0f} GB/s")
+
+# conv1 itself (space-to-depth packed image): pack, tcgen05 forward, tcgen05 weight gradient
+img = torch.randn(N, 3, 224, 224, device=dev)
+xp = torch.empty(N, 115, 115, 16, device=dev, dtype=torch.bfloat16)
+w2 = torch.randn(64, 256, device=dev).to(torch.bfloat16)
+yc = torch.empty(N, 112, 112, 64, device=dev, dtype=torch.bfloat16)
+dws = torch.empty(256, 64, device=dev, dtype=torch.float32)
+P = N * 112 * 112
+t = timed(lambda: ops.stem_pack(img, xp, N, 224, 224))
+print(f"stem_pack      {t:7.3f} ms  {(12.0 * N * 224 * 224 + 32.0 * N * 115 * 115) / t / 1e6:7.0f} GB/s")
+t = timed(lambda: ops.stem_fprop(xp, w2, yc, N, 224, 224))
+print(f"stem_fprop     {t:7.3f} ms  {2.0 * 256 * 64 * P / t / 1e9:7.0f} TF/s  {(32.0 * N * 115 * 115 + 128.0 * P) / t / 1e6:7.0f} GB/s")
+t = timed(lambda: ops.stem_wgrad(xp, dx.view(N, 112, 112, 64), dws, N, 224, 224))
+print(f"stem_wgrad     {t:7.3f} ms  {2.0 * 256 * 64 * P / t / 1e9:7.0f} TF/s")
