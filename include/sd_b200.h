@@ -188,6 +188,13 @@ int sd_stem_wgrad_s2d_bf16(const void* xs2d, const void* dy, float* dw_s2d, int 
  * TMEM accumulators.  Returns SD_E_UNSUPPORTED when W/2 is not a multiple of 8 in [8,128] or the driver has no tensor-map
  * encoder (callers then use the library convolution). */
 int sd_stem_fprop_s2d_bf16(const void* xs2d, const void* w_s2d, void* y, int N, int H, int W, void* stream);
+/* Same, plus the per-channel sums of y and y*y over all pixels (fp32 accumulator values) into sums[2][64] (zeroed by the
+ * call): bn1's batch statistics come out of the convolution's epilogue instead of another pass over the 112x112 map;
+ * sd_bn_finalize turns them into mean / invstd / running statistics (nn.BatchNorm2d training semantics). */
+int sd_stem_fprop_s2d_bf16_stats(const void* xs2d, const void* w_s2d, void* y, double* sums, int N, int H, int W,
+                                 void* stream);
+int sd_bn_finalize(const double* sums, long long R, int C, float eps, float momentum, float* mean, float* invstd,
+                   float* running_mean, float* running_var, void* stream);
 /* Fused stem: maxpool3x3s2(relu(bn(x))) without materialising the activated 112x112 map; backward recomputes the
  * ReLU mask from x (torchvision ResNet stem bn1 -> relu -> maxpool). mean/invstd from sd_bn_stats_nhwc_bf16.
  * With C = 64 and W <= 112 (sd_stem_band_supported) both directions run as row-band kernels: the forward stages its

@@ -95,6 +95,8 @@ SIGNATURES = {
     "sd_stem_pack_s2d_bf16": [c_f, c_f, c_i, c_i, c_i, c_f],
     "sd_stem_pack_s2d_u8": [c_f, c_f, c_i, c_i, c_i, c_fl, c_fl, c_fl, c_fl, c_fl, c_fl, c_f],
     "sd_stem_fprop_s2d_bf16": [c_f, c_f, c_f, c_i, c_i, c_i, c_f],
+    "sd_stem_fprop_s2d_bf16_stats": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_f],
+    "sd_bn_finalize": [c_f, c_ll, c_i, c_fl, c_fl, c_f, c_f, c_f, c_f, c_f],
     "sd_stem_wgrad_s2d_bf16": [c_f, c_f, c_f, c_i, c_i, c_i, c_f],
     "sd_stem_band_supported": [c_i, c_i, c_i],
     "sd_stem_bn_relu_pool_nhwc_bf16_fwd": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f],

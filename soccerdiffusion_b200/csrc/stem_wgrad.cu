@@ -260,24 +260,30 @@ __global__ void __launch_bounds__(NT, 1) stem_wgrad_tma_kernel(const __grid_cons
 // [64][256] stay resident in shared memory.  Warp 0: TMA producer, warp 1: MMA issuer, warps 4-7: epilogue
 // (TMEM -> bf16 -> one 128-byte NHWC row per thread) with two TMEM accumulators so that the epilogue of tile i overlaps
 // the loads and MMAs of tile i+1.
+constexpr int RING = 8;   // input-row tiles resident in shared memory (4 live + up to 4 in flight)
+
+// Input-row ring: the patch tile of packed-image row (n, ho + kh) is the SAME for every (ho, kh) with equal ho + kh, so
+// consecutive output rows share three of their four operand tiles.  Tiles are loaded once into a ring of RING slots
+// (tile sequence number x -> slot x % RING) and each output row's MMAs read the four newest tiles; a tile is released
+// (tcgen05.commit -> its empty barrier) after the last output row that uses it.  L2 -> shared-memory traffic drops
+// from four tiles per output row to one (17 GB -> 4.3 GB at bs=256: the first version was L2-bound at 72 % LTS).
 __global__ void __launch_bounds__(NT, 1) stem_fprop_tma_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const uint4* __restrict__ w_s2d, uint4* __restrict__ y,
-                                                               int HO, int WO, int Hp, int Wp, long long rows_total,
-                                                               int rows_per_cta) {
+                                                               double* __restrict__ sums, int HO, int WO, int Hp, int Wp,
+                                                               long long rows_total, int rows_per_cta) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full[TMA_STAGES];
-    __shared__ __align__(8) uint64_t bar_empty[TMA_STAGES];
+    __shared__ __align__(8) uint64_t bar_full[RING];
+    __shared__ __align__(8) uint64_t bar_empty[RING];
     __shared__ __align__(8) uint64_t acc_full[2];
     __shared__ __align__(8) uint64_t acc_empty[2];
     __shared__ uint32_t tmem_slot;
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int blk = WO * 128;                 // one filter row of WO patches
-    const int stage_bytes = 4 * blk;
-    uint8_t* Ws = smem + TMA_STAGES * stage_bytes;   // 4 tiles [64 channels][64 k] K-major, 8 KB each (+ slack for M=128 reads)
+    const int blk = WO * 128;                 // one tile: WO patches x 64 elements (one filter row)
+    uint8_t* Ws = smem + RING * blk;          // 4 tiles [64 channels][64 k] K-major, 8 KB each (+ slack for M=128 reads)
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < TMA_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+        for (int s = 0; s < RING; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
 #pragma unroll
         for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 1); }
         mbar_fence_init();
@@ -297,41 +303,57 @@ __global__ void __launch_bounds__(NT, 1) stem_fprop_tma_kernel(const __grid_cons
     const long long r_begin = (long long)blockIdx.x * rows_per_cta;
     const long long r_end = min(rows_total, r_begin + rows_per_cta);
     const int nrows = (int)max(0LL, r_end - r_begin);
+    const int ho_begin = (int)(r_begin % HO);   // output row i of this CTA is image row (ho_begin + i) % HO
+    // a "fresh" output row starts a new tile window (first row of the CTA or of an image): 4 new tiles, otherwise 1
 
     if (warp == 0 && lane == 0) {
-        for (int ci = 0; ci < nrows; ++ci) {
-            const int s = ci % TMA_STAGES;
-            mbar_wait(&bar_empty[s], (uint32_t)(((ci / TMA_STAGES) & 1) ^ 1));
-            const long long r = r_begin + ci;
+        int x = 0;   // tile sequence number
+        for (int i = 0; i < nrows; ++i) {
+            const long long r = r_begin + i;
             const int n = (int)(r / HO), ho = (int)(r - (long long)n * HO);
-            const uint32_t base = smem_u32(smem + s * stage_bytes);
-            mbar_arrive_expect_tx(&bar_full[s], (uint32_t)stage_bytes);
-#pragma unroll
-            for (int kh = 0; kh < 4; ++kh)
-                tma_load_2d(base + kh * blk, &tmA, 0, (n * Hp + ho + kh) * Wp, &bar_full[s]);
+            const bool fresh = i == 0 || ho == 0;
+            for (int kh = fresh ? 0 : 3; kh < 4; ++kh, ++x) {
+                const int s = x % RING;
+                mbar_wait(&bar_empty[s], (uint32_t)(((x / RING) & 1) ^ 1));
+                mbar_arrive_expect_tx(&bar_full[s], (uint32_t)blk);
+                tma_load_2d(smem_u32(smem + s * blk), &tmA, 0, (n * Hp + ho + kh) * Wp, &bar_full[s]);
+            }
         }
     } else if (warp == 1 && lane == 0) {
         const uint32_t idesc = instr_desc_bf16(128, 64, 0, 0);
-        for (int ci = 0; ci < nrows; ++ci) {
-            const int s = ci % TMA_STAGES, a = ci & 1;
-            mbar_wait(&acc_empty[a], (uint32_t)(((ci >> 1) & 1) ^ 1));   // epilogue drained this accumulator
-            mbar_wait(&bar_full[s], (uint32_t)((ci / TMA_STAGES) & 1));
-            tc_fence_after_sync();
-            const uint32_t base = smem_u32(smem + s * stage_bytes);
+        int L = 0;   // tiles loaded up to and including this output row's
+        for (int i = 0; i < nrows; ++i) {
+            const int ho = (ho_begin + i) % HO;
+            const bool fresh = i == 0 || ho == 0;
+            L += fresh ? 4 : 1;
+            const int a = i & 1;
+            mbar_wait(&acc_empty[a], (uint32_t)(((i >> 1) & 1) ^ 1));   // epilogue drained this accumulator
 #pragma unroll
             for (int kh = 0; kh < 4; ++kh) {
-                const uint64_t da = smem_desc_k_sw128(base + kh * blk);
+                const int x = L - 4 + kh, s = x % RING;
+                mbar_wait(&bar_full[s], (uint32_t)((x / RING) & 1));
+                tc_fence_after_sync();
+                const uint64_t da = smem_desc_k_sw128(smem_u32(smem + s * blk));
                 const uint64_t db = smem_desc_k_sw128(smem_u32(Ws) + kh * 8192);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
                     mma_bf16_ss(tmem + a * 64, da + 2 * ks, db + 2 * ks, idesc, (kh | ks) ? 1u : 0u);
             }
-            mma_commit(&bar_empty[s]);
+            // release the tiles no later output row reads: the oldest one, or all four at the end of the window
+            const bool next_fresh = i + 1 >= nrows || (ho_begin + i + 1) % HO == 0;
+            for (int x = L - 4; x < (next_fresh ? L : L - 3); ++x) mma_commit(&bar_empty[x % RING]);
             mma_commit(&acc_full[a]);
         }
     } else if (warp >= 4) {
         const int q = warp & 3;
         const int row = q * 32 + lane;        // pixel within the image row
+        // per-warp staging block [32 pixels][128 B], 16-byte chunks XOR-swizzled by the pixel index: conflict-free both
+        // for the row-per-thread writes and for the read-back in global-memory order (the warp's 32 pixels are 4 KB of
+        // contiguous NHWC output, stored with fully coalesced 512-byte requests)
+        uint8_t* stg = Ws + 4 * 8192 + 4096 + q * 4096;
+        float s1[64], s2[64];                  // BatchNorm statistics of this thread's pixel column over all its rows
+#pragma unroll
+        for (int c = 0; c < 64; ++c) s1[c] = s2[c] = 0.f;
         for (int ci = 0; ci < nrows; ++ci) {
             const int a = ci & 1;
             mbar_wait(&acc_full[a], (uint32_t)((ci >> 1) & 1));
@@ -343,13 +365,42 @@ __global__ void __launch_bounds__(NT, 1) stem_fprop_tma_kernel(const __grid_cons
             // all four epilogue warps have read the accumulator -> hand it back to the MMA warp
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (tid == 128) mbar_arrive(&acc_empty[a]);
-            if (row < WO) {
-                uint4* dst = y + ((r_begin + ci) * WO + row) * 8;
+            if (sums != nullptr && row < WO) {
 #pragma unroll
-                for (int c8 = 0; c8 < 4; ++c8) dst[c8] = pack8_bf16(v0 + 8 * c8);
-#pragma unroll
-                for (int c8 = 0; c8 < 4; ++c8) dst[4 + c8] = pack8_bf16(v1 + 8 * c8);
+                for (int c = 0; c < 32; ++c) {
+                    s1[c] += v0[c]; s2[c] = fmaf(v0[c], v0[c], s2[c]);
+                    s1[32 + c] += v1[c]; s2[32 + c] = fmaf(v1[c], v1[c], s2[32 + c]);
+                }
             }
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+                *reinterpret_cast<uint4*>(stg + lane * 128 + ((c8 ^ (lane & 7)) << 4)) = pack8_bf16(v0 + 8 * c8);
+                *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 + c8) ^ (lane & 7)) << 4)) = pack8_bf16(v1 + 8 * c8);
+            }
+            __syncwarp();
+            uint4* dst = y + ((r_begin + ci) * WO + q * 32) * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int g = j * 32 + lane, pr = g >> 3, c = g & 7;   // chunk g of the warp's block: pixel pr, chunk c
+                if (q * 32 + pr < WO) dst[g] = *reinterpret_cast<const uint4*>(stg + pr * 128 + ((c ^ (pr & 7)) << 4));
+            }
+            __syncwarp();
+        }
+        if (sums != nullptr) {
+            // cross-pixel reduction of the 128 epilogue threads through the (now idle) tile ring, one double atomic per
+            // (statistic, channel) and CTA
+            asm volatile("bar.sync 1, 128;" ::: "memory");   // every MMA of this CTA has completed (all acc_full consumed)
+            float* red = reinterpret_cast<float*>(smem);      // [128 values][129]
+            const int t = tid - 128;
+#pragma unroll
+            for (int c = 0; c < 64; ++c) {
+                red[c * 129 + t] = s1[c];
+                red[(64 + c) * 129 + t] = s2[c];
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            float tot = 0.f;
+            for (int i = 0; i < 128; ++i) tot += red[t * 129 + i];
+            atomicAdd(&sums[t], (double)tot);                 // t < 64: sum x of channel t ; t >= 64: sum x^2 of channel t - 64
         }
     }
     tc_fence_before_sync();
@@ -498,12 +549,21 @@ extern "C" int sd_stem_wgrad_s2d_bf16(const void* xs2d, const void* dy, float* d
 // y (N, H/2, W/2, 64) bf16 NHWC = conv1 of the packed image with w_s2d[64][256] bf16 (row = output channel,
 // column = kh*64 + kw*16 + ci).  Returns SD_E_UNSUPPORTED when the shape / driver cannot use the TMA kernel (the
 // caller then runs cuDNN).
+extern "C" int sd_stem_fprop_s2d_bf16_stats(const void* xs2d, const void* w_s2d, void* y, double* sums, int N, int H, int W,
+                                            void* stream);
 extern "C" int sd_stem_fprop_s2d_bf16(const void* xs2d, const void* w_s2d, void* y, int N, int H, int W, void* stream) {
+    return sd_stem_fprop_s2d_bf16_stats(xs2d, w_s2d, y, nullptr, N, H, W, stream);
+}
+
+// Same, and the epilogue also accumulates the per-channel sums of y and y^2 (fp32 accumulator values, before the bf16
+// rounding) into sums[2][64] (zeroed here): the BatchNorm statistics of bn1 without another pass over the 112x112 map.
+extern "C" int sd_stem_fprop_s2d_bf16_stats(const void* xs2d, const void* w_s2d, void* y, double* sums, int N, int H, int W,
+                                            void* stream) {
     if (N <= 0) return SD_OK;
     if (!xs2d || !w_s2d || !y || (H & 1) || (W & 1)) return SD_ERR_BAD_ARG;
     const int Hp = (H + 6) / 2, Wp = (W + 6) / 2, HO = H / 2, WO = W / 2;
     if (!use_tma() || WO % 8 != 0 || WO > 128 || WO < 8) return SD_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)TMA_STAGES * 4 * WO * 128 + 4 * 8192 + 4096 + 1024;   // stages + weights + M=128 over-read slack
+    const size_t smem = (size_t)RING * WO * 128 + 4 * 8192 + 4096 + 4 * 4096 + 1024;   // tile ring + weights + M=128 over-read slack + store staging
     if (smem > 227 * 1024 - 256) return SD_ERR_UNSUPPORTED;
     CUtensorMap tmA;
     if (!encode_patch_map(&tmA, xs2d, N, Hp, Wp, WO)) return SD_ERR_UNSUPPORTED;
@@ -518,7 +578,8 @@ extern "C" int sd_stem_fprop_s2d_bf16(const void* xs2d, const void* w_s2d, void*
     const long long rows = (long long)N * HO;
     const int grid = (int)min((long long)148, rows);
     const int per = (int)((rows + grid - 1) / grid);
-    stem_fprop_tma_kernel<<<grid, NT, smem, (cudaStream_t)stream>>>(tmA, (const uint4*)w_s2d, (uint4*)y, HO, WO, Hp, Wp, rows, per);
+    if (sums) SD_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 128, (cudaStream_t)stream));
+    stem_fprop_tma_kernel<<<grid, NT, smem, (cudaStream_t)stream>>>(tmA, (const uint4*)w_s2d, (uint4*)y, sums, HO, WO, Hp, Wp, rows, per);
     SD_LAUNCH_CHECK();
     return SD_OK;
 }

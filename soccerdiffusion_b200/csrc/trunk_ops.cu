@@ -581,6 +581,17 @@ extern "C" int sd_bn_stats_nhwc_bf16(const void* x, long long R, int C, double* 
     return SD_OK;
 }
 
+// mean / invstd / running statistics from per-channel sums produced elsewhere (the stem convolution's epilogue)
+extern "C" int sd_bn_finalize(const double* sums, long long R, int C, float eps, float momentum, float* mean, float* invstd,
+                              float* running_mean, float* running_var, void* stream) {
+    if (R <= 0) return SD_OK;
+    if (!sums || !mean || !invstd || C <= 0) return SD_ERR_BAD_ARG;
+    bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, R, C, eps, momentum, mean, invstd, running_mean,
+                                                                          running_var);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+}
+
 extern "C" int sd_bn_apply_nhwc_bf16(const void* x, const void* residual, const float* mean, const float* invstd,
                                      const float* gamma, const float* beta, int relu, void* y, void* relu_mask,
                                      long long R, int C, void* stream) {

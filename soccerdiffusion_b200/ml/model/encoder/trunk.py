@@ -94,14 +94,19 @@ class StemBNReLUPool(torch.autograd.Function):
     """maxpool3x3s2(relu(BN(x))) in one pass (torchvision ResNet stem after conv1)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, training: bool, momentum: float, eps: float):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, training: bool, momentum: float, eps: float,
+                presums=None):
+        """``presums``: per-channel (sum x, sum x^2) already accumulated by the producer of x (the stem convolution's
+        epilogue) — the statistics pass over x is skipped."""
         x = _cl(x)
         N, C, H, W = x.shape
         dev = x.device
         mean = torch.empty(C, device=dev, dtype=torch.float32)
         invstd = torch.empty(C, device=dev, dtype=torch.float32)
         sums = torch.empty(2 * C, device=dev, dtype=torch.float64)
-        if training:
+        if training and presums is not None and presums.numel() == 2 * C:
+            ops.bn_finalize(presums, N * H * W, C, eps, momentum, mean, invstd, running_mean, running_var)
+        elif training:
             ops.bn_stats(x, N * H * W, C, sums, eps, momentum, mean, invstd, running_mean, running_var)
         else:
             mean.copy_(running_mean)
@@ -134,7 +139,7 @@ class StemBNReLUPool(torch.autograd.Function):
             dact = torch.empty_like(x)
             ops.maxpool_bwd(dy, idx, dact, N, H, W, C)
             ops.bn_bwd(dact, None, x, mean, invstd, gamma, ctx.sums, dx, None, dgamma, dbeta, N * H * W, C, beta_recompute=beta)
-        return dx, dgamma, dbeta, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, None, None
 
 
 def _bn(bn, x, residual=None, relu=True):
@@ -178,14 +183,20 @@ class StemConvS2D(torch.autograd.Function):
     for the backward pass (1.1 GB at bs=256) instead of being re-packed."""
 
     @staticmethod
-    def forward(ctx, images, weight):
+    def forward(ctx, images, weight, want_stats: bool = False):
+        """Returns (y, sums): ``sums`` (float64[2*Cout], sum y / sum y^2 per channel from the convolution's epilogue) when
+        ``want_stats`` and the tcgen05 kernel ran, else an empty tensor."""
         with torch.no_grad():
-            y, xp = _stem_conv_s2d_raw(images, weight, return_packed=True)
+            sums = torch.empty(2 * weight.shape[0], device=images.device, dtype=torch.float64) if want_stats else None
+            y, xp, have = _stem_conv_s2d_raw(images, weight, return_packed=True, sums=sums)
+            if not have:
+                sums = torch.empty(0, device=images.device, dtype=torch.float64)
         ctx.save_for_backward(images, weight, xp)
-        return y
+        ctx.mark_non_differentiable(sums)
+        return y, sums
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dsums=None):
         images, weight, xp = ctx.saved_tensors
         N, Cin, H, W = images.shape
         Cout = weight.shape[0]
@@ -195,11 +206,11 @@ class StemConvS2D(torch.autograd.Function):
             g = dws.view(4, 4, 16, Cout)[:, :, : Cin * 4]                  # (kh, kw, ci=(c,dy,dx), cout)
             g = g.reshape(4, 4, Cin, 2, 2, Cout).permute(5, 2, 0, 3, 1, 4)  # (cout, c, kh, dy, kw, dx)
             gw = g.reshape(Cout, Cin, 8, 8)[:, :, :7, :7]
-            return None, gw.to(weight.dtype).contiguous()
+            return None, gw.to(weight.dtype).contiguous(), None
         x = normalize_u8(images).to(dtype=torch.bfloat16, memory_format=torch.channels_last)
         gw = torch.ops.aten.convolution_backward(_cl(dy), x, weight.to(torch.bfloat16), None, (2, 2), (3, 3), (1, 1), False,
                                                  (0, 0), 1, (False, True, False))[1]
-        return None, gw.to(weight.dtype)
+        return None, gw.to(weight.dtype), None
 
 
 def normalize_u8(images: torch.Tensor) -> torch.Tensor:
@@ -212,7 +223,8 @@ def normalize_u8(images: torch.Tensor) -> torch.Tensor:
     return images.to(torch.float32).mul_(1.0 / 255).sub_(mean).div_(std)
 
 
-def _stem_conv_s2d_raw(images, weight, return_packed: bool = False):
+def _stem_conv_s2d_raw(images, weight, return_packed: bool = False, sums=None):
+    """conv1 on the packed image.  With ``return_packed``: (y, packed image, whether ``sums`` was filled)."""
     N, Cin, H, W = images.shape
     Cout = weight.shape[0]
     Hp, Wp = (H + 6) // 2, (W + 6) // 2
@@ -228,10 +240,10 @@ def _stem_conv_s2d_raw(images, weight, return_packed: bool = False):
         # TMA + tcgen05 kernel: weights as [cout][kh][kw][ci] = [64][256]
         w2 = w.permute(0, 2, 3, 1).reshape(Cout, 256).contiguous()
         y = torch.empty((N, Cout, H // 2, W // 2), device=images.device, dtype=torch.bfloat16, memory_format=torch.channels_last)
-        if ops.stem_fprop(xp, w2, y, N, H, W):
-            return (y, xp) if return_packed else y
+        if ops.stem_fprop(xp, w2, y, N, H, W, sums=sums):
+            return (y, xp, sums is not None) if return_packed else y
     y = F.conv2d(xp.permute(0, 3, 1, 2), w.contiguous(memory_format=torch.channels_last), None, 1, 0)
-    return (y, xp) if return_packed else y
+    return (y, xp, False) if return_packed else y
 
 
 def _stem_is_s2d_compatible(conv, images) -> bool:
@@ -254,18 +266,19 @@ def resnet_trunk_bf16(encoder, images: torch.Tensor) -> torch.Tensor:
 
     # cuDNN autotuning for the (fixed) convolution shapes of the trunk; restored on exit
     with torch.backends.cudnn.flags(enabled=True, benchmark=True), torch.autocast("cuda", dtype=torch.bfloat16):
+        bn1 = encoder.bn1
+        presums = None
         if _stem_is_s2d_compatible(encoder.conv1, images):
             if images.dtype in (torch.float32, torch.uint8) and not images.requires_grad and encoder.conv1.bias is None:
-                x = StemConvS2D.apply(images, encoder.conv1.weight)
+                x, presums = StemConvS2D.apply(images, encoder.conv1.weight, bool(bn1.training))
             else:
                 x = _stem_conv_s2d(encoder.conv1, normalize_u8(images))
         else:
             x = _conv(encoder.conv1, normalize_u8(images).to(dtype=torch.bfloat16, memory_format=torch.channels_last))
-        bn1 = encoder.bn1
         if bn1.training and bn1.track_running_stats and bn1.num_batches_tracked is not None:
             bn1.num_batches_tracked.add_(1)
         x = StemBNReLUPool.apply(x, bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var, bn1.training,
-                                 float(0.1 if bn1.momentum is None else bn1.momentum), float(bn1.eps))
+                                 float(0.1 if bn1.momentum is None else bn1.momentum), float(bn1.eps), presums)
         for layer in (encoder.layer1, encoder.layer2, encoder.layer3, encoder.layer4):
             for blk in layer:
                 identity = x

@@ -376,13 +376,23 @@ def stem_wgrad(xs2d, dy, dw, N, H, W):
     _count(2)
 
 
-def stem_fprop(xs2d, w_s2d, y, N, H, W) -> bool:
-    """conv1 forward on the packed image; False when the TMA/tcgen05 kernel does not support this shape."""
+def stem_fprop(xs2d, w_s2d, y, N, H, W, sums=None) -> bool:
+    """conv1 forward on the packed image; False when the TMA/tcgen05 kernel does not support this shape.  ``sums``
+    (float64[128]): the epilogue also accumulates bn1's batch statistics (sum y, sum y^2 per channel)."""
     P = N * (H // 2) * (W // 2)
     with _Timed("stem_fprop_s2d", 2.0 * 256 * 64 * P, 32.0 * N * ((H + 6) // 2) * ((W + 6) // 2) + 128.0 * P, f"[N{N} H{H}]"):
-        rc = _lib.lib().sd_stem_fprop_s2d_bf16(xs2d.data_ptr(), w_s2d.data_ptr(), y.data_ptr(), N, H, W, stream_ptr())
+        rc = _lib.lib().sd_stem_fprop_s2d_bf16_stats(xs2d.data_ptr(), w_s2d.data_ptr(), y.data_ptr(),
+                                                     sums.data_ptr() if sums is not None else None, N, H, W, stream_ptr())
     if rc == -2:
         return False
-    check(rc, "sd_stem_fprop_s2d_bf16")
+    check(rc, "sd_stem_fprop_s2d_bf16_stats")
     _count()
     return True
+
+
+def bn_finalize(sums, R, C, eps, momentum, mean, invstd, running_mean, running_var):
+    check(_lib.lib().sd_bn_finalize(sums.data_ptr(), R, C, eps, momentum, mean.data_ptr(), invstd.data_ptr(),
+                                    running_mean.data_ptr() if running_mean is not None else None,
+                                    running_var.data_ptr() if running_var is not None else None, stream_ptr()),
+          "sd_bn_finalize")
+    _count()

@@ -163,7 +163,7 @@ def test_stem_wgrad_tcgen05_matches_cudnn(N, H, W):
         T._USE_TC_STEM_WGRAD = mode
         try:
             wg = w.clone().requires_grad_(True)
-            y = T.StemConvS2D.apply(img, wg)
+            y, _ = T.StemConvS2D.apply(img, wg)
             y.backward(dy)
             got[mode] = wg.grad.clone()
         finally:
@@ -294,3 +294,24 @@ def test_model_accepts_raw_uint8_frames(precision):
     finally:
         runtime.set_dropout(0.1)
         sd.set_precision(prev)
+
+
+@pytest.mark.parametrize("N,H,W", [(3, 224, 224), (2, 64, 96)])
+def test_stem_fprop_epilogue_statistics(N, H, W):
+    """sd_stem_fprop_s2d_bf16_stats: the per-channel sums accumulated in the convolution's epilogue give the same
+    BatchNorm batch statistics as a pass over the stored bf16 map (they are taken before the bf16 rounding)."""
+    from soccerdiffusion_b200.ml.model.encoder import trunk as T
+
+    torch.manual_seed(11)
+    img = torch.randn(N, 3, H, W, device="cuda")
+    w = torch.randn(64, 3, 7, 7, device="cuda") * 0.05
+    sums = torch.full((128,), 7.0, device="cuda", dtype=torch.float64)      # the call zeroes it
+    y, _, have = T._stem_conv_s2d_raw(img, w, return_packed=True, sums=sums)
+    assert have
+    yf = y.float()
+    n = yf.numel() // 64
+    mean_ref, var_ref = yf.mean((0, 2, 3)).double(), yf.var((0, 2, 3), unbiased=False).double()
+    mean = sums[:64] / n
+    var = sums[64:] / n - mean * mean
+    assert ((mean - mean_ref).abs() < 1e-3 * var_ref.sqrt()).all()
+    assert ((var / var_ref - 1).abs() < 2e-3).all()
