@@ -261,6 +261,7 @@ __global__ void __launch_bounds__(NT, 1) stem_wgrad_tma_kernel(const __grid_cons
 // (TMEM -> bf16 -> one 128-byte NHWC row per thread) with two TMEM accumulators so that the epilogue of tile i overlaps
 // the loads and MMAs of tile i+1.
 constexpr int RING = 8;   // input-row tiles resident in shared memory (4 live + up to 4 in flight)
+constexpr int NACC = 4;   // TMEM accumulators (64 columns each): the MMA warp runs up to NACC - 1 rows ahead of the epilogue
 
 // Input-row ring: the patch tile of packed-image row (n, ho + kh) is the SAME for every (ho, kh) with equal ho + kh, so
 // consecutive output rows share three of their four operand tiles.  Tiles are loaded once into a ring of RING slots
@@ -274,8 +275,8 @@ __global__ void __launch_bounds__(NT, 1) stem_fprop_tma_kernel(const __grid_cons
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[RING];
     __shared__ __align__(8) uint64_t bar_empty[RING];
-    __shared__ __align__(8) uint64_t acc_full[2];
-    __shared__ __align__(8) uint64_t acc_empty[2];
+    __shared__ __align__(8) uint64_t acc_full[NACC];
+    __shared__ __align__(8) uint64_t acc_empty[NACC];
     __shared__ uint32_t tmem_slot;
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -285,10 +286,10 @@ __global__ void __launch_bounds__(NT, 1) stem_fprop_tma_kernel(const __grid_cons
 #pragma unroll
         for (int s = 0; s < RING; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
 #pragma unroll
-        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 1); }
+        for (int a = 0; a < NACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 1); }
         mbar_fence_init();
     }
-    if (warp == 0) tmem_alloc(&tmem_slot, 128);
+    if (warp == 0) tmem_alloc(&tmem_slot, NACC * 64);
     // weights: w_s2d[c][j] bf16 (j = kh*64 + kw*16 + ci) -> tile kh, row c, 16-byte chunk (j % 64) / 8
     for (int i = tid; i < 64 * 32; i += NT) {
         const int c = i >> 5, ch = i & 31;    // 32 chunks of 8 bf16 per output channel
@@ -326,8 +327,8 @@ __global__ void __launch_bounds__(NT, 1) stem_fprop_tma_kernel(const __grid_cons
             const int ho = (ho_begin + i) % HO;
             const bool fresh = i == 0 || ho == 0;
             L += fresh ? 4 : 1;
-            const int a = i & 1;
-            mbar_wait(&acc_empty[a], (uint32_t)(((i >> 1) & 1) ^ 1));   // epilogue drained this accumulator
+            const int a = i % NACC;
+            mbar_wait(&acc_empty[a], (uint32_t)(((i / NACC) & 1) ^ 1));   // epilogue drained this accumulator
 #pragma unroll
             for (int kh = 0; kh < 4; ++kh) {
                 const int x = L - 4 + kh, s = x % RING;
@@ -355,8 +356,8 @@ __global__ void __launch_bounds__(NT, 1) stem_fprop_tma_kernel(const __grid_cons
 #pragma unroll
         for (int c = 0; c < 64; ++c) s1[c] = s2[c] = 0.f;
         for (int ci = 0; ci < nrows; ++ci) {
-            const int a = ci & 1;
-            mbar_wait(&acc_full[a], (uint32_t)((ci >> 1) & 1));
+            const int a = ci % NACC;
+            mbar_wait(&acc_full[a], (uint32_t)((ci / NACC) & 1));
             tc_fence_after_sync();
             float v0[32], v1[32];
             tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 64), v0);
@@ -405,7 +406,7 @@ __global__ void __launch_bounds__(NT, 1) stem_fprop_tma_kernel(const __grid_cons
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 128);
+    if (warp == 0) tmem_dealloc(tmem, NACC * 64);
 }
 
 bool use_tma() {   // SD_B200_STEM_WGRAD_TMA=0 selects the cp.async-fed kernel
