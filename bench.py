@@ -511,13 +511,26 @@ def ddim_latency(model, hp, dev, precision, reps=200):
     out = {}
     from soccerdiffusion_b200.ml.inference import TrajectorySampler
 
+    from soccerdiffusion_b200.ml.inference import FrameEmbeddingCache
+
     graphed = TrajectorySampler(model, sch, 30, use_cuda_graph=True)
+    # (f)-2: one NEW camera frame per tick is embedded and cached; the tick itself runs on the cached frame tokens
+    cache = FrameEmbeddingCache(model)
+    cache.push(batch["image_data"][0])
+    cached_batch = {k: v for k, v in batch.items() if k != "image_data"}
+    new_frame = batch["image_data"][0, -1]
+
+    def tick_cached():
+        cache.push(new_frame)
+        return graphed({**cached_batch, "image_tokens": cache.tokens()}, x_T)
+
     with torch.no_grad():
         ctx = model.encode_input_data(batch)
         for name, fn in (("sampler", lambda: model.sample(ctx, x_T, sch, denormalize=True)),
                          ("sampler_cta", lambda: model.sample(ctx, x_T, sch, denormalize=True, sampler="cta")),
                          ("tick", lambda: model.sample(model.encode_input_data(batch), x_T, sch, denormalize=True)),
-                         ("tick_graph", lambda: graphed(batch, x_T))):
+                         ("tick_graph", lambda: graphed(batch, x_T)),
+                         ("tick_cached_frames", tick_cached)):
             for _ in range(5):
                 fn()
             torch.cuda.synchronize()
@@ -556,7 +569,8 @@ def ddim_latency(model, hp, dev, precision, reps=200):
     out["sampler_kernel"] = getattr(model, "last_sampler", "?")
     out["note"] = ("sampler = x_T -> x_0 with the context given (one persistent-kernel launch; 16-CTA cluster kernel, "
                    "sampler_cta = single-CTA kernel); tick = encode_input_data (10x224^2 frames) + sampler, launched "
-                   "kernel by kernel; tick_graph = the same tick replayed from one captured CUDA graph")
+                   "kernel by kernel; tick_graph = the same tick replayed from one captured CUDA graph; tick_cached_frames = embed "
+                   "ONE new frame (trunk on 1 frame, eager launches) + graph-replayed tick on the cached frame tokens")
     out["encoder_precision_mode"] = precision
     model.train()
     return out

@@ -1,1 +1,1 @@
-from soccerdiffusion_b200.ml.inference.sampler import TrajectorySampler, sample_loop  # noqa: F401
+from soccerdiffusion_b200.ml.inference.sampler import FrameEmbeddingCache, TrajectorySampler, sample_loop  # noqa: F401

@@ -2,6 +2,7 @@
 
     sample_loop         the reference's step-at-a-time loop (ros.py:301-310), kept working unchanged
     TrajectorySampler   encode once -> ONE persistent-kernel launch for all DDIM steps -> denormalise
+    FrameEmbeddingCache per-frame image embeddings computed once per camera frame (the TODO at ros.py:180-183)
 """
 from __future__ import annotations
 
@@ -18,6 +19,41 @@ def sample_loop(model, scheduler, context, x_T, num_steps: int):
         noise_pred = model.forward_with_context(context, trajectory, torch.full((B,), int(t), device=x_T.device))
         trajectory = scheduler.step(noise_pred, t, trajectory).prev_sample
     return trajectory
+
+
+class FrameEmbeddingCache:
+    """Per-frame image embeddings across control ticks (the TODO at ml/inference/ros.py:180-183 and
+    ml/model/model.py:134: "calculate the embedding first ... for now we calculate them every timestep for the whole
+    sequence").  ``push(frame)`` runs trunk + token head on the NEW frame(s) only and keeps the last
+    ``image_context_length`` tokens; a tick then passes ``batch["image_tokens"] = cache.tokens()`` instead of
+    ``batch["image_data"]`` and only the frame-sequence encoder runs.  Eval mode only (BatchNorm with running
+    statistics is per-frame independent, so the tokens equal those of the whole-sequence call)."""
+
+    def __init__(self, model, context_length: int | None = None):
+        if model.image_sequence_encoder is None:
+            raise ValueError("the model has no image encoder")
+        self.encoder = model.image_sequence_encoder.image_encoder
+        self.capacity = int(context_length or model.image_sequence_encoder.transformer_encoder.positional_encoding.pe.shape[1])
+        self._tokens: list[torch.Tensor] = []
+
+    def __len__(self) -> int:
+        return len(self._tokens)
+
+    @torch.no_grad()
+    def push(self, frames: torch.Tensor) -> None:
+        """``frames``: (3,R,R) or (n,3,R,R); normalised float32 like the reference's preprocessing output, or raw uint8."""
+        if self.encoder.training:
+            raise RuntimeError("FrameEmbeddingCache needs model.eval(): train-mode BatchNorm couples the frames of a batch")
+        x = frames if frames.dim() == 4 else frames.unsqueeze(0)
+        tok = self.encoder(x.unsqueeze(0))[0]                      # (n, d)
+        self._tokens.extend(tok[i] for i in range(tok.shape[0]))
+        self._tokens = self._tokens[-self.capacity:]
+
+    def tokens(self) -> torch.Tensor:
+        """(1, frames, d) — the cached embeddings, oldest first (ros.py:269 stacks the frame buffer the same way)."""
+        if not self._tokens:
+            raise RuntimeError("no frame has been pushed yet")
+        return torch.stack(self._tokens, dim=0).unsqueeze(0)
 
 
 class TrajectorySampler:
@@ -50,7 +86,8 @@ class TrajectorySampler:
             x_T = torch.randn(B, m.diffusion_action_generator.max_seq_len, m.num_joints, device=any_t.device)
         if not self.use_cuda_graph:
             return self._tick(batch, x_T, denormalize)
-        keys = [k for k in ("joint_command_history", "rotation", "joint_state", "image_data", "game_state") if k in batch]
+        keys = [k for k in ("joint_command_history", "rotation", "joint_state", "image_data", "image_tokens", "game_state")
+                if k in batch]
         sig = (tuple((k, tuple(batch[k].shape), batch[k].dtype) for k in keys), tuple(x_T.shape), denormalize)
         entry = self._graphs.get(sig)
         if entry is None:

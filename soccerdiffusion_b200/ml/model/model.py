@@ -172,7 +172,12 @@ class End2EndDiffusionTransformer(nn.Module):
         if self.joint_states_encoder is not None:
             jobs.append((self.joint_states_encoder, input_data["joint_state"], False))
         if self.image_sequence_encoder is not None:
-            jobs.append((self.image_sequence_encoder, input_data["image_data"], True))
+            if "image_tokens" in input_data and "image_data" not in input_data:
+                # per-frame embeddings computed when the frames arrived (FrameEmbeddingCache; the TODO at
+                # ml/inference/ros.py:180-183): only the frame-sequence encoder runs per tick
+                jobs.append((self.image_sequence_encoder.transformer_encoder, input_data["image_tokens"], True))
+            else:
+                jobs.append((self.image_sequence_encoder, input_data["image_data"], True))
         if self.game_state_encoder is not None:
             jobs.append((self.game_state_encoder, input_data["game_state"], True))
         n_side = sum(1 for _, x, main in jobs if not main)

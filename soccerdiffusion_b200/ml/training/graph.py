@@ -33,6 +33,7 @@ class GraphedTrainStep:
             for _ in range(warmup_steps):
                 self.opt.prepare_captured_step()
                 self._body()
+                self.opt._opt_called = True    # the optimizer step ran (step_captured): what lr_scheduler's order check tracks
                 if self.lrs is not None:
                     self.lrs.step()
         torch.cuda.current_stream().wait_stream(side)
@@ -79,6 +80,7 @@ class GraphedTrainStep:
         self.opt.prepare_captured_step()
         self.graph.replay()
         ops._count(self.launches_per_replay)
+        self.opt._opt_called = True            # the replayed graph contains the optimizer step
         if self.lrs is not None:
             self.lrs.step()
         return self.loss

@@ -316,6 +316,36 @@ def test_trajectory_sampler_control_tick_and_distilled():
     assert rel(d1, w1) < TOL
 
 
+def test_frame_embedding_cache_matches_whole_sequence_tick():
+    """per-frame embeddings cached as the frames arrive give the same trajectory as re-encoding the
+    whole frame history every tick (ros.py:180-183 TODO); the cache slides like the reference's frame buffer."""
+    from soccerdiffusion_b200.ml.inference import FrameEmbeddingCache, TrajectorySampler
+    from soccerdiffusion_b200.schedulers import DDIMScheduler
+
+    hp = synth.PATCH_HP
+    model, _ = synth_model(hp, 1)
+    batch = to_dev(synth.synth_batch(hp, 1, 4))
+    x_T = synth.synth_noise("x_T", hp, 1, 4).cuda()
+    sch = DDIMScheduler(beta_schedule="squaredcos_cap_v2", clip_sample=False)
+    ts = TrajectorySampler(model, sch, 30)
+    want = ts(batch, x_T)
+    frames = batch["image_data"][0]                       # (F, 3, R, R)
+    F = frames.shape[0]
+    cache = FrameEmbeddingCache(model)
+    cache.push(torch.randn_like(frames[0]))               # an older frame that must slide out
+    cache.push(frames[:2])                                # several frames at once
+    for f in frames[2:]:
+        cache.push(f)                                     # one frame per camera callback
+    assert len(cache) == F
+    b2 = {k: v for k, v in batch.items() if k != "image_data"}
+    b2["image_tokens"] = cache.tokens()
+    assert rel(ts(b2, x_T), want) < TOL
+    model.train()
+    with pytest.raises(RuntimeError):
+        cache.push(frames[0])
+    model.eval()
+
+
 def test_empty_batch_and_ragged_sizes():
     hp = synth.PATCH_HP
     model, sd = synth_model(hp, 2)
