@@ -399,6 +399,17 @@ def run_ours(args):
                             launches_per_step=v["launches"] // nprof, avg_launch_ms=v["ms"] / v["launches"],
                             algorithmic_bytes_per_launch=v["bytes"] / v["launches"],
                             share_of_step=round(v["ms"] / nprof / step_ms, 4))
+    if roofline is not None and args.workload == "full" and args.config == "default" and bs == 256:
+        # DRAM bytes per launch of the dominant kernel class from the committed ncu capture of this very command
+        # (profiles/r01_dram_traffic.json, written by tools/ncu_summary.py traffic); null when no capture covers it
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_dram_traffic.json")) as fh:
+                tr = json.load(fh)
+            if roofline["kernel"] in tr:
+                roofline["traffic"] = tr[roofline["kernel"]]["dram_bytes_per_launch"]
+                roofline["traffic_source"] = tr.get("_source")
+        except (OSError, ValueError, KeyError):
+            pass
     if world > 1:
         dist.barrier()
 
@@ -515,7 +526,7 @@ def ddim_latency(model, hp, dev, precision, reps=200):
 
     graphed = TrajectorySampler(model, sch, 30, use_cuda_graph=True)
     # (f)-2: one NEW camera frame per tick is embedded and cached; the tick itself runs on the cached frame tokens
-    cache = FrameEmbeddingCache(model)
+    cache = FrameEmbeddingCache(model, use_cuda_graph=True)
     cache.push(batch["image_data"][0])
     cached_batch = {k: v for k, v in batch.items() if k != "image_data"}
     new_frame = batch["image_data"][0, -1]
@@ -570,7 +581,7 @@ def ddim_latency(model, hp, dev, precision, reps=200):
     out["note"] = ("sampler = x_T -> x_0 with the context given (one persistent-kernel launch; 16-CTA cluster kernel, "
                    "sampler_cta = single-CTA kernel); tick = encode_input_data (10x224^2 frames) + sampler, launched "
                    "kernel by kernel; tick_graph = the same tick replayed from one captured CUDA graph; tick_cached_frames = embed "
-                   "ONE new frame (trunk on 1 frame, eager launches) + graph-replayed tick on the cached frame tokens")
+                   "ONE new frame (trunk on 1 frame, its own graph replay) + graph-replayed tick on the cached frame tokens")
     out["encoder_precision_mode"] = precision
     model.train()
     return out

@@ -29,10 +29,12 @@ class FrameEmbeddingCache:
     ``batch["image_data"]`` and only the frame-sequence encoder runs.  Eval mode only (BatchNorm with running
     statistics is per-frame independent, so the tokens equal those of the whole-sequence call)."""
 
-    def __init__(self, model, context_length: int | None = None):
+    def __init__(self, model, context_length: int | None = None, use_cuda_graph: bool = False):
         if model.image_sequence_encoder is None:
             raise ValueError("the model has no image encoder")
         self.encoder = model.image_sequence_encoder.image_encoder
+        self.use_cuda_graph = use_cuda_graph      # single-frame pushes: trunk + token head replayed from one captured graph
+        self._graphs: dict = {}
         self.capacity = int(context_length or model.image_sequence_encoder.transformer_encoder.positional_encoding.pe.shape[1])
         self._tokens: list[torch.Tensor] = []
 
@@ -45,9 +47,33 @@ class FrameEmbeddingCache:
         if self.encoder.training:
             raise RuntimeError("FrameEmbeddingCache needs model.eval(): train-mode BatchNorm couples the frames of a batch")
         x = frames if frames.dim() == 4 else frames.unsqueeze(0)
-        tok = self.encoder(x.unsqueeze(0))[0]                      # (n, d)
+        if self.use_cuda_graph and x.shape[0] == 1:
+            tok = self._push_graphed(x)
+        else:
+            tok = self.encoder(x.unsqueeze(0))[0]                  # (n, d)
         self._tokens.extend(tok[i] for i in range(tok.shape[0]))
         self._tokens = self._tokens[-self.capacity:]
+
+    def _push_graphed(self, x: torch.Tensor) -> torch.Tensor:
+        sig = (tuple(x.shape), x.dtype)
+        entry = self._graphs.get(sig)
+        if entry is None:
+            static_in = x.clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):                                  # allocations, cuDNN autotuning
+                    self.encoder(static_in.unsqueeze(0))
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self.encoder(static_in.unsqueeze(0))[0]
+            entry = (graph, static_in, static_out)
+            self._graphs[sig] = entry
+        graph, static_in, static_out = entry
+        static_in.copy_(x, non_blocking=True)
+        graph.replay()
+        return static_out.clone()
 
     def tokens(self) -> torch.Tensor:
         """(1, frames, d) — the cached embeddings, oldest first (ros.py:269 stacks the frame buffer the same way)."""

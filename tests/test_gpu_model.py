@@ -322,7 +322,7 @@ def test_frame_embedding_cache_matches_whole_sequence_tick():
     from soccerdiffusion_b200.ml.inference import FrameEmbeddingCache, TrajectorySampler
     from soccerdiffusion_b200.schedulers import DDIMScheduler
 
-    hp = synth.PATCH_HP
+    hp = synth.TINY_HP
     model, _ = synth_model(hp, 1)
     batch = to_dev(synth.synth_batch(hp, 1, 4))
     x_T = synth.synth_noise("x_T", hp, 1, 4).cuda()
@@ -340,6 +340,11 @@ def test_frame_embedding_cache_matches_whole_sequence_tick():
     b2 = {k: v for k, v in batch.items() if k != "image_data"}
     b2["image_tokens"] = cache.tokens()
     assert rel(ts(b2, x_T), want) < TOL
+    # single-frame pushes replayed from a captured CUDA graph give the same tokens
+    gc = FrameEmbeddingCache(model, use_cuda_graph=True)
+    for f in frames:
+        gc.push(f)
+    assert rel(gc.tokens(), cache.tokens()) < 1e-5
     model.train()
     with pytest.raises(RuntimeError):
         cache.push(frames[0])

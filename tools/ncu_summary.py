@@ -2,6 +2,7 @@
 
     python tools/ncu_summary.py launches <launches.csv> <out.md> [title]
     python tools/ncu_summary.py full <report.ncu-rep> <out.md> [title]
+    python tools/ncu_summary.py traffic <dram_metrics.csv> <out.json> [note]
 """
 import csv
 import re
@@ -74,7 +75,48 @@ def full(rep, out, title):
     print(open(out).read()[:2500])
 
 
+
+
+def traffic(path, out_json, note):
+    """`ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --csv` of one training step ->
+    DRAM bytes per bench kernel class (the classes of soccerdiffusion_b200.ops._Timed), per class launch."""
+    import json
+
+    rows = [r for r in csv.reader(open(path, errors="replace")) if len(r) > 5]
+    hdr = rows[0]
+    i_name, i_val, i_metric, i_unit = (hdr.index(k) for k in ("Kernel Name", "Metric Value", "Metric Name", "Metric Unit"))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3}
+    # bench class <- kernels it launches (one class launch = one sd_* entry point call)
+    classes = {"bn_bwd": ("bn_reduce_kernel<1>", "bn_bwd_apply_kernel", "bn_param_grads_kernel"),
+               "bn_stats": ("bn_reduce_kernel<0>", "bn_finalize_kernel"),
+               "bn_apply": ("bn_apply_kernel",),
+               "stem_bn_relu_pool_fwd": ("stem_fwd_band_kernel",),
+               "stem_bn_relu_pool_bwd": ("stem_bwd_block_kernel",),
+               "stem_fprop_s2d": ("stem_fprop_tma_kernel",),
+               "stem_wgrad_s2d": ("stem_wgrad_tma_kernel",),
+               "stem_pack_s2d": ("stem_pack_kernel",)}
+    primary = {"bn_bwd": "bn_bwd_apply_kernel", "bn_stats": "bn_reduce_kernel<0>", "stem_bn_relu_pool_bwd": "stem_bwd_block_kernel<1>"}
+    agg = {c: {"dram_bytes": 0.0, "us": 0.0, "launches": 0} for c in classes}
+    for r in rows[1:]:
+        name = r[i_name]
+        for c, kernels in classes.items():
+            if any(k in name for k in kernels):
+                v = float(r[i_val].replace(",", "")) * scale.get(r[i_unit], 1.0)
+                if r[i_metric].startswith("dram__bytes"):
+                    agg[c]["dram_bytes"] += v
+                elif r[i_metric] == "gpu__time_duration.sum":
+                    agg[c]["us"] += v
+                    if primary.get(c, kernels[0]) in name:
+                        agg[c]["launches"] += 1
+    res = {c: {"dram_bytes_per_launch": v["dram_bytes"] / v["launches"], "launches": v["launches"],
+               "kernel_us_per_launch": v["us"] / v["launches"]} for c, v in agg.items() if v["launches"]}
+    res["_source"] = note
+    with open(out_json, "w") as fh:
+        json.dump(res, fh, indent=1)
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
     kind, src, out = sys.argv[1:4]
     title = sys.argv[4] if len(sys.argv) > 4 else src
-    (launches if kind == "launches" else full)(src, out, title)
+    {"launches": launches, "full": full, "traffic": traffic}[kind](src, out, title)
