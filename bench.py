@@ -240,13 +240,15 @@ def run_ours(args):
     batch = {k: v.to(dev) for k, v in host.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values())
 
-    img_tokens = None
     if args.workload == "inscope":
-        # image tokens precomputed: the trunk (library cuDNN, SURVEY.md §8 a8') is outside the timed step
-        img_tokens = torch.randn(bs, hp["image_context_length"], hp["hidden_dim"], device=dev)
+        # image tokens precomputed: the trunk (library cuDNN, SURVEY.md §8 a8') is outside the timed step; the model takes
+        # them through its ``image_tokens`` input (the per-frame embedding interface of FrameEmbeddingCache)
+        host["image_tokens"] = torch.randn(bs, hp["image_context_length"], hp["hidden_dim"]).pin_memory()
+        batch["image_tokens"] = host["image_tokens"].to(dev)
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
 
     graphed = None
-    if args.graph and args.workload in ("full", "denoiser") and not args.ncu_range:
+    if args.graph and not args.ncu_range:
         from soccerdiffusion_b200.ml.training import GraphedTrainStep
 
         try:
@@ -260,12 +262,8 @@ def run_ours(args):
     def step(b):
         if graphed is not None:
             return graphed(b)
-        if args.workload == "full":
-            return train_step(model, opt, sch, norm, b, lr_scheduler=lrs, data_parallel=world > 1)
-        if args.workload == "denoiser":
-            return train_step(model, opt, sch, norm, b, lr_scheduler=lrs, data_parallel=world > 1,
-                              decoder_pretraining=True)
-        return _inscope_step(model, opt, sch, b, img_tokens, lrs, world > 1)
+        return train_step(model, opt, sch, norm, b, lr_scheduler=lrs, data_parallel=world > 1,
+                          decoder_pretraining=args.workload == "denoiser")
 
     def sync():
         if world > 1:
@@ -362,12 +360,8 @@ def run_ours(args):
     pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pe0.record()
     def eager_step(b):
-        if args.workload == "full":
-            return train_step(model, opt, sch, norm, b, lr_scheduler=lrs, data_parallel=world > 1)
-        if args.workload == "denoiser":
-            return train_step(model, opt, sch, norm, b, lr_scheduler=lrs, data_parallel=world > 1,
-                              decoder_pretraining=True)
-        return _inscope_step(model, opt, sch, b, img_tokens, lrs, world > 1)
+        return train_step(model, opt, sch, norm, b, lr_scheduler=lrs, data_parallel=world > 1,
+                          decoder_pretraining=args.workload == "denoiser")
 
     for _ in range(nprof):
         eager_step(batch)
@@ -477,32 +471,6 @@ def _run_e2e(step, feeder, dev):
         pending[0].synchronize()
         losses.append(float(pending[1][0]))
     return losses
-
-
-def _inscope_step(model, opt, sch, batch, img_tokens, lrs, dp):
-    """train.py:193-240 with the image tokens given (trunk outside): every kernel in the step is libsd_b200's."""
-    import torch
-
-    from soccerdiffusion_b200.functional import mse_loss
-    from soccerdiffusion_b200.ml.training.step import allreduce_gradients, q_sample
-
-    jt = batch["joint_command"]
-    bsz = jt.size(0)
-    opt.zero_grad()
-    t = torch.randint(0, 1000, (bsz,), device=jt.device)
-    noise = torch.randn(jt.shape, device=jt.device)
-    noisy = q_sample(sch, model, jt, noise, t)
-    ctx = [model.action_history_encoder(batch["joint_command_history"]), model.imu_encoder(batch["rotation"]),
-           model.joint_states_encoder(batch["joint_state"]),
-           model.image_sequence_encoder.transformer_encoder(img_tokens), model.game_state_encoder(batch["game_state"])]
-    pred = model.forward_with_context(ctx, noisy, t)
-    loss = mse_loss(pred, noise)
-    loss.backward()
-    if dp:
-        allreduce_gradients(opt)
-    opt.step()
-    lrs.step()
-    return loss.detach()
 
 
 def ddim_latency(model, hp, dev, precision, reps=200):
