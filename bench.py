@@ -344,6 +344,20 @@ def run_ours(args):
         ms_e2e_u8 = e4.elapsed_time(e5)
         del step8
 
+    # pinned host -> device copy bandwidth of this box (explains the gap between `value` and `e2e`: at bs=256 the fp32 frames
+    # are 1.55 GB per step)
+    probe = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+    probe_dev = torch.empty_like(probe, device=dev)
+    probe_dev.copy_(probe, non_blocking=True)
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record()
+    for _ in range(4):
+        probe_dev.copy_(probe, non_blocking=True)
+    h1.record()
+    torch.cuda.synchronize()
+    h2d_gbps = 4 * probe.numel() / (h0.elapsed_time(h1) * 1e6)
+    del probe, probe_dev
+
     if world > 1:
         tt = torch.tensor([ms, ms_e2e, ms_e2e_u8 or 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -432,6 +446,7 @@ def run_ours(args):
                         launch="one CUDA graph replay per step" if used_graph else "kernel by kernel"),
             e2e=dict(value=gb * args.steps / (ms_e2e / 1e3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                      loss_readback="every step, pinned async copy, read on the host one step behind the launch front",
+                     h2d_gbps_measured=round(h2d_gbps, 1),
                      input="float32 frames preprocessed on the host (the reference's dataset output)"),
             e2e_uint8=(dict(value=gb * args.steps / (ms_e2e_u8 / 1e3), unit=UNIT, h2d_bytes_per_step=h2d_u8, d2h_bytes_per_step=4,
                             input="raw uint8 frames; ToDtype(scale)+Normalize fused into the stem packing kernel on the device")
