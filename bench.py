@@ -301,15 +301,8 @@ def run_ours(args):
     from soccerdiffusion_b200.ml.training import DevicePrefetcher
 
     step({k: v.to(dev, non_blocking=True) for k, v in host.items()}).item()
-    _run_e2e(step, DevicePrefetcher((host for _ in range(2)), dev), dev)   # untimed: allocations of the feeder path
     sync()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    feeder = DevicePrefetcher((host for _ in range(args.steps)), dev)   # first copies are issued inside the timed region
-    losses = _run_e2e(step, feeder, dev)
-    e3.record()
-    sync()
-    ms_e2e = e2.elapsed_time(e3)
+    ms_e2e = _run_e2e(step, host, dev, warm=2, timed=args.steps)
 
     # ---- e2e with RAW uint8 frames: the reference's host preprocessing (ToDtype + Normalize) runs on
     #      the device inside the stem's packing kernel; the per-step host->device copy is 4x smaller ---------------------
@@ -334,14 +327,8 @@ def run_ours(args):
         if step8 is None:
             step8 = lambda b: train_step(model, opt, sch, norm, b, lr_scheduler=lrs, data_parallel=world > 1)
         step8({k: v.to(dev, non_blocking=True) for k, v in host8.items()}).item()
-        _run_e2e(step8, DevicePrefetcher((host8 for _ in range(2)), dev), dev)   # untimed: allocations of the feeder path
         sync()
-        e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e4.record()
-        _run_e2e(step8, DevicePrefetcher((host8 for _ in range(args.steps)), dev), dev)
-        e5.record()
-        sync()
-        ms_e2e_u8 = e4.elapsed_time(e5)
+        ms_e2e_u8 = _run_e2e(step8, host8, dev, warm=2, timed=args.steps)
         del step8
 
     # pinned host -> device copy bandwidth of this box (explains the gap between `value` and `e2e`: at bs=256 the fp32 frames
@@ -426,6 +413,13 @@ def run_ours(args):
     if rank == 0 and not args.no_ddim:
         ddim = ddim_latency(model, hp, dev, args.precision)
 
+    distill = None
+    if rank == 0 and world == 1 and args.workload == "full" and not args.no_ddim:
+        try:
+            distill = distill_throughput(hp, dev, min(bs, 64), args.precision)
+        except Exception as e:   # an extra leg must never cost the headline line
+            sys.stderr.write(f"[bench] distillation leg failed: {type(e).__name__}: {e}\n")
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -446,12 +440,13 @@ def run_ours(args):
                         launch="one CUDA graph replay per step" if used_graph else "kernel by kernel"),
             e2e=dict(value=gb * args.steps / (ms_e2e / 1e3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                      loss_readback="every step, pinned async copy, read on the host one step behind the launch front",
+                     pipeline="steady state: feeder two batches ahead, K copies issued and K steps executed between the events",
                      h2d_gbps_measured=round(h2d_gbps, 1),
                      input="float32 frames preprocessed on the host (the reference's dataset output)"),
             e2e_uint8=(dict(value=gb * args.steps / (ms_e2e_u8 / 1e3), unit=UNIT, h2d_bytes_per_step=h2d_u8, d2h_bytes_per_step=4,
                             input="raw uint8 frames; ToDtype(scale)+Normalize fused into the stem packing kernel on the device")
                        if ms_e2e_u8 else None),
-            gpu_launches=launches, clocks=clk, roofline=roofline, kernel_classes=kernel_classes, cpu_baseline=cpu, ddim=ddim)
+            gpu_launches=launches, clocks=clk, roofline=roofline, kernel_classes=kernel_classes, cpu_baseline=cpu, ddim=ddim, distill=distill)
         emit(line)
     if world > 1:
         # all ranks leave together; a hard exit avoids tearing down NCCL communicators that captured CUDA graphs still
@@ -463,29 +458,42 @@ def run_ours(args):
         os._exit(0)
 
 
-def _run_e2e(step, feeder, dev):
-    """End-to-end loop: every step's loss is copied device->host (pinned, asynchronous) and READ on the host inside the
-    timed region, one step behind the launch front — the host blocks on step i-1's loss while step i runs, so the
-    device never idles waiting for the next launch (a training loop that logs its loss does exactly this)."""
+def _run_e2e(step, host_batch, dev, warm: int, timed: int) -> float:
+    """End-to-end loop in steady state; returns the device time (ms) of ``timed`` consecutive iterations.
+
+    One DevicePrefetcher feeds ``warm + timed + 2`` batches from pinned host memory: it runs two batches ahead, so between
+    the two timing events exactly ``timed`` host->device copies are issued (for the batches two iterations later) while
+    ``timed`` steps execute — copies overlap compute, which is the design being measured; the ``warm`` untimed iterations
+    fill that pipeline (with a cold pipeline the first step would wait ~28 ms for its 1.5 GB batch, which a 5-step
+    measurement would amortise as +5 ms/step).  Every step's loss is copied device->host (pinned, asynchronous) and read
+    on the host one step behind the launch front, inside the timed region, so the device never idles waiting for the
+    next launch (a training loop that logs its loss does exactly this)."""
     import torch
 
+    from soccerdiffusion_b200.ml.training import DevicePrefetcher
+
+    feeder = iter(DevicePrefetcher((host_batch for _ in range(warm + timed + 2)), dev))
     bufs = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
-    pending, losses, i = None, [], 0
-    for b in feeder:
-        loss = step(b)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cur = torch.cuda.current_stream(dev)
+    pending, losses = None, []
+    for i in range(warm + timed):
+        if i == warm:
+            e0.record(cur)           # in stream order: after the last warm step, before the first timed one
+        loss = step(next(feeder))
         buf = bufs[i % 2]
         buf.copy_(loss.reshape(1), non_blocking=True)
         ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(dev))
+        ev.record(cur)
         if pending is not None:
             pending[0].synchronize()
             losses.append(float(pending[1][0]))
         pending = (ev, buf)
-        i += 1
-    if pending is not None:
-        pending[0].synchronize()
-        losses.append(float(pending[1][0]))
-    return losses
+    e1.record(cur)
+    pending[0].synchronize()
+    losses.append(float(pending[1][0]))
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1)
 
 
 def ddim_latency(model, hp, dev, precision, reps=200):
@@ -568,6 +576,38 @@ def ddim_latency(model, hp, dev, precision, reps=200):
     out["encoder_precision_mode"] = precision
     model.train()
     return out
+
+
+def distill_throughput(hp, dev, bs, precision, steps=3):
+    """distill.py:160-205 as one workload: the teacher encodes the batch and samples a 30-step DDIM
+    trajectory per sample under no_grad (persistent sampler kernels), the student is trained for one step on the
+    teacher's context (forward_with_context at t = 0, MSE, backward, FusedAdamW)."""
+    import torch
+
+    from soccerdiffusion_b200 import config
+    from soccerdiffusion_b200.ml.training import FusedAdamW, distill_step
+    from soccerdiffusion_b200.schedulers import DDIMScheduler
+
+    torch.manual_seed(1)
+    teacher = config.build_model(hp).to(dev).eval()
+    student = config.build_model(hp).to(dev).train()
+    opt = FusedAdamW(student.parameters(), lr=hp["lr"])
+    sch = DDIMScheduler(beta_schedule="squaredcos_cap_v2", clip_sample=False)
+    batch = config.synthetic_batch(hp, bs, dev, seed=3)
+    for _ in range(2):
+        distill_step(teacher, student, opt, sch, batch, 30)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        distill_step(teacher, student, opt, sch, batch, 30)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del teacher, student, opt
+    return dict(ms_per_step=ms, samples_per_s=bs * 1e3 / ms, batch=bs, teacher_steps=30, precision_mode=precision,
+                note="teacher: eval-mode encode + 30-step DDIM per sample (no_grad); student: one training step on the "
+                     "teacher's context; launched kernel by kernel")
 
 
 _REAL_STDOUT = None

@@ -74,6 +74,43 @@ struct SamplerArgs {
     long long* dbg;       // optional: clock64() stamps of the cluster kernel's phases (CTA 0, thread 0), 96 per step
 };
 
+// acc[t] += sum_{k0 <= k < k1} W[k] * x[k][t] for one output column: the weights come from L2 (__ldcg), 16 loads in flight
+// per thread before the first use (the loop is L2-latency-bound: with 4 in flight a 128-deep column cost ~10 us), the
+// activations are shared-memory broadcasts.
+template <int TR>
+__device__ __forceinline__ void cta_dot_column(float (&acc)[TR], const float* __restrict__ wp, int ldw,
+                                               const float* __restrict__ xp, int k0, int k1) {
+    int k = k0;
+    for (; k + 16 <= k1; k += 16) {
+        float w[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w[j] = __ldcg(wp + (long long)(k + j) * ldw);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+#pragma unroll
+            for (int q = 0; q < TR / 4; ++q) {
+                const float4 x4 = *reinterpret_cast<const float4*>(xp + (k + j) * TR + 4 * q);
+                acc[4 * q + 0] = fmaf(w[j], x4.x, acc[4 * q + 0]);
+                acc[4 * q + 1] = fmaf(w[j], x4.y, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(w[j], x4.z, acc[4 * q + 2]);
+                acc[4 * q + 3] = fmaf(w[j], x4.w, acc[4 * q + 3]);
+            }
+        }
+    }
+#pragma unroll 4
+    for (; k < k1; ++k) {
+        const float w = __ldcg(wp + (long long)k * ldw);
+#pragma unroll
+        for (int q = 0; q < TR / 4; ++q) {
+            const float4 x4 = *reinterpret_cast<const float4*>(xp + k * TR + 4 * q);
+            acc[4 * q + 0] = fmaf(w, x4.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(w, x4.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(w, x4.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(w, x4.w, acc[4 * q + 3]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // CTA-wide skinny GEMM:  out[t][i] = sum_k xT[b(i)][k][t] * Wt[b(i)][k][n(i)],  t < TR rows kept in
 // registers, one output column per thread, K split across thread groups when columns are scarce.
@@ -95,18 +132,7 @@ __device__ __forceinline__ void cta_gemm(const float* Wt, int ldw, long long w_b
             float acc[TR];
 #pragma unroll
             for (int t = 0; t < TR; ++t) acc[t] = 0.f;
-#pragma unroll 4
-            for (int k = k0; k < k1; ++k) {
-                const float w = __ldcg(wp + (long long)k * ldw);
-#pragma unroll
-                for (int q = 0; q < TR / 4; ++q) {
-                    const float4 x4 = *reinterpret_cast<const float4*>(xp + k * TR + 4 * q);
-                    acc[4 * q + 0] = fmaf(w, x4.x, acc[4 * q + 0]);
-                    acc[4 * q + 1] = fmaf(w, x4.y, acc[4 * q + 1]);
-                    acc[4 * q + 2] = fmaf(w, x4.z, acc[4 * q + 2]);
-                    acc[4 * q + 3] = fmaf(w, x4.w, acc[4 * q + 3]);
-                }
-            }
+            cta_dot_column<TR>(acc, wp, ldw, xp, k0, k1);
 #pragma unroll
             for (int t = 0; t < TR; ++t) scr[(g * TR + t) * items + i] = acc[t];
         }
@@ -125,18 +151,7 @@ __device__ __forceinline__ void cta_gemm(const float* Wt, int ldw, long long w_b
             float acc[TR];
 #pragma unroll
             for (int t = 0; t < TR; ++t) acc[t] = 0.f;
-#pragma unroll 4
-            for (int k = 0; k < K; ++k) {
-                const float w = __ldcg(wp + (long long)k * ldw);
-#pragma unroll
-                for (int q = 0; q < TR / 4; ++q) {
-                    const float4 x4 = *reinterpret_cast<const float4*>(xp + k * TR + 4 * q);
-                    acc[4 * q + 0] = fmaf(w, x4.x, acc[4 * q + 0]);
-                    acc[4 * q + 1] = fmaf(w, x4.y, acc[4 * q + 1]);
-                    acc[4 * q + 2] = fmaf(w, x4.z, acc[4 * q + 2]);
-                    acc[4 * q + 3] = fmaf(w, x4.w, acc[4 * q + 3]);
-                }
-            }
+            cta_dot_column<TR>(acc, wp, ldw, xp, 0, K);
 #pragma unroll
             for (int t = 0; t < TR; ++t)
                 if (t < T) epi(bidx, n, t, acc[t]);

@@ -12,9 +12,24 @@ from __future__ import annotations
 import torch
 
 
+def _chunked_copy(dst: torch.Tensor, src: torch.Tensor, chunk_bytes: int) -> None:
+    """Host->device copy issued as several DMA transfers of at most ``chunk_bytes``: a single 1.5 GB transfer occupies
+    its copy engine for ~28 ms, and the memsets / device-to-device copies inside the replayed training-step graph that
+    land on the same engine wait behind it; short transfers let them interleave."""
+    n = src.numel() * src.element_size()
+    if chunk_bytes <= 0 or n <= chunk_bytes or not (src.is_contiguous() and dst.is_contiguous()):
+        dst.copy_(src, non_blocking=True)
+        return
+    d, s_ = dst.view(-1), src.view(-1)
+    step = max(1, chunk_bytes // src.element_size())
+    for i in range(0, s_.numel(), step):
+        d[i:i + step].copy_(s_[i:i + step], non_blocking=True)
+
+
 class DevicePrefetcher:
-    def __init__(self, batches, device, depth: int = 2):
+    def __init__(self, batches, device, depth: int = 2, chunk_bytes: int = 32 << 20):
         """``batches``: iterable of dicts of (ideally pinned) host tensors, all of the same shapes."""
+        self.chunk_bytes = chunk_bytes
         self.it = iter(batches)
         self.device = device
         self.copy_stream = torch.cuda.Stream(device=device)
@@ -43,7 +58,7 @@ class DevicePrefetcher:
             if free is not None:
                 self.copy_stream.wait_event(free)      # the step that read this buffer set has finished
             for k, v in host.items():
-                dev[k].copy_(v, non_blocking=True)
+                _chunked_copy(dev[k], v, self.chunk_bytes)
             ready.record(self.copy_stream)
         self.queue.append(i)
 
