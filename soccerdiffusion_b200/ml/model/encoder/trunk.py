@@ -8,13 +8,12 @@ Parameters are read from the torchvision modules (they stay the ``state_dict`` h
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn.functional as F
 
 from soccerdiffusion_b200 import ops
-
-
-import os
 
 _USE_TC_STEM_WGRAD = os.environ.get("SD_B200_STEM_WGRAD", "tc") == "tc"
 _USE_TC_STEM_FPROP = os.environ.get("SD_B200_STEM_FPROP", "tc") == "tc"
@@ -260,12 +259,17 @@ def supported(encoder) -> bool:
     return ok and mp.kernel_size == 3 and mp.stride == 2 and mp.padding == 1 and isinstance(encoder.bn1, torch.nn.BatchNorm2d)
 
 
+# how many cuDNN algorithms the autotuner times per convolution shape (torch default 10; 0 = all)
+_CUDNN_BENCHMARK_LIMIT = int(os.environ.get("SD_B200_CUDNN_BENCHMARK_LIMIT", "10"))
+
+
 def resnet_trunk_bf16(encoder, images: torch.Tensor) -> torch.Tensor:
     """(n,3,R,R) -> (n,C,h,w) bf16 channels_last: conv1..layer4 of a torchvision ResNet."""
     from torchvision.models.resnet import BasicBlock
 
     # cuDNN autotuning for the (fixed) convolution shapes of the trunk; restored on exit
-    with torch.backends.cudnn.flags(enabled=True, benchmark=True), torch.autocast("cuda", dtype=torch.bfloat16):
+    with torch.backends.cudnn.flags(enabled=True, benchmark=True, benchmark_limit=_CUDNN_BENCHMARK_LIMIT), \
+            torch.autocast("cuda", dtype=torch.bfloat16):
         bn1 = encoder.bn1
         presums = None
         if _stem_is_s2d_compatible(encoder.conv1, images):
