@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(NT, 1) stem_wgrad_tma_kernel(const __grid_cons
         mbar_init(&bar_done, 1);
         mbar_fence_init();
     }
-    if (warp == 0) tmem_alloc(&tmem_slot, 128);
+    if (warp == 0) tmem_alloc(&tmem_slot, 256);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -215,21 +215,20 @@ __global__ void __launch_bounds__(NT, 1) stem_wgrad_tma_kernel(const __grid_cons
             tma_load_2d(base + 4 * blk, &tmB, 0, (int)(r * WO), &bar_full[s]);
         }
     } else if (warp == 1 && lane == 0) {
-        const uint32_t idesc = instr_desc_bf16(128, 64, 1, 1);
+        // D[64 output channels][256 = (kh, kw, ci)] += dy^T (M = 64, MN-major A) x patches (N = 256: the four filter-row
+        // tiles are the four 64-wide MN blocks of ONE MN-major B operand, LBO = blk).  One 64 x 256 x 16 instruction per 16
+        // pixels instead of two 128 x 64 x 16: with N = 64 the tensor pipe ran at ~110 clk per instruction (25 % active).
+        const uint32_t idesc = instr_desc_bf16(64, 256, 1, 1);
         const int ksteps = KCr / 16;
         for (int ci = 0; ci < nrows; ++ci) {
             const int s = ci % TMA_STAGES;
             mbar_wait(&bar_full[s], (uint32_t)((ci / TMA_STAGES) & 1));
             tc_fence_after_sync();
             const uint32_t base = smem_u32(smem + s * stage_bytes);
-            const uint64_t db = smem_desc_mn_sw128(base + 4 * blk, (uint32_t)blk, 1024);
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-                const uint64_t da = smem_desc_mn_sw128(base + mt * 2 * blk, (uint32_t)blk, 1024);
-                for (int ks = 0; ks < ksteps; ++ks)
-                    mma_bf16_ss(tmem + mt * 64, da + (uint64_t)(128 * ks), db + (uint64_t)(128 * ks), idesc,
-                                (ci > 0 || ks > 0) ? 1u : 0u);
-            }
+            const uint64_t da = smem_desc_mn_sw128(base + 4 * blk, (uint32_t)blk, 1024);   // dy tile: 64 channels wide
+            const uint64_t db = smem_desc_mn_sw128(base, (uint32_t)blk, 1024);             // 4 x 64 patch elements
+            for (int ks = 0; ks < ksteps; ++ks)
+                mma_bf16_ss(tmem, da + (uint64_t)(128 * ks), db + (uint64_t)(128 * ks), idesc, (ci > 0 || ks > 0) ? 1u : 0u);
             mma_commit(&bar_empty[s]);
             if (ci == nrows - 1) mma_commit(&bar_done);
         }
@@ -238,19 +237,23 @@ __global__ void __launch_bounds__(NT, 1) stem_wgrad_tma_kernel(const __grid_cons
     if (nrows > 0) {
         mbar_wait(&bar_done, 0);
         tc_fence_after_sync();
-        const int q = warp & 3, mt = warp >> 2;
-        const int j = mt * 128 + q * 32 + lane;
+        // M = 64 accumulator layout: output channel c lives in TMEM lane (c % 16) + 32 * (c / 16); column = k index j
+        const int q = warp & 3, half = warp >> 2;
+        const int c = q * 16 + lane;
 #pragma unroll
-        for (int cb = 0; cb < 2; ++cb) {
+        for (int cb = 0; cb < 4; ++cb) {
+            const int j0 = half * 128 + cb * 32;
             float v[32];
-            tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 64 + cb * 32), v);
+            tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)j0, v);
+            if (lane < 16) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) atomicAdd(dw + j * 64 + cb * 32 + c, v[c]);
+                for (int j = 0; j < 32; ++j) atomicAdd(dw + (j0 + j) * 64 + c, v[j]);
+            }
         }
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 128);
+    if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
 // ---- conv1 forward (space-to-depth form) on the same TMA tensor map: y[p][c] = sum_j patch[p][j] * W[c][j] ------------
