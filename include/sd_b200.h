@@ -169,6 +169,12 @@ int sd_bn_apply_nhwc_bf16(const void* x, const void* residual, const float* mean
 int sd_bn_bwd_nhwc_bf16(const void* dy, const void* relu_mask, const void* x, const float* mean, const float* invstd,
                         const float* gamma, const float* beta_recompute, double* sums, void* dx, void* dres, float* dgamma, float* dbeta, long long R,
                         int C, void* stream);
+/* Same with TWO incoming gradients (dy2 may be NULL): when the BatchNorm output feeds two consumers (a residual block's
+ * output goes to the next block's convolution AND its identity path) the two gradients are summed in fp32 inside the
+ * reduction and apply kernels instead of by a separate elementwise-add pass over the tensor. */
+int sd_bn_bwd2_nhwc_bf16(const void* dy, const void* dy2, const void* relu_mask, const void* x, const float* mean,
+                         const float* invstd, const float* gamma, const float* beta_recompute, double* sums, void* dx,
+                         void* dres, float* dgamma, float* dbeta, long long R, int C, void* stream);
 /* fp32 NCHW images (N,3,H,W), H and W even -> bf16 NHWC (N,(H+6)/2,(W+6)/2,16): 3-pixel zero padding + 2x2
  * space-to-depth (channel = c*4 + dy*2 + dx, 12 used), the layout in which the 7x7/s2/p3 stem convolution
  * (torchvision resnet conv1; ml/model/encoder/image.py:55-73) is a 4x4/s1 convolution with Cin=16 */

@@ -92,6 +92,7 @@ SIGNATURES = {
     "sd_bn_stats_nhwc_bf16": [c_f, c_ll, c_i, c_f, c_fl, c_fl, c_f, c_f, c_f, c_f, c_f],
     "sd_bn_apply_nhwc_bf16": [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_ll, c_i, c_f],
     "sd_bn_bwd_nhwc_bf16": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_ll, c_i, c_f],
+    "sd_bn_bwd2_nhwc_bf16": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_ll, c_i, c_f],
     "sd_stem_pack_s2d_bf16": [c_f, c_f, c_i, c_i, c_i, c_f],
     "sd_stem_pack_s2d_u8": [c_f, c_f, c_i, c_i, c_i, c_fl, c_fl, c_fl, c_fl, c_fl, c_fl, c_f],
     "sd_stem_fprop_s2d_bf16": [c_f, c_f, c_f, c_i, c_i, c_i, c_f],

@@ -50,7 +50,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kT, MODE == 0 ? 6 : 3) bn_reduce_kernel(
     const uint4* __restrict__ x, const uint4* __restrict__ dy, const unsigned char* __restrict__ y,
     const float* __restrict__ mean, const float* __restrict__ invstd, long long nvec, int CV, double* __restrict__ out, int C,
-    const float* __restrict__ gamma_rc, const float* __restrict__ beta_rc) {
+    const float* __restrict__ gamma_rc, const float* __restrict__ beta_rc, const uint4* __restrict__ dy2) {
     __shared__ float red[2][kT][8 + 1];
     const int tid = threadIdx.x;
     const int cv = tid % CV;   // kT % CV == 0: a thread keeps its channel group for every vector it visits
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(kT, MODE == 0 ? 6 : 3) bn_reduce_kernel(
     const long long v0 = blockIdx.x * per_cta, v1 = min(nvec, v0 + per_cta);
     constexpr int U = MODE == 0 ? 4 : 2;   // vectors per iteration: all their loads are issued before any use
     for (long long v = v0 + tid; v < v1; v += U * kT) {
-        uint4 ux[U], ud[U];
+        uint4 ux[U], ud[U], ue[U];
         unsigned mk[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(kT, MODE == 0 ? 6 : 3) bn_reduce_kernel(
                 ux[u] = ld_stream(x + w);
                 if (MODE == 1) {
                     ud[u] = ld_stream(dy + w);
+                    if (dy2) ue[u] = ld_stream(dy2 + w);
                     if (y) mk[u] = y[w];
                 }
             }
@@ -96,6 +97,12 @@ __global__ void __launch_bounds__(kT, MODE == 0 ? 6 : 3) bn_reduce_kernel(
             } else {
                 float g[8];
                 unpack8(ud[u], g);
+                if (dy2) {   // the output had two consumers: their gradients are summed here, in fp32
+                    float g2[8];
+                    unpack8(ue[u], g2);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) g[i] += g2[i];
+                }
                 if (y) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) g[i] = (mk[u] >> i) & 1u ? g[i] : 0.f;
@@ -205,7 +212,8 @@ __global__ void __launch_bounds__(kT, 3) bn_bwd_apply_kernel(const uint4* __rest
                                                              const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                              const double* __restrict__ sums, long long R,
                                                              uint4* __restrict__ dx, uint4* __restrict__ dres, long long nvec,
-                                                             int CV, int C, const float* __restrict__ beta_rc) {
+                                                             int CV, int C, const float* __restrict__ beta_rc,
+                                                             const uint4* __restrict__ dy2) {
     const long long stride = (long long)gridDim.x * kT;
     const long long v0 = (long long)blockIdx.x * kT + threadIdx.x;
     const int cv = threadIdx.x % CV;
@@ -224,13 +232,15 @@ __global__ void __launch_bounds__(kT, 3) bn_bwd_apply_kernel(const uint4* __rest
     for (long long v = v0; v < nvec; v += 2 * stride) {
         const long long w = v + stride;
         const bool two = w < nvec;
-        uint4 ud[2], ux[2];
+        uint4 ud[2], ux[2], ue[2];
         unsigned mk[2] = {0xFFu, 0xFFu};
         ud[0] = ld_stream(dy + v);
         ux[0] = ld_stream(x + v);
+        if (dy2) ue[0] = ld_stream(dy2 + v);
         if (two) {
             ud[1] = ld_stream(dy + w);
             ux[1] = ld_stream(x + w);
+            if (dy2) ue[1] = ld_stream(dy2 + w);
         }
         if (y) {
             mk[0] = y[v];
@@ -243,6 +253,12 @@ __global__ void __launch_bounds__(kT, 3) bn_bwd_apply_kernel(const uint4* __rest
             float g[8], fx[8];
             unpack8(ud[u], g);
             unpack8(ux[u], fx);
+            if (dy2) {
+                float g2[8];
+                unpack8(ue[u], g2);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) g[i] += g2[i];
+            }
             if (y) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) g[i] = (mk[u] >> i) & 1u ? g[i] : 0.f;
@@ -574,7 +590,7 @@ extern "C" int sd_bn_stats_nhwc_bf16(const void* x, long long R, int C, double* 
     if (!occ_grid) occ_grid = wave_grid(bn_reduce_kernel<0>, 1ll << 40, 1);
     const int grid = (int)min((long long)occ_grid, (nvec + kT - 1) / kT);
     bn_reduce_kernel<0><<<grid, kT, 0, st>>>((const uint4*)x, nullptr, nullptr, nullptr, nullptr, nvec, C / 8, sums, C, nullptr,
-                                             nullptr);
+                                             nullptr, nullptr);
     SD_LAUNCH_CHECK();
     bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, R, C, eps, momentum, mean, invstd, running_mean, running_var);
     SD_LAUNCH_CHECK();
@@ -604,7 +620,7 @@ extern "C" int sd_bn_apply_nhwc_bf16(const void* x, const void* residual, const 
     return SD_OK;
 }
 
-extern "C" int sd_bn_bwd_nhwc_bf16(const void* dy, const void* relu_mask, const void* x, const float* mean,
+extern "C" int sd_bn_bwd2_nhwc_bf16(const void* dy, const void* dy2, const void* relu_mask, const void* x, const float* mean,
                                    const float* invstd, const float* gamma, const float* beta_recompute, double* sums,
                                    void* dx, void* dres, float* dgamma, float* dbeta, long long R, int C, void* stream) {
     if (R <= 0) return SD_OK;
@@ -619,15 +635,22 @@ extern "C" int sd_bn_bwd_nhwc_bf16(const void* dy, const void* relu_mask, const 
     }
     const int grid = (int)min((long long)occ_grid, (nvec + kT - 1) / kT);
     bn_reduce_kernel<1><<<grid, kT, 0, st>>>((const uint4*)x, (const uint4*)dy, (const unsigned char*)relu_mask, mean, invstd, nvec,
-                                             C / 8, sums, C, gamma, relu_mask ? nullptr : beta_recompute);
+                                             C / 8, sums, C, gamma, relu_mask ? nullptr : beta_recompute, (const uint4*)dy2);
     SD_LAUNCH_CHECK();
     bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, C, dgamma, dbeta);
     SD_LAUNCH_CHECK();
     bn_bwd_apply_kernel<<<(int)min((long long)occ_grid_apply, (nvec + kT - 1) / kT), kT, 0, st>>>((const uint4*)dy, (const unsigned char*)relu_mask, (const uint4*)x, mean,
                                                           invstd, gamma, sums, R, (uint4*)dx, (uint4*)dres, nvec, C / 8, C,
-                                                          relu_mask ? nullptr : beta_recompute);
+                                                          relu_mask ? nullptr : beta_recompute, (const uint4*)dy2);
     SD_LAUNCH_CHECK();
     return SD_OK;
+}
+
+extern "C" int sd_bn_bwd_nhwc_bf16(const void* dy, const void* relu_mask, const void* x, const float* mean,
+                                   const float* invstd, const float* gamma, const float* beta_recompute, double* sums,
+                                   void* dx, void* dres, float* dgamma, float* dbeta, long long R, int C, void* stream) {
+    return sd_bn_bwd2_nhwc_bf16(dy, nullptr, relu_mask, x, mean, invstd, gamma, beta_recompute, sums, dx, dres, dgamma, dbeta, R,
+                                C, stream);
 }
 
 extern "C" int sd_maxpool3x3s2_nhwc_bf16_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, void* stream) {

@@ -28,7 +28,11 @@ class FusedBNAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta, running_mean, running_var, residual, relu: bool, training: bool, momentum: float,
-                eps: float):
+                eps: float, fork: bool = False):
+        """``fork``: return the output TWICE (two tensors sharing storage).  A residual block's output feeds the next
+        block's convolution and its identity path; handing each consumer its own output makes autograd deliver the two
+        gradients separately, and the backward kernels sum them on the fly (sd_bn_bwd2_nhwc_bf16) instead of autograd
+        running an elementwise add over the whole tensor first."""
         x = _cl(x)
         N, C, H, W = x.shape
         R = N * H * W
@@ -49,21 +53,29 @@ class FusedBNAct(torch.autograd.Function):
         ctx.save_for_backward(x, mask, mean, invstd, gamma)
         ctx.meta = (R, C, residual is not None, training)
         ctx.sums = sums
+        if fork:
+            ctx.set_materialize_grads(False)   # an unused twin yields None, not a zero tensor
+            return y, y.view_as(y)
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dy2=None):
         x, mask, mean, invstd, gamma = ctx.saved_tensors
         R, C, has_res, training = ctx.meta
         if not training:
             raise RuntimeError("FusedBNAct backward implements train-mode BatchNorm only")
+        if dy is None:
+            dy, dy2 = dy2, None
+        if dy is None:
+            return (None,) * 11
         dy = _cl(dy)
+        dy2 = _cl(dy2) if dy2 is not None else None
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if has_res else None
         dgamma = torch.empty(C, device=x.device, dtype=torch.float32)
         dbeta = torch.empty(C, device=x.device, dtype=torch.float32)
-        ops.bn_bwd(dy, mask, x, mean, invstd, gamma, ctx.sums, dx, dres, dgamma, dbeta, R, C)
-        return dx, dgamma, dbeta, None, None, dres, None, None, None, None
+        ops.bn_bwd(dy, mask, x, mean, invstd, gamma, ctx.sums, dx, dres, dgamma, dbeta, R, C, dy2=dy2)
+        return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None
 
 
 class MaxPool3x3s2(torch.autograd.Function):
@@ -141,12 +153,12 @@ class StemBNReLUPool(torch.autograd.Function):
         return dx, dgamma, dbeta, None, None, None, None, None, None
 
 
-def _bn(bn, x, residual=None, relu=True):
+def _bn(bn, x, residual=None, relu=True, fork=False):
     if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
     momentum = 0.1 if bn.momentum is None else bn.momentum
     return FusedBNAct.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual, relu, bn.training,
-                            float(momentum), float(bn.eps))
+                            float(momentum), float(bn.eps), fork)
 
 
 def _conv(conv, x):
@@ -259,6 +271,7 @@ def supported(encoder) -> bool:
     return ok and mp.kernel_size == 3 and mp.stride == 2 and mp.padding == 1 and isinstance(encoder.bn1, torch.nn.BatchNorm2d)
 
 
+_BN_FORK = os.environ.get("SD_B200_BN_FORK", "1") == "1"   # twin block outputs: gradients summed inside the BN backward kernels
 # how many cuDNN algorithms the autotuner times per convolution shape (torch default 10; 0 = all)
 _CUDNN_BENCHMARK_LIMIT = int(os.environ.get("SD_B200_CUDNN_BENCHMARK_LIMIT", "10"))
 
@@ -283,16 +296,22 @@ def resnet_trunk_bf16(encoder, images: torch.Tensor) -> torch.Tensor:
             bn1.num_batches_tracked.add_(1)
         x = StemBNReLUPool.apply(x, bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var, bn1.training,
                                  float(0.1 if bn1.momentum is None else bn1.momentum), float(bn1.eps), presums)
-        for layer in (encoder.layer1, encoder.layer2, encoder.layer3, encoder.layer4):
-            for blk in layer:
-                identity = x
-                if blk.downsample is not None:
-                    identity = _bn(blk.downsample[1], _conv(blk.downsample[0], x), None, False)
-                if isinstance(blk, BasicBlock):
-                    out = _bn(blk.bn1, _conv(blk.conv1, x), None, True)
-                    x = _bn(blk.bn2, _conv(blk.conv2, out), identity, True)
-                else:
-                    out = _bn(blk.bn1, _conv(blk.conv1, x), None, True)
-                    out = _bn(blk.bn2, _conv(blk.conv2, out), None, True)
-                    x = _bn(blk.bn3, _conv(blk.conv3, out), identity, True)
+        blocks = [blk for layer in (encoder.layer1, encoder.layer2, encoder.layer3, encoder.layer4) for blk in layer]
+        # a block's output feeds the next block's first convolution (x_main) AND its identity path (x_skip): with
+        # ``fork`` the two consumers get twin outputs, so their gradients reach the BatchNorm backward separately and
+        # are summed inside its kernels (no elementwise-add pass over the activation gradient)
+        x_main = x_skip = x
+        for i, blk in enumerate(blocks):
+            fork = _BN_FORK and torch.is_grad_enabled() and i + 1 < len(blocks)
+            identity = x_skip
+            if blk.downsample is not None:
+                identity = _bn(blk.downsample[1], _conv(blk.downsample[0], x_skip), None, False)
+            out = _bn(blk.bn1, _conv(blk.conv1, x_main), None, True)
+            if isinstance(blk, BasicBlock):
+                res = _bn(blk.bn2, _conv(blk.conv2, out), identity, True, fork and blk.bn2.training)
+            else:
+                out = _bn(blk.bn2, _conv(blk.conv2, out), None, True)
+                res = _bn(blk.bn3, _conv(blk.conv3, out), identity, True, fork and blk.bn3.training)
+            x_main, x_skip = res if isinstance(res, tuple) else (res, res)
+        x = x_main
     return x

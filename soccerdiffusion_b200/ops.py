@@ -300,14 +300,16 @@ def bn_apply(x, residual, mean, invstd, gamma, beta, relu, y, mask, R, C):
     _count()
 
 
-def bn_bwd(dy, y_relu, x, mean, invstd, gamma, sums, dx, dres, dgamma, dbeta, R, C, beta_recompute=None):
-    nb = 2.0 * R * C * (2 * 2 + 1 + (1 if dres is not None else 0)) + (2.0 * R * C / 8 if y_relu is not None else 0)
+def bn_bwd(dy, y_relu, x, mean, invstd, gamma, sums, dx, dres, dgamma, dbeta, R, C, beta_recompute=None, dy2=None):
+    """``dy2``: optional second incoming gradient (the output had two consumers); summed with ``dy`` inside the kernels."""
+    nb = 2.0 * R * C * (2 * (2 + (1 if dy2 is not None else 0)) + 1 + (1 if dres is not None else 0)) \
+        + (2.0 * R * C / 8 if y_relu is not None else 0)
     with _Timed("bn_bwd", 0.0, nb, f"[R{R} C{C}]"):
-        check(_lib.lib().sd_bn_bwd_nhwc_bf16(dy.data_ptr(), _lib.ptr(y_relu), x.data_ptr(), mean.data_ptr(),
-                                             invstd.data_ptr(), gamma.data_ptr(), _lib.ptr(beta_recompute), sums.data_ptr(),
-                                             dx.data_ptr(), _lib.ptr(dres), dgamma.data_ptr(), dbeta.data_ptr(), R, C,
-                                             stream_ptr()),
-              "sd_bn_bwd_nhwc_bf16")
+        check(_lib.lib().sd_bn_bwd2_nhwc_bf16(dy.data_ptr(), _lib.ptr(dy2), _lib.ptr(y_relu), x.data_ptr(), mean.data_ptr(),
+                                              invstd.data_ptr(), gamma.data_ptr(), _lib.ptr(beta_recompute), sums.data_ptr(),
+                                              dx.data_ptr(), _lib.ptr(dres), dgamma.data_ptr(), dbeta.data_ptr(), R, C,
+                                              stream_ptr()),
+              "sd_bn_bwd2_nhwc_bf16")
     _count(3)
 
 

@@ -315,3 +315,39 @@ def test_stem_fprop_epilogue_statistics(N, H, W):
     var = sums[64:] / n - mean * mean
     assert ((mean - mean_ref).abs() < 1e-3 * var_ref.sqrt()).all()
     assert ((var / var_ref - 1).abs() < 2e-3).all()
+
+
+@pytest.mark.parametrize("res", [False, True])
+def test_fused_bn_fork_sums_two_gradients(res):
+    """FusedBNAct(fork=True) returns twin outputs; their two gradients are summed inside the backward kernels
+    (sd_bn_bwd2_nhwc_bf16) — same result as BatchNorm backward on the fp32 sum; an unused twin costs nothing."""
+    from soccerdiffusion_b200.ml.model.encoder.trunk import FusedBNAct
+
+    torch.manual_seed(21)
+    N, C, H, W = 3, 64, 20, 24
+    x = (_cl_bf16(N, C, H, W) * 1.7 + 0.3).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    r = _cl_bf16(N, C, H, W) if res else None
+    gamma = (torch.rand(C, device="cuda") + 0.5).requires_grad_(True)
+    beta = (torch.randn(C, device="cuda") * 0.1).requires_grad_(True)
+    ga, gb = _cl_bf16(N, C, H, W), _cl_bf16(N, C, H, W)
+    for use_b in (True, False):
+        gamma.grad = beta.grad = None
+        xg = x.clone().requires_grad_(True)
+        rg = r.clone().requires_grad_(True) if res else None
+        rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+        y1, y2 = FusedBNAct.apply(xg, gamma, beta, rm, rv, rg, True, True, 0.1, 1e-5, True)
+        assert y1.data_ptr() == y2.data_ptr()
+        if use_b:
+            torch.autograd.backward([y1, y2], [ga, gb])
+        else:
+            y2.backward(ga)                                   # only the second twin is consumed
+        xf = x.float().requires_grad_(True)
+        rf = r.float().requires_grad_(True) if res else None
+        g2, b2 = gamma.detach().clone().requires_grad_(True), beta.detach().clone().requires_grad_(True)
+        yf = F.batch_norm(xf, torch.zeros(C, device="cuda"), torch.ones(C, device="cuda"), g2, b2, True, 0.1, 1e-5)
+        yf = F.relu(yf + rf if res else yf)
+        yf.backward(ga.float() + gb.float() if use_b else ga.float())
+        assert rel(xg.grad.float(), xf.grad) < 1.5e-2
+        assert rel(gamma.grad, g2.grad) < 1.5e-2 and rel(beta.grad, b2.grad) < 1.5e-2
+        if res:
+            assert rel(rg.grad.float(), rf.grad) < 1e-2
