@@ -102,6 +102,7 @@ SIGNATURES = {
     "sd_stem_band_supported": [c_i, c_i, c_i],
     "sd_stem_bn_relu_pool_nhwc_bf16_fwd": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f],
     "sd_stem_bn_relu_pool_nhwc_bf16_bwd": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f],
+    "sd_stem_bn_relu_pool_nhwc_bf16_bwd2": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f],
     "sd_maxpool3x3s2_nhwc_bf16_fwd": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f],
     "sd_maxpool3x3s2_nhwc_bf16_bwd": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f],
     "sd_plan_create": [C.POINTER(PlanConfig), C.POINTER(C.c_void_p)],

@@ -112,8 +112,8 @@ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) 
 bool stem_band_supported(int H, int W, int C);
 int stem_band_fwd(const void* x, const float* mean, const float* invstd, const float* gamma, const float* beta, void* y,
                   void* idx, int N, int H, int W, cudaStream_t st);
-int stem_band_bwd(const void* dpool, const void* idx, const void* x, const float* mean, const float* invstd,
-                  const float* gamma, const float* beta, double* sums, void* dx, int N, int H, int W, int pass,
-                  cudaStream_t st);
+int stem_band_bwd(const void* dpool, const void* idx, const void* x, const void* y_pooled, const float* mean,
+                  const float* invstd, const float* gamma, const float* beta, double* sums, void* dx, int N, int H, int W,
+                  int pass, cudaStream_t st);
 
 }  // namespace sd

@@ -129,6 +129,82 @@ __device__ __forceinline__ void fma_if_pos(float& v, float act, float s, float g
     asm("{\n\t.reg .pred q;\n\tsetp.gt.f32 q, %1, 0f00000000;\n\t@q fma.rn.f32 %0, %2, %3, %0;\n\t}" : "+f"(v) : "f"(act), "f"(s), "f"(g));
 }
 
+// ---- backward reductions in the POOLED domain -----------------------------------------------------------------
+// sum_pixels g*mask and sum_pixels g*mask*xhat only involve the arg-max pixel of every pooling window:
+//   g[pixel] = sum of dp over the windows that selected it, mask[pixel] = (y_window > 0), and at the arg-max
+//   gamma*xhat + beta = y_window when positive, so   sum g*mask*xhat = sum_windows dp * (y > 0) * (y - beta) / gamma.
+// The per-channel reductions therefore need the pooled gradient and the pooled OUTPUT (both 1/4 of the map: 2 GB instead
+// of 5.6 GB at bs=256) and no tap routing at all.  y is bf16-rounded, i.e. xhat carries an unbiased relative error of
+// 2^-9 (|xhat| + |beta/gamma|) per element, which averages out over the millions of windows of a channel; when some
+// channel has |beta/gamma| > 16 or gamma ~ 0 the exact kernel (stem_bwd_block_kernel<0>) runs instead: both kernels
+// evaluate the same predicate on the parameters and exactly one of them accumulates.
+__device__ __forceinline__ bool pooled_sums_ok(const float* __restrict__ gamma, const float* __restrict__ beta) {
+    const int lane = threadIdx.x & 31;
+    bool ok = true;
+#pragma unroll
+    for (int c = lane; c < 64; c += 32) {
+        const float g = fabsf(gamma[c]), b = fabsf(beta[c]);
+        ok = ok && g > 1e-6f && b <= 16.f * g;
+    }
+    return __all_sync(0xffffffffu, ok);
+}
+
+__global__ void __launch_bounds__(kT, 3) stem_bwd_sums_pooled_kernel(const uint4* __restrict__ dp, const uint4* __restrict__ y,
+                                                                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                     double* __restrict__ sums, long long nvec) {
+    __shared__ float red[2 * kT * 9];
+    if (!pooled_sums_ok(gamma, beta)) return;
+    const int tid = threadIdx.x, cv = tid & 7;
+    float ig[8], be[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        ig[i] = 1.0f / gamma[cv * 8 + i];
+        be[i] = beta[cv * 8 + i];
+    }
+    float a0[8], a1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.f;
+    const long long per_cta = ((nvec + gridDim.x - 1) / gridDim.x + kT - 1) / kT * kT;   // multiple of 8: cv stays fixed
+    const long long v0 = blockIdx.x * per_cta, v1 = min(nvec, v0 + per_cta);
+    for (long long v = v0 + tid; v < v1; v += 4 * kT) {
+        uint4 ud[4], uy[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long w = v + (long long)u * kT;
+            if (w < v1) {
+                ud[u] = ld_stream(dp + w);
+                uy[u] = ld_stream(y + w);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (v + (long long)u * kT >= v1) break;
+            float g[8], fy[8];
+            unpack8(ud[u], g);
+            unpack8(uy[u], fy);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float gm = fy[i] > 0.f ? g[i] : 0.f;
+                a0[i] += gm;
+                a1[i] = fmaf(gm, (fy[i] - be[i]) * ig[i], a1[i]);   // xhat at the arg-max
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        red[tid * 9 + i] = a0[i];
+        red[(kT + tid) * 9 + i] = a1[i];
+    }
+    __syncthreads();
+    if (tid < 128) {
+        const int which = tid >> 6, c = tid & 63;
+        float s = 0.f;
+        for (int r = c >> 3; r < kT; r += 8) s += red[(which * kT + r) * 9 + (c & 7)];
+        atomicAdd(&sums[which * 64 + c], (double)s);
+    }
+}
+
 // ---- backward --------------------------------------------------------------------------------------------------
 // Thread = (2x2 block of input pixels, 8-channel vector).  The block is reached by exactly four pooling windows
 // (ho in {j, j+1}, wo in {a, a+1} for block rows 2j,2j+1 and columns 2a,2a+1) and by nine (window, tap) pairs in
@@ -140,8 +216,10 @@ __global__ void __launch_bounds__(kT, 2) stem_bwd_block_kernel(const uint4* __re
                                                                const uint4* __restrict__ x, const float* __restrict__ mean,
                                                                const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, double* __restrict__ sums,
-                                                               uint4* __restrict__ dx, int N, int H, int W, int HO, int WO) {
+                                                               uint4* __restrict__ dx, int N, int H, int W, int HO, int WO,
+                                                               int pooled_sums_launched) {
     __shared__ float red[PASS == 0 ? 2 * kT * 9 : 1];
+    if (PASS == 0 && pooled_sums_launched && pooled_sums_ok(gamma, beta)) return;   // stem_bwd_sums_pooled_kernel did it
     const int tid = threadIdx.x, cv = tid & 7;
     const double invR = 1.0 / (double)((long long)N * H * W);
     float sc[8], sh[8], kx[8], kc[8];
@@ -283,9 +361,9 @@ int stem_band_fwd(const void* x, const float* mean, const float* invstd, const f
     return SD_OK;
 }
 
-int stem_band_bwd(const void* dpool, const void* idx, const void* x, const float* mean, const float* invstd,
-                  const float* gamma, const float* beta, double* sums, void* dx, int N, int H, int W, int pass,
-                  cudaStream_t st) {
+int stem_band_bwd(const void* dpool, const void* idx, const void* x, const void* y_pooled, const float* mean,
+                  const float* invstd, const float* gamma, const float* beta, double* sums, void* dx, int N, int H, int W,
+                  int pass, cudaStream_t st) {
     const int HO = (H + 2 - 3) / 2 + 1, WO = (W + 2 - 3) / 2 + 1;
     static int grid0 = 0, grid1 = 0;
     if (!grid0) {
@@ -300,12 +378,29 @@ int stem_band_bwd(const void* dpool, const void* idx, const void* x, const float
     const long long items = (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * 8;
     if (items >= (1ll << 31)) return SD_ERR_UNSUPPORTED;
     const long long ctas = (items + kT - 1) / kT;
-    if (pass == 0)
+    if (pass == 0) {
+        if (y_pooled) {   // reductions from the pooled tensors; the exact kernel below returns at once unless the parameters
+                          // fail pooled_sums_ok
+            static int gridp = 0;
+            if (!gridp) {
+                int occ = 0, sms = 148, dev = 0;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stem_bwd_sums_pooled_kernel, kT, 0) != cudaSuccess || occ < 1) occ = 2;
+                gridp = sms * occ;
+            }
+            const long long nvec = (long long)N * HO * WO * 8;
+            stem_bwd_sums_pooled_kernel<<<(int)min((long long)gridp, (nvec + kT - 1) / kT), kT, 0, st>>>(
+                (const uint4*)dpool, (const uint4*)y_pooled, mean, invstd, gamma, beta, sums, nvec);
+            SD_LAUNCH_CHECK();
+        }
         stem_bwd_block_kernel<0><<<(int)min((long long)grid0, ctas), kT, 0, st>>>(
-            (const uint4*)dpool, (const uint2*)idx, (const uint4*)x, mean, invstd, gamma, beta, sums, nullptr, N, H, W, HO, WO);
-    else
+            (const uint4*)dpool, (const uint2*)idx, (const uint4*)x, mean, invstd, gamma, beta, sums, nullptr, N, H, W, HO, WO,
+            y_pooled ? 1 : 0);
+    } else {
         stem_bwd_block_kernel<1><<<(int)min((long long)grid1, ctas), kT, 0, st>>>(
-            (const uint4*)dpool, (const uint2*)idx, (const uint4*)x, mean, invstd, gamma, beta, sums, (uint4*)dx, N, H, W, HO, WO);
+            (const uint4*)dpool, (const uint2*)idx, (const uint4*)x, mean, invstd, gamma, beta, sums, (uint4*)dx, N, H, W, HO, WO, 0);
+    }
     SD_LAUNCH_CHECK();
     return SD_OK;
 }

@@ -705,7 +705,8 @@ extern "C" int sd_stem_bn_relu_pool_nhwc_bf16_fwd(const void* x, const float* me
     return SD_OK;
 }
 
-extern "C" int sd_stem_bn_relu_pool_nhwc_bf16_bwd(const void* dpool, const void* idx, const void* x, const float* mean,
+extern "C" int sd_stem_bn_relu_pool_nhwc_bf16_bwd2(const void* dpool, const void* idx, const void* x, const void* y_pooled,
+                                                   const float* mean,
                                                   const float* invstd, const float* gamma, const float* beta, double* sums,
                                                   void* dx, float* dgamma, float* dbeta, int N, int H, int W, int C,
                                                   void* stream) {
@@ -716,11 +717,11 @@ extern "C" int sd_stem_bn_relu_pool_nhwc_bf16_bwd(const void* dpool, const void*
     const int HO = (H + 2 - 3) / 2 + 1, WO = (W + 2 - 3) / 2 + 1;
     SD_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
     if (stem_band_supported(H, W, C)) {   // scatter-in-shared-memory row bands (stem_band.cu)
-        int rc = stem_band_bwd(dpool, idx, x, mean, invstd, gamma, beta, sums, nullptr, N, H, W, 0, st);
+        int rc = stem_band_bwd(dpool, idx, x, y_pooled, mean, invstd, gamma, beta, sums, nullptr, N, H, W, 0, st);
         if (rc != SD_OK) return rc;
         bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, C, dgamma, dbeta);
         SD_LAUNCH_CHECK();
-        return stem_band_bwd(dpool, idx, x, mean, invstd, gamma, beta, sums, dx, N, H, W, 1, st);
+        return stem_band_bwd(dpool, idx, x, y_pooled, mean, invstd, gamma, beta, sums, dx, N, H, W, 1, st);
     }
     const long long nvec = (long long)N * H * W * (C / 8);
     const int grid = (int)min((long long)148 * 8, (nvec + kT - 1) / kT);
@@ -733,6 +734,14 @@ extern "C" int sd_stem_bn_relu_pool_nhwc_bf16_bwd(const void* dpool, const void*
                                             sums, (uint4*)dx, N, H, W, C / 8, HO, WO, C);
     SD_LAUNCH_CHECK();
     return SD_OK;
+}
+
+extern "C" int sd_stem_bn_relu_pool_nhwc_bf16_bwd(const void* dpool, const void* idx, const void* x, const float* mean,
+                                                  const float* invstd, const float* gamma, const float* beta, double* sums,
+                                                  void* dx, float* dgamma, float* dbeta, int N, int H, int W, int C,
+                                                  void* stream) {
+    return sd_stem_bn_relu_pool_nhwc_bf16_bwd2(dpool, idx, x, nullptr, mean, invstd, gamma, beta, sums, dx, dgamma, dbeta, N, H, W,
+                                               C, stream);
 }
 
 extern "C" int sd_stem_pack_s2d_bf16(const float* images, void* out, int N, int H, int W, void* stream) {

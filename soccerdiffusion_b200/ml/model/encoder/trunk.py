@@ -126,14 +126,14 @@ class StemBNReLUPool(torch.autograd.Function):
         y = torch.empty((N, C, HO, WO), device=dev, dtype=x.dtype, memory_format=torch.channels_last)
         idx = torch.empty((N, HO, WO, C), device=dev, dtype=torch.uint8)
         ops.stem_fwd(x, mean, invstd, gamma, beta, y, idx, N, H, W, C)
-        ctx.save_for_backward(x, idx, mean, invstd, gamma, beta)
+        ctx.save_for_backward(x, idx, mean, invstd, gamma, beta, y)   # y: the backward's reductions run in the pooled domain
         ctx.sums = sums
         ctx.training = training
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, idx, mean, invstd, gamma, beta = ctx.saved_tensors
+        x, idx, mean, invstd, gamma, beta, y_pooled = ctx.saved_tensors
         if not ctx.training:
             raise RuntimeError("StemBNReLUPool backward implements train-mode BatchNorm only")
         N, C, H, W = x.shape
@@ -144,7 +144,7 @@ class StemBNReLUPool(torch.autograd.Function):
         if ops.stem_band_supported(H, W, C):
             # row-band kernels: the pooled gradient is scattered into shared memory, the ReLU mask recomputed from x;
             # pass 0 = per-channel reductions, pass 1 = dx.  The activated map's gradient is never materialised.
-            ops.stem_bwd(dy, idx, x, mean, invstd, gamma, beta, ctx.sums, dx, dgamma, dbeta, N, H, W, C)
+            ops.stem_bwd(dy, idx, x, mean, invstd, gamma, beta, ctx.sums, dx, dgamma, dbeta, N, H, W, C, y_pooled=y_pooled)
         else:
             # generic shapes: gradient w.r.t. the activated map, then BatchNorm backward with the recomputed ReLU mask
             dact = torch.empty_like(x)

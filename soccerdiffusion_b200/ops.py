@@ -339,16 +339,19 @@ def stem_band_supported(H, W, C) -> bool:
     return _lib.lib().sd_stem_band_supported(H, W, C) == 1
 
 
-def stem_bwd(dpool, idx, x, mean, invstd, gamma, beta, sums, dx, dgamma, dbeta, N, H, W, C):
-    # two passes, each reads x once (2 B/elem) and the pooled gradient + taps (3 B per pooled elem); the second writes dx
-    nb = 2.0 * N * H * W * C * 3 + 2 * (3.0 * N * H * W * C / 4)
-    with _Timed("stem_bn_relu_pool_bwd", 0.0, nb, f"[N{N} H{H} C{C}]"):
-        check(_lib.lib().sd_stem_bn_relu_pool_nhwc_bf16_bwd(dpool.data_ptr(), idx.data_ptr(), x.data_ptr(), mean.data_ptr(),
-                                                            invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                                                            sums.data_ptr(), dx.data_ptr(), dgamma.data_ptr(),
-                                                            dbeta.data_ptr(), N, H, W, C, stream_ptr()),
-              "sd_stem_bn_relu_pool_nhwc_bf16_bwd")
-    _count(3)
+def stem_bwd(dpool, idx, x, mean, invstd, gamma, beta, sums, dx, dgamma, dbeta, N, H, W, C, y_pooled=None):
+    """``y_pooled``: the forward's pooled output; with it the per-channel reductions run in the pooled domain (2 B + 2 B per
+    pooled element) instead of a pass over x."""
+    # dx pass: x (2 B/elem) + pooled gradient and taps (3 B per pooled elem) + dx; reductions: pooled pair or the same reads
+    dx_pass = 2.0 * N * H * W * C * 2 + 3.0 * N * H * W * C / 4
+    red_pass = 4.0 * N * H * W * C / 4 if y_pooled is not None else 2.0 * N * H * W * C + 3.0 * N * H * W * C / 4
+    with _Timed("stem_bn_relu_pool_bwd", 0.0, dx_pass + red_pass, f"[N{N} H{H} C{C}]"):
+        check(_lib.lib().sd_stem_bn_relu_pool_nhwc_bf16_bwd2(dpool.data_ptr(), idx.data_ptr(), x.data_ptr(), _lib.ptr(y_pooled),
+                                                             mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+                                                             beta.data_ptr(), sums.data_ptr(), dx.data_ptr(), dgamma.data_ptr(),
+                                                             dbeta.data_ptr(), N, H, W, C, stream_ptr()),
+              "sd_stem_bn_relu_pool_nhwc_bf16_bwd2")
+    _count(4 if y_pooled is not None else 3)
 
 
 def stem_pack(images, out, N, H, W):

@@ -235,7 +235,8 @@ def _bf(x):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 128), (1, 128, 128), (37, 20, 20), (130, 384, 128), (1000, 128, 20),
-                                   (257, 144, 65), (300, 256, 256), (513, 32, 1568), (25600, 384, 128)])
+                                   (257, 144, 65), (300, 256, 256), (513, 32, 1568), (25600, 384, 128),
+                                   (37, 22, 22), (203, 22, 128)])   # J = 22 joints: scalar epilogue path
 def test_tc_gemm_forward_epilogues(ops, M, N, K):
     torch.manual_seed(M + N + K)
     A, W, bias = torch.randn(M, K), torch.randn(N, K) / math.sqrt(K), torch.randn(N)
@@ -262,7 +263,7 @@ def test_tc_gemm_forward_epilogues(ops, M, N, K):
     assert rel(C, exact + pe.double()[torch.arange(M) % 7]) < 5e-6
 
 
-@pytest.mark.parametrize("M,N,K", [(37, 20, 128), (1000, 128, 384), (25600, 128, 128), (3120, 256, 128)])
+@pytest.mark.parametrize("M,N,K", [(37, 20, 128), (1000, 128, 384), (25600, 128, 128), (3120, 256, 128), (203, 128, 22)])
 def test_tc_gemm_dgrad_wgrad(ops, M, N, K):
     torch.manual_seed(1)
     dY, W, X = torch.randn(M, N), torch.randn(N, K), torch.randn(M, K)

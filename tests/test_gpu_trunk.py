@@ -137,7 +137,7 @@ def test_stem_band_backward_matches_two_kernel_path(N, H, W):
     xg = x.clone().requires_grad_(True)
     y = StemBNReLUPool.apply(xg, gamma, beta, rm, rv, True, 0.1, 1e-5)
     go = _cl_bf16(*y.shape)
-    xs, idx, mean, invstd, g_, b_ = y.grad_fn.saved_tensors   # read before backward() frees them
+    xs, idx, mean, invstd, g_, b_, _y = y.grad_fn.saved_tensors   # read before backward() frees them
     y.backward(go)                                            # band kernels
     # generic two-kernel path from the same saved tensors
     sums = torch.empty(2 * C, device="cuda", dtype=torch.float64)
@@ -351,3 +351,44 @@ def test_fused_bn_fork_sums_two_gradients(res):
         assert rel(gamma.grad, g2.grad) < 1.5e-2 and rel(beta.grad, b2.grad) < 1.5e-2
         if res:
             assert rel(rg.grad.float(), rf.grad) < 1e-2
+
+
+@pytest.mark.parametrize("case", ["typical", "fallback_large_beta_over_gamma", "fallback_zero_gamma"])
+def test_stem_backward_pooled_domain_reductions(case):
+    """sd_stem_bn_relu_pool_nhwc_bf16_bwd2 with the pooled output: the per-channel reductions taken over pooling windows
+    (sum dp*(y>0), sum dp*(y>0)*(y-beta)/gamma) equal the pixel-domain ones; parameters outside the safe range (|beta/gamma|
+    > 16, gamma ~ 0) take the exact kernel on the device."""
+    from soccerdiffusion_b200 import ops
+
+    torch.manual_seed(9)
+    N, C, H, W = 4, 64, 64, 96
+    x = (_cl_bf16(N, C, H, W) * 1.2 + 0.1).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    gamma = torch.rand(C, device="cuda") + 0.5
+    beta = torch.randn(C, device="cuda") * 0.3
+    if case == "fallback_large_beta_over_gamma":
+        gamma[5], beta[5] = 0.01, 0.9
+    elif case == "fallback_zero_gamma":
+        gamma[7] = 0.0
+    mean, invstd = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    sums = torch.empty(2 * C, device="cuda", dtype=torch.float64)
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    ops.bn_stats(x, N * H * W, C, sums, 1e-5, 0.1, mean, invstd, rm, rv)
+    HO, WO = H // 2, W // 2
+    y = torch.empty((N, C, HO, WO), device="cuda", dtype=torch.bfloat16, memory_format=torch.channels_last)
+    idx = torch.empty((N, HO, WO, C), device="cuda", dtype=torch.uint8)
+    ops.stem_fwd(x, mean, invstd, gamma, beta, y, idx, N, H, W, C)
+    dp = _cl_bf16(N, C, HO, WO)
+    out = {}
+    for use_y in (False, True):
+        dx = torch.empty_like(x)
+        dg, db = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+        ops.stem_bwd(dp, idx, x, mean, invstd, gamma, beta, sums, dx, dg, db, N, H, W, C, y_pooled=y if use_y else None)
+        out[use_y] = (dx.float(), dg.clone(), db.clone())
+    if case == "typical":
+        assert rel(out[True][2], out[False][2]) < 1e-5                      # sum g: same terms, other order
+        # sum g*xhat: xhat is recovered from the bf16-rounded y (relative error <= 2^-9 per term, like dp's own rounding);
+        # with random dp the sum is itself only sqrt(n)-sized, so the relative difference sits at the bf16 level
+        assert rel(out[True][1], out[False][1]) < 5e-3
+        assert rel(out[True][0], out[False][0]) < 5e-3
+    else:                                                                   # exact kernel ran in both calls
+        assert rel(out[True][1], out[False][1]) < 1e-5 and rel(out[True][0], out[False][0]) < 1e-5

@@ -45,7 +45,9 @@ print(f"bn_stats       {t:7.3f} ms  {2 * elems / t / 1e6:7.0f} GB/s")
 t = timed(lambda: ops.stem_fwd(x, mean, invstd, gamma, beta, y, idx, N, H, W, C))
 print(f"stem_fwd       {t:7.3f} ms  {(2 * elems + 3 * pooled) / t / 1e6:7.0f} GB/s")
 t = timed(lambda: ops.stem_bwd(dp, idx, x, mean, invstd, gamma, beta, sums, dx, dg, db, N, H, W, C))
-print(f"stem_bwd (2p)  {t:7.3f} ms  {(6 * elems + 6 * pooled) / t / 1e6:7.0f} GB/s")
+print(f"stem_bwd (2p)  {t:7.3f} ms  {(6 * elems + 6 * pooled) / t / 1e6:7.0f} GB/s   (reductions over pixels)")
+t = timed(lambda: ops.stem_bwd(dp, idx, x, mean, invstd, gamma, beta, sums, dx, dg, db, N, H, W, C, y_pooled=y))
+print(f"stem_bwd pooled{t:7.3f} ms  {(4 * elems + 7 * pooled) / t / 1e6:7.0f} GB/s   (reductions over pooling windows)")
 
 # conv1 itself (space-to-depth packed image): pack, tcgen05 forward, tcgen05 weight gradient
 img = torch.randn(N, 3, 224, 224, device=dev)
