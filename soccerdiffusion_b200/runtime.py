@@ -87,13 +87,16 @@ def concurrent_encoders() -> bool:
 
 
 _side_streams: dict = {}
+_SIDE_STREAM_PRIORITY = int(os.environ.get("SD_B200_SIDE_STREAM_PRIORITY", "0"))
 
 
 def side_streams(device, n: int):
     """Process-wide pool of side CUDA streams per device (created lazily, reused by every model instance)."""
     lst = _side_streams.setdefault((device.type, device.index), [])
     while len(lst) < n:
-        lst.append(torch.cuda.Stream(device=device))
+        # (a higher stream priority for these many-small-kernel streams was A/B-tested next to the trunk's GPU-filling
+        # kernels: no measurable difference, so the default priority is kept)
+        lst.append(torch.cuda.Stream(device=device, priority=_SIDE_STREAM_PRIORITY))
     return lst[:n]
 
 
