@@ -91,7 +91,7 @@ def traffic(path, out_json, note):
                "bn_stats": ("bn_reduce_kernel<0>", "bn_finalize_kernel"),
                "bn_apply": ("bn_apply_kernel",),
                "stem_bn_relu_pool_fwd": ("stem_fwd_band_kernel",),
-               "stem_bn_relu_pool_bwd": ("stem_bwd_block_kernel",),
+               "stem_bn_relu_pool_bwd": ("stem_bwd_block_kernel", "stem_bwd_sums_pooled_kernel"),
                "stem_fprop_s2d": ("stem_fprop_tma_kernel",),
                "stem_wgrad_s2d": ("stem_wgrad_tma_kernel",),
                "stem_pack_s2d": ("stem_pack_kernel",)}
