@@ -73,18 +73,23 @@ __global__ void __launch_bounds__(kT, 3) stem_fwd_band_kernel(const uint4* __res
         sc[i] = invstd[c] * gamma[c];
         sh[i] = beta[c] - mean[c] * sc[i];
     }
+    uint32_t sgn[4];   // sign-bit flips that make a = x*sc + sh increasing in the flipped x, per packed channel pair
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sgn[k] = (sc[2 * k] < 0.f ? 0x00008000u : 0u) | (sc[2 * k + 1] < 0.f ? 0x80000000u : 0u);
     mbar_wait(&bar, 0);
     const int per_row = WO * 8;
     for (int i = tid; i < npr * per_row; i += kT) {
         const int pr = i >= per_row ? 1 : 0;
         const int wo = (i - pr * per_row) >> 3;
         const int ho = ho0 + pr;
-        // arg-max over the window of a = x*sc + sh (ReLU is monotone: it is applied to the winner; when every tap is
-        // <= 0 the winner's gradient is masked by the recomputed ReLU mask in the backward pass anyway)
-        float best[8];
-        unsigned bi[8];
+        // arg-max over the window of a = x*sc + sh.  a is monotone in x (increasing for sc >= 0, decreasing otherwise), so
+        // the 9-tap max / arg-max runs on the RAW bf16 pairs with the sign bit flipped where sc < 0 — packed compare
+        // (__hgt2_mask) + two bit-selects per tap and channel PAIR instead of unpack, fma, compare and two selects per
+        // channel; the affine map and the ReLU are applied once to the winner.  (When every tap is <= 0 the winner's
+        // gradient is masked by the recomputed ReLU mask in the backward pass anyway.)
+        uint32_t bestp[4], bip[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { best[k] = -INFINITY; bi[k] = 0; }
+        for (int k = 0; k < 4; ++k) { bestp[k] = 0xFF80FF80u; bip[k] = 0u; }   // (-inf, -inf)
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
             const int h = 2 * ho - 1 + dy;
@@ -94,17 +99,29 @@ __global__ void __launch_bounds__(kT, 3) stem_fwd_band_kernel(const uint4* __res
             for (int dxx = 0; dxx < 3; ++dxx) {
                 const int w = 2 * wo - 1 + dxx;
                 if (w < 0 || w >= W) continue;
-                float f[8];
-                unpack8(*reinterpret_cast<const uint4*>(rowp + w * 128), f);
+                const uint4 u = *reinterpret_cast<const uint4*>(rowp + w * 128);
+                const uint32_t xw[4] = {u.x, u.y, u.z, u.w};
+                const uint32_t tap2 = (uint32_t)(dy * 3 + dxx) * 0x00010001u;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float a = fmaf(f[k], sc[k], sh[k]);
-                    if (a > best[k]) { best[k] = a; bi[k] = (unsigned)(dy * 3 + dxx); }
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t xs = xw[k] ^ sgn[k];
+                    const uint32_t m = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&xs),
+                                                   *reinterpret_cast<const __nv_bfloat162*>(&bestp[k]));
+                    bestp[k] = (xs & m) | (bestp[k] & ~m);
+                    bip[k] = (tap2 & m) | (bip[k] & ~m);
                 }
             }
         }
+        float best[8];
+        unsigned bi[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) best[k] = fmaxf(best[k], 0.f);
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t xr = bestp[k] ^ sgn[k];
+            best[2 * k] = fmaxf(fmaf(__uint_as_float(xr << 16), sc[2 * k], sh[2 * k]), 0.f);
+            best[2 * k + 1] = fmaxf(fmaf(__uint_as_float(xr & 0xFFFF0000u), sc[2 * k + 1], sh[2 * k + 1]), 0.f);
+            bi[2 * k] = bip[k] & 0xFFu;
+            bi[2 * k + 1] = (bip[k] >> 16) & 0xFFu;
+        }
         const long long o = (((long long)n * HO + ho) * WO + wo) * 8 + cv;
         y[o] = pack8(best);
         uint2 pk;
