@@ -162,3 +162,21 @@ def test_data_parallel_gradient_exchange_world2_gloo():
     loss = 0.5 * (ref(xs[:3]).pow(2).mean() + ref(xs[3:]).pow(2).mean())
     loss.backward()
     assert np.allclose(g0, ref.weight.grad.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_uint8_frame_preprocessing_equals_torchvision_pipeline():
+    """normalize_u8 (the generic device-side path for raw uint8 frames; pure torch ops, so it runs on
+    the CPU too) reproduces the reference's host preprocessing — v2.ToDtype(float32, scale=True) followed by
+    v2.Normalize(ImageNet mean/std) (dataset/pytorch.py:198-204, ml/inference/ros.py:190-196) — bit for bit, and passes
+    float frames through unchanged."""
+    import torch
+    from torchvision.transforms import v2
+
+    from soccerdiffusion_b200.ml.model.encoder.trunk import normalize_u8
+
+    g = torch.Generator().manual_seed(0)
+    u8 = torch.randint(0, 256, (2, 3, 3, 32, 48), generator=g, dtype=torch.uint8)
+    pre = v2.Compose([v2.ToDtype(torch.float32, scale=True), v2.Normalize((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))])
+    ref = torch.stack([pre(img) for img in u8.flatten(0, 1)]).view(2, 3, 3, 32, 48)
+    assert torch.equal(normalize_u8(u8.flatten(0, 1)).view_as(ref), ref)
+    assert normalize_u8(ref) is ref
