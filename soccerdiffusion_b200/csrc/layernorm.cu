@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) ln_stats_kernel(const float* __restrict__
 // dx = dres + rstd * (g*gamma - mean_c(g*gamma) - xhat * mean_c(g*gamma*xhat));
 // dgamma += sum_m g*xhat ; dbeta += sum_m g
 template <int NV>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ g, long long ldg,
+__global__ void __launch_bounds__(256, NV <= 4 ? 2 : 1) ln_bwd_kernel(const float* __restrict__ g, long long ldg,
                                                      const float* __restrict__ x, long long ldx,
                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                                      const float* __restrict__ gamma, const float* __restrict__ dres,
@@ -62,29 +62,48 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ g
         ag[i] = 0.f;
         ab[i] = 0.f;
     }
-    for (long long r = warp; r < M; r += nwarps) {
-        const float mu = mean[r], rs = rstd[r];
-        float gv[NV], xh[NV];
-        float s1 = 0.f, s2 = 0.f;
+    // RB rows per warp iteration: every global load of the batch (g, x, the residual-path gradient, mean, rstd) is issued
+    // before the first warp reduction, so a batch costs one DRAM round trip instead of two per row
+    constexpr int RB = NV <= 4 ? 4 : 2;
+    for (long long r0 = warp * RB; r0 < M; r0 += nwarps * RB) {
+        float gv[RB][NV], xv[RB][NV], dr[RB][NV], mu[RB], rs[RB];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int c = lane + 32 * i;
-            gv[i] = g[r * ldg + c];
-            xh[i] = (x[r * ldx + c] - mu) * rs;
-            const float gg = gv[i] * gam[i];
-            s1 += gg;
-            s2 = fmaf(gg, xh[i], s2);
-            ag[i] = fmaf(gv[i], xh[i], ag[i]);
-            ab[i] += gv[i];
+        for (int b = 0; b < RB; ++b) {
+            const long long r = r0 + b;
+            if (r < M) {
+                mu[b] = mean[r];
+                rs[b] = rstd[r];
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    const int c = lane + 32 * i;
+                    gv[b][i] = g[r * ldg + c];
+                    xv[b][i] = x[r * ldx + c];
+                    dr[b][i] = dres ? dres[r * ldres + c] : 0.f;
+                }
+            }
         }
-        s1 = warp_sum(s1) * (1.0f / D);
-        s2 = warp_sum(s2) * (1.0f / D);
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int c = lane + 32 * i;
-            float v = rs * (gv[i] * gam[i] - s1 - xh[i] * s2);
-            if (dres) v += dres[r * ldres + c];
-            dx[r * lddx + c] = v;
+        for (int b = 0; b < RB; ++b) {
+            const long long r = r0 + b;
+            if (r >= M) break;
+            float xh[NV];
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                xh[i] = (xv[b][i] - mu[b]) * rs[b];
+                const float gg = gv[b][i] * gam[i];
+                s1 += gg;
+                s2 = fmaf(gg, xh[i], s2);
+                ag[i] = fmaf(gv[b][i], xh[i], ag[i]);
+                ab[i] += gv[b][i];
+            }
+            s1 = warp_sum(s1) * (1.0f / D);
+            s2 = warp_sum(s2) * (1.0f / D);
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int c = lane + 32 * i;
+                dx[r * lddx + c] = rs[b] * (gv[b][i] * gam[i] - s1 - xh[i] * s2) + dr[b][i];
+            }
         }
     }
 #pragma unroll
@@ -133,7 +152,8 @@ extern "C" int sd_ln_bwd(const float* g, long long ldg, const float* x, long lon
                          long long lddx, float* dgamma, float* dbeta, long long M, int d, void* stream) {
     if (M <= 0) return SD_OK;
     if (!g || !x || !mean || !rstd || !gamma || !dx || !dgamma || !dbeta) return SD_ERR_BAD_ARG;
-    const int blocks = (int)min((long long)148 * 2, (M + 7) / 8);
+    // 2 resident CTAs per SM (the row batches live in registers); rows are handed out in batches of 4 (2 for d > 128)
+    const int blocks = (int)min((long long)148 * 2, (M + 31) / 32);
     cudaStream_t st = (cudaStream_t)stream;
     SD_DISPATCH_NV(d, (ln_bwd_kernel<NV><<<blocks, 256, 0, st>>>(g, ldg, x, ldx, mean, rstd, gamma, dres, ldres, dx,
                                                                  lddx, dgamma, dbeta, M)));
