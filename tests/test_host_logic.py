@@ -180,3 +180,26 @@ def test_uint8_frame_preprocessing_equals_torchvision_pipeline():
     ref = torch.stack([pre(img) for img in u8.flatten(0, 1)]).view(2, 3, 3, 32, 48)
     assert torch.equal(normalize_u8(u8.flatten(0, 1)).view_as(ref), ref)
     assert normalize_u8(ref) is ref
+
+
+def test_prefetcher_chunked_copy_is_a_plain_copy():
+    """DevicePrefetcher issues large host->device copies as several DMA transfers; whatever the chunking, the destination
+    ends up equal to the source (odd sizes, chunk larger than the tensor, non-contiguous source falls back to one copy)."""
+    import torch
+
+    from soccerdiffusion_b200.ml.training.data import _chunked_copy
+
+    g = torch.Generator().manual_seed(1)
+    for shape, chunk in (((7, 13, 5), 64), ((1000,), 4096), ((33, 3), 1 << 20), ((5, 4), 0)):
+        src = torch.randn(*shape, generator=g)
+        dst = torch.zeros_like(src)
+        _chunked_copy(dst, src, chunk)
+        assert torch.equal(dst, src)
+    src = torch.randn(6, 8, generator=g).t()          # non-contiguous
+    dst = torch.zeros(8, 6)
+    _chunked_copy(dst, src, 16)
+    assert torch.equal(dst, src)
+    u8 = torch.randint(0, 256, (3, 1001), generator=g, dtype=torch.uint8)
+    d8 = torch.zeros_like(u8)
+    _chunked_copy(d8, u8, 100)
+    assert torch.equal(d8, u8)
