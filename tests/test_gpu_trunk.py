@@ -233,6 +233,45 @@ def test_fused_trunk_matches_library_trunk_bf16():
         assert ea < max(2.0 * eb, 2e-2), (k, ea, eb)
 
 
+def test_fused_trunk_resnet50_bottleneck_blocks():
+    """ImageEncoderType.RESNET50 (Bottleneck blocks: three BatchNorms per block, forked block outputs) through the fused
+    trunk, train mode, against the fp32 trunk — judged like the ResNet18 test above."""
+    import soccerdiffusion_b200 as sdb
+    from soccerdiffusion_b200 import runtime
+    from soccerdiffusion_b200.ml.model.encoder.image import ImageEncoderType, ResNetImageEncoder
+
+    g = torch.Generator().manual_seed(17)
+    imgs = torch.randn(8, 3, 128, 128, generator=g).cuda()   # 128 samples per channel in layer4: train-mode BN stays well conditioned
+    outs = {}
+    try:
+        for name, prec, fused in (("fp32", "fp32", False), ("fused", "bf16", True), ("lib", "bf16", False)):
+            sdb.set_precision(prec)
+            runtime.set_fused_trunk(fused)
+            torch.manual_seed(5)
+            enc = ResNetImageEncoder(ImageEncoderType.RESNET50, 32, True, 128)
+            # a random-initialised 50-layer net in train mode amplifies bf16 rounding to O(1) errors (both bf16 paths
+            # alike); five Bottleneck blocks keep the comparison discriminating
+            r = enc.encoder
+            r.layer1, r.layer2, r.layer3, r.layer4 = r.layer1[:2], r.layer2[:1], r.layer3[:1], r.layer4[:1]
+            enc = enc.cuda().train()
+            feat = enc.trunk(imgs)
+            if name == "fp32":
+                tgt = torch.randn(feat.shape, generator=g).cuda()
+            (feat.float() * tgt).mean().backward()
+            e = enc.encoder
+            outs[name] = dict(feat=feat.float().detach(), g_c3=e.layer1[0].conv3.weight.grad.clone(),
+                              g_bn3=e.layer2[0].bn3.weight.grad.clone(), g_ds=e.layer3[0].downsample[0].weight.grad.clone(),
+                              g_conv1=e.conv1.weight.grad.clone(), rv=e.layer1[1].bn2.running_var.clone())
+    finally:
+        runtime.set_fused_trunk(True)
+        sdb.set_precision("fp32")
+    ref, a, b = outs["fp32"], outs["fused"], outs["lib"]
+    for k in ("feat", "rv", "g_c3", "g_bn3", "g_ds", "g_conv1"):
+        ea, eb = rel(a[k], ref[k]), rel(b[k], ref[k])
+        print(f"{k}: fused-vs-fp32 {ea:.3e}  torch-bf16-vs-fp32 {eb:.3e}")
+        assert ea < max(2.0 * eb, 3e-2), (k, ea, eb)
+
+
 @pytest.mark.parametrize("N,H,W", [(3, 224, 224), (2, 20, 36)])
 def test_uint8_stem_pack_equals_reference_preprocessing(N, H, W):
     """Raw uint8 frames packed by sd_stem_pack_s2d_u8 == the reference's host preprocessing (torchvision v2.ToDtype(float32,
