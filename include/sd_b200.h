@@ -203,9 +203,10 @@ int sd_bn_finalize(const double* sums, long long R, int C, float eps, float mome
                    float* running_mean, float* running_var, void* stream);
 /* Fused stem: maxpool3x3s2(relu(bn(x))) without materialising the activated 112x112 map; backward recomputes the
  * ReLU mask from x (torchvision ResNet stem bn1 -> relu -> maxpool). mean/invstd from sd_bn_stats_nhwc_bf16.
- * With C = 64 and W <= 112 (sd_stem_band_supported) both directions run as row-band kernels: the forward stages its
- * input rows with one TMA bulk copy per CTA, the backward scatters the pooled gradient into a shared-memory
- * accumulator (csrc/stem_band.cu); other shapes use generic gather kernels. */
+ * With C = 64 and W <= 112 (sd_stem_band_supported) the specialised kernels of csrc/stem_band.cu run: the forward stages
+ * its input rows with one TMA bulk copy per CTA and takes the 9-tap arg-max on packed bf16 pairs; the backward routes the
+ * pooled gradient of the four windows reaching a 2x2 pixel block into registers (see also _bwd2 for the pooled-domain
+ * reductions); other shapes use generic gather kernels. */
 int sd_stem_band_supported(int H, int W, int C);
 int sd_stem_bn_relu_pool_nhwc_bf16_fwd(const void* x, const float* mean, const float* invstd, const float* gamma,
                                        const float* beta, void* y, void* idx, int N, int H, int W, int C, void* stream);

@@ -716,7 +716,7 @@ extern "C" int sd_stem_bn_relu_pool_nhwc_bf16_bwd2(const void* dpool, const void
     cudaStream_t st = (cudaStream_t)stream;
     const int HO = (H + 2 - 3) / 2 + 1, WO = (W + 2 - 3) / 2 + 1;
     SD_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
-    if (stem_band_supported(H, W, C)) {   // scatter-in-shared-memory row bands (stem_band.cu)
+    if (stem_band_supported(H, W, C)) {   // pooled-domain reductions + 2x2-block routing for dx (stem_band.cu)
         int rc = stem_band_bwd(dpool, idx, x, y_pooled, mean, invstd, gamma, beta, sums, nullptr, N, H, W, 0, st);
         if (rc != SD_OK) return rc;
         bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, C, dgamma, dbeta);

@@ -142,8 +142,9 @@ class StemBNReLUPool(torch.autograd.Function):
         dbeta = torch.empty(C, device=x.device, dtype=torch.float32)
         dx = torch.empty_like(x)
         if ops.stem_band_supported(H, W, C):
-            # row-band kernels: the pooled gradient is scattered into shared memory, the ReLU mask recomputed from x;
-            # pass 0 = per-channel reductions, pass 1 = dx.  The activated map's gradient is never materialised.
+            # per-channel reductions over the POOLED tensors (dy, y: only arg-max pixels carry gradient), then one pass
+            # that routes the pooled gradient to 2x2 pixel blocks, recomputes the ReLU mask from x and writes dx.  The
+            # activated map's gradient is never materialised.
             ops.stem_bwd(dy, idx, x, mean, invstd, gamma, beta, ctx.sums, dx, dgamma, dbeta, N, H, W, C, y_pooled=y_pooled)
         else:
             # generic shapes: gradient w.r.t. the activated map, then BatchNorm backward with the recomputed ReLU mask
