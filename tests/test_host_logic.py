@@ -203,3 +203,32 @@ def test_prefetcher_chunked_copy_is_a_plain_copy():
     d8 = torch.zeros_like(u8)
     _chunked_copy(d8, u8, 100)
     assert torch.equal(d8, u8)
+
+
+def test_committed_dram_traffic_matches_its_ncu_capture(tmp_path):
+    """profiles/r01_dram_traffic.json (what bench.py reports as roofline.traffic) is exactly what tools/ncu_summary.py derives
+    from the committed ncu CSV, and the measured DRAM bytes of the HBM-bound kernel classes equal their algorithmic bytes
+    (no wasted re-reads): BatchNorm backward at bs=256 moves 10.25-14.25 B per element of its tensors."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csv = os.path.join(root, "profiles", "dram_r01_full_step_bf16_s22.csv")
+    committed = json.load(open(os.path.join(root, "profiles", "r01_dram_traffic.json")))
+    out = tmp_path / "traffic.json"
+    subprocess.run([sys.executable, os.path.join(root, "tools", "ncu_summary.py"), "traffic", csv, str(out), "test"],
+                   check=True, capture_output=True)
+    fresh = json.load(open(out))
+    for k, v in fresh.items():
+        if k != "_source":
+            assert committed[k]["launches"] == v["launches"]
+            assert abs(committed[k]["dram_bytes_per_launch"] - v["dram_bytes_per_launch"]) <= 1e-6 * v["dram_bytes_per_launch"]
+    assert fresh["bn_bwd"]["launches"] == 19 and fresh["bn_apply"]["launches"] == 19
+    # 19 BatchNorm layers of ResNet18 after the stem at 2560 frames: 11 activations of 56x56x64-equivalent size in total
+    elems = 2560 * (4 * 56 * 56 * 64 + 5 * 28 * 28 * 128 + 5 * 14 * 14 * 256 + 5 * 7 * 7 * 512)
+    per_elem = fresh["bn_bwd"]["dram_bytes_per_launch"] * 19 / elems
+    assert 10.0 < per_elem < 14.5, per_elem
+    per_elem_apply = fresh["bn_apply"]["dram_bytes_per_launch"] * 19 / elems
+    assert 4.0 < per_elem_apply < 6.5, per_elem_apply
