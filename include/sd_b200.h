@@ -274,6 +274,43 @@ int sd_plan_set_debug_stamps(sd_plan* plan, long long* device_buffer);
 /* one forward_with_context (model.py:159-179) against the cached context, per-sample t */
 int sd_plan_denoise(sd_plan* plan, const float* x, const void* t, int t_is_float, float* eps_out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Layer-fused tensor-core path (bf16 mode, d_model = ff = 128: default.yaml and the scaled-up config).
+ *
+ * sd_pack_weights_bf16: fp32 weight matrices [rows][K] -> rows of ONE packed bf16 matrix [*][K] that the fused
+ * kernels read through a TMA tensor map (one launch for all layers of a stack).  Row order per ENCODER layer:
+ * in_proj (3d: Wq;Wk;Wv) | out_proj (d) | linear1 (d) | linear2 (d) = 768 rows; per DECODER layer:
+ * self_attn.in_proj (3d) | self_attn.out_proj | multihead_attn.in_proj (3d) | multihead_attn.out_proj | linear1 |
+ * linear2 = 1280 rows.
+ */
+#define SD_PACK_MAX_SEGMENTS 64
+typedef struct sd_pack_args {
+    const float* src[SD_PACK_MAX_SEGMENTS];
+    int rows[SD_PACK_MAX_SEGMENTS];
+    int dst_row0[SD_PACK_MAX_SEGMENTS];
+    int K;
+    void* dst; /* bf16 */
+} sd_pack_args;
+int sd_pack_weights_bf16(const sd_pack_args* args, int n_segments, void* stream);
+
+/* One pre-LN encoder layer (nn.TransformerEncoderLayer(norm_first=True, activation="gelu", dim_feedforward=d),
+ * encoder/base.py:29-40; torch/nn/modules/transformer.py:944-950) as ONE kernel: LN1 -> QKV -> per-head softmax
+ * attention -> out-proj + dropout + residual -> LN2 -> FC1 + GELU + dropout -> FC2 + dropout + residual.
+ * x, y: fp32 [B*S][128] (may alias).  One CTA per tile of floor(128/S) samples.  Dropout streams: dropout_stream + 0
+ * (attention probabilities, element ((b*H+h)*S+t)*S+m), +1 (out-proj, element row*128+c), +2 (FC1), +3 (FC2).
+ * Optional saves for the backward pass (all NULL in inference): x1_save fp32 [B*S][128] (residual stream after the
+ * attention block), xn1/attn/xn2/hact_save bf16 [B*S][128] (LN1(x), attention output, LN2(x1), hidden activation). */
+typedef struct sd_enc_layer_desc {
+    const float* x; float* y;
+    int B, S, H;
+    const void* w_packed; int w_rows_total; int w_row0; /* packed bf16 weights [w_rows_total][128]; this layer's first row */
+    const float *in_b, *out_b, *l1_b, *l2_b, *n1_w, *n1_b, *n2_w, *n2_b;
+    float* x1_save; void* xn1_save; void* attn_save; void* xn2_save; void* hact_save;
+    float dropout_p; unsigned long long dropout_seed; unsigned int dropout_stream;
+} sd_enc_layer_desc;
+int sd_enc_layer_supported(int d, int ff, int S, int H);
+int sd_enc_layer_fwd(const sd_enc_layer_desc* desc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

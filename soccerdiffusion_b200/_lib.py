@@ -59,6 +59,23 @@ class DecoderLayerWeights(C.Structure):
     )]
 
 
+PACK_MAX_SEGMENTS = 64
+
+
+class PackArgs(C.Structure):
+    _fields_ = [("src", c_f * PACK_MAX_SEGMENTS), ("rows", c_i * PACK_MAX_SEGMENTS), ("dst_row0", c_i * PACK_MAX_SEGMENTS),
+                ("K", c_i), ("dst", c_f)]
+
+
+class EncLayerDesc(C.Structure):
+    _fields_ = [("x", c_f), ("y", c_f), ("B", c_i), ("S", c_i), ("H", c_i),
+                ("w_packed", c_f), ("w_rows_total", c_i), ("w_row0", c_i),
+                ("in_b", c_f), ("out_b", c_f), ("l1_b", c_f), ("l2_b", c_f),
+                ("n1_w", c_f), ("n1_b", c_f), ("n2_w", c_f), ("n2_b", c_f),
+                ("x1_save", c_f), ("xn1_save", c_f), ("attn_save", c_f), ("xn2_save", c_f), ("hact_save", c_f),
+                ("dropout_p", c_fl), ("dropout_seed", c_ull), ("dropout_stream", c_u)]
+
+
 # name -> argtypes (restype is always int unless noted); mirrors include/sd_b200.h one to one
 SIGNATURES = {
     "sd_abi_version": [],
@@ -116,6 +133,9 @@ SIGNATURES = {
     "sd_plan_set_sampler": [C.c_void_p, c_i],
     "sd_plan_last_sampler": [C.c_void_p],
     "sd_plan_set_debug_stamps": [C.c_void_p, c_f],
+    "sd_pack_weights_bf16": [C.POINTER(PackArgs), c_i, c_f],
+    "sd_enc_layer_supported": [c_i, c_i, c_i, c_i],
+    "sd_enc_layer_fwd": [C.POINTER(EncLayerDesc), c_f],
 }
 
 _lib = None

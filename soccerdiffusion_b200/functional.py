@@ -198,6 +198,24 @@ def _zero_grads(params):
     return bufs, rets
 
 
+def _fused_enc_ok(cfg: RunCfg, d: int, ff: int, S: int, H: int) -> bool:
+    from . import runtime
+
+    return (cfg.precision == ops.PREC_BF16 and runtime.fused_layers() and ops.enc_layer_supported(d, ff, S, H))
+
+
+def _pack_enc_weights(layer_params, L: int, d: int):
+    """bf16 copies of the L layers' GEMM weights as ONE [L*768][d] matrix (the TMA tensor map of the fused kernels)."""
+    wp = torch.empty((L * ops.ENC_ROWS_PER_LAYER, d), device=layer_params[0].device, dtype=torch.bfloat16)
+    mats = []
+    for l in range(L):
+        in_w, _, out_w, _, l1_w, _, l2_w = layer_params[l * ENC_PARAMS_PER_LAYER: l * ENC_PARAMS_PER_LAYER + 7]
+        r0 = l * ops.ENC_ROWS_PER_LAYER
+        mats += [(in_w, 3 * d, r0), (out_w, d, r0 + 3 * d), (l1_w, d, r0 + 4 * d), (l2_w, d, r0 + 5 * d)]
+    ops.pack_weights_bf16(mats, wp, d)
+    return wp
+
+
 # --------------------------------------------------------------------------------------------------
 class EncoderStackFn(torch.autograd.Function):
     """Conv1d patch embedding (as a GEMM) + PE + L pre-LN encoder layers (base.py:49-53)."""
@@ -211,6 +229,15 @@ class EncoderStackFn(torch.autograd.Function):
         save = any(ctx.needs_input_grad)  # grad mode is always off inside forward(); this reflects the caller's
         h = _empty((M, d), x_in)
         ops.gemm(x_in, Kin, MK, emb_w, Kin, NK, h, d, M, d, Kin, precision=cfg.precision, bias=emb_b, pe=pe, pe_period=S)
+        if not save and L > 0 and _fused_enc_ok(cfg, d, layer_params[4].shape[0], S, H):
+            # layer-fused tensor-core path (one kernel per layer, weights by TMA); the residual stream is updated in place
+            wp = _pack_enc_weights(layer_params, L, d)
+            for l in range(L):
+                (in_w, in_b, out_w, out_b, l1_w, l1_b, l2_w, l2_b, n1_w, n1_b, n2_w, n2_b) = layer_params[
+                    l * ENC_PARAMS_PER_LAYER: (l + 1) * ENC_PARAMS_PER_LAYER]
+                ops.enc_layer_fwd(h, h, B, S, H, wp, l * ops.ENC_ROWS_PER_LAYER, in_b, out_b, l1_b, l2_b, n1_w, n1_b, n2_w,
+                                  n2_b, saves=None, dropout=cfg.drop(8 * l))
+            return h.view(B, S, d)
         acts = []
         for l in range(L):
             in_w, in_b, out_w, out_b, l1_w, l1_b, l2_w, l2_b, n1_w, n1_b, n2_w, n2_b = layer_params[

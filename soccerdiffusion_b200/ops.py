@@ -401,3 +401,48 @@ def bn_finalize(sums, R, C, eps, momentum, mean, invstd, running_mean, running_v
                                     running_var.data_ptr() if running_var is not None else None, stream_ptr()),
           "sd_bn_finalize")
     _count()
+
+
+# ---- layer-fused tensor-core path (bf16 mode, d_model = ff = 128) ------------------------------------------------------
+ENC_ROWS_PER_LAYER = 768     # in_proj (384) | out_proj | linear1 | linear2
+DEC_ROWS_PER_LAYER = 1280    # sa.in_proj (384) | sa.out_proj | ca.in_proj (384) | ca.out_proj | linear1 | linear2
+
+
+def pack_weights_bf16(mats, dst: torch.Tensor, K: int):
+    """``mats``: list of (fp32 weight tensor or raw pointer, rows, first destination row) -> rows of the packed bf16 matrix ``dst``
+    (one launch per 64 matrices)."""
+    lib = _lib.lib()
+    for i0 in range(0, len(mats), _lib.PACK_MAX_SEGMENTS):
+        chunk = mats[i0: i0 + _lib.PACK_MAX_SEGMENTS]
+        a = _lib.PackArgs()
+        for i, (w, rows, row0) in enumerate(chunk):
+            a.src[i] = w if isinstance(w, int) else w.data_ptr()
+            a.rows[i] = rows
+            a.dst_row0[i] = row0
+        a.K = K
+        a.dst = dst.data_ptr()
+        check(lib.sd_pack_weights_bf16(C.byref(a), len(chunk), stream_ptr()), "sd_pack_weights_bf16")
+        _count()
+
+
+def enc_layer_supported(d: int, ff: int, S: int, H: int) -> bool:
+    return bool(_lib.lib().sd_enc_layer_supported(d, ff, S, H))
+
+
+def enc_layer_fwd(x, y, B, S, H, w_packed, w_row0, in_b, out_b, l1_b, l2_b, n1_w, n1_b, n2_w, n2_b, saves=None, dropout=None):
+    """One fused encoder layer (sd_enc_layer_fwd).  ``saves`` = (x1 fp32, xn1, attn, xn2, hact bf16) or None."""
+    d = _lib.EncLayerDesc()
+    d.x, d.y, d.B, d.S, d.H = x.data_ptr(), y.data_ptr(), B, S, H
+    d.w_packed, d.w_rows_total, d.w_row0 = w_packed.data_ptr(), w_packed.shape[0], w_row0
+    d.in_b, d.out_b, d.l1_b, d.l2_b = in_b.data_ptr(), out_b.data_ptr(), l1_b.data_ptr(), l2_b.data_ptr()
+    d.n1_w, d.n1_b, d.n2_w, d.n2_b = n1_w.data_ptr(), n1_b.data_ptr(), n2_w.data_ptr(), n2_b.data_ptr()
+    if saves is not None:
+        d.x1_save, d.xn1_save, d.attn_save, d.xn2_save, d.hact_save = (t.data_ptr() for t in saves)
+    if dropout is not None and dropout[0] > 0.0:
+        d.dropout_p, d.dropout_seed, d.dropout_stream = dropout
+    M = B * S
+    # algorithmic work of the layer (SURVEY.md §8d): 12 S d^2 + 4 S^2 d per sample
+    with _Timed("fused_enc_layer_fwd", B * (12.0 * S * 128 * 128 + 4.0 * S * S * 128),
+                M * 128 * (8.0 + (4.0 + 8.0 if saves is not None else 0.0)), f"[B{B} S{S} H{H}]"):
+        check(_lib.lib().sd_enc_layer_fwd(C.byref(d), stream_ptr()), "sd_enc_layer_fwd")
+    _count()

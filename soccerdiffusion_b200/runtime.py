@@ -71,6 +71,20 @@ def set_dropout(p: float):
     DROPOUT_P = float(p)
 
 
+_fused_layers = os.environ.get("SD_B200_FUSED_LAYERS", "1") == "1"
+
+
+def set_fused_layers(on: bool):
+    """bf16 mode, d_model = 128: run each transformer layer as ONE layer-fused tcgen05 kernel (weights by TMA, residual
+    stream in registers) instead of one kernel per GEMM / attention / LayerNorm.  Default on."""
+    global _fused_layers
+    _fused_layers = bool(on)
+
+
+def fused_layers() -> bool:
+    return _fused_layers
+
+
 _concurrent_encoders = os.environ.get("SD_B200_CONCURRENT_ENCODERS", "1") == "1"
 
 

@@ -1,0 +1,112 @@
+"""GPU parity of the layer-fused tcgen05 kernels (bf16 mode: rel-L2 <= 2e-2 against an fp32 restatement of the reference
+layer, torch/nn/modules/transformer.py:944-950 as instantiated by ml/model/encoder/base.py:29-40; observed ~3e-3), and
+equality with the unfused kernel-per-op path under identical dropout masks."""
+import math
+
+import pytest
+import torch
+
+from util_gpu import rel
+
+pytestmark = pytest.mark.gpu
+TOL_BF16 = 2e-2
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from soccerdiffusion_b200 import _lib, ops
+
+    _lib.load()
+    return ops
+
+
+def make_layer(d, ff, gen, scale=1.0):
+    r = lambda *s: (torch.randn(*s, generator=gen) * scale)
+    return dict(in_w=r(3 * d, d) / math.sqrt(d), in_b=r(3 * d) * 0.1, out_w=r(d, d) / math.sqrt(d), out_b=r(d) * 0.1,
+                l1_w=r(ff, d) / math.sqrt(d), l1_b=r(ff) * 0.1, l2_w=r(d, ff) / math.sqrt(ff), l2_b=r(d) * 0.1,
+                n1_w=1 + 0.1 * r(d), n1_b=0.1 * r(d), n2_w=1 + 0.1 * r(d), n2_b=0.1 * r(d))
+
+
+def enc_layer_ref(x, P, B, S, H):
+    """fp32 restatement (pre-LN encoder layer, erf GELU, no dropout); also returns the tensors the kernel saves."""
+    F = torch.nn.functional
+    d = x.shape[-1]
+    dh = d // H
+    xn1 = F.layer_norm(x, (d,), P["n1_w"], P["n1_b"], 1e-5)
+    qkv = xn1 @ P["in_w"].T + P["in_b"]
+    q, k, v = (t.view(B, S, H, dh).transpose(1, 2) for t in qkv.split(d, dim=-1))
+    a = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(dh), dim=-1) @ v
+    attn = a.transpose(1, 2).reshape(B * S, d)
+    x1 = x + attn @ P["out_w"].T + P["out_b"]
+    xn2 = F.layer_norm(x1, (d,), P["n2_w"], P["n2_b"], 1e-5)
+    hact = F.gelu(xn2 @ P["l1_w"].T + P["l1_b"])
+    y = x1 + hact @ P["l2_w"].T + P["l2_b"]
+    return y, dict(x1=x1, xn1=xn1, attn=attn, xn2=xn2, hact=hact)
+
+
+@pytest.mark.parametrize("B,S,H", [(5, 100, 4), (30, 10, 8), (3, 20, 4), (2, 128, 4), (13, 10, 4), (1, 7, 2)])
+def test_enc_layer_fwd_matches_fp32_restatement(ops, B, S, H):
+    d = 128
+    assert ops.enc_layer_supported(d, d, S, H)
+    gen = torch.Generator().manual_seed(B * 1000 + S)
+    P = {k: v.cuda() for k, v in make_layer(d, d, gen).items()}
+    x = torch.randn(B * S, d, generator=gen).cuda()
+    want, saved = enc_layer_ref(x, P, B, S, H)
+    wp = torch.empty(ops.ENC_ROWS_PER_LAYER + 128, d, device="cuda", dtype=torch.bfloat16)   # layer at a non-zero row offset
+    r0 = 128
+    ops.pack_weights_bf16([(P["in_w"], 3 * d, r0), (P["out_w"], d, r0 + 3 * d), (P["l1_w"], d, r0 + 4 * d),
+                           (P["l2_w"], d, r0 + 5 * d)], wp, d)
+    assert torch.equal(wp[r0: r0 + 3 * d], P["in_w"].to(torch.bfloat16))
+    y = torch.full_like(x, float("nan"))
+    x1 = torch.empty_like(x)
+    bf = [torch.empty(B * S, d, device="cuda", dtype=torch.bfloat16) for _ in range(4)]
+    ops.enc_layer_fwd(x, y, B, S, H, wp, r0, P["in_b"], P["out_b"], P["l1_b"], P["l2_b"], P["n1_w"], P["n1_b"], P["n2_w"],
+                      P["n2_b"], saves=(x1, *bf))
+    torch.cuda.synchronize()
+    assert torch.isfinite(y).all()
+    assert rel(y, want) < TOL_BF16, rel(y, want)
+    assert rel(x1, saved["x1"]) < TOL_BF16
+    for got, name in zip(bf, ("xn1", "attn", "xn2", "hact")):
+        assert rel(got.float(), saved[name]) < TOL_BF16, (name, rel(got.float(), saved[name]))
+    # inference form (no saves), in place
+    x2 = x.clone()
+    ops.enc_layer_fwd(x2, x2, B, S, H, wp, r0, P["in_b"], P["out_b"], P["l1_b"], P["l2_b"], P["n1_w"], P["n1_b"], P["n2_w"],
+                      P["n2_b"])
+    assert torch.equal(x2, y)
+
+
+def _stack(B, S, H, L, p, fused, seed=5):
+    from soccerdiffusion_b200 import runtime
+    from soccerdiffusion_b200.functional import EncoderStackFn, RunCfg
+    from soccerdiffusion_b200 import ops as O
+
+    d, kin = 128, 20
+    gen = torch.Generator().manual_seed(seed)
+    layers = []
+    for _ in range(L):
+        P = make_layer(d, d, gen)
+        layers += [P[k].cuda() for k in ("in_w", "in_b", "out_w", "out_b", "l1_w", "l1_b", "l2_w", "l2_b", "n1_w", "n1_b",
+                                         "n2_w", "n2_b")]
+    emb_w = (torch.randn(d, kin, generator=gen) / math.sqrt(kin)).cuda()
+    emb_b = torch.zeros(d).cuda()
+    pe = (0.1 * torch.randn(S, d, generator=gen)).cuda()
+    x = torch.randn(B * S, kin, generator=gen).cuda()
+    runtime.set_fused_layers(fused)
+    try:
+        with torch.no_grad():
+            return EncoderStackFn.apply(RunCfg(precision=O.PREC_BF16, p=p, seed=77, stream_base=0), B, S, H, pe, x, emb_w,
+                                        emb_b, *layers)
+    finally:
+        runtime.set_fused_layers(True)
+
+
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_fused_stack_equals_unfused_stack_with_same_dropout_masks(ops, p):
+    """Both paths draw their dropout masks from the same counter-based streams, so they must agree to bf16 rounding
+    noise with dropout live (p = 0.1, the reference's training value)."""
+    a = _stack(6, 100, 4, 2, p, fused=True)
+    b = _stack(6, 100, 4, 2, p, fused=False)
+    assert rel(a, b) < 1e-2, rel(a, b)
+    a = _stack(29, 10, 8, 1, p, fused=True)
+    b = _stack(29, 10, 8, 1, p, fused=False)
+    assert rel(a, b) < 1e-2, rel(a, b)
