@@ -260,8 +260,10 @@ int sd_plan_set_schedule(sd_plan* plan, int num_steps, const long long* timestep
                          void* stream);
 /* model.encode_input_data output, concatenated (B, ctx_tokens, d): projects K/V for all layers once */
 int sd_plan_set_context(sd_plan* plan, const float* ctx, int B, void* stream);
-/* x_T (B,T,J) -> x_0 (B,T,J); eps_trace optional (steps,B,T,J); denormalize: x*std+mean (ros.py:313) */
-int sd_plan_sample(sd_plan* plan, const float* x_T, float* x_out, float* eps_trace, int denormalize, void* stream);
+/* x_T (B,T,J) -> x_0 (B,T,J); eps_trace optional (steps,B,T,J); denormalize: x*std+mean (ros.py:313).
+ * B = trajectories held by x_T / x_out: SD_E_BAD_ARG unless it equals the batch of the last sd_plan_set_context
+ * (the reference raises a shape error for mismatched context / sample batches). */
+int sd_plan_sample(sd_plan* plan, const float* x_T, float* x_out, float* eps_trace, int denormalize, int B, void* stream);
 /* Sampler kernel selection: 0 = auto (cluster kernel for batches of <= 18 trajectories when the device can co-schedule it),
  * 1 = one CTA per trajectory, 2 = one 16-CTA thread-block cluster per trajectory (weights resident in the
  * cluster's shared memory, activations exchanged through distributed shared memory).  Env SD_B200_SAMPLER=
@@ -272,7 +274,7 @@ int sd_plan_last_sampler(const sd_plan* plan);
  * phases (CTA 0); NULL disables */
 int sd_plan_set_debug_stamps(sd_plan* plan, long long* device_buffer);
 /* one forward_with_context (model.py:159-179) against the cached context, per-sample t */
-int sd_plan_denoise(sd_plan* plan, const float* x, const void* t, int t_is_float, float* eps_out, void* stream);
+int sd_plan_denoise(sd_plan* plan, const float* x, const void* t, int t_is_float, float* eps_out, int B, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Layer-fused tensor-core path (bf16 mode, d_model = ff = 128: default.yaml and the scaled-up config).

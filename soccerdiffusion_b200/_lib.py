@@ -128,8 +128,8 @@ SIGNATURES = {
     "sd_plan_set_io": [C.c_void_p, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f],
     "sd_plan_set_schedule": [C.c_void_p, c_i, C.POINTER(c_ll), C.POINTER(c_fl), c_f],
     "sd_plan_set_context": [C.c_void_p, c_f, c_i, c_f],
-    "sd_plan_sample": [C.c_void_p, c_f, c_f, c_f, c_i, c_f],
-    "sd_plan_denoise": [C.c_void_p, c_f, c_f, c_i, c_f, c_f],
+    "sd_plan_sample": [C.c_void_p, c_f, c_f, c_f, c_i, c_i, c_f],
+    "sd_plan_denoise": [C.c_void_p, c_f, c_f, c_i, c_f, c_i, c_f],
     "sd_plan_set_sampler": [C.c_void_p, c_i],
     "sd_plan_last_sampler": [C.c_void_p],
     "sd_plan_set_debug_stamps": [C.c_void_p, c_f],

@@ -2,12 +2,14 @@
 // TMA tensor-map encoding on the host, TMA tile loads, and the thread <-> accumulator mapping used by every
 // fused epilogue.
 //
-// Thread mapping of a 256-thread CTA working on one 128-row tile (row = TMEM lane):
-//   warp w: lane quarter q = w & 3 (the only TMEM lanes the warp may read), column half hf = w >> 2
-//   thread: row r = 32 q + lane, columns [64 hf, 64 hf + 64) of every 128-column fp32 accumulator.
-// The fp32 residual stream of the tile lives in REGISTERS in exactly this mapping (64 floats per thread) from the
+// Thread mapping of a 512-thread CTA working on one 128-row tile (row = TMEM lane):
+//   warp w: lane quarter q = w & 3 (the only TMEM lanes the warp may read), column quarter cq = w >> 2
+//   thread: row r = 32 q + lane, columns [32 cq, 32 cq + 32) of every 128-column fp32 accumulator.
+// The fp32 residual stream of the tile lives in REGISTERS in exactly this mapping (32 floats per thread) from the
 // first load to the last store of a layer; bf16 copies are written into 128-byte-swizzled [128][64] operand tiles
-// (tile hf <-> columns [64 hf, 64 hf + 64)) for the tensor core.
+// (tile cq >> 1, 16-byte chunks 4 (cq & 1) .. 4 (cq & 1) + 3) for the tensor core.
+// (16 warps: the epilogues are issue- and latency-bound, and a kernel this long must stay small enough for the
+// instruction cache — a 256-thread / 64-column version ran 8x slower than its instruction count on fetch stalls.)
 #pragma once
 #include <cuda.h>
 
@@ -19,7 +21,7 @@ namespace sdlf {
 using namespace sd;
 using namespace sdtc;
 
-constexpr int LNT = 256;            // threads per CTA
+constexpr int LNT = 512;            // threads per CTA
 constexpr int LTILE = 128 * 128;    // bytes of one [128 rows][64 bf16] operand tile
 constexpr float LN_EPS = 1e-5f;     // nn.LayerNorm default (never overridden by the reference)
 
@@ -72,30 +74,42 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
 
 // ---- accumulator access in the fused-epilogue mapping -------------------------------------------------------------------
 struct Lane {
-    int tid, warp, lane, q, hf, row;
+    int tid, warp, lane, q, cq, row, col0;
     uint32_t tlane;   // TMEM lane field of this warp's quarter
     __device__ __forceinline__ Lane() {
         tid = threadIdx.x;
         warp = tid >> 5;
         lane = tid & 31;
         q = warp & 3;
-        hf = warp >> 2;
+        cq = warp >> 2;
         row = q * 32 + lane;
+        col0 = 32 * cq;
         tlane = (uint32_t)(q * 32) << 16;
     }
 };
-// this thread's 64 columns of the accumulator at TMEM column `col`
-__device__ __forceinline__ void ld_acc64(uint32_t tmem, const Lane& L, int col, float* v) {
-    tmem_ld_32x32(tmem + L.tlane + (uint32_t)(col + 64 * L.hf), v);
-    tmem_ld_32x32(tmem + L.tlane + (uint32_t)(col + 64 * L.hf + 32), v + 32);
+// this thread's 32 columns of the accumulator at TMEM column `col`
+__device__ __forceinline__ void ld_acc32(uint32_t tmem, const Lane& L, int col, float* v) {
+    tmem_ld_32x32(tmem + L.tlane + (uint32_t)(col + L.col0), v);
 }
-// 64 fp32 values -> bf16 row `r` of a [128][64] swizzled tile (and, optionally, the same 128 bytes to global memory)
-__device__ __forceinline__ void st_row64(uint8_t* tile, int r, const float* v, uint4* gsave) {
+// 32 fp32 values -> bf16 columns [32 cq, 32 cq + 32) of row r of a 128-wide operand (two [128][64] swizzled tiles at
+// `tiles`), and, optionally, the same 64 bytes to global memory
+__device__ __forceinline__ void st_row32(uint8_t* tiles, const Lane& L, const float* v, uint4* gsave) {
+    uint8_t* tile = tiles + (L.cq >> 1) * LTILE;
+    const int c0 = (L.cq & 1) * 4;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < 4; ++c) {
         const uint4 u = pack8_bf16(v + 8 * c);
-        *reinterpret_cast<uint4*>(tile + sw128_chunk_off(r, c)) = u;
+        *reinterpret_cast<uint4*>(tile + sw128_chunk_off(L.row, c0 + c)) = u;
         if (gsave) gsave[c] = u;
+    }
+}
+// 32 consecutive fp32 parameters (16-byte aligned) through the read-only path
+__device__ __forceinline__ void ldg32(const float* __restrict__ p, float* out) {
+    const float4* g = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 t = __ldg(g + j);
+        out[4 * j] = t.x; out[4 * j + 1] = t.y; out[4 * j + 2] = t.z; out[4 * j + 3] = t.w;
     }
 }
 __device__ __forceinline__ void unpack8_bf16(const uint4& u, float* f) {
@@ -129,32 +143,34 @@ __device__ __forceinline__ void mma_a_k_b_mn(uint32_t tmem_d, uint32_t a_addr, u
     }
 }
 
-// pair exchange through shared memory: the two threads that share a row (tid and tid ^ 128) combine a partial value.
-// `buf` alternates between two [256]-float arrays so that consecutive exchanges need one barrier each.
-__device__ __forceinline__ float pair_sum(float v, float* red, int tid) {
+// row exchange through shared memory: the four threads that share a row (tid & 127 + 128 k) combine a partial value.
+// `red` alternates between two [512]-float arrays so that consecutive exchanges need one barrier each.
+__device__ __forceinline__ float row_sum(float v, float* red, int tid) {
     red[tid] = v;
     __syncthreads();
-    return v + red[tid ^ 128];
+    const int b = tid & 127;
+    return (red[b] + red[b + 128]) + (red[b + 256] + red[b + 384]);
 }
-__device__ __forceinline__ float pair_max(float v, float* red, int tid) {
+__device__ __forceinline__ float row_max(float v, float* red, int tid) {
     red[tid] = v;
     __syncthreads();
-    return fmaxf(v, red[tid ^ 128]);
+    const int b = tid & 127;
+    return fmaxf(fmaxf(red[b], red[b + 128]), fmaxf(red[b + 256], red[b + 384]));
 }
 
 // LayerNorm of the register-resident row fragment: returns mean / rstd of the full 128-wide row
 __device__ __forceinline__ void row_stats(const float* xr, float* red0, float* red1, int tid, float& mean, float& rstd) {
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 64; ++j) s += xr[j];
-    mean = pair_sum(s, red0, tid) * (1.0f / 128.0f);
+    for (int j = 0; j < 32; ++j) s += xr[j];
+    mean = row_sum(s, red0, tid) * (1.0f / 128.0f);
     float s2 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 64; ++j) {
+    for (int j = 0; j < 32; ++j) {
         const float c = xr[j] - mean;
         s2 = fmaf(c, c, s2);
     }
-    rstd = rsqrtf(pair_sum(s2, red1, tid) * (1.0f / 128.0f) + LN_EPS);
+    rstd = rsqrtf(row_sum(s2, red1, tid) * (1.0f / 128.0f) + LN_EPS);
 }
 
 }  // namespace sdlf

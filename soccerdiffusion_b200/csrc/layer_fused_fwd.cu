@@ -4,7 +4,7 @@
 //     x1 = x  + Drop(OutProj(MHA(LN1 x)))          torch/nn/modules/transformer.py:944-950 (norm_first)
 //     y  = x1 + Drop(W2 Drop(GELU_erf(W1 LN2 x1)))  reference call sites: ml/model/encoder/base.py:29-53
 //
-// One CTA (256 threads) per 128-row tile holding floor(128 / S) whole samples (S tokens each; 1 sample at S = 100,
+// One CTA (512 threads) per 128-row tile holding floor(128 / S) whole samples (S tokens each; 1 sample at S = 100,
 // 12 at S = 10).  The fp32 residual stream of the tile is read from HBM once, lives in registers (layer_common.cuh
 // mapping) and is written once; everything in between stays on chip:
 //
@@ -46,6 +46,7 @@ struct EncFwdParams {
     Dropout drop;   // .stream = first dropout stream of this layer (sites +0 attention, +1 out-proj, +2 FC1, +3 FC2)
 };
 
+template <bool DROP>
 __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const EncFwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar[NBAR];
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);
     const Lane L;
-    const int tid = L.tid, r = L.row, hf = L.hf;
+    const int tid = L.tid, r = L.row, c0 = L.col0;
 
     if (tid == 0) {
         for (int i = 0; i < NBAR; ++i) mbar_init(&bar[i], 1);
@@ -84,29 +85,30 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
     const int Rv = nsamp * S;                          // valid rows of this tile
     const long long grow = (long long)samp0 * S + r;   // global row of this thread
     const bool rv = r < Rv;
-    const uint64_t dseed = p.drop.resolve();
-    const bool dropping = p.drop.thresh != 0;
+    const long long goff = grow * 128 + c0;            // this thread's first element in every [rows][128] matrix
+    const uint64_t dseed = DROP ? p.drop.resolve() : 0ull;
 
     // ---- residual fragment + LN1 --------------------------------------------------------------------------------------
-    float xr[64];
+    float xr[32];
     if (rv) {
-        const float4* g = reinterpret_cast<const float4*>(p.x + grow * 128 + 64 * hf);
+        const float4* g = reinterpret_cast<const float4*>(p.x + goff);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 8; ++j) {
             const float4 t = g[j];
             xr[4 * j] = t.x; xr[4 * j + 1] = t.y; xr[4 * j + 2] = t.z; xr[4 * j + 3] = t.w;
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < 64; ++j) xr[j] = 0.f;
+        for (int j = 0; j < 32; ++j) xr[j] = 0.f;
     }
     {
-        float mean, rstd, v[64];
+        float mean, rstd, v[32], ga[32], be[32];
+        ldg32(p.n1_w + c0, ga);
+        ldg32(p.n1_b + c0, be);
         row_stats(xr, red[0], red[1], tid, mean, rstd);
 #pragma unroll
-        for (int j = 0; j < 64; ++j)
-            v[j] = rv ? fmaf((xr[j] - mean) * rstd, __ldg(p.n1_w + 64 * hf + j), __ldg(p.n1_b + 64 * hf + j)) : 0.f;
-        st_row64(smem + OFF_XN + hf * LTILE, r, v, (rv && p.xn1_save) ? p.xn1_save + (grow * 128 + 64 * hf) / 8 : nullptr);
+        for (int j = 0; j < 32; ++j) v[j] = rv ? fmaf((xr[j] - mean) * rstd, ga[j], be[j]) : 0.f;
+        st_row32(smem + OFF_XN, L, v, (rv && p.xn1_save) ? p.xn1_save + goff / 8 : nullptr);
     }
     fence_proxy_async_smem();
     tc_fence_before_sync();
@@ -133,28 +135,30 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
 
     // ---- Q, K, V^T epilogues: + bias -> bf16 operand tiles -------------------------------------------------------------
     {
-        float v[64];
+        float v[32], b[32];
+        ldg32(p.in_b + c0, b);
         mbar_wait(&bar[BQ], 0);
         tc_fence_after_sync();
-        ld_acc64(tmem, L, ACC0, v);
+        ld_acc32(tmem, L, ACC0, v);
 #pragma unroll
-        for (int j = 0; j < 64; ++j) v[j] += __ldg(p.in_b + 64 * hf + j);
-        st_row64(smem + OFF_QS + hf * LTILE, r, v, nullptr);
+        for (int j = 0; j < 32; ++j) v[j] += b[j];
+        st_row32(smem + OFF_QS, L, v, nullptr);
+        ldg32(p.in_b + 128 + c0, b);
         mbar_wait(&bar[BK], 0);
         tc_fence_after_sync();
-        ld_acc64(tmem, L, ACC1, v);
+        ld_acc32(tmem, L, ACC1, v);
 #pragma unroll
-        for (int j = 0; j < 64; ++j) v[j] += __ldg(p.in_b + 128 + 64 * hf + j);
-        st_row64(smem + OFF_KS + hf * LTILE, r, v, nullptr);
+        for (int j = 0; j < 32; ++j) v[j] += b[j];
+        st_row32(smem + OFF_KS, L, v, nullptr);
+        const float bv = __ldg(p.in_b + 256 + r);
         mbar_wait(&bar[BV], 0);
         tc_fence_after_sync();
         if (tid == 0) load_w(4);   // slot A drained by the V^T MMAs
         __syncwarp();
-        ld_acc64(tmem, L, ACC2, v);   // row = feature r, columns = tokens
-        const float bv = __ldg(p.in_b + 256 + r);
+        ld_acc32(tmem, L, ACC2, v);   // row = feature r, columns = tokens
 #pragma unroll
-        for (int j = 0; j < 64; ++j) v[j] += bv;
-        st_row64(smem + OFF_VT + hf * LTILE, r, v, nullptr);
+        for (int j = 0; j < 32; ++j) v[j] += bv;
+        st_row32(smem + OFF_VT, L, v, nullptr);
     }
     fence_proxy_async_smem();
     tc_fence_before_sync();
@@ -183,34 +187,34 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
     const int t_tok = r - lo;
 #pragma unroll 1
     for (int h = 0; h < H; ++h) {
-        float v[64];
+        float v[32];
         mbar_wait(&bar[BS0 + h], 0);
         tc_fence_after_sync();
-        ld_acc64(tmem, L, (h & 1) ? ACC1 : ACC0, v);
+        ld_acc32(tmem, L, (h & 1) ? ACC1 : ACC0, v);
         float mx = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
-            const int m = 64 * hf + j;
+        for (int j = 0; j < 32; ++j) {
+            const int m = c0 + j;
             if (m >= lo && m < hi) mx = fmaxf(mx, v[j]);
         }
-        mx = pair_max(mx, red[0], tid);
+        mx = row_max(mx, red[0], tid);
         float sum = 0.f;
         const uint64_t didx = (((uint64_t)(samp0 + s_idx) * H + h) * S + t_tok) * (uint64_t)S;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
-            const int m = 64 * hf + j;
+        for (int j = 0; j < 32; ++j) {
+            const int m = c0 + j;
             float e = 0.f;
             if (rv && m >= lo && m < hi) {
                 e = exp2f((v[j] - mx) * sc);
                 sum += e;
-                if (dropping) e *= p.drop.at(dseed, didx + (m - lo));
+                if (DROP) e *= dropout_scale(dseed, p.drop.stream, didx + (m - lo), p.drop.thresh, p.drop.inv_keep);
             }
             v[j] = e;
         }
-        sum = pair_sum(sum, red[1], tid);
-        if (hf == 0) rsum[h][r] = rv ? 1.0f / sum : 0.f;
+        sum = row_sum(sum, red[1], tid);
+        if (L.cq == 0) rsum[h][r] = rv ? 1.0f / sum : 0.f;
         if (h > 0) mbar_wait(&bar[BP0 + h - 1], 0);   // P of the previous head has been consumed
-        st_row64(smem + OFF_XN + hf * LTILE, r, v, nullptr);
+        st_row32(smem + OFF_XN, L, v, nullptr);
         fence_proxy_async_smem();
         tc_fence_before_sync();
         __syncthreads();
@@ -231,15 +235,15 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
     mbar_wait(&bar[BP0 + H - 1], 0);
     tc_fence_after_sync();
     {
-        float v[64];
-        ld_acc64(tmem, L, ACC3, v);
+        float v[32];
+        ld_acc32(tmem, L, ACC3, v);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            const float inv = rsum[(64 * hf + 16 * g) / dh][r];
+        for (int g = 0; g < 2; ++g) {
+            const float inv = rsum[(c0 + 16 * g) / dh][r];
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[16 * g + j] *= inv;
         }
-        st_row64(smem + OFF_XN + hf * LTILE, r, v, (rv && p.attn_save) ? p.attn_save + (grow * 128 + 64 * hf) / 8 : nullptr);
+        st_row32(smem + OFF_XN, L, v, (rv && p.attn_save) ? p.attn_save + goff / 8 : nullptr);
     }
     fence_proxy_async_smem();
     tc_fence_before_sync();
@@ -252,31 +256,34 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
     }
     __syncwarp();
     // ---- out-projection epilogue: x1 = x + Drop(acc + b) ; LN2 -----------------------------------------------------------
-    mbar_wait(&bar[BOUT], 0);
-    tc_fence_after_sync();
-    if (tid == 0) load_w(5);   // slot B drained by the out-projection
-    __syncwarp();
     {
-        float v[64];
-        ld_acc64(tmem, L, ACC0, v);
-        const uint64_t didx = (uint64_t)grow * 128 + 64 * hf;
+        float v[32], b[32];
+        ldg32(p.out_b + c0, b);
+        mbar_wait(&bar[BOUT], 0);
+        tc_fence_after_sync();
+        if (tid == 0) load_w(5);   // slot B drained by the out-projection
+        __syncwarp();
+        ld_acc32(tmem, L, ACC0, v);
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
-            float t = v[j] + __ldg(p.out_b + 64 * hf + j);
-            if (dropping) t *= dropout_scale(dseed, p.drop.stream + 1, didx + j, p.drop.thresh, p.drop.inv_keep);
+        for (int j = 0; j < 32; ++j) {
+            float t = v[j] + b[j];
+            if (DROP) t *= dropout_scale(dseed, p.drop.stream + 1, (uint64_t)goff + j, p.drop.thresh, p.drop.inv_keep);
             xr[j] = rv ? xr[j] + t : 0.f;
         }
         if (rv && p.x1_save) {
-            float4* g = reinterpret_cast<float4*>(p.x1_save + grow * 128 + 64 * hf);
+            float4* g = reinterpret_cast<float4*>(p.x1_save + goff);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) g[j] = make_float4(xr[4 * j], xr[4 * j + 1], xr[4 * j + 2], xr[4 * j + 3]);
+            for (int j = 0; j < 8; ++j) g[j] = make_float4(xr[4 * j], xr[4 * j + 1], xr[4 * j + 2], xr[4 * j + 3]);
         }
         float mean, rstd;
+        ldg32(p.n2_w + c0, b);
         row_stats(xr, red[0], red[1], tid, mean, rstd);
 #pragma unroll
-        for (int j = 0; j < 64; ++j)
-            v[j] = rv ? fmaf((xr[j] - mean) * rstd, __ldg(p.n2_w + 64 * hf + j), __ldg(p.n2_b + 64 * hf + j)) : 0.f;
-        st_row64(smem + OFF_XN + hf * LTILE, r, v, (rv && p.xn2_save) ? p.xn2_save + (grow * 128 + 64 * hf) / 8 : nullptr);
+        for (int j = 0; j < 32; ++j) v[j] = (xr[j] - mean) * rstd * b[j];
+        ldg32(p.n2_b + c0, b);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = rv ? v[j] + b[j] : 0.f;
+        st_row32(smem + OFF_XN, L, v, (rv && p.xn2_save) ? p.xn2_save + goff / 8 : nullptr);
     }
     fence_proxy_async_smem();
     tc_fence_before_sync();
@@ -288,19 +295,19 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
         mma_commit(&bar[BF1]);
     }
     __syncwarp();
-    mbar_wait(&bar[BF1], 0);
-    tc_fence_after_sync();
     {
-        float v[64];
-        ld_acc64(tmem, L, ACC1, v);
-        const uint64_t didx = (uint64_t)grow * 128 + 64 * hf;
+        float v[32], b[32];
+        ldg32(p.l1_b + c0, b);
+        mbar_wait(&bar[BF1], 0);
+        tc_fence_after_sync();
+        ld_acc32(tmem, L, ACC1, v);
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
-            float t = gelu_erf(v[j] + __ldg(p.l1_b + 64 * hf + j));
-            if (dropping) t *= dropout_scale(dseed, p.drop.stream + 2, didx + j, p.drop.thresh, p.drop.inv_keep);
+        for (int j = 0; j < 32; ++j) {
+            float t = gelu_erf(v[j] + b[j]);
+            if (DROP) t *= dropout_scale(dseed, p.drop.stream + 2, (uint64_t)goff + j, p.drop.thresh, p.drop.inv_keep);
             v[j] = rv ? t : 0.f;
         }
-        st_row64(smem + OFF_QS + hf * LTILE, r, v, (rv && p.hact_save) ? p.hact_save + (grow * 128 + 64 * hf) / 8 : nullptr);
+        st_row32(smem + OFF_QS, L, v, (rv && p.hact_save) ? p.hact_save + goff / 8 : nullptr);
     }
     fence_proxy_async_smem();
     tc_fence_before_sync();
@@ -312,22 +319,22 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
         mma_commit(&bar[BF2]);
     }
     __syncwarp();
-    mbar_wait(&bar[BF2], 0);
-    tc_fence_after_sync();
     {
-        float v[64];
-        ld_acc64(tmem, L, ACC0, v);
+        float v[32], b[32];
+        ldg32(p.l2_b + c0, b);
+        mbar_wait(&bar[BF2], 0);
+        tc_fence_after_sync();
+        ld_acc32(tmem, L, ACC0, v);
         if (rv) {
-            const uint64_t didx = (uint64_t)grow * 128 + 64 * hf;
-            float4* g = reinterpret_cast<float4*>(p.y + grow * 128 + 64 * hf);
+            float4* g = reinterpret_cast<float4*>(p.y + goff);
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
-                float t = v[j] + __ldg(p.l2_b + 64 * hf + j);
-                if (dropping) t *= dropout_scale(dseed, p.drop.stream + 3, didx + j, p.drop.thresh, p.drop.inv_keep);
+            for (int j = 0; j < 32; ++j) {
+                float t = v[j] + b[j];
+                if (DROP) t *= dropout_scale(dseed, p.drop.stream + 3, (uint64_t)goff + j, p.drop.thresh, p.drop.inv_keep);
                 v[j] = xr[j] + t;
             }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) g[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 8; ++j) g[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
     }
     tc_fence_before_sync();
@@ -400,11 +407,13 @@ extern "C" int sd_enc_layer_fwd(const sd_enc_layer_desc* d, void* stream) {
     p.drop = make_dropout(d->dropout_p, d->dropout_seed, d->dropout_stream);
     static bool configured = false;
     if (!configured) {
-        SD_CUDA(cudaFuncSetAttribute(enc_layer_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
+        SD_CUDA(cudaFuncSetAttribute(enc_layer_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
+        SD_CUDA(cudaFuncSetAttribute(enc_layer_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
         configured = true;
     }
     const int tiles = ceil_div(d->B, p.spt);
-    enc_layer_fwd_kernel<<<tiles, LNT, SMEM_DYN, (cudaStream_t)stream>>>(tmW, p);
+    if (p.drop.thresh != 0) enc_layer_fwd_kernel<true><<<tiles, LNT, SMEM_DYN, (cudaStream_t)stream>>>(tmW, p);
+    else enc_layer_fwd_kernel<false><<<tiles, LNT, SMEM_DYN, (cudaStream_t)stream>>>(tmW, p);
     SD_LAUNCH_CHECK();
     return SD_OK;
 }

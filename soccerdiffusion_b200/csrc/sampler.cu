@@ -1274,11 +1274,12 @@ void fill_args(sd_plan* p, SamplerArgs& a) {
 }
 }  // namespace
 
-extern "C" int sd_plan_sample(sd_plan* p, const float* x_T, float* x_out, float* eps_trace, int denormalize,
+extern "C" int sd_plan_sample(sd_plan* p, const float* x_T, float* x_out, float* eps_trace, int denormalize, int B,
                               void* stream) {
     if (!p) return SD_ERR_NO_PLAN;
     if (!x_T || !x_out) return SD_ERR_BAD_ARG;
     if (p->ctx_B <= 0 || p->num_steps <= 0) return SD_ERR_BAD_ARG;  // set_context / set_schedule first
+    if (B != p->ctx_B) return SD_ERR_BAD_ARG;   // x_T / x_out hold B trajectories: must be the context's batch
     SamplerArgs a{};
     fill_args(p, a);
     a.tok_mode = 0; a.t_ptr = nullptr; a.t_is_float = 0;
@@ -1302,11 +1303,11 @@ extern "C" int sd_plan_set_debug_stamps(sd_plan* p, long long* device_buffer) {
 
 extern "C" int sd_plan_last_sampler(const sd_plan* p) { return p ? p->last_sampler : SD_ERR_NO_PLAN; }
 
-extern "C" int sd_plan_denoise(sd_plan* p, const float* x, const void* t, int t_is_float, float* eps_out,
+extern "C" int sd_plan_denoise(sd_plan* p, const float* x, const void* t, int t_is_float, float* eps_out, int B,
                                void* stream) {
     if (!p) return SD_ERR_NO_PLAN;
     if (!x || !t || !eps_out) return SD_ERR_BAD_ARG;
-    if (p->ctx_B <= 0) return SD_ERR_BAD_ARG;
+    if (p->ctx_B <= 0 || B != p->ctx_B) return SD_ERR_BAD_ARG;
     SamplerArgs a{};
     fill_args(p, a);
     a.num_steps = 1; a.tok_mode = 1; a.t_ptr = t; a.t_is_float = t_is_float;

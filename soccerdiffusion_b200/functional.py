@@ -190,6 +190,7 @@ def _zero_grads(params):
         if ip:
             bufs.append(p.grad)
             rets.append(None)
+            runtime.mark_grad_written(p)   # autograd never sees this gradient: tell the optimizer it exists
         else:
             v = flat[off: off + p.numel()].view_as(p)
             off += p.numel()

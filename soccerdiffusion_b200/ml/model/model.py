@@ -42,17 +42,42 @@ class _Plan:
         self.context_sig = None
         self.schedule_sig = None
 
+    def close(self):
+        if self.handle:
+            handle, self.handle = self.handle, None
+            _lib.check(_lib.lib().sd_plan_destroy(handle), "sd_plan_destroy")
+
     def __del__(self):
+        # interpreter shutdown may already have torn the library binding down: that (and only that) is ignored
         try:
-            if self.handle:
-                _lib.lib().sd_plan_destroy(self.handle)
-                self.handle = None
-        except Exception:
+            self.close()
+        except (AttributeError, TypeError, ImportError):
             pass
 
 
 def _sig(tensors):
-    return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
+    """Identity of the CONTENTS of ``tensors`` as far as the host can know it, or None when it cannot.
+
+    libsd_b200 writes through raw pointers, which never bumps ``Tensor._version``, and the caching allocator hands the
+    same addresses out again tick after tick — so (pointer, version, shape) alone would call two different contexts
+    equal.  Tensors produced by this package carry a process-wide generation stamp (``runtime.stamp``); weights carry
+    the optimizer generation (``runtime.weights_generation``, advanced by every FusedAdamW step / graph replay).
+    A tensor without a stamp (a caller's own ``torch.randn`` context, train.py:222) gives None: never cached."""
+    from soccerdiffusion_b200 import runtime
+
+    out = []
+    for t in tensors:
+        gen = getattr(t, "_sd_gen", None)
+        if gen is None:
+            return None
+        out.append((t.data_ptr(), t._version, tuple(t.shape), gen))
+    return tuple(out) + (runtime.weights_generation(),)
+
+
+def _weights_sig(tensors):
+    from soccerdiffusion_b200 import runtime
+
+    return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors) + (runtime.weights_generation(),)
 
 
 class End2EndDiffusionTransformer(nn.Module):
@@ -182,7 +207,7 @@ class End2EndDiffusionTransformer(nn.Module):
             jobs.append((self.game_state_encoder, input_data["game_state"], True))
         n_side = sum(1 for _, x, main in jobs if not main)
         if not (runtime.concurrent_encoders() and n_side >= 1 and len(jobs) >= 2 and all(x.is_cuda for _, x, _ in jobs)):
-            return [enc(x) for enc, x, _ in jobs]
+            return [runtime.stamp(enc(x)) for enc, x, _ in jobs]
         cur = torch.cuda.current_stream()
         side = runtime.side_streams(cur.device, n_side)
         out: list = [None] * len(jobs)
@@ -203,7 +228,7 @@ class End2EndDiffusionTransformer(nn.Module):
         for i, (_, _, main) in enumerate(jobs):
             if not main:
                 out[i].record_stream(cur)   # allocated on a side stream, consumed on the caller's
-        return out
+        return [runtime.stamp(o) for o in out]
 
     def forward(
         self, input_data: dict[str, torch.Tensor], noisy_action_predictions: torch.Tensor, step: torch.Tensor
@@ -248,7 +273,7 @@ class End2EndDiffusionTransformer(nn.Module):
             self._plans[key] = plan
         tensors = [dag.embedding.weight, dag.embedding.bias, dag.fc_out.weight, dag.fc_out.bias,
                    self.step_encoding.token, self.mean, self.std, *dag.transformer_decoder.tensors()]
-        sig = _sig(tensors)
+        sig = _weights_sig(tensors)
         if plan.weights_sig != sig:
             st = _lib.stream_ptr()
             lib = _lib.lib()
@@ -278,9 +303,12 @@ class End2EndDiffusionTransformer(nn.Module):
 
     def _set_context(self, plan: _Plan, context: list[torch.Tensor]):
         sig = _sig(context)
-        if plan.context_sig == sig:
+        if sig is not None and plan.context_sig == sig:
             return
         B = context[0].shape[0]
+        for c in context:
+            if c.shape[0] != B:
+                raise RuntimeError(f"context tensors disagree on the batch size: {[tuple(c.shape) for c in context]}")
         d = self.hidden_dim
         lens = [c.shape[1] for c in context]
         Mc = sum(lens)
@@ -303,6 +331,8 @@ class End2EndDiffusionTransformer(nn.Module):
         from soccerdiffusion_b200.ml.model.misc import normalize_steps
 
         B, T, J = x.shape
+        if context[0].shape[0] != B:
+            raise RuntimeError(f"batch size of the context ({context[0].shape[0]}) and of the noisy actions ({B}) differ")
         plan = self._plan_for(sum(c.shape[1] for c in context), T)
         self._set_context(plan, context)
         steps = normalize_steps(step, x.device)
@@ -311,7 +341,7 @@ class End2EndDiffusionTransformer(nn.Module):
         xin = x.float().contiguous()
         out = torch.empty_like(xin)
         _lib.check(_lib.lib().sd_plan_denoise(plan.handle, xin.data_ptr(), steps.data_ptr(),
-                                              1 if steps.dtype == torch.float32 else 0, out.data_ptr(),
+                                              1 if steps.dtype == torch.float32 else 0, out.data_ptr(), B,
                                               _lib.stream_ptr()), "sd_plan_denoise")
         ops._count()
         return out
@@ -330,6 +360,8 @@ class End2EndDiffusionTransformer(nn.Module):
         if num_inference_steps is not None:
             scheduler.set_timesteps(num_inference_steps)
         B, T, J = x_T.shape
+        if context[0].shape[0] != B:
+            raise RuntimeError(f"batch size of the context ({context[0].shape[0]}) and of x_T ({B}) differ")
         plan = self._plan_for(sum(c.shape[1] for c in context), T)
         _lib.check(_lib.lib().sd_plan_set_sampler(plan.handle, {"auto": 0, "cta": 1, "cluster": 2}[sampler]),
                    "sd_plan_set_sampler")
@@ -348,7 +380,7 @@ class End2EndDiffusionTransformer(nn.Module):
         out = torch.empty_like(xin)
         trace = torch.empty((len(ts), B, T, J), device=xin.device, dtype=torch.float32) if return_trace else None
         _lib.check(_lib.lib().sd_plan_sample(plan.handle, xin.data_ptr(), out.data_ptr(), _lib.ptr(trace),
-                                             1 if denormalize else 0, _lib.stream_ptr()), "sd_plan_sample")
+                                             1 if denormalize else 0, B, _lib.stream_ptr()), "sd_plan_sample")
         ops._count()
         self.last_sampler = {1: "cta", 2: "cluster"}.get(_lib.lib().sd_plan_last_sampler(plan.handle), "?")
         return (out, trace) if return_trace else out

@@ -26,6 +26,10 @@ class GraphedTrainStep:
         self.seed_counter = runtime.device_seed_counter(next(model.parameters()).device)
         self.direct_grads = direct_grads
         self.launches_per_replay = 0
+        # Warm-up must leave no trace (the reference's loop takes exactly epochs * len(dataloader) optimizer and
+        # OneCycleLR steps, train.py:172,239-240): parameters, AdamW moments and step counters, BatchNorm running
+        # statistics, the LR schedule and the dropout seed counter are snapshotted here and restored after the capture.
+        snap = self._snapshot()
         # warm-up on a side stream: allocations, cuDNN autotuning, lazy kernel attributes, NCCL communicators
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -45,7 +49,40 @@ class GraphedTrainStep:
             self.loss = self._body()
         self.launches_per_replay = ops.launches() - n0
         self.opt.rollback_captured_step()      # the capture executed nothing: undo its step-counter increment
-        self.warmup_steps = warmup_steps       # optimizer steps already taken on ``example_batch``
+        self._restore(snap)
+        self.warmup_steps = 0                  # optimizer / scheduler steps left behind by the constructor: none
+
+    def _snapshot(self):
+        import copy
+
+        flats = [{k: f[k].clone() for k in ("p", "m", "v")} if f is not None else None for f in self.opt._flat]
+        steps = [f["step"] if f is not None else None for f in self.opt._flat]
+        groups = [{k: copy.deepcopy(v) for k, v in g.items() if k != "params"} for g in self.opt.param_groups]
+        buffers = [b.clone() for b in self.model.buffers()]
+        lrs = copy.deepcopy(self.lrs.state_dict()) if self.lrs is not None else None
+        return dict(flats=flats, steps=steps, groups=groups, buffers=buffers, lrs=lrs, seed=self.seed_counter.clone(),
+                    opt_called=getattr(self.opt, "_opt_called", False))
+
+    def _restore(self, snap):
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            for f, saved, step in zip(self.opt._flat, snap["flats"], snap["steps"]):
+                if f is None:
+                    continue
+                for k in ("p", "m", "v"):
+                    f[k].copy_(saved[k])
+                f["g"].zero_()
+                f["step"] = step
+                f["step_t"].fill_(float(step))
+            for g, saved in zip(self.opt.param_groups, snap["groups"]):
+                g.update(saved)
+            for b, saved in zip(self.model.buffers(), snap["buffers"]):
+                b.copy_(saved)
+            self.seed_counter.copy_(snap["seed"])
+        if self.lrs is not None:
+            self.lrs.load_state_dict(snap["lrs"])
+            # OneCycleLR also mirrors its state into the param groups (lr / betas): restored above
+        runtime.bump_weights_generation()
 
     def _body(self):
         b = self.static
@@ -75,6 +112,13 @@ class GraphedTrainStep:
 
     def __call__(self, batch: dict) -> torch.Tensor:
         """One training iteration on ``batch`` (device tensors); returns the (static) loss tensor."""
+        if any(tuple(batch[k].shape) != tuple(v.shape) or batch[k].dtype != v.dtype for k, v in self.static.items()):
+            # e.g. the smaller last batch of an epoch (train.py:193-199): the graph is shape-specialised, this step runs
+            # kernel by kernel
+            from soccerdiffusion_b200.ml.training.step import train_step
+
+            return train_step(self.model, self.opt, self.sch, self.model, batch, lr_scheduler=self.lrs,
+                              decoder_pretraining=self.pretrain, group=self.group, data_parallel=self.dp)
         for k, v in self.static.items():
             v.copy_(batch[k], non_blocking=True)
         self.opt.prepare_captured_step()
@@ -83,4 +127,5 @@ class GraphedTrainStep:
         self.opt._opt_called = True            # the replayed graph contains the optimizer step
         if self.lrs is not None:
             self.lrs.step()
+        runtime.bump_weights_generation()
         return self.loss

@@ -48,17 +48,50 @@ class FusedAdamW(torch.optim.Optimizer):
             flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
             flat_m = torch.zeros(total, device=dev, dtype=torch.float32)
             flat_v = torch.zeros(total, device=dev, dtype=torch.float32)
+            # ONE step tensor per group, shared by the state of all its parameters and updated in place: state_dict()
+            # (the reference checkpoints optimizer_state_dict, train.py:244-252) always carries the true step count,
+            # whichever of step() / step_captured() ran, without 296 tensor constructions per iteration
+            step_t = torch.tensor(0.0)
             for p, o in zip(ps, offs):
                 n = p.numel()
                 flat_p[o:o + n].copy_(p.data.reshape(-1))
                 p.data = flat_p[o:o + n].view(p.shape)
                 p.grad = flat_g[o:o + n].view(p.shape)
-                self.state[p] = dict(step=torch.tensor(0.0), exp_avg=flat_m[o:o + n].view(p.shape),
+                self.state[p] = dict(step=step_t, exp_avg=flat_m[o:o + n].view(p.shape),
                                      exp_avg_sq=flat_v[o:o + n].view(p.shape))
-            self._flat.append(dict(p=flat_p, g=flat_g, m=flat_m, v=flat_v, params=ps, offs=offs, step=0))
+                # torch.optim.AdamW skips parameters whose .grad is None (unused this step: e.g. every encoder under
+                # --decoder-pretraining, train.py:221-224).  The flat gradient views always exist, so "received a gradient
+                # this step" is tracked instead: by this hook for gradients accumulated by autograd, by
+                # functional._zero_grads (runtime.mark_grad_written) for kernels that write p.grad in place.
+                p.register_post_accumulate_grad_hook(self._mark)
+            self._flat.append(dict(p=flat_p, g=flat_g, m=flat_m, v=flat_v, params=ps, offs=offs, step=0, step_t=step_t,
+                                   index={id(p): i for i, p in enumerate(ps)}))
+        self._touched: set[int] = set()
+        self._frozen_runs = None
+        from soccerdiffusion_b200 import runtime
+
+        runtime.register_grad_listener(self._mark)
+
+    def _mark(self, p):
+        self._touched.add(id(p))
+
+    def _runs(self, f):
+        """Contiguous [begin, end) element ranges of the flat buffers covering exactly the parameters that received a
+        gradient since the last zero_grad() (all of them in ordinary training: one range = one launch)."""
+        runs, cur = [], None
+        for p, o in zip(f["params"], f["offs"]):
+            if id(p) in self._touched:
+                end = o + _round_up(p.numel(), 4)
+                if cur is not None and cur[1] == o:
+                    cur[1] = end
+                else:
+                    cur = [o, end]
+                    runs.append(cur)
+        return [tuple(r) for r in runs]
 
     # gradients stay allocated so autograd accumulates into the flat buffer (set_to_none would drop the views)
     def zero_grad(self, set_to_none: bool = False):
+        self._touched.clear()
         for f in self._flat:
             if f is None:
                 continue
@@ -78,12 +111,14 @@ class FusedAdamW(torch.optim.Optimizer):
         # a caller may have replaced p.grad (e.g. zero_grad(set_to_none=True) by a framework): fold it back
         for p, o in zip(f["params"], f["offs"]):
             want = f["g"].data_ptr() + 4 * o
-            if p.grad is None:
+            if p.grad is None:   # no gradient this step: skipped like torch.optim.AdamW does (the view is restored)
+                self._touched.discard(id(p))
                 f["g"][o:o + p.numel()].zero_()
                 p.grad = f["g"][o:o + p.numel()].view(p.shape)
             elif p.grad.data_ptr() != want:
                 f["g"][o:o + p.numel()].copy_(p.grad.reshape(-1))
                 p.grad = f["g"][o:o + p.numel()].view(p.shape)
+                self._touched.add(id(p))
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
@@ -96,11 +131,14 @@ class FusedAdamW(torch.optim.Optimizer):
                 continue
             self._gather_stray_grads(f)
             f["step"] += 1
+            f["step_t"].fill_(float(f["step"]))
             b1, b2 = group["betas"]
-            ops.adamw_step(f["p"], f["g"], f["m"], f["v"], float(group["lr"]), float(b1), float(b2),
-                           float(group["eps"]), float(group["weight_decay"]), f["step"], grad_scale)
-            for p in f["params"]:
-                self.state[p]["step"] = torch.tensor(float(f["step"]))
+            for a, b in self._runs(f):
+                ops.adamw_step(f["p"][a:b], f["g"][a:b], f["m"][a:b], f["v"][a:b], float(group["lr"]), float(b1), float(b2),
+                               float(group["eps"]), float(group["weight_decay"]), f["step"], grad_scale)
+        from soccerdiffusion_b200 import runtime
+
+        runtime.bump_weights_generation()
         return loss
 
     # ---- CUDA-graph friendly stepping: hyper-parameters travel through device memory ------------------------
@@ -111,9 +149,13 @@ class FusedAdamW(torch.optim.Optimizer):
             if f is None:
                 continue
             if "hp_host" not in f:
-                f["hp_host"] = torch.empty(8, dtype=torch.float32).pin_memory()
+                # PAGEABLE on purpose: cudaMemcpyAsync from pageable memory stages the bytes before it returns, so the
+                # buffer can be rewritten for the next step while earlier graph replays are still queued (a pinned
+                # buffer would be read by the DMA engine later — the host runs many steps ahead of the device)
+                f["hp_host"] = torch.empty(8, dtype=torch.float32)
                 f["hp_dev"] = torch.empty(8, dtype=torch.float32, device=f["p"].device)
             f["step"] += 1
+            f["step_t"].fill_(float(f["step"]))
             b1, b2 = group["betas"]
             t = f["step"]
             bc1 = 1.0 - float(b1) ** t
@@ -127,6 +169,7 @@ class FusedAdamW(torch.optim.Optimizer):
         for f in self._flat:
             if f is not None:
                 f["step"] -= 1
+                f["step_t"].fill_(float(f["step"]))
 
     @torch.no_grad()
     def step_captured(self):
@@ -137,7 +180,11 @@ class FusedAdamW(torch.optim.Optimizer):
             if "hp_dev" not in f:
                 raise RuntimeError("call prepare_captured_step() once before capturing step_captured()")
             self._gather_stray_grads(f)
-            ops.adamw_step_dev(f["p"], f["g"], f["m"], f["v"], f["hp_dev"])
+            for a, b in self._runs(f):
+                ops.adamw_step_dev(f["p"][a:b], f["g"][a:b], f["m"][a:b], f["v"][a:b], f["hp_dev"])
+        from soccerdiffusion_b200 import runtime
+
+        runtime.bump_weights_generation()
 
     # torch's loader would replace the state tensors by copies; keep the flat views instead
     def load_state_dict(self, state_dict):
@@ -158,6 +205,9 @@ class FusedAdamW(torch.optim.Optimizer):
                 self.state[p]["exp_avg"].copy_(st["exp_avg"])
                 self.state[p]["exp_avg_sq"].copy_(st["exp_avg_sq"])
                 step = max(step, int(st["step"]))
-                self.state[p]["step"] = torch.tensor(float(int(st["step"])))
             if f is not None:
                 f["step"] = step
+                f["step_t"].fill_(float(step))
+        from soccerdiffusion_b200 import runtime
+
+        runtime.bump_weights_generation()

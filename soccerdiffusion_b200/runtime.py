@@ -146,3 +146,51 @@ def make_cfg(training: bool, dropout_p: float | None = None):
 
     p = (DROPOUT_P if dropout_p is None else dropout_p) if training else 0.0
     return RunCfg(precision=_precision, p=p, seed=next_seed() if p > 0.0 else 0, stream_base=0)
+
+
+# ---- content generations (what the plan caches of ml/model/model.py key on) --------------------------------------------
+_gen = 0
+_weights_gen = 0
+
+
+def stamp(t):
+    """Marks ``t`` as freshly produced by this package (a new process-wide generation number): caches keyed on
+    tensor identity treat it as new content even when the allocator reuses its address."""
+    global _gen
+    _gen += 1
+    try:
+        t._sd_gen = _gen
+    except AttributeError:
+        pass
+    return t
+
+
+def bump_weights_generation():
+    """Called by everything that rewrites parameters through raw pointers (FusedAdamW steps, graph replays)."""
+    global _weights_gen
+    _weights_gen += 1
+
+
+def weights_generation() -> int:
+    return _weights_gen
+
+
+# ---- "this parameter's gradient was written in place" notifications (functional._zero_grads -> FusedAdamW) ---------------
+import weakref
+
+_grad_listeners: list = []
+
+
+def register_grad_listener(bound_method):
+    _grad_listeners.append(weakref.WeakMethod(bound_method))
+
+
+def mark_grad_written(p):
+    alive = False
+    for ref in _grad_listeners:
+        fn = ref()
+        if fn is not None:
+            alive = True
+            fn(p)
+    if not alive and _grad_listeners:
+        _grad_listeners.clear()

@@ -438,15 +438,27 @@ def test_graphed_train_step_matches_eager_steps():
     eager = []
     for b in [batches[0]] * 3 + batches[1:]:
         eager.append(train_step(m1, o1, sch, n1, b, lr_scheduler=l1, noise=noise, timesteps=t).item())
-    # graphed: 3 warm-up steps on batches[0] inside the constructor, then replays
+    # graphed: the constructor's 3 warm-up steps leave NO trace (parameters, moments, step counters, BatchNorm running
+    # statistics, LR schedule are restored), then the same 6 iterations as replays
     m2, _ = synth_model(hp, seed)
     m2.train()
     o2 = FusedAdamW(m2.parameters(), lr=1e-3)
     l2 = torch.optim.lr_scheduler.OneCycleLR(o2, max_lr=1e-3, total_steps=20)
+    before = {n: p.detach().clone() for n, p in m2.state_dict().items()}
+    lr_before = o2.param_groups[0]["lr"]
     g = GraphedTrainStep(m2, o2, sch, batches[0], lr_scheduler=l2, warmup_steps=3, noise=noise, timesteps=t)
-    got = [g(b).item() for b in batches[1:]]
-    for a, b_ in zip(got, eager[3:]):
+    for n, v in m2.state_dict().items():
+        assert torch.equal(v, before[n]), n
+    assert o2.param_groups[0]["lr"] == lr_before and l2.last_epoch == 0
+    assert all(float(st["step"]) == 0.0 for st in o2.state.values())
+    got = [g(b).item() for b in [batches[0]] * 3 + batches[1:]]
+    for a, b_ in zip(got, eager):
         assert abs(a - b_) < 1e-5 * abs(b_), (got, eager)
+    # the optimizer state a checkpoint would carry counts the graph-replayed steps (state_dict round trip)
+    assert all(float(st["step"]) == 6.0 for st in o2.state_dict()["state"].values())
+    # a batch of another size (the smaller last batch of an epoch) runs kernel by kernel instead of raising
+    small = {k: v[:2] for k, v in batches[1].items()}
+    assert torch.isfinite(g(small)).item()
     for (n, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
         # bias corrections are float32 on the host vs double inside sd_adamw_step, and Adam's m/sqrt(v) amplifies
         # rounding on near-zero gradients: compare absolutely (the updates themselves are ~lr = 1e-3 per step)
