@@ -143,6 +143,41 @@ __device__ __forceinline__ void mma_a_k_b_mn(uint32_t tmem_d, uint32_t a_addr, u
     }
 }
 
+// ---- cheap transcendental forms for the bf16 path (results are rounded to bf16 right after: |error| << 2^-9) ---------------
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// erf(|z|) by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7): two MUFU ops and seven FMAs instead of erff's ~40
+// instructions and two branches; e2 = exp(-z^2) is returned for the derivative of GELU
+__device__ __forceinline__ float erf_pos(float z, float& e2) {
+    const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    e2 = ex2_approx(-1.4426950408889634f * z * z);
+    return fmaf(-poly * t, e2, 1.0f);
+}
+// exact-form (erf) GELU of activation="gelu" (encoder/base.py:36, decoder.py:31), bf16-path evaluation
+__device__ __forceinline__ float gelu_fast(float x) {
+    float e2;
+    const float er = erf_pos(fabsf(x) * 0.70710678118654752440f, e2);
+    return 0.5f * x * (1.0f + copysignf(er, x));
+}
+// d/dx gelu(x) = Phi(x) + x phi(x)
+__device__ __forceinline__ float gelu_fast_grad(float x) {
+    float e2;   // exp(-x^2 / 2)
+    const float er = erf_pos(fabsf(x) * 0.70710678118654752440f, e2);
+    return fmaf(0.39894228040143267794f * x, e2, 0.5f * (1.0f + copysignf(er, x)));
+}
+
 // row exchange through shared memory: the four threads that share a row (tid & 127 + 128 k) combine a partial value.
 // `red` alternates between two [512]-float arrays so that consecutive exchanges need one barrier each.
 __device__ __forceinline__ float row_sum(float v, float* red, int tid) {

@@ -31,7 +31,13 @@ constexpr int OFF_QS = 2 * LTILE;     // Q  [token][feature]            -> hidde
 constexpr int OFF_KS = 4 * LTILE;     // K  [token][feature]
 constexpr int OFF_VT = 6 * LTILE;     // V^T [feature][token]
 constexpr int OFF_W = 8 * LTILE;      // weight ring: slot A = tiles 0,1 ; slot B = tiles 2,3
-constexpr int SMEM_DYN = 12 * LTILE + 1024;
+constexpr int OFF_U = 12 * LTILE;     // sample one-hot tile (softmax mask by MMA, see below)
+constexpr int SMEM_DYN = 13 * LTILE + 1024;
+// Softmax mask on the tensor core: row r of U holds 32 at column (sample of r inside the tile) for valid rows, zeros for
+// padding rows; one extra k step S += U U^T adds 1024 to every (query, key) pair of the SAME sample.  After the row
+// maximum is subtracted, keys of other samples and padding keys sit 1024 below it and their exponentials flush to
+// exactly zero: the softmax loops carry no per-element mask logic (they are issue-bound).
+constexpr float U_VAL = 32.0f;
 
 enum { BW0 = 0, BQ = 6, BK, BV, BOUT, BF1, BF2, BS0, BP0 = BS0 + 8, NBAR = BP0 + 8 };
 
@@ -109,6 +115,14 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = rv ? fmaf((xr[j] - mean) * rstd, ga[j], be[j]) : 0.f;
         st_row32(smem + OFF_XN, L, v, (rv && p.xn1_save) ? p.xn1_save + goff / 8 : nullptr);
+        if (L.cq == 0) {   // one-hot sample indicator of this row: columns 0..15 of the U tile (spt <= 16)
+            float u[16];
+            const int s_of_r = r / p.S;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) u[j] = (rv && j == s_of_r) ? U_VAL : 0.f;
+            *reinterpret_cast<uint4*>(smem + OFF_U + sw128_chunk_off(r, 0)) = pack8_bf16(u);
+            *reinterpret_cast<uint4*>(smem + OFF_U + sw128_chunk_off(r, 1)) = pack8_bf16(u + 8);
+        }
     }
     fence_proxy_async_smem();
     tc_fence_before_sync();
@@ -173,6 +187,8 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
         const uint64_t da = smem_desc_k_sw128(sbase + OFF_QS + (hoff >> 6) * LTILE) + ((hoff & 63) >> 3);
         const uint64_t db = smem_desc_k_sw128(sbase + OFF_KS + (hoff >> 6) * LTILE) + ((hoff & 63) >> 3);
         for (int j = 0; j < dh / 16; ++j) mma_bf16_ss(tmem + ((h & 1) ? ACC1 : ACC0), da + 2 * j, db + 2 * j, idS, j > 0);
+        const uint64_t du = smem_desc_k_sw128(sbase + OFF_U);
+        mma_bf16_ss(tmem + ((h & 1) ? ACC1 : ACC0), du, du, idS, 1u);   // + 1024 on same-sample pairs
         mma_commit(&bar[BS0 + h]);
     };
     if (tid == 0) {
@@ -183,7 +199,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
     __syncwarp();
     const float sc = rsqrtf((float)dh) * 1.4426950408889634f;   // softmax scale * log2(e)
     const int s_idx = r / S;                                     // sample of this row inside the tile
-    const int lo = s_idx * S, hi = lo + S;                       // its keys
+    const int lo = s_idx * S;                                    // its first key
     const int t_tok = r - lo;
 #pragma unroll 1
     for (int h = 0; h < H; ++h) {
@@ -191,25 +207,22 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
         mbar_wait(&bar[BS0 + h], 0);
         tc_fence_after_sync();
         ld_acc32(tmem, L, (h & 1) ? ACC1 : ACC0, v);
-        float mx = -INFINITY;
+        float mx = v[0];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const int m = c0 + j;
-            if (m >= lo && m < hi) mx = fmaxf(mx, v[j]);
-        }
-        mx = row_max(mx, red[0], tid);
+        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+        mx = row_max(mx, red[0], tid) * sc;
         float sum = 0.f;
-        const uint64_t didx = (((uint64_t)(samp0 + s_idx) * H + h) * S + t_tok) * (uint64_t)S;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-            const int m = c0 + j;
-            float e = 0.f;
-            if (rv && m >= lo && m < hi) {
-                e = exp2f((v[j] - mx) * sc);
-                sum += e;
-                if (DROP) e *= dropout_scale(dseed, p.drop.stream, didx + (m - lo), p.drop.thresh, p.drop.inv_keep);
-            }
-            v[j] = e;
+            v[j] = ex2_approx(fmaf(v[j], sc, -mx));   // exactly 0 for keys of other samples / padding keys
+            sum += v[j];
+        }
+        if (DROP) {
+            // element ((b*H + h)*S + t)*S + m of the attention-probability dropout stream; m - lo may be out of range for
+            // keys whose probability is zero anyway
+            const uint64_t didx = (((uint64_t)(samp0 + s_idx) * H + h) * S + t_tok) * (uint64_t)S + (uint64_t)(long long)(c0 - lo);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= dropout_scale(dseed, p.drop.stream, didx + j, p.drop.thresh, p.drop.inv_keep);
         }
         sum = row_sum(sum, red[1], tid);
         if (L.cq == 0) rsum[h][r] = rv ? 1.0f / sum : 0.f;
@@ -303,7 +316,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
         ld_acc32(tmem, L, ACC1, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-            float t = gelu_erf(v[j] + b[j]);
+            float t = gelu_fast(v[j] + b[j]);
             if (DROP) t *= dropout_scale(dseed, p.drop.stream + 2, (uint64_t)goff + j, p.drop.thresh, p.drop.inv_keep);
             v[j] = rv ? t : 0.f;
         }
@@ -378,7 +391,7 @@ extern "C" int sd_pack_weights_bf16(const sd_pack_args* a, int nseg, void* strea
 }
 
 extern "C" int sd_enc_layer_supported(int d, int ff, int S, int H) {
-    if (d != 128 || ff != 128 || S < 1 || S > 128 || H < 1 || H > 8 || d % H != 0) return 0;
+    if (d != 128 || ff != 128 || S < 8 || S > 128 || H < 1 || H > 8 || d % H != 0) return 0;   // S >= 8: <= 16 samples per tile
     const int dh = d / H;
     if (dh != 16 && dh != 32 && dh != 64) return 0;
     return tensor_map_encoder() != nullptr ? 1 : 0;

@@ -44,7 +44,7 @@ def enc_layer_ref(x, P, B, S, H):
     return y, dict(x1=x1, xn1=xn1, attn=attn, xn2=xn2, hact=hact)
 
 
-@pytest.mark.parametrize("B,S,H", [(5, 100, 4), (30, 10, 8), (3, 20, 4), (2, 128, 4), (13, 10, 4), (1, 7, 2)])
+@pytest.mark.parametrize("B,S,H", [(5, 100, 4), (30, 10, 8), (3, 20, 4), (2, 128, 4), (13, 10, 4), (1, 8, 2), (5, 9, 4)])
 def test_enc_layer_fwd_matches_fp32_restatement(ops, B, S, H):
     d = 128
     assert ops.enc_layer_supported(d, d, S, H)
