@@ -313,6 +313,36 @@ typedef struct sd_enc_layer_desc {
 int sd_enc_layer_supported(int d, int ff, int S, int H);
 int sd_enc_layer_fwd(const sd_enc_layer_desc* desc, void* stream);
 
+/* Backward of the same layer, data path, as ONE kernel (autograd of the layer above): dy -> dx (fp32 [B*S][128], may
+ * alias), recomputing hpre, Q, K, V and the softmax from the forward's saves x (layer input), x1, xn1, xn2.
+ * Outputs for the weight-gradient GEMMs (bf16): g2 = dy*mask3, dhpre, g1 = dx1*mask1 ([B*S][128]) and dqkv ([B*S][384]:
+ * dq | dk | dv).  LayerNorm weight / bias gradients are ACCUMULATED into g_n1_w, g_n1_b, g_n2_w, g_n2_b (fp32 [128]). */
+typedef struct sd_enc_layer_bwd_desc {
+    const float* dy; float* dx;
+    const float* x; const float* x1; const void* xn1; const void* xn2;
+    void* g2; void* dhpre; void* g1; void* dqkv;
+    float *g_n1_w, *g_n1_b, *g_n2_w, *g_n2_b;
+    int B, S, H;
+    const void* w_packed; int w_rows_total; int w_row0;
+    const float *in_b, *l1_b, *n1_w, *n2_w;
+    float dropout_p; unsigned long long dropout_seed; unsigned int dropout_stream;
+} sd_enc_layer_bwd_desc;
+int sd_enc_layer_bwd(const sd_enc_layer_bwd_desc* desc, void* stream);
+
+/* Weight gradients of linear layers from bf16 activations, TMA-fed tcgen05 GEMMs with split K over the tokens:
+ *   for each job j:  dW_j[n][k] += sum_t G_j[t][n] * X_j[t][k]   and (optionally)   db_j[n] += sum_t G_j[t][n]
+ * G_j: bf16 [rows][ldg] (128 columns starting at column g_col0), X_j: bf16 [rows][ldx] (128 columns starting at column
+ * x_col0), dW_j: fp32 [128][ldw], db_j: fp32 [128] or NULL.  All jobs share `rows`.  The bias gradient is one more MMA
+ * against a tile of ones.  Replaces the autograd of nn.Linear / packed in_proj weights (torch/nn/functional.py:5849). */
+#define SD_WGRAD_MAX_JOBS 8
+typedef struct sd_wgrad_job {
+    const void* G; long long ldg; int g_col0;
+    const void* X; long long ldx; int x_col0;
+    float* dW; long long ldw;
+    float* db;
+} sd_wgrad_job;
+int sd_wgrad_bf16(const sd_wgrad_job* jobs, int n_jobs, long long rows, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,6 +76,24 @@ class EncLayerDesc(C.Structure):
                 ("dropout_p", c_fl), ("dropout_seed", c_ull), ("dropout_stream", c_u)]
 
 
+class EncLayerBwdDesc(C.Structure):
+    _fields_ = [("dy", c_f), ("dx", c_f), ("x", c_f), ("x1", c_f), ("xn1", c_f), ("xn2", c_f),
+                ("g2", c_f), ("dhpre", c_f), ("g1", c_f), ("dqkv", c_f),
+                ("g_n1_w", c_f), ("g_n1_b", c_f), ("g_n2_w", c_f), ("g_n2_b", c_f),
+                ("B", c_i), ("S", c_i), ("H", c_i),
+                ("w_packed", c_f), ("w_rows_total", c_i), ("w_row0", c_i),
+                ("in_b", c_f), ("l1_b", c_f), ("n1_w", c_f), ("n2_w", c_f),
+                ("dropout_p", c_fl), ("dropout_seed", c_ull), ("dropout_stream", c_u)]
+
+
+WGRAD_MAX_JOBS = 8
+
+
+class WgradJob(C.Structure):
+    _fields_ = [("G", c_f), ("ldg", c_ll), ("g_col0", c_i), ("X", c_f), ("ldx", c_ll), ("x_col0", c_i),
+                ("dW", c_f), ("ldw", c_ll), ("db", c_f)]
+
+
 # name -> argtypes (restype is always int unless noted); mirrors include/sd_b200.h one to one
 SIGNATURES = {
     "sd_abi_version": [],
@@ -136,6 +154,8 @@ SIGNATURES = {
     "sd_pack_weights_bf16": [C.POINTER(PackArgs), c_i, c_f],
     "sd_enc_layer_supported": [c_i, c_i, c_i, c_i],
     "sd_enc_layer_fwd": [C.POINTER(EncLayerDesc), c_f],
+    "sd_enc_layer_bwd": [C.POINTER(EncLayerBwdDesc), c_f],
+    "sd_wgrad_bf16": [C.POINTER(WgradJob), c_i, c_ll, c_f],
 }
 
 _lib = None

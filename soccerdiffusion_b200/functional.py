@@ -217,6 +217,33 @@ def _pack_enc_weights(layer_params, L: int, d: int):
     return wp
 
 
+def _enc_stack_fused_bwd(ctx, dh, layer_params, g_layers):
+    """Backward through the fused layers: per layer ONE data-gradient kernel + ONE launch for all six weight gradients."""
+    cfg = ctx.cfg
+    B, S, H, d, Kin, L = ctx.dims
+    M = B * S
+    wp = ctx.fused
+    bf = lambda n: torch.empty((M, n), device=dh.device, dtype=torch.bfloat16)
+    g2, dhpre, g1, dqkv = bf(d), bf(d), bf(d), bf(3 * d)   # reused by every layer (same stream: consumed before rewritten)
+    dx = _empty((M, d), dh)                                 # never write into autograd's own gradient tensor
+    for l in reversed(range(L)):
+        in_w, in_b, out_w, out_b, l1_w, l1_b, l2_w, l2_b, n1_w, n1_b, n2_w, n2_b = layer_params[
+            l * ENC_PARAMS_PER_LAYER: (l + 1) * ENC_PARAMS_PER_LAYER]
+        (g_in_w, g_in_b, g_out_w, g_out_b, g_l1_w, g_l1_b, g_l2_w, g_l2_b, g_n1_w, g_n1_b, g_n2_w,
+         g_n2_b) = g_layers[l * ENC_PARAMS_PER_LAYER: (l + 1) * ENC_PARAMS_PER_LAYER]
+        h_in, x1, xn1, attn, xn2, hact = ctx.acts[l]
+        ops.enc_layer_bwd(dh, dx, h_in, x1, xn1, xn2, g2, dhpre, g1, dqkv, g_n1_w, g_n1_b, g_n2_w, g_n2_b, B, S, H, wp,
+                          l * ops.ENC_ROWS_PER_LAYER, in_b, l1_b, n1_w, n2_w, dropout=cfg.drop(8 * l))
+        ops.wgrad_bf16([(dqkv, 0, xn1, 0, _p(g_in_w), d, _p(g_in_b)),
+                        (dqkv, d, xn1, 0, _p(g_in_w, d * d), d, _p(g_in_b, d)),
+                        (dqkv, 2 * d, xn1, 0, _p(g_in_w, 2 * d * d), d, _p(g_in_b, 2 * d)),
+                        (g1, 0, attn, 0, _p(g_out_w), d, _p(g_out_b)),
+                        (dhpre, 0, xn2, 0, _p(g_l1_w), d, _p(g_l1_b)),
+                        (g2, 0, hact, 0, _p(g_l2_w), d, _p(g_l2_b))], M)
+        dh = dx   # the next (earlier) layer reads and rewrites dx in place
+    return dh
+
+
 # --------------------------------------------------------------------------------------------------
 class EncoderStackFn(torch.autograd.Function):
     """Conv1d patch embedding (as a GEMM) + PE + L pre-LN encoder layers (base.py:49-53)."""
@@ -230,14 +257,28 @@ class EncoderStackFn(torch.autograd.Function):
         save = any(ctx.needs_input_grad)  # grad mode is always off inside forward(); this reflects the caller's
         h = _empty((M, d), x_in)
         ops.gemm(x_in, Kin, MK, emb_w, Kin, NK, h, d, M, d, Kin, precision=cfg.precision, bias=emb_b, pe=pe, pe_period=S)
-        if not save and L > 0 and _fused_enc_ok(cfg, d, layer_params[4].shape[0], S, H):
-            # layer-fused tensor-core path (one kernel per layer, weights by TMA); the residual stream is updated in place
+        if L > 0 and _fused_enc_ok(cfg, d, layer_params[4].shape[0], S, H):
+            # layer-fused tensor-core path: ONE kernel per layer (weights by TMA, residual stream in registers).  Inference
+            # updates the stream in place; training keeps each layer's input and the activations its backward needs.
             wp = _pack_enc_weights(layer_params, L, d)
+            fsaves = []
             for l in range(L):
                 (in_w, in_b, out_w, out_b, l1_w, l1_b, l2_w, l2_b, n1_w, n1_b, n2_w, n2_b) = layer_params[
                     l * ENC_PARAMS_PER_LAYER: (l + 1) * ENC_PARAMS_PER_LAYER]
-                ops.enc_layer_fwd(h, h, B, S, H, wp, l * ops.ENC_ROWS_PER_LAYER, in_b, out_b, l1_b, l2_b, n1_w, n1_b, n2_w,
-                                  n2_b, saves=None, dropout=cfg.drop(8 * l))
+                if save:
+                    y = _empty((M, d), h)
+                    x1 = _empty((M, d), h)
+                    bf = [torch.empty((M, d), device=h.device, dtype=torch.bfloat16) for _ in range(4)]   # xn1, attn, xn2, hact
+                    ops.enc_layer_fwd(h, y, B, S, H, wp, l * ops.ENC_ROWS_PER_LAYER, in_b, out_b, l1_b, l2_b, n1_w, n1_b,
+                                      n2_w, n2_b, saves=(x1, *bf), dropout=cfg.drop(8 * l))
+                    fsaves.append((h, x1, *bf))
+                    h = y
+                else:
+                    ops.enc_layer_fwd(h, h, B, S, H, wp, l * ops.ENC_ROWS_PER_LAYER, in_b, out_b, l1_b, l2_b, n1_w, n1_b,
+                                      n2_w, n2_b, saves=None, dropout=cfg.drop(8 * l))
+            if save:
+                ctx.cfg, ctx.dims, ctx.acts, ctx.fused = cfg, (B, S, H, d, Kin, L), fsaves, wp
+                ctx.save_for_backward(x_in, emb_w, emb_b, *layer_params)
             return h.view(B, S, d)
         acts = []
         for l in range(L):
@@ -247,7 +288,7 @@ class EncoderStackFn(torch.autograd.Function):
             h, s2 = _ffn_fwd(h, l1_w, l1_b, l2_w, l2_b, n2_w, n2_b, cfg, 8 * l + 2, save)
             acts.append((s1, s2))
         if save:
-            ctx.cfg, ctx.dims, ctx.acts = cfg, (B, S, H, d, Kin, L), acts
+            ctx.cfg, ctx.dims, ctx.acts, ctx.fused = cfg, (B, S, H, d, Kin, L), acts, None
             ctx.save_for_backward(x_in, emb_w, emb_b, *layer_params)
         return h.view(B, S, d)
 
@@ -260,7 +301,9 @@ class EncoderStackFn(torch.autograd.Function):
         grads, rets = _zero_grads([emb_w, emb_b, *layer_params])
         g_emb_w, g_emb_b, g_layers = grads[0], grads[1], grads[2:]
         dh = dy.contiguous().view(M, d)
-        for l in reversed(range(L)):
+        if ctx.fused is not None:
+            dh = _enc_stack_fused_bwd(ctx, dh, layer_params, g_layers)
+        for l in reversed(range(L if ctx.fused is None else 0)):
             in_w, in_b, out_w, out_b, l1_w, l1_b, l2_w, l2_b, n1_w, n1_b, n2_w, n2_b = layer_params[
                 l * ENC_PARAMS_PER_LAYER: (l + 1) * ENC_PARAMS_PER_LAYER]
             (g_in_w, g_in_b, g_out_w, g_out_b, g_l1_w, g_l1_b, g_l2_w, g_l2_b, g_n1_w, g_n1_b, g_n2_w,

@@ -446,3 +446,38 @@ def enc_layer_fwd(x, y, B, S, H, w_packed, w_row0, in_b, out_b, l1_b, l2_b, n1_w
                 M * 128 * (8.0 + (4.0 + 8.0 if saves is not None else 0.0)), f"[B{B} S{S} H{H}]"):
         check(_lib.lib().sd_enc_layer_fwd(C.byref(d), stream_ptr()), "sd_enc_layer_fwd")
     _count()
+
+
+def enc_layer_bwd(dy, dx, x, x1, xn1, xn2, g2, dhpre, g1, dqkv, g_n1_w, g_n1_b, g_n2_w, g_n2_b, B, S, H, w_packed, w_row0,
+                  in_b, l1_b, n1_w, n2_w, dropout=None):
+    """Data-path backward of one fused encoder layer (sd_enc_layer_bwd)."""
+    d = _lib.EncLayerBwdDesc()
+    d.dy, d.dx, d.x, d.x1, d.xn1, d.xn2 = (t.data_ptr() for t in (dy, dx, x, x1, xn1, xn2))
+    d.g2, d.dhpre, d.g1, d.dqkv = (t.data_ptr() for t in (g2, dhpre, g1, dqkv))
+    d.g_n1_w, d.g_n1_b, d.g_n2_w, d.g_n2_b = (t.data_ptr() for t in (g_n1_w, g_n1_b, g_n2_w, g_n2_b))
+    d.B, d.S, d.H = B, S, H
+    d.w_packed, d.w_rows_total, d.w_row0 = w_packed.data_ptr(), w_packed.shape[0], w_row0
+    d.in_b, d.l1_b, d.n1_w, d.n2_w = in_b.data_ptr(), l1_b.data_ptr(), n1_w.data_ptr(), n2_w.data_ptr()
+    if dropout is not None and dropout[0] > 0.0:
+        d.dropout_p, d.dropout_seed, d.dropout_stream = dropout
+    M = B * S
+    # data gradients: 2x the forward GEMMs minus the weight gradients' share, plus the recomputed forward
+    with _Timed("fused_enc_layer_bwd", B * (16.0 * S * 128 * 128 + 12.0 * S * S * 128), M * 128 * (4.0 * 4 + 2.0 * 2 + 2.0 * 6),
+                f"[B{B} S{S} H{H}]"):
+        check(_lib.lib().sd_enc_layer_bwd(C.byref(d), stream_ptr()), "sd_enc_layer_bwd")
+    _count()
+
+
+def wgrad_bf16(jobs, rows: int):
+    """``jobs``: list of (G bf16 [rows][ldg], g_col0, X bf16 [rows][ldx], x_col0, dW fp32 view [128][ldw], ldw, db or None):
+    dW += G[:, g_col0:g_col0+128]^T X[:, x_col0:x_col0+128], db += column sums of G (sd_wgrad_bf16, one launch)."""
+    arr = (_lib.WgradJob * len(jobs))()
+    for a, (G, g_col0, X, x_col0, dW, ldw, db) in zip(arr, jobs):
+        a.G, a.ldg, a.g_col0 = G.data_ptr(), G.shape[1], g_col0
+        a.X, a.ldx, a.x_col0 = X.data_ptr(), X.shape[1], x_col0
+        a.dW = dW if isinstance(dW, int) else dW.data_ptr()
+        a.ldw = ldw
+        a.db = None if db is None else (db if isinstance(db, int) else db.data_ptr())
+    with _Timed("tma_wgrad", 2.0 * rows * 128 * 128 * len(jobs), 2.0 * rows * 256 * len(jobs), f"[{len(jobs)}x{rows}]"):
+        check(_lib.lib().sd_wgrad_bf16(arr, len(jobs), rows, stream_ptr()), "sd_wgrad_bf16")
+    _count()
