@@ -47,14 +47,23 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 }
 
 // Stateless counter-based RNG for dropout: one 32-bit draw per (seed, stream, element).
-// (splitmix64 finaliser; the same function is exported through sd_dropout_mask so a test can
-// hand the oracle exactly the masks the fused kernels used.)
+// The (seed, stream) pair is mixed into two 32-bit keys (loop invariant: computed once per thread), the element index is
+// combined with them and finalised with a 32-bit avalanche mixer (two multiplies, three xor-shifts) — the draw sits in
+// the inner loop of every fused epilogue, which is issue-bound (the previous 64-bit splitmix finaliser cost ~25
+// instructions per element).  The same function is exported through sd_dropout_mask so a test can hand the oracle
+// exactly the masks the fused kernels used.
 __host__ __device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint32_t stream, uint64_t idx) {
-    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1) + ((uint64_t)stream << 40);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z = z ^ (z >> 31);
-    return (uint32_t)(z >> 32);
+    uint64_t k = seed * 0x9E3779B97F4A7C15ull + (((uint64_t)stream << 32) | stream) * 0xD6E8FEB86659FD93ull;
+    k ^= k >> 32;
+    k *= 0xD6E8FEB86659FD93ull;
+    k ^= k >> 32;
+    uint32_t h = ((uint32_t)idx ^ (uint32_t)k) * 0x9E3779B1u + ((uint32_t)(idx >> 32) ^ (uint32_t)(k >> 32)) * 0xC2B2AE3Du;
+    h ^= h >> 16;
+    h *= 0x7FEB352Du;
+    h ^= h >> 15;
+    h *= 0x846CA68Bu;
+    h ^= h >> 16;
+    return h;
 }
 // returns 0 (dropped) or 1/(1-p) (kept)
 __host__ __device__ __forceinline__ float dropout_scale(uint64_t seed, uint32_t stream, uint64_t idx, uint32_t thresh,
