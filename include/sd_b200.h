@@ -302,13 +302,20 @@ int sd_pack_weights_bf16(const sd_pack_args* args, int n_segments, void* stream)
  * (attention probabilities, element ((b*H+h)*S+t)*S+m), +1 (out-proj, element row*128+c), +2 (FC1), +3 (FC2).
  * Optional saves for the backward pass (all NULL in inference): x1_save fp32 [B*S][128] (residual stream after the
  * attention block), xn1/attn/xn2/hact_save bf16 [B*S][128] (LN1(x), attention output, LN2(x1), hidden activation). */
+#define SD_LAYER_SA 1  /* the self-attention block  x1 = x + Drop(OutProj(MHA(LN1 x))) */
+#define SD_LAYER_FFN 2 /* the feed-forward block    y = x1 + Drop(W2 Drop(GELU(W1 LN2 x1))) */
 typedef struct sd_enc_layer_desc {
     const float* x; float* y;
     int B, S, H;
-    const void* w_packed; int w_rows_total; int w_row0; /* packed bf16 weights [w_rows_total][128]; this layer's first row */
+    const void* w_packed; int w_rows_total; int w_row0; /* packed bf16 weights [w_rows_total][128]; first row of Wq|Wk|Wv|Wout */
     const float *in_b, *out_b, *l1_b, *l2_b, *n1_w, *n1_b, *n2_w, *n2_b;
     float* x1_save; void* xn1_save; void* attn_save; void* xn2_save; void* hact_save;
     float dropout_p; unsigned long long dropout_seed; unsigned int dropout_stream;
+    /* A DECODER layer (decoder.py:25-35; torch transformer.py:1131-1143) runs the two halves as separate launches around its
+     * cross-attention block: blocks = SD_LAYER_SA (y = x1; LN1 / attention parameters only) or SD_LAYER_FFN (x is x1; n2_* /
+     * l*_b are the layer's norm3 / linear parameters).  0 = both (an encoder layer).  w_row_ffn: first packed row of W1|W2
+     * (0 = w_row0 + 512); dropout_stream_ffn: first dropout stream of the feed-forward block (0 = dropout_stream + 2). */
+    int blocks; int w_row_ffn; unsigned int dropout_stream_ffn;
 } sd_enc_layer_desc;
 int sd_enc_layer_supported(int d, int ff, int S, int H);
 int sd_enc_layer_fwd(const sd_enc_layer_desc* desc, void* stream);
@@ -326,6 +333,7 @@ typedef struct sd_enc_layer_bwd_desc {
     const void* w_packed; int w_rows_total; int w_row0;
     const float *in_b, *l1_b, *n1_w, *n2_w;
     float dropout_p; unsigned long long dropout_seed; unsigned int dropout_stream;
+    int blocks; int w_row_ffn; unsigned int dropout_stream_ffn; /* as in sd_enc_layer_desc; SA only: x1 unused, FFN only: x unused */
 } sd_enc_layer_bwd_desc;
 int sd_enc_layer_bwd(const sd_enc_layer_bwd_desc* desc, void* stream);
 

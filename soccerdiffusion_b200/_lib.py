@@ -73,7 +73,8 @@ class EncLayerDesc(C.Structure):
                 ("in_b", c_f), ("out_b", c_f), ("l1_b", c_f), ("l2_b", c_f),
                 ("n1_w", c_f), ("n1_b", c_f), ("n2_w", c_f), ("n2_b", c_f),
                 ("x1_save", c_f), ("xn1_save", c_f), ("attn_save", c_f), ("xn2_save", c_f), ("hact_save", c_f),
-                ("dropout_p", c_fl), ("dropout_seed", c_ull), ("dropout_stream", c_u)]
+                ("dropout_p", c_fl), ("dropout_seed", c_ull), ("dropout_stream", c_u),
+                ("blocks", c_i), ("w_row_ffn", c_i), ("dropout_stream_ffn", c_u)]
 
 
 class EncLayerBwdDesc(C.Structure):
@@ -83,7 +84,8 @@ class EncLayerBwdDesc(C.Structure):
                 ("B", c_i), ("S", c_i), ("H", c_i),
                 ("w_packed", c_f), ("w_rows_total", c_i), ("w_row0", c_i),
                 ("in_b", c_f), ("l1_b", c_f), ("n1_w", c_f), ("n2_w", c_f),
-                ("dropout_p", c_fl), ("dropout_seed", c_ull), ("dropout_stream", c_u)]
+                ("dropout_p", c_fl), ("dropout_seed", c_ull), ("dropout_stream", c_u),
+                ("blocks", c_i), ("w_row_ffn", c_i), ("dropout_stream_ffn", c_u)]
 
 
 WGRAD_MAX_JOBS = 8

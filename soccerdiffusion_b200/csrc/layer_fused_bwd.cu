@@ -44,7 +44,8 @@ struct EncBwdParams {
     float *g_n1_w, *g_n1_b, *g_n2_w, *g_n2_b;
     const float *in_b, *l1_b, *n1_w, *n2_w;
     int B, S, spt, H, dh;
-    int w_row0;
+    int w_row0, w_row_ffn;
+    uint32_t ffn_stream;
     Dropout drop;
 };
 
@@ -99,7 +100,7 @@ __device__ __forceinline__ void ln_backward(float* gr, float* dxn, const float* 
     atomicAdd(colacc_b + L.col0 + L.lane, cb);
 }
 
-template <bool DROP>
+template <bool DROP, bool SA, bool FFN>
 __global__ void __launch_bounds__(LNT, 1) enc_layer_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const EncBwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar[NBAR];
@@ -127,11 +128,20 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_bwd_kernel(const __grid_cons
     // weight matrix mi of the layer (0 Wq, 1 Wk, 2 Wv, 3 Wout, 4 W1, 5 W2) -> the tile pair at byte offset `pair`
     auto load_w = [&](int mi, int pair, int b) {
         const uint32_t dst = sbase + pair;
+        const int row = mi < 4 ? p.w_row0 + 128 * mi : p.w_row_ffn + 128 * (mi - 4);
         mbar_arrive_expect_tx(&bar[b], 2 * LTILE);
-        tma_tile_2d(dst, &tmW, 0, p.w_row0 + 128 * mi, &bar[b]);
-        tma_tile_2d(dst + LTILE, &tmW, 64, p.w_row0 + 128 * mi, &bar[b]);
+        tma_tile_2d(dst, &tmW, 0, row, &bar[b]);
+        tma_tile_2d(dst + LTILE, &tmW, 64, row, &bar[b]);
     };
-    if (tid == 0) { load_w(4, P4, BW_W1); load_w(5, P5, BW_W2); }
+    auto load_attn_w = [&]() {
+        load_w(3, P5, BW_OUT);
+        load_w(0, P2, BW_Q);
+        load_w(1, P3, BW_K);
+        load_w(2, P4, BW_V);
+    };
+    if (tid == 0) {
+        if (FFN) { load_w(4, P4, BW_W1); load_w(5, P5, BW_W2); } else load_attn_w();
+    }
 
     const int S = p.S, H = p.H, dh = p.dh;
     const int samp0 = blockIdx.x * p.spt;
@@ -158,12 +168,13 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_bwd_kernel(const __grid_cons
 #pragma unroll
         for (int j = 0; j < 32; ++j) gr[j] = 0.f;
     }
+    if constexpr (FFN) {
     {
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             v[j] = gr[j];
-            if (DROP) v[j] *= dropout_scale(dseed, p.drop.stream + 3, (uint64_t)goff + j, p.drop.thresh, p.drop.inv_keep);
+            if (DROP) v[j] *= dropout_scale(dseed, p.ffn_stream + 1, (uint64_t)goff + j, p.drop.thresh, p.drop.inv_keep);
         }
         st_row32(smem + P0, L, v, rv ? p.g2 + goff / 8 : nullptr);      // g2 = dy * mask3 : A operand of dhact, saved for dW2
         copy_row32(smem + P1, L, p.xn2 + goff / 8, rv);                // LN2(x1): A operand of the hpre recomputation
@@ -190,7 +201,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_bwd_kernel(const __grid_cons
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             float t = dh_[j] * gelu_fast_grad(hp[j] + b[j]);
-            if (DROP) t *= dropout_scale(dseed, p.drop.stream + 2, (uint64_t)goff + j, p.drop.thresh, p.drop.inv_keep);
+            if (DROP) t *= dropout_scale(dseed, p.ffn_stream, (uint64_t)goff + j, p.drop.thresh, p.drop.inv_keep);
             dh_[j] = rv ? t : 0.f;
         }
         st_row32(smem + P2, L, dh_, rv ? p.dhpre + goff / 8 : nullptr);   // dhpre: A operand of d(LN2 out), saved for dW1
@@ -202,11 +213,10 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_bwd_kernel(const __grid_cons
         tc_fence_after_sync();
         mma_a_k_b_mn(tmem + ACC2, sbase + P2, LTILE, sbase + P4, LTILE, id_km, 8, false);      // d(LN2 out) = dhpre W1
         mma_commit(&bar[B_F4]);
-        mbar_wait(&bar[B_F4], 0);   // P2 (dhpre), P4 (W1), P5 (W2) are free: prefetch the attention block's weights
-        load_w(3, P5, BW_OUT);
-        load_w(0, P2, BW_Q);
-        load_w(1, P3, BW_K);
-        load_w(2, P4, BW_V);
+        if (SA) {
+            mbar_wait(&bar[B_F4], 0);   // P2 (dhpre), P4 (W1), P5 (W2) are free: prefetch the attention block's weights
+            load_attn_w();
+        }
     }
     __syncwarp();
     {
@@ -232,7 +242,16 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_bwd_kernel(const __grid_cons
         ld_acc32(tmem, L, ACC2, dxn);
         ln_backward(gr, dxn, xh, rstd, p.n2_w, colacc[0], colacc[1], red[0], red[1], L);
     }
+    }   // FFN
+    if constexpr (!SA) {
+        if (rv) {
+            float4* g = reinterpret_cast<float4*>(p.dx + goff);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = make_float4(gr[4 * j], gr[4 * j + 1], gr[4 * j + 2], gr[4 * j + 3]);
+        }
+    }
     // ---- attention backward -------------------------------------------------------------------------------------------------
+    if constexpr (SA) {
     {
         float v[32];
 #pragma unroll
@@ -459,9 +478,10 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_bwd_kernel(const __grid_cons
             for (int j = 0; j < 8; ++j) g[j] = make_float4(gr[4 * j], gr[4 * j + 1], gr[4 * j + 2], gr[4 * j + 3]);
         }
     }
+    }   // SA
     tc_fence_before_sync();
     __syncthreads();
-    {
+    if ((tid < 256) ? FFN : SA) {
         float* dst = (tid < 128) ? p.g_n2_w : (tid < 256) ? p.g_n2_b : (tid < 384) ? p.g_n1_w : p.g_n1_b;
         atomicAdd(dst + (tid & 127), colacc[tid >> 7][tid & 127]);
     }
@@ -470,13 +490,33 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_bwd_kernel(const __grid_cons
 
 }  // namespace
 
+namespace {
+template <bool DROP, bool SA, bool FFN>
+int launch_bwd(const CUtensorMap& tmW, const EncBwdParams& p, int tiles, cudaStream_t st) {
+    auto kernel = enc_layer_bwd_kernel<DROP, SA, FFN>;
+    static bool configured = false;
+    if (!configured) {
+        SD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
+        configured = true;
+    }
+    kernel<<<tiles, LNT, SMEM_DYN, st>>>(tmW, p);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+}
+}  // namespace
+
 extern "C" int sd_enc_layer_bwd(const sd_enc_layer_bwd_desc* d, void* stream) {
-    if (!d || !d->dy || !d->dx || !d->x || !d->x1 || !d->xn1 || !d->xn2 || !d->g2 || !d->dhpre || !d->g1 || !d->dqkv ||
-        !d->g_n1_w || !d->g_n1_b || !d->g_n2_w || !d->g_n2_b || !d->in_b || !d->l1_b || !d->n1_w || !d->n2_w || !d->w_packed)
-        return SD_ERR_BAD_ARG;
+    if (!d || !d->dy || !d->dx || !d->w_packed) return SD_ERR_BAD_ARG;
+    const int blocks = d->blocks == 0 ? (SD_LAYER_SA | SD_LAYER_FFN) : d->blocks;
+    const bool sa = (blocks & SD_LAYER_SA) != 0, ffn = (blocks & SD_LAYER_FFN) != 0;
+    if ((blocks & ~(SD_LAYER_SA | SD_LAYER_FFN)) != 0) return SD_ERR_BAD_ARG;
+    if (sa && (!d->x || !d->xn1 || !d->g1 || !d->dqkv || !d->g_n1_w || !d->g_n1_b || !d->in_b || !d->n1_w)) return SD_ERR_BAD_ARG;
+    if (ffn && (!d->x1 || !d->xn2 || !d->g2 || !d->dhpre || !d->g_n2_w || !d->g_n2_b || !d->l1_b || !d->n2_w)) return SD_ERR_BAD_ARG;
     if (d->B <= 0) return SD_OK;
     if (!sd_enc_layer_supported(128, 128, d->S, d->H)) return SD_ERR_UNSUPPORTED;
-    if (d->w_row0 < 0 || d->w_row0 + 768 > d->w_rows_total) return SD_ERR_BAD_ARG;
+    const int w_row_ffn = d->w_row_ffn > 0 ? d->w_row_ffn : d->w_row0 + 512;
+    if (sa && (d->w_row0 < 0 || d->w_row0 + 512 > d->w_rows_total)) return SD_ERR_BAD_ARG;
+    if (ffn && (w_row_ffn < 0 || w_row_ffn + 256 > d->w_rows_total)) return SD_ERR_BAD_ARG;
     if ((((uintptr_t)d->dy) | ((uintptr_t)d->dx) | ((uintptr_t)d->x) | ((uintptr_t)d->x1) | ((uintptr_t)d->xn1) | ((uintptr_t)d->xn2) |
          ((uintptr_t)d->g2) | ((uintptr_t)d->dhpre) | ((uintptr_t)d->g1) | ((uintptr_t)d->dqkv)) & 15)
         return SD_ERR_BAD_ARG;
@@ -487,17 +527,13 @@ extern "C" int sd_enc_layer_bwd(const sd_enc_layer_bwd_desc* d, void* stream) {
     p.g2 = (uint4*)d->g2; p.dhpre = (uint4*)d->dhpre; p.g1 = (uint4*)d->g1; p.dqkv = (uint4*)d->dqkv;
     p.g_n1_w = d->g_n1_w; p.g_n1_b = d->g_n1_b; p.g_n2_w = d->g_n2_w; p.g_n2_b = d->g_n2_b;
     p.in_b = d->in_b; p.l1_b = d->l1_b; p.n1_w = d->n1_w; p.n2_w = d->n2_w;
-    p.B = d->B; p.S = d->S; p.spt = 128 / d->S; p.H = d->H; p.dh = 128 / d->H; p.w_row0 = d->w_row0;
+    p.B = d->B; p.S = d->S; p.spt = 128 / d->S; p.H = d->H; p.dh = 128 / d->H; p.w_row0 = d->w_row0; p.w_row_ffn = w_row_ffn;
     p.drop = make_dropout(d->dropout_p, d->dropout_seed, d->dropout_stream);
-    static bool configured = false;
-    if (!configured) {
-        SD_CUDA(cudaFuncSetAttribute(enc_layer_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
-        SD_CUDA(cudaFuncSetAttribute(enc_layer_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
-        configured = true;
-    }
+    p.ffn_stream = d->dropout_stream_ffn != 0 ? d->dropout_stream_ffn : d->dropout_stream + 2;
     const int tiles = ceil_div(d->B, p.spt);
-    if (p.drop.thresh != 0) enc_layer_bwd_kernel<true><<<tiles, LNT, SMEM_DYN, (cudaStream_t)stream>>>(tmW, p);
-    else enc_layer_bwd_kernel<false><<<tiles, LNT, SMEM_DYN, (cudaStream_t)stream>>>(tmW, p);
-    SD_LAUNCH_CHECK();
-    return SD_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool drop = p.drop.thresh != 0;
+    if (sa && ffn) return drop ? launch_bwd<true, true, true>(tmW, p, tiles, st) : launch_bwd<false, true, true>(tmW, p, tiles, st);
+    if (sa) return drop ? launch_bwd<true, true, false>(tmW, p, tiles, st) : launch_bwd<false, true, false>(tmW, p, tiles, st);
+    return drop ? launch_bwd<true, false, true>(tmW, p, tiles, st) : launch_bwd<false, false, true>(tmW, p, tiles, st);
 }

@@ -45,14 +45,18 @@ struct EncFwdParams {
     const float* x;
     float* y;
     int B, S, spt, H, dh;
-    int w_row0;
+    int w_row0;      // first packed-weight row of the attention block (Wq | Wk | Wv | Wout)
+    int w_row_ffn;   // first packed-weight row of the feed-forward block (W1 | W2)
+    uint32_t ffn_stream;   // first dropout stream of the feed-forward block (sites +0 FC1, +1 FC2)
     const float *in_b, *out_b, *l1_b, *l2_b, *n1_w, *n1_b, *n2_w, *n2_b;
     float* x1_save;
     uint4 *xn1_save, *attn_save, *xn2_save, *hact_save;
     Dropout drop;   // .stream = first dropout stream of this layer (sites +0 attention, +1 out-proj, +2 FC1, +3 FC2)
 };
 
-template <bool DROP>
+// SA: run the self-attention block; FFN: run the feed-forward block (an encoder layer is both; a decoder layer runs the
+// two halves as separate launches around its cross-attention block)
+template <bool DROP, bool SA, bool FFN>
 __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const EncFwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar[NBAR];
@@ -79,11 +83,14 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
     // weight matrix mi (0 Wq, 1 Wk, 2 Wv, 3 Wout, 4 W1, 5 W2) -> ring slot (mi & 1)
     auto load_w = [&](int mi) {
         const uint32_t dst = sbase + OFF_W + (mi & 1) * 2 * LTILE;
+        const int row = mi < 4 ? p.w_row0 + 128 * mi : p.w_row_ffn + 128 * (mi - 4);
         mbar_arrive_expect_tx(&bar[BW0 + mi], 2 * LTILE);
-        tma_tile_2d(dst, &tmW, 0, p.w_row0 + 128 * mi, &bar[BW0 + mi]);
-        tma_tile_2d(dst + LTILE, &tmW, 64, p.w_row0 + 128 * mi, &bar[BW0 + mi]);
+        tma_tile_2d(dst, &tmW, 0, row, &bar[BW0 + mi]);
+        tma_tile_2d(dst + LTILE, &tmW, 64, row, &bar[BW0 + mi]);
     };
-    if (tid == 0) { load_w(0); load_w(1); }
+    if (tid == 0) {
+        if (SA) { load_w(0); load_w(1); } else { load_w(4); load_w(5); }
+    }
 
     const int S = p.S, H = p.H, dh = p.dh;
     const int samp0 = blockIdx.x * p.spt;
@@ -107,6 +114,8 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
 #pragma unroll
         for (int j = 0; j < 32; ++j) xr[j] = 0.f;
     }
+    const uint32_t id128 = instr_desc_bf16(128, 128);
+    if constexpr (SA) {
     {
         float mean, rstd, v[32], ga[32], be[32];
         ldg32(p.n1_w + c0, ga);
@@ -128,7 +137,6 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
     tc_fence_before_sync();
     __syncthreads();
 
-    const uint32_t id128 = instr_desc_bf16(128, 128);
     if (tid == 0) {
         tc_fence_after_sync();
         mbar_wait(&bar[BW0 + 0], 0);
@@ -167,7 +175,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
         const float bv = __ldg(p.in_b + 256 + r);
         mbar_wait(&bar[BV], 0);
         tc_fence_after_sync();
-        if (tid == 0) load_w(4);   // slot A drained by the V^T MMAs
+        if (FFN && tid == 0) load_w(4);   // slot A drained by the V^T MMAs
         __syncwarp();
         ld_acc32(tmem, L, ACC2, v);   // row = feature r, columns = tokens
 #pragma unroll
@@ -274,7 +282,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
         ldg32(p.out_b + c0, b);
         mbar_wait(&bar[BOUT], 0);
         tc_fence_after_sync();
-        if (tid == 0) load_w(5);   // slot B drained by the out-projection
+        if (FFN && tid == 0) load_w(5);   // slot B drained by the out-projection
         __syncwarp();
         ld_acc32(tmem, L, ACC0, v);
 #pragma unroll
@@ -283,11 +291,17 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
             if (DROP) t *= dropout_scale(dseed, p.drop.stream + 1, (uint64_t)goff + j, p.drop.thresh, p.drop.inv_keep);
             xr[j] = rv ? xr[j] + t : 0.f;
         }
-        if (rv && p.x1_save) {
-            float4* g = reinterpret_cast<float4*>(p.x1_save + goff);
+        float* x1_dst = FFN ? p.x1_save : p.y;   // attention block alone: x1 is the output
+        if (rv && x1_dst) {
+            float4* g = reinterpret_cast<float4*>(x1_dst + goff);
 #pragma unroll
             for (int j = 0; j < 8; ++j) g[j] = make_float4(xr[4 * j], xr[4 * j + 1], xr[4 * j + 2], xr[4 * j + 3]);
         }
+    }
+    }   // SA
+    if constexpr (FFN) {
+    {
+        float v[32], b[32];
         float mean, rstd;
         ldg32(p.n2_w + c0, b);
         row_stats(xr, red[0], red[1], tid, mean, rstd);
@@ -317,7 +331,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             float t = gelu_fast(v[j] + b[j]);
-            if (DROP) t *= dropout_scale(dseed, p.drop.stream + 2, (uint64_t)goff + j, p.drop.thresh, p.drop.inv_keep);
+            if (DROP) t *= dropout_scale(dseed, p.ffn_stream, (uint64_t)goff + j, p.drop.thresh, p.drop.inv_keep);
             v[j] = rv ? t : 0.f;
         }
         st_row32(smem + OFF_QS, L, v, (rv && p.hact_save) ? p.hact_save + goff / 8 : nullptr);
@@ -343,13 +357,14 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 float t = v[j] + b[j];
-                if (DROP) t *= dropout_scale(dseed, p.drop.stream + 3, (uint64_t)goff + j, p.drop.thresh, p.drop.inv_keep);
+                if (DROP) t *= dropout_scale(dseed, p.ffn_stream + 1, (uint64_t)goff + j, p.drop.thresh, p.drop.inv_keep);
                 v[j] = xr[j] + t;
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) g[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
     }
+    }   // FFN
     tc_fence_before_sync();
     __syncthreads();
     if (L.warp == 0) tmem_dealloc(tmem, 512);
@@ -397,13 +412,33 @@ extern "C" int sd_enc_layer_supported(int d, int ff, int S, int H) {
     return tensor_map_encoder() != nullptr ? 1 : 0;
 }
 
+namespace {
+template <bool DROP, bool SA, bool FFN>
+int launch_fwd(const CUtensorMap& tmW, const EncFwdParams& p, int tiles, cudaStream_t st) {
+    auto kernel = enc_layer_fwd_kernel<DROP, SA, FFN>;
+    static bool configured = false;   // one flag per instantiation
+    if (!configured) {
+        SD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
+        configured = true;
+    }
+    kernel<<<tiles, LNT, SMEM_DYN, st>>>(tmW, p);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+}
+}  // namespace
+
 extern "C" int sd_enc_layer_fwd(const sd_enc_layer_desc* d, void* stream) {
-    if (!d || !d->x || !d->y || !d->w_packed || !d->in_b || !d->out_b || !d->l1_b || !d->l2_b || !d->n1_w || !d->n1_b ||
-        !d->n2_w || !d->n2_b)
-        return SD_ERR_BAD_ARG;
+    if (!d || !d->x || !d->y || !d->w_packed) return SD_ERR_BAD_ARG;
+    const int blocks = d->blocks == 0 ? (SD_LAYER_SA | SD_LAYER_FFN) : d->blocks;
+    const bool sa = (blocks & SD_LAYER_SA) != 0, ffn = (blocks & SD_LAYER_FFN) != 0;
+    if ((blocks & ~(SD_LAYER_SA | SD_LAYER_FFN)) != 0) return SD_ERR_BAD_ARG;
+    if (sa && (!d->in_b || !d->out_b || !d->n1_w || !d->n1_b)) return SD_ERR_BAD_ARG;
+    if (ffn && (!d->l1_b || !d->l2_b || !d->n2_w || !d->n2_b)) return SD_ERR_BAD_ARG;
     if (d->B <= 0) return SD_OK;
     if (!sd_enc_layer_supported(128, 128, d->S, d->H)) return SD_ERR_UNSUPPORTED;
-    if (d->w_row0 < 0 || d->w_row0 + 768 > d->w_rows_total) return SD_ERR_BAD_ARG;
+    const int w_row_ffn = d->w_row_ffn > 0 ? d->w_row_ffn : d->w_row0 + 512;
+    if (sa && (d->w_row0 < 0 || d->w_row0 + 512 > d->w_rows_total)) return SD_ERR_BAD_ARG;
+    if (ffn && (w_row_ffn < 0 || w_row_ffn + 256 > d->w_rows_total)) return SD_ERR_BAD_ARG;
     if ((((uintptr_t)d->x) | ((uintptr_t)d->y) | ((uintptr_t)d->x1_save) | ((uintptr_t)d->xn1_save) | ((uintptr_t)d->attn_save) |
          ((uintptr_t)d->xn2_save) | ((uintptr_t)d->hact_save)) & 15)
         return SD_ERR_BAD_ARG;
@@ -411,22 +446,18 @@ extern "C" int sd_enc_layer_fwd(const sd_enc_layer_desc* d, void* stream) {
     if (!encode_bf16_2d(&tmW, d->w_packed, d->w_rows_total, 128, 128, 128)) return SD_ERR_UNSUPPORTED;
     EncFwdParams p;
     p.x = d->x; p.y = d->y; p.B = d->B; p.S = d->S; p.spt = 128 / d->S; p.H = d->H; p.dh = 128 / d->H;
-    p.w_row0 = d->w_row0;
+    p.w_row0 = d->w_row0; p.w_row_ffn = w_row_ffn;
     p.in_b = d->in_b; p.out_b = d->out_b; p.l1_b = d->l1_b; p.l2_b = d->l2_b;
     p.n1_w = d->n1_w; p.n1_b = d->n1_b; p.n2_w = d->n2_w; p.n2_b = d->n2_b;
     p.x1_save = d->x1_save;
     p.xn1_save = (uint4*)d->xn1_save; p.attn_save = (uint4*)d->attn_save; p.xn2_save = (uint4*)d->xn2_save;
     p.hact_save = (uint4*)d->hact_save;
     p.drop = make_dropout(d->dropout_p, d->dropout_seed, d->dropout_stream);
-    static bool configured = false;
-    if (!configured) {
-        SD_CUDA(cudaFuncSetAttribute(enc_layer_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
-        SD_CUDA(cudaFuncSetAttribute(enc_layer_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
-        configured = true;
-    }
+    p.ffn_stream = d->dropout_stream_ffn != 0 ? d->dropout_stream_ffn : d->dropout_stream + 2;
     const int tiles = ceil_div(d->B, p.spt);
-    if (p.drop.thresh != 0) enc_layer_fwd_kernel<true><<<tiles, LNT, SMEM_DYN, (cudaStream_t)stream>>>(tmW, p);
-    else enc_layer_fwd_kernel<false><<<tiles, LNT, SMEM_DYN, (cudaStream_t)stream>>>(tmW, p);
-    SD_LAUNCH_CHECK();
-    return SD_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool drop = p.drop.thresh != 0;
+    if (sa && ffn) return drop ? launch_fwd<true, true, true>(tmW, p, tiles, st) : launch_fwd<false, true, true>(tmW, p, tiles, st);
+    if (sa) return drop ? launch_fwd<true, true, false>(tmW, p, tiles, st) : launch_fwd<false, true, false>(tmW, p, tiles, st);
+    return drop ? launch_fwd<true, false, true>(tmW, p, tiles, st) : launch_fwd<false, false, true>(tmW, p, tiles, st);
 }

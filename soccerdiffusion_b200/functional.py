@@ -323,6 +323,82 @@ class EncoderStackFn(torch.autograd.Function):
         return (None, None, None, None, None, dx_in, *rets)
 
 
+def _pack_dec_weights(layer_params, L: int, d: int):
+    """bf16 copies of the decoder layers' GEMM weights as ONE [L*1280][d] matrix (rows per layer: self_attn.in_proj |
+    self_attn.out_proj | multihead_attn.in_proj | multihead_attn.out_proj | linear1 | linear2)."""
+    wp = torch.empty((L * ops.DEC_ROWS_PER_LAYER, d), device=layer_params[0].device, dtype=torch.bfloat16)
+    mats = []
+    for l in range(L):
+        P = layer_params[l * DEC_PARAMS_PER_LAYER: (l + 1) * DEC_PARAMS_PER_LAYER]
+        r0 = l * ops.DEC_ROWS_PER_LAYER
+        mats += [(P[0], 3 * d, r0), (P[2], d, r0 + 3 * d), (P[4], 3 * d, r0 + 4 * d), (P[6], d, r0 + 7 * d),
+                 (P[8], d, r0 + 8 * d), (P[10], d, r0 + 9 * d)]
+    ops.pack_weights_bf16(mats, wp, d)
+    return wp
+
+
+def _bf16(shape, like):
+    return torch.empty(shape, device=like.device, dtype=torch.bfloat16)
+
+
+def _dec_layer_fused_fwd(h, mem2, B, T, Mm, H, P, wp, l, cfg: RunCfg, save: bool):
+    """One decoder layer with the self-attention and feed-forward blocks as fused kernels (the cross-attention block in
+    between runs on the per-op kernels: its keys / values are the 312-token memory)."""
+    (sa_in_w, sa_in_b, sa_out_w, sa_out_b, ca_in_w, ca_in_b, ca_out_w, ca_out_b, l1_w, l1_b, l2_w, l2_b, n1_w, n1_b, n2_w, n2_b,
+     n3_w, n3_b) = P
+    d = h.shape[-1]
+    M = B * T
+    r0 = l * ops.DEC_ROWS_PER_LAYER
+    if save:
+        x1 = _empty((M, d), h)
+        xn1, attn = _bf16((M, d), h), _bf16((M, d), h)
+        ops.enc_layer_fwd(h, x1, B, T, H, wp, r0, sa_in_b, sa_out_b, None, None, n1_w, n1_b, None, None,
+                          saves=(None, xn1, attn, None, None), dropout=cfg.drop(8 * l), blocks=ops.LAYER_SA)
+    else:
+        x1, xn1, attn = h, None, None
+        ops.enc_layer_fwd(h, h, B, T, H, wp, r0, sa_in_b, sa_out_b, None, None, n1_w, n1_b, None, None,
+                          dropout=cfg.drop(8 * l), blocks=ops.LAYER_SA)
+    x2, s2 = _ca_fwd(x1, mem2, B, T, Mm, H, ca_in_w, ca_in_b, ca_out_w, ca_out_b, n2_w, n2_b, cfg, 8 * l + 2, save)
+    drop = cfg.drop(8 * l + 4)
+    kw = dict(dropout=drop, blocks=ops.LAYER_FFN, w_row_ffn=r0 + 1024, dropout_stream_ffn=cfg.stream_base + 8 * l + 4)
+    if save:
+        y = _empty((M, d), h)
+        xn3, hact = _bf16((M, d), h), _bf16((M, d), h)
+        ops.enc_layer_fwd(x2, y, B, T, H, wp, r0, None, None, l1_b, l2_b, None, None, n3_w, n3_b,
+                          saves=(None, None, None, xn3, hact), **kw)
+        return y, (h, xn1, attn, s2, x2, xn3, hact)
+    ops.enc_layer_fwd(x2, x2, B, T, H, wp, r0, None, None, l1_b, l2_b, None, None, n3_w, n3_b, **kw)
+    return x2, None
+
+
+def _dec_layer_fused_bwd(dh, saved, mem2, dmem, B, T, Mm, H, P, G, wp, l, cfg: RunCfg, bufs):
+    (sa_in_w, sa_in_b, sa_out_w, sa_out_b, ca_in_w, ca_in_b, ca_out_w, ca_out_b, l1_w, l1_b, l2_w, l2_b, n1_w, n1_b, n2_w, n2_b,
+     n3_w, n3_b) = P
+    (g_sa_in_w, g_sa_in_b, g_sa_out_w, g_sa_out_b, g_ca_in_w, g_ca_in_b, g_ca_out_w, g_ca_out_b, g_l1_w, g_l1_b, g_l2_w, g_l2_b,
+     g_n1_w, g_n1_b, g_n2_w, g_n2_b, g_n3_w, g_n3_b) = G
+    h_in, xn1, attn, s2, x2, xn3, hact = saved
+    g2, dhpre, g1, dqkv, dx = bufs
+    d = h_in.shape[-1]
+    M = B * T
+    r0 = l * ops.DEC_ROWS_PER_LAYER
+    # feed-forward block
+    ops.enc_layer_bwd(dh, dx, None, x2, None, xn3, g2, dhpre, None, None, None, None, g_n3_w, g_n3_b, B, T, H, wp, r0, None, l1_b,
+                      None, n3_w, dropout=cfg.drop(8 * l + 4), blocks=ops.LAYER_FFN, w_row_ffn=r0 + 1024,
+                      dropout_stream_ffn=cfg.stream_base + 8 * l + 4)
+    ops.wgrad_bf16([(dhpre, 0, xn3, 0, _p(g_l1_w), d, _p(g_l1_b)), (g2, 0, hact, 0, _p(g_l2_w), d, _p(g_l2_b))], M)
+    # cross-attention block (per-op kernels)
+    dh = _ca_bwd(dx, s2, mem2, dmem, B, T, Mm, H, ca_in_w, ca_out_w, n2_w, n2_b, g_ca_in_w, g_ca_in_b, g_ca_out_w, g_ca_out_b,
+                 g_n2_w, g_n2_b, cfg, 8 * l + 2)
+    # self-attention block
+    ops.enc_layer_bwd(dh, dx, h_in, None, xn1, None, None, None, g1, dqkv, g_n1_w, g_n1_b, None, None, B, T, H, wp, r0, sa_in_b,
+                      None, n1_w, None, dropout=cfg.drop(8 * l), blocks=ops.LAYER_SA)
+    ops.wgrad_bf16([(dqkv, 0, xn1, 0, _p(g_sa_in_w), d, _p(g_sa_in_b)),
+                    (dqkv, d, xn1, 0, _p(g_sa_in_w, d * d), d, _p(g_sa_in_b, d)),
+                    (dqkv, 2 * d, xn1, 0, _p(g_sa_in_w, 2 * d * d), d, _p(g_sa_in_b, 2 * d)),
+                    (g1, 0, attn, 0, _p(g_sa_out_w), d, _p(g_sa_out_b))], M)
+    return dx
+
+
 class DenoiserFn(torch.autograd.Function):
     """Linear(J->d)+PE, L pre-LN decoder layers over memory, Linear(d->J) (decoder.py:47-54)."""
 
@@ -338,9 +414,16 @@ class DenoiserFn(torch.autograd.Function):
         h = _empty((Mq, d), mem2)
         ops.gemm(x2, J, MK, emb_w, J, NK, h, d, Mq, d, J, precision=cfg.precision, bias=emb_b, pe=pe, pe_period=T)
         acts = []
+        fused = L > 0 and _fused_enc_ok(cfg, d, layer_params[8].shape[0], T, H)
+        wp = _pack_dec_weights(layer_params, L, d) if fused else None
         for l in range(L):
+            P = layer_params[l * DEC_PARAMS_PER_LAYER: (l + 1) * DEC_PARAMS_PER_LAYER]
+            if fused:
+                h, sv = _dec_layer_fused_fwd(h, mem2, B, T, Mm, H, P, wp, l, cfg, save)
+                acts.append(sv)
+                continue
             (sa_in_w, sa_in_b, sa_out_w, sa_out_b, ca_in_w, ca_in_b, ca_out_w, ca_out_b, l1_w, l1_b, l2_w, l2_b, n1_w,
-             n1_b, n2_w, n2_b, n3_w, n3_b) = layer_params[l * DEC_PARAMS_PER_LAYER: (l + 1) * DEC_PARAMS_PER_LAYER]
+             n1_b, n2_w, n2_b, n3_w, n3_b) = P
             h, s1 = _sa_fwd(h, B, T, H, sa_in_w, sa_in_b, sa_out_w, sa_out_b, n1_w, n1_b, cfg, 8 * l, save)
             h, s2 = _ca_fwd(h, mem2, B, T, Mm, H, ca_in_w, ca_in_b, ca_out_w, ca_out_b, n2_w, n2_b, cfg, 8 * l + 2, save)
             h, s3 = _ffn_fwd(h, l1_w, l1_b, l2_w, l2_b, n3_w, n3_b, cfg, 8 * l + 4, save)
@@ -348,7 +431,7 @@ class DenoiserFn(torch.autograd.Function):
         out = _empty((Mq, J), mem2)
         ops.gemm(h, d, MK, fc_w, d, NK, out, J, Mq, J, d, precision=cfg.precision, bias=fc_b)
         if save:
-            ctx.cfg, ctx.dims, ctx.acts, ctx.h_last = cfg, (B, T, Mm, H, d, J, L), acts, h
+            ctx.cfg, ctx.dims, ctx.acts, ctx.h_last, ctx.fused = cfg, (B, T, Mm, H, d, J, L), acts, h, wp
             ctx.save_for_backward(x2, mem2, emb_w, emb_b, fc_w, fc_b, *layer_params)
         return out.view(B, T, J)
 
@@ -367,7 +450,15 @@ class DenoiserFn(torch.autograd.Function):
         ops.gemm(do, J, MK, fc_w, d, KN, dh, d, Mq, d, J, precision=cfg.precision)
         need_dmem = ctx.needs_input_grad[7]
         dmem = torch.zeros((B * Mm, d), device=mem2.device, dtype=torch.float32) if need_dmem else None
+        bufs = None
+        if ctx.fused is not None:
+            bufs = (_bf16((Mq, d), mem2), _bf16((Mq, d), mem2), _bf16((Mq, d), mem2), _bf16((Mq, 3 * d), mem2), _empty((Mq, d), mem2))
         for l in reversed(range(L)):
+            if ctx.fused is not None:
+                dh = _dec_layer_fused_bwd(dh, ctx.acts[l], mem2, dmem, B, T, Mm, H,
+                                          layer_params[l * DEC_PARAMS_PER_LAYER: (l + 1) * DEC_PARAMS_PER_LAYER],
+                                          g_layers[l * DEC_PARAMS_PER_LAYER: (l + 1) * DEC_PARAMS_PER_LAYER], ctx.fused, l, cfg, bufs)
+                continue
             (sa_in_w, sa_in_b, sa_out_w, sa_out_b, ca_in_w, ca_in_b, ca_out_w, ca_out_b, l1_w, l1_b, l2_w, l2_b, n1_w,
              n1_b, n2_w, n2_b, n3_w, n3_b) = layer_params[l * DEC_PARAMS_PER_LAYER: (l + 1) * DEC_PARAMS_PER_LAYER]
             (g_sa_in_w, g_sa_in_b, g_sa_out_w, g_sa_out_b, g_ca_in_w, g_ca_in_b, g_ca_out_w, g_ca_out_b, g_l1_w, g_l1_b,

@@ -429,41 +429,56 @@ def enc_layer_supported(d: int, ff: int, S: int, H: int) -> bool:
     return bool(_lib.lib().sd_enc_layer_supported(d, ff, S, H))
 
 
-def enc_layer_fwd(x, y, B, S, H, w_packed, w_row0, in_b, out_b, l1_b, l2_b, n1_w, n1_b, n2_w, n2_b, saves=None, dropout=None):
-    """One fused encoder layer (sd_enc_layer_fwd).  ``saves`` = (x1 fp32, xn1, attn, xn2, hact bf16) or None."""
+LAYER_SA, LAYER_FFN = 1, 2   # sd_enc_layer_desc.blocks
+
+
+def _dp(t):
+    return None if t is None else t.data_ptr()
+
+
+def enc_layer_fwd(x, y, B, S, H, w_packed, w_row0, in_b, out_b, l1_b, l2_b, n1_w, n1_b, n2_w, n2_b, saves=None, dropout=None,
+                  blocks=0, w_row_ffn=0, dropout_stream_ffn=0):
+    """One fused layer forward (sd_enc_layer_fwd).  ``saves`` = (x1 fp32, xn1, attn, xn2, hact bf16) or None; ``blocks``:
+    0 = whole encoder layer, LAYER_SA / LAYER_FFN = one half (decoder layers; unused parameters / saves may be None)."""
     d = _lib.EncLayerDesc()
     d.x, d.y, d.B, d.S, d.H = x.data_ptr(), y.data_ptr(), B, S, H
     d.w_packed, d.w_rows_total, d.w_row0 = w_packed.data_ptr(), w_packed.shape[0], w_row0
-    d.in_b, d.out_b, d.l1_b, d.l2_b = in_b.data_ptr(), out_b.data_ptr(), l1_b.data_ptr(), l2_b.data_ptr()
-    d.n1_w, d.n1_b, d.n2_w, d.n2_b = n1_w.data_ptr(), n1_b.data_ptr(), n2_w.data_ptr(), n2_b.data_ptr()
+    d.in_b, d.out_b, d.l1_b, d.l2_b = _dp(in_b), _dp(out_b), _dp(l1_b), _dp(l2_b)
+    d.n1_w, d.n1_b, d.n2_w, d.n2_b = _dp(n1_w), _dp(n1_b), _dp(n2_w), _dp(n2_b)
     if saves is not None:
-        d.x1_save, d.xn1_save, d.attn_save, d.xn2_save, d.hact_save = (t.data_ptr() for t in saves)
+        d.x1_save, d.xn1_save, d.attn_save, d.xn2_save, d.hact_save = (_dp(t) for t in saves)
     if dropout is not None and dropout[0] > 0.0:
         d.dropout_p, d.dropout_seed, d.dropout_stream = dropout
+    d.blocks, d.w_row_ffn, d.dropout_stream_ffn = blocks, w_row_ffn, dropout_stream_ffn
     M = B * S
-    # algorithmic work of the layer (SURVEY.md §8d): 12 S d^2 + 4 S^2 d per sample
-    with _Timed("fused_enc_layer_fwd", B * (12.0 * S * 128 * 128 + 4.0 * S * S * 128),
-                M * 128 * (8.0 + (4.0 + 8.0 if saves is not None else 0.0)), f"[B{B} S{S} H{H}]"):
+    sa, ffn = blocks in (0, LAYER_SA), blocks in (0, LAYER_FFN)
+    # algorithmic work (SURVEY.md §8d): attention block 8 S d^2 + 4 S^2 d, feed-forward block 4 S d^2 per sample
+    flops = B * ((8.0 * S * 128 * 128 + 4.0 * S * S * 128) * sa + 4.0 * S * 128 * 128 * ffn)
+    name = "fused_enc_layer_fwd" if blocks == 0 else ("fused_sa_block_fwd" if sa else "fused_ffn_block_fwd")
+    with _Timed(name, flops, M * 128 * (8.0 + (4.0 + 8.0 if saves is not None else 0.0)), f"[B{B} S{S} H{H}]"):
         check(_lib.lib().sd_enc_layer_fwd(C.byref(d), stream_ptr()), "sd_enc_layer_fwd")
     _count()
 
 
 def enc_layer_bwd(dy, dx, x, x1, xn1, xn2, g2, dhpre, g1, dqkv, g_n1_w, g_n1_b, g_n2_w, g_n2_b, B, S, H, w_packed, w_row0,
-                  in_b, l1_b, n1_w, n2_w, dropout=None):
-    """Data-path backward of one fused encoder layer (sd_enc_layer_bwd)."""
+                  in_b, l1_b, n1_w, n2_w, dropout=None, blocks=0, w_row_ffn=0, dropout_stream_ffn=0):
+    """Data-path backward of one fused layer / half layer (sd_enc_layer_bwd)."""
     d = _lib.EncLayerBwdDesc()
-    d.dy, d.dx, d.x, d.x1, d.xn1, d.xn2 = (t.data_ptr() for t in (dy, dx, x, x1, xn1, xn2))
-    d.g2, d.dhpre, d.g1, d.dqkv = (t.data_ptr() for t in (g2, dhpre, g1, dqkv))
-    d.g_n1_w, d.g_n1_b, d.g_n2_w, d.g_n2_b = (t.data_ptr() for t in (g_n1_w, g_n1_b, g_n2_w, g_n2_b))
+    d.dy, d.dx, d.x, d.x1, d.xn1, d.xn2 = (_dp(t) for t in (dy, dx, x, x1, xn1, xn2))
+    d.g2, d.dhpre, d.g1, d.dqkv = (_dp(t) for t in (g2, dhpre, g1, dqkv))
+    d.g_n1_w, d.g_n1_b, d.g_n2_w, d.g_n2_b = (_dp(t) for t in (g_n1_w, g_n1_b, g_n2_w, g_n2_b))
     d.B, d.S, d.H = B, S, H
     d.w_packed, d.w_rows_total, d.w_row0 = w_packed.data_ptr(), w_packed.shape[0], w_row0
-    d.in_b, d.l1_b, d.n1_w, d.n2_w = in_b.data_ptr(), l1_b.data_ptr(), n1_w.data_ptr(), n2_w.data_ptr()
+    d.in_b, d.l1_b, d.n1_w, d.n2_w = _dp(in_b), _dp(l1_b), _dp(n1_w), _dp(n2_w)
     if dropout is not None and dropout[0] > 0.0:
         d.dropout_p, d.dropout_seed, d.dropout_stream = dropout
+    d.blocks, d.w_row_ffn, d.dropout_stream_ffn = blocks, w_row_ffn, dropout_stream_ffn
     M = B * S
-    # data gradients: 2x the forward GEMMs minus the weight gradients' share, plus the recomputed forward
-    with _Timed("fused_enc_layer_bwd", B * (16.0 * S * 128 * 128 + 12.0 * S * S * 128), M * 128 * (4.0 * 4 + 2.0 * 2 + 2.0 * 6),
-                f"[B{B} S{S} H{H}]"):
+    sa, ffn = blocks in (0, LAYER_SA), blocks in (0, LAYER_FFN)
+    # data gradients + the recomputed forward GEMMs (weight gradients are sd_wgrad_bf16's)
+    flops = B * ((12.0 * S * 128 * 128 + 12.0 * S * S * 128) * sa + 6.0 * S * 128 * 128 * ffn)
+    name = "fused_enc_layer_bwd" if blocks == 0 else ("fused_sa_block_bwd" if sa else "fused_ffn_block_bwd")
+    with _Timed(name, flops, M * 128 * (4.0 * 4 + 2.0 * 2 + 2.0 * 6), f"[B{B} S{S} H{H}]"):
         check(_lib.lib().sd_enc_layer_bwd(C.byref(d), stream_ptr()), "sd_enc_layer_bwd")
     _count()
 
