@@ -80,3 +80,58 @@ class DevicePrefetcher:
         cur.wait_event(ready)
         self.in_use = i
         return dev
+
+
+# ---- NUMA placement of the feeding process ---------------------------------------------------------------------------------
+def _parse_cpulist(text: str) -> set:
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_node(device_index: int, sysfs: str = "/sys") -> int | None:
+    """NUMA node the GPU's PCIe root is attached to (from sysfs), or None when the platform does not say."""
+    import os
+
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(os.path.join(sysfs, "bus", "pci", "devices", bdf, "numa_node")) as fh:
+            node = int(fh.read().strip())
+        return node if node >= 0 else None
+    except (OSError, ValueError, AttributeError, RuntimeError, AssertionError):
+        return None
+
+
+def bind_to_numa_node(node: int | None, sysfs: str = "/sys") -> dict:
+    """Pins the calling process (one rank per GPU) to the CPUs of ``node`` and prefers that node for its allocations, so the
+    pinned staging buffers it creates afterwards sit next to the GPU's PCIe root (with 8 ranks feeding 8 GPUs from one
+    socket's memory, the far socket's ranks copy across the inter-socket link: measured H2D 52 -> 25 GB/s).
+    No-op (and says so) when the node is unknown or the platform refuses."""
+    import ctypes
+    import os
+
+    info = dict(node=node, cpus=None, mempolicy=False)
+    if node is None:
+        return info
+    try:
+        with open(os.path.join(sysfs, "devices", "system", "node", f"node{node}", "cpulist")) as fh:
+            cpus = _parse_cpulist(fh.read())
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["cpus"] = len(allowed)
+    except (OSError, ValueError):
+        return info
+    try:   # set_mempolicy(MPOL_PREFERRED, {node}) — x86_64 syscall 238; best effort
+        libc = ctypes.CDLL(None, use_errno=True)
+        mask = (ctypes.c_ulong * 16)()
+        mask[node // 64] = 1 << (node % 64)
+        info["mempolicy"] = libc.syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(16 * 64)) == 0
+    except (OSError, AttributeError, ValueError):
+        pass
+    return info
