@@ -97,7 +97,7 @@ def run_case(name, hp, batch_size, ddim_steps, seed, with_grads=True, full_grads
             norms.append(float(p.grad.double().norm()))
             # full gradients only for the in-scope stack (small); trunk gradients by norm
             if ".image_encoder.encoder." not in n or n.endswith(("fc.weight", "fc.bias", "avgpool.weight", "avgpool.bias")):
-                if p.grad.numel() <= 70000 and (full_grads is None or any(k in n for k in full_grads)):
+                if p.grad.numel() <= (70000 if hp["hidden_dim"] <= 128 else 20000) and (full_grads is None or any(k in n for k in full_grads)):
                     out["grad/" + n] = p.grad.numpy().copy()
         out["grad_names"] = np.asarray(names)
         out["grad_norms"] = np.asarray(norms, dtype=np.float64)
@@ -118,6 +118,11 @@ def main():
     manifest["cases"]["default"] = run_case(
         "default", synth.DEFAULT_HP, 2, 30, 2,
         full_grads=("layers.0.", "layers.3.", "embedding", "fc_out", "step_encoding", "avgpool.bias", "fc.bias"))
+    # the reference's other shipped configurations (frame resolution reduced, see oracle/synth.py) and the scaled-up one
+    small = ("layers.0.", "embedding", "fc_out", "step_encoding", "fc.bias", "norm")
+    manifest["cases"]["larger"] = run_case("larger", synth.LARGER_HP, 1, 10, 5, full_grads=small)
+    manifest["cases"]["sim_scratch"] = run_case("sim_scratch", synth.SIM_SCRATCH_HP, 2, 10, 6, full_grads=small)
+    manifest["cases"]["scaled_img"] = run_case("scaled_img", synth.SCALED_IMG_HP, 2, 10, 7, full_grads=small)
     with open(os.path.join(GOLDEN, "manifest.json"), "w") as fh:
         json.dump(manifest, fh, indent=1)
     for f in sorted(os.listdir(GOLDEN)):

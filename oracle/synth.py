@@ -209,6 +209,41 @@ SCALED_HP = dict(
     trajectory_prediction_length=20,
 )
 
+# ml/training/config/larger_model.yaml:1-27 verbatim (d=512, dh=128, encoders 4/4/4/1, 8 decoder layers; the YAML sets
+# neither image_resolution nor image_use_final_avgpool -> train.py's .get defaults 480 / True), except the resolution of the
+# synthetic frames (the avg-pooled head makes every other shape independent of it)
+LARGER_HP = dict(
+    DEFAULT_HP,
+    hidden_dim=512,
+    num_action_history_encoder_layers=4,
+    num_imu_encoder_layers=4,
+    joint_state_encoder_layers=4,
+    num_image_sequence_encoder_layers=1,
+    num_decoder_layers=8,
+    image_use_final_avgpool=True,
+    image_resolution=96,
+)
+
+# ml/training/config/sim_scratch.yaml verbatim (d=256, patch 5, five_dim IMU, no joint states, no game state, 6 decoder
+# layers, un-pooled image head), except the frame resolution (224 -> 64: the fc layer of the head follows it)
+SIM_SCRATCH_HP = dict(
+    DEFAULT_HP,
+    hidden_dim=256,
+    num_action_history_encoder_layers=4,
+    imu_orientation_embedding_method="five_dim",
+    num_imu_encoder_layers=2,
+    use_joint_states=False,
+    joint_state_encoder_layers=4,
+    image_use_final_avgpool=False,
+    image_resolution=64,
+    num_decoder_layers=6,
+    use_gamestate=False,
+    encoder_patch_size=5,
+)
+
+# the scaled-up configuration WITH its image branch, at a frame size a fixture can afford
+SCALED_IMG_HP = dict(SCALED_HP, image_resolution=64)
+
 # a patchified, five_dim, J=22 variant exercising the non-default branches (sim_scratch-like)
 PATCH_HP = dict(
     TINY_HP,
