@@ -130,8 +130,11 @@ int sd_affine_joints(const float* x, const float* mean, const float* std, float*
 int sd_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int step, float grad_scale, void* stream);
 /* the same update with the hyper-parameters in device memory: hyper_dev = {lr, beta1, beta2, eps, weight_decay,
- * lr/(1-beta1^t), 1/sqrt(1-beta2^t), grad_scale} — capturable in a CUDA graph while OneCycleLR advances on the host */
-int sd_adamw_step_dev(float* p, const float* g, float* m, float* v, long long n, const float* hyper_dev, void* stream);
+ * lr/(1-beta1^t), 1/sqrt(1-beta2^t), grad_scale} — capturable in a CUDA graph while OneCycleLR advances on the host.
+ * step_dev != NULL: t is read from device memory (a counter the captured graph itself advances) and the two bias
+ * corrections are computed in the kernel; hyper_dev[5..6] are then ignored. */
+int sd_adamw_step_dev(float* p, const float* g, float* m, float* v, long long n, const float* hyper_dev, const int* step_dev,
+                      void* stream);
 /* device-resident counter added to every dropout seed (NULL = off): advancing it between CUDA-graph replays gives
  * each replay fresh masks although the host-side seeds are frozen in the graph */
 int sd_set_dropout_seed_offset(const unsigned long long* device_counter);

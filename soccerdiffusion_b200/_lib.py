@@ -117,7 +117,7 @@ SIGNATURES = {
     "sd_mse_bwd": [c_f, c_f, c_ll, c_f, c_f, c_f],
     "sd_affine_joints": [c_f, c_f, c_f, c_f, c_ll, c_i, c_i, c_f],
     "sd_adamw_step": [c_f, c_f, c_f, c_f, c_ll, c_fl, c_fl, c_fl, c_fl, c_fl, c_i, c_fl, c_f],
-    "sd_adamw_step_dev": [c_f, c_f, c_f, c_f, c_ll, c_f, c_f],
+    "sd_adamw_step_dev": [c_f, c_f, c_f, c_f, c_ll, c_f, c_f, c_f],
     "sd_set_dropout_seed_offset": [c_f],
     "sd_gather_rows": [c_f, c_f, c_i, c_f, c_ll, c_i, c_i, c_f, c_f],
     "sd_scatter_add_rows": [c_f, c_ll, c_f, c_i, c_f, c_i, c_i, c_f],

@@ -397,9 +397,22 @@ extern "C" int sd_set_dropout_seed_offset(const unsigned long long* device_count
 // inv_sqrt_bc2, grad_scale} (step_size = lr / (1 - beta1^t), inv_sqrt_bc2 = 1/sqrt(1 - beta2^t)).  Lets the
 // optimizer launch live inside a captured CUDA graph while the learning-rate schedule advances on the host.
 __global__ void adamw_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                 float* __restrict__ v, long long n, const float* __restrict__ hp) {
-    const float lr = hp[0], b1 = hp[1], b2 = hp[2], eps = hp[3], wd = hp[4], step_size = hp[5], inv_sqrt_bc2 = hp[6],
-                gscale = hp[7];
+                                 float* __restrict__ v, long long n, const float* __restrict__ hp,
+                                 const int* __restrict__ step_dev) {
+    const float lr = hp[0], b1 = hp[1], b2 = hp[2], eps = hp[3], wd = hp[4], gscale = hp[7];
+    float step_size = hp[5], inv_sqrt_bc2 = hp[6];
+    if (step_dev != nullptr) {
+        // the step count lives on the device (advanced inside the captured graph): bias corrections in double, once per block
+        __shared__ float bc[2];
+        if (threadIdx.x == 0) {
+            const double t = (double)max(*step_dev, 1);
+            bc[0] = (float)((double)lr / (1.0 - pow((double)b1, t)));
+            bc[1] = (float)(1.0 / sqrt(1.0 - pow((double)b2, t)));
+        }
+        __syncthreads();
+        step_size = bc[0];
+        inv_sqrt_bc2 = bc[1];
+    }
     const long long n4 = n >> 2;
     const float decay = 1.0f - lr * wd;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -434,13 +447,13 @@ __global__ void adamw_dev_kernel(float* __restrict__ p, const float* __restrict_
     }
 }
 extern "C" int sd_adamw_step_dev(float* p, const float* g, float* m, float* v, long long n, const float* hyper_dev,
-                                 void* stream) {
+                                 const int* step_dev, void* stream) {
     if (n <= 0) return SD_OK;
     if (!p || !g || !m || !v || !hyper_dev) return SD_ERR_BAD_ARG;
     if ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) != 0) return SD_ERR_BAD_ARG;
     const int threads = 256;
     const int blocks = min(ceil_div((n + 3) / 4, threads), 148 * 8);
-    adamw_dev_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(p, g, m, v, n, hyper_dev);
+    adamw_dev_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(p, g, m, v, n, hyper_dev, step_dev);
     SD_LAUNCH_CHECK();
     return SD_OK;
 }

@@ -35,14 +35,15 @@ class GraphedTrainStep:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup_steps):
-                self.opt.prepare_captured_step()
+                self.opt.prepare_captured_step(self._grad_scale())
                 self._body()
+                self.opt.commit_captured_step()
                 self.opt._opt_called = True    # the optimizer step ran (step_captured): what lr_scheduler's order check tracks
                 if self.lrs is not None:
                     self.lrs.step()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.opt.prepare_captured_step()
+        self.opt.prepare_captured_step(self._grad_scale())
         n0 = ops.launches()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
@@ -55,8 +56,8 @@ class GraphedTrainStep:
     def _snapshot(self):
         import copy
 
-        flats = [{k: f[k].clone() for k in ("p", "m", "v")} if f is not None else None for f in self.opt._flat]
-        steps = [f["step"] if f is not None else None for f in self.opt._flat]
+        flats = [{k: f[k].clone() for k in ("p", "m", "v", "pstep_dev")} if f is not None else None for f in self.opt._flat]
+        steps = [list(f["pstep"]) if f is not None else None for f in self.opt._flat]
         groups = [{k: copy.deepcopy(v) for k, v in g.items() if k != "params"} for g in self.opt.param_groups]
         buffers = [b.clone() for b in self.model.buffers()]
         lrs = copy.deepcopy(self.lrs.state_dict()) if self.lrs is not None else None
@@ -69,11 +70,10 @@ class GraphedTrainStep:
             for f, saved, step in zip(self.opt._flat, snap["flats"], snap["steps"]):
                 if f is None:
                     continue
-                for k in ("p", "m", "v"):
+                for k in ("p", "m", "v", "pstep_dev"):
                     f[k].copy_(saved[k])
                 f["g"].zero_()
-                f["step"] = step
-                f["step_t"].fill_(float(step))
+                f["pstep"][:] = step
             for g, saved in zip(self.opt.param_groups, snap["groups"]):
                 g.update(saved)
             for b, saved in zip(self.model.buffers(), snap["buffers"]):
@@ -106,9 +106,16 @@ class GraphedTrainStep:
         finally:
             runtime.set_direct_grads(prev)
         if self.dp:
-            allreduce_gradients(self.opt, self.group)
+            allreduce_gradients(self.opt, self.group, average=False)   # the 1/world factor is the AdamW kernel's grad_scale
         self.opt.step_captured()
         return loss.detach()
+
+    def _grad_scale(self) -> float:
+        if not self.dp:
+            return 1.0
+        import torch.distributed as dist
+
+        return 1.0 / dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1.0
 
     def __call__(self, batch: dict) -> torch.Tensor:
         """One training iteration on ``batch`` (device tensors); returns the (static) loss tensor."""
@@ -121,8 +128,9 @@ class GraphedTrainStep:
                               decoder_pretraining=self.pretrain, group=self.group, data_parallel=self.dp)
         for k, v in self.static.items():
             v.copy_(batch[k], non_blocking=True)
-        self.opt.prepare_captured_step()
+        self.opt.prepare_captured_step(self._grad_scale())
         self.graph.replay()
+        self.opt.commit_captured_step()
         ops._count(self.launches_per_replay)
         self.opt._opt_called = True            # the replayed graph contains the optimizer step
         if self.lrs is not None:

@@ -26,9 +26,10 @@ def broadcast_parameters(model: torch.nn.Module, src: int = 0, group=None):
             dist.broadcast(t.data, src=src, group=group)
 
 
-def allreduce_gradients(optimizer_or_tensors, group=None):
-    """Mean of the gradients over ranks.  Accepts a FusedAdamW (flat buffers: one collective per
-    parameter group) or an iterable of gradient tensors."""
+def allreduce_gradients(optimizer_or_tensors, group=None, average: bool = True):
+    """Mean of the gradients over ranks (``average=False``: the sum — the caller folds 1/world into the optimizer
+    kernel's ``grad_scale``).  Accepts a FusedAdamW (flat buffers: one collective per parameter group) or an iterable of
+    gradient tensors."""
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()):
@@ -40,7 +41,8 @@ def allreduce_gradients(optimizer_or_tensors, group=None):
         optimizer_or_tensors)
     for g in bufs:
         dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
-        g.mul_(1.0 / world)
+        if average:
+            g.mul_(1.0 / world)
 
 
 def q_sample(scheduler, normalizer_or_model, joint_command, noise, timesteps):
@@ -77,9 +79,16 @@ def train_step(model, optimizer, scheduler, normalizer, batch, *, lr_scheduler=N
         pred = model(batch, noisy, timesteps)
     loss = mse_loss(pred, noise)
     loss.backward()
-    if data_parallel:
-        allreduce_gradients(optimizer, group)
-    optimizer.step()
+    if data_parallel and hasattr(optimizer, "flat_gradients"):
+        import torch.distributed as dist
+
+        allreduce_gradients(optimizer, group, average=False)
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        optimizer.step(grad_scale=1.0 / world)      # the mean over ranks is taken inside the AdamW kernel
+    else:
+        if data_parallel:
+            allreduce_gradients(optimizer, group)
+        optimizer.step()
     if lr_scheduler is not None:
         lr_scheduler.step()
     return loss.detach()

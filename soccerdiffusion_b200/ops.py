@@ -223,10 +223,12 @@ def adamw_step(p, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale=1.0):
     _count()
 
 
-def adamw_step_dev(p, g, m, v, hyper_dev):
+def adamw_step_dev(p, g, m, v, hyper_dev, step_dev=None):
+    """``step_dev``: 1-element int32 device tensor holding t (bias corrections computed in the kernel), or None."""
     with _Timed("adamw", 0.0, 28.0 * p.numel()):
         check(_lib.lib().sd_adamw_step_dev(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(),
-                                           hyper_dev.data_ptr(), stream_ptr()), "sd_adamw_step_dev")
+                                           hyper_dev.data_ptr(), None if step_dev is None else step_dev.data_ptr(),
+                                           stream_ptr()), "sd_adamw_step_dev")
     _count()
 
 

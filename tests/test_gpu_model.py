@@ -467,7 +467,7 @@ def test_graphed_train_step_matches_eager_steps():
     for n, v in m2.state_dict().items():
         assert torch.equal(v, before[n]), n
     assert o2.param_groups[0]["lr"] == lr_before and l2.last_epoch == 0
-    assert all(float(st["step"]) == 0.0 for st in o2.state.values())
+    assert all(float(st["step"]) == 0.0 for st in o2.state_dict()["state"].values())
     got = [g(b).item() for b in [batches[0]] * 3 + batches[1:]]
     for a, b_ in zip(got, eager):
         assert abs(a - b_) < 1e-5 * abs(b_), (got, eager)
@@ -547,3 +547,102 @@ def test_scaled_up_config_forward_and_batched_sampler():
         x0 = model.sample(ctx, x_T.cuda(), sch, sampler=kind)
         assert rel(x0, w0) < TOL, kind
         assert model.last_sampler == kind
+
+
+# ---------------------------------------------------------------------------------------------------
+# plan caches and optimizer semantics across CALLS (the kernels write through raw pointers: tensor versions never move,
+# and the caching allocator reuses addresses)
+def test_consecutive_ticks_and_training_do_not_reuse_stale_plans():
+    from soccerdiffusion_b200.ml.inference import TrajectorySampler
+    from soccerdiffusion_b200.ml.training import FusedAdamW, train_step
+    from soccerdiffusion_b200.dataset.pytorch import Normalizer
+    from soccerdiffusion_b200.schedulers import DDIMScheduler
+
+    hp = synth.TINY_HP
+    model, sd = synth_model(hp, 3)
+    model.eval()
+    sch = DDIMScheduler(beta_schedule="squaredcos_cap_v2", clip_sample=False)
+    ts = TrajectorySampler(model, sch, 10)                     # the non-graph control loop (ros.py:259-318)
+    for seed in (4, 5, 6, 4):                                  # every tick: new inputs at (most likely) the same addresses
+        b = synth.synth_batch(hp, 1, seed)
+        x_T = synth.synth_noise("x_T", hp, 1, seed)
+        got = ts(to_dev(b), x_T.cuda())
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            ctx = model_ref.encode_input_data(b, sd, hp)
+            want, _ = model_ref.sample_ddim(ctx, x_T, sd, hp, 10)
+        assert rel(got, want * sd["std"] + sd["mean"]) < TOL, seed
+    # sample -> train step -> sample: the packed sampler weights follow the optimizer
+    b = synth.synth_batch(hp, 2, 9)
+    x_T = synth.synth_noise("x_T", hp, 2, 9).cuda()
+    sch.set_timesteps(10)
+    with torch.no_grad():
+        ctx = model.encode_input_data(to_dev(b))
+        before = model.sample(ctx, x_T, sch).clone()
+    model.train()
+    opt = FusedAdamW(model.parameters(), lr=5e-2)
+    train_step(model, opt, sch, Normalizer(model.mean, model.std), to_dev(b))
+    model.eval()
+    sch.set_timesteps(10)
+    with torch.no_grad():
+        ctx2 = model.encode_input_data(to_dev(b))
+        after = model.sample(ctx2, x_T, sch)
+        sd2 = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        c2 = model_ref.encode_input_data(b, sd2, hp)
+        want, _ = model_ref.sample_ddim(c2, x_T.cpu(), sd2, hp, 10)
+    assert rel(after, before) > 1e-3          # the step changed the model ...
+    assert rel(after, want) < 5e-4            # ... and the sampler ran on the NEW weights
+    # mismatched batch sizes raise instead of reading out of bounds
+    with pytest.raises(RuntimeError):
+        model.sample(ctx2, x_T[:1], sch)
+
+
+def test_distill_step_twice_uses_each_batchs_own_teacher_context():
+    from soccerdiffusion_b200 import runtime
+    from soccerdiffusion_b200.ml.training import FusedAdamW, distill_step
+    from soccerdiffusion_b200.schedulers import DDIMScheduler
+
+    runtime.set_dropout(0.0)
+    hp = synth.PATCH_HP
+    B = 2
+    teacher, sd_t = synth_model(hp, 31)
+    student, sd_s = synth_model(hp, 32)
+    student.train()
+    sch = DDIMScheduler(beta_schedule="squaredcos_cap_v2", clip_sample=False)
+    opt = FusedAdamW(student.parameters(), lr=0.0)
+    for seed in (33, 34, 35):
+        batch = synth.synth_batch(hp, B, seed)
+        noise = synth.synth_noise("x_T", hp, B, seed)
+        loss = distill_step(teacher, student, opt, sch, to_dev(batch), 30, noise=noise.cuda())
+        with torch.no_grad():
+            ctx = model_ref.encode_input_data(batch, sd_t, hp)
+            traj, _ = model_ref.sample_ddim(ctx, noise, sd_t, hp, 30)
+            pred = model_ref.forward_with_context(ctx, noise, torch.zeros(B), sd_s, hp)
+            want = torch.nn.functional.mse_loss(pred, traj)
+        assert abs(loss.item() - want.item()) < 2e-4 * abs(want.item()), seed
+
+
+def test_fused_adamw_skips_parameters_without_gradient_like_torch():
+    """--decoder-pretraining (train.py:221-224): the encoders receive no gradient; torch.optim.AdamW leaves such parameters
+    untouched (no weight decay either), and so must FusedAdamW."""
+    from soccerdiffusion_b200.ml.training import FusedAdamW
+
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(37, device="cuda")) for _ in range(5)]
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    o1 = FusedAdamW(ps, lr=1e-2, weight_decay=0.1)
+    o2 = torch.optim.AdamW(qs, lr=1e-2, weight_decay=0.1)
+    for it in range(3):
+        used = [0, 2, 3] if it != 1 else [2, 4]
+        o1.zero_grad()
+        o2.zero_grad()
+        gs = [torch.randn(37, device="cuda") for _ in used]
+        sum((ps[i] * g).sum() for i, g in zip(used, gs)).backward()
+        sum((qs[i] * g).sum() for i, g in zip(used, gs)).backward()
+        o1.step()
+        o2.step()
+        for i, (a, b) in enumerate(zip(ps, qs)):
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-7), (it, i)
+    assert torch.equal(ps[1].detach(), qs[1].detach())     # never used: bit-identical to its initial value
+    st = o1.state_dict()["state"]
+    assert all(float(v["step"]) == 3.0 for v in st.values())
