@@ -644,5 +644,6 @@ def test_fused_adamw_skips_parameters_without_gradient_like_torch():
         for i, (a, b) in enumerate(zip(ps, qs)):
             assert torch.allclose(a, b, rtol=1e-5, atol=1e-7), (it, i)
     assert torch.equal(ps[1].detach(), qs[1].detach())     # never used: bit-identical to its initial value
-    st = o1.state_dict()["state"]
-    assert all(float(v["step"]) == 3.0 for v in st.values())
+    st, st_t = o1.state_dict()["state"], o2.state_dict()["state"]
+    assert [float(st[i]["step"]) for i in range(5)] == [2.0, 0.0, 3.0, 2.0, 1.0]          # per parameter, as torch counts
+    assert all(float(st[i]["step"]) == float(st_t[i]["step"]) for i in st_t)
