@@ -576,6 +576,25 @@ class GatherRowsFn(torch.autograd.Function):
         return dtable, None
 
 
+class GradReadyFn(torch.autograd.Function):
+    """Identity in the forward pass; its backward fires ``runtime.grad_ready(tag)`` once ALL ``state["need"]`` twins of the
+    marked activation have received their gradient — every backward node downstream of the mark has then run."""
+
+    @staticmethod
+    def forward(ctx, x, tag: str, state: dict):
+        ctx.tag, ctx.state = tag, state
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import runtime
+
+        ctx.state["seen"] += 1
+        if ctx.state["seen"] == ctx.state["need"]:
+            runtime.grad_ready(ctx.tag)
+        return g, None, None
+
+
 class MseLossFn(torch.autograd.Function):
     """F.mse_loss(pred, target) with mean reduction (train.py:229)."""
 

@@ -13,7 +13,7 @@ import os
 import torch
 import torch.nn.functional as F
 
-from soccerdiffusion_b200 import ops
+from soccerdiffusion_b200 import ops, runtime
 
 _USE_TC_STEM_WGRAD = os.environ.get("SD_B200_STEM_WGRAD", "tc") == "tc"
 _USE_TC_STEM_FPROP = os.environ.get("SD_B200_STEM_FPROP", "tc") == "tc"
@@ -302,7 +302,18 @@ def resnet_trunk_bf16(encoder, images: torch.Tensor) -> torch.Tensor:
         # ``fork`` the two consumers get twin outputs, so their gradients reach the BatchNorm backward separately and
         # are summed inside its kernels (no elementwise-add pass over the activation gradient)
         x_main = x_skip = x
+        n12 = len(encoder.layer1) + len(encoder.layer2)
         for i, blk in enumerate(blocks):
+            if i == n12 and torch.is_grad_enabled() and runtime.grad_ready_enabled() and x_main.requires_grad:
+                # backward-pass milestone: once the gradient reaches this point, layer3, layer4 and everything after the
+                # trunk (89 % of the parameters) have their gradients — the data-parallel all-reduce of that bucket starts
+                # here and overlaps the backward pass of layer2, layer1 and the stem
+                from soccerdiffusion_b200.functional import GradReadyFn
+
+                same = x_main is x_skip
+                st = {"need": 1 if same else 2, "seen": 0}
+                x_main = GradReadyFn.apply(x_main, "trunk.layer3_onward", st)
+                x_skip = x_main if same else GradReadyFn.apply(x_skip, "trunk.layer3_onward", st)
             fork = _BN_FORK and torch.is_grad_enabled() and i + 1 < len(blocks)
             identity = x_skip
             if blk.downsample is not None:

@@ -12,7 +12,7 @@ import torch
 
 from soccerdiffusion_b200 import ops, runtime
 from soccerdiffusion_b200.functional import mse_loss
-from soccerdiffusion_b200.ml.training.step import allreduce_gradients, q_sample
+from soccerdiffusion_b200.ml.training.step import BucketedAllReduce, q_sample
 
 
 class GraphedTrainStep:
@@ -26,6 +26,7 @@ class GraphedTrainStep:
         self.seed_counter = runtime.device_seed_counter(next(model.parameters()).device)
         self.direct_grads = direct_grads
         self.launches_per_replay = 0
+        self.reducer = BucketedAllReduce(model, optimizer, group) if data_parallel else None
         # Warm-up must leave no trace (the reference's loop takes exactly epochs * len(dataloader) optimizer and
         # OneCycleLR steps, train.py:172,239-240): parameters, AdamW moments and step counters, BatchNorm running
         # statistics, the LR schedule and the dropout seed counter are snapshotted here and restored after the capture.
@@ -101,12 +102,14 @@ class GraphedTrainStep:
         loss = mse_loss(pred, noise)
         prev = runtime.direct_grads()
         runtime.set_direct_grads(self.direct_grads)   # gradients land in FusedAdamW's flat buffer without autograd adds
+        if self.reducer is not None:
+            self.reducer.begin()                       # the big gradient bucket is all-reduced DURING the backward pass
         try:
             loss.backward()
         finally:
             runtime.set_direct_grads(prev)
-        if self.dp:
-            allreduce_gradients(self.opt, self.group, average=False)   # the 1/world factor is the AdamW kernel's grad_scale
+            if self.reducer is not None:
+                self.reducer.finish()                  # sum over ranks; the 1/world factor is the AdamW kernel's grad_scale
         self.opt.step_captured()
         return loss.detach()
 

@@ -45,6 +45,76 @@ def allreduce_gradients(optimizer_or_tensors, group=None, average: bool = True):
             g.mul_(1.0 / world)
 
 
+class BucketedAllReduce:
+    """Gradient SUM over the data-parallel ranks in two buckets, the first one overlapped with the backward pass.
+
+    The flat gradient buffer of ``FusedAdamW`` follows ``model.parameters()``: [step token, the three sequence encoders,
+    trunk conv1 .. layer2 | trunk layer3, layer4, image head, frame-sequence encoder, game state, denoiser].  The backward
+    pass finishes the second part first (it holds 89 % of the parameters); when its gradient milestone fires
+    (``runtime.grad_ready("trunk.layer3_onward")``, raised inside the trunk's backward) that bucket is all-reduced on a
+    communication stream while layer2, layer1 and the stem are still being differentiated.  ``finish()`` reduces the rest
+    (~5 MB) and joins the streams.  The mean (1/world) is applied by the optimizer kernel's ``grad_scale``.
+    Works eagerly and inside CUDA-graph capture (the communication stream forks from / joins the capturing stream)."""
+
+    SPLIT_PREFIX = "image_sequence_encoder.image_encoder.encoder.layer3."
+
+    def __init__(self, model: torch.nn.Module, optimizer, group=None):
+        self.opt, self.group = optimizer, group
+        self.split = None          # (flat group index, element offset) of the first parameter of the early bucket
+        flats = [f for f in optimizer._flat if f is not None]
+        if len(flats) == 1:
+            f = flats[0]
+            off_of = {id(p): o for p, o in zip(f["params"], f["offs"])}
+            for name, p in model.named_parameters():
+                if name.startswith(self.SPLIT_PREFIX) and id(p) in off_of:
+                    self.split = off_of[id(p)]
+                    break
+        self.comm = None
+        self.early_done = False
+
+    def _stream(self):
+        if self.comm is None:
+            self.comm = torch.cuda.Stream()
+        return self.comm
+
+    def begin(self):
+        """Call before the backward pass of a step."""
+        from soccerdiffusion_b200 import runtime
+
+        self.early_done = False
+        if self.split is not None:
+            runtime.set_grad_ready_callback(self._on_ready)
+
+    def _on_ready(self, tag: str):
+        import torch.distributed as dist
+
+        if tag != "trunk.layer3_onward" or self.early_done or self.split is None:
+            return
+        g = self.opt.flat_gradients()[0]
+        cur = torch.cuda.current_stream()
+        comm = self._stream()
+        comm.wait_stream(cur)
+        with torch.cuda.stream(comm):
+            dist.all_reduce(g[self.split:], op=dist.ReduceOp.SUM, group=self.group)
+        self.early_done = True
+
+    def finish(self):
+        """Call after the backward pass: reduces what the milestone did not cover and joins the communication stream."""
+        import torch.distributed as dist
+
+        from soccerdiffusion_b200 import runtime
+
+        runtime.set_grad_ready_callback(None)
+        cur = torch.cuda.current_stream()
+        if self.early_done:
+            g = self.opt.flat_gradients()[0]
+            dist.all_reduce(g[: self.split], op=dist.ReduceOp.SUM, group=self.group)
+            cur.wait_stream(self.comm)
+        else:
+            for g in self.opt.flat_gradients():
+                dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+
+
 def q_sample(scheduler, normalizer_or_model, joint_command, noise, timesteps):
     """normalise (train.py:204) + add_noise (train.py:218) in one kernel. Returns x_t."""
     jc = joint_command.float().contiguous()

@@ -194,3 +194,23 @@ def mark_grad_written(p):
             fn(p)
     if not alive and _grad_listeners:
         _grad_listeners.clear()
+
+
+# ---- "the gradients of this part of the model are complete" notifications (backward pass -> overlapped all-reduce) ----------
+_grad_ready_cb = None
+
+
+def set_grad_ready_callback(fn):
+    """``fn(tag)`` is called from inside the backward pass when every parameter gradient produced AFTER the tagged point
+    of the forward pass (i.e. earlier in the backward pass) is complete.  Tags: "trunk.layer3_onward"."""
+    global _grad_ready_cb
+    _grad_ready_cb = fn
+
+
+def grad_ready_enabled() -> bool:
+    return _grad_ready_cb is not None
+
+
+def grad_ready(tag: str):
+    if _grad_ready_cb is not None:
+        _grad_ready_cb(tag)
