@@ -91,6 +91,9 @@ class GraphedTrainStep:
         bs, dev = jt.size(0), jt.device
         self.seed_counter.add_(1)
         self.opt.zero_grad()
+        if self.reducer is not None:
+            self.reducer.begin()   # BEFORE the forward pass (it plants the backward milestone): the big gradient bucket is
+                                   # all-reduced DURING the backward pass
         t = self.fixed_t if self.fixed_t is not None else torch.randint(0, self.sch.config["num_train_timesteps"], (bs,), device=dev)
         noise = self.fixed_noise if self.fixed_noise is not None else torch.randn(jt.shape, device=dev, dtype=torch.float32)
         noisy = q_sample(self.sch, self.model, jt, noise, t)
@@ -102,8 +105,6 @@ class GraphedTrainStep:
         loss = mse_loss(pred, noise)
         prev = runtime.direct_grads()
         runtime.set_direct_grads(self.direct_grads)   # gradients land in FusedAdamW's flat buffer without autograd adds
-        if self.reducer is not None:
-            self.reducer.begin()                       # the big gradient bucket is all-reduced DURING the backward pass
         try:
             loss.backward()
         finally:

@@ -78,7 +78,7 @@ class BucketedAllReduce:
         return self.comm
 
     def begin(self):
-        """Call before the backward pass of a step."""
+        """Call before the FORWARD pass of a step (the forward pass plants the backward milestone)."""
         from soccerdiffusion_b200 import runtime
 
         self.early_done = False

@@ -38,10 +38,10 @@ def main():
 
     def backward(reducer):
         opt.zero_grad()
-        pred = model(batch, q_sample(sch, model, batch["joint_command"], noise, t), t)
-        loss = mse_loss(pred, noise)
         if reducer is not None:
             reducer.begin()
+        pred = model(batch, q_sample(sch, model, batch["joint_command"], noise, t), t)
+        loss = mse_loss(pred, noise)
         loss.backward()
         if reducer is not None:
             reducer.finish()
