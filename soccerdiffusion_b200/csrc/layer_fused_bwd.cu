@@ -388,13 +388,20 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_bwd_kernel(const __grid_cons
             // One accumulation chain per loop.  (Interleaving the dV and dK chains instruction by instruction — two
             // accumulators, four descriptors per iteration — produced a wrong result in whichever chain's descriptor
             // registers were recycled first; every contiguous chain in this library is exact.)
+            // The head's dh columns of the MN-major B operands are addressed by a byte offset INSIDE the 128-byte swizzle
+            // row (the hardware applies the swizzle to the final address, exactly as for the k offset of K-major operands):
+            // N = dh instead of a full-width N = 128 product of which 1/H would be kept.
+            const uint32_t b_off = (uint32_t)((hoff >> 6) * LTILE + (hoff & 63) * 2);
+            const uint32_t id_mm_h = instr_desc_bf16(128, dh, 1, 1), id_km_h = instr_desc_bf16(128, dh, 0, 1);
             for (int j = 0; j < Kp16; ++j)   // dV[m][c] = sum_t P'[t][m] dO[t][c]   (contraction over the query rows t)
-                mma_bf16_ss(tmem + ACC2, smem_desc_mn_sw128(sbase + P0, LTILE, 1024) + 128 * (uint64_t)j,
-                            smem_desc_mn_sw128(sbase + P5, LTILE, 1024) + 128 * (uint64_t)j, id_mm, j > 0);
+                mma_bf16_ss(tmem + ACC2 + hoff, smem_desc_mn_sw128(sbase + P0, LTILE, 1024) + 128 * (uint64_t)j,
+                            smem_desc_mn_sw128(sbase + P5 + b_off, LTILE, 1024) + 128 * (uint64_t)j, id_mm_h, j > 0);
             for (int j = 0; j < Kp16; ++j)   // dK[m][c] = sum_t dS[t][m] Q[t][c]
-                mma_bf16_ss(tmem + ACC3, smem_desc_mn_sw128(sbase + P1, LTILE, 1024) + 128 * (uint64_t)j,
-                            smem_desc_mn_sw128(sbase + P2, LTILE, 1024) + 128 * (uint64_t)j, id_mm, j > 0);
-            mma_a_k_b_mn(tmem + ACC1, sbase + P1, LTILE, sbase + P3, LTILE, id_km, Kp16, false);   // dQ[t][c] = sum_m dS[t][m] K[m][c]
+                mma_bf16_ss(tmem + ACC3 + hoff, smem_desc_mn_sw128(sbase + P1, LTILE, 1024) + 128 * (uint64_t)j,
+                            smem_desc_mn_sw128(sbase + P2 + b_off, LTILE, 1024) + 128 * (uint64_t)j, id_mm_h, j > 0);
+            for (int j = 0; j < Kp16; ++j)   // dQ[t][c] = sum_m dS[t][m] K[m][c]
+                mma_bf16_ss(tmem + ACC1 + hoff, smem_desc_k_sw128(sbase + P1 + (j >> 2) * LTILE) + 2 * (j & 3),
+                            smem_desc_mn_sw128(sbase + P3 + b_off, LTILE, 1024) + 128 * (uint64_t)j, id_km_h, j > 0);
             mma_commit(&bar[B_H0 + h]);
         }
         __syncwarp();

@@ -59,6 +59,23 @@ def main():
                 ms = timed_graph(lambda: EncoderStackFn.apply(cfg, B, S, H, pe, x, emb_w, emb_b, *layers))
             print(f"enc stack fwd no_grad B={B} S={S} H={H} L={L} p={p} fused={fused}: {ms*1e3:.1f} us "
                   f"({flops/ms/1e9:.1f} TF/s algorithmic)")
+    # training path: forward with saves + fused backward + TMA weight-gradient GEMM
+    gout = torch.randn(B, S, d, device="cuda")
+    params = [emb_w, emb_b, *layers]
+    for t in params:
+        t.requires_grad_(True)
+    for p in (0.0, 0.1):
+        for fused in (True, False):
+            runtime.set_fused_layers(fused)
+            cfg = RunCfg(precision=ops.PREC_BF16, p=p, seed=3, stream_base=0)
+
+            def fb():
+                for t in params:
+                    t.grad = None
+                EncoderStackFn.apply(cfg, B, S, H, pe, x, emb_w, emb_b, *layers).backward(gout)
+
+            ms = timed_graph(fb)
+            print(f"enc stack fwd+bwd B={B} S={S} H={H} L={L} p={p} fused={fused}: {ms*1e3:.1f} us ({3*flops/ms/1e9:.1f} TF/s algorithmic)")
     runtime.set_fused_layers(True)
 
 
