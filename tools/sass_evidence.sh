@@ -1,7 +1,7 @@
 #!/bin/bash
 # SASS evidence that the tensor-core / TMA kernels of libsd_b200.so really use tcgen05 + TMEM + TMA on sm_100a
 # (B200_PROFILING.md: UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTMALDG = cp.async.bulk.tensor, UBLKCP = cp.async.bulk,
-# SYNCS = mbarrier, UTCBAR = tcgen05.commit).   usage: tools/sass_evidence.sh > profiles/r01_sass_evidence.md
+# SYNCS = mbarrier, UTCBAR = tcgen05.commit).   usage: tools/sass_evidence.sh > profiles/r02_sass_evidence.md
 so=${1:-soccerdiffusion_b200/libsd_b200.so}
 echo "# SASS evidence — tcgen05 / TMEM / TMA instructions per kernel of \`$so\` (cuobjdump -sass, sm_100a)"
 echo
