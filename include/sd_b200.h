@@ -354,6 +354,58 @@ typedef struct sd_wgrad_job {
 } sd_wgrad_job;
 int sd_wgrad_bf16(const sd_wgrad_job* jobs, int n_jobs, long long rows, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The decoder layer's cross-attention block, layer-fused on tcgen05 + TMA (bf16 mode; d_model = 128, 4 heads,
+ * T <= 16 query tokens, memory length M <= 384).  Replaces, per decoder layer, LN2 -> q projection -> k/v projection
+ * of the memory -> nn.MultiheadAttention core -> out-projection + dropout + residual
+ * (torch/nn/modules/transformer.py:1137-1139; ml/model/decoder.py:25-54) and its autograd.
+ *
+ * sd_cast_bf16: fp32 -> bf16 copy (n a multiple of 8, 16-byte aligned).
+ * sd_kv_proj_bf16: the memory's K | V projections of ALL layers in one GEMM:
+ *   kv[row][256 l + n] = sum_k mem[row][k] * W[w_row0 + l*w_stride + n][k] + biases[l][n]      (n < 256: Wk rows, Wv rows)
+ *   mem bf16 [rows][128]; W = the packed bf16 weight matrix of sd_pack_weights_bf16; kv bf16 [rows][ldkv].
+ * sd_kv_dgrad_bf16: dmem[row][n] (+)= sum_{l,k} dkv[row][256 l + k] * W[w_row0 + l*w_stride + k][n]   (fp32 [rows][lddmem]).
+ * (The k/v weight gradients are sd_wgrad_bf16 jobs with G = dkv, X = the bf16 memory.) */
+#define SD_KV_MAX_LAYERS 16
+int sd_cast_bf16(const float* src, void* dst_bf16, long long n, void* stream);
+int sd_kv_proj_bf16(const void* mem_bf16, long long rows, const void* w_packed, int w_rows_total, int w_row0, int w_stride,
+                    int n_layers, const float* const* biases, void* kv_out, long long ldkv, void* stream);
+int sd_kv_dgrad_bf16(const void* dkv_bf16, long long rows, long long lddkv, const void* w_packed, int w_rows_total, int w_row0,
+                     int w_stride, int n_layers, float* dmem, long long lddmem, int accumulate, void* stream);
+
+/* y = x + Drop(OutProj(MHA(LN(x), kv))) for B samples of T query rows; one CTA per sample.  x, y fp32 [B*T][128] (may
+ * alias).  kv: bf16 [B*M][ldkv], this layer's K at columns [kv_col0, kv_col0+128), V at [kv_col0+128, kv_col0+256).
+ * Dropout streams: dropout_stream + 0 (attention probabilities, element ((b*4+h)*T+t)*M+m), + 1 (out-proj, row*128+c).
+ * Optional saves for the backward pass (NULL in inference): xn (LN output), q (projected queries incl. bias), attn
+ * (attention output) as bf16 [B*T][128]; stats fp32 [B*T][2] (mean, rstd); lse fp32 [B][4][T] (log2 domain). */
+typedef struct sd_ca_block_desc {
+    const float* x; float* y;
+    int B, T, M;
+    const void* w_packed; int w_rows_total; int w_row_q; int w_row_o;
+    const void* kv; long long ldkv; int kv_col0;
+    const float *q_b, *out_b, *n_w, *n_b;
+    void* xn_save; void* q_save; void* attn_save; float* stats_save; float* lse_save;
+    float dropout_p; unsigned long long dropout_seed; unsigned int dropout_stream;
+} sd_ca_block_desc;
+int sd_ca_block_supported(int d, int H, int T, int M);
+int sd_ca_block_fwd(const sd_ca_block_desc* desc, void* stream);
+
+/* Backward of the block (data path): dy -> dx (fp32 [B*T][128], may alias), g1 = dy*mask and dq (bf16 [B*T][128], the G
+ * operands of the out-proj / q-proj weight gradients), dkv (bf16 [B*M][lddkv], this layer's dK | dV at the kv columns);
+ * LayerNorm weight / bias gradients are ACCUMULATED into g_n_w / g_n_b (fp32 [128]). */
+typedef struct sd_ca_block_bwd_desc {
+    const float* dy; float* dx;
+    const float* x; const void* q; const void* attn; const float* stats; const float* lse;
+    int B, T, M;
+    const void* w_packed; int w_rows_total; int w_row_q; int w_row_o;
+    const void* kv; long long ldkv; int kv_col0;
+    const float* n_w;
+    void* g1; void* dq; void* dkv; long long lddkv;
+    float *g_n_w, *g_n_b;
+    float dropout_p; unsigned long long dropout_seed; unsigned int dropout_stream;
+} sd_ca_block_bwd_desc;
+int sd_ca_block_bwd(const sd_ca_block_bwd_desc* desc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -96,6 +96,29 @@ class WgradJob(C.Structure):
                 ("dW", c_f), ("ldw", c_ll), ("db", c_f)]
 
 
+KV_MAX_LAYERS = 16
+
+
+class CaBlockDesc(C.Structure):
+    _fields_ = [("x", c_f), ("y", c_f), ("B", c_i), ("T", c_i), ("M", c_i),
+                ("w_packed", c_f), ("w_rows_total", c_i), ("w_row_q", c_i), ("w_row_o", c_i),
+                ("kv", c_f), ("ldkv", c_ll), ("kv_col0", c_i),
+                ("q_b", c_f), ("out_b", c_f), ("n_w", c_f), ("n_b", c_f),
+                ("xn_save", c_f), ("q_save", c_f), ("attn_save", c_f), ("stats_save", c_f), ("lse_save", c_f),
+                ("dropout_p", c_fl), ("dropout_seed", c_ull), ("dropout_stream", c_u)]
+
+
+class CaBlockBwdDesc(C.Structure):
+    _fields_ = [("dy", c_f), ("dx", c_f), ("x", c_f), ("q", c_f), ("attn", c_f), ("stats", c_f), ("lse", c_f),
+                ("B", c_i), ("T", c_i), ("M", c_i),
+                ("w_packed", c_f), ("w_rows_total", c_i), ("w_row_q", c_i), ("w_row_o", c_i),
+                ("kv", c_f), ("ldkv", c_ll), ("kv_col0", c_i),
+                ("n_w", c_f),
+                ("g1", c_f), ("dq", c_f), ("dkv", c_f), ("lddkv", c_ll),
+                ("g_n_w", c_f), ("g_n_b", c_f),
+                ("dropout_p", c_fl), ("dropout_seed", c_ull), ("dropout_stream", c_u)]
+
+
 # name -> argtypes (restype is always int unless noted); mirrors include/sd_b200.h one to one
 SIGNATURES = {
     "sd_abi_version": [],
@@ -158,6 +181,12 @@ SIGNATURES = {
     "sd_enc_layer_fwd": [C.POINTER(EncLayerDesc), c_f],
     "sd_enc_layer_bwd": [C.POINTER(EncLayerBwdDesc), c_f],
     "sd_wgrad_bf16": [C.POINTER(WgradJob), c_i, c_ll, c_f],
+    "sd_cast_bf16": [c_f, c_f, c_ll, c_f],
+    "sd_kv_proj_bf16": [c_f, c_ll, c_f, c_i, c_i, c_i, c_i, C.POINTER(c_f), c_f, c_ll, c_f],
+    "sd_kv_dgrad_bf16": [c_f, c_ll, c_ll, c_f, c_i, c_i, c_i, c_i, c_f, c_ll, c_i, c_f],
+    "sd_ca_block_supported": [c_i, c_i, c_i, c_i],
+    "sd_ca_block_fwd": [C.POINTER(CaBlockDesc), c_f],
+    "sd_ca_block_bwd": [C.POINTER(CaBlockBwdDesc), c_f],
 }
 
 _lib = None

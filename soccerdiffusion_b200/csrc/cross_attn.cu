@@ -1,0 +1,968 @@
+// The decoder layer's CROSS-ATTENTION block on tcgen05 tensor cores, fed by TMA (bf16 operands, fp32 accumulation in TMEM),
+// d_model = 128, 4 heads of 32, T <= 16 query tokens per sample, memory length M <= 384 (default.yaml: T = 10, M = 312):
+//
+//     y = x + Drop(OutProj(MHA(LN2 x, mem, mem)))        torch/nn/modules/transformer.py:1137-1139 (norm_first),
+//                                                        reference call sites ml/model/decoder.py:25-54, model.py:176-179
+//
+// The memory is NOT layer-normed and is shared by all decoder layers, so its K / V projections of ALL layers are one GEMM
+// (sd_kv_proj_bf16: [B*M][128] x [L*256][128]^T -> bf16 [B*M][L*256], TMA in, tcgen05, bias in the epilogue); its
+// backward is one GEMM too (sd_kv_dgrad_bf16: dmem = dKV_all x W_all, K = L*256) plus sd_wgrad_bf16 jobs.
+//
+// sd_ca_block_fwd / sd_ca_block_bwd: one CTA (128 threads = the 128 TMEM lanes) per SAMPLE.  With only T = 10 queries the
+// operand roles are swapped so that no MMA wastes its 128 rows on 10 tokens:
+//   * projections are computed transposed, D^T[feature][t] = W[feature][:] . act[t][:]  (A = the weight matrix, N = 16):
+//     thread = feature, every global access "row t, thread = column" is coalesced;
+//   * scores are computed transposed for all heads at once, S^T[m][(h,t)] = K[m][:] . Qblk[(h,t)][:], where Qblk is the
+//     block-diagonal expansion of Q (row (h,t) holds Q[t] on the columns of head h, zeros elsewhere): A = 128 keys of the
+//     TMA-loaded K tile (the natural row-major layout), N = 4 heads x 16 = 64.  Softmax runs over the TMEM LANES (keys):
+//     register-transposing warp reductions + one shared-memory exchange;
+//   * O^T[c][(h,t)] = sum_m V[m][c] P^T[m][(h,t)]: A = the TMA-loaded V tile used MN-major, B = P^T written row per key.
+// Backward uses the same forms: dP^T = V dOblk^T, dS^T elementwise per key, dV = Pd^T dOblk, dK = dS^T Qblk (N = 128),
+// dQ^T += K^T dS^T, chunk by chunk over the keys (no cross-chunk dependency: the forward saved the log-sum-exp).
+#include "layer_common.cuh"
+#include "../../include/sd_b200.h"
+
+using namespace sdlf;
+
+namespace {
+
+constexpr int CNT = 128;            // threads per CTA
+constexpr int TP = 16;              // padded query tokens per sample
+constexpr int NQ = 64;              // 4 heads x TP columns of the transposed score matrix
+constexpr int CA_H = 4, CA_DH = 32;
+constexpr int MAXCH = 3;            // key chunks of 128
+
+// lane l ends with the reduction over the warp of v[l] (31 shuffles instead of 160)
+template <bool MAX>
+__device__ __forceinline__ float warp_reduce32_cols(float (&v)[32], int lane) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int k = 0; k < o; ++k) {
+            const float keep = up ? v[k + o] : v[k];
+            const float send = up ? v[k] : v[k + o];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, o);
+            v[k] = MAX ? fmaxf(keep, recv) : keep + recv;
+        }
+    }
+    return v[0];
+}
+
+__device__ __forceinline__ void ld_lane32(uint32_t tmem, int warp, int col, float* v) {
+    tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)col, v);
+}
+__device__ __forceinline__ void ld_lane16(uint32_t tmem, int warp, int col, float* v) {
+    tmem_ld_32x16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)col, v);
+}
+// bf16 element (row r, column c) of a 128-wide K-major operand made of two [rows][64] swizzled tiles `tile_bytes` apart
+__device__ __forceinline__ uint32_t elem_off(int r, int c, int tile_bytes) {
+    return (uint32_t)((c >> 6) * tile_bytes) + sw128_chunk_off(r, (c & 63) >> 3) + (uint32_t)((c & 7) * 2);
+}
+__device__ __forceinline__ unsigned short bf16_bits(float f) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(f);
+    return *reinterpret_cast<const unsigned short*>(&h);
+}
+__device__ __forceinline__ float bf16_to_f(unsigned short u) {
+    return __uint_as_float(((uint32_t)u) << 16);
+}
+
+// =====================================================================================================================
+// fp32 -> bf16 (the memory / any activation matrix): 8 elements per thread
+__global__ void cast_bf16_kernel(const float* __restrict__ src, uint4* __restrict__ dst, long long n8) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        const float4 a = reinterpret_cast<const float4*>(src)[2 * i], b = reinterpret_cast<const float4*>(src)[2 * i + 1];
+        const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        dst[i] = pack8_bf16(f);
+    }
+}
+
+// =====================================================================================================================
+// K/V projection of the memory for all layers: C[row][256 j + n] = sum_k A[row][k] W[w_row0 + j w_stride + n][k] + bias_j[n]
+struct KvProjParams {
+    long long rows;
+    int nblk, w_row0, w_stride;
+    const float* bias[SD_KV_MAX_LAYERS];
+    __nv_bfloat16* C;
+    long long ldc;
+};
+constexpr int KP_SMEM = 2 * LTILE + 2 * 4 * LTILE + 1024;   // A tile + two weight blocks of [256][128]
+
+__global__ void __launch_bounds__(CNT, 1) kv_proj_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                                                         const KvProjParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_a, bar_b[2], bar_m[2];
+    __shared__ uint32_t tmem_slot;
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const long long row0 = (long long)blockIdx.x * 128;
+    if (tid == 0) {
+        mbar_init(&bar_a, 1);
+        mbar_init(&bar_b[0], 1); mbar_init(&bar_b[1], 1);
+        mbar_init(&bar_m[0], 1); mbar_init(&bar_m[1], 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmW);
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t OFF_B = 2 * LTILE;
+    // weight block j: 256 rows as two TMA boxes of 128 rows per 64-column half -> tiles [k half][row half]
+    auto load_b = [&](int j) {
+        const uint32_t dst = sbase + OFF_B + (j & 1) * 4 * LTILE;
+        const int r = p.w_row0 + j * p.w_stride;
+        mbar_arrive_expect_tx(&bar_b[j & 1], 4 * LTILE);
+        tma_tile_2d(dst, &tmW, 0, r, &bar_b[j & 1]);
+        tma_tile_2d(dst + LTILE, &tmW, 0, r + 128, &bar_b[j & 1]);
+        tma_tile_2d(dst + 2 * LTILE, &tmW, 64, r, &bar_b[j & 1]);
+        tma_tile_2d(dst + 3 * LTILE, &tmW, 64, r + 128, &bar_b[j & 1]);
+    };
+    // [256 rows][64 k] as two consecutive [128][64] tiles: 8-row groups stay 1024 B apart across the tile boundary
+    const uint32_t id256 = instr_desc_bf16(128, 256);
+    auto issue = [&](int j) {
+        mbar_wait(&bar_b[j & 1], (uint32_t)((j >> 1) & 1));
+        tc_fence_after_sync();
+        mma_k_tiles(tmem + (j & 1) * 256, sbase, LTILE, sbase + OFF_B + (j & 1) * 4 * LTILE, 2 * LTILE, id256, 2, false);
+        mma_commit(&bar_m[j & 1]);
+    };
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&bar_a, 2 * LTILE);
+        tma_tile_2d(sbase, &tmA, 0, (int)row0, &bar_a);
+        tma_tile_2d(sbase + LTILE, &tmA, 64, (int)row0, &bar_a);
+        load_b(0);
+        if (p.nblk > 1) load_b(1);
+        mbar_wait(&bar_a, 0);
+        issue(0);
+    }
+    __syncwarp();
+    const long long grow = row0 + tid;
+    const bool rv = grow < p.rows;
+    for (int j = 0; j < p.nblk; ++j) {
+        if (tid == 0 && j + 1 < p.nblk) issue(j + 1);
+        __syncwarp();
+        mbar_wait(&bar_m[j & 1], (uint32_t)((j >> 1) & 1));
+        tc_fence_after_sync();
+        if (tid == 0 && j + 2 < p.nblk) load_b(j + 2);   // the MMAs that read slot j & 1 have completed
+        __syncwarp();
+        const float* bias = p.bias[j];
+        __nv_bfloat16* crow = p.C + grow * p.ldc + 256 * j;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+            float v[32], b[32];
+            if (bias) ldg32(bias + c0, b);
+            ld_lane32(tmem, warp, (j & 1) * 256 + c0, v);
+            if (bias) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += b[i];
+            }
+            if (rv) {
+                uint4* g = reinterpret_cast<uint4*>(crow + c0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) g[i] = pack8_bf16(v + 8 * i);
+            }
+        }
+        tc_fence_before_sync();
+        __syncthreads();   // accumulator j & 1 drained by every thread before block j + 2 is issued into it
+        tc_fence_after_sync();
+    }
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// =====================================================================================================================
+// dmem[row][n] (+)= sum_k dKV[row][k] W[k][n],  k = 256 j + kk -> packed weight row w_row0 + j w_stride + kk
+struct KvDgradParams {
+    long long rows;
+    int nblk, w_row0, w_stride;
+    float* C;
+    long long ldc;
+    int accumulate;
+};
+constexpr int KD_STAGES = 4;
+constexpr int KD_STAGE = 2 * LTILE;   // A [128 rows][64 k] + W [64 k][128 n] (two [64][64] boxes)
+constexpr int KD_SMEM = KD_STAGES * KD_STAGE + 1024;
+
+__global__ void __launch_bounds__(CNT, 1) kv_dgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                                                          const KvDgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[KD_STAGES], bar_empty[KD_STAGES], bar_done;
+    __shared__ uint32_t tmem_slot;
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long row0 = (long long)blockIdx.x * 128;
+    if (tid == 0) {
+        for (int s = 0; s < KD_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+        mbar_init(&bar_done, 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmW);
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, 128);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const int nk = p.nblk * 4;   // k tiles of 64
+    if (warp == 0 && lane == 0) {          // TMA producer
+        for (int i = 0; i < nk; ++i) {
+            const int s = i % KD_STAGES;
+            mbar_wait(&bar_empty[s], (uint32_t)(((i / KD_STAGES) & 1) ^ 1));
+            const uint32_t dst = sbase + s * KD_STAGE;
+            const int wrow = p.w_row0 + (i >> 2) * p.w_stride + (i & 3) * 64;
+            mbar_arrive_expect_tx(&bar_full[s], KD_STAGE);
+            tma_tile_2d(dst, &tmA, 64 * i, (int)row0, &bar_full[s]);
+            tma_tile_2d(dst + LTILE, &tmW, 0, wrow, &bar_full[s]);
+            tma_tile_2d(dst + LTILE + LTILE / 2, &tmW, 64, wrow, &bar_full[s]);
+        }
+    } else if (warp == 1 && lane == 0) {   // MMA issuer: A K-major, B MN-major ([64 k rows][64 n] x 2 blocks 8 KB apart)
+        const uint32_t idesc = instr_desc_bf16(128, 128, 0, 1);
+        for (int i = 0; i < nk; ++i) {
+            const int s = i % KD_STAGES;
+            mbar_wait(&bar_full[s], (uint32_t)((i / KD_STAGES) & 1));
+            tc_fence_after_sync();
+            mma_a_k_b_mn(tmem, sbase + s * KD_STAGE, 0, sbase + s * KD_STAGE + LTILE, LTILE / 2, idesc, 4, i > 0);
+            mma_commit(&bar_empty[s]);
+        }
+        mma_commit(&bar_done);
+    }
+    __syncwarp();
+    mbar_wait(&bar_done, 0);
+    tc_fence_after_sync();
+    const long long grow = row0 + tid;
+    const bool rv = grow < p.rows;
+    float* crow = p.C + grow * p.ldc;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+        float v[32];
+        ld_lane32(tmem, warp, c0, v);   // warp-collective: every lane takes part
+        if (rv) {
+            float4* g = reinterpret_cast<float4*>(crow + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                if (p.accumulate) { const float4 t = g[i]; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+                g[i] = o;
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+// =====================================================================================================================
+// forward block
+constexpr int F_OFF_KV = 0;                      // 3 chunks x (lo, hi) [128 keys][64] tiles: K, later V
+constexpr int F_OFF_W = 6 * LTILE;               // Wq, later Wout: two [128][64] tiles
+constexpr int F_OFF_QB = F_OFF_W + 2 * LTILE;    // Qblk: two [64][64] tiles of 8 KB
+constexpr int F_OFF_P = F_OFF_QB + LTILE;        // P^T: 3 chunks of [128 keys][64]
+constexpr int F_OFF_XB = F_OFF_P + 3 * LTILE;    // LN2(x) / attention output as B operand: two [16][64] tiles of 2 KB
+constexpr int F_SMEM = F_OFF_XB + 4096 + 1024;
+constexpr int XB_TILE = 2048, QB_TILE = 8192;
+
+struct CaFwdParams {
+    const float* x;
+    float* y;
+    int B, T, M;
+    int w_row_q, w_row_o;      // packed-weight rows of Wq and Wout
+    int kv_col0;               // first column of this layer's K | V inside the all-layer K/V matrix
+    const float *q_b, *out_b, *n_w, *n_b;
+    __nv_bfloat16 *xn_save, *q_save, *attn_save;
+    float *stats_save, *lse_save;   // [B*T][2] (mean, rstd) ; [B][4][T] log2-domain log-sum-exp
+    Dropout drop;              // stream + 0: attention probabilities, + 1: out-projection
+};
+
+enum { FB_WQ = 0, FB_WO, FB_Q, FB_S, FB_O, FB_Y, FB_K0, FB_V0 = FB_K0 + MAXCH, FB_N = FB_V0 + MAXCH };
+
+template <bool DROP>
+__global__ void __launch_bounds__(CNT, 1) ca_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmKV,
+                                                        const CaFwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar[FB_N];
+    __shared__ float red[4][NQ];
+    __shared__ __align__(16) float fin_max[NQ];
+    __shared__ __align__(16) float fin_inv[NQ];
+    __shared__ uint32_t tmem_slot;
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.x, T = p.T, M = p.M;
+    const int nch = (M + 127) >> 7;
+    const long long krow0 = (long long)b * M;
+
+    if (tid == 0) {
+        for (int i = 0; i < FB_N; ++i) mbar_init(&bar[i], 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&tmW);
+        tma_prefetch_desc(&tmKV);
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    constexpr uint32_t ST = 64, OT = 256, QT = 320, YT = 352;
+
+    auto load_w = [&](int row, int bi) {
+        mbar_arrive_expect_tx(&bar[bi], 2 * LTILE);
+        tma_tile_2d(sbase + F_OFF_W, &tmW, 0, row, &bar[bi]);
+        tma_tile_2d(sbase + F_OFF_W + LTILE, &tmW, 64, row, &bar[bi]);
+    };
+    auto load_kv = [&](int j, int col, int bi) {
+        mbar_arrive_expect_tx(&bar[bi + j], 2 * LTILE);
+        tma_tile_2d(sbase + F_OFF_KV + 2 * j * LTILE, &tmKV, col, (int)(krow0 + 128 * j), &bar[bi + j]);
+        tma_tile_2d(sbase + F_OFF_KV + (2 * j + 1) * LTILE, &tmKV, col + 64, (int)(krow0 + 128 * j), &bar[bi + j]);
+    };
+    if (tid == 0) {
+        load_w(p.w_row_q, FB_WQ);
+        for (int j = 0; j < nch; ++j) load_kv(j, p.kv_col0, FB_K0);
+    }
+    // Qblk starts as zeros (the off-diagonal blocks stay zero)
+    for (int i = tid; i < LTILE / 16; i += CNT) reinterpret_cast<uint4*>(smem + F_OFF_QB)[i] = make_uint4(0u, 0u, 0u, 0u);
+    const uint64_t dseed = DROP ? p.drop.resolve() : 0ull;
+
+    // ---- LN2 of the T rows (warp per row, lane = 4 features) -> B operand [t][k] ------------------------------------------
+    {
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(p.n_w) + lane);
+        const float4 be = __ldg(reinterpret_cast<const float4*>(p.n_b) + lane);
+        for (int t = warp; t < TP; t += 4) {
+            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+            const long long grow = (long long)b * T + t;
+            if (t < T) xv = reinterpret_cast<const float4*>(p.x + grow * 128)[lane];
+            const float mean = warp_sum((xv.x + xv.y) + (xv.z + xv.w)) * (1.0f / 128.0f);
+            const float c0 = xv.x - mean, c1 = xv.y - mean, c2 = xv.z - mean, c3 = xv.w - mean;
+            const float rstd = rsqrtf(warp_sum(fmaf(c0, c0, c1 * c1) + fmaf(c2, c2, c3 * c3)) * (1.0f / 128.0f) + LN_EPS);
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (t < T) {
+                v[0] = fmaf(c0 * rstd, ga.x, be.x); v[1] = fmaf(c1 * rstd, ga.y, be.y);
+                v[2] = fmaf(c2 * rstd, ga.z, be.z); v[3] = fmaf(c3 * rstd, ga.w, be.w);
+            }
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+            uint2 u;
+            u.x = *reinterpret_cast<uint32_t*>(&lo);
+            u.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(smem + F_OFF_XB + elem_off(t, 4 * lane, XB_TILE)) = u;
+            if (t < T) {
+                if (p.xn_save) reinterpret_cast<uint2*>(p.xn_save + grow * 128)[lane] = u;
+                if (p.stats_save && lane == 0) { p.stats_save[2 * grow] = mean; p.stats_save[2 * grow + 1] = rstd; }
+            }
+        }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    // ---- Q^T[n][t] = Wq[n][:] . xn[t][:] ---------------------------------------------------------------------------------
+    const uint32_t id16 = instr_desc_bf16(128, 16);
+    if (tid == 0) {
+        tc_fence_after_sync();
+        mbar_wait(&bar[FB_WQ], 0);
+        mma_k_tiles(tmem + QT, sbase + F_OFF_W, LTILE, sbase + F_OFF_XB, XB_TILE, id16, 2, false);
+        mma_commit(&bar[FB_Q]);
+    }
+    __syncwarp();
+    {
+        const float bq = __ldg(p.q_b + tid);
+        float q[16];
+        mbar_wait(&bar[FB_Q], 0);
+        tc_fence_after_sync();
+        if (tid == 0) load_w(p.w_row_o, FB_WO);   // the Q projection has consumed the weight slot
+        __syncwarp();
+        ld_lane16(tmem, warp, QT, q);
+        const int h = tid >> 5;
+#pragma unroll
+        for (int t = 0; t < TP; ++t) {
+            const unsigned short u = t < T ? bf16_bits(q[t] + bq) : (unsigned short)0;
+            *reinterpret_cast<unsigned short*>(smem + F_OFF_QB + elem_off(h * TP + t, tid, QB_TILE)) = u;
+            if (t < T && p.q_save) reinterpret_cast<unsigned short*>(p.q_save)[((long long)b * T + t) * 128 + tid] = u;
+        }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    // ---- S^T chunks ------------------------------------------------------------------------------------------------------
+    const uint32_t id64 = instr_desc_bf16(128, NQ);
+    if (tid == 0) {
+        tc_fence_after_sync();
+        for (int j = 0; j < nch; ++j) {
+            mbar_wait(&bar[FB_K0 + j], 0);
+            mma_k_tiles(tmem + ST + NQ * j, sbase + F_OFF_KV + 2 * j * LTILE, LTILE, sbase + F_OFF_QB, QB_TILE, id64, 2, false);
+        }
+        mma_commit(&bar[FB_S]);
+        mbar_wait(&bar[FB_S], 0);     // every K tile has been read: the V tiles take their place
+        for (int j = 0; j < nch; ++j) load_kv(j, p.kv_col0 + 128, FB_V0);
+    }
+    __syncwarp();
+    mbar_wait(&bar[FB_S], 0);
+    tc_fence_after_sync();
+    // ---- softmax over the keys (TMEM lanes): thread = key 128 j + tid of every chunk ----------------------------------------
+    const float sc = rsqrtf((float)CA_DH) * 1.4426950408889634f;
+#pragma unroll 1
+    for (int g = 0; g < 2; ++g) {
+        float mx[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx[i] = -INFINITY;
+        for (int j = 0; j < nch; ++j) {
+            float s[32];
+            ld_lane32(tmem, warp, ST + NQ * j + 32 * g, s);
+            if (128 * j + tid < M) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx[i] = fmaxf(mx[i], s[i]);
+            }
+        }
+        const float m = warp_reduce32_cols<true>(mx, lane);
+        red[warp][32 * g + lane] = m;
+    }
+    __syncthreads();
+    if (tid < NQ) fin_max[tid] = fmaxf(fmaxf(red[0][tid], red[1][tid]), fmaxf(red[2][tid], red[3][tid])) * sc;
+    __syncthreads();
+#pragma unroll 1
+    for (int g = 0; g < 2; ++g) {
+        float mxs[32], sum[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 t4 = reinterpret_cast<const float4*>(fin_max)[8 * g + i];
+            mxs[4 * i] = t4.x; mxs[4 * i + 1] = t4.y; mxs[4 * i + 2] = t4.z; mxs[4 * i + 3] = t4.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sum[i] = 0.f;
+        for (int j = 0; j < nch; ++j) {
+            float s[32];
+            ld_lane32(tmem, warp, ST + NQ * j + 32 * g, s);
+            const int m = 128 * j + tid;
+            const bool kv = m < M;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float e = kv ? ex2_approx(fmaf(s[i], sc, -mxs[i])) : 0.f;
+                sum[i] += e;
+                s[i] = e;
+            }
+            if (DROP && kv) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int h = (32 * g + i) >> 4, t = i & 15;
+                    if (t < T)
+                        s[i] *= dropout_scale(dseed, p.drop.stream, (((uint64_t)b * CA_H + h) * T + t) * (uint64_t)M + m, p.drop.thresh,
+                                              p.drop.inv_keep);
+                }
+            }
+            // row `tid` of the [128 keys][64] P^T tile: chunks 4 g .. 4 g + 3
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4*>(smem + F_OFF_P + j * LTILE + sw128_chunk_off(tid, 4 * g + c)) = pack8_bf16(s + 8 * c);
+        }
+        const float sm = warp_reduce32_cols<false>(sum, lane);
+        red[warp][32 * g + lane] = sm;
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    if (tid < NQ) {
+        const float sum = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+        fin_inv[tid] = 1.0f / sum;
+        const int h = tid >> 4, t = tid & 15;
+        if (t < T && p.lse_save) p.lse_save[((long long)b * CA_H + h) * T + t] = fin_max[tid] + log2f(sum);
+    }
+    // ---- O^T[c][(h,t)] = sum_m V[m][c] P^T[m][(h,t)] -------------------------------------------------------------------------
+    if (tid == 0) {
+        tc_fence_after_sync();
+        const uint32_t idesc = instr_desc_bf16(128, NQ, 1, 1);
+        for (int j = 0; j < nch; ++j) {
+            mbar_wait(&bar[FB_V0 + j], 0);
+            const int ks = min(8, (M - 128 * j + 15) >> 4);   // keys beyond M carry zero probabilities
+            for (int k = 0; k < ks; ++k)
+                mma_bf16_ss(tmem + OT, smem_desc_mn_sw128(sbase + F_OFF_KV + 2 * j * LTILE, LTILE, 1024) + 128 * (uint64_t)k,
+                            smem_desc_mn_sw128(sbase + F_OFF_P + j * LTILE, 1024, 1024) + 128 * (uint64_t)k, idesc, (j > 0 || k > 0) ? 1u : 0u);
+        }
+        mma_commit(&bar[FB_O]);
+    }
+    __syncthreads();   // fin_inv visible
+    // residual rows of this thread's column: issued ahead of the waits
+    float xr[TP];
+#pragma unroll
+    for (int t = 0; t < TP; ++t) xr[t] = t < T ? p.x[((long long)b * T + t) * 128 + tid] : 0.f;
+    {
+        float o[16];
+        const int h = tid >> 5;
+        mbar_wait(&bar[FB_O], 0);
+        tc_fence_after_sync();
+        ld_lane16(tmem, warp, OT + TP * h, o);
+#pragma unroll
+        for (int t = 0; t < TP; ++t) {
+            const unsigned short u = t < T ? bf16_bits(o[t] * fin_inv[TP * h + t]) : (unsigned short)0;
+            *reinterpret_cast<unsigned short*>(smem + F_OFF_XB + elem_off(t, tid, XB_TILE)) = u;
+            if (t < T && p.attn_save) reinterpret_cast<unsigned short*>(p.attn_save)[((long long)b * T + t) * 128 + tid] = u;
+        }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    // ---- Y^T[n][t] = Wout[n][:] . attn[t][:] ; y = x + Drop(Y + b) ----------------------------------------------------------
+    if (tid == 0) {
+        tc_fence_after_sync();
+        mbar_wait(&bar[FB_WO], 0);
+        mma_k_tiles(tmem + YT, sbase + F_OFF_W, LTILE, sbase + F_OFF_XB, XB_TILE, id16, 2, false);
+        mma_commit(&bar[FB_Y]);
+    }
+    __syncwarp();
+    {
+        const float bo = __ldg(p.out_b + tid);
+        float v[16];
+        mbar_wait(&bar[FB_Y], 0);
+        tc_fence_after_sync();
+        ld_lane16(tmem, warp, YT, v);
+#pragma unroll
+        for (int t = 0; t < TP; ++t) {
+            if (t < T) {
+                const long long e = ((long long)b * T + t) * 128 + tid;
+                float a = v[t] + bo;
+                if (DROP) a *= dropout_scale(dseed, p.drop.stream + 1, (uint64_t)e, p.drop.thresh, p.drop.inv_keep);
+                p.y[e] = xr[t] + a;
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// =====================================================================================================================
+// backward block
+constexpr int B_OFF_KV = 0;                      // 2 stages x (K lo, K hi, V lo, V hi); the last free stage takes Wq
+constexpr int B_OFF_QB = 8 * LTILE;              // Qblk  [64][128]
+constexpr int B_OFF_DOB = B_OFF_QB + LTILE;      // dOblk [64][128]
+constexpr int B_OFF_PD = B_OFF_DOB + LTILE;      // Pd^T [128 keys][64] ; first: Wout lo
+constexpr int B_OFF_DS = B_OFF_PD + LTILE;       // dS^T [128 keys][64] ; first: Wout hi
+constexpr int B_OFF_XB = B_OFF_DS + LTILE;       // g1 / dq as B operand: two [16][64] tiles
+constexpr int B_SMEM = B_OFF_XB + 4096 + 1024;
+
+struct CaBwdParams {
+    const float* dy;
+    float* dx;
+    const float* x;
+    const __nv_bfloat16 *q, *attn;
+    const float *stats, *lse;
+    int B, T, M;
+    int w_row_q, w_row_o, kv_col0;
+    const float* n_w;
+    __nv_bfloat16 *g1, *dq, *dkv;   // g1, dq: [B*T][128]; dkv: the all-layer dK | dV matrix (row stride lddkv), same columns as kv
+    long long lddkv;
+    float *g_n_w, *g_n_b;
+    Dropout drop;
+};
+
+enum { BB_WO = 0, BB_WQ, BB_DA, BB_SD, BB_G, BB_X, BB_KV0, BB_N = BB_KV0 + 2 };
+
+template <bool DROP>
+__global__ void __launch_bounds__(CNT, 1) ca_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmKV,
+                                                        const CaBwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar[BB_N];
+    __shared__ __align__(16) float s_lse[NQ];
+    __shared__ __align__(16) float s_delta[NQ];
+    __shared__ float red[4][32];
+    __shared__ float fin[32];
+    __shared__ uint32_t tmem_slot;
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.x, T = p.T, M = p.M;
+    const int nch = (M + 127) >> 7;
+    const long long krow0 = (long long)b * M;
+
+    if (tid == 0) {
+        for (int i = 0; i < BB_N; ++i) mbar_init(&bar[i], 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&tmW);
+        tma_prefetch_desc(&tmKV);
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    // S^T / dV share columns, dP^T / dK share columns (one warpgroup works through the chunks serially)
+    constexpr uint32_t SC = 0, DPC = 128, DVC = 0, DKC = 128, DQC = 256, DAC = 320, DXC = 352;
+
+    auto load_chunk = [&](int j) {   // K and V tiles of chunk j -> stage j & 1
+        const uint32_t dst = sbase + B_OFF_KV + (j & 1) * 4 * LTILE;
+        const int row = (int)(krow0 + 128 * j);
+        mbar_arrive_expect_tx(&bar[BB_KV0 + (j & 1)], 4 * LTILE);
+        tma_tile_2d(dst, &tmKV, p.kv_col0, row, &bar[BB_KV0 + (j & 1)]);
+        tma_tile_2d(dst + LTILE, &tmKV, p.kv_col0 + 64, row, &bar[BB_KV0 + (j & 1)]);
+        tma_tile_2d(dst + 2 * LTILE, &tmKV, p.kv_col0 + 128, row, &bar[BB_KV0 + (j & 1)]);
+        tma_tile_2d(dst + 3 * LTILE, &tmKV, p.kv_col0 + 192, row, &bar[BB_KV0 + (j & 1)]);
+    };
+    const uint32_t wq_addr = sbase + B_OFF_KV + (nch & 1) * 4 * LTILE;   // the stage the last chunk does NOT use
+    auto load_wq = [&]() {
+        mbar_arrive_expect_tx(&bar[BB_WQ], 2 * LTILE);
+        tma_tile_2d(wq_addr, &tmW, 0, p.w_row_q, &bar[BB_WQ]);
+        tma_tile_2d(wq_addr + LTILE, &tmW, 64, p.w_row_q, &bar[BB_WQ]);
+    };
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&bar[BB_WO], 2 * LTILE);
+        tma_tile_2d(sbase + B_OFF_PD, &tmW, 0, p.w_row_o, &bar[BB_WO]);
+        tma_tile_2d(sbase + B_OFF_DS, &tmW, 64, p.w_row_o, &bar[BB_WO]);
+        load_chunk(0);
+        if (nch > 1) load_chunk(1);
+        else load_wq();   // single chunk: stage 1 is never used by a chunk
+    }
+    for (int i = tid; i < 2 * LTILE / 16; i += CNT) reinterpret_cast<uint4*>(smem + B_OFF_QB)[i] = make_uint4(0u, 0u, 0u, 0u);
+    const uint64_t dseed = DROP ? p.drop.resolve() : 0ull;
+
+    // ---- g1 = dy * mask (thread = feature n) -> B operand [t][n] -----------------------------------------------------------
+    float dyr[TP];
+#pragma unroll
+    for (int t = 0; t < TP; ++t) {
+        const long long e = ((long long)b * T + t) * 128 + tid;
+        dyr[t] = t < T ? p.dy[e] : 0.f;
+        float g = dyr[t];
+        if (DROP && t < T) g *= dropout_scale(dseed, p.drop.stream + 1, (uint64_t)e, p.drop.thresh, p.drop.inv_keep);
+        const unsigned short u = bf16_bits(g);
+        *reinterpret_cast<unsigned short*>(smem + B_OFF_XB + elem_off(t, tid, XB_TILE)) = u;
+        if (t < T && p.g1) reinterpret_cast<unsigned short*>(p.g1)[e] = u;
+    }
+    if (tid < NQ) {
+        const int h = tid >> 4, t = tid & 15;
+        s_lse[tid] = t < T ? p.lse[((long long)b * CA_H + h) * T + t] : 0.f;
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    // ---- dattn^T[c][t] = sum_n Wout[n][c] g1[t][n] : A = Wout used MN-major ------------------------------------------------
+    if (tid == 0) {
+        tc_fence_after_sync();
+        mbar_wait(&bar[BB_WO], 0);
+        const uint32_t idesc = instr_desc_bf16(128, 16, 1, 0);
+        for (int k = 0; k < 8; ++k)
+            mma_bf16_ss(tmem + DAC, smem_desc_mn_sw128(sbase + B_OFF_PD, LTILE, 1024) + 128 * (uint64_t)k,
+                        smem_desc_k_sw128(sbase + B_OFF_XB + (k >> 2) * XB_TILE) + 2 * (k & 3), idesc, k > 0);
+        mma_commit(&bar[BB_DA]);
+    }
+    __syncwarp();
+    {
+        float da[16];
+        const int h = tid >> 5;
+        // saved forward values of this thread's column (issued ahead of the wait)
+        unsigned short at[TP], qv[TP];
+#pragma unroll
+        for (int t = 0; t < TP; ++t) {
+            const long long e = ((long long)b * T + t) * 128 + tid;
+            at[t] = t < T ? reinterpret_cast<const unsigned short*>(p.attn)[e] : (unsigned short)0;
+            qv[t] = t < T ? reinterpret_cast<const unsigned short*>(p.q)[e] : (unsigned short)0;
+        }
+        mbar_wait(&bar[BB_DA], 0);
+        tc_fence_after_sync();
+        ld_lane16(tmem, warp, DAC, da);
+#pragma unroll
+        for (int t = 0; t < TP; ++t) {
+            // delta[(h,t)] = sum over the head's 32 features (= this warp) of dattn * attn
+            const float d = warp_sum(da[t] * bf16_to_f(at[t]));
+            if (lane == 0) s_delta[TP * h + t] = d;
+            *reinterpret_cast<unsigned short*>(smem + B_OFF_DOB + elem_off(h * TP + t, tid, QB_TILE)) = t < T ? bf16_bits(da[t]) : (unsigned short)0;
+            *reinterpret_cast<unsigned short*>(smem + B_OFF_QB + elem_off(h * TP + t, tid, QB_TILE)) = qv[t];
+        }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+
+    const float sc = rsqrtf((float)CA_DH) * 1.4426950408889634f;
+    const float scale = rsqrtf((float)CA_DH);
+    const uint32_t id64 = instr_desc_bf16(128, NQ);
+#pragma unroll 1
+    for (int j = 0; j < nch; ++j) {
+        const uint32_t kv = sbase + B_OFF_KV + (j & 1) * 4 * LTILE;
+        if (tid == 0) {
+            tc_fence_after_sync();
+            mbar_wait(&bar[BB_KV0 + (j & 1)], (uint32_t)((j >> 1) & 1));
+            mma_k_tiles(tmem + SC, kv, LTILE, sbase + B_OFF_QB, QB_TILE, id64, 2, false);                  // S^T
+            mma_k_tiles(tmem + DPC, kv + 2 * LTILE, LTILE, sbase + B_OFF_DOB, QB_TILE, id64, 2, false);    // dP^T = V dOblk^T
+            mma_commit(&bar[BB_SD]);
+        }
+        __syncwarp();
+        mbar_wait(&bar[BB_SD], (uint32_t)(j & 1));
+        tc_fence_after_sync();
+        const int m = 128 * j + tid;
+        const bool kvld = m < M;
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+            float s[32], dp[32];
+            ld_lane32(tmem, warp, SC + 32 * g, s);
+            ld_lane32(tmem, warp, DPC + 32 * g, dp);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int c = 32 * g + i, t = i & 15, h = c >> 4;
+                float pd = 0.f, ds = 0.f;
+                if (kvld && t < T) {
+                    const float pr = ex2_approx(fmaf(s[i], sc, -s_lse[c]));
+                    float dm = 1.0f;
+                    if (DROP)
+                        dm = dropout_scale(dseed, p.drop.stream, (((uint64_t)b * CA_H + h) * T + t) * (uint64_t)M + m, p.drop.thresh,
+                                           p.drop.inv_keep);
+                    pd = pr * dm;
+                    ds = pr * (dp[i] * dm - s_delta[c]) * scale;
+                }
+                s[i] = pd;
+                dp[i] = ds;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                *reinterpret_cast<uint4*>(smem + B_OFF_PD + sw128_chunk_off(tid, 4 * g + c)) = pack8_bf16(s + 8 * c);
+                *reinterpret_cast<uint4*>(smem + B_OFF_DS + sw128_chunk_off(tid, 4 * g + c)) = pack8_bf16(dp + 8 * c);
+            }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after_sync();
+            const uint32_t id_kn = instr_desc_bf16(128, 128, 0, 1);
+            // dV[m][c] = sum_(h,t) Pd^T[m][(h,t)] dOblk[(h,t)][c] ; dK[m][c] = sum dS^T[m][(h,t)] Qblk[(h,t)][c]
+            mma_a_k_b_mn(tmem + DVC, sbase + B_OFF_PD, 0, sbase + B_OFF_DOB, QB_TILE, id_kn, 4, false);
+            mma_a_k_b_mn(tmem + DKC, sbase + B_OFF_DS, 0, sbase + B_OFF_QB, QB_TILE, id_kn, 4, false);
+            // dQ^T[c][(h,t)] += sum_m K[m][c] dS^T[m][(h,t)]
+            const uint32_t id_mm = instr_desc_bf16(128, NQ, 1, 1);
+            const int ks = min(8, (M - 128 * j + 15) >> 4);
+            for (int k = 0; k < ks; ++k)
+                mma_bf16_ss(tmem + DQC, smem_desc_mn_sw128(kv, LTILE, 1024) + 128 * (uint64_t)k,
+                            smem_desc_mn_sw128(sbase + B_OFF_DS, 1024, 1024) + 128 * (uint64_t)k, id_mm, (j > 0 || k > 0) ? 1u : 0u);
+            mma_commit(&bar[BB_G]);
+        }
+        __syncwarp();
+        mbar_wait(&bar[BB_G], (uint32_t)(j & 1));
+        tc_fence_after_sync();
+        if (tid == 0) {   // stage j & 1 is free: it takes the next-but-one chunk, or Wq once no chunk needs it any more
+            if (j + 2 < nch) load_chunk(j + 2);
+            else if (j == nch - 2) load_wq();
+        }
+        __syncwarp();
+        // dK | dV rows of this key -> bf16 all-layer gradient matrix
+        {
+            __nv_bfloat16* drow = p.dkv + (krow0 + m) * p.lddkv + p.kv_col0;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 256; c0 += 32) {
+                float v[32];
+                ld_lane32(tmem, warp, (c0 < 128 ? DKC + c0 : DVC + c0 - 128), v);
+                if (kvld) {
+                    uint4* gp = reinterpret_cast<uint4*>(drow + c0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) gp[i] = pack8_bf16(v + 8 * i);
+                }
+            }
+        }
+        tc_fence_before_sync();
+        __syncthreads();   // accumulators and Pd / dS tiles are free for the next chunk
+        tc_fence_after_sync();
+    }
+    // ---- dq[t][c] (thread = feature c) -> global + B operand ---------------------------------------------------------------
+    {
+        float dq[16];
+        const int h = tid >> 5;
+        ld_lane16(tmem, warp, DQC + TP * h, dq);
+#pragma unroll
+        for (int t = 0; t < TP; ++t) {
+            const unsigned short u = t < T ? bf16_bits(dq[t]) : (unsigned short)0;
+            *reinterpret_cast<unsigned short*>(smem + B_OFF_XB + elem_off(t, tid, XB_TILE)) = u;
+            if (t < T && p.dq) reinterpret_cast<unsigned short*>(p.dq)[((long long)b * T + t) * 128 + tid] = u;
+        }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    // ---- dxn^T[k][t] = sum_c Wq[c][k] dq[t][c] : A = Wq used MN-major ---------------------------------------------------------
+    if (tid == 0) {
+        tc_fence_after_sync();
+        mbar_wait(&bar[BB_WQ], 0);
+        const uint32_t idesc = instr_desc_bf16(128, 16, 1, 0);
+        for (int k = 0; k < 8; ++k)
+            mma_bf16_ss(tmem + DXC, smem_desc_mn_sw128(wq_addr, LTILE, 1024) + 128 * (uint64_t)k,
+                        smem_desc_k_sw128(sbase + B_OFF_XB + (k >> 2) * XB_TILE) + 2 * (k & 3), idesc, k > 0);
+        mma_commit(&bar[BB_X]);
+    }
+    __syncwarp();
+    // ---- LayerNorm backward (thread = feature k), dx = dy + LN'(dxn) -----------------------------------------------------------
+    {
+        float xh[TP], v[32];
+        const float ga = __ldg(p.n_w + tid);
+#pragma unroll
+        for (int t = 0; t < TP; ++t) {
+            const long long grow = (long long)b * T + t;
+            xh[t] = t < T ? (p.x[grow * 128 + tid] - p.stats[2 * grow]) * p.stats[2 * grow + 1] : 0.f;
+        }
+        float dxn[16];
+        mbar_wait(&bar[BB_X], 0);
+        tc_fence_after_sync();
+        ld_lane16(tmem, warp, DXC, dxn);
+        float gw = 0.f, gb = 0.f;
+#pragma unroll
+        for (int t = 0; t < TP; ++t) {
+            if (t >= T) dxn[t] = 0.f;
+            gw = fmaf(dxn[t], xh[t], gw);
+            gb += dxn[t];
+            const float g = dxn[t] * ga;
+            v[t] = g;             // sum_k g
+            v[16 + t] = g * xh[t];   // sum_k g xhat
+            dxn[t] = g;
+        }
+        const float r = warp_reduce32_cols<false>(v, lane);
+        red[warp][lane] = r;
+        __syncthreads();
+        if (tid < 32) fin[tid] = ((red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid])) * (1.0f / 128.0f);
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < TP; ++t) {
+            if (t < T) {
+                const long long grow = (long long)b * T + t;
+                const float rstd = p.stats[2 * grow + 1];
+                p.dx[grow * 128 + tid] = dyr[t] + rstd * (dxn[t] - fin[t] - xh[t] * fin[16 + t]);
+            }
+        }
+        if (p.g_n_w) atomicAdd(p.g_n_w + tid, gw);
+        if (p.g_n_b) atomicAdd(p.g_n_b + tid, gb);
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+inline bool al16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+}  // namespace
+
+extern "C" int sd_cast_bf16(const float* src, void* dst, long long n, void* stream) {
+    if (n <= 0) return SD_OK;
+    if (!src || !dst || n % 8 != 0 || !al16(src) || !al16(dst)) return SD_ERR_BAD_ARG;
+    const long long n8 = n / 8;
+    const int blocks = (int)std::min<long long>((n8 + 255) / 256, 148 * 16);
+    cast_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<uint4*>(dst), n8);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+}
+
+extern "C" int sd_ca_block_supported(int d, int H, int T, int M) {
+    if (d != 128 || H != CA_H || T < 1 || T > TP || M < 1 || M > 128 * MAXCH) return 0;
+    return tensor_map_encoder() != nullptr ? 1 : 0;
+}
+
+extern "C" int sd_kv_proj_bf16(const void* mem_bf16, long long rows, const void* w_packed, int w_rows_total, int w_row0,
+                               int w_stride, int n_layers, const float* const* biases, void* kv_out, long long ldkv,
+                               void* stream) {
+    if (rows <= 0) return SD_OK;
+    if (!mem_bf16 || !w_packed || !kv_out || n_layers < 1 || n_layers > SD_KV_MAX_LAYERS) return SD_ERR_BAD_ARG;
+    if (ldkv < 256LL * n_layers || ldkv % 8 != 0 || !al16(kv_out)) return SD_ERR_BAD_ARG;
+    if (w_row0 < 0 || w_row0 + (long long)(n_layers - 1) * w_stride + 256 > w_rows_total) return SD_ERR_BAD_ARG;
+    CUtensorMap tmA, tmW;
+    if (!encode_bf16_2d(&tmA, mem_bf16, rows, 128, 128, 128)) return SD_ERR_UNSUPPORTED;
+    if (!encode_bf16_2d(&tmW, w_packed, w_rows_total, 128, 128, 128)) return SD_ERR_UNSUPPORTED;
+    KvProjParams p{};
+    p.rows = rows; p.nblk = n_layers; p.w_row0 = w_row0; p.w_stride = w_stride;
+    for (int i = 0; i < n_layers; ++i) p.bias[i] = biases ? biases[i] : nullptr;
+    p.C = reinterpret_cast<__nv_bfloat16*>(kv_out); p.ldc = ldkv;
+    static bool configured = false;
+    if (!configured) {
+        SD_CUDA(cudaFuncSetAttribute(kv_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KP_SMEM));
+        configured = true;
+    }
+    kv_proj_kernel<<<ceil_div(rows, 128), CNT, KP_SMEM, (cudaStream_t)stream>>>(tmA, tmW, p);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+}
+
+extern "C" int sd_kv_dgrad_bf16(const void* dkv_bf16, long long rows, long long lddkv, const void* w_packed, int w_rows_total,
+                                int w_row0, int w_stride, int n_layers, float* dmem, long long lddmem, int accumulate,
+                                void* stream) {
+    if (rows <= 0) return SD_OK;
+    if (!dkv_bf16 || !w_packed || !dmem || n_layers < 1 || n_layers > SD_KV_MAX_LAYERS) return SD_ERR_BAD_ARG;
+    if (lddkv < 256LL * n_layers || lddmem < 128 || lddmem % 4 != 0 || !al16(dmem)) return SD_ERR_BAD_ARG;
+    if (w_row0 < 0 || w_row0 + (long long)(n_layers - 1) * w_stride + 256 > w_rows_total) return SD_ERR_BAD_ARG;
+    CUtensorMap tmA, tmW;
+    if (!encode_bf16_2d(&tmA, dkv_bf16, rows, 256LL * n_layers, lddkv, 128)) return SD_ERR_UNSUPPORTED;
+    if (!encode_bf16_2d(&tmW, w_packed, w_rows_total, 128, 128, 64)) return SD_ERR_UNSUPPORTED;
+    KvDgradParams p{};
+    p.rows = rows; p.nblk = n_layers; p.w_row0 = w_row0; p.w_stride = w_stride;
+    p.C = dmem; p.ldc = lddmem; p.accumulate = accumulate;
+    static bool configured = false;
+    if (!configured) {
+        SD_CUDA(cudaFuncSetAttribute(kv_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KD_SMEM));
+        configured = true;
+    }
+    kv_dgrad_kernel<<<ceil_div(rows, 128), CNT, KD_SMEM, (cudaStream_t)stream>>>(tmA, tmW, p);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+}
+
+namespace {
+template <bool DROP>
+int launch_ca_fwd(const CUtensorMap& tmW, const CUtensorMap& tmKV, const CaFwdParams& p, cudaStream_t st) {
+    auto kernel = ca_fwd_kernel<DROP>;
+    static bool configured = false;
+    if (!configured) {
+        SD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
+        configured = true;
+    }
+    kernel<<<p.B, CNT, F_SMEM, st>>>(tmW, tmKV, p);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+}
+template <bool DROP>
+int launch_ca_bwd(const CUtensorMap& tmW, const CUtensorMap& tmKV, const CaBwdParams& p, cudaStream_t st) {
+    auto kernel = ca_bwd_kernel<DROP>;
+    static bool configured = false;
+    if (!configured) {
+        SD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+        configured = true;
+    }
+    kernel<<<p.B, CNT, B_SMEM, st>>>(tmW, tmKV, p);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+}
+}  // namespace
+
+extern "C" int sd_ca_block_fwd(const sd_ca_block_desc* d, void* stream) {
+    if (!d || !d->x || !d->y || !d->w_packed || !d->kv || !d->q_b || !d->out_b || !d->n_w || !d->n_b) return SD_ERR_BAD_ARG;
+    if (d->B <= 0) return SD_OK;
+    if (!sd_ca_block_supported(128, 4, d->T, d->M)) return SD_ERR_UNSUPPORTED;
+    if (d->w_row_q < 0 || d->w_row_q + 128 > d->w_rows_total || d->w_row_o < 0 || d->w_row_o + 128 > d->w_rows_total) return SD_ERR_BAD_ARG;
+    if (d->kv_col0 < 0 || d->kv_col0 + 256 > d->ldkv || d->kv_col0 % 8 != 0) return SD_ERR_BAD_ARG;
+    if (!al16(d->x) || !al16(d->y) || !al16(d->xn_save) || !al16(d->q_save) || !al16(d->attn_save)) return SD_ERR_BAD_ARG;
+    CUtensorMap tmW, tmKV;
+    if (!encode_bf16_2d(&tmW, d->w_packed, d->w_rows_total, 128, 128, 128)) return SD_ERR_UNSUPPORTED;
+    if (!encode_bf16_2d(&tmKV, d->kv, (long long)d->B * d->M, d->ldkv, d->ldkv, 128)) return SD_ERR_UNSUPPORTED;
+    CaFwdParams p{};
+    p.x = d->x; p.y = d->y; p.B = d->B; p.T = d->T; p.M = d->M;
+    p.w_row_q = d->w_row_q; p.w_row_o = d->w_row_o; p.kv_col0 = d->kv_col0;
+    p.q_b = d->q_b; p.out_b = d->out_b; p.n_w = d->n_w; p.n_b = d->n_b;
+    p.xn_save = (__nv_bfloat16*)d->xn_save; p.q_save = (__nv_bfloat16*)d->q_save; p.attn_save = (__nv_bfloat16*)d->attn_save;
+    p.stats_save = d->stats_save; p.lse_save = d->lse_save;
+    p.drop = make_dropout(d->dropout_p, d->dropout_seed, d->dropout_stream);
+    return p.drop.thresh != 0 ? launch_ca_fwd<true>(tmW, tmKV, p, (cudaStream_t)stream)
+                              : launch_ca_fwd<false>(tmW, tmKV, p, (cudaStream_t)stream);
+}
+
+extern "C" int sd_ca_block_bwd(const sd_ca_block_bwd_desc* d, void* stream) {
+    if (!d || !d->dy || !d->dx || !d->x || !d->q || !d->attn || !d->stats || !d->lse || !d->w_packed || !d->kv || !d->dkv ||
+        !d->n_w)
+        return SD_ERR_BAD_ARG;
+    if (d->B <= 0) return SD_OK;
+    if (!sd_ca_block_supported(128, 4, d->T, d->M)) return SD_ERR_UNSUPPORTED;
+    if (d->w_row_q < 0 || d->w_row_q + 128 > d->w_rows_total || d->w_row_o < 0 || d->w_row_o + 128 > d->w_rows_total) return SD_ERR_BAD_ARG;
+    if (d->kv_col0 < 0 || d->kv_col0 + 256 > d->ldkv || d->kv_col0 + 256 > d->lddkv || d->kv_col0 % 8 != 0 || d->lddkv % 8 != 0)
+        return SD_ERR_BAD_ARG;
+    if (!al16(d->dkv)) return SD_ERR_BAD_ARG;
+    CUtensorMap tmW, tmKV;
+    if (!encode_bf16_2d(&tmW, d->w_packed, d->w_rows_total, 128, 128, 128)) return SD_ERR_UNSUPPORTED;
+    if (!encode_bf16_2d(&tmKV, d->kv, (long long)d->B * d->M, d->ldkv, d->ldkv, 128)) return SD_ERR_UNSUPPORTED;
+    CaBwdParams p{};
+    p.dy = d->dy; p.dx = d->dx; p.x = d->x; p.q = (const __nv_bfloat16*)d->q; p.attn = (const __nv_bfloat16*)d->attn;
+    p.stats = d->stats; p.lse = d->lse; p.B = d->B; p.T = d->T; p.M = d->M;
+    p.w_row_q = d->w_row_q; p.w_row_o = d->w_row_o; p.kv_col0 = d->kv_col0; p.n_w = d->n_w;
+    p.g1 = (__nv_bfloat16*)d->g1; p.dq = (__nv_bfloat16*)d->dq; p.dkv = (__nv_bfloat16*)d->dkv; p.lddkv = d->lddkv;
+    p.g_n_w = d->g_n_w; p.g_n_b = d->g_n_b;
+    p.drop = make_dropout(d->dropout_p, d->dropout_seed, d->dropout_stream);
+    return p.drop.thresh != 0 ? launch_ca_bwd<true>(tmW, tmKV, p, (cudaStream_t)stream)
+                              : launch_ca_bwd<false>(tmW, tmKV, p, (cudaStream_t)stream);
+}

@@ -435,7 +435,8 @@ LAYER_SA, LAYER_FFN = 1, 2   # sd_enc_layer_desc.blocks
 
 
 def _dp(t):
-    return None if t is None else t.data_ptr()
+    """tensor -> device pointer; raw integer pointers (views at an element offset) and None pass through"""
+    return t if (t is None or isinstance(t, int)) else t.data_ptr()
 
 
 def enc_layer_fwd(x, y, B, S, H, w_packed, w_row0, in_b, out_b, l1_b, l2_b, n1_w, n1_b, n2_w, n2_b, saves=None, dropout=None,
@@ -497,4 +498,75 @@ def wgrad_bf16(jobs, rows: int):
         a.db = None if db is None else (db if isinstance(db, int) else db.data_ptr())
     with _Timed("tma_wgrad", 2.0 * rows * 128 * 128 * len(jobs), 2.0 * rows * 256 * len(jobs), f"[{len(jobs)}x{rows}]"):
         check(_lib.lib().sd_wgrad_bf16(arr, len(jobs), rows, stream_ptr()), "sd_wgrad_bf16")
+    _count()
+
+
+# ---- layer-fused cross-attention block (csrc/cross_attn.cu) --------------------------------------------------------
+def ca_block_supported(d: int, H: int, T: int, M: int) -> bool:
+    return bool(_lib.lib().sd_ca_block_supported(d, H, T, M))
+
+
+def cast_bf16(src: torch.Tensor, dst: torch.Tensor):
+    """fp32 -> bf16 copy of a contiguous tensor (numel a multiple of 8)."""
+    n = src.numel()
+    with _Timed("cast_bf16", 0.0, 6.0 * n, f"[{n}]"):
+        check(_lib.lib().sd_cast_bf16(_f32(src).data_ptr(), dst.data_ptr(), n, stream_ptr()), "sd_cast_bf16")
+    _count()
+
+
+def kv_proj_bf16(mem_bf, w_packed, w_row0: int, w_stride: int, biases, kv_out):
+    """kv_out[:, 256 l : 256 l + 256] = mem_bf @ w_packed[w_row0 + l*w_stride : +256].T + biases[l]  for every layer l
+    (sd_kv_proj_bf16; ``biases``: list of raw pointers / tensors of 256 floats, one per layer)."""
+    rows, L = mem_bf.shape[0], len(biases)
+    arr = (_lib.c_f * L)(*[b if isinstance(b, int) else b.data_ptr() for b in biases])
+    with _Timed("kv_proj_all_layers", 2.0 * rows * 128 * 256 * L, rows * (256.0 + 512.0 * L), f"[R{rows} L{L}]"):
+        check(_lib.lib().sd_kv_proj_bf16(mem_bf.data_ptr(), rows, w_packed.data_ptr(), w_packed.shape[0], w_row0, w_stride, L, arr,
+                                         kv_out.data_ptr(), kv_out.shape[1], stream_ptr()), "sd_kv_proj_bf16")
+    _count()
+
+
+def kv_dgrad_bf16(dkv, w_packed, w_row0: int, w_stride: int, L: int, dmem, accumulate: bool):
+    """dmem (+)= dkv @ [Wkv_0; ...; Wkv_{L-1}]  (sd_kv_dgrad_bf16; dmem fp32 [rows][128])."""
+    rows = dkv.shape[0]
+    with _Timed("kv_dgrad_all_layers", 2.0 * rows * 128 * 256 * L, rows * (512.0 * L + 512.0), f"[R{rows} L{L}]"):
+        check(_lib.lib().sd_kv_dgrad_bf16(dkv.data_ptr(), rows, dkv.shape[1], w_packed.data_ptr(), w_packed.shape[0], w_row0, w_stride,
+                                          L, _f32(dmem).data_ptr(), dmem.shape[1], int(accumulate), stream_ptr()), "sd_kv_dgrad_bf16")
+    _count()
+
+
+def ca_block_fwd(x, y, B, T, M, w_packed, w_row_q, w_row_o, kv, kv_col0, q_b, out_b, n_w, n_b, saves=None, dropout=None):
+    """Fused cross-attention block forward (sd_ca_block_fwd).  ``saves`` = (xn, q, attn bf16 [B*T][128], stats fp32 [B*T][2],
+    lse fp32 [B][4][T]) or None; ``q_b`` / ``out_b`` may be raw pointers."""
+    d = _lib.CaBlockDesc()
+    d.x, d.y, d.B, d.T, d.M = x.data_ptr(), y.data_ptr(), B, T, M
+    d.w_packed, d.w_rows_total, d.w_row_q, d.w_row_o = w_packed.data_ptr(), w_packed.shape[0], w_row_q, w_row_o
+    d.kv, d.ldkv, d.kv_col0 = kv.data_ptr(), kv.shape[1], kv_col0
+    d.q_b, d.out_b, d.n_w, d.n_b = _dp(q_b), _dp(out_b), _dp(n_w), _dp(n_b)
+    if saves is not None:
+        d.xn_save, d.q_save, d.attn_save, d.stats_save, d.lse_save = (_dp(t) for t in saves)
+    if dropout is not None and dropout[0] > 0.0:
+        d.dropout_p, d.dropout_seed, d.dropout_stream = dropout
+    # LN + q-proj + out-proj (4 T d^2) + scores and P.V (4 T M d) per sample; reads x, K | V (bf16), writes y
+    flops = B * (4.0 * T * 128 * 128 + 4.0 * T * M * 128)
+    with _Timed("fused_ca_block_fwd", flops, B * (T * 128 * 8.0 + M * 512.0), f"[B{B} T{T} M{M}]"):
+        check(_lib.lib().sd_ca_block_fwd(C.byref(d), stream_ptr()), "sd_ca_block_fwd")
+    _count()
+
+
+def ca_block_bwd(dy, dx, x, q, attn, stats, lse, B, T, M, w_packed, w_row_q, w_row_o, kv, kv_col0, n_w, g1, dq, dkv, g_n_w, g_n_b,
+                 dropout=None):
+    """Fused cross-attention block backward, data path (sd_ca_block_bwd)."""
+    d = _lib.CaBlockBwdDesc()
+    d.dy, d.dx, d.x, d.q, d.attn, d.stats, d.lse = (_dp(t) for t in (dy, dx, x, q, attn, stats, lse))
+    d.B, d.T, d.M = B, T, M
+    d.w_packed, d.w_rows_total, d.w_row_q, d.w_row_o = w_packed.data_ptr(), w_packed.shape[0], w_row_q, w_row_o
+    d.kv, d.ldkv, d.kv_col0 = kv.data_ptr(), kv.shape[1], kv_col0
+    d.n_w = _dp(n_w)
+    d.g1, d.dq, d.dkv, d.lddkv = _dp(g1), _dp(dq), dkv.data_ptr(), dkv.shape[1]
+    d.g_n_w, d.g_n_b = _dp(g_n_w), _dp(g_n_b)
+    if dropout is not None and dropout[0] > 0.0:
+        d.dropout_p, d.dropout_seed, d.dropout_stream = dropout
+    flops = B * (4.0 * T * 128 * 128 + 10.0 * T * M * 128)
+    with _Timed("fused_ca_block_bwd", flops, B * (T * 128 * 16.0 + M * 1024.0), f"[B{B} T{T} M{M}]"):
+        check(_lib.lib().sd_ca_block_bwd(C.byref(d), stream_ptr()), "sd_ca_block_bwd")
     _count()
