@@ -341,9 +341,9 @@ def _bf16(shape, like):
     return torch.empty(shape, device=like.device, dtype=torch.bfloat16)
 
 
-def _dec_layer_fused_fwd(h, mem2, B, T, Mm, H, P, wp, l, cfg: RunCfg, save: bool):
-    """One decoder layer with the self-attention and feed-forward blocks as fused kernels (the cross-attention block in
-    between runs on the per-op kernels: its keys / values are the 312-token memory)."""
+def _dec_layer_fused_fwd(h, mem2, B, T, Mm, H, P, wp, l, cfg: RunCfg, save: bool, kv_all=None):
+    """One decoder layer as three fused kernels: self-attention block, cross-attention block (``kv_all``: the memory's K | V
+    projections of all layers, bf16; None -> per-op kernels, shapes outside sd_ca_block_supported), feed-forward block."""
     (sa_in_w, sa_in_b, sa_out_w, sa_out_b, ca_in_w, ca_in_b, ca_out_w, ca_out_b, l1_w, l1_b, l2_w, l2_b, n1_w, n1_b, n2_w, n2_b,
      n3_w, n3_b) = P
     d = h.shape[-1]
@@ -358,7 +358,18 @@ def _dec_layer_fused_fwd(h, mem2, B, T, Mm, H, P, wp, l, cfg: RunCfg, save: bool
         x1, xn1, attn = h, None, None
         ops.enc_layer_fwd(h, h, B, T, H, wp, r0, sa_in_b, sa_out_b, None, None, n1_w, n1_b, None, None,
                           dropout=cfg.drop(8 * l), blocks=ops.LAYER_SA)
-    x2, s2 = _ca_fwd(x1, mem2, B, T, Mm, H, ca_in_w, ca_in_b, ca_out_w, ca_out_b, n2_w, n2_b, cfg, 8 * l + 2, save)
+    if kv_all is None:
+        x2, s2 = _ca_fwd(x1, mem2, B, T, Mm, H, ca_in_w, ca_in_b, ca_out_w, ca_out_b, n2_w, n2_b, cfg, 8 * l + 2, save)
+    elif save:
+        x2 = _empty((M, d), h)
+        xn2, q2, attn2 = _bf16((M, d), h), _bf16((M, d), h), _bf16((M, d), h)
+        stats, lse = _empty((M, 2), h), _empty((B, H, T), h)
+        ops.ca_block_fwd(x1, x2, B, T, Mm, wp, r0 + 512, r0 + 896, kv_all, 256 * l, ca_in_b, ca_out_b, n2_w, n2_b,
+                         saves=(xn2, q2, attn2, stats, lse), dropout=cfg.drop(8 * l + 2))
+        s2 = (x1, xn2, q2, attn2, stats, lse)
+    else:
+        ops.ca_block_fwd(x1, x1, B, T, Mm, wp, r0 + 512, r0 + 896, kv_all, 256 * l, ca_in_b, ca_out_b, n2_w, n2_b)
+        x2, s2 = x1, None
     drop = cfg.drop(8 * l + 4)
     kw = dict(dropout=drop, blocks=ops.LAYER_FFN, w_row_ffn=r0 + 1024, dropout_stream_ffn=cfg.stream_base + 8 * l + 4)
     if save:
@@ -371,7 +382,7 @@ def _dec_layer_fused_fwd(h, mem2, B, T, Mm, H, P, wp, l, cfg: RunCfg, save: bool
     return x2, None
 
 
-def _dec_layer_fused_bwd(dh, saved, mem2, dmem, B, T, Mm, H, P, G, wp, l, cfg: RunCfg, bufs):
+def _dec_layer_fused_bwd(dh, saved, mem2, dmem, B, T, Mm, H, P, G, wp, l, cfg: RunCfg, bufs, kvctx=None):
     (sa_in_w, sa_in_b, sa_out_w, sa_out_b, ca_in_w, ca_in_b, ca_out_w, ca_out_b, l1_w, l1_b, l2_w, l2_b, n1_w, n1_b, n2_w, n2_b,
      n3_w, n3_b) = P
     (g_sa_in_w, g_sa_in_b, g_sa_out_w, g_sa_out_b, g_ca_in_w, g_ca_in_b, g_ca_out_w, g_ca_out_b, g_l1_w, g_l1_b, g_l2_w, g_l2_b,
@@ -386,9 +397,17 @@ def _dec_layer_fused_bwd(dh, saved, mem2, dmem, B, T, Mm, H, P, G, wp, l, cfg: R
                       None, n3_w, dropout=cfg.drop(8 * l + 4), blocks=ops.LAYER_FFN, w_row_ffn=r0 + 1024,
                       dropout_stream_ffn=cfg.stream_base + 8 * l + 4)
     ops.wgrad_bf16([(dhpre, 0, xn3, 0, _p(g_l1_w), d, _p(g_l1_b)), (g2, 0, hact, 0, _p(g_l2_w), d, _p(g_l2_b))], M)
-    # cross-attention block (per-op kernels)
-    dh = _ca_bwd(dx, s2, mem2, dmem, B, T, Mm, H, ca_in_w, ca_out_w, n2_w, n2_b, g_ca_in_w, g_ca_in_b, g_ca_out_w, g_ca_out_b,
-                 g_n2_w, g_n2_b, cfg, 8 * l + 2)
+    # cross-attention block
+    if kvctx is None:
+        dh = _ca_bwd(dx, s2, mem2, dmem, B, T, Mm, H, ca_in_w, ca_out_w, n2_w, n2_b, g_ca_in_w, g_ca_in_b, g_ca_out_w, g_ca_out_b,
+                     g_n2_w, g_n2_b, cfg, 8 * l + 2)
+    else:
+        kv_all, dkv_all = kvctx
+        x1, xn2, q2, attn2, stats, lse = s2
+        ops.ca_block_bwd(dx, dx, x1, q2, attn2, stats, lse, B, T, Mm, wp, r0 + 512, r0 + 896, kv_all, 256 * l, n2_w, g1, dhpre, dkv_all,
+                         g_n2_w, g_n2_b, dropout=cfg.drop(8 * l + 2))   # g1 / dhpre: free bf16 buffers at this point
+        ops.wgrad_bf16([(g1, 0, attn2, 0, _p(g_ca_out_w), d, _p(g_ca_out_b)), (dhpre, 0, xn2, 0, _p(g_ca_in_w), d, _p(g_ca_in_b))], M)
+        dh = dx
     # self-attention block
     ops.enc_layer_bwd(dh, dx, h_in, None, xn1, None, None, None, g1, dqkv, g_n1_w, g_n1_b, None, None, B, T, H, wp, r0, sa_in_b,
                       None, n1_w, None, dropout=cfg.drop(8 * l), blocks=ops.LAYER_SA)
@@ -416,10 +435,18 @@ class DenoiserFn(torch.autograd.Function):
         acts = []
         fused = L > 0 and _fused_enc_ok(cfg, d, layer_params[8].shape[0], T, H)
         wp = _pack_dec_weights(layer_params, L, d) if fused else None
+        mem_bf = kv_all = None
+        if fused and L <= ops.KV_MAX_LAYERS and ops.ca_block_supported(d, H, T, Mm):
+            # the memory is not layer-normed and every layer reads it: ONE bf16 copy, ONE GEMM for the K | V of all layers
+            mem_bf = _bf16((B * Mm, d), mem2)
+            ops.cast_bf16(mem2, mem_bf)
+            kv_all = _bf16((B * Mm, 256 * L), mem2)
+            ops.kv_proj_bf16(mem_bf, wp, 640, ops.DEC_ROWS_PER_LAYER, [_p(layer_params[l * DEC_PARAMS_PER_LAYER + 5], d) for l in range(L)],
+                             kv_all)
         for l in range(L):
             P = layer_params[l * DEC_PARAMS_PER_LAYER: (l + 1) * DEC_PARAMS_PER_LAYER]
             if fused:
-                h, sv = _dec_layer_fused_fwd(h, mem2, B, T, Mm, H, P, wp, l, cfg, save)
+                h, sv = _dec_layer_fused_fwd(h, mem2, B, T, Mm, H, P, wp, l, cfg, save, kv_all)
                 acts.append(sv)
                 continue
             (sa_in_w, sa_in_b, sa_out_w, sa_out_b, ca_in_w, ca_in_b, ca_out_w, ca_out_b, l1_w, l1_b, l2_w, l2_b, n1_w,
@@ -432,6 +459,7 @@ class DenoiserFn(torch.autograd.Function):
         ops.gemm(h, d, MK, fc_w, d, NK, out, J, Mq, J, d, precision=cfg.precision, bias=fc_b)
         if save:
             ctx.cfg, ctx.dims, ctx.acts, ctx.h_last, ctx.fused = cfg, (B, T, Mm, H, d, J, L), acts, h, wp
+            ctx.kv = (mem_bf, kv_all)
             ctx.save_for_backward(x2, mem2, emb_w, emb_b, fc_w, fc_b, *layer_params)
         return out.view(B, T, J)
 
@@ -449,7 +477,13 @@ class DenoiserFn(torch.autograd.Function):
         dh = _empty((Mq, d), mem2)
         ops.gemm(do, J, MK, fc_w, d, KN, dh, d, Mq, d, J, precision=cfg.precision)
         need_dmem = ctx.needs_input_grad[7]
-        dmem = torch.zeros((B * Mm, d), device=mem2.device, dtype=torch.float32) if need_dmem else None
+        mem_bf, kv_all = ctx.kv
+        kvctx = None
+        if kv_all is not None:
+            kvctx = (kv_all, _bf16((B * Mm, 256 * L), mem2))   # every element is written by the layers' backward kernels
+            dmem = _empty((B * Mm, d), mem2) if need_dmem else None
+        else:
+            dmem = torch.zeros((B * Mm, d), device=mem2.device, dtype=torch.float32) if need_dmem else None
         bufs = None
         if ctx.fused is not None:
             bufs = (_bf16((Mq, d), mem2), _bf16((Mq, d), mem2), _bf16((Mq, d), mem2), _bf16((Mq, 3 * d), mem2), _empty((Mq, d), mem2))
@@ -457,7 +491,8 @@ class DenoiserFn(torch.autograd.Function):
             if ctx.fused is not None:
                 dh = _dec_layer_fused_bwd(dh, ctx.acts[l], mem2, dmem, B, T, Mm, H,
                                           layer_params[l * DEC_PARAMS_PER_LAYER: (l + 1) * DEC_PARAMS_PER_LAYER],
-                                          g_layers[l * DEC_PARAMS_PER_LAYER: (l + 1) * DEC_PARAMS_PER_LAYER], ctx.fused, l, cfg, bufs)
+                                          g_layers[l * DEC_PARAMS_PER_LAYER: (l + 1) * DEC_PARAMS_PER_LAYER], ctx.fused, l, cfg, bufs,
+                                          kvctx)
                 continue
             (sa_in_w, sa_in_b, sa_out_w, sa_out_b, ca_in_w, ca_in_b, ca_out_w, ca_out_b, l1_w, l1_b, l2_w, l2_b, n1_w,
              n1_b, n2_w, n2_b, n3_w, n3_b) = layer_params[l * DEC_PARAMS_PER_LAYER: (l + 1) * DEC_PARAMS_PER_LAYER]
@@ -470,6 +505,19 @@ class DenoiserFn(torch.autograd.Function):
                          g_ca_out_w, g_ca_out_b, g_n2_w, g_n2_b, cfg, 8 * l + 2)
             dh = _sa_bwd(dh, s1, B, T, H, sa_in_w, sa_out_w, n1_w, n1_b, g_sa_in_w, g_sa_in_b, g_sa_out_w, g_sa_out_b,
                          g_n1_w, g_n1_b, cfg, 8 * l)
+        if kvctx is not None:
+            # k / v projection of the memory: weight / bias gradients of all layers (rows d:3d of each in_proj) and ONE data GEMM
+            dkv_all = kvctx[1]
+            jobs = []
+            for l in range(L):
+                g_w, g_b = g_layers[l * DEC_PARAMS_PER_LAYER + 4], g_layers[l * DEC_PARAMS_PER_LAYER + 5]
+                jobs += [(dkv_all, 256 * l, mem_bf, 0, _p(g_w, d * d), d, _p(g_b, d)),
+                         (dkv_all, 256 * l + 128, mem_bf, 0, _p(g_w, 2 * d * d), d, _p(g_b, 2 * d))]
+            for i in range(0, len(jobs), ops.WGRAD_MAX_JOBS):
+                ops.wgrad_bf16(jobs[i: i + ops.WGRAD_MAX_JOBS], B * Mm)
+            if dmem is not None:
+                ops.kv_dgrad_bf16(dkv_all, ctx.fused, 640, ops.DEC_ROWS_PER_LAYER, L, dmem, False)
+        ctx.kv = None
         ops.colsum_accum(dh, d, Mq, d, g_emb_b)
         ops.gemm(dh, d, KM, x2, J, KN, g_emb_w, J, d, J, Mq, precision=cfg.precision, accumulate=True)
         dx = None

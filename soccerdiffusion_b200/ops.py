@@ -407,6 +407,8 @@ def bn_finalize(sums, R, C, eps, momentum, mean, invstd, running_mean, running_v
 
 # ---- layer-fused tensor-core path (bf16 mode, d_model = ff = 128) ------------------------------------------------------
 ENC_ROWS_PER_LAYER = 768     # in_proj (384) | out_proj | linear1 | linear2
+WGRAD_MAX_JOBS = _lib.WGRAD_MAX_JOBS
+KV_MAX_LAYERS = _lib.KV_MAX_LAYERS
 DEC_ROWS_PER_LAYER = 1280    # sa.in_proj (384) | sa.out_proj | ca.in_proj (384) | ca.out_proj | linear1 | linear2
 
 
