@@ -394,6 +394,11 @@ def run_ours(args):
 
     hp = dict(config.SCALED if args.config == "scaled" else config.DEFAULT)
     bs = args.batch
+    strong = args.global_batch > 0
+    if strong:
+        if args.global_batch % world != 0:
+            raise SystemExit(f"--global-batch {args.global_batch} is not divisible by {world} GPUs")
+        bs = args.global_batch // world
     torch.manual_seed(0)
     model = config.build_model(hp).to(dev)
     model.mean.fill_(3.14159)
@@ -627,6 +632,12 @@ def run_ours(args):
     if rank == 0 and not args.no_ddim:
         ddim = ddim_latency(model, hp, dev, args.precision)
 
+    # ---- batched inference, sharded by trajectory over ALL ranks (BASELINE.json configs[4]; no collective) ----
+    batched = None
+    if not args.no_ddim:
+        hpn = dict(hp, _name=args.config)
+        batched = batched_inference(model, hpn, dev, args.precision, rank, world, scaled_too=args.config != "scaled")
+
     distill = None
     if rank == 0 and world == 1 and args.workload == "full" and not args.no_ddim:
         try:
@@ -679,7 +690,7 @@ def run_ours(args):
                     input=fmt_in[not use_u8]) if ms_e2e_u8 else None)
         line = dict(
             metric=METRIC, value=gb * args.steps / (ms / 1e3), unit=UNIT, n_gpus=world, steps=args.steps,
-            warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+            warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong" if strong else "weak", vs_baseline=None,
             dtype="f32" if args.precision == "fp32" else "bf16", data="synthetic", impl="ours",
             config=dict(architecture=args.config, workload={"full": "default.yaml full training step incl. ResNet18 trunk (layer1-4 convolutions = cuDNN library calls)",
                                   "inscope": "default.yaml training step, image tokens precomputed (trunk outside the step)",
@@ -693,7 +704,7 @@ def run_ours(args):
                      loss_readback="every step, pinned async copy, read on the host one step behind the launch front",
                      pipeline="steady state: feeder two batches ahead, K copies issued and K steps executed between the events",
                      h2d_gbps_measured=round(h2d_gbps, 1), input=fmt_in[use_u8] if args.workload == "full" else "no frames"),
-            gpu_launches=launches, clocks=clk, kernel_classes=kernel_classes, ddim=ddim, distill=distill,
+            gpu_launches=launches, clocks=clk, kernel_classes=kernel_classes, ddim=ddim, batched_inference=batched, distill=distill,
             **({"e2e_float32_frames" if use_u8 else "e2e_uint8": alt}),
             roofline=roofline, roofline_own=roofline_own, cpu_baseline=cpu, extra=extra)
         emit(line)
@@ -838,6 +849,73 @@ def ddim_latency(model, hp, dev, precision, reps=200):
     return out
 
 
+def batched_inference(model, hp, dev, precision, rank, world, per_gpu=(64, 512), scaled_too=True):
+    """Batched inference sharded by INDEPENDENT trajectories (BASELINE.json configs[4]): every rank samples
+    its own `per_gpu` trajectories with the 30-step DDIM loop, no collective on the data path; timed on the device per rank
+    between barriers, MAX over ranks; trajectories/s is the whole-job aggregate.  "auto" = the tensor-core sampler in bf16
+    mode (layer-fused tcgen05 kernels, context K | V projected once, the loop replayed from one CUDA graph); "cta" = the fp32
+    persistent one-CTA-per-trajectory kernel, for comparison."""
+    import torch
+    import torch.distributed as dist
+
+    from soccerdiffusion_b200 import config
+    from soccerdiffusion_b200.schedulers import DDIMScheduler
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(m, h, B, kind, reps):
+        d = h["hidden_dim"]
+        g = torch.Generator(device=dev).manual_seed(100 + rank)
+        lens = [h["action_context_length"], h["imu_context_length"], h["joint_state_context_length"], h["image_context_length"], 1]
+        ctx = [torch.randn(B, n, d, device=dev, generator=g) for n in lens]
+        x = torch.randn(B, h["trajectory_prediction_length"], h["num_joints"], device=dev, generator=g)
+        sch = DDIMScheduler(beta_schedule="squaredcos_cap_v2", clip_sample=False)
+        sch.set_timesteps(30)
+        for _ in range(3):
+            m.sample(ctx, x, sch, denormalize=True, sampler=kind)
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            m.sample(ctx, x, sch, denormalize=True, sampler=kind)
+        e1.record()
+        sync()
+        ms = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms.item())
+        return dict(ms_per_batch=round(ms, 3), trajectories_per_s=round(world * B * 1e3 / ms, 1), global_trajectories=world * B,
+                    kernel=getattr(m, "last_sampler", "?"))
+
+    out = dict(n_gpus=world, sharding="independent trajectories per rank, no data-path collective", ddim_steps=30,
+               precision_mode=precision, timing="CUDA events per rank between barriers, max over ranks")
+    model.eval()
+    with torch.no_grad():
+        for B in per_gpu:
+            for kind in (("auto", "cta") if B <= 64 else ("auto",)):
+                try:
+                    out[f"{hp.get('_name', 'arch')}_per_gpu_{B}_{kind}"] = run(model, hp, B, kind, 10 if B <= 64 else 5)
+                except Exception as e:   # noqa: BLE001
+                    out[f"per_gpu_{B}_{kind}"] = dict(error=f"{type(e).__name__}: {e}"[:160])
+                    torch.cuda.synchronize()
+        if scaled_too:
+            try:
+                shp = dict(config.SCALED)
+                torch.manual_seed(3)
+                sm = config.build_model(shp).to(dev).eval()
+                out["scaled_per_gpu_64_auto"] = run(sm, shp, 64, "auto", 5)
+                out["scaled_per_gpu_64_cta"] = run(sm, shp, 64, "cta", 3)
+                del sm
+            except Exception as e:   # noqa: BLE001
+                out["scaled_per_gpu_64_auto"] = dict(error=f"{type(e).__name__}: {e}"[:160])
+                torch.cuda.synchronize()
+    model.train()
+    return out
+
+
 def distill_throughput(hp, dev, bs, precision, steps=3):
     """distill.py:160-205 as one workload: the teacher encodes the batch and samples a 30-step DDIM
     trajectory per sample under no_grad (persistent sampler kernels), the student is trained for one step on the
@@ -900,6 +978,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("SD_B200_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="STRONG scaling: total batch over all GPUs (per-GPU batch = global / N; BASELINE.json configs[3] asks 2048); "
+                         "0 = weak scaling with --batch per GPU")
     ap.add_argument("--cpu-batch", type=int, default=8, help="bounded CPU sample batch")
     ap.add_argument("--workload", default="full", choices=["full", "inscope", "denoiser"])
     ap.add_argument("--config", default="default", choices=["default", "scaled"],

@@ -368,6 +368,10 @@ int sd_wgrad_bf16(const sd_wgrad_job* jobs, int n_jobs, long long rows, void* st
  * (The k/v weight gradients are sd_wgrad_bf16 jobs with G = dkv, X = the bf16 memory.) */
 #define SD_KV_MAX_LAYERS 16
 int sd_cast_bf16(const float* src, void* dst_bf16, long long n, void* stream);
+/* dst[(b*block_rows + row)*ld + c] = src_row[c] for b < B, c < ncols (bf16; the step token's K | V row of one DDIM step
+ * written into every trajectory's cached K | V, ros.py:301-310 calls the model with the same t for the whole batch) */
+int sd_bcast_row_bf16(void* dst, long long ld, long long block_rows, long long row, int B, const void* src_row, int ncols,
+                      void* stream);
 int sd_kv_proj_bf16(const void* mem_bf16, long long rows, const void* w_packed, int w_rows_total, int w_row0, int w_stride,
                     int n_layers, const float* const* biases, void* kv_out, long long ldkv, void* stream);
 int sd_kv_dgrad_bf16(const void* dkv_bf16, long long rows, long long lddkv, const void* w_packed, int w_rows_total, int w_row0,
@@ -387,7 +391,8 @@ typedef struct sd_ca_block_desc {
     void* xn_save; void* q_save; void* attn_save; float* stats_save; float* lse_save;
     float dropout_p; unsigned long long dropout_seed; unsigned int dropout_stream;
 } sd_ca_block_desc;
-int sd_ca_block_supported(int d, int H, int T, int M);
+int sd_ca_block_supported(int d, int H, int T, int M);     /* forward with saves + backward: T <= 16 */
+int sd_ca_block_fwd_supported(int d, int H, int T, int M); /* forward without saves (inference): T <= 64, rows in groups of <= 16 */
 int sd_ca_block_fwd(const sd_ca_block_desc* desc, void* stream);
 
 /* Backward of the block (data path): dy -> dx (fp32 [B*T][128], may alias), g1 = dy*mask and dq (bf16 [B*T][128], the G

@@ -182,9 +182,11 @@ SIGNATURES = {
     "sd_enc_layer_bwd": [C.POINTER(EncLayerBwdDesc), c_f],
     "sd_wgrad_bf16": [C.POINTER(WgradJob), c_i, c_ll, c_f],
     "sd_cast_bf16": [c_f, c_f, c_ll, c_f],
+    "sd_bcast_row_bf16": [c_f, c_ll, c_ll, c_ll, c_i, c_f, c_i, c_f],
     "sd_kv_proj_bf16": [c_f, c_ll, c_f, c_i, c_i, c_i, c_i, C.POINTER(c_f), c_f, c_ll, c_f],
     "sd_kv_dgrad_bf16": [c_f, c_ll, c_ll, c_f, c_i, c_i, c_i, c_i, c_f, c_ll, c_i, c_f],
     "sd_ca_block_supported": [c_i, c_i, c_i, c_i],
+    "sd_ca_block_fwd_supported": [c_i, c_i, c_i, c_i],
     "sd_ca_block_fwd": [C.POINTER(CaBlockDesc), c_f],
     "sd_ca_block_bwd": [C.POINTER(CaBlockBwdDesc), c_f],
 }

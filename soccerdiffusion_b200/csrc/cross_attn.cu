@@ -77,6 +77,15 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, uint4* __restric
     }
 }
 
+// one bf16 row broadcast into row `row` of each of the B blocks of `block_rows` rows (the step token's K | V of a DDIM step)
+__global__ void bcast_row_bf16_kernel(uint4* __restrict__ dst, long long ld8, long long block_rows, long long row, int B,
+                                      const uint4* __restrict__ src, int n8) {
+    const int b = blockIdx.x;
+    if (b >= B) return;
+    uint4* d = dst + ((long long)b * block_rows + row) * ld8;
+    for (int i = threadIdx.x; i < n8; i += blockDim.x) d[i] = src[i];
+}
+
 // =====================================================================================================================
 // K/V projection of the memory for all layers: C[row][256 j + n] = sum_k A[row][k] W[w_row0 + j w_stride + n][k] + bias_j[n]
 struct KvProjParams {
@@ -268,6 +277,7 @@ struct CaFwdParams {
     const float* x;
     float* y;
     int B, T, M;
+    int groups, Tg;            // query-row groups per sample, rows per group (<= 16)
     int w_row_q, w_row_o;      // packed-weight rows of Wq and Wout
     int kv_col0;               // first column of this layer's K | V inside the all-layer K/V matrix
     const float *q_b, *out_b, *n_w, *n_b;
@@ -290,7 +300,10 @@ __global__ void __launch_bounds__(CNT, 1) ca_fwd_kernel(const __grid_constant__ 
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.x, T = p.T, M = p.M;
+    // a sample's T query rows are handled in p.groups groups of p.Tg <= 16 rows, one CTA each (the rows of a cross-attention
+    // are independent): T = this group's row count, Tf = the sample's, t0 = the group's first row
+    const int b = blockIdx.x / p.groups, t0 = (blockIdx.x % p.groups) * p.Tg, Tf = p.T, T = min(p.Tg, Tf - t0), M = p.M;
+    const long long rowb = (long long)b * Tf + t0;
     const int nch = (M + 127) >> 7;
     const long long krow0 = (long long)b * M;
 
@@ -331,7 +344,7 @@ __global__ void __launch_bounds__(CNT, 1) ca_fwd_kernel(const __grid_constant__ 
         const float4 be = __ldg(reinterpret_cast<const float4*>(p.n_b) + lane);
         for (int t = warp; t < TP; t += 4) {
             float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-            const long long grow = (long long)b * T + t;
+            const long long grow = rowb + t;
             if (t < T) xv = reinterpret_cast<const float4*>(p.x + grow * 128)[lane];
             const float mean = warp_sum((xv.x + xv.y) + (xv.z + xv.w)) * (1.0f / 128.0f);
             const float c0 = xv.x - mean, c1 = xv.y - mean, c2 = xv.z - mean, c3 = xv.w - mean;
@@ -377,7 +390,7 @@ __global__ void __launch_bounds__(CNT, 1) ca_fwd_kernel(const __grid_constant__ 
         for (int t = 0; t < TP; ++t) {
             const unsigned short u = t < T ? bf16_bits(q[t] + bq) : (unsigned short)0;
             *reinterpret_cast<unsigned short*>(smem + F_OFF_QB + elem_off(h * TP + t, tid, QB_TILE)) = u;
-            if (t < T && p.q_save) reinterpret_cast<unsigned short*>(p.q_save)[((long long)b * T + t) * 128 + tid] = u;
+            if (t < T && p.q_save) reinterpret_cast<unsigned short*>(p.q_save)[(rowb + t) * 128 + tid] = u;
         }
     }
     fence_proxy_async_smem();
@@ -445,7 +458,7 @@ __global__ void __launch_bounds__(CNT, 1) ca_fwd_kernel(const __grid_constant__ 
                 for (int i = 0; i < 32; ++i) {
                     const int h = (32 * g + i) >> 4, t = i & 15;
                     if (t < T)
-                        s[i] *= dropout_scale(dseed, p.drop.stream, (((uint64_t)b * CA_H + h) * T + t) * (uint64_t)M + m, p.drop.thresh,
+                        s[i] *= dropout_scale(dseed, p.drop.stream, (((uint64_t)b * CA_H + h) * Tf + t0 + t) * (uint64_t)M + m, p.drop.thresh,
                                               p.drop.inv_keep);
                 }
             }
@@ -464,7 +477,7 @@ __global__ void __launch_bounds__(CNT, 1) ca_fwd_kernel(const __grid_constant__ 
         const float sum = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
         fin_inv[tid] = 1.0f / sum;
         const int h = tid >> 4, t = tid & 15;
-        if (t < T && p.lse_save) p.lse_save[((long long)b * CA_H + h) * T + t] = fin_max[tid] + log2f(sum);
+        if (t < T && p.lse_save) p.lse_save[((long long)b * CA_H + h) * Tf + t0 + t] = fin_max[tid] + log2f(sum);
     }
     // ---- O^T[c][(h,t)] = sum_m V[m][c] P^T[m][(h,t)] -------------------------------------------------------------------------
     if (tid == 0) {
@@ -483,7 +496,7 @@ __global__ void __launch_bounds__(CNT, 1) ca_fwd_kernel(const __grid_constant__ 
     // residual rows of this thread's column: issued ahead of the waits
     float xr[TP];
 #pragma unroll
-    for (int t = 0; t < TP; ++t) xr[t] = t < T ? p.x[((long long)b * T + t) * 128 + tid] : 0.f;
+    for (int t = 0; t < TP; ++t) xr[t] = t < T ? p.x[(rowb + t) * 128 + tid] : 0.f;
     {
         float o[16];
         const int h = tid >> 5;
@@ -494,7 +507,7 @@ __global__ void __launch_bounds__(CNT, 1) ca_fwd_kernel(const __grid_constant__ 
         for (int t = 0; t < TP; ++t) {
             const unsigned short u = t < T ? bf16_bits(o[t] * fin_inv[TP * h + t]) : (unsigned short)0;
             *reinterpret_cast<unsigned short*>(smem + F_OFF_XB + elem_off(t, tid, XB_TILE)) = u;
-            if (t < T && p.attn_save) reinterpret_cast<unsigned short*>(p.attn_save)[((long long)b * T + t) * 128 + tid] = u;
+            if (t < T && p.attn_save) reinterpret_cast<unsigned short*>(p.attn_save)[(rowb + t) * 128 + tid] = u;
         }
     }
     fence_proxy_async_smem();
@@ -517,7 +530,7 @@ __global__ void __launch_bounds__(CNT, 1) ca_fwd_kernel(const __grid_constant__ 
 #pragma unroll
         for (int t = 0; t < TP; ++t) {
             if (t < T) {
-                const long long e = ((long long)b * T + t) * 128 + tid;
+                const long long e = (rowb + t) * 128 + tid;
                 float a = v[t] + bo;
                 if (DROP) a *= dropout_scale(dseed, p.drop.stream + 1, (uint64_t)e, p.drop.thresh, p.drop.inv_keep);
                 p.y[e] = xr[t] + a;
@@ -843,8 +856,25 @@ extern "C" int sd_cast_bf16(const float* src, void* dst, long long n, void* stre
     return SD_OK;
 }
 
+extern "C" int sd_bcast_row_bf16(void* dst, long long ld, long long block_rows, long long row, int B, const void* src_row,
+                                 int ncols, void* stream) {
+    if (B <= 0 || ncols <= 0) return SD_OK;
+    if (!dst || !src_row || ld % 8 != 0 || ncols % 8 != 0 || ncols > ld || row < 0 || row >= block_rows || !al16(dst) || !al16(src_row))
+        return SD_ERR_BAD_ARG;
+    bcast_row_bf16_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint4*>(dst), ld / 8, block_rows, row, B,
+                                                                reinterpret_cast<const uint4*>(src_row), ncols / 8);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+}
+
 extern "C" int sd_ca_block_supported(int d, int H, int T, int M) {
     if (d != 128 || H != CA_H || T < 1 || T > TP || M < 1 || M > 128 * MAXCH) return 0;
+    return tensor_map_encoder() != nullptr ? 1 : 0;
+}
+
+// inference (no saves): any T <= 64 — the query rows are split into groups of <= 16, one CTA each
+extern "C" int sd_ca_block_fwd_supported(int d, int H, int T, int M) {
+    if (d != 128 || H != CA_H || T < 1 || T > 4 * TP || M < 1 || M > 128 * MAXCH) return 0;
     return tensor_map_encoder() != nullptr ? 1 : 0;
 }
 
@@ -904,7 +934,7 @@ int launch_ca_fwd(const CUtensorMap& tmW, const CUtensorMap& tmKV, const CaFwdPa
         SD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
         configured = true;
     }
-    kernel<<<p.B, CNT, F_SMEM, st>>>(tmW, tmKV, p);
+    kernel<<<p.B * p.groups, CNT, F_SMEM, st>>>(tmW, tmKV, p);
     SD_LAUNCH_CHECK();
     return SD_OK;
 }
@@ -925,7 +955,10 @@ int launch_ca_bwd(const CUtensorMap& tmW, const CUtensorMap& tmKV, const CaBwdPa
 extern "C" int sd_ca_block_fwd(const sd_ca_block_desc* d, void* stream) {
     if (!d || !d->x || !d->y || !d->w_packed || !d->kv || !d->q_b || !d->out_b || !d->n_w || !d->n_b) return SD_ERR_BAD_ARG;
     if (d->B <= 0) return SD_OK;
-    if (!sd_ca_block_supported(128, 4, d->T, d->M)) return SD_ERR_UNSUPPORTED;
+    if (!sd_ca_block_fwd_supported(128, 4, d->T, d->M)) return SD_ERR_UNSUPPORTED;
+    // the backward kernel works on whole samples: saves are only produced for T <= 16
+    const bool saves = d->xn_save || d->q_save || d->attn_save || d->stats_save || d->lse_save;
+    if (saves && !sd_ca_block_supported(128, 4, d->T, d->M)) return SD_ERR_UNSUPPORTED;
     if (d->w_row_q < 0 || d->w_row_q + 128 > d->w_rows_total || d->w_row_o < 0 || d->w_row_o + 128 > d->w_rows_total) return SD_ERR_BAD_ARG;
     if (d->kv_col0 < 0 || d->kv_col0 + 256 > d->ldkv || d->kv_col0 % 8 != 0) return SD_ERR_BAD_ARG;
     if (!al16(d->x) || !al16(d->y) || !al16(d->xn_save) || !al16(d->q_save) || !al16(d->attn_save)) return SD_ERR_BAD_ARG;
@@ -934,6 +967,8 @@ extern "C" int sd_ca_block_fwd(const sd_ca_block_desc* d, void* stream) {
     if (!encode_bf16_2d(&tmKV, d->kv, (long long)d->B * d->M, d->ldkv, d->ldkv, 128)) return SD_ERR_UNSUPPORTED;
     CaFwdParams p{};
     p.x = d->x; p.y = d->y; p.B = d->B; p.T = d->T; p.M = d->M;
+    p.groups = (d->T + TP - 1) / TP;
+    p.Tg = (d->T + p.groups - 1) / p.groups;
     p.w_row_q = d->w_row_q; p.w_row_o = d->w_row_o; p.kv_col0 = d->kv_col0;
     p.q_b = d->q_b; p.out_b = d->out_b; p.n_w = d->n_w; p.n_b = d->n_b;
     p.xn_save = (__nv_bfloat16*)d->xn_save; p.q_save = (__nv_bfloat16*)d->q_save; p.attn_save = (__nv_bfloat16*)d->attn_save;

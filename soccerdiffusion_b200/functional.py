@@ -418,6 +418,53 @@ def _dec_layer_fused_bwd(dh, saved, mem2, dmem, B, T, Mm, H, P, G, wp, l, cfg: R
     return dx
 
 
+def tc_sampler_supported(d: int, H: int, T: int, Mm: int, L: int, ff: int) -> bool:
+    """The tensor-core batched sampler needs every block of the decoder layer on the fused kernels."""
+    return (L > 0 and L <= ops.KV_MAX_LAYERS and ops.enc_layer_supported(d, ff, T, H) and ops.ca_block_fwd_supported(d, H, T, Mm))
+
+
+def ddim_sample_tc(B: int, T: int, Mm: int, H: int, pe, x_T, mem, tok, emb_w, emb_b, fc_w, fc_b, layer_params, coefs, trace=None):
+    """The complete eta=0 DDIM loop (ros.py:301-310, distill.py:179-189) for a BATCH of trajectories on the layer-fused
+    tensor-core kernels, eval mode.  ``mem`` fp32 (B*Mm, d): the assembled context whose LAST row per trajectory is the step
+    token (its content is irrelevant here); ``tok`` fp32 (S, d): the step token of every scheduled timestep; ``coefs``:
+    per-step (sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev)).  The context's K | V of all layers are projected ONCE
+    (the reference re-projects them in each of the S*L cross-attention calls); per step only the step token's K | V row
+    changes: it comes from an (S, L*256) table computed by the same GEMM.  Returns x_0 (B, T, J) fp32."""
+    d, J = emb_w.shape
+    L = len(layer_params) // DEC_PARAMS_PER_LAYER
+    S = tok.shape[0]
+    cfg = RunCfg(precision=ops.PREC_BF16)
+    wp = _pack_dec_weights(layer_params, L, d)
+    biases = [_p(layer_params[l * DEC_PARAMS_PER_LAYER + 5], d) for l in range(L)]
+    mem_bf = _bf16((B * Mm, d), mem)
+    ops.cast_bf16(mem, mem_bf)
+    kv_all = _bf16((B * Mm, 256 * L), mem)
+    ops.kv_proj_bf16(mem_bf, wp, 640, ops.DEC_ROWS_PER_LAYER, biases, kv_all)
+    Sp = (S + 7) // 8 * 8   # sd_cast_bf16 works on multiples of 8 elements
+    tok_bf = torch.zeros((Sp, d), device=mem.device, dtype=torch.bfloat16)
+    tok_p = tok if Sp == S else torch.cat([tok, tok.new_zeros(Sp - S, d)])
+    ops.cast_bf16(tok_p.contiguous(), tok_bf)
+    kv_tok = _bf16((Sp, 256 * L), mem)
+    ops.kv_proj_bf16(tok_bf, wp, 640, ops.DEC_ROWS_PER_LAYER, biases, kv_tok)
+    Mq = B * T
+    x = x_T.contiguous().view(Mq, J).clone()
+    x_next = torch.empty_like(x)
+    h = _empty((Mq, d), mem)
+    eps = _empty((Mq, J), mem)
+    for s in range(S):
+        ops.bcast_row_bf16(kv_all, Mm, Mm - 1, B, kv_tok.data_ptr() + 2 * s * 256 * L, 256 * L)
+        ops.gemm(x, J, MK, emb_w, J, NK, h, d, Mq, d, J, precision=cfg.precision, bias=emb_b, pe=pe, pe_period=T)
+        for l in range(L):
+            P = layer_params[l * DEC_PARAMS_PER_LAYER: (l + 1) * DEC_PARAMS_PER_LAYER]
+            h, _ = _dec_layer_fused_fwd(h, None, B, T, Mm, H, P, wp, l, cfg, False, kv_all)
+        ops.gemm(h, d, MK, fc_w, d, NK, eps, J, Mq, J, d, precision=cfg.precision, bias=fc_b)
+        if trace is not None:
+            trace[s].view(Mq, J).copy_(eps)
+        ops.ddim_step(x, eps, x_next, None, coefs[s])
+        x, x_next = x_next, x
+    return x.view(B, T, J)
+
+
 class DenoiserFn(torch.autograd.Function):
     """Linear(J->d)+PE, L pre-LN decoder layers over memory, Linear(d->J) (decoder.py:47-54)."""
 

@@ -178,6 +178,7 @@ class End2EndDiffusionTransformer(nn.Module):
         self.register_buffer("std", torch.ones(num_joints))
 
         self._plans: dict[int, _Plan] = {}
+        self._tc_graphs: dict = {}   # tensor-core sampler: captured DDIM loops by input signature
 
     # ----------------------------------------------------------------------------------------
     def encode_input_data(self, input_data: dict[str, torch.Tensor]) -> list[torch.Tensor]:
@@ -346,13 +347,92 @@ class End2EndDiffusionTransformer(nn.Module):
         ops._count()
         return out
 
+    # ----------------------------------------------------------------------------------------
+    # tensor-core batched sampler (bf16 mode): the DDIM loop on the layer-fused kernels, replayed from one CUDA graph
+    def tc_sampler_supported(self, context_tokens: int, T: int) -> bool:
+        from soccerdiffusion_b200.functional import tc_sampler_supported
+
+        dag = self.diffusion_action_generator
+        layers = dag.transformer_decoder.layers
+        return tc_sampler_supported(self.hidden_dim, dag.num_heads, T, context_tokens + 1, len(layers),
+                                    layers[0].linear1.weight.shape[0] if len(layers) else 0)
+
+    def _sample_tc(self, context, x_T, scheduler, denormalize: bool, return_trace: bool, use_graph: bool = True):
+        from soccerdiffusion_b200.functional import ddim_sample_tc
+
+        B, T, J = x_T.shape
+        d = self.hidden_dim
+        dag = self.diffusion_action_generator
+        lens = tuple(int(c.shape[1]) for c in context)
+        Mm = sum(lens) + 1
+        ts, coef = scheduler.schedule_tables()
+        S = len(ts)
+        dev = x_T.device
+        key = (B, T, J, lens, tuple(ts), coef.tobytes(), bool(denormalize), bool(return_trace), dev.index)
+        ent = self._tc_graphs.get(key) if use_graph else None
+        tsd = torch.tensor(ts, device=dev, dtype=torch.int64) if ent is None else ent[4]
+
+        def run(ctx_list, x_in):
+            mem = torch.empty((B, Mm, d), device=dev, dtype=torch.float32)
+            off = 0
+            for c, n in zip(ctx_list, lens):
+                cc = c.float().contiguous()
+                ops.copy_rows(cc.data_ptr(), n * d, d, mem.data_ptr() + 4 * off * d, Mm * d, d, B, n, d)
+                off += n
+            ops.copy_rows(self.step_encoding.token.data_ptr(), 0, d, mem.data_ptr() + 4 * off * d, Mm * d, d, B, 1, d)  # placeholder row
+            tok = torch.empty((S, d), device=dev, dtype=torch.float32)
+            ops.step_token(tsd, self.step_encoding.freqs, self.step_encoding.token, tok, d, S, d)
+            trace = torch.empty((S, B, T, J), device=dev, dtype=torch.float32) if return_trace else None
+            x0 = ddim_sample_tc(B, T, Mm, dag.num_heads, dag.positional_encoding.table(T).contiguous(), x_in.float(),
+                                mem.view(B * Mm, d), tok, dag.embedding.weight, dag.embedding.bias, dag.fc_out.weight,
+                                dag.fc_out.bias, dag.transformer_decoder.tensors(), [tuple(map(float, c)) for c in coef], trace)
+            if denormalize:
+                out = torch.empty_like(x0)
+                ops.affine_joints(x0.contiguous(), self.mean.contiguous(), self.std.contiguous(), out, 1)
+                x0 = out
+            return x0, trace
+
+        if not use_graph or torch.cuda.is_current_stream_capturing():
+            x0, trace = run(context, x_T)   # kernel by kernel (inside a caller's capture: part of the caller's graph)
+            return (x0, trace) if return_trace else x0
+        if ent is None:
+            if len(self._tc_graphs) >= 4:
+                self._tc_graphs.pop(next(iter(self._tc_graphs)))
+            s_ctx = [torch.empty((B, n, d), device=dev, dtype=torch.float32) for n in lens]
+            s_x = torch.empty((B, T, J), device=dev, dtype=torch.float32)
+            for dst, c in zip(s_ctx, context):
+                dst.copy_(c)
+            s_x.copy_(x_T)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                run(s_ctx, s_x)   # warm-up outside the capture (lazy kernel attributes, allocator)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = run(s_ctx, s_x)
+            ent = self._tc_graphs[key] = (g, s_ctx, s_x, out, tsd)
+        g, s_ctx, s_x, (x0, trace), _ = ent
+        for dst, c in zip(s_ctx, context):
+            dst.copy_(c)
+        s_x.copy_(x_T)
+        g.replay()
+        x0 = x0.clone()
+        return (x0, trace.clone()) if return_trace else x0
+
     @torch.no_grad()
     def sample(self, context: list[torch.Tensor], x_T: torch.Tensor, scheduler, num_inference_steps: int | None = None,
                denormalize: bool = False, return_trace: bool = False, sampler: str = "auto"):
-        """Runs the complete DDIM loop of ros.py:301-310 / distill.py:179-189 in one persistent kernel.
+        """Runs the complete DDIM loop of ros.py:301-310 / distill.py:179-189.
 
         ``scheduler`` is a ``soccerdiffusion_b200.schedulers.DDIMScheduler`` whose ``set_timesteps`` has
         been called (or pass ``num_inference_steps``).  Returns x_0 (denormalised like ros.py:313 if asked).
+
+        ``sampler``: "cluster" / "cta" = the fp32 persistent kernels (one launch for the whole loop; 16-CTA cluster or one
+        CTA per trajectory), "tc" = the bf16 tensor-core path (layer-fused tcgen05 kernels over the whole batch, context
+        K | V projected once, the loop replayed from one CUDA graph), "auto" = "tc" in bf16 precision mode for batches
+        of ``runtime.tc_sampler_min_batch()`` trajectories or more when the shapes are supported, else the fp32 kernels.
         """
         _lib.require_cuda(x_T, *context)
         if self.training:
@@ -362,6 +442,26 @@ class End2EndDiffusionTransformer(nn.Module):
         B, T, J = x_T.shape
         if context[0].shape[0] != B:
             raise RuntimeError(f"batch size of the context ({context[0].shape[0]}) and of x_T ({B}) differ")
+        for c in context:
+            if c.shape[0] != B:
+                raise RuntimeError(f"context tensors disagree on the batch size: {[tuple(c.shape) for c in context]}")
+        if sampler not in ("auto", "cta", "cluster", "tc"):
+            raise ValueError(f"unknown sampler {sampler!r}")
+        from soccerdiffusion_b200 import runtime
+
+        use_tc = sampler == "tc"
+        n_layers = len(self.diffusion_action_generator.transformer_decoder.layers)
+        # measured on a B200 (tools/sampler_micro.py): one trajectory of the default architecture is fastest on the 16-CTA
+        # cluster kernel (3.4 ms vs 4.4 ms); batches, and deeper / longer decoders even at one trajectory (scaled-up
+        # config: 8.6 ms vs 15.9 ms), on the tensor-core path
+        if sampler == "auto" and runtime.get_precision() == ops.PREC_BF16 and (B >= runtime.tc_sampler_min_batch()
+                                                                               or n_layers * T >= 80):
+            use_tc = self.tc_sampler_supported(sum(c.shape[1] for c in context), T)
+        if use_tc:
+            if not self.tc_sampler_supported(sum(c.shape[1] for c in context), T):
+                raise _lib.SdError("sampler='tc': shapes outside the fused tensor-core kernels (d=128, 4 heads, T<=64, memory<=384)")
+            self.last_sampler = "tc"
+            return self._sample_tc(context, x_T, scheduler, denormalize, return_trace)
         plan = self._plan_for(sum(c.shape[1] for c in context), T)
         _lib.check(_lib.lib().sd_plan_set_sampler(plan.handle, {"auto": 0, "cta": 1, "cluster": 2}[sampler]),
                    "sd_plan_set_sampler")

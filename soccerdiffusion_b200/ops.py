@@ -508,11 +508,23 @@ def ca_block_supported(d: int, H: int, T: int, M: int) -> bool:
     return bool(_lib.lib().sd_ca_block_supported(d, H, T, M))
 
 
+def ca_block_fwd_supported(d: int, H: int, T: int, M: int) -> bool:
+    """forward without saves (inference): T <= 64"""
+    return bool(_lib.lib().sd_ca_block_fwd_supported(d, H, T, M))
+
+
 def cast_bf16(src: torch.Tensor, dst: torch.Tensor):
     """fp32 -> bf16 copy of a contiguous tensor (numel a multiple of 8)."""
     n = src.numel()
     with _Timed("cast_bf16", 0.0, 6.0 * n, f"[{n}]"):
         check(_lib.lib().sd_cast_bf16(_f32(src).data_ptr(), dst.data_ptr(), n, stream_ptr()), "sd_cast_bf16")
+    _count()
+
+
+def bcast_row_bf16(dst, block_rows: int, row: int, B: int, src_row_ptr: int, ncols: int):
+    """dst[b*block_rows + row, :ncols] = the bf16 row at ``src_row_ptr`` for every b < B (sd_bcast_row_bf16)."""
+    check(_lib.lib().sd_bcast_row_bf16(dst.data_ptr(), dst.shape[1], block_rows, row, B, src_row_ptr, ncols, stream_ptr()),
+          "sd_bcast_row_bf16")
     _count()
 
 

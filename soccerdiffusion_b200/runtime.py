@@ -85,6 +85,20 @@ def fused_layers() -> bool:
     return _fused_layers
 
 
+# model.sample(sampler="auto") in bf16 precision mode: batches of at least this many trajectories run the DDIM loop on the
+# layer-fused tensor-core kernels (ml/model/model.py:_sample_tc); smaller ones on the fp32 persistent kernels
+_tc_sampler_min_batch = int(os.environ.get("SD_B200_TC_SAMPLER_MIN_BATCH", "8"))
+
+
+def set_tc_sampler_min_batch(n: int):
+    global _tc_sampler_min_batch
+    _tc_sampler_min_batch = max(1, int(n))
+
+
+def tc_sampler_min_batch() -> int:
+    return _tc_sampler_min_batch
+
+
 _concurrent_encoders = os.environ.get("SD_B200_CONCURRENT_ENCODERS", "1") == "1"
 
 

@@ -205,3 +205,125 @@ def test_ca_block_bwd_matches_autograd_of_restatement(ops, B, T, M, p):
     ops.ca_block_bwd(dy2, dy2, x, q_s, attn_s, stats, lse, B, T, M, wp, 0, 3 * D, kv_all, col0, P["n_w"], None, None, dkv, None, None,
                      dropout=drop)
     assert torch.equal(dy2, dx)
+
+
+# ---- the tensor-core batched sampler (model.sample(sampler="tc")) ----------------------------------------------------------
+def test_tc_sampler_matches_reference_golden_default(manifest):
+    """bf16 mode, default.yaml: the final trajectory and the per-step predicted noise of the tensor-core DDIM loop against
+    the REAL reference's golden trace (north_star: bf16 mode within 2e-2)."""
+    import soccerdiffusion_b200 as sd
+    from conftest import load_golden
+    from oracle import synth
+    from soccerdiffusion_b200.schedulers import DDIMScheduler
+    from util_gpu import synth_model
+
+    c = manifest["cases"]["default"]
+    hp, B, seed, steps = synth.DEFAULT_HP, c["batch_size"], c["seed"], c["ddim_steps"]
+    g = load_golden("default")
+    model, sdict = synth_model(hp, seed)
+    model.eval()
+    ctx = [torch.from_numpy(g[k]).cuda() for k in sorted(k for k in g.files if k.startswith("ctx"))]
+    x_T = synth.synth_noise("x_T", hp, B, seed).cuda()
+    sch = DDIMScheduler(beta_schedule="squaredcos_cap_v2", clip_sample=False)
+    sch.config["num_train_timesteps"] = 1000
+    sch.set_timesteps(steps)
+    sd.set_precision("bf16")
+    try:
+        assert model.tc_sampler_supported(sum(t.shape[1] for t in ctx), x_T.shape[1])
+        x0, trace = model.sample(ctx, x_T, sch, return_trace=True, sampler="tc")
+        assert model.last_sampler == "tc"
+        assert rel(x0, g["ddim_x0"]) < TOL_BF16, rel(x0, g["ddim_x0"])
+        assert rel(trace, g["ddim_eps_trace"]) < TOL_BF16, rel(trace, g["ddim_eps_trace"])
+        # replay of the captured loop on new inputs == a fresh kernel-by-kernel run on them
+        x_T2 = synth.synth_noise("x_T", hp, B, seed + 1).cuda()
+        ctx2 = [t + 0.05 * torch.randn_like(t) for t in ctx]
+        a = model.sample(ctx2, x_T2, sch, sampler="tc")
+        b = model._sample_tc(ctx2, x_T2, sch, False, False, use_graph=False)
+        assert torch.equal(a, b)
+        assert not torch.equal(a, x0)
+        # denormalised output (ros.py:313)
+        xd = model.sample(ctx, x_T, sch, denormalize=True, sampler="tc")
+        assert rel(xd, g["ddim_x0"] * sdict["std"].numpy() + sdict["mean"].numpy()) < TOL_BF16
+        # "auto" picks the tensor-core path in bf16 mode for batches, the fp32 persistent kernels for one trajectory
+        from soccerdiffusion_b200 import runtime
+
+        n = runtime.tc_sampler_min_batch()
+        rep = lambda t: t.repeat((n + B - 1) // B, 1, 1)[:n].contiguous()
+        model.sample([rep(t) for t in ctx], rep(x_T), sch)
+        assert model.last_sampler == "tc"
+        model.sample([t[:1] for t in ctx], x_T[:1], sch)
+        assert model.last_sampler in ("cluster", "cta")
+    finally:
+        sd.set_precision("fp32")
+
+
+def test_tc_sampler_batch_70_matches_fp32_kernels():
+    """70 trajectories (6 self-attention tiles, the last one ragged) against the fp32 persistent sampler on the same inputs."""
+    import soccerdiffusion_b200 as sd
+    from oracle import synth
+    from soccerdiffusion_b200.schedulers import DDIMScheduler
+    from util_gpu import synth_model
+
+    hp = dict(synth.DEFAULT_HP)
+    B, d = 70, hp["hidden_dim"]
+    model, _ = synth_model(hp, 3)
+    model.eval()
+    gen = torch.Generator().manual_seed(11)
+    ctx = [torch.randn(B, n, d, generator=gen).cuda() for n in (100, 100, 100, 10, 1)]
+    x_T = torch.randn(B, hp["trajectory_prediction_length"], hp["num_joints"], generator=gen).cuda()
+    sch = DDIMScheduler(beta_schedule="squaredcos_cap_v2", clip_sample=False)
+    sch.set_timesteps(10)
+    want = model.sample(ctx, x_T, sch, sampler="cta")
+    sd.set_precision("bf16")
+    try:
+        got = model.sample(ctx, x_T, sch, sampler="tc")
+    finally:
+        sd.set_precision("fp32")
+    assert rel(got, want) < TOL_BF16, rel(got, want)
+
+
+@pytest.mark.parametrize("B,T,M,p", [(3, 20, 322, 0.0), (2, 33, 384, 0.0), (2, 64, 100, 0.0), (3, 17, 312, 0.1)])
+def test_ca_block_fwd_inference_row_groups(ops, B, T, M, p):
+    """T > 16 without saves (the scaled-up config's sampler, T = 20): the query rows run in groups of <= 16, one CTA each."""
+    assert ops.ca_block_fwd_supported(D, H, T, M) and not ops.ca_block_supported(D, H, T, M)
+    gen = torch.Generator().manual_seed(B * 1000 + T * 10 + M)
+    P = {k: v.cuda() for k, v in make_block(gen).items()}
+    x = torch.randn(B * T, D, generator=gen).cuda()
+    kv = torch.randn(B * M, 256, generator=gen).cuda().to(torch.bfloat16)
+    wp = pack(ops, P, 0, 4 * D)
+    seed, sid = 5, 20
+    m_attn = ops.dropout_mask(B * H * T * M, p, seed, sid, "cuda").view(B, H, T, M) if p > 0 else None
+    m_out = ops.dropout_mask(B * T * D, p, seed, sid + 1, "cuda").view(B * T, D) if p > 0 else None
+    want, _ = ca_ref(x, kv.float(), P, B, T, M, m_attn, m_out)
+    y, _ = run_fwd(ops, x, kv, 0, P, wp, 0, B, T, M, drop=(p, seed, sid) if p > 0 else None, save=False)
+    assert rel(y, want) < 6e-3, rel(y, want)
+    with pytest.raises(Exception):   # saves (training) need whole samples per CTA
+        run_fwd(ops, x, kv, 0, P, wp, 0, B, T, M, save=True)
+
+
+def test_tc_sampler_scaled_config_matches_fp32_kernels():
+    """BASELINE.json configs[4] architecture (8 decoder layers, T = 20, 322 memory tokens): tensor-core sampler vs the fp32
+    persistent kernels on the same inputs."""
+    import soccerdiffusion_b200 as sd
+    from soccerdiffusion_b200 import config
+    from soccerdiffusion_b200.schedulers import DDIMScheduler
+
+    hp = dict(config.SCALED)
+    B, d = 9, hp["hidden_dim"]
+    torch.manual_seed(5)
+    model = config.build_model(hp).cuda().eval()
+    gen = torch.Generator().manual_seed(12)
+    lens = (hp["action_context_length"], hp["imu_context_length"], hp["joint_state_context_length"], hp["image_context_length"], 1)
+    ctx = [torch.randn(B, n, d, generator=gen).cuda() for n in lens]
+    x_T = torch.randn(B, hp["trajectory_prediction_length"], hp["num_joints"], generator=gen).cuda()
+    sch = DDIMScheduler(beta_schedule="squaredcos_cap_v2", clip_sample=False)
+    sch.set_timesteps(30)
+    want = model.sample(ctx, x_T, sch, sampler="cta")
+    sd.set_precision("bf16")
+    try:
+        assert model.tc_sampler_supported(sum(lens), x_T.shape[1])
+        got = model.sample(ctx, x_T, sch)
+        assert model.last_sampler == "tc"
+    finally:
+        sd.set_precision("fp32")
+    assert rel(got, want) < TOL_BF16, rel(got, want)
