@@ -95,16 +95,27 @@ struct KvProjParams {
     __nv_bfloat16* C;
     long long ldc;
 };
-constexpr int KP_SMEM = 2 * LTILE + 2 * 4 * LTILE + 1024;   // A tile + two weight blocks of [256][128]
+constexpr int KP_NT = 256;                                          // two warpgroups: 128 rows x (2 column halves)
+constexpr int KP_SMEM = 2 * LTILE + 2 * 4 * LTILE + 4 * LTILE + 1024;   // A tile + two weight blocks of [256][128] + output staging
 
-__global__ void __launch_bounds__(CNT, 1) kv_proj_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                                                         const KvProjParams p) {
+// TMA tile store (shared -> global, SASS: UTMASTG); completion tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src_smem, int col0, int row0) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm), "r"(col0), "r"(row0),
+                 "r"(src_smem)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__global__ void __launch_bounds__(KP_NT, 1) kv_proj_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                                                           const __grid_constant__ CUtensorMap tmC, const KvProjParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_a, bar_b[2], bar_m[2];
     __shared__ uint32_t tmem_slot;
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, r = tid & 127;
     const long long row0 = (long long)blockIdx.x * 128;
     if (tid == 0) {
         mbar_init(&bar_a, 1);
@@ -113,22 +124,23 @@ __global__ void __launch_bounds__(CNT, 1) kv_proj_kernel(const __grid_constant__
         mbar_fence_init();
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmW);
+        tma_prefetch_desc(&tmC);
     }
     if (warp == 0) tmem_alloc(&tmem_slot, 512);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = tmem_slot;
-    const uint32_t OFF_B = 2 * LTILE;
+    const uint32_t OFF_B = 2 * LTILE, OFF_C = 10 * LTILE;
     // weight block j: 256 rows as two TMA boxes of 128 rows per 64-column half -> tiles [k half][row half]
     auto load_b = [&](int j) {
         const uint32_t dst = sbase + OFF_B + (j & 1) * 4 * LTILE;
-        const int r = p.w_row0 + j * p.w_stride;
+        const int wr = p.w_row0 + j * p.w_stride;
         mbar_arrive_expect_tx(&bar_b[j & 1], 4 * LTILE);
-        tma_tile_2d(dst, &tmW, 0, r, &bar_b[j & 1]);
-        tma_tile_2d(dst + LTILE, &tmW, 0, r + 128, &bar_b[j & 1]);
-        tma_tile_2d(dst + 2 * LTILE, &tmW, 64, r, &bar_b[j & 1]);
-        tma_tile_2d(dst + 3 * LTILE, &tmW, 64, r + 128, &bar_b[j & 1]);
+        tma_tile_2d(dst, &tmW, 0, wr, &bar_b[j & 1]);
+        tma_tile_2d(dst + LTILE, &tmW, 0, wr + 128, &bar_b[j & 1]);
+        tma_tile_2d(dst + 2 * LTILE, &tmW, 64, wr, &bar_b[j & 1]);
+        tma_tile_2d(dst + 3 * LTILE, &tmW, 64, wr + 128, &bar_b[j & 1]);
     };
     // [256 rows][64 k] as two consecutive [128][64] tiles: 8-row groups stay 1024 B apart across the tile boundary
     const uint32_t id256 = instr_desc_bf16(128, 256);
@@ -148,36 +160,44 @@ __global__ void __launch_bounds__(CNT, 1) kv_proj_kernel(const __grid_constant__
         issue(0);
     }
     __syncwarp();
-    const long long grow = row0 + tid;
-    const bool rv = grow < p.rows;
     for (int j = 0; j < p.nblk; ++j) {
-        if (tid == 0 && j + 1 < p.nblk) issue(j + 1);
-        __syncwarp();
+        if (tid == 0) {
+            if (j + 1 < p.nblk) issue(j + 1);
+            tma_store_wait_read();   // the previous block's stores have read the staging tiles
+        }
+        __syncthreads();
         mbar_wait(&bar_m[j & 1], (uint32_t)((j >> 1) & 1));
         tc_fence_after_sync();
         if (tid == 0 && j + 2 < p.nblk) load_b(j + 2);   // the MMAs that read slot j & 1 have completed
         __syncwarp();
         const float* bias = p.bias[j];
-        __nv_bfloat16* crow = p.C + grow * p.ldc + 256 * j;
+        // warpgroup wg: columns [128 wg, 128 wg + 128) of the block -> staging tiles 2 wg, 2 wg + 1 (row r = this thread's lane)
 #pragma unroll 1
-        for (int c0 = 0; c0 < 256; c0 += 32) {
+        for (int q = 0; q < 4; ++q) {
+            const int c0 = 128 * wg + 32 * q;
             float v[32], b[32];
             if (bias) ldg32(bias + c0, b);
-            ld_lane32(tmem, warp, (j & 1) * 256 + c0, v);
+            ld_lane32(tmem, warp & 3, (j & 1) * 256 + c0, v);
             if (bias) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] += b[i];
             }
-            if (rv) {
-                uint4* g = reinterpret_cast<uint4*>(crow + c0);
+            uint8_t* tile = smem + OFF_C + (2 * wg + (q >> 1)) * LTILE;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) g[i] = pack8_bf16(v + 8 * i);
-            }
+            for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(tile + sw128_chunk_off(r, 4 * (q & 1) + i)) = pack8_bf16(v + 8 * i);
         }
+        fence_proxy_async_smem();
         tc_fence_before_sync();
-        __syncthreads();   // accumulator j & 1 drained by every thread before block j + 2 is issued into it
+        __syncthreads();   // staging complete; accumulator j & 1 drained by every thread before block j + 2 is issued into it
         tc_fence_after_sync();
+        if (tid == 0) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) tma_store_2d(&tmC, sbase + OFF_C + t * LTILE, 256 * j + 64 * t, (int)row0);
+            tma_store_commit();
+        }
     }
+    if (tid == 0) tma_store_wait_all();
+    __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
@@ -885,9 +905,10 @@ extern "C" int sd_kv_proj_bf16(const void* mem_bf16, long long rows, const void*
     if (!mem_bf16 || !w_packed || !kv_out || n_layers < 1 || n_layers > SD_KV_MAX_LAYERS) return SD_ERR_BAD_ARG;
     if (ldkv < 256LL * n_layers || ldkv % 8 != 0 || !al16(kv_out)) return SD_ERR_BAD_ARG;
     if (w_row0 < 0 || w_row0 + (long long)(n_layers - 1) * w_stride + 256 > w_rows_total) return SD_ERR_BAD_ARG;
-    CUtensorMap tmA, tmW;
+    CUtensorMap tmA, tmW, tmC;
     if (!encode_bf16_2d(&tmA, mem_bf16, rows, 128, 128, 128)) return SD_ERR_UNSUPPORTED;
     if (!encode_bf16_2d(&tmW, w_packed, w_rows_total, 128, 128, 128)) return SD_ERR_UNSUPPORTED;
+    if (!encode_bf16_2d(&tmC, kv_out, rows, 256LL * n_layers, ldkv, 128)) return SD_ERR_UNSUPPORTED;   // stores clip at `rows`
     KvProjParams p{};
     p.rows = rows; p.nblk = n_layers; p.w_row0 = w_row0; p.w_stride = w_stride;
     for (int i = 0; i < n_layers; ++i) p.bias[i] = biases ? biases[i] : nullptr;
@@ -897,7 +918,7 @@ extern "C" int sd_kv_proj_bf16(const void* mem_bf16, long long rows, const void*
         SD_CUDA(cudaFuncSetAttribute(kv_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KP_SMEM));
         configured = true;
     }
-    kv_proj_kernel<<<ceil_div(rows, 128), CNT, KP_SMEM, (cudaStream_t)stream>>>(tmA, tmW, p);
+    kv_proj_kernel<<<ceil_div(rows, 128), KP_NT, KP_SMEM, (cudaStream_t)stream>>>(tmA, tmW, tmC, p);
     SD_LAUNCH_CHECK();
     return SD_OK;
 }

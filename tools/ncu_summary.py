@@ -46,7 +46,8 @@ def is_ours(k):
     return any(s in k for s in ("gemm_tc_kernel", "gemm_f32_kernel", "attn_", "ln_stats", "ln_bwd", "sampler", "adamw", "colsum",
                                 "q_sample", "ddim_step", "mse_", "copy_rows", "step_token", "gather_rows", "scatter_add",
                                 "dropout_", "affine_joints", "add_kernel", "kv_relayout", "transpose_kernel", "layer_", "bn_reduce",
-                                "bn_apply", "bn_bwd", "bn_finalize", "bn_param", "stem_", "maxpool_"))
+                                "bn_apply", "bn_bwd", "bn_finalize", "bn_param", "stem_", "maxpool_", "ca_fwd", "ca_bwd", "kv_proj", "kv_dgrad",
+                                "wgrad_tma", "pack_bf16", "cast_bf16", "bcast_row", "enc_layer"))
 
 
 WANT = ["launch__grid_size", "launch__block_size", "launch__registers_per_thread", "gpu__time_duration.sum",
