@@ -366,6 +366,20 @@ int sd_wgrad_bf16(const sd_wgrad_job* jobs, int n_jobs, long long rows, void* st
  *   mem bf16 [rows][128]; W = the packed bf16 weight matrix of sd_pack_weights_bf16; kv bf16 [rows][ldkv].
  * sd_kv_dgrad_bf16: dmem[row][n] (+)= sum_{l,k} dkv[row][256 l + k] * W[w_row0 + l*w_stride + k][n]   (fp32 [rows][lddmem]).
  * (The k/v weight gradients are sd_wgrad_bf16 jobs with G = dkv, X = the bf16 memory.) */
+/* Programmatic dependent launch for chains of short kernels (the tensor-core sampler's 16 launches per DDIM step):
+ * on != 0 -> sd_gemm (bf16 mode), sd_enc_layer_fwd, sd_ca_block_fwd, sd_bcast_row_bf16 and sd_ddim_step are launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization; each of them runs its prologue under the preceding kernel's tail and
+ * executes griddepcontrol.wait before touching activations.  Returns the previous setting. */
+int sd_set_pdl(int on);
+/* One launch between two denoiser evaluations of the batched DDIM loop (ros.py:301-310; decoder.py:48,54): output
+ * projection eps = h fc_w^T + fc_b (h fp32 [rows][128], fc_w [J][128]), the eta=0 update x_next = sap*(x - sb*eps)/sa + sbp*eps
+ * (optionally eps_out), the next step's embedding h_next = x_next emb_w^T + emb_b + pe[row % T] (emb_w [128][J]; NULL on
+ * the last step; h_next may alias h), and the broadcast of the next step token's K | V row (src_row NULL: none; arguments as
+ * sd_bcast_row_bf16).  J <= 32; fp32 arithmetic. */
+int sd_ddim_glue(const float* h, const float* fc_w, const float* fc_b, const float* x, float* x_next, float* eps_out, int rows,
+                 int J, float sqrt_beta_t, float sqrt_alpha_t, float sqrt_alpha_prev, float sqrt_beta_prev, const float* emb_w,
+                 const float* emb_b, const float* pe, int T, float* h_next, void* kv, long long ldkv, long long block_rows,
+                 long long row, int B, const void* src_row, int ncols, void* stream);
 #define SD_KV_MAX_LAYERS 16
 int sd_cast_bf16(const float* src, void* dst_bf16, long long n, void* stream);
 /* dst[(b*block_rows + row)*ld + c] = src_row[c] for b < B, c < ncols (bf16; the step token's K | V row of one DDIM step

@@ -181,6 +181,9 @@ SIGNATURES = {
     "sd_enc_layer_fwd": [C.POINTER(EncLayerDesc), c_f],
     "sd_enc_layer_bwd": [C.POINTER(EncLayerBwdDesc), c_f],
     "sd_wgrad_bf16": [C.POINTER(WgradJob), c_i, c_ll, c_f],
+    "sd_set_pdl": [c_i],
+    "sd_ddim_glue": [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_fl, c_fl, c_fl, c_fl, c_f, c_f, c_f, c_i, c_f, c_f, c_ll, c_ll, c_ll,
+                     c_i, c_f, c_i, c_f],
     "sd_cast_bf16": [c_f, c_f, c_ll, c_f],
     "sd_bcast_row_bf16": [c_f, c_ll, c_ll, c_ll, c_i, c_f, c_i, c_f],
     "sd_kv_proj_bf16": [c_f, c_ll, c_f, c_i, c_i, c_i, c_i, C.POINTER(c_f), c_f, c_ll, c_f],

@@ -117,6 +117,32 @@ static inline Dropout make_dropout(float p, uint64_t seed, uint32_t stream) {
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch (sd_set_pdl) ----------------------------------------------------------------------
+// Chains of short kernels (the tensor-core sampler: 16 launches per DDIM step): with the launch attribute set, kernel N+1
+// is scheduled as soon as every CTA of kernel N has executed pdl_trigger(), runs its prologue (barrier init, TMEM
+// allocation, tensor-map prefetch, weight TMA loads) under kernel N's tail, and blocks in pdl_wait() until kernel N has
+// completed and its writes are visible.  Rules kept by every kernel launched through launch_chain():
+//   * pdl_wait() precedes the first read of anything a preceding kernel of the chain may have written and every global
+//     write; only data produced by NON-triggering kernels (packed weights, biases, LayerNorm parameters) is read earlier
+//     (a non-triggering kernel releases its successor at completion, so nothing later in the stream starts before it ends);
+//   * without the attribute both instructions are no-ops.
+extern int g_pdl;   // defined in elementwise.cu
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 // stem_band.cu: row-band kernels for maxpool3x3s2(relu(bn(x))) with 64 channels (used by trunk_ops.cu's entry points)
 bool stem_band_supported(int H, int W, int C);
 int stem_band_fwd(const void* x, const float* mean, const float* invstd, const float* gamma, const float* beta, void* y,

@@ -81,9 +81,90 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, uint4* __restric
 __global__ void bcast_row_bf16_kernel(uint4* __restrict__ dst, long long ld8, long long block_rows, long long row, int B,
                                       const uint4* __restrict__ src, int n8) {
     const int b = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
     if (b >= B) return;
     uint4* d = dst + ((long long)b * block_rows + row) * ld8;
     for (int i = threadIdx.x; i < n8; i += blockDim.x) d[i] = src[i];
+}
+
+// =====================================================================================================================
+// Between two denoiser evaluations of the batched DDIM loop (ros.py:301-310): output projection of step s, the eta = 0
+// scheduler update, the embedding (+ positional encoding) of step s+1 and the broadcast of step s+1's step-token K | V row,
+// as ONE launch instead of four (the loop is a latency-bound chain of short kernels).  fp32 CUDA-core arithmetic: the two
+// projections have J = 20 columns / K = 20.
+//   eps = h fc_w^T + fc_b ;  x0 = (x - sb eps) / sa ;  x' = sap x0 + sbp eps ;  h' = x' emb_w^T + emb_b + PE
+constexpr int GL_ROWS = 8, GL_NT = 256, GL_JMAX = 32;
+struct GlueParams {
+    const float *h, *fc_w, *fc_b, *x;
+    float *x_next, *eps_out;
+    float sb, sa, sap, sbp;
+    const float *emb_w, *emb_b, *pe;   // emb_w == nullptr: last step, no next embedding
+    float* h_next;
+    int rows, J, T, row_blocks;
+    uint4* kv; long long ld8, block_rows, row; int B; const uint4* src; int n8;   // src == nullptr: no broadcast
+};
+__global__ void __launch_bounds__(GL_NT) ddim_glue_kernel(const GlueParams p) {
+    __shared__ float fcw[GL_JMAX][129];
+    __shared__ float embw[128][GL_JMAX + 1];
+    __shared__ float hs[GL_ROWS][128];
+    __shared__ float xs[GL_ROWS][GL_JMAX];
+    const int tid = threadIdx.x;
+    pdl_trigger();
+    if ((int)blockIdx.x >= p.row_blocks) {   // broadcast CTAs: one sample each
+        const int b = blockIdx.x - p.row_blocks;
+        pdl_wait();
+        if (p.src && b < p.B) {
+            uint4* d = p.kv + ((long long)b * p.block_rows + p.row) * p.ld8;
+            for (int i = tid; i < p.n8; i += GL_NT) d[i] = p.src[i];
+        }
+        return;
+    }
+    // parameters (never written inside the chain) before the wait
+    const int J = p.J;
+    for (int i = tid; i < J * 128; i += GL_NT) fcw[i >> 7][i & 127] = __ldg(p.fc_w + i);
+    if (p.emb_w)
+        for (int i = tid; i < 128 * J; i += GL_NT) embw[i / J][i % J] = __ldg(p.emb_w + i);
+    pdl_wait();
+    const int r0 = blockIdx.x * GL_ROWS;
+    for (int i = tid; i < GL_ROWS * 128; i += GL_NT) {
+        const int r = r0 + (i >> 7);
+        hs[i >> 7][i & 127] = r < p.rows ? p.h[(long long)r * 128 + (i & 127)] : 0.f;
+    }
+    __syncthreads();
+    {
+        const int r = tid >> 5, j = tid & 31, gr = r0 + r;
+        if (j < J && gr < p.rows) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+            for (int k = 0; k < 128; k += 4) {
+                a0 = fmaf(hs[r][k], fcw[j][k], a0); a1 = fmaf(hs[r][k + 1], fcw[j][k + 1], a1);
+                a2 = fmaf(hs[r][k + 2], fcw[j][k + 2], a2); a3 = fmaf(hs[r][k + 3], fcw[j][k + 3], a3);
+            }
+            const float e = (a0 + a1) + (a2 + a3) + __ldg(p.fc_b + j);
+            const long long idx = (long long)gr * J + j;
+            const float x0 = (p.x[idx] - p.sb * e) / p.sa;
+            const float xn = p.sap * x0 + p.sbp * e;
+            if (p.eps_out) p.eps_out[idx] = e;
+            p.x_next[idx] = xn;
+            xs[r][j] = xn;
+        }
+    }
+    if (!p.emb_w) return;
+    __syncthreads();
+    {
+        const int n = tid & 127;
+        const float eb = __ldg(p.emb_b + n);
+#pragma unroll
+        for (int i = 0; i < GL_ROWS / 2; ++i) {
+            const int r = (tid >> 7) + 2 * i, gr = r0 + r;
+            if (gr < p.rows) {
+                float a = eb + __ldg(p.pe + (long long)(gr % p.T) * 128 + n);
+                for (int j = 0; j < J; ++j) a = fmaf(xs[r][j], embw[n][j], a);
+                p.h_next[(long long)gr * 128 + n] = a;
+            }
+        }
+    }
 }
 
 // =====================================================================================================================
@@ -350,12 +431,13 @@ __global__ void __launch_bounds__(CNT, 1) ca_fwd_kernel(const __grid_constant__ 
         tma_tile_2d(sbase + F_OFF_KV + 2 * j * LTILE, &tmKV, col, (int)(krow0 + 128 * j), &bar[bi + j]);
         tma_tile_2d(sbase + F_OFF_KV + (2 * j + 1) * LTILE, &tmKV, col + 64, (int)(krow0 + 128 * j), &bar[bi + j]);
     };
-    if (tid == 0) {
-        load_w(p.w_row_q, FB_WQ);
-        for (int j = 0; j < nch; ++j) load_kv(j, p.kv_col0, FB_K0);
-    }
+    if (tid == 0) load_w(p.w_row_q, FB_WQ);   // packed weights: written by a non-triggering kernel
     // Qblk starts as zeros (the off-diagonal blocks stay zero)
     for (int i = tid; i < LTILE / 16; i += CNT) reinterpret_cast<uint4*>(smem + F_OFF_QB)[i] = make_uint4(0u, 0u, 0u, 0u);
+    pdl_trigger();
+    pdl_wait();   // K | V and the residual stream come from preceding kernels of the chain
+    if (tid == 0)
+        for (int j = 0; j < nch; ++j) load_kv(j, p.kv_col0, FB_K0);
     const uint64_t dseed = DROP ? p.drop.resolve() : 0ull;
 
     // ---- LN2 of the T rows (warp per row, lane = 4 features) -> B operand [t][k] ------------------------------------------
@@ -881,9 +963,29 @@ extern "C" int sd_bcast_row_bf16(void* dst, long long ld, long long block_rows, 
     if (B <= 0 || ncols <= 0) return SD_OK;
     if (!dst || !src_row || ld % 8 != 0 || ncols % 8 != 0 || ncols > ld || row < 0 || row >= block_rows || !al16(dst) || !al16(src_row))
         return SD_ERR_BAD_ARG;
-    bcast_row_bf16_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint4*>(dst), ld / 8, block_rows, row, B,
-                                                                reinterpret_cast<const uint4*>(src_row), ncols / 8);
-    SD_LAUNCH_CHECK();
+    SD_CUDA(launch_chain(bcast_row_bf16_kernel, dim3(B), dim3(128), 0, (cudaStream_t)stream, reinterpret_cast<uint4*>(dst), ld / 8,
+                         block_rows, row, B, reinterpret_cast<const uint4*>(src_row), ncols / 8));
+    return SD_OK;
+}
+
+extern "C" int sd_ddim_glue(const float* h, const float* fc_w, const float* fc_b, const float* x, float* x_next, float* eps_out,
+                            int rows, int J, float sqrt_beta_t, float sqrt_alpha_t, float sqrt_alpha_prev, float sqrt_beta_prev,
+                            const float* emb_w, const float* emb_b, const float* pe, int T, float* h_next, void* kv, long long ldkv,
+                            long long block_rows, long long row, int B, const void* src_row, int ncols, void* stream) {
+    if (rows <= 0) return SD_OK;
+    if (!h || !fc_w || !fc_b || !x || !x_next || J < 1 || J > GL_JMAX) return SD_ERR_BAD_ARG;
+    if (emb_w && (!emb_b || !pe || !h_next || T < 1)) return SD_ERR_BAD_ARG;
+    if (src_row && (!kv || ldkv % 8 != 0 || ncols % 8 != 0 || ncols > ldkv || row < 0 || row >= block_rows || B < 1 || !al16(kv) ||
+                    !al16(src_row)))
+        return SD_ERR_BAD_ARG;
+    GlueParams p{};
+    p.h = h; p.fc_w = fc_w; p.fc_b = fc_b; p.x = x; p.x_next = x_next; p.eps_out = eps_out;
+    p.sb = sqrt_beta_t; p.sa = sqrt_alpha_t; p.sap = sqrt_alpha_prev; p.sbp = sqrt_beta_prev;
+    p.emb_w = emb_w; p.emb_b = emb_b; p.pe = pe; p.h_next = h_next;
+    p.rows = rows; p.J = J; p.T = T; p.row_blocks = ceil_div(rows, GL_ROWS);
+    p.kv = reinterpret_cast<uint4*>(kv); p.ld8 = ldkv / 8; p.block_rows = block_rows; p.row = row; p.B = src_row ? B : 0;
+    p.src = reinterpret_cast<const uint4*>(src_row); p.n8 = ncols / 8;
+    SD_CUDA(launch_chain(ddim_glue_kernel, dim3(p.row_blocks + p.B), dim3(GL_NT), 0, (cudaStream_t)stream, p));
     return SD_OK;
 }
 
@@ -955,8 +1057,7 @@ int launch_ca_fwd(const CUtensorMap& tmW, const CUtensorMap& tmKV, const CaFwdPa
         SD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
         configured = true;
     }
-    kernel<<<p.B * p.groups, CNT, F_SMEM, st>>>(tmW, tmKV, p);
-    SD_LAUNCH_CHECK();
+    SD_CUDA(launch_chain(kernel, dim3(p.B * p.groups), dim3(CNT), F_SMEM, st, tmW, tmKV, p));
     return SD_OK;
 }
 template <bool DROP>

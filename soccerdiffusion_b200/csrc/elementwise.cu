@@ -108,6 +108,8 @@ extern "C" int sd_q_sample(const float* joint_command, const float* mean, const 
 //   x0_hat = (x - sb*eps)/sa ; prev = sap*x0_hat + sbp*eps
 __global__ void ddim_step_kernel(const float* __restrict__ x, const float* __restrict__ eps, float* __restrict__ prev,
                                  float* __restrict__ x0, long long n, float sb, float sa, float sap, float sbp) {
+    pdl_trigger();
+    pdl_wait();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float e = eps[i];
         const float p0 = (x[i] - sb * e) / sa;
@@ -121,9 +123,8 @@ extern "C" int sd_ddim_step(const float* x, const float* eps, float* prev, float
     if (!x || !eps || !prev) return SD_ERR_BAD_ARG;
     const int threads = 256;
     const int blocks = min(ceil_div(n, threads), 148 * 8);
-    ddim_step_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(x, eps, prev, x0_pred, n, sqrt_beta_t, sqrt_alpha_t,
-                                                                  sqrt_alpha_prev, sqrt_beta_prev);
-    SD_LAUNCH_CHECK();
+    SD_CUDA(launch_chain(ddim_step_kernel, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, x, eps, prev, x0_pred, n, sqrt_beta_t,
+                         sqrt_alpha_t, sqrt_alpha_prev, sqrt_beta_prev));
     return SD_OK;
 }
 
@@ -386,7 +387,7 @@ extern "C" int sd_dropout_mask(float* out, long long n, float p, unsigned long l
 }
 
 // ------------------------------------------------------------------------------------------
-namespace sd { const unsigned long long* g_dropout_seed_dev = nullptr; }
+namespace sd { const unsigned long long* g_dropout_seed_dev = nullptr; int g_pdl = 0; }
 
 extern "C" int sd_set_dropout_seed_offset(const unsigned long long* device_counter) {
     sd::g_dropout_seed_dev = device_counter;
@@ -484,4 +485,11 @@ extern "C" int sd_dropout_apply(const float* x, float* y, long long n, float p, 
     dropout_apply_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, y, n, make_dropout(p, seed, stream_id));
     SD_LAUNCH_CHECK();
     return SD_OK;
+}
+
+// programmatic dependent launch for the kernels launched through launch_chain() (common.cuh); returns the previous setting
+extern "C" int sd_set_pdl(int on) {
+    const int prev = sd::g_pdl;
+    sd::g_pdl = on ? 1 : 0;
+    return prev;
 }

@@ -216,11 +216,13 @@ __global__ void __launch_bounds__(NT) gemm_tc_kernel(const TcParams p) {
         mbar_init(&bar_done, 1);
         mbar_fence_init();
     }
+    pdl_trigger();
     if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = tmem_slot;
+    pdl_wait();   // every operand may come from the preceding kernel
 
     const int m0 = blockIdx.y * TM, n0 = blockIdx.x * BN;
     const int kb = blockIdx.z * p.k_per_slice;
@@ -434,8 +436,7 @@ int launch_impl(dim3 grid, size_t smem, cudaStream_t st, const TcParams& p) {
                                      STAGES * (A_STAGE_BYTES + 256 * TK * 2) + 1024));
         configured = true;
     }
-    kernel<<<grid, NT, smem, st>>>(p);
-    SD_LAUNCH_CHECK();
+    SD_CUDA(launch_chain(kernel, grid, dim3(NT), smem, st, p));
     return SD_OK;
 }
 

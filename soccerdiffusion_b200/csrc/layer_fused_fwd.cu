@@ -89,8 +89,10 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
         tma_tile_2d(dst + LTILE, &tmW, 64, row, &bar[BW0 + mi]);
     };
     if (tid == 0) {
-        if (SA) { load_w(0); load_w(1); } else { load_w(4); load_w(5); }
+        if (SA) { load_w(0); load_w(1); } else { load_w(4); load_w(5); }   // packed weights: written by a non-triggering kernel
     }
+    pdl_trigger();
+    pdl_wait();   // the residual stream below comes from the preceding kernel of the chain
 
     const int S = p.S, H = p.H, dh = p.dh;
     const int samp0 = blockIdx.x * p.spt;
@@ -421,8 +423,7 @@ int launch_fwd(const CUtensorMap& tmW, const EncFwdParams& p, int tiles, cudaStr
         SD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
         configured = true;
     }
-    kernel<<<tiles, LNT, SMEM_DYN, st>>>(tmW, p);
-    SD_LAUNCH_CHECK();
+    SD_CUDA(launch_chain(kernel, dim3(tiles), dim3(LNT), SMEM_DYN, st, tmW, p));
     return SD_OK;
 }
 }  // namespace

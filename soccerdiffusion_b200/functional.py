@@ -451,17 +451,33 @@ def ddim_sample_tc(B: int, T: int, Mm: int, H: int, pe, x_T, mem, tok, emb_w, em
     x_next = torch.empty_like(x)
     h = _empty((Mq, d), mem)
     eps = _empty((Mq, J), mem)
-    for s in range(S):
-        ops.bcast_row_bf16(kv_all, Mm, Mm - 1, B, kv_tok.data_ptr() + 2 * s * 256 * L, 256 * L)
-        ops.gemm(x, J, MK, emb_w, J, NK, h, d, Mq, d, J, precision=cfg.precision, bias=emb_b, pe=pe, pe_period=T)
-        for l in range(L):
-            P = layer_params[l * DEC_PARAMS_PER_LAYER: (l + 1) * DEC_PARAMS_PER_LAYER]
-            h, _ = _dec_layer_fused_fwd(h, None, B, T, Mm, H, P, wp, l, cfg, False, kv_all)
-        ops.gemm(h, d, MK, fc_w, d, NK, eps, J, Mq, J, d, precision=cfg.precision, bias=fc_b)
-        if trace is not None:
-            trace[s].view(Mq, J).copy_(eps)
-        ops.ddim_step(x, eps, x_next, None, coefs[s])
-        x, x_next = x_next, x
+    from . import runtime
+
+    # the loop is a chain of 16 short kernels per step: programmatic dependent launch lets each one run its prologue
+    # (barriers, TMEM allocation, weight TMA loads) under its predecessor's tail
+    pdl_before = ops.set_pdl(runtime.pdl_enabled())
+    glue = J <= ops.DDIM_GLUE_MAX_J   # output projection + scheduler update + next embedding + K | V row broadcast in one launch
+    try:
+        for s in range(S):
+            if s == 0 or not glue:
+                ops.bcast_row_bf16(kv_all, Mm, Mm - 1, B, kv_tok.data_ptr() + 2 * s * 256 * L, 256 * L)
+                ops.gemm(x, J, MK, emb_w, J, NK, h, d, Mq, d, J, precision=cfg.precision, bias=emb_b, pe=pe, pe_period=T)
+            for l in range(L):
+                P = layer_params[l * DEC_PARAMS_PER_LAYER: (l + 1) * DEC_PARAMS_PER_LAYER]
+                h, _ = _dec_layer_fused_fwd(h, None, B, T, Mm, H, P, wp, l, cfg, False, kv_all)
+            if glue:
+                last = s + 1 == S
+                ops.ddim_glue(h, fc_w, fc_b, x, x_next, None if trace is None else trace[s], coefs[s],
+                              emb=None if last else (emb_w, emb_b, pe, T),
+                              kv_bcast=None if last else (kv_all, Mm, Mm - 1, B, kv_tok.data_ptr() + 2 * (s + 1) * 256 * L, 256 * L))
+            else:
+                ops.gemm(h, d, MK, fc_w, d, NK, eps, J, Mq, J, d, precision=cfg.precision, bias=fc_b)
+                if trace is not None:
+                    trace[s].view(Mq, J).copy_(eps)
+                ops.ddim_step(x, eps, x_next, None, coefs[s])
+            x, x_next = x_next, x
+    finally:
+        ops.set_pdl(pdl_before)
     return x.view(B, T, J)
 
 

@@ -504,6 +504,11 @@ def wgrad_bf16(jobs, rows: int):
 
 
 # ---- layer-fused cross-attention block (csrc/cross_attn.cu) --------------------------------------------------------
+def set_pdl(on: bool) -> bool:
+    """Programmatic dependent launch for the kernel chains (sd_set_pdl); returns the previous setting."""
+    return bool(_lib.lib().sd_set_pdl(1 if on else 0))
+
+
 def ca_block_supported(d: int, H: int, T: int, M: int) -> bool:
     return bool(_lib.lib().sd_ca_block_supported(d, H, T, M))
 
@@ -525,6 +530,23 @@ def bcast_row_bf16(dst, block_rows: int, row: int, B: int, src_row_ptr: int, nco
     """dst[b*block_rows + row, :ncols] = the bf16 row at ``src_row_ptr`` for every b < B (sd_bcast_row_bf16)."""
     check(_lib.lib().sd_bcast_row_bf16(dst.data_ptr(), dst.shape[1], block_rows, row, B, src_row_ptr, ncols, stream_ptr()),
           "sd_bcast_row_bf16")
+    _count()
+
+
+DDIM_GLUE_MAX_J = 32
+
+
+def ddim_glue(h, fc_w, fc_b, x, x_next, eps_out, coef, emb=None, kv_bcast=None):
+    """sd_ddim_glue: eps = h fc_w^T + fc_b; x_next = DDIM(x, eps); optionally h <- embedding(x_next) + PE (``emb`` = (emb_w, emb_b,
+    pe, T)) and the next step token's K | V row into every trajectory (``kv_bcast`` = (kv, block_rows, row, B, src_ptr, ncols))."""
+    rows, J = x.shape
+    sb, sa, sap, sbp = coef
+    ew, eb, pe, T = emb if emb is not None else (None, None, None, 0)
+    kv, block_rows, row, B, src, ncols = kv_bcast if kv_bcast is not None else (None, 0, 0, 0, None, 0)
+    check(_lib.lib().sd_ddim_glue(h.data_ptr(), fc_w.data_ptr(), fc_b.data_ptr(), x.data_ptr(), x_next.data_ptr(), _dp(eps_out), rows, J,
+                                  sb, sa, sap, sbp, _dp(ew), _dp(eb), _dp(pe), T, h.data_ptr() if emb is not None else None,
+                                  _dp(kv), kv.shape[1] if kv is not None else 0, block_rows, row, B, src, ncols, stream_ptr()),
+          "sd_ddim_glue")
     _count()
 
 

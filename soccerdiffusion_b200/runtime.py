@@ -99,6 +99,19 @@ def tc_sampler_min_batch() -> int:
     return _tc_sampler_min_batch
 
 
+# programmatic dependent launch inside the tensor-core sampler's kernel chain (functional.ddim_sample_tc)
+_pdl = os.environ.get("SD_B200_PDL", "1") == "1"
+
+
+def set_pdl(on: bool):
+    global _pdl
+    _pdl = bool(on)
+
+
+def pdl_enabled() -> bool:
+    return _pdl
+
+
 _concurrent_encoders = os.environ.get("SD_B200_CONCURRENT_ENCODERS", "1") == "1"
 
 

@@ -327,3 +327,32 @@ def test_tc_sampler_scaled_config_matches_fp32_kernels():
     finally:
         sd.set_precision("fp32")
     assert rel(got, want) < TOL_BF16, rel(got, want)
+
+
+@pytest.mark.parametrize("B,T,J,last", [(3, 10, 20, False), (5, 7, 32, False), (2, 10, 20, True), (70, 10, 20, False)])
+def test_ddim_glue_matches_separate_ops(ops, B, T, J, last):
+    """fc_out + eta=0 DDIM update + next embedding (+ PE) + step-token K | V broadcast in one launch == the fp32 formulas."""
+    gen = torch.Generator().manual_seed(B + T + J)
+    r = lambda *s: torch.randn(*s, generator=gen).cuda()
+    rows, L, Mm = B * T, 2, 9
+    h, x = r(rows, D), r(rows, J)
+    fc_w, fc_b, emb_w, emb_b, pe = r(J, D) / math.sqrt(D), 0.1 * r(J), r(D, J) / math.sqrt(J), 0.1 * r(D), 0.1 * r(T, D)
+    coef = (0.6, 0.8, 0.9, 0.43588989)
+    eps_want = h @ fc_w.T + fc_b
+    x0 = (x - coef[0] * eps_want) / coef[1]
+    xn_want = coef[2] * x0 + coef[3] * eps_want
+    h_want = xn_want @ emb_w.T + emb_b + pe.repeat(B, 1)
+    kv = torch.zeros(B * Mm, 256 * L, device="cuda", dtype=torch.bfloat16)
+    src = r(2, 256 * L).to(torch.bfloat16)
+    x_next, eps = torch.full_like(x, float("nan")), torch.full_like(x, float("nan"))
+    hh = h.clone()
+    ops.ddim_glue(hh, fc_w, fc_b, x, x_next, eps, coef, emb=None if last else (emb_w, emb_b, pe, T),
+                  kv_bcast=None if last else (kv, Mm, Mm - 1, B, src.data_ptr() + 2 * 256 * L, 256 * L))
+    torch.cuda.synchronize()
+    assert rel(eps, eps_want) < 1e-5 and rel(x_next, xn_want) < 1e-5
+    if last:
+        assert torch.equal(hh, h) and not kv.any()
+    else:
+        assert rel(hh, h_want) < 1e-5
+        got = kv.view(B, Mm, -1)
+        assert torch.equal(got[:, Mm - 1], src[1].expand(B, -1)) and not got[:, :Mm - 1].any()
