@@ -391,6 +391,14 @@ int sd_kv_proj_bf16(const void* mem_bf16, long long rows, const void* w_packed, 
 int sd_kv_dgrad_bf16(const void* dkv_bf16, long long rows, long long lddkv, const void* w_packed, int w_rows_total, int w_row0,
                      int w_stride, int n_layers, float* dmem, long long lddmem, int accumulate, void* stream);
 
+/* Data gradient of a 1x1, stride-2, padding-0 convolution (the downsample path of a ResNet stage, torchvision resnet.py
+ * `downsample = conv1x1(inplanes, planes, stride)`; ml/model/encoder/image.py:55-73): dx[n][2ho][2wo][ci] = sum_co dy[n][ho][wo][co]
+ * * w[co][ci], zero at the pixels the stride skips.  dy bf16 NHWC [frames][Hin/2][Win/2][Cout], w bf16 [Cout][Cin], dx bf16 NHWC
+ * [frames][Hin][Win][Cin]; Hin, Win even, Cin in {64,128,256}, Cout a multiple of 64.  TMA-fed tcgen05 GEMM. */
+int sd_conv1x1s2_dgrad_supported(int Hin, int Win, int Cin, int Cout);
+int sd_conv1x1s2_dgrad_bf16(const void* dy, const void* w_bf16, void* dx, int frames, int Hin, int Win, int Cin, int Cout,
+                            void* stream);
+
 /* y = x + Drop(OutProj(MHA(LN(x), kv))) for B samples of T query rows; one CTA per sample.  x, y fp32 [B*T][128] (may
  * alias).  kv: bf16 [B*M][ldkv], this layer's K at columns [kv_col0, kv_col0+128), V at [kv_col0+128, kv_col0+256).
  * Dropout streams: dropout_stream + 0 (attention probabilities, element ((b*4+h)*T+t)*M+m), + 1 (out-proj, row*128+c).

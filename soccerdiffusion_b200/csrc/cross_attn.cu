@@ -283,20 +283,23 @@ __global__ void __launch_bounds__(KP_NT, 1) kv_proj_kernel(const __grid_constant
 }
 
 // =====================================================================================================================
-// dmem[row][n] (+)= sum_k dKV[row][k] W[k][n],  k = 256 j + kk -> packed weight row w_row0 + j w_stride + kk
-struct KvDgradParams {
+// C[row][n] (+)= sum_k A[row][k] W[k][n]: A bf16 [rows][K] K-major by TMA, W bf16 [K][N] used MN-major straight from its
+// row-major matrix ([64 k][64 n] TMA boxes), N = 64 / 128 / 256, 4-stage TMA ring, warp-specialised producer / MMA issuer.
+//   * sd_kv_dgrad_bf16: dmem = dKV_all x W_all (k tile i -> packed weight row w_row0 + (i / 4) * w_stride + (i % 4) * 64), fp32 out;
+//   * sd_conv1x1s2_dgrad_bf16: data gradient of a 1x1 stride-2 convolution (the ResNet downsample path): row p = output pixel
+//     (n, ho, wo), result written as the bf16 NHWC input pixel (n, 2 ho, 2 wo); the other pixels are zeroed beforehand.
+struct MnGemmParams {
     long long rows;
-    int nblk, w_row0, w_stride;
-    float* C;
-    long long ldc;
-    int accumulate;
+    int ktiles, N;
+    int w_row0, w_stride, tiles_per_blk;
+    float* Cf; long long ldc; int accumulate;
+    __nv_bfloat16* Cb; int Ho, Wo, Hin, Win;
 };
 constexpr int KD_STAGES = 4;
-constexpr int KD_STAGE = 2 * LTILE;   // A [128 rows][64 k] + W [64 k][128 n] (two [64][64] boxes)
-constexpr int KD_SMEM = KD_STAGES * KD_STAGE + 1024;
+inline int kd_stage_bytes(int N) { return LTILE + N * 128; }   // A [128 rows][64 k] + W [64 k][N]
 
-__global__ void __launch_bounds__(CNT, 1) kv_dgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                                                          const KvDgradParams p) {
+__global__ void __launch_bounds__(CNT, 1) mn_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                                                         const MnGemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[KD_STAGES], bar_empty[KD_STAGES], bar_done;
     __shared__ uint32_t tmem_slot;
@@ -304,6 +307,7 @@ __global__ void __launch_bounds__(CNT, 1) kv_dgrad_kernel(const __grid_constant_
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long row0 = (long long)blockIdx.x * 128;
+    const int N = p.N, stage = LTILE + N * 128;
     if (tid == 0) {
         for (int s = 0; s < KD_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
         mbar_init(&bar_done, 1);
@@ -311,30 +315,29 @@ __global__ void __launch_bounds__(CNT, 1) kv_dgrad_kernel(const __grid_constant_
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmW);
     }
-    if (warp == 0) tmem_alloc(&tmem_slot, 128);
+    if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)N);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = tmem_slot;
-    const int nk = p.nblk * 4;   // k tiles of 64
+    const int nk = p.ktiles;
     if (warp == 0 && lane == 0) {          // TMA producer
         for (int i = 0; i < nk; ++i) {
             const int s = i % KD_STAGES;
             mbar_wait(&bar_empty[s], (uint32_t)(((i / KD_STAGES) & 1) ^ 1));
-            const uint32_t dst = sbase + s * KD_STAGE;
-            const int wrow = p.w_row0 + (i >> 2) * p.w_stride + (i & 3) * 64;
-            mbar_arrive_expect_tx(&bar_full[s], KD_STAGE);
+            const uint32_t dst = sbase + s * stage;
+            const int wrow = p.w_row0 + (i / p.tiles_per_blk) * p.w_stride + (i % p.tiles_per_blk) * 64;
+            mbar_arrive_expect_tx(&bar_full[s], (uint32_t)stage);
             tma_tile_2d(dst, &tmA, 64 * i, (int)row0, &bar_full[s]);
-            tma_tile_2d(dst + LTILE, &tmW, 0, wrow, &bar_full[s]);
-            tma_tile_2d(dst + LTILE + LTILE / 2, &tmW, 64, wrow, &bar_full[s]);
+            for (int nb = 0; nb < N / 64; ++nb) tma_tile_2d(dst + LTILE + nb * (LTILE / 2), &tmW, 64 * nb, wrow, &bar_full[s]);
         }
-    } else if (warp == 1 && lane == 0) {   // MMA issuer: A K-major, B MN-major ([64 k rows][64 n] x 2 blocks 8 KB apart)
-        const uint32_t idesc = instr_desc_bf16(128, 128, 0, 1);
+    } else if (warp == 1 && lane == 0) {   // MMA issuer: A K-major, B MN-major ([64 k rows][64 n] blocks 8 KB apart)
+        const uint32_t idesc = instr_desc_bf16(128, N, 0, 1);
         for (int i = 0; i < nk; ++i) {
             const int s = i % KD_STAGES;
             mbar_wait(&bar_full[s], (uint32_t)((i / KD_STAGES) & 1));
             tc_fence_after_sync();
-            mma_a_k_b_mn(tmem, sbase + s * KD_STAGE, 0, sbase + s * KD_STAGE + LTILE, LTILE / 2, idesc, 4, i > 0);
+            mma_a_k_b_mn(tmem, sbase + s * stage, 0, sbase + s * stage + LTILE, LTILE / 2, idesc, 4, i > 0);
             mma_commit(&bar_empty[s]);
         }
         mma_commit(&bar_done);
@@ -344,24 +347,44 @@ __global__ void __launch_bounds__(CNT, 1) kv_dgrad_kernel(const __grid_constant_
     tc_fence_after_sync();
     const long long grow = row0 + tid;
     const bool rv = grow < p.rows;
-    float* crow = p.C + grow * p.ldc;
-#pragma unroll 1
-    for (int c0 = 0; c0 < 128; c0 += 32) {
-        float v[32];
-        ld_lane32(tmem, warp, c0, v);   // warp-collective: every lane takes part
+    if (p.Cb) {
+        __nv_bfloat16* dst = nullptr;
         if (rv) {
-            float4* g = reinterpret_cast<float4*>(crow + c0);
+            const long long hw = (long long)p.Ho * p.Wo;
+            const long long n = grow / hw;
+            const int rem = (int)(grow - n * hw), ho = rem / p.Wo, wo = rem - ho * p.Wo;
+            dst = p.Cb + ((n * p.Hin + 2 * ho) * p.Win + 2 * wo) * N;
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < N; c0 += 32) {
+            float v[32];
+            ld_lane32(tmem, warp, c0, v);   // warp-collective: every lane takes part
+            if (rv) {
+                uint4* g = reinterpret_cast<uint4*>(dst + c0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                if (p.accumulate) { const float4 t = g[i]; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-                g[i] = o;
+                for (int i = 0; i < 4; ++i) g[i] = pack8_bf16(v + 8 * i);
+            }
+        }
+    } else {
+        float* crow = p.Cf + grow * p.ldc;
+#pragma unroll 1
+        for (int c0 = 0; c0 < N; c0 += 32) {
+            float v[32];
+            ld_lane32(tmem, warp, c0, v);
+            if (rv) {
+                float4* g = reinterpret_cast<float4*>(crow + c0);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    if (p.accumulate) { const float4 t = g[i]; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+                    g[i] = o;
+                }
             }
         }
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 128);
+    if (warp == 0) tmem_dealloc(tmem, (uint32_t)N);
 }
 
 // =====================================================================================================================
@@ -1025,6 +1048,18 @@ extern "C" int sd_kv_proj_bf16(const void* mem_bf16, long long rows, const void*
     return SD_OK;
 }
 
+static int launch_mn_gemm(const CUtensorMap& tmA, const CUtensorMap& tmW, const MnGemmParams& p, cudaStream_t st) {
+    const int smem = KD_STAGES * kd_stage_bytes(p.N) + 1024;
+    static int configured = 0;
+    if (configured < smem) {
+        SD_CUDA(cudaFuncSetAttribute(mn_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
+    }
+    mn_gemm_kernel<<<ceil_div(p.rows, 128), CNT, smem, st>>>(tmA, tmW, p);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+}
+
 extern "C" int sd_kv_dgrad_bf16(const void* dkv_bf16, long long rows, long long lddkv, const void* w_packed, int w_rows_total,
                                 int w_row0, int w_stride, int n_layers, float* dmem, long long lddmem, int accumulate,
                                 void* stream) {
@@ -1035,17 +1070,33 @@ extern "C" int sd_kv_dgrad_bf16(const void* dkv_bf16, long long rows, long long 
     CUtensorMap tmA, tmW;
     if (!encode_bf16_2d(&tmA, dkv_bf16, rows, 256LL * n_layers, lddkv, 128)) return SD_ERR_UNSUPPORTED;
     if (!encode_bf16_2d(&tmW, w_packed, w_rows_total, 128, 128, 64)) return SD_ERR_UNSUPPORTED;
-    KvDgradParams p{};
-    p.rows = rows; p.nblk = n_layers; p.w_row0 = w_row0; p.w_stride = w_stride;
-    p.C = dmem; p.ldc = lddmem; p.accumulate = accumulate;
-    static bool configured = false;
-    if (!configured) {
-        SD_CUDA(cudaFuncSetAttribute(kv_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KD_SMEM));
-        configured = true;
-    }
-    kv_dgrad_kernel<<<ceil_div(rows, 128), CNT, KD_SMEM, (cudaStream_t)stream>>>(tmA, tmW, p);
-    SD_LAUNCH_CHECK();
-    return SD_OK;
+    MnGemmParams p{};
+    p.rows = rows; p.ktiles = 4 * n_layers; p.N = 128; p.w_row0 = w_row0; p.w_stride = w_stride; p.tiles_per_blk = 4;
+    p.Cf = dmem; p.ldc = lddmem; p.accumulate = accumulate;
+    return launch_mn_gemm(tmA, tmW, p, (cudaStream_t)stream);
+}
+
+extern "C" int sd_conv1x1s2_dgrad_supported(int Hin, int Win, int Cin, int Cout) {
+    if (Hin < 2 || Win < 2 || (Hin & 1) || (Win & 1) || (Cin != 64 && Cin != 128 && Cin != 256) || Cout < 64 || Cout % 64 != 0) return 0;
+    return tensor_map_encoder() != nullptr ? 1 : 0;
+}
+
+extern "C" int sd_conv1x1s2_dgrad_bf16(const void* dy, const void* w_bf16, void* dx, int frames, int Hin, int Win, int Cin, int Cout,
+                                       void* stream) {
+    if (frames <= 0) return SD_OK;
+    if (!dy || !w_bf16 || !dx) return SD_ERR_BAD_ARG;
+    if (!sd_conv1x1s2_dgrad_supported(Hin, Win, Cin, Cout)) return SD_ERR_UNSUPPORTED;
+    const int Ho = Hin / 2, Wo = Win / 2;
+    const long long rows = (long long)frames * Ho * Wo;
+    CUtensorMap tmA, tmW;
+    if (!encode_bf16_2d(&tmA, dy, rows, Cout, Cout, 128)) return SD_ERR_UNSUPPORTED;
+    if (!encode_bf16_2d(&tmW, w_bf16, Cout, Cin, Cin, 64)) return SD_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    SD_CUDA(cudaMemsetAsync(dx, 0, (size_t)frames * Hin * Win * Cin * 2, st));   // the three pixels of each 2x2 block the stride skips
+    MnGemmParams p{};
+    p.rows = rows; p.ktiles = Cout / 64; p.N = Cin; p.w_row0 = 0; p.w_stride = 0; p.tiles_per_blk = p.ktiles;
+    p.Cb = reinterpret_cast<__nv_bfloat16*>(dx); p.Ho = Ho; p.Wo = Wo; p.Hin = Hin; p.Win = Win;
+    return launch_mn_gemm(tmA, tmW, p, st);
 }
 
 namespace {

@@ -529,6 +529,16 @@ struct PackNorm { float mean[3], std[3]; };
 template <bool U8>
 __global__ void __launch_bounds__(kT) stem_pack_kernel(const void* __restrict__ in_, uint4* __restrict__ out, int N, int H,
                                                        int W, int Hp, int Wp, PackNorm nm) {
+    // uint8 input: a channel has only 256 possible normalised values — a shared-memory table built with exactly the fp32
+    // operations above replaces 12 IEEE divisions per packed pixel (the kernel was issue-bound at 1.9 TB/s)
+    __shared__ float lut[U8 ? 3 * 256 : 1];
+    if (U8) {
+        for (int i = threadIdx.x; i < 3 * 256; i += kT) {
+            const int c = i >> 8;
+            lut[i] = __fdiv_rn(__fsub_rn(__fmul_rn((float)(i & 255), (float)(1.0 / 255.0)), nm.mean[c]), nm.std[c]);
+        }
+        __syncthreads();
+    }
     const long long total = (long long)N * Hp * Wp;
     for (long long o = (long long)blockIdx.x * kT + threadIdx.x; o < total; o += (long long)gridDim.x * kT) {
         const int wp = (int)(o % Wp);
@@ -550,12 +560,8 @@ __global__ void __launch_bounds__(kT) stem_pack_kernel(const void* __restrict__ 
                     const int w = 2 * wp + dx - 3;
                     if (w < 0 || w >= W) continue;
                     const long long i = plane + (long long)h * W + w;
-                    if (U8) {
-                        const float u = (float)__ldg(reinterpret_cast<const unsigned char*>(in_) + i);
-                        f[c * 4 + dy * 2 + dx] = __fdiv_rn(__fsub_rn(__fmul_rn(u, (float)(1.0 / 255.0)), nm.mean[c]), nm.std[c]);
-                    } else {
-                        f[c * 4 + dy * 2 + dx] = __ldg(reinterpret_cast<const float*>(in_) + i);
-                    }
+                    if (U8) f[c * 4 + dy * 2 + dx] = lut[c * 256 + __ldg(reinterpret_cast<const unsigned char*>(in_) + i)];
+                    else f[c * 4 + dy * 2 + dx] = __ldg(reinterpret_cast<const float*>(in_) + i);
                 }
             }
         }

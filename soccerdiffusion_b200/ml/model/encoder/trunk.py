@@ -166,6 +166,47 @@ def _conv(conv, x):
     return F.conv2d(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
 
 
+class DownsampleConv1x1S2(torch.autograd.Function):
+    """The 1x1 stride-2 convolution of a ResNet stage's downsample path (torchvision resnet.py conv1x1(inplanes, planes,
+    stride); image.py:55-73).  Forward and weight gradient stay library calls (0.05-0.15 ms each); the DATA gradient is
+    libsd_b200's TMA-fed tcgen05 GEMM with a strided scatter epilogue (sd_conv1x1s2_dgrad_bf16): cuDNN serves this shape with
+    a legacy sm80 kernel at 45 TFLOP/s (0.72 ms for the 64->128 stage at 2560 frames, tools/conv_probe.py)."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        x = _cl(x)
+        Cout, Cin = weight.shape[0], weight.shape[1]
+        wb = torch.empty((Cout, Cin), device=x.device, dtype=torch.bfloat16)
+        ops.cast_bf16(weight.detach().contiguous().view(Cout, Cin), wb)
+        w4 = wb.view(Cout, Cin, 1, 1).contiguous(memory_format=torch.channels_last)
+        y = torch.ops.aten.convolution(x, w4, None, [2, 2], [0, 0], [1, 1], False, [0, 0], 1)
+        ctx.save_for_backward(x, wb)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wb = ctx.saved_tensors
+        dy = _cl(dy)
+        n, Cin, H, W = x.shape
+        Cout = wb.shape[0]
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)   # channels_last storage [n][H][W][Cin]
+            ops.conv1x1s2_dgrad(dy, wb, dx, n, H, W, Cin, Cout)
+        if ctx.needs_input_grad[1]:
+            w4 = wb.view(Cout, Cin, 1, 1).contiguous(memory_format=torch.channels_last)
+            dw = torch.ops.aten.convolution_backward(dy, x, w4, None, [2, 2], [0, 0], [1, 1], False, [0, 0], 1,
+                                                     [False, True, False])[1].float().reshape(Cout, Cin, 1, 1)
+        return dx, dw
+
+
+def _own_ds_dgrad(conv, x) -> bool:
+    return (_OWN_DS_DGRAD and torch.is_grad_enabled() and x.requires_grad and x.dtype == torch.bfloat16 and x.dim() == 4
+            and conv.kernel_size == (1, 1) and conv.stride == (2, 2) and conv.padding == (0, 0) and conv.dilation == (1, 1)
+            and conv.groups == 1 and conv.bias is None and conv.weight.dtype == torch.float32
+            and ops.conv1x1s2_dgrad_supported(x.shape[2], x.shape[3], conv.in_channels, conv.out_channels))
+
+
 def _stem_conv_s2d(conv, images: torch.Tensor) -> torch.Tensor:
     """conv1 (7x7, stride 2, pad 3, Cin=3) evaluated as a 4x4 stride-1 convolution over the 2x2 space-to-depth
     image (Cin = 3*2*2 = 12, zero-padded to 16): the same products and sums (the extra taps/channels are exact
@@ -272,6 +313,7 @@ def supported(encoder) -> bool:
     return ok and mp.kernel_size == 3 and mp.stride == 2 and mp.padding == 1 and isinstance(encoder.bn1, torch.nn.BatchNorm2d)
 
 
+_OWN_DS_DGRAD = os.environ.get("SD_B200_OWN_DS_DGRAD", "1") == "1"   # downsample 1x1/s2 data gradient on libsd_b200's GEMM
 _BN_FORK = os.environ.get("SD_B200_BN_FORK", "1") == "1"   # twin block outputs: gradients summed inside the BN backward kernels
 # how many cuDNN algorithms the autotuner times per convolution shape (torch default 10; 0 = all)
 _CUDNN_BENCHMARK_LIMIT = int(os.environ.get("SD_B200_CUDNN_BENCHMARK_LIMIT", "10"))
@@ -317,7 +359,9 @@ def resnet_trunk_bf16(encoder, images: torch.Tensor) -> torch.Tensor:
             fork = _BN_FORK and torch.is_grad_enabled() and i + 1 < len(blocks)
             identity = x_skip
             if blk.downsample is not None:
-                identity = _bn(blk.downsample[1], _conv(blk.downsample[0], x_skip), None, False)
+                ds = blk.downsample[0]
+                ds_out = DownsampleConv1x1S2.apply(x_skip, ds.weight) if _own_ds_dgrad(ds, x_skip) else _conv(ds, x_skip)
+                identity = _bn(blk.downsample[1], ds_out, None, False)
             out = _bn(blk.bn1, _conv(blk.conv1, x_main), None, True)
             if isinstance(blk, BasicBlock):
                 res = _bn(blk.bn2, _conv(blk.conv2, out), identity, True, fork and blk.bn2.training)

@@ -606,3 +606,17 @@ def ca_block_bwd(dy, dx, x, q, attn, stats, lse, B, T, M, w_packed, w_row_q, w_r
     with _Timed("fused_ca_block_bwd", flops, B * (T * 128 * 16.0 + M * 1024.0), f"[B{B} T{T} M{M}]"):
         check(_lib.lib().sd_ca_block_bwd(C.byref(d), stream_ptr()), "sd_ca_block_bwd")
     _count()
+
+
+def conv1x1s2_dgrad_supported(Hin: int, Win: int, Cin: int, Cout: int) -> bool:
+    return bool(_lib.lib().sd_conv1x1s2_dgrad_supported(Hin, Win, Cin, Cout))
+
+
+def conv1x1s2_dgrad(dy, w_bf16, dx, frames, Hin, Win, Cin, Cout):
+    """dx (bf16 NHWC storage [frames][Hin][Win][Cin]) = data gradient of a 1x1 stride-2 convolution (sd_conv1x1s2_dgrad_bf16)."""
+    rows = frames * (Hin // 2) * (Win // 2)
+    with _Timed("conv1x1s2_dgrad", 2.0 * rows * Cin * Cout, rows * 2.0 * Cout + frames * Hin * Win * Cin * 2.0,
+                f"[N{frames} H{Hin} C{Cin}->{Cout}]"):
+        check(_lib.lib().sd_conv1x1s2_dgrad_bf16(dy.data_ptr(), w_bf16.data_ptr(), dx.data_ptr(), frames, Hin, Win, Cin, Cout,
+                                                 stream_ptr()), "sd_conv1x1s2_dgrad_bf16")
+    _count()

@@ -431,3 +431,33 @@ def test_stem_backward_pooled_domain_reductions(case):
         assert rel(out[True][0], out[False][0]) < 5e-3
     else:                                                                   # exact kernel ran in both calls
         assert rel(out[True][1], out[False][1]) < 1e-5 and rel(out[True][0], out[False][0]) < 1e-5
+
+
+@pytest.mark.parametrize("n,H,cin,cout", [(6, 56, 64, 128), (5, 28, 128, 256), (7, 14, 256, 512), (3, 8, 64, 64)])
+def test_downsample_conv1x1s2_dgrad_matches_library(n, H, cin, cout):
+    """sd_conv1x1s2_dgrad_bf16 (TMA + tcgen05 GEMM, strided scatter) against torch's convolution_backward on the same bf16
+    operands, and the autograd node of the trunk's downsample path against F.conv2d's autograd."""
+    from soccerdiffusion_b200 import ops
+    from soccerdiffusion_b200.ml.model.encoder.trunk import DownsampleConv1x1S2
+
+    gen = torch.Generator().manual_seed(n + H)
+    cl = torch.channels_last
+    x = torch.randn(n, cin, H, H, generator=gen).cuda().to(torch.bfloat16).contiguous(memory_format=cl)
+    w = (torch.randn(cout, cin, 1, 1, generator=gen) / cin ** 0.5).cuda()
+    assert ops.conv1x1s2_dgrad_supported(H, H, cin, cout)
+    wb4 = w.to(torch.bfloat16).contiguous(memory_format=cl)
+    y = torch.ops.aten.convolution(x, wb4, None, [2, 2], [0, 0], [1, 1], False, [0, 0], 1)
+    dy = torch.randn(y.shape, generator=gen).cuda().to(torch.bfloat16).contiguous(memory_format=cl)
+    want_dx, want_dw, _ = torch.ops.aten.convolution_backward(dy, x, wb4, None, [2, 2], [0, 0], [1, 1], False, [0, 0], 1,
+                                                              [True, True, False])
+    dx = torch.full_like(x, float("nan"))
+    ops.conv1x1s2_dgrad(dy, w.to(torch.bfloat16).view(cout, cin).contiguous(), dx, n, H, H, cin, cout)
+    assert rel(dx.float(), want_dx.float()) < 5e-3, rel(dx.float(), want_dx.float())
+    assert not dx[:, :, 1::2, :].any() and not dx[:, :, :, 1::2].any()   # the pixels the stride skips
+    xr = x.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    out = DownsampleConv1x1S2.apply(xr, wr)
+    assert rel(out.float(), y.float()) < 1e-6
+    out.backward(dy)
+    assert rel(xr.grad.float(), want_dx.float()) < 5e-3
+    assert wr.grad.dtype == torch.float32 and rel(wr.grad, want_dw.float()) < 5e-3
