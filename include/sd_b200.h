@@ -371,6 +371,12 @@ int sd_wgrad_bf16(const sd_wgrad_job* jobs, int n_jobs, long long rows, void* st
  * cudaLaunchAttributeProgrammaticStreamSerialization; each of them runs its prologue under the preceding kernel's tail and
  * executes griddepcontrol.wait before touching activations.  Returns the previous setting. */
 int sd_set_pdl(int on);
+/* Hardware probe used by tests / tools only: D[128][64*nblk_b] = A B^T over 16*ksteps k rows, where A and B are MN-major
+ * SWIZZLE_128B views of TMA-loaded bf16 [rows][64] tiles X and Y starting at row shift_a / shift_b (any row, not only
+ * multiples of 8), A's two and B's nblk_b 64-wide MN blocks lbo bytes apart (blocks may overlap).  cycles: clock64 ticks of
+ * `reps` repetitions of the MMA sequence (or NULL). */
+int sd_debug_shifted_mma(const void* X, const void* Y, int rows, int shift_a, int lbo_a, int shift_b, int lbo_b, int nblk_b,
+                         int ksteps, int use_base_offset, int reps, float* D, long long* cycles, void* stream);
 /* One launch between two denoiser evaluations of the batched DDIM loop (ros.py:301-310; decoder.py:48,54): output
  * projection eps = h fc_w^T + fc_b (h fp32 [rows][128], fc_w [J][128]), the eta=0 update x_next = sap*(x - sb*eps)/sa + sbp*eps
  * (optionally eps_out), the next step's embedding h_next = x_next emb_w^T + emb_b + pe[row % T] (emb_w [128][J]; NULL on
@@ -398,6 +404,16 @@ int sd_kv_dgrad_bf16(const void* dkv_bf16, long long rows, long long lddkv, cons
 int sd_conv1x1s2_dgrad_supported(int Hin, int Win, int Cin, int Cout);
 int sd_conv1x1s2_dgrad_bf16(const void* dy, const void* w_bf16, void* dx, int frames, int Hin, int Win, int Cin, int Cout,
                             void* stream);
+
+/* Weight gradient of a 3x3, stride-1, padding-1 convolution with 64 input and 64 output channels (ResNet18 layer1;
+ * torchvision resnet.py BasicBlock, ml/model/encoder/image.py:55-73) as an implicit GEMM over the pixels on tcgen05 + TMA:
+ * dW[co][ci][kh][kw] (+)= sum_{n,h,w} dy[n][h][w][co] * x[n][h+kh-1][w+kw-1][ci].  x, dy: bf16 NHWC [frames][H][W][64];
+ * dW: fp32 [64][64][3][3] contiguous; scratch: sd_conv3x3_wgrad_c64_scratch_bytes() bytes of device memory (per-CTA partial
+ * sums, added in a fixed order: the result is deterministic). */
+int sd_conv3x3_wgrad_c64_supported(int H, int W);
+int sd_conv3x3_wgrad_c64_scratch_bytes(void);
+int sd_conv3x3_wgrad_c64_bf16(const void* x, const void* dy, float* dW, int frames, int H, int W, float* scratch, int accumulate,
+                              void* stream);
 
 /* y = x + Drop(OutProj(MHA(LN(x), kv))) for B samples of T query rows; one CTA per sample.  x, y fp32 [B*T][128] (may
  * alias).  kv: bf16 [B*M][ldkv], this layer's K at columns [kv_col0, kv_col0+128), V at [kv_col0+128, kv_col0+256).

@@ -1,0 +1,85 @@
+// Hardware probe (test infrastructure, not on any product path): tcgen05.mma with MN-major SWIZZLE_128B operands that are
+// SHIFTED VIEWS of one TMA-loaded [rows][64] tile — start addresses that are multiples of 128 B but not of the 1024-byte
+// swizzle atom, and MN blocks that overlap (leading byte offset = a few rows).  An implicit-GEMM weight gradient needs exactly
+// this: dW[tap] = sum_p x[p + off(tap)] dy[p] with every tap a row-shifted view of the same shared-memory halo tile.
+#include "layer_common.cuh"
+#include "../../include/sd_b200.h"
+
+using namespace sdlf;
+
+namespace {
+
+__device__ __forceinline__ uint64_t desc_mn_sw128_off(uint32_t addr, uint32_t lbo, uint32_t sbo, int use_base_offset) {
+    uint64_t d = smem_desc_mn_sw128(addr, lbo, sbo);
+    if (use_base_offset) d |= (uint64_t)((addr >> 7) & 7) << 49;   // matrix-descriptor base offset: row phase inside the atom
+    return d;
+}
+
+struct DbgParams {
+    int rows;              // rows of the X / Y tiles (multiple of 8, <= 128)
+    int shift_a, lbo_a;    // A view: first k row, byte offset between its two 64-wide MN blocks
+    int shift_b, lbo_b, nblk_b;
+    int ksteps, use_base_offset, reps;
+    float* D;              // [128][64 * nblk_b]
+    long long* cycles;
+};
+
+__global__ void __launch_bounds__(128, 1) dbg_shifted_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+                                                                const DbgParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_l, bar_m;
+    __shared__ uint32_t tmem_slot;
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) { mbar_init(&bar_l, 1); mbar_init(&bar_m, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc(&tmem_slot, 256);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const int N = 64 * p.nblk_b;
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&bar_l, 2 * p.rows * 128);
+        tma_tile_2d(sbase, &tmX, 0, 0, &bar_l);
+        tma_tile_2d(sbase + LTILE, &tmY, 0, 0, &bar_l);
+        mbar_wait(&bar_l, 0);
+        const uint32_t idesc = instr_desc_bf16(128, N, 1, 1);
+        const long long t0 = clock64();
+        for (int r = 0; r < p.reps; ++r)
+            for (int k = 0; k < p.ksteps; ++k) {
+                const uint32_t a = sbase + (p.shift_a + 16 * k) * 128, b = sbase + LTILE + (p.shift_b + 16 * k) * 128;
+                mma_bf16_ss(tmem, desc_mn_sw128_off(a, p.lbo_a, 1024, p.use_base_offset), desc_mn_sw128_off(b, p.lbo_b, 1024, p.use_base_offset),
+                            idesc, (k > 0 || r > 0) ? 1u : 0u);
+            }
+        mma_commit(&bar_m);
+        mbar_wait(&bar_m, 0);
+        if (p.cycles) *p.cycles = clock64() - t0;
+    }
+    __syncthreads();
+    mbar_wait(&bar_m, 0);
+    tc_fence_after_sync();
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        float v[32];
+        tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+        for (int i = 0; i < 32; ++i) p.D[(long long)tid * N + c0 + i] = v[i];
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+}  // namespace
+
+extern "C" int sd_debug_shifted_mma(const void* X, const void* Y, int rows, int shift_a, int lbo_a, int shift_b, int lbo_b, int nblk_b,
+                                    int ksteps, int use_base_offset, int reps, float* D, long long* cycles, void* stream) {
+    if (!X || !Y || !D || rows < 8 || rows > 128 || rows % 8 || nblk_b < 1 || nblk_b > 4 || ksteps < 1 || reps < 1) return SD_ERR_BAD_ARG;
+    CUtensorMap tmX, tmY;
+    if (!encode_bf16_2d(&tmX, X, rows, 64, 64, rows) || !encode_bf16_2d(&tmY, Y, rows, 64, 64, rows)) return SD_ERR_UNSUPPORTED;
+    DbgParams p{rows, shift_a, lbo_a, shift_b, lbo_b, nblk_b, ksteps, use_base_offset, reps, D, cycles};
+    const int smem = 2 * LTILE + 1024;
+    SD_CUDA(cudaFuncSetAttribute(dbg_shifted_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    dbg_shifted_mma_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(tmX, tmY, p);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+}

@@ -163,6 +163,8 @@ def _bn(bn, x, residual=None, relu=True, fork=False):
 
 
 def _conv(conv, x):
+    if _own_wgrad_c64(conv, x):
+        return Conv3x3C64.apply(x, conv.weight)
     return F.conv2d(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
 
 
@@ -198,6 +200,42 @@ class DownsampleConv1x1S2(torch.autograd.Function):
             dw = torch.ops.aten.convolution_backward(dy, x, w4, None, [2, 2], [0, 0], [1, 1], False, [0, 0], 1,
                                                      [False, True, False])[1].float().reshape(Cout, Cin, 1, 1)
         return dx, dw
+
+
+class Conv3x3C64(torch.autograd.Function):
+    """A 3x3 / stride 1 / padding 1 convolution with 64 -> 64 channels (ResNet18 layer1, torchvision resnet.py BasicBlock).
+    Forward and data gradient stay library calls (cuDNN's weight-stationary kernels run them at 1.2 PFLOP/s); the WEIGHT
+    gradient is libsd_b200's implicit GEMM over the pixels (sd_conv3x3_wgrad_c64_bf16: 0.55 ms vs 0.87 ms for cuDNN's
+    64x64x64 kernel at 2560 frames of 56x56, tools/wgrad_micro.py)."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        x = _cl(x)
+        wb = weight.detach().to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+        y = torch.ops.aten.convolution(x, wb, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1)
+        ctx.save_for_backward(x, wb)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wb = ctx.saved_tensors
+        dy = _cl(dy)
+        n, _, H, W = x.shape
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.ops.aten.convolution_backward(dy, x, wb, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
+                                                     [True, False, False])[0]
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty((64, 64, 3, 3), device=x.device, dtype=torch.float32)
+            ops.conv3x3_wgrad_c64(x, dy, dw, n, H, W)
+        return dx, dw
+
+
+def _own_wgrad_c64(conv, x) -> bool:
+    return (_OWN_WGRAD_C64 and torch.is_grad_enabled() and conv.weight.requires_grad and x.dtype == torch.bfloat16 and x.dim() == 4
+            and conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.padding == (1, 1) and conv.dilation == (1, 1)
+            and conv.groups == 1 and conv.bias is None and conv.in_channels == 64 and conv.out_channels == 64
+            and conv.weight.dtype == torch.float32 and ops.conv3x3_wgrad_c64_supported(x.shape[2], x.shape[3]))
 
 
 def _own_ds_dgrad(conv, x) -> bool:
@@ -313,6 +351,7 @@ def supported(encoder) -> bool:
     return ok and mp.kernel_size == 3 and mp.stride == 2 and mp.padding == 1 and isinstance(encoder.bn1, torch.nn.BatchNorm2d)
 
 
+_OWN_WGRAD_C64 = os.environ.get("SD_B200_OWN_WGRAD_C64", "1") == "1"   # layer1 weight gradients on libsd_b200's implicit GEMM
 _OWN_DS_DGRAD = os.environ.get("SD_B200_OWN_DS_DGRAD", "1") == "1"   # downsample 1x1/s2 data gradient on libsd_b200's GEMM
 _BN_FORK = os.environ.get("SD_B200_BN_FORK", "1") == "1"   # twin block outputs: gradients summed inside the BN backward kernels
 # how many cuDNN algorithms the autotuner times per convolution shape (torch default 10; 0 = all)

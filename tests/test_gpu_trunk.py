@@ -461,3 +461,29 @@ def test_downsample_conv1x1s2_dgrad_matches_library(n, H, cin, cout):
     out.backward(dy)
     assert rel(xr.grad.float(), want_dx.float()) < 5e-3
     assert wr.grad.dtype == torch.float32 and rel(wr.grad, want_dw.float()) < 5e-3
+
+
+@pytest.mark.parametrize("n,H,W", [(3, 56, 56), (2, 8, 12), (5, 7, 20), (1, 4, 4), (148, 12, 12)])
+def test_conv3x3_wgrad_c64_matches_library(n, H, W):
+    """sd_conv3x3_wgrad_c64_bf16 (implicit GEMM over the pixels, every tap a shifted view of two TMA tiles) against torch's
+    convolution_backward on the same bf16 operands; deterministic; accumulate mode."""
+    from soccerdiffusion_b200 import ops
+
+    assert ops.conv3x3_wgrad_c64_supported(H, W)
+    gen = torch.Generator().manual_seed(n * 100 + H + W)
+    cl = torch.channels_last
+    x = torch.randn(n, 64, H, W, generator=gen).cuda().to(torch.bfloat16).contiguous(memory_format=cl)
+    dy = torch.randn(n, 64, H, W, generator=gen).cuda().to(torch.bfloat16).contiguous(memory_format=cl)
+    w = torch.zeros(64, 64, 3, 3, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=cl)
+    want = torch.ops.aten.convolution_backward(dy.float(), x.float(), w.float(), None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
+                                               [False, True, False])[1]
+    dW = torch.full((64, 64, 3, 3), float("nan"), device="cuda")
+    ops.conv3x3_wgrad_c64(x, dy, dW, n, H, W)
+    assert rel(dW, want) < 2e-3, rel(dW, want)
+    dW2 = torch.full((64, 64, 3, 3), float("nan"), device="cuda")
+    ops.conv3x3_wgrad_c64(x, dy, dW2, n, H, W)
+    assert torch.equal(dW, dW2)
+    base = torch.randn(64, 64, 3, 3, generator=gen).cuda()
+    acc = base.clone()
+    ops.conv3x3_wgrad_c64(x, dy, acc, n, H, W, accumulate=True)
+    assert rel(acc, base + want) < 2e-3
