@@ -203,43 +203,52 @@ RESNET18_CONVS = (   # (cin, cout, kernel, stride, input H=W) of layer1..layer4 
 
 
 def conv_library_probe(dev, frames: int, resolution: int):
-    """Device time of the trunk's LIBRARY convolutions alone (cuDNN: layer1-4 of ResNet18, fprop + dgrad + wgrad, bf16
-    channels_last exactly as encoder/trunk.py issues them).  Every distinct shape is run back to back (forward op, backward
-    op) between two CUDA events after a warm-up; each call is 0.1-1 ms of device work, so the queue never runs dry and the
-    events see device time only — no profiler.  -> (ms per training step, algorithmic flops per step)."""
+    """Device time of the trunk's LIBRARY convolutions alone (cuDNN: layer1-4 of ResNet18, bf16 channels_last exactly as
+    encoder/trunk.py issues them).  Only the passes that ARE library calls are timed: forward, data gradient and weight gradient of
+    every convolution EXCEPT the weight gradient of the four 3x3 64->64 convolutions of layer1 and the data gradient of the three
+    1x1 stride-2 downsample convolutions, which run on libsd_b200's own kernels (sd_conv3x3_wgrad_c64_bf16,
+    sd_conv1x1s2_dgrad_bf16).  Every distinct shape is run back to back between two CUDA events after a warm-up; each call is
+    0.05-1 ms of device work, so the queue never runs dry and the events see device time only — no profiler.
+    -> (ms per training step, algorithmic flops per step, number of library launches per step)."""
     import collections
 
     import torch
 
     scale = resolution / 224.0
-    total_ms, total_flops = 0.0, 0.0
+    total_ms, total_flops, launches = 0.0, 0.0, 0
     reps = 3
     for (cin, cout, k, st, hin), mult in collections.Counter(RESNET18_CONVS).items():
         hin = int(round(hin * scale))
         cl = torch.channels_last
         x = torch.randn(frames, cin, hin, hin, device=dev, dtype=torch.bfloat16).contiguous(memory_format=cl)
         w = torch.randn(cout, cin, k, k, device=dev, dtype=torch.bfloat16).contiguous(memory_format=cl)
-        conv = lambda: torch.ops.aten.convolution(x, w, None, [st, st], [k // 2, k // 2], [1, 1], False, [0, 0], 1)
-        y = conv()
+        args = ([st, st], [k // 2, k // 2], [1, 1], False, [0, 0], 1)
+        y = torch.ops.aten.convolution(x, w, None, *args)
         gy = torch.randn_like(y)
-        bwd = lambda: torch.ops.aten.convolution_backward(gy, x, w, None, [st, st], [k // 2, k // 2], [1, 1], False, [0, 0], 1,
-                                                          [True, True, False])
+        own_wgrad = (cin, cout, k, st) == (64, 64, 3, 1)
+        own_dgrad = k == 1 and st == 2
+        passes = [lambda: torch.ops.aten.convolution(x, w, None, *args)]
+        if not own_dgrad:
+            passes.append(lambda: torch.ops.aten.convolution_backward(gy, x, w, None, *args, [True, False, False]))
+        if not own_wgrad:
+            passes.append(lambda: torch.ops.aten.convolution_backward(gy, x, w, None, *args, [False, True, False]))
         for _ in range(2):
-            conv()
-            bwd()
+            for f in passes:
+                f()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
-            conv()
-            bwd()
+            for f in passes:
+                f()
         e1.record()
         torch.cuda.synchronize()
         total_ms += mult * e0.elapsed_time(e1) / reps
-        total_flops += mult * 3 * 2.0 * frames * y.shape[2] * y.shape[3] * cout * cin * k * k
+        total_flops += mult * len(passes) * 2.0 * frames * y.shape[2] * y.shape[3] * cout * cin * k * k
+        launches += mult * len(passes)
         del x, w, y, gy
         torch.cuda.empty_cache()
-    return total_ms, total_flops
+    return total_ms, total_flops, launches
 
 
 def time_training_leg(hp, bs, dev, precision, workload="full", steps=3, warm=3):
@@ -577,11 +586,13 @@ def run_ours(args):
         conv_ms = conv_flops = None
         if args.workload == "full" and args.precision == "bf16":
             try:
-                conv_ms, conv_flops = conv_library_probe(dev, bs * hp["image_context_length"], hp["image_resolution"])
+                conv_ms, conv_flops, conv_launches = conv_library_probe(dev, bs * hp["image_context_length"], hp["image_resolution"])
                 kernel_classes["cudnn_conv_layer1_4"] = dict(
                     library=True, ms_per_step=round(conv_ms, 3), tflops=round(conv_flops / conv_ms / 1e9, 1),
                     share_of_step=round(conv_ms / step_ms, 4),
-                    note="fprop + dgrad + wgrad of the 19 convolutions of ResNet18 layer1-4 (library calls, not libsd_b200 kernels), each "
+                    launches_per_step=conv_launches,
+                    note="the LIBRARY passes of the 19 convolutions of ResNet18 layer1-4: fprop + dgrad + wgrad except layer1's four weight "
+                         "gradients and the three downsample data gradients (libsd_b200 kernels: conv3x3_wgrad_c64, conv1x1s2_dgrad); each "
                          "distinct shape run alone, back to back, between CUDA events")
             except Exception as e:   # noqa: BLE001
                 sys.stderr.write(f"[bench] conv library probe failed: {type(e).__name__}: {e}\n")
@@ -605,19 +616,19 @@ def run_ours(args):
             # the dominant kernel class of the step is a LIBRARY class: report it as such (no kernel credit is claimed for it);
             # `roofline_own` is the largest class of this repo's own kernels
             ach = conv_flops / conv_ms / 1e9
-            roofline = dict(kernel="cudnn_conv_layer1_4 (fprop+dgrad+wgrad, library)", library=True, bound="tensor", achieved=ach,
+            roofline = dict(kernel="cudnn_conv_layer1_4 (library passes of the layer1-4 convolutions)", library=True, bound="tensor", achieved=ach,
                             peak=peaks["tf_sust"], unit="TFLOP/s", frac=ach / peaks["tf_sust"], traffic=None,
-                            peak_source=peaks["source"] + " (sustained bf16)", launches_per_step=3 * len(RESNET18_CONVS),
-                            avg_launch_ms=conv_ms / (3 * len(RESNET18_CONVS)), algorithmic_flops_per_launch=conv_flops / (3 * len(RESNET18_CONVS)),
+                            peak_source=peaks["source"] + " (sustained bf16)", launches_per_step=conv_launches,
+                            avg_launch_ms=conv_ms / conv_launches, algorithmic_flops_per_launch=conv_flops / conv_launches,
                             share_of_step=round(conv_ms / step_ms, 4),
                             how="each distinct convolution shape run alone, back to back, between CUDA events (no profiler)")
         else:
             roofline = roofline_own
     if roofline_own is not None and args.workload == "full" and args.config == "default" and bs == 256:
         # DRAM bytes per launch of the dominant own kernel class from the committed ncu capture of this very command
-        # (profiles/r01_dram_traffic.json, written by tools/ncu_summary.py traffic); null when no capture covers it
+        # (profiles/r02_dram_traffic.json, written by tools/ncu_summary.py traffic); null when no capture covers it
         try:
-            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_dram_traffic.json")) as fh:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_dram_traffic.json")) as fh:
                 tr = json.load(fh)
             if roofline_own["kernel"] in tr:
                 roofline_own["traffic"] = tr[roofline_own["kernel"]]["dram_bytes_per_launch"]
@@ -692,7 +703,8 @@ def run_ours(args):
             metric=METRIC, value=gb * args.steps / (ms / 1e3), unit=UNIT, n_gpus=world, steps=args.steps,
             warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong" if strong else "weak", vs_baseline=None,
             dtype="f32" if args.precision == "fp32" else "bf16", data="synthetic", impl="ours",
-            config=dict(architecture=args.config, workload={"full": "default.yaml full training step incl. ResNet18 trunk (layer1-4 convolutions = cuDNN library calls)",
+            config=dict(architecture=args.config, workload={"full": "default.yaml full training step incl. ResNet18 trunk (layer1-4 convolutions = cuDNN library calls except "
+                                                  "layer1's weight gradients and the downsample data gradients)",
                                   "inscope": "default.yaml training step, image tokens precomputed (trunk outside the step)",
                                   "denoiser": "denoiser-only training step (train.py:221-224)"}[args.workload],
                         global_batch=gb, per_gpu_batch=bs, parallelism=f"dp{world}", dropout_p=0.1,

@@ -205,8 +205,9 @@ def test_prefetcher_chunked_copy_is_a_plain_copy():
     assert torch.equal(d8, u8)
 
 
-def test_committed_dram_traffic_matches_its_ncu_capture(tmp_path):
-    """profiles/r01_dram_traffic.json (what bench.py reports as roofline.traffic) is exactly what tools/ncu_summary.py derives
+@pytest.mark.parametrize("rnd,capture", [("r01", "dram_r01_full_step_bf16_s22.csv"), ("r02", "dram_r02_full_step_bf16.csv")])
+def test_committed_dram_traffic_matches_its_ncu_capture(tmp_path, rnd, capture):
+    """profiles/rNN_dram_traffic.json (what bench.py reports as roofline.traffic) is exactly what tools/ncu_summary.py derives
     from the committed ncu CSV, and the measured DRAM bytes of the HBM-bound kernel classes equal their algorithmic bytes
     (no wasted re-reads): BatchNorm backward at bs=256 moves 10.25-14.25 B per element of its tensors."""
     import json
@@ -215,8 +216,8 @@ def test_committed_dram_traffic_matches_its_ncu_capture(tmp_path):
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    csv = os.path.join(root, "profiles", "dram_r01_full_step_bf16_s22.csv")
-    committed = json.load(open(os.path.join(root, "profiles", "r01_dram_traffic.json")))
+    csv = os.path.join(root, "profiles", capture)
+    committed = json.load(open(os.path.join(root, "profiles", f"{rnd}_dram_traffic.json")))
     out = tmp_path / "traffic.json"
     subprocess.run([sys.executable, os.path.join(root, "tools", "ncu_summary.py"), "traffic", csv, str(out), "test"],
                    check=True, capture_output=True)
