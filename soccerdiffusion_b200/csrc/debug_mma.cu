@@ -19,7 +19,7 @@ struct DbgParams {
     int rows;              // rows of the X / Y tiles (multiple of 8, <= 128)
     int shift_a, lbo_a;    // A view: first k row, byte offset between its two 64-wide MN blocks
     int shift_b, lbo_b, nblk_b;
-    int ksteps, use_base_offset, reps;
+    int ksteps, use_base_offset, reps, kmajor;
     float* D;              // [128][64 * nblk_b]
     long long* cycles;
 };
@@ -44,8 +44,14 @@ __global__ void __launch_bounds__(128, 1) dbg_shifted_mma_kernel(const __grid_co
         tma_tile_2d(sbase, &tmX, 0, 0, &bar_l);
         tma_tile_2d(sbase + LTILE, &tmY, 0, 0, &bar_l);
         mbar_wait(&bar_l, 0);
-        const uint32_t idesc = instr_desc_bf16(128, N, 1, 1);
+        const uint32_t idesc = instr_desc_bf16(128, N, p.kmajor ? 0 : 1, p.kmajor ? 0 : 1);
         const long long t0 = clock64();
+        if (p.kmajor) {   // timing only: both operands K-major [rows][64], k step = 32 bytes inside the swizzle row
+            for (int r = 0; r < p.reps; ++r)
+                for (int k = 0; k < p.ksteps; ++k)
+                    mma_bf16_ss(tmem, smem_desc_k_sw128(sbase) + 2 * (k & 3), smem_desc_k_sw128(sbase + LTILE) + 2 * (k & 3), idesc,
+                                (k > 0 || r > 0) ? 1u : 0u);
+        } else
         for (int r = 0; r < p.reps; ++r)
             for (int k = 0; k < p.ksteps; ++k) {
                 const uint32_t a = sbase + (p.shift_a + 16 * k) * 128, b = sbase + LTILE + (p.shift_b + 16 * k) * 128;
@@ -73,11 +79,13 @@ __global__ void __launch_bounds__(128, 1) dbg_shifted_mma_kernel(const __grid_co
 
 extern "C" int sd_debug_shifted_mma(const void* X, const void* Y, int rows, int shift_a, int lbo_a, int shift_b, int lbo_b, int nblk_b,
                                     int ksteps, int use_base_offset, int reps, float* D, long long* cycles, void* stream) {
+    const int kmajor = (use_base_offset & 2) ? 1 : 0;   // bit 1: K-major operands (issue-rate measurement)
+    use_base_offset &= 1;
     if (!X || !Y || !D || rows < 8 || rows > 128 || rows % 8 || nblk_b < 1 || nblk_b > 4 || ksteps < 1 || reps < 1) return SD_ERR_BAD_ARG;
     CUtensorMap tmX, tmY;
     if (!encode_bf16_2d(&tmX, X, rows, 64, 64, rows) || !encode_bf16_2d(&tmY, Y, rows, 64, 64, rows)) return SD_ERR_UNSUPPORTED;
-    DbgParams p{rows, shift_a, lbo_a, shift_b, lbo_b, nblk_b, ksteps, use_base_offset, reps, D, cycles};
-    const int smem = 2 * LTILE + 1024;
+    DbgParams p{rows, shift_a, lbo_a, shift_b, lbo_b, nblk_b, ksteps, use_base_offset, reps, kmajor, D, cycles};
+    const int smem = 2 * LTILE + 2 * LTILE + 1024;   // + slack: N = 256 K-major reads 256 rows of the Y tile
     SD_CUDA(cudaFuncSetAttribute(dbg_shifted_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     dbg_shifted_mma_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(tmX, tmY, p);
     SD_LAUNCH_CHECK();

@@ -257,28 +257,40 @@ __global__ void __launch_bounds__(NT, 1) stem_wgrad_tma_kernel(const __grid_cons
 }
 
 // ---- conv1 forward (space-to-depth form) on the same TMA tensor map: y[p][c] = sum_j patch[p][j] * W[c][j] ------------
-// One image row of output pixels per tile (M = 128 >= WO rows of the accumulator, rows >= WO are ignored), N = 64 output
-// channels, K = 256 = 4 filter rows x 64.  The four patch segments of a pixel are the K-major rows of four [WO][64]
-// operand tiles (the very boxes the weight-gradient kernel loads, read here with K-major descriptors); the weights
-// [64][256] stay resident in shared memory.  Warp 0: TMA producer, warp 1: MMA issuer, warps 4-7: epilogue
-// (TMEM -> bf16 -> one 128-byte NHWC row per thread) with two TMEM accumulators so that the epilogue of tile i overlaps
-// the loads and MMAs of tile i+1.
-constexpr int RING = 8;   // input-row tiles resident in shared memory (4 live + up to 4 in flight)
-constexpr int NACC = 4;   // TMEM accumulators (64 columns each): the MMA warp runs up to NACC - 1 rows ahead of the epilogue
+// The patch tile of packed-image row t ([WO pixels][64], the very boxes the weight-gradient kernel loads, read here with
+// K-major descriptors) is the operand of output row t - kh for every filter row kh.  A tcgen05.mma of 128 x 64 x 16 costs
+// no less than one of 128 x 128 x 16 (~94 clk either way, tools/probe_shifted_mma.py), so TWO filter rows share each
+// instruction: N = 128 = [W_kh ; W_kh+1] (the weight tiles are adjacent in shared memory).  Per input tile t:
+//     G1:  S(t)   = P_t [W0;W1]^T     columns 0..63 -> output row t (kh = 0), columns 64..127 -> output row t-1 (kh = 1)
+//     G2:  S(t-2) += P_t [W2;W3]^T    columns 0..63 -> output row t-2 (kh = 2), columns 64..127 -> output row t-3 (kh = 3)
+// i.e. accumulator slot S(t) (128 TMEM columns) ends up holding the kh in {0,2} half of output row t in its low columns
+// and the kh in {1,3} half of output row t-1 in its high columns:  y[r] = S(r).lo + S(r+1).hi, complete after tile r+3.
+// 8 instructions per output row instead of 16, every tile is read during one step only (the ring is a prefetch queue).
+// Warp 0: TMA producer, warp 1: MMA issuer, warps 4-7: epilogue (thread = pixel: adds the two halves in registers,
+// BatchNorm statistics, bf16, one 128-byte NHWC row per thread through a swizzled staging block).
+constexpr int RING = 8;   // input-row tiles in flight
+constexpr int NACC = 4;   // accumulator slots of 128 TMEM columns
+constexpr int FNT = 384;  // warp 0 producer, warp 1 MMA issuer, warps 4-7 / 8-11: epilogue of channels 0-31 / 32-63
 
-// Input-row ring: the patch tile of packed-image row (n, ho + kh) is the SAME for every (ho, kh) with equal ho + kh, so
-// consecutive output rows share three of their four operand tiles.  Tiles are loaded once into a ring of RING slots
-// (tile sequence number x -> slot x % RING) and each output row's MMAs read the four newest tiles; a tile is released
-// (tcgen05.commit -> its empty barrier) after the last output row that uses it.  L2 -> shared-memory traffic drops
-// from four tiles per output row to one (17 GB -> 4.3 GB at bs=256: the first version was L2-bound at 72 % LTS).
-__global__ void __launch_bounds__(NT, 1) stem_fprop_tma_kernel(const __grid_constant__ CUtensorMap tmA,
+// the CTA's output rows [r_begin, r_end) as windows of consecutive rows of one image
+struct RowWindow { int n, ho_a, ho_b; };
+__device__ __forceinline__ bool next_window(long long& r, long long r_end, int HO, RowWindow& w) {
+    if (r >= r_end) return false;
+    w.n = (int)(r / HO);
+    w.ho_a = (int)(r - (long long)w.n * HO);
+    w.ho_b = (int)min((long long)HO - 1, w.ho_a + (r_end - r) - 1);
+    r += w.ho_b - w.ho_a + 1;
+    return true;
+}
+
+__global__ void __launch_bounds__(FNT, 1) stem_fprop_tma_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const uint4* __restrict__ w_s2d, uint4* __restrict__ y,
                                                                double* __restrict__ sums, int HO, int WO, int Hp, int Wp,
                                                                long long rows_total, int rows_per_cta) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[RING];
     __shared__ __align__(8) uint64_t bar_empty[RING];
-    __shared__ __align__(8) uint64_t acc_full[NACC];
+    __shared__ __align__(8) uint64_t row_full[NACC];
     __shared__ __align__(8) uint64_t acc_empty[NACC];
     __shared__ uint32_t tmem_slot;
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -289,12 +301,12 @@ __global__ void __launch_bounds__(NT, 1) stem_fprop_tma_kernel(const __grid_cons
 #pragma unroll
         for (int s = 0; s < RING; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
 #pragma unroll
-        for (int a = 0; a < NACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 1); }
+        for (int a = 0; a < NACC; ++a) { mbar_init(&row_full[a], 1); mbar_init(&acc_empty[a], 1); }
         mbar_fence_init();
     }
-    if (warp == 0) tmem_alloc(&tmem_slot, NACC * 64);
+    if (warp == 0) tmem_alloc(&tmem_slot, NACC * 128);
     // weights: w_s2d[c][j] bf16 (j = kh*64 + kw*16 + ci) -> tile kh, row c, 16-byte chunk (j % 64) / 8
-    for (int i = tid; i < 64 * 32; i += NT) {
+    for (int i = tid; i < 64 * 32; i += FNT) {
         const int c = i >> 5, ch = i & 31;    // 32 chunks of 8 bf16 per output channel
         *reinterpret_cast<uint4*>(Ws + (ch >> 3) * 8192 + sw128_chunk_off(c, ch & 7)) = w_s2d[i];
     }
@@ -307,109 +319,130 @@ __global__ void __launch_bounds__(NT, 1) stem_fprop_tma_kernel(const __grid_cons
     const long long r_begin = (long long)blockIdx.x * rows_per_cta;
     const long long r_end = min(rows_total, r_begin + rows_per_cta);
     const int nrows = (int)max(0LL, r_end - r_begin);
-    const int ho_begin = (int)(r_begin % HO);   // output row i of this CTA is image row (ho_begin + i) % HO
-    // a "fresh" output row starts a new tile window (first row of the CTA or of an image): 4 new tiles, otherwise 1
 
     if (warp == 0 && lane == 0) {
-        int x = 0;   // tile sequence number
-        for (int i = 0; i < nrows; ++i) {
-            const long long r = r_begin + i;
-            const int n = (int)(r / HO), ho = (int)(r - (long long)n * HO);
-            const bool fresh = i == 0 || ho == 0;
-            for (int kh = fresh ? 0 : 3; kh < 4; ++kh, ++x) {
-                const int s = x % RING;
-                mbar_wait(&bar_empty[s], (uint32_t)(((x / RING) & 1) ^ 1));
+        int g = 0;   // tile sequence number
+        long long r = r_begin;
+        RowWindow w;
+        while (next_window(r, r_end, HO, w))
+            for (int t = w.ho_a; t <= w.ho_b + 3; ++t, ++g) {
+                const int s = g % RING;
+                mbar_wait(&bar_empty[s], (uint32_t)(((g / RING) & 1) ^ 1));
                 mbar_arrive_expect_tx(&bar_full[s], (uint32_t)blk);
-                tma_load_2d(smem_u32(smem + s * blk), &tmA, 0, (n * Hp + ho + kh) * Wp, &bar_full[s]);
+                tma_load_2d(smem_u32(smem + s * blk), &tmA, 0, (w.n * Hp + t) * Wp, &bar_full[s]);
             }
-        }
     } else if (warp == 1 && lane == 0) {
-        const uint32_t idesc = instr_desc_bf16(128, 64, 0, 0);
-        int L = 0;   // tiles loaded up to and including this output row's
-        for (int i = 0; i < nrows; ++i) {
-            const int ho = (ho_begin + i) % HO;
-            const bool fresh = i == 0 || ho == 0;
-            L += fresh ? 4 : 1;
-            const int a = i % NACC;
-            mbar_wait(&acc_empty[a], (uint32_t)(((i / NACC) & 1) ^ 1));   // epilogue drained this accumulator
-#pragma unroll
-            for (int kh = 0; kh < 4; ++kh) {
-                const int x = L - 4 + kh, s = x % RING;
-                mbar_wait(&bar_full[s], (uint32_t)((x / RING) & 1));
+        const uint32_t idesc = instr_desc_bf16(128, 128, 0, 0);
+        const uint64_t db01 = smem_desc_k_sw128(smem_u32(Ws)), db23 = smem_desc_k_sw128(smem_u32(Ws) + 2 * 8192);
+        int g = 0, u = 0, v = 0;   // tile / accumulator-slot / output-row sequence numbers
+        long long r = r_begin;
+        RowWindow w;
+        while (next_window(r, r_end, HO, w)) {
+            const int u0 = u;      // S(ho_a)
+            for (int t = w.ho_a; t <= w.ho_b + 3; ++t, ++g) {
+                const int s = g % RING;
+                mbar_wait(&bar_full[s], (uint32_t)((g / RING) & 1));
                 tc_fence_after_sync();
                 const uint64_t da = smem_desc_k_sw128(smem_u32(smem + s * blk));
-                const uint64_t db = smem_desc_k_sw128(smem_u32(Ws) + kh * 8192);
+                // G2 first: it completes output row t-3 and needs no free slot, so the epilogue of that row (and its release
+                // of a slot) overlaps G1 below instead of sitting between two tiles' MMAs
+                if (t - 2 >= w.ho_a) {            // G2: S(t-2) += P_t [W2;W3]^T
+                    const int us = u0 + (t - 2 - w.ho_a);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                    mma_bf16_ss(tmem + a * 64, da + 2 * ks, db + 2 * ks, idesc, (kh | ks) ? 1u : 0u);
+                    for (int ks = 0; ks < 4; ++ks) mma_bf16_ss(tmem + (us % NACC) * 128, da + 2 * ks, db23 + 2 * ks, idesc, 1u);
+                }
+                if (t - 3 >= w.ho_a) {            // output row t-3 = S(t-3).lo + S(t-2).hi is complete
+                    mma_commit(&row_full[v % NACC]);
+                    ++v;
+                }
+                if (t <= w.ho_b + 1) {            // G1: S(t) = P_t [W0;W1]^T
+                    const int us = u0 + (t - w.ho_a);
+                    mbar_wait(&acc_empty[us % NACC], (uint32_t)(((us / NACC) & 1) ^ 1));
+                    tc_fence_after_sync();
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) mma_bf16_ss(tmem + (us % NACC) * 128, da + 2 * ks, db01 + 2 * ks, idesc, ks ? 1u : 0u);
+                }
+                mma_commit(&bar_empty[s]);        // the tile is read during this step only
             }
-            // release the tiles no later output row reads: the oldest one, or all four at the end of the window
-            const bool next_fresh = i + 1 >= nrows || (ho_begin + i + 1) % HO == 0;
-            for (int x = L - 4; x < (next_fresh ? L : L - 3); ++x) mma_commit(&bar_empty[x % RING]);
-            mma_commit(&acc_full[a]);
+            u = u0 + (w.ho_b - w.ho_a + 2);
         }
     } else if (warp >= 4) {
-        const int q = warp & 3;
+        // the epilogue is issue-bound (per output row and pixel: 64 sums, 128 statistics FMAs, bf16 packing, staging): two
+        // warps share a pixel group, warp (q, half) takes channels [32 half, 32 half + 32)
+        const int q = warp & 3, half = (warp >> 2) - 1;
         const int row = q * 32 + lane;        // pixel within the image row
-        // per-warp staging block [32 pixels][128 B], 16-byte chunks XOR-swizzled by the pixel index: conflict-free both
-        // for the row-per-thread writes and for the read-back in global-memory order (the warp's 32 pixels are 4 KB of
-        // contiguous NHWC output, stored with fully coalesced 512-byte requests)
+        // per-pixel-group staging block [32 pixels][128 B], 16-byte chunks XOR-swizzled by the pixel index: conflict-free
+        // both for the row-per-thread writes and for the read-back in global-memory order (the group's 32 pixels are 4 KB
+        // of contiguous NHWC output, stored with fully coalesced 512-byte requests)
         uint8_t* stg = Ws + 4 * 8192 + 4096 + q * 4096;
-        float s1[64], s2[64];                  // BatchNorm statistics of this thread's pixel column over all its rows
+        float s1[32], s2[32];                  // BatchNorm statistics of this thread's pixel column over all its rows
 #pragma unroll
-        for (int c = 0; c < 64; ++c) s1[c] = s2[c] = 0.f;
-        for (int ci = 0; ci < nrows; ++ci) {
-            const int a = ci % NACC;
-            mbar_wait(&acc_full[a], (uint32_t)((ci / NACC) & 1));
-            tc_fence_after_sync();
-            float v0[32], v1[32];
-            tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 64), v0);
-            tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 64 + 32), v1);
-            tc_fence_before_sync();
-            // all four epilogue warps have read the accumulator -> hand it back to the MMA warp
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (tid == 128) mbar_arrive(&acc_empty[a]);
-            if (sums != nullptr && row < WO) {
+        for (int c = 0; c < 32; ++c) s1[c] = s2[c] = 0.f;
+        int u = 0, ci = 0;
+        long long r = r_begin;
+        RowWindow w;
+        while (next_window(r, r_end, HO, w)) {
+            const int u0 = u;
+            for (int ho = w.ho_a; ho <= w.ho_b; ++ho, ++ci) {
+                mbar_wait(&row_full[ci % NACC], (uint32_t)((ci / NACC) & 1));
+                tc_fence_after_sync();
+                const int slo = (u0 + ho - w.ho_a) % NACC, shi = (u0 + ho - w.ho_a + 1) % NACC;
+                float v0[32];
+                {
+                    float h0[32];
+                    tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(slo * 128 + 32 * half), v0);
+                    tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(shi * 128 + 64 + 32 * half), h0);
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    s1[c] += v0[c]; s2[c] = fmaf(v0[c], v0[c], s2[c]);
-                    s1[32 + c] += v1[c]; s2[32 + c] = fmaf(v1[c], v1[c], s2[32 + c]);
+                    for (int c = 0; c < 32; ++c) v0[c] += h0[c];
                 }
-            }
+                tc_fence_before_sync();
+                // all eight epilogue warps have read the slots -> S(ho) (and, after a window's last row, S(ho+1)) go back to the MMA warp
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (tid == 128) {
+                    mbar_arrive(&acc_empty[slo]);
+                    if (ho == w.ho_b) mbar_arrive(&acc_empty[shi]);
+                }
+                if (sums != nullptr && row < WO) {
 #pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8) {
-                *reinterpret_cast<uint4*>(stg + lane * 128 + ((c8 ^ (lane & 7)) << 4)) = pack8_bf16(v0 + 8 * c8);
-                *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 + c8) ^ (lane & 7)) << 4)) = pack8_bf16(v1 + 8 * c8);
-            }
-            __syncwarp();
-            uint4* dst = y + ((r_begin + ci) * WO + q * 32) * 8;
+                    for (int c = 0; c < 32; ++c) { s1[c] += v0[c]; s2[c] = fmaf(v0[c], v0[c], s2[c]); }
+                }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int g = j * 32 + lane, pr = g >> 3, c = g & 7;   // chunk g of the warp's block: pixel pr, chunk c
-                if (q * 32 + pr < WO) dst[g] = *reinterpret_cast<const uint4*>(stg + pr * 128 + ((c ^ (pr & 7)) << 4));
+                for (int c8 = 0; c8 < 4; ++c8)
+                    *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 * half + c8) ^ (lane & 7)) << 4)) = pack8_bf16(v0 + 8 * c8);
+                asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");   // the two warps of this pixel group
+                uint4* dst = y + ((r_begin + ci) * WO + q * 32) * 8;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int g = (4 * half + j) * 32 + lane, pr = g >> 3, c = g & 7;   // chunk g of the group's block: pixel pr, chunk c
+                    if (q * 32 + pr < WO) dst[g] = *reinterpret_cast<const uint4*>(stg + pr * 128 + ((c ^ (pr & 7)) << 4));
+                }
+                asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");   // staging block free for the next row
             }
-            __syncwarp();
+            u = u0 + (w.ho_b - w.ho_a + 2);
         }
         if (sums != nullptr) {
-            // cross-pixel reduction of the 128 epilogue threads through the (now idle) tile ring, one double atomic per
+            // cross-pixel reduction of the epilogue threads through the (now idle) tile ring, one double atomic per
             // (statistic, channel) and CTA
-            asm volatile("bar.sync 1, 128;" ::: "memory");   // every MMA of this CTA has completed (all acc_full consumed)
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // every MMA of this CTA has completed (all rows consumed)
             float* red = reinterpret_cast<float*>(smem);      // [128 values][129]
-            const int t = tid - 128;
+            const int pix = q * 32 + lane;
 #pragma unroll
-            for (int c = 0; c < 64; ++c) {
-                red[c * 129 + t] = s1[c];
-                red[(64 + c) * 129 + t] = s2[c];
+            for (int c = 0; c < 32; ++c) {
+                red[(32 * half + c) * 129 + pix] = s1[c];
+                red[(64 + 32 * half + c) * 129 + pix] = s2[c];
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            float tot = 0.f;
-            for (int i = 0; i < 128; ++i) tot += red[t * 129 + i];
-            atomicAdd(&sums[t], (double)tot);                 // t < 64: sum x of channel t ; t >= 64: sum x^2 of channel t - 64
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (half == 0) {
+                float tot = 0.f;
+                for (int i = 0; i < 128; ++i) tot += red[pix * 129 + i];
+                atomicAdd(&sums[pix], (double)tot);           // pix < 64: sum x of channel pix ; pix >= 64: sum x^2 of channel pix - 64
+            }
         }
     }
+    (void)nrows;
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, NACC * 64);
+    if (warp == 0) tmem_dealloc(tmem, NACC * 128);
 }
 
 bool use_tma() {   // SD_B200_STEM_WGRAD_TMA=0 selects the cp.async-fed kernel
@@ -583,7 +616,7 @@ extern "C" int sd_stem_fprop_s2d_bf16_stats(const void* xs2d, const void* w_s2d,
     const int grid = (int)min((long long)148, rows);
     const int per = (int)((rows + grid - 1) / grid);
     if (sums) SD_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 128, (cudaStream_t)stream));
-    stem_fprop_tma_kernel<<<grid, NT, smem, (cudaStream_t)stream>>>(tmA, (const uint4*)w_s2d, (uint4*)y, sums, HO, WO, Hp, Wp, rows, per);
+    stem_fprop_tma_kernel<<<grid, FNT, smem, (cudaStream_t)stream>>>(tmA, (const uint4*)w_s2d, (uint4*)y, sums, HO, WO, Hp, Wp, rows, per);
     SD_LAUNCH_CHECK();
     return SD_OK;
 }

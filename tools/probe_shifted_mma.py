@@ -53,5 +53,14 @@ def main():
             print(f"N={64*nb:3d} A shift {sa} lbo {la:4d}: {c / (256 * 4):7.1f} clk per 128x{64*nb}x16 MMA  (floor {64*nb//2})")
 
 
+def kmajor_rate():
+    X = torch.randn(128, 64, device="cuda").to(torch.bfloat16)
+    Y = torch.randn(128, 64, device="cuda").to(torch.bfloat16)
+    for nb in (1, 2, 3, 4):
+        _, c = run(X, Y, 0, 1024, 0, 1024, nb, 4, 2, reps=256)
+        print(f"K-major operands N={64*nb:3d}: {c / (256 * 4):7.1f} clk per 128x{64*nb}x16 MMA  (floor {64*nb//2})")
+
+
 if __name__ == "__main__":
+    kmajor_rate()
     main()
