@@ -117,6 +117,17 @@ static inline Dropout make_dropout(float p, uint64_t seed, uint32_t stream) {
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// cuTensorMapEncodeTiled is a DRIVER call: it fails with CUDA_ERROR_INVALID_CONTEXT when no context is bound to the calling
+// thread from the driver API's point of view — observed when another library (cuDNN through PyTorch) ran between two calls
+// into this one and no kernel of this library's own runtime instance had been launched on the thread yet.  Entry points that
+// encode tensor maps bind the runtime's primary context first (two sub-microsecond runtime calls).
+static inline void bind_primary_context() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaSetDevice(dev);
+    cudaFree(nullptr);
+}
+
 // ---- programmatic dependent launch (sd_set_pdl) ----------------------------------------------------------------------
 // Chains of short kernels (the tensor-core sampler: 16 launches per DDIM step): with the launch attribute set, kernel N+1
 // is scheduled as soon as every CTA of kernel N has executed pdl_trigger(), runs its prologue (barrier init, TMEM

@@ -36,6 +36,7 @@ typedef CUresult (*EncodeTiledFn4)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
 inline bool encode_nhwc64(CUtensorMap* tm, const void* base, long long N, int H, int W, int box_w, int box_h) {
     EncodeTiledFn4 encode = (EncodeTiledFn4)tensor_map_encoder();
     if (!encode || (((uintptr_t)base) & 15) || box_w > 256 || box_h > 256) return false;
+    bind_primary_context();
     const cuuint64_t gdim[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t gstr[3] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128};
     const cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};

@@ -12,6 +12,8 @@
 // instruction cache — a 256-thread / 64-column version ran 8x slower than its instruction count on fetch stalls.)
 #pragma once
 #include <cuda.h>
+#include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -34,6 +36,8 @@ inline EncodeTiledFn tensor_map_encoder() {
     static bool tried = false;
     if (!tried) {
         tried = true;
+        cudaFree(nullptr);   // the driver call below needs this runtime's context bound to the thread (CUDA_ERROR_INVALID_CONTEXT
+                             // when a tensor-map encode is the very first call into the library)
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
@@ -55,9 +59,21 @@ inline bool encode_bf16_2d(CUtensorMap* tm, const void* base, long long rows, lo
     const cuuint64_t gstr[1] = {(cuuint64_t)ld_elems * 2};
     const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    CUresult rc = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc == CUDA_ERROR_INVALID_CONTEXT) {
+        // no context bound to this thread from the driver API's point of view (observed when the caller's other library
+        // calls — cuDNN through PyTorch — ran in between): bind this runtime's primary context explicitly and retry
+        bind_primary_context();
+        rc = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (rc != CUDA_SUCCESS && getenv("SD_B200_DEBUG"))
+        fprintf(stderr, "[sd_b200] cuTensorMapEncodeTiled failed (%d): base %p rows %lld cols %lld ld %lld box_rows %d\n", (int)rc, base,
+                rows, cols, ld_elems, box_rows);
+    return rc == CUDA_SUCCESS;
 }
 
 // ---- device: TMA tile load (SASS: UTMALDG) ----------------------------------------------------------------------------

@@ -463,6 +463,8 @@ EncodeFn tensor_map_encoder() {
     static bool tried = false;
     if (!tried) {
         tried = true;
+        cudaFree(nullptr);   // the driver call below needs this runtime's context bound to the thread (CUDA_ERROR_INVALID_CONTEXT
+                             // when a tensor-map encode is the very first call into the library)
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
@@ -477,6 +479,7 @@ EncodeFn tensor_map_encoder() {
 bool encode_patch_map(CUtensorMap* tm, const void* xs2d, int N, int Hp, int Wp, int WO) {
     EncodeFn encode = tensor_map_encoder();
     if (!encode) return false;
+    bind_primary_context();
     const cuuint64_t gdim[2] = {64, (cuuint64_t)N * Hp * Wp - 3};
     const cuuint64_t gstr[1] = {32};
     const cuuint32_t box[2] = {64, (cuuint32_t)WO};
@@ -494,6 +497,7 @@ int launch_tma(const void* xs2d, const void* dy, float* dw, int N, int HO, int W
     if (smem > 227 * 1024 - 256) return SD_OK;
     static bool usable = true;
     if (!usable) return SD_OK;
+    bind_primary_context();
     // the driver entry point is resolved at run time (the library must load on machines without libcuda.so.1)
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

@@ -487,3 +487,40 @@ def test_conv3x3_wgrad_c64_matches_library(n, H, W):
     acc = base.clone()
     ops.conv3x3_wgrad_c64(x, dy, acc, n, H, W, accumulate=True)
     assert rel(acc, base + want) < 2e-3
+
+
+def test_tensor_map_kernels_as_first_call_in_a_fresh_process():
+    """cuTensorMapEncodeTiled needs a context bound to the thread: each TMA-fed entry point must work when it is the FIRST call into
+    the library after another library (cuDNN) has run — run in a fresh interpreter so no earlier test has initialised anything."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from soccerdiffusion_b200 import ops
+which = sys.argv[1]
+cl = torch.channels_last
+x = torch.randn(2, 64, 16, 16, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=cl)
+w = torch.randn(64, 64, 3, 3, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=cl)
+y = torch.ops.aten.convolution(x, w, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1)   # cuDNN first
+if which == "wgrad":
+    dW = torch.empty(64, 64, 3, 3, device="cuda")
+    ops.conv3x3_wgrad_c64(x, y, dW, 2, 16, 16)
+elif which == "ds":
+    dy = torch.randn(2, 128, 8, 8, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=cl)
+    wb = torch.randn(128, 64, device="cuda", dtype=torch.bfloat16)
+    ops.conv1x1s2_dgrad(dy, wb, torch.empty_like(x), 2, 16, 16, 64, 128)
+elif which == "stem":
+    from soccerdiffusion_b200.ml.model.encoder import trunk as T
+    out, _, have = T._stem_conv_s2d_raw(torch.randn(2, 3, 64, 64, device="cuda"), torch.randn(64, 3, 7, 7, device="cuda") * 0.05,
+                                        return_packed=True, sums=torch.zeros(128, device="cuda", dtype=torch.float64))
+    assert have, "the TMA stem kernel was not used"
+torch.cuda.synchronize()
+print("ok")
+''' % root
+    for which in ("wgrad", "ds", "stem"):
+        r = subprocess.run([sys.executable, "-c", code, which], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "ok" in r.stdout, (which, r.stdout[-500:], r.stderr[-1500:])
