@@ -626,16 +626,11 @@ def conv3x3_wgrad_c64_supported(H: int, W: int) -> bool:
     return bool(_lib.lib().sd_conv3x3_wgrad_c64_supported(H, W))
 
 
-_wgrad_scratch = {}
-
-
 def conv3x3_wgrad_c64(x, dy, dW, frames, H, W, accumulate=False):
     """dW (fp32 [64][64][3][3]) (+)= weight gradient of a 3x3/s1/p1 64->64 convolution; x, dy bf16 NHWC storage
-    (sd_conv3x3_wgrad_c64_bf16).  The per-CTA partial-sum scratch is one buffer per device."""
-    dev = x.device.index
-    sc = _wgrad_scratch.get(dev)
-    if sc is None:
-        sc = _wgrad_scratch[dev] = torch.empty(_lib.lib().sd_conv3x3_wgrad_c64_scratch_bytes() // 4, device=x.device, dtype=torch.float32)
+    (sd_conv3x3_wgrad_c64_bf16).  The per-CTA partial-sum scratch (21.8 MB) is allocated per call from the caching allocator
+    (stream-ordered reuse; inside a CUDA-graph capture it comes from the graph's pool)."""
+    sc = torch.empty(_lib.lib().sd_conv3x3_wgrad_c64_scratch_bytes() // 4, device=x.device, dtype=torch.float32)
     with _Timed("conv3x3_wgrad_c64", 2.0 * frames * H * W * 9 * 64 * 64, frames * H * W * 256.0, f"[N{frames} H{H}]"):
         check(_lib.lib().sd_conv3x3_wgrad_c64_bf16(x.data_ptr(), dy.data_ptr(), _f32(dW).data_ptr(), frames, H, W, sc.data_ptr(),
                                                    int(accumulate), stream_ptr()), "sd_conv3x3_wgrad_c64_bf16")
