@@ -176,8 +176,8 @@ struct KvProjParams {
     __nv_bfloat16* C;
     long long ldc;
 };
-constexpr int KP_NT = 256;                                          // two warpgroups: 128 rows x (2 column halves)
-constexpr int KP_SMEM = 2 * LTILE + 2 * 4 * LTILE + 4 * LTILE + 1024;   // A tile + two weight blocks of [256][128] + output staging
+constexpr int KP_NT = 320;                                          // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue
+constexpr int KP_SMEM = 4 * LTILE + 2 * 2 * LTILE + 4 * LTILE + 1024;   // resident weight block [256][128] + two A tiles + output staging
 
 // TMA tile store (shared -> global, SASS: UTMASTG); completion tracked by the issuing thread's bulk async-group
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src_smem, int col0, int row0) {
@@ -189,19 +189,23 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// Persistent and weight-stationary: CTA (block j, group g) keeps the 256 weight rows of block j (64 KB) in shared memory and
+// streams the row tiles g, g + G, ... of A through a 2-slot TMA ring; two TMEM accumulators of 256 columns let the MMAs of
+// tile i+1 run under the epilogue of tile i (8 warps: TMEM -> + bias -> bf16 -> swizzled staging -> TMA store).
 __global__ void __launch_bounds__(KP_NT, 1) kv_proj_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                                                            const __grid_constant__ CUtensorMap tmC, const KvProjParams p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_a, bar_b[2], bar_m[2];
+    __shared__ __align__(8) uint64_t bar_w, a_full[2], a_empty[2], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_slot;
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);
-    const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, r = tid & 127;
-    const long long row0 = (long long)blockIdx.x * 128;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int j = blockIdx.x % p.nblk, g = blockIdx.x / p.nblk, G = gridDim.x / p.nblk;
+    const int ntiles_all = (int)((p.rows + 127) / 128);
+    const int nt = g < ntiles_all ? (ntiles_all - g + G - 1) / G : 0;   // tiles g, g + G, ...
     if (tid == 0) {
-        mbar_init(&bar_a, 1);
-        mbar_init(&bar_b[0], 1); mbar_init(&bar_b[1], 1);
-        mbar_init(&bar_m[0], 1); mbar_init(&bar_m[1], 1);
+        mbar_init(&bar_w, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 1); }
         mbar_fence_init();
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmW);
@@ -212,72 +216,73 @@ __global__ void __launch_bounds__(KP_NT, 1) kv_proj_kernel(const __grid_constant
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = tmem_slot;
-    const uint32_t OFF_B = 2 * LTILE, OFF_C = 10 * LTILE;
-    // weight block j: 256 rows as two TMA boxes of 128 rows per 64-column half -> tiles [k half][row half]
-    auto load_b = [&](int j) {
-        const uint32_t dst = sbase + OFF_B + (j & 1) * 4 * LTILE;
+    const uint32_t OFF_A = 4 * LTILE, OFF_C = 8 * LTILE;
+
+    if (warp == 0 && lane == 0) {          // ---- TMA producer: the weight block once, then the A tiles ------------------
         const int wr = p.w_row0 + j * p.w_stride;
-        mbar_arrive_expect_tx(&bar_b[j & 1], 4 * LTILE);
-        tma_tile_2d(dst, &tmW, 0, wr, &bar_b[j & 1]);
-        tma_tile_2d(dst + LTILE, &tmW, 0, wr + 128, &bar_b[j & 1]);
-        tma_tile_2d(dst + 2 * LTILE, &tmW, 64, wr, &bar_b[j & 1]);
-        tma_tile_2d(dst + 3 * LTILE, &tmW, 64, wr + 128, &bar_b[j & 1]);
-    };
-    // [256 rows][64 k] as two consecutive [128][64] tiles: 8-row groups stay 1024 B apart across the tile boundary
-    const uint32_t id256 = instr_desc_bf16(128, 256);
-    auto issue = [&](int j) {
-        mbar_wait(&bar_b[j & 1], (uint32_t)((j >> 1) & 1));
-        tc_fence_after_sync();
-        mma_k_tiles(tmem + (j & 1) * 256, sbase, LTILE, sbase + OFF_B + (j & 1) * 4 * LTILE, 2 * LTILE, id256, 2, false);
-        mma_commit(&bar_m[j & 1]);
-    };
-    if (tid == 0) {
-        mbar_arrive_expect_tx(&bar_a, 2 * LTILE);
-        tma_tile_2d(sbase, &tmA, 0, (int)row0, &bar_a);
-        tma_tile_2d(sbase + LTILE, &tmA, 64, (int)row0, &bar_a);
-        load_b(0);
-        if (p.nblk > 1) load_b(1);
-        mbar_wait(&bar_a, 0);
-        issue(0);
-    }
-    __syncwarp();
-    for (int j = 0; j < p.nblk; ++j) {
-        if (tid == 0) {
-            if (j + 1 < p.nblk) issue(j + 1);
-            tma_store_wait_read();   // the previous block's stores have read the staging tiles
+        mbar_arrive_expect_tx(&bar_w, 4 * LTILE);
+        tma_tile_2d(sbase, &tmW, 0, wr, &bar_w);                    // tiles [k half][row half]: 256 rows x 64 k contiguous
+        tma_tile_2d(sbase + LTILE, &tmW, 0, wr + 128, &bar_w);
+        tma_tile_2d(sbase + 2 * LTILE, &tmW, 64, wr, &bar_w);
+        tma_tile_2d(sbase + 3 * LTILE, &tmW, 64, wr + 128, &bar_w);
+        for (int i = 0; i < nt; ++i) {
+            const int s = i & 1;
+            mbar_wait(&a_empty[s], (uint32_t)(((i >> 1) & 1) ^ 1));
+            const int row0 = (g + i * G) * 128;
+            mbar_arrive_expect_tx(&a_full[s], 2 * LTILE);
+            tma_tile_2d(sbase + OFF_A + s * 2 * LTILE, &tmA, 0, row0, &a_full[s]);
+            tma_tile_2d(sbase + OFF_A + s * 2 * LTILE + LTILE, &tmA, 64, row0, &a_full[s]);
         }
-        __syncthreads();
-        mbar_wait(&bar_m[j & 1], (uint32_t)((j >> 1) & 1));
-        tc_fence_after_sync();
-        if (tid == 0 && j + 2 < p.nblk) load_b(j + 2);   // the MMAs that read slot j & 1 have completed
-        __syncwarp();
+    } else if (warp == 1 && lane == 0) {   // ---- MMA issuer ---------------------------------------------------------------
+        const uint32_t id256 = instr_desc_bf16(128, 256);
+        mbar_wait(&bar_w, 0);
+        for (int i = 0; i < nt; ++i) {
+            const int s = i & 1;
+            mbar_wait(&a_full[s], (uint32_t)((i >> 1) & 1));
+            mbar_wait(&acc_empty[s], (uint32_t)(((i >> 1) & 1) ^ 1));
+            tc_fence_after_sync();
+            mma_k_tiles(tmem + s * 256, sbase + OFF_A + s * 2 * LTILE, LTILE, sbase, 2 * LTILE, id256, 2, false);
+            mma_commit(&a_empty[s]);
+            mma_commit(&acc_full[s]);
+        }
+    } else if (warp >= 2) {                // ---- epilogue: 8 warps, lane quarter = warp % 4, column half = (warp - 2) / 4 ---
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int r = q * 32 + lane;
         const float* bias = p.bias[j];
-        // warpgroup wg: columns [128 wg, 128 wg + 128) of the block -> staging tiles 2 wg, 2 wg + 1 (row r = this thread's lane)
+        for (int i = 0; i < nt; ++i) {
+            const int s = i & 1;
+            mbar_wait(&acc_full[s], (uint32_t)((i >> 1) & 1));
+            tc_fence_after_sync();
+            if (tid == 64) tma_store_wait_read();   // the previous tile's stores have read the staging tiles
+            asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
-            const int c0 = 128 * wg + 32 * q;
-            float v[32], b[32];
-            if (bias) ldg32(bias + c0, b);
-            ld_lane32(tmem, warp & 3, (j & 1) * 256 + c0, v);
-            if (bias) {
+            for (int qq = 0; qq < 4; ++qq) {
+                const int c0 = 128 * half + 32 * qq;
+                float v[32], b[32];
+                if (bias) ldg32(bias + c0, b);
+                tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 256 + c0), v);
+                if (bias) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] += b[i];
+                    for (int k = 0; k < 32; ++k) v[k] += b[k];
+                }
+                uint8_t* tile = smem + OFF_C + (2 * half + (qq >> 1)) * LTILE;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(tile + sw128_chunk_off(r, 4 * (qq & 1) + k)) = pack8_bf16(v + 8 * k);
             }
-            uint8_t* tile = smem + OFF_C + (2 * wg + (q >> 1)) * LTILE;
+            fence_proxy_async_smem();
+            tc_fence_before_sync();
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // staging complete, accumulator s drained by all eight warps
+            if (tid == 64) {
+                mbar_arrive(&acc_empty[s]);
+                const int row0 = (g + i * G) * 128;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(tile + sw128_chunk_off(r, 4 * (q & 1) + i)) = pack8_bf16(v + 8 * i);
+                for (int t = 0; t < 4; ++t) tma_store_2d(&tmC, sbase + OFF_C + t * LTILE, 256 * j + 64 * t, row0);
+                tma_store_commit();
+            }
         }
-        fence_proxy_async_smem();
-        tc_fence_before_sync();
-        __syncthreads();   // staging complete; accumulator j & 1 drained by every thread before block j + 2 is issued into it
-        tc_fence_after_sync();
-        if (tid == 0) {
-#pragma unroll
-            for (int t = 0; t < 4; ++t) tma_store_2d(&tmC, sbase + OFF_C + t * LTILE, 256 * j + 64 * t, (int)row0);
-            tma_store_commit();
-        }
+        if (tid == 64) tma_store_wait_all();
     }
-    if (tid == 0) tma_store_wait_all();
+    tc_fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
@@ -1043,7 +1048,12 @@ extern "C" int sd_kv_proj_bf16(const void* mem_bf16, long long rows, const void*
         SD_CUDA(cudaFuncSetAttribute(kv_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KP_SMEM));
         configured = true;
     }
-    kv_proj_kernel<<<ceil_div(rows, 128), KP_NT, KP_SMEM, (cudaStream_t)stream>>>(tmA, tmW, tmC, p);
+    // one weight block per CTA, the SMs split evenly over the blocks
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int groups = std::max(1, std::min(ceil_div(rows, 128), sms / n_layers));
+    kv_proj_kernel<<<groups * n_layers, KP_NT, KP_SMEM, (cudaStream_t)stream>>>(tmA, tmW, tmC, p);
     SD_LAUNCH_CHECK();
     return SD_OK;
 }
