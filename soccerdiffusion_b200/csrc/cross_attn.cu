@@ -393,14 +393,18 @@ __global__ void __launch_bounds__(CNT, 1) mn_gemm_kernel(const __grid_constant__
 }
 
 // =====================================================================================================================
-// forward block
-constexpr int F_OFF_KV = 0;                      // 3 chunks x (lo, hi) [128 keys][64] tiles: K, later V
-constexpr int F_OFF_W = 6 * LTILE;               // Wq, later Wout: two [128][64] tiles
-constexpr int F_OFF_QB = F_OFF_W + 2 * LTILE;    // Qblk: two [64][64] tiles of 8 KB
-constexpr int F_OFF_P = F_OFF_QB + LTILE;        // P^T: 3 chunks of [128 keys][64]
-constexpr int F_OFF_XB = F_OFF_P + 3 * LTILE;    // LN2(x) / attention output as B operand: two [16][64] tiles of 2 KB
+// forward block.  Shared memory is kept near 100 KB and TMEM at 256 columns so that TWO CTAs share an SM (one CTA is a chain of
+// dependent phases: the second one fills its waits): every 32 KB operand — Wq, the K chunks, the V chunks, Wout — streams
+// through ONE 2-slot TMA ring in the order it is consumed (a dedicated producer warp refills a slot as soon as the MMAs that
+// read it have completed), P^T is produced chunk by chunk into two tiles (the first one takes Qblk's place once the scores
+// exist), and the small projection accumulators alias the score columns.
+constexpr int F_OFF_RING = 0;                    // 2 slots x (lo, hi) [128][64] tiles
+constexpr int F_OFF_QB = 4 * LTILE;              // Qblk: two [64][64] tiles of 8 KB; after the scores: P^T buffer 0
+constexpr int F_OFF_P1 = F_OFF_QB + LTILE;       // P^T buffer 1
+constexpr int F_OFF_XB = F_OFF_P1 + LTILE;       // LN2(x) / attention output as B operand: two [16][64] tiles of 2 KB
 constexpr int F_SMEM = F_OFF_XB + 4096 + 1024;
 constexpr int XB_TILE = 2048, QB_TILE = 8192;
+constexpr int F_NT = CNT + 32;                   // warps 0-3: the 128 TMEM lanes, warp 4: TMA producer
 
 struct CaFwdParams {
     const float* x;
@@ -415,11 +419,11 @@ struct CaFwdParams {
     Dropout drop;              // stream + 0: attention probabilities, + 1: out-projection
 };
 
-enum { FB_WQ = 0, FB_WO, FB_Q, FB_S, FB_O, FB_Y, FB_K0, FB_V0 = FB_K0 + MAXCH, FB_N = FB_V0 + MAXCH };
+enum { FB_FULL0 = 0, FB_EMPTY0 = 2, FB_Q = 4, FB_S, FB_O, FB_Y, FB_PD0, FB_N = FB_PD0 + 2 };
 
 template <bool DROP>
-__global__ void __launch_bounds__(CNT, 1) ca_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmKV,
-                                                        const CaFwdParams p) {
+__global__ void __launch_bounds__(F_NT, 2) ca_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmKV,
+                                                         const CaFwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar[FB_N];
     __shared__ float red[4][NQ];
@@ -442,31 +446,46 @@ __global__ void __launch_bounds__(CNT, 1) ca_fwd_kernel(const __grid_constant__ 
         tma_prefetch_desc(&tmW);
         tma_prefetch_desc(&tmKV);
     }
-    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    if (warp == 0) tmem_alloc(&tmem_slot, 256);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = tmem_slot;
-    constexpr uint32_t ST = 64, OT = 256, QT = 320, YT = 352;
+    constexpr uint32_t ST = 0, OT = 192, QT = 0, YT = 0;   // the projection accumulators alias the score columns
+    // ring items in consumption order: 0 Wq | 1 .. nch K chunks | nch+1 .. 2 nch V chunks | 2 nch + 1 Wout ; slot = item & 1
+    const int IT_K = 1, IT_V = 1 + nch, IT_WO = 1 + 2 * nch;
+    auto slot_addr = [&](int item) { return sbase + F_OFF_RING + (uint32_t)(item & 1) * 2 * LTILE; };
+    auto wait_item = [&](int item) { mbar_wait(&bar[FB_FULL0 + (item & 1)], (uint32_t)((item >> 1) & 1)); };
+    auto free_item = [&](int item) { mma_commit(&bar[FB_EMPTY0 + (item & 1)]); };   // when the MMAs issued so far have completed
 
-    auto load_w = [&](int row, int bi) {
-        mbar_arrive_expect_tx(&bar[bi], 2 * LTILE);
-        tma_tile_2d(sbase + F_OFF_W, &tmW, 0, row, &bar[bi]);
-        tma_tile_2d(sbase + F_OFF_W + LTILE, &tmW, 64, row, &bar[bi]);
-    };
-    auto load_kv = [&](int j, int col, int bi) {
-        mbar_arrive_expect_tx(&bar[bi + j], 2 * LTILE);
-        tma_tile_2d(sbase + F_OFF_KV + 2 * j * LTILE, &tmKV, col, (int)(krow0 + 128 * j), &bar[bi + j]);
-        tma_tile_2d(sbase + F_OFF_KV + (2 * j + 1) * LTILE, &tmKV, col + 64, (int)(krow0 + 128 * j), &bar[bi + j]);
-    };
-    if (tid == 0) load_w(p.w_row_q, FB_WQ);   // packed weights: written by a non-triggering kernel
+    pdl_trigger();
+    if (warp == 4) {
+        // ---- TMA producer ---------------------------------------------------------------------------------------------------
+        if (lane == 0) {
+            for (int item = 0; item <= IT_WO; ++item) {
+                const int s = item & 1;
+                if (item >= 2) mbar_wait(&bar[FB_EMPTY0 + s], (uint32_t)(((item >> 1) & 1) ^ 1));
+                if (item == 1) pdl_wait();   // K | V come from preceding kernels of the chain (the packed weights do not)
+                const uint32_t dst = slot_addr(item);
+                mbar_arrive_expect_tx(&bar[FB_FULL0 + s], 2 * LTILE);
+                if (item == 0 || item == IT_WO) {
+                    const int row = item == 0 ? p.w_row_q : p.w_row_o;
+                    tma_tile_2d(dst, &tmW, 0, row, &bar[FB_FULL0 + s]);
+                    tma_tile_2d(dst + LTILE, &tmW, 64, row, &bar[FB_FULL0 + s]);
+                } else {
+                    const bool isv = item >= IT_V;
+                    const int j = isv ? item - IT_V : item - IT_K;
+                    const int col = p.kv_col0 + (isv ? 128 : 0);
+                    tma_tile_2d(dst, &tmKV, col, (int)(krow0 + 128 * j), &bar[FB_FULL0 + s]);
+                    tma_tile_2d(dst + LTILE, &tmKV, col + 64, (int)(krow0 + 128 * j), &bar[FB_FULL0 + s]);
+                }
+            }
+        }
+    } else {
     // Qblk starts as zeros (the off-diagonal blocks stay zero)
     for (int i = tid; i < LTILE / 16; i += CNT) reinterpret_cast<uint4*>(smem + F_OFF_QB)[i] = make_uint4(0u, 0u, 0u, 0u);
-    pdl_trigger();
-    pdl_wait();   // K | V and the residual stream come from preceding kernels of the chain
-    if (tid == 0)
-        for (int j = 0; j < nch; ++j) load_kv(j, p.kv_col0, FB_K0);
     const uint64_t dseed = DROP ? p.drop.resolve() : 0ull;
+    pdl_wait();   // the residual stream comes from the preceding kernel of the chain
 
     // ---- LN2 of the T rows (warp per row, lane = 4 features) -> B operand [t][k] ------------------------------------------
     {
@@ -497,13 +516,14 @@ __global__ void __launch_bounds__(CNT, 1) ca_fwd_kernel(const __grid_constant__ 
     }
     fence_proxy_async_smem();
     tc_fence_before_sync();
-    __syncthreads();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     // ---- Q^T[n][t] = Wq[n][:] . xn[t][:] ---------------------------------------------------------------------------------
     const uint32_t id16 = instr_desc_bf16(128, 16);
     if (tid == 0) {
         tc_fence_after_sync();
-        mbar_wait(&bar[FB_WQ], 0);
-        mma_k_tiles(tmem + QT, sbase + F_OFF_W, LTILE, sbase + F_OFF_XB, XB_TILE, id16, 2, false);
+        wait_item(0);
+        mma_k_tiles(tmem + QT, slot_addr(0), LTILE, sbase + F_OFF_XB, XB_TILE, id16, 2, false);
+        free_item(0);
         mma_commit(&bar[FB_Q]);
     }
     __syncwarp();
@@ -512,8 +532,6 @@ __global__ void __launch_bounds__(CNT, 1) ca_fwd_kernel(const __grid_constant__ 
         float q[16];
         mbar_wait(&bar[FB_Q], 0);
         tc_fence_after_sync();
-        if (tid == 0) load_w(p.w_row_o, FB_WO);   // the Q projection has consumed the weight slot
-        __syncwarp();
         ld_lane16(tmem, warp, QT, q);
         const int h = tid >> 5;
 #pragma unroll
@@ -525,18 +543,17 @@ __global__ void __launch_bounds__(CNT, 1) ca_fwd_kernel(const __grid_constant__ 
     }
     fence_proxy_async_smem();
     tc_fence_before_sync();
-    __syncthreads();
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // Qblk complete; Q^T columns consumed
     // ---- S^T chunks ------------------------------------------------------------------------------------------------------
     const uint32_t id64 = instr_desc_bf16(128, NQ);
     if (tid == 0) {
         tc_fence_after_sync();
         for (int j = 0; j < nch; ++j) {
-            mbar_wait(&bar[FB_K0 + j], 0);
-            mma_k_tiles(tmem + ST + NQ * j, sbase + F_OFF_KV + 2 * j * LTILE, LTILE, sbase + F_OFF_QB, QB_TILE, id64, 2, false);
+            wait_item(IT_K + j);
+            mma_k_tiles(tmem + ST + NQ * j, slot_addr(IT_K + j), LTILE, sbase + F_OFF_QB, QB_TILE, id64, 2, false);
+            free_item(IT_K + j);
         }
         mma_commit(&bar[FB_S]);
-        mbar_wait(&bar[FB_S], 0);     // every K tile has been read: the V tiles take their place
-        for (int j = 0; j < nch; ++j) load_kv(j, p.kv_col0 + 128, FB_V0);
     }
     __syncwarp();
     mbar_wait(&bar[FB_S], 0);
@@ -559,30 +576,31 @@ __global__ void __launch_bounds__(CNT, 1) ca_fwd_kernel(const __grid_constant__ 
         const float m = warp_reduce32_cols<true>(mx, lane);
         red[warp][32 * g + lane] = m;
     }
-    __syncthreads();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     if (tid < NQ) fin_max[tid] = fmaxf(fmaxf(red[0][tid], red[1][tid]), fmaxf(red[2][tid], red[3][tid])) * sc;
-    __syncthreads();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    red[warp][lane] = 0.f;        // from here on: this lane's running column sums of its warp's keys (one owner per entry, fixed
+    red[warp][32 + lane] = 0.f;   // order of additions: results are bit-reproducible)
+    // probabilities chunk by chunk: P^T_j -> buffer j & 1 (buffer 0 = Qblk's place: every score MMA has completed), its
+    // O^T += V_j^T P^T_j issued right away; the column sums of the three chunks meet in shared memory
+    const uint32_t idPV = instr_desc_bf16(128, NQ, 1, 1);
 #pragma unroll 1
-    for (int g = 0; g < 2; ++g) {
-        float mxs[32], sum[32];
+    for (int j = 0; j < nch; ++j) {
+        uint8_t* Pb = smem + ((j & 1) ? F_OFF_P1 : F_OFF_QB);
+        if (j >= 2) { mbar_wait(&bar[FB_PD0 + (j & 1)], (uint32_t)(((j >> 1) - 1) & 1)); }   // the MMAs that read this buffer are done
+        const int m = 128 * j + tid;
+        const bool kv = m < M;
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+            float s[32], mxs[32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float4 t4 = reinterpret_cast<const float4*>(fin_max)[8 * g + i];
-            mxs[4 * i] = t4.x; mxs[4 * i + 1] = t4.y; mxs[4 * i + 2] = t4.z; mxs[4 * i + 3] = t4.w;
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) sum[i] = 0.f;
-        for (int j = 0; j < nch; ++j) {
-            float s[32];
-            ld_lane32(tmem, warp, ST + NQ * j + 32 * g, s);
-            const int m = 128 * j + tid;
-            const bool kv = m < M;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float e = kv ? ex2_approx(fmaf(s[i], sc, -mxs[i])) : 0.f;
-                sum[i] += e;
-                s[i] = e;
+            for (int i = 0; i < 8; ++i) {
+                const float4 t4 = reinterpret_cast<const float4*>(fin_max)[8 * g + i];
+                mxs[4 * i] = t4.x; mxs[4 * i + 1] = t4.y; mxs[4 * i + 2] = t4.z; mxs[4 * i + 3] = t4.w;
             }
+            ld_lane32(tmem, warp, ST + NQ * j + 32 * g, s);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { s[i] = kv ? ex2_approx(fmaf(s[i], sc, -mxs[i])) : 0.f; mxs[i] = s[i]; }
             if (DROP && kv) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
@@ -592,37 +610,35 @@ __global__ void __launch_bounds__(CNT, 1) ca_fwd_kernel(const __grid_constant__ 
                                               p.drop.inv_keep);
                 }
             }
-            // row `tid` of the [128 keys][64] P^T tile: chunks 4 g .. 4 g + 3
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-                *reinterpret_cast<uint4*>(smem + F_OFF_P + j * LTILE + sw128_chunk_off(tid, 4 * g + c)) = pack8_bf16(s + 8 * c);
+            for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(Pb + sw128_chunk_off(tid, 4 * g + c)) = pack8_bf16(s + 8 * c);
+            const float sm = warp_reduce32_cols<false>(mxs, lane);   // sums of the UNdropped probabilities
+            red[warp][32 * g + lane] += sm;
         }
-        const float sm = warp_reduce32_cols<false>(sum, lane);
-        red[warp][32 * g + lane] = sm;
-    }
-    fence_proxy_async_smem();
-    tc_fence_before_sync();
-    __syncthreads();
-    if (tid < NQ) {
-        const float sum = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
-        fin_inv[tid] = 1.0f / sum;
-        const int h = tid >> 4, t = tid & 15;
-        if (t < T && p.lse_save) p.lse_save[((long long)b * CA_H + h) * Tf + t0 + t] = fin_max[tid] + log2f(sum);
-    }
-    // ---- O^T[c][(h,t)] = sum_m V[m][c] P^T[m][(h,t)] -------------------------------------------------------------------------
-    if (tid == 0) {
-        tc_fence_after_sync();
-        const uint32_t idesc = instr_desc_bf16(128, NQ, 1, 1);
-        for (int j = 0; j < nch; ++j) {
-            mbar_wait(&bar[FB_V0 + j], 0);
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid == 0) {
+            tc_fence_after_sync();
+            wait_item(IT_V + j);
             const int ks = min(8, (M - 128 * j + 15) >> 4);   // keys beyond M carry zero probabilities
             for (int k = 0; k < ks; ++k)
-                mma_bf16_ss(tmem + OT, smem_desc_mn_sw128(sbase + F_OFF_KV + 2 * j * LTILE, LTILE, 1024) + 128 * (uint64_t)k,
-                            smem_desc_mn_sw128(sbase + F_OFF_P + j * LTILE, 1024, 1024) + 128 * (uint64_t)k, idesc, (j > 0 || k > 0) ? 1u : 0u);
+                mma_bf16_ss(tmem + OT, smem_desc_mn_sw128(slot_addr(IT_V + j), LTILE, 1024) + 128 * (uint64_t)k,
+                            smem_desc_mn_sw128(smem_u32(Pb), 1024, 1024) + 128 * (uint64_t)k, idPV, (j > 0 || k > 0) ? 1u : 0u);
+            free_item(IT_V + j);
+            mma_commit(&bar[FB_PD0 + (j & 1)]);
+            if (j == nch - 1) mma_commit(&bar[FB_O]);
         }
-        mma_commit(&bar[FB_O]);
+        __syncwarp();
     }
-    __syncthreads();   // fin_inv visible
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // every warp's column sums are complete
+    if (tid < NQ) {
+        const float sum = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+        const int h = tid >> 4, t = tid & 15;
+        if (t < T && p.lse_save) p.lse_save[((long long)b * CA_H + h) * Tf + t0 + t] = fin_max[tid] + log2f(sum);
+        fin_inv[tid] = 1.0f / sum;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     // residual rows of this thread's column: issued ahead of the waits
     float xr[TP];
 #pragma unroll
@@ -642,12 +658,12 @@ __global__ void __launch_bounds__(CNT, 1) ca_fwd_kernel(const __grid_constant__ 
     }
     fence_proxy_async_smem();
     tc_fence_before_sync();
-    __syncthreads();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     // ---- Y^T[n][t] = Wout[n][:] . attn[t][:] ; y = x + Drop(Y + b) ----------------------------------------------------------
     if (tid == 0) {
         tc_fence_after_sync();
-        mbar_wait(&bar[FB_WO], 0);
-        mma_k_tiles(tmem + YT, sbase + F_OFF_W, LTILE, sbase + F_OFF_XB, XB_TILE, id16, 2, false);
+        wait_item(IT_WO);
+        mma_k_tiles(tmem + YT, slot_addr(IT_WO), LTILE, sbase + F_OFF_XB, XB_TILE, id16, 2, false);
         mma_commit(&bar[FB_Y]);
     }
     __syncwarp();
@@ -667,9 +683,10 @@ __global__ void __launch_bounds__(CNT, 1) ca_fwd_kernel(const __grid_constant__ 
             }
         }
     }
+    }   // warps 0-3
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 512);
+    if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
 // =====================================================================================================================
@@ -1116,9 +1133,10 @@ int launch_ca_fwd(const CUtensorMap& tmW, const CUtensorMap& tmKV, const CaFwdPa
     static bool configured = false;
     if (!configured) {
         SD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
+        SD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));   // two CTAs per SM
         configured = true;
     }
-    SD_CUDA(launch_chain(kernel, dim3(p.B * p.groups), dim3(CNT), F_SMEM, st, tmW, tmKV, p));
+    SD_CUDA(launch_chain(kernel, dim3(p.B * p.groups), dim3(F_NT), F_SMEM, st, tmW, tmKV, p));
     return SD_OK;
 }
 template <bool DROP>
