@@ -120,12 +120,12 @@ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) 
 // cuTensorMapEncodeTiled is a DRIVER call: it fails with CUDA_ERROR_INVALID_CONTEXT when no context is bound to the calling
 // thread from the driver API's point of view — observed when another library (cuDNN through PyTorch) ran between two calls
 // into this one and no kernel of this library's own runtime instance had been launched on the thread yet.  Entry points that
-// encode tensor maps bind the runtime's primary context first (two sub-microsecond runtime calls).
+// encode tensor maps bind the runtime's primary context first (two sub-microsecond runtime calls; both are legal inside a
+// stream capture — cudaFree is not, so the classic cudaFree(0) idiom is not used here).
 static inline void bind_primary_context() {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaSetDevice(dev);
-    cudaFree(nullptr);
 }
 
 // ---- programmatic dependent launch (sd_set_pdl) ----------------------------------------------------------------------

@@ -36,8 +36,6 @@ inline EncodeTiledFn tensor_map_encoder() {
     static bool tried = false;
     if (!tried) {
         tried = true;
-        cudaFree(nullptr);   // the driver call below needs this runtime's context bound to the thread (CUDA_ERROR_INVALID_CONTEXT
-                             // when a tensor-map encode is the very first call into the library)
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&

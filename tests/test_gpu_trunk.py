@@ -524,3 +524,36 @@ print("ok")
     for which in ("wgrad", "ds", "stem"):
         r = subprocess.run([sys.executable, "-c", code, which], capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and "ok" in r.stdout, (which, r.stdout[-500:], r.stderr[-1500:])
+
+
+def test_tensor_map_kernels_inside_cuda_graph_capture():
+    """Every TMA-fed trunk entry point must be capturable (the training step is one CUDA graph): no call that is illegal during
+    stream capture on their host paths (a cudaFree(0) there once invalidated the capture of the whole step)."""
+    from soccerdiffusion_b200 import ops
+    from soccerdiffusion_b200.ml.model.encoder import trunk as T
+
+    cl = torch.channels_last
+    torch.manual_seed(0)
+    x = torch.randn(2, 64, 16, 16, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=cl)
+    dy = torch.randn(2, 64, 16, 16, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=cl)
+    dyd = torch.randn(2, 128, 8, 8, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=cl)
+    wb = torch.randn(128, 64, device="cuda", dtype=torch.bfloat16)
+    img = torch.randn(2, 3, 64, 64, device="cuda")
+    w7 = torch.randn(64, 3, 7, 7, device="cuda") * 0.05
+    dW, dx = torch.zeros(64, 64, 3, 3, device="cuda"), torch.zeros_like(x)
+
+    def run():
+        ops.conv3x3_wgrad_c64(x, dy, dW, 2, 16, 16)
+        ops.conv1x1s2_dgrad(dyd, wb, dx, 2, 16, 16, 64, 128)
+        return T._stem_conv_s2d_raw(img, w7)
+
+    want = run().clone()
+    want_dW, want_dx = dW.clone(), dx.clone()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = run()
+    dW.zero_(); dx.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, want) and torch.equal(dW, want_dW) and torch.equal(dx, want_dx)
