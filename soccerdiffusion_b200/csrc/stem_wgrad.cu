@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(NT, 1) stem_wgrad_tma_kernel(const __grid_cons
 // BatchNorm statistics, bf16, one 128-byte NHWC row per thread through a swizzled staging block).
 constexpr int RING = 8;   // input-row tiles in flight
 constexpr int NACC = 4;   // accumulator slots of 128 TMEM columns
+constexpr bool kDirectStore = false;  // A/B: epilogue stores straight from registers (true) or through the swizzled staging block
 constexpr int FNT = 384;  // warp 0 producer, warp 1 MMA issuer, warps 4-7 / 8-11: epilogue of channels 0-31 / 32-63
 
 // the CTA's output rows [r_begin, r_end) as windows of consecutive rows of one image
@@ -406,17 +407,26 @@ __global__ void __launch_bounds__(FNT, 1) stem_fprop_tma_kernel(const __grid_con
 #pragma unroll
                     for (int c = 0; c < 32; ++c) { s1[c] += v0[c]; s2[c] = fmaf(v0[c], v0[c], s2[c]); }
                 }
+                if (kDirectStore) {
+                    // this thread's 32 channels = 64 contiguous bytes of the NHWC row: four 16-byte stores, no staging, no barriers
+                    if (row < WO) {
+                        uint4* dst = y + ((r_begin + ci) * WO + row) * 8 + 4 * half;
 #pragma unroll
-                for (int c8 = 0; c8 < 4; ++c8)
-                    *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 * half + c8) ^ (lane & 7)) << 4)) = pack8_bf16(v0 + 8 * c8);
-                asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");   // the two warps of this pixel group
-                uint4* dst = y + ((r_begin + ci) * WO + q * 32) * 8;
+                        for (int c8 = 0; c8 < 4; ++c8) dst[c8] = pack8_bf16(v0 + 8 * c8);
+                    }
+                } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int g = (4 * half + j) * 32 + lane, pr = g >> 3, c = g & 7;   // chunk g of the group's block: pixel pr, chunk c
-                    if (q * 32 + pr < WO) dst[g] = *reinterpret_cast<const uint4*>(stg + pr * 128 + ((c ^ (pr & 7)) << 4));
+                    for (int c8 = 0; c8 < 4; ++c8)
+                        *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 * half + c8) ^ (lane & 7)) << 4)) = pack8_bf16(v0 + 8 * c8);
+                    asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");   // the two warps of this pixel group
+                    uint4* dst = y + ((r_begin + ci) * WO + q * 32) * 8;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int g = (4 * half + j) * 32 + lane, pr = g >> 3, c = g & 7;   // chunk g of the group's block: pixel pr, chunk c
+                        if (q * 32 + pr < WO) dst[g] = *reinterpret_cast<const uint4*>(stg + pr * 128 + ((c ^ (pr & 7)) << 4));
+                    }
+                    asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");   // staging block free for the next row
                 }
-                asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");   // staging block free for the next row
             }
             u = u0 + (w.ho_b - w.ho_a + 2);
         }
