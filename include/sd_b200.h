@@ -307,6 +307,9 @@ int sd_pack_weights_bf16(const sd_pack_args* args, int n_segments, void* stream)
  * attention block), xn1/attn/xn2/hact_save bf16 [B*S][128] (LN1(x), attention output, LN2(x1), hidden activation). */
 #define SD_LAYER_SA 1  /* the self-attention block  x1 = x + Drop(OutProj(MHA(LN1 x))) */
 #define SD_LAYER_FFN 2 /* the feed-forward block    y = x1 + Drop(W2 Drop(GELU(W1 LN2 x1))) */
+#define SD_LAYER_FFN_FIRST 4 /* with SA | FFN, inference only: the feed-forward block (w_row_ffn, l*_b, n2_*) runs BEFORE the attention
+                              * block (w_row0, in_b, out_b, n1_*) - the feed-forward half of decoder layer l and the self-attention
+                              * half of layer l+1 as one launch */
 typedef struct sd_enc_layer_desc {
     const float* x; float* y;
     int B, S, H;

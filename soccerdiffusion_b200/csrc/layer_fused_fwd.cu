@@ -56,7 +56,10 @@ struct EncFwdParams {
 
 // SA: run the self-attention block; FFN: run the feed-forward block (an encoder layer is both; a decoder layer runs the
 // two halves as separate launches around its cross-attention block)
-template <bool DROP, bool SA, bool FFN>
+// FFN_FIRST (inference, SA && FFN): the feed-forward block runs BEFORE the attention block, each with its own weights — the
+// feed-forward half of decoder layer l fused with the self-attention half of layer l+1 (one kernel boundary less per layer in
+// the tensor-core sampler's latency-bound chain)
+template <bool DROP, bool SA, bool FFN, bool FFN_FIRST = false>
 __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const EncFwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar[NBAR];
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
         tma_tile_2d(dst + LTILE, &tmW, 64, row, &bar[BW0 + mi]);
     };
     if (tid == 0) {
-        if (SA) { load_w(0); load_w(1); } else { load_w(4); load_w(5); }   // packed weights: written by a non-triggering kernel
+        if (SA && !FFN_FIRST) { load_w(0); load_w(1); } else { load_w(4); load_w(5); }   // packed weights: written by a non-triggering kernel
     }
     pdl_trigger();
     pdl_wait();   // the residual stream below comes from the preceding kernel of the chain
@@ -117,6 +120,9 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
         for (int j = 0; j < 32; ++j) xr[j] = 0.f;
     }
     const uint32_t id128 = instr_desc_bf16(128, 128);
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph) {   // two phases in compile-time order: attention then feed-forward, or the reverse
+    if ((ph == 0) != FFN_FIRST) {
     if constexpr (SA) {
     {
         float mean, rstd, v[32], ga[32], be[32];
@@ -177,7 +183,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
         const float bv = __ldg(p.in_b + 256 + r);
         mbar_wait(&bar[BV], 0);
         tc_fence_after_sync();
-        if (FFN && tid == 0) load_w(4);   // slot A drained by the V^T MMAs
+        if (FFN && !FFN_FIRST && tid == 0) load_w(4);   // slot A drained by the V^T MMAs
         __syncwarp();
         ld_acc32(tmem, L, ACC2, v);   // row = feature r, columns = tokens
 #pragma unroll
@@ -284,7 +290,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
         ldg32(p.out_b + c0, b);
         mbar_wait(&bar[BOUT], 0);
         tc_fence_after_sync();
-        if (FFN && tid == 0) load_w(5);   // slot B drained by the out-projection
+        if (FFN && !FFN_FIRST && tid == 0) load_w(5);   // slot B drained by the out-projection
         __syncwarp();
         ld_acc32(tmem, L, ACC0, v);
 #pragma unroll
@@ -293,7 +299,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
             if (DROP) t *= dropout_scale(dseed, p.drop.stream + 1, (uint64_t)goff + j, p.drop.thresh, p.drop.inv_keep);
             xr[j] = rv ? xr[j] + t : 0.f;
         }
-        float* x1_dst = FFN ? p.x1_save : p.y;   // attention block alone: x1 is the output
+        float* x1_dst = (FFN && !FFN_FIRST) ? p.x1_save : p.y;   // attention block alone or last: its result is the output
         if (rv && x1_dst) {
             float4* g = reinterpret_cast<float4*>(x1_dst + goff);
 #pragma unroll
@@ -301,6 +307,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
         }
     }
     }   // SA
+    } else {
     if constexpr (FFN) {
     {
         float v[32], b[32];
@@ -329,6 +336,8 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
         ldg32(p.l1_b + c0, b);
         mbar_wait(&bar[BF1], 0);
         tc_fence_after_sync();
+        if (FFN_FIRST && tid == 0) load_w(0);   // slot A drained by FC1: the attention block's Wq
+        __syncwarp();
         ld_acc32(tmem, L, ACC1, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -353,8 +362,13 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
         ldg32(p.l2_b + c0, b);
         mbar_wait(&bar[BF2], 0);
         tc_fence_after_sync();
+        if (FFN_FIRST && tid == 0) load_w(1);   // slot B drained by FC2: the attention block's Wk
+        __syncwarp();
         ld_acc32(tmem, L, ACC0, v);
-        if (rv) {
+        if (FFN_FIRST) {   // the attention block follows: the residual stream stays in registers
+#pragma unroll
+            for (int j = 0; j < 32; ++j) xr[j] = rv ? xr[j] + (v[j] + b[j]) : 0.f;
+        } else if (rv) {
             float4* g = reinterpret_cast<float4*>(p.y + goff);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -367,6 +381,8 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
         }
     }
     }   // FFN
+    }
+    }   // phases
     tc_fence_before_sync();
     __syncthreads();
     if (L.warp == 0) tmem_dealloc(tmem, 512);
@@ -415,9 +431,9 @@ extern "C" int sd_enc_layer_supported(int d, int ff, int S, int H) {
 }
 
 namespace {
-template <bool DROP, bool SA, bool FFN>
+template <bool DROP, bool SA, bool FFN, bool FFN_FIRST = false>
 int launch_fwd(const CUtensorMap& tmW, const EncFwdParams& p, int tiles, cudaStream_t st) {
-    auto kernel = enc_layer_fwd_kernel<DROP, SA, FFN>;
+    auto kernel = enc_layer_fwd_kernel<DROP, SA, FFN, FFN_FIRST>;
     static bool configured = false;   // one flag per instantiation
     if (!configured) {
         SD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN));
@@ -431,8 +447,11 @@ int launch_fwd(const CUtensorMap& tmW, const EncFwdParams& p, int tiles, cudaStr
 extern "C" int sd_enc_layer_fwd(const sd_enc_layer_desc* d, void* stream) {
     if (!d || !d->x || !d->y || !d->w_packed) return SD_ERR_BAD_ARG;
     const int blocks = d->blocks == 0 ? (SD_LAYER_SA | SD_LAYER_FFN) : d->blocks;
-    const bool sa = (blocks & SD_LAYER_SA) != 0, ffn = (blocks & SD_LAYER_FFN) != 0;
-    if ((blocks & ~(SD_LAYER_SA | SD_LAYER_FFN)) != 0) return SD_ERR_BAD_ARG;
+    const bool sa = (blocks & SD_LAYER_SA) != 0, ffn = (blocks & SD_LAYER_FFN) != 0, ffn_first = (blocks & SD_LAYER_FFN_FIRST) != 0;
+    if ((blocks & ~(SD_LAYER_SA | SD_LAYER_FFN | SD_LAYER_FFN_FIRST)) != 0) return SD_ERR_BAD_ARG;
+    // feed-forward first: inference only (no dropout, no saves), both blocks present
+    if (ffn_first && (!sa || !ffn || d->dropout_p > 0.f || d->x1_save || d->xn1_save || d->attn_save || d->xn2_save || d->hact_save))
+        return SD_ERR_BAD_ARG;
     if (sa && (!d->in_b || !d->out_b || !d->n1_w || !d->n1_b)) return SD_ERR_BAD_ARG;
     if (ffn && (!d->l1_b || !d->l2_b || !d->n2_w || !d->n2_b)) return SD_ERR_BAD_ARG;
     if (d->B <= 0) return SD_OK;
@@ -458,6 +477,7 @@ extern "C" int sd_enc_layer_fwd(const sd_enc_layer_desc* d, void* stream) {
     const int tiles = ceil_div(d->B, p.spt);
     cudaStream_t st = (cudaStream_t)stream;
     const bool drop = p.drop.thresh != 0;
+    if (ffn_first) return launch_fwd<false, true, true, true>(tmW, p, tiles, st);
     if (sa && ffn) return drop ? launch_fwd<true, true, true>(tmW, p, tiles, st) : launch_fwd<false, true, true>(tmW, p, tiles, st);
     if (sa) return drop ? launch_fwd<true, true, false>(tmW, p, tiles, st) : launch_fwd<false, true, false>(tmW, p, tiles, st);
     return drop ? launch_fwd<true, false, true>(tmW, p, tiles, st) : launch_fwd<false, false, true>(tmW, p, tiles, st);

@@ -462,9 +462,22 @@ def ddim_sample_tc(B: int, T: int, Mm: int, H: int, pe, x_T, mem, tok, emb_w, em
             if s == 0 or not glue:
                 ops.bcast_row_bf16(kv_all, Mm, Mm - 1, B, kv_tok.data_ptr() + 2 * s * 256 * L, 256 * L)
                 ops.gemm(x, J, MK, emb_w, J, NK, h, d, Mq, d, J, precision=cfg.precision, bias=emb_b, pe=pe, pe_period=T)
+            # per layer: self-attention | cross-attention | feed-forward, with the feed-forward half of layer l and the
+            # self-attention half of layer l+1 as ONE launch (they are adjacent row-tile kernels): 2 L + 1 launches, not 3 L
             for l in range(L):
-                P = layer_params[l * DEC_PARAMS_PER_LAYER: (l + 1) * DEC_PARAMS_PER_LAYER]
-                h, _ = _dec_layer_fused_fwd(h, None, B, T, Mm, H, P, wp, l, cfg, False, kv_all)
+                (sa_in_w, sa_in_b, sa_out_w, sa_out_b, ca_in_w, ca_in_b, ca_out_w, ca_out_b, l1_w, l1_b, l2_w, l2_b, n1_w, n1_b, n2_w, n2_b,
+                 n3_w, n3_b) = layer_params[l * DEC_PARAMS_PER_LAYER: (l + 1) * DEC_PARAMS_PER_LAYER]
+                r0 = l * ops.DEC_ROWS_PER_LAYER
+                if l == 0:
+                    ops.enc_layer_fwd(h, h, B, T, H, wp, r0, sa_in_b, sa_out_b, None, None, n1_w, n1_b, None, None, blocks=ops.LAYER_SA)
+                ops.ca_block_fwd(h, h, B, T, Mm, wp, r0 + 512, r0 + 896, kv_all, 256 * l, ca_in_b, ca_out_b, n2_w, n2_b)
+                if l + 1 < L:
+                    nx = layer_params[(l + 1) * DEC_PARAMS_PER_LAYER: (l + 2) * DEC_PARAMS_PER_LAYER]
+                    ops.enc_layer_fwd(h, h, B, T, H, wp, r0 + ops.DEC_ROWS_PER_LAYER, nx[1], nx[3], l1_b, l2_b, nx[12], nx[13], n3_w, n3_b,
+                                      blocks=ops.LAYER_SA | ops.LAYER_FFN | ops.LAYER_FFN_FIRST, w_row_ffn=r0 + 1024)
+                else:
+                    ops.enc_layer_fwd(h, h, B, T, H, wp, r0, None, None, l1_b, l2_b, None, None, n3_w, n3_b, blocks=ops.LAYER_FFN,
+                                      w_row_ffn=r0 + 1024)
             if glue:
                 last = s + 1 == S
                 ops.ddim_glue(h, fc_w, fc_b, x, x_next, None if trace is None else trace[s], coefs[s],

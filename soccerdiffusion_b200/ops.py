@@ -433,7 +433,7 @@ def enc_layer_supported(d: int, ff: int, S: int, H: int) -> bool:
     return bool(_lib.lib().sd_enc_layer_supported(d, ff, S, H))
 
 
-LAYER_SA, LAYER_FFN = 1, 2   # sd_enc_layer_desc.blocks
+LAYER_SA, LAYER_FFN, LAYER_FFN_FIRST = 1, 2, 4   # sd_enc_layer_desc.blocks
 
 
 def _dp(t):
@@ -456,10 +456,11 @@ def enc_layer_fwd(x, y, B, S, H, w_packed, w_row0, in_b, out_b, l1_b, l2_b, n1_w
         d.dropout_p, d.dropout_seed, d.dropout_stream = dropout
     d.blocks, d.w_row_ffn, d.dropout_stream_ffn = blocks, w_row_ffn, dropout_stream_ffn
     M = B * S
-    sa, ffn = blocks in (0, LAYER_SA), blocks in (0, LAYER_FFN)
+    sa, ffn = blocks == 0 or bool(blocks & LAYER_SA), blocks == 0 or bool(blocks & LAYER_FFN)
     # algorithmic work: attention block 8 S d^2 + 4 S^2 d, feed-forward block 4 S d^2 per sample
     flops = B * ((8.0 * S * 128 * 128 + 4.0 * S * S * 128) * sa + 4.0 * S * 128 * 128 * ffn)
-    name = "fused_enc_layer_fwd" if blocks == 0 else ("fused_sa_block_fwd" if sa else "fused_ffn_block_fwd")
+    name = ("fused_enc_layer_fwd" if blocks == 0 else "fused_ffn_sa_blocks_fwd" if blocks & LAYER_FFN_FIRST else
+            "fused_sa_block_fwd" if sa else "fused_ffn_block_fwd")
     with _Timed(name, flops, M * 128 * (8.0 + (4.0 + 8.0 if saves is not None else 0.0)), f"[B{B} S{S} H{H}]"):
         check(_lib.lib().sd_enc_layer_fwd(C.byref(d), stream_ptr()), "sd_enc_layer_fwd")
     _count()
