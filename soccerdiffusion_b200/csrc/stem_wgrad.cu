@@ -256,6 +256,130 @@ __global__ void __launch_bounds__(NT, 1) stem_wgrad_tma_kernel(const __grid_cons
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
+// ---- paired variant: two patch tiles x two dy rows per instruction ---------------------------------------------------
+// The patch tile T[t] of packed-image row t serves filter row kh of output row t - kh.  One 128 x 128 x 16 instruction per 16
+// pixels covers all four filter rows:  A = (T[t], T[t+1]) (M = 128 = (a, j), the tiles adjacent in a ring),
+// B = (dy[t-2], dy[t]) (N = 128 = (b, co), two ring slots apart):  D[(a,j)][(b,co)] += sum_pixels T[t+a][.][j] dy[r_b][.][co]
+// = dW[kh = a + 2 (1 - b)][j][co], accumulated over t = 0 .. HO+1 of every image (dy rows outside the image arrive as zeros
+// from the 4-D tensor map).  Against the 64 x 256 x 16 form: 94 instead of 128 clk per 16 pixels (an M = 64 instruction costs
+// what an M = 128 one does) and 2.75 instead of 5 tile loads per output row (each tile is loaded once, plus the "shadow" copies
+// that keep pairs contiguous across the ring's wrap-around).
+constexpr int RT = 6, RD = 6;        // ring sizes (tiles in flight: the deeper the ring, the further the producer runs ahead)
+constexpr int PT_SLOTS = RT + 1;     // patch-tile ring + shadow of slot 0 behind the last slot
+constexpr int PD_SLOTS = RD + 2;     // dy ring + shadows of slots 0, 1 behind the last slot
+constexpr int PSTG = 16;      // stage-completion barriers
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+        "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__global__ void __launch_bounds__(NT, 1) stem_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmB4, float* __restrict__ dw,
+                                                                int Nimg, int HO, int WO, int Hp, int Wp) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_t[RT], full_d[RD], stage_done[PSTG], bar_done;
+    __shared__ uint32_t tmem_slot;
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int blk = WO * 128;
+    const uint32_t tbase = smem_u32(smem), dbase = tbase + PT_SLOTS * blk;
+    if (tid == 0) {
+        for (int i = 0; i < RT; ++i) mbar_init(&full_t[i], 1);
+        for (int i = 0; i < RD; ++i) mbar_init(&full_d[i], 1);
+        for (int i = 0; i < PSTG; ++i) mbar_init(&stage_done[i], 1);
+        mbar_init(&bar_done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, 128);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const int n0 = (int)((long long)Nimg * blockIdx.x / gridDim.x), n1 = (int)((long long)Nimg * (blockIdx.x + 1) / gridDim.x);
+    const int nst = HO + 2;            // stages per image
+    const int ntl = HO + 3, ndl = HO + 4;   // patch tiles / dy tiles per image
+
+    if (warp == 0 && lane == 0) {
+        // ---- producer: tiles in the order the stages first need them; a slot is refilled once the last stage that read its
+        //      previous tile has completed (stages complete in order: one running maximum of waited stages suffices)
+        int last_t[RT], last_d[RD];   // global stage of the last read of each slot's tile
+        for (int i = 0; i < RT; ++i) last_t[i] = -1;
+        for (int i = 0; i < RD; ++i) last_d[i] = -1;
+        int waited = -1;
+        auto wait_stage = [&](int g) {
+            if (g > waited) { mbar_wait(&stage_done[g % PSTG], (uint32_t)((g / PSTG) & 1)); waited = g; }
+        };
+        int yt = 0, wd = 0;            // global tile counters
+        for (int n = n0; n < n1; ++n) {
+            const int gbase = (n - n0) * nst;
+            int it = 0, id = 0;        // next patch / dy tile of this image
+            for (int t = 0; t < nst; ++t) {
+                while (it <= t + RT - 3 && it < ntl) {  // stage t reads T[t], T[t+1]; run ahead as far as the ring allows
+                    const int s = yt % RT;
+                    wait_stage(last_t[s]);
+                    const uint32_t bytes = (uint32_t)blk * (s == 0 ? 2u : 1u);
+                    mbar_arrive_expect_tx(&full_t[s], bytes);
+                    tma_load_2d(tbase + s * blk, &tmA, 0, (n * Hp + it) * Wp, &full_t[s]);
+                    if (s == 0) tma_load_2d(tbase + RT * blk, &tmA, 0, (n * Hp + it) * Wp, &full_t[s]);
+                    last_t[s] = gbase + min(it, nst - 1);
+                    ++it; ++yt;
+                }
+                while (id <= t + RD - 2 && id < ndl) {  // stage t reads dy tiles t (row t-2) and t+2 (row t)
+                    const int s = wd % RD;
+                    wait_stage(last_d[s]);
+                    const uint32_t bytes = (uint32_t)blk * (s < 2 ? 2u : 1u);
+                    mbar_arrive_expect_tx(&full_d[s], bytes);
+                    tma_load_4d(dbase + s * blk, &tmB4, 0, 0, id - 2, n, &full_d[s]);
+                    if (s < 2) tma_load_4d(dbase + (s + RD) * blk, &tmB4, 0, 0, id - 2, n, &full_d[s]);
+                    last_d[s] = gbase + min(id, nst - 1);
+                    ++id; ++wd;
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        const uint32_t idesc = instr_desc_bf16(128, 128, 1, 1);
+        const int ksteps = WO / 16;
+        int wt = 0, wdd = 0;           // tiles whose full barrier has been waited for
+        int g = 0;
+        for (int n = n0; n < n1; ++n) {
+            const int ybase = (n - n0) * ntl, zbase = (n - n0) * ndl;
+            for (int t = 0; t < nst; ++t, ++g) {
+                const int x = ybase + t, z = zbase + t;
+                while (wt <= x + 1) { mbar_wait(&full_t[wt % RT], (uint32_t)((wt / RT) & 1)); ++wt; }
+                while (wdd <= z + 2) { mbar_wait(&full_d[wdd % RD], (uint32_t)((wdd / RD) & 1)); ++wdd; }
+                tc_fence_after_sync();
+                const uint64_t da = smem_desc_mn_sw128(tbase + (x % RT) * blk, (uint32_t)blk, 1024);        // T[t], T[t+1]
+                const uint64_t db = smem_desc_mn_sw128(dbase + (z % RD) * blk, (uint32_t)(2 * blk), 1024);  // dy[t-2], dy[t]
+                for (int ks = 0; ks < ksteps; ++ks)
+                    mma_bf16_ss(tmem, da + (uint64_t)(128 * ks), db + (uint64_t)(128 * ks), idesc, (g > 0 || ks > 0) ? 1u : 0u);
+                mma_commit(&stage_done[g % PSTG]);
+            }
+        }
+        mma_commit(&bar_done);
+    }
+    __syncwarp();
+    if (n1 > n0 && warp < 4) {
+        mbar_wait(&bar_done, 0);
+        tc_fence_after_sync();
+        const int a = warp >> 1, j = (warp & 1) * 32 + lane;   // accumulator row = (a, j)
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+            float v[32];
+            tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+            const int b = c0 >> 6, kh = a + 2 * (1 - b);
+            float* dst = dw + (kh * 64 + j) * 64 + (c0 & 63);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) atomicAdd(dst + c, v[c]);
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
 // ---- conv1 forward (space-to-depth form) on the same TMA tensor map: y[p][c] = sum_j patch[p][j] * W[c][j] ------------
 // The patch tile of packed-image row t ([WO pixels][64], the very boxes the weight-gradient kernel loads, read here with
 // K-major descriptors) is the operand of output row t - kh for every filter row kh.  A tcgen05.mma of 128 x 64 x 16 costs
@@ -545,6 +669,32 @@ int launch_tma(const void* xs2d, const void* dy, float* dw, int N, int HO, int W
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
             usable = false;
             return SD_OK;
+        }
+    }
+    {   // paired kernel (SD_B200_STEM_WGRAD_PAIR=0 selects the 64 x 256 x 16 form below)
+        static int use_pair = -1;
+        if (use_pair < 0) { const char* e = getenv("SD_B200_STEM_WGRAD_PAIR"); use_pair = (e && e[0] == '0') ? 0 : 1; }
+        const size_t psmem = (size_t)(PT_SLOTS + PD_SLOTS) * WO * 128 + 1024;
+        if (use_pair && psmem <= 227 * 1024 - 512) {
+            CUtensorMap tmB4;
+            const cuuint64_t gdim[4] = {64, (cuuint64_t)WO, (cuuint64_t)HO, (cuuint64_t)N};
+            const cuuint64_t gstr[3] = {128, (cuuint64_t)WO * 128, (cuuint64_t)HO * WO * 128};
+            const cuuint32_t box[4] = {64, (cuuint32_t)WO, 1, 1};
+            const cuuint32_t estr[4] = {1, 1, 1, 1};
+            if (encode(&tmB4, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+                static size_t pconfigured = 0;
+                if (pconfigured < psmem && cudaFuncSetAttribute(stem_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                                (int)psmem) == cudaSuccess)
+                    pconfigured = psmem;
+                if (pconfigured >= psmem) {
+                    stem_wgrad_pair_kernel<<<min(148, N), NT, psmem, st>>>(tmA, tmB4, dw, N, HO, WO, Hp, Wp);
+                    SD_LAUNCH_CHECK();
+                    *done = true;
+                    return SD_OK;
+                }
+                cudaGetLastError();
+            }
         }
     }
     static size_t configured = 0;   // dynamic + static shared memory must stay within the 227 KB opt-in limit

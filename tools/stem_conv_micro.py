@@ -26,6 +26,10 @@ def main():
     y = torch.empty((frames, 64, 112, 112), device="cuda", dtype=torch.bfloat16, memory_format=torch.channels_last)
     t = timed(lambda: ops.stem_fprop(xp, w2, y, frames, 224, 224, sums=sums))
     tp = timed(lambda: ops.stem_pack_u8(img, xp, frames, 224, 224))
+    dy = torch.randn(frames, 112, 112, 64, device="cuda").to(torch.bfloat16)
+    dw = torch.empty(256, 64, device="cuda")
+    tw = timed(lambda: ops.stem_wgrad(xp, dy, dw, frames, 224, 224))
+    print(f"{frames} frames: conv1 weight gradient {tw:.3f} ms ({gf / tw:.0f} TF/s)  [SD_B200_STEM_WGRAD_PAIR={os.environ.get('SD_B200_STEM_WGRAD_PAIR', '1')}]")
     print(f"{frames} frames: conv1 forward + statistics {t:.3f} ms ({gf / t:.0f} TF/s, {(xp.numel() * 2 + y.numel() * 2) / t / 1e6:.0f} GB/s);  uint8 packing {tp:.3f} ms")
 
 
