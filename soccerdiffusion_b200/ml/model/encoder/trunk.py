@@ -163,6 +163,8 @@ def _bn(bn, x, residual=None, relu=True, fork=False):
 
 
 def _conv(conv, x):
+    if _trunk_conv_ok(conv, x):
+        return TrunkConv.apply(x, conv.weight, conv.stride[0], conv.padding[0])
     if _own_wgrad_c64(conv, x):
         return Conv3x3C64.apply(x, conv.weight)
     return F.conv2d(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
@@ -229,6 +231,83 @@ class Conv3x3C64(torch.autograd.Function):
             dw = torch.empty((64, 64, 3, 3), device=x.device, dtype=torch.float32)
             ops.conv3x3_wgrad_c64(x, dy, dw, n, H, W)
         return dx, dw
+
+
+class TrunkConv(torch.autograd.Function):
+    """A convolution of the trunk's residual stages (3x3 / 1x1, stride 1 / 2, no bias; torchvision resnet.py) for the bf16 path.
+    Forward: library call on the bf16 copy of the weight.  Backward: the data gradient on the current stream
+    (sd_conv1x1s2_dgrad_bf16 for the downsample convolutions, the library otherwise), the WEIGHT gradient
+    (sd_conv3x3_wgrad_c64_bf16 for layer1, the library otherwise) — when gradients are accumulated straight into the optimizer's
+    flat buffer (runtime.direct_grads) — on the side stream of runtime.wgrad_stream(): it is a leaf of the backward pass, so the
+    tensor-bound weight-gradient GEMMs overlap the HBM-bound BatchNorm backward kernels of the main chain; the optimizer /
+    all-reduce side joins through runtime.join_wgrad_stream()."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride: int, padding: int):
+        x = _cl(x)
+        wb = weight.detach().to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+        y = torch.ops.aten.convolution(x, wb, None, [stride, stride], [padding, padding], [1, 1], False, [0, 0], 1)
+        ctx.save_for_backward(x, wb)
+        ctx.conv = (stride, padding)
+        ctx.param = weight
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wb = ctx.saved_tensors
+        stride, padding = ctx.conv
+        weight = ctx.param
+        dy = _cl(dy)
+        n, Cin, H, W = x.shape
+        Cout, k = wb.shape[0], wb.shape[2]
+        args = ([stride, stride], [padding, padding], [1, 1], False, [0, 0], 1)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            if _OWN_DS_DGRAD and k == 1 and stride == 2 and padding == 0 and ops.conv1x1s2_dgrad_supported(H, W, Cin, Cout):
+                dx = torch.empty_like(x)
+                ops.conv1x1s2_dgrad(dy, wb.view(Cout, Cin), dx, n, H, W, Cin, Cout)
+            else:
+                dx = torch.ops.aten.convolution_backward(dy, x, wb, None, *args, [True, False, False])[0]
+        if ctx.needs_input_grad[1]:
+            own = (_OWN_WGRAD_C64 and k == 3 and stride == 1 and padding == 1 and Cin == 64 and Cout == 64
+                   and ops.conv3x3_wgrad_c64_supported(H, W))
+            g = weight.grad
+            direct = (runtime.direct_grads() and weight.is_leaf and g is not None and g.dtype == torch.float32 and g.is_contiguous()
+                      and g.shape == weight.shape)
+
+            def compute(into):
+                if own:
+                    out = into if into is not None else torch.empty((64, 64, 3, 3), device=x.device, dtype=torch.float32)
+                    ops.conv3x3_wgrad_c64(x, dy, out, n, H, W, accumulate=into is not None)
+                    return out
+                dwb = torch.ops.aten.convolution_backward(dy, x, wb, None, *args, [False, True, False])[1]
+                if into is not None:
+                    into.add_(dwb.reshape(into.shape))
+                    return into
+                return dwb.float().reshape(weight.shape)
+
+            if direct and runtime.wgrad_overlap():
+                cur = torch.cuda.current_stream()
+                side = runtime.wgrad_stream(x.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    compute(g)
+                for t in (dy, x, wb):
+                    t.record_stream(side)
+                runtime.mark_grad_written(weight)
+            elif direct:
+                compute(g)
+                runtime.mark_grad_written(weight)
+            else:
+                dw = compute(None)
+        return dx, dw, None, None
+
+
+def _trunk_conv_ok(conv, x) -> bool:
+    return (_TRUNK_CONV and torch.is_grad_enabled() and x.dtype == torch.bfloat16 and x.dim() == 4 and conv.bias is None
+            and conv.groups == 1 and conv.dilation == (1, 1) and conv.weight.dtype == torch.float32
+            and conv.kernel_size[0] == conv.kernel_size[1] and conv.stride[0] == conv.stride[1] and conv.padding[0] == conv.padding[1]
+            and (x.requires_grad or conv.weight.requires_grad))
 
 
 def _own_wgrad_c64(conv, x) -> bool:
@@ -351,6 +430,7 @@ def supported(encoder) -> bool:
     return ok and mp.kernel_size == 3 and mp.stride == 2 and mp.padding == 1 and isinstance(encoder.bn1, torch.nn.BatchNorm2d)
 
 
+_TRUNK_CONV = os.environ.get("SD_B200_TRUNK_CONV", "1") == "1"   # one autograd node per trunk convolution (split data / weight gradients)
 _OWN_WGRAD_C64 = os.environ.get("SD_B200_OWN_WGRAD_C64", "1") == "1"   # layer1 weight gradients on libsd_b200's implicit GEMM
 _OWN_DS_DGRAD = os.environ.get("SD_B200_OWN_DS_DGRAD", "1") == "1"   # downsample 1x1/s2 data gradient on libsd_b200's GEMM
 _BN_FORK = os.environ.get("SD_B200_BN_FORK", "1") == "1"   # twin block outputs: gradients summed inside the BN backward kernels
@@ -399,7 +479,10 @@ def resnet_trunk_bf16(encoder, images: torch.Tensor) -> torch.Tensor:
             identity = x_skip
             if blk.downsample is not None:
                 ds = blk.downsample[0]
-                ds_out = DownsampleConv1x1S2.apply(x_skip, ds.weight) if _own_ds_dgrad(ds, x_skip) else _conv(ds, x_skip)
+                if _trunk_conv_ok(ds, x_skip):
+                    ds_out = _conv(ds, x_skip)
+                else:
+                    ds_out = DownsampleConv1x1S2.apply(x_skip, ds.weight) if _own_ds_dgrad(ds, x_skip) else _conv(ds, x_skip)
                 identity = _bn(blk.downsample[1], ds_out, None, False)
             out = _bn(blk.bn1, _conv(blk.conv1, x_main), None, True)
             if isinstance(blk, BasicBlock):

@@ -109,6 +109,7 @@ class GraphedTrainStep:
             loss.backward()
         finally:
             runtime.set_direct_grads(prev)
+            runtime.join_wgrad_stream()                # weight gradients launched on the side stream (encoder/trunk.py: TrunkConv)
             if self.reducer is not None:
                 self.reducer.finish()                  # sum over ranks; the 1/world factor is the AdamW kernel's grad_scale
         self.opt.step_captured()

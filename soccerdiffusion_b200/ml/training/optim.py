@@ -141,6 +141,7 @@ class FusedAdamW(torch.optim.Optimizer):
     # ---- eager step ---------------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
+        runtime.join_wgrad_stream()   # weight gradients the trunk launched on its side stream (no-op when none are pending)
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -186,6 +187,7 @@ class FusedAdamW(torch.optim.Optimizer):
     def step_captured(self):
         """Device side (this is what a CUDA graph captures): advance the touched parameters' device step counters, then one
         sd_adamw_step_dev launch per run."""
+        runtime.join_wgrad_stream()
         for f in self._flat:
             if f is None:
                 continue

@@ -32,6 +32,9 @@ def allreduce_gradients(optimizer_or_tensors, group=None, average: bool = True):
     gradient tensors."""
     import torch.distributed as dist
 
+    from soccerdiffusion_b200 import runtime
+
+    runtime.join_wgrad_stream()
     if not (dist.is_available() and dist.is_initialized()):
         return
     world = dist.get_world_size(group)
@@ -88,12 +91,15 @@ class BucketedAllReduce:
     def _on_ready(self, tag: str):
         import torch.distributed as dist
 
+        from soccerdiffusion_b200 import runtime
+
         if tag != "trunk.layer3_onward" or self.early_done or self.split is None:
             return
         g = self.opt.flat_gradients()[0]
         cur = torch.cuda.current_stream()
         comm = self._stream()
         comm.wait_stream(cur)
+        runtime.join_wgrad_stream(comm, clear=False)   # layer3 / layer4 weight gradients run on the trunk's side stream
         with torch.cuda.stream(comm):
             dist.all_reduce(g[self.split:], op=dist.ReduceOp.SUM, group=self.group)
         self.early_done = True
@@ -105,6 +111,7 @@ class BucketedAllReduce:
         from soccerdiffusion_b200 import runtime
 
         runtime.set_grad_ready_callback(None)
+        runtime.join_wgrad_stream()
         cur = torch.cuda.current_stream()
         if self.early_done:
             g = self.opt.flat_gradients()[0]

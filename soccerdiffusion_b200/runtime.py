@@ -141,6 +141,42 @@ def side_streams(device, n: int):
     return lst[:n]
 
 
+# ---- weight gradients of the trunk's convolutions on a side stream ---------------------------------------------------------
+# In the backward pass the weight gradient of a convolution is a leaf: nothing downstream waits for it until the optimizer
+# (or the gradient all-reduce) reads it.  With direct gradient accumulation (below) the trunk launches them on ONE side stream:
+# tensor-bound weight-gradient GEMMs then run beside the HBM-bound BatchNorm backward kernels of the main chain.
+_wgrad_overlap = os.environ.get("SD_B200_WGRAD_OVERLAP", "1") == "1"
+_wgrad_streams: dict = {}
+_wgrad_pending: dict = {}
+
+
+def set_wgrad_overlap(on: bool):
+    global _wgrad_overlap
+    _wgrad_overlap = bool(on)
+
+
+def wgrad_overlap() -> bool:
+    return _wgrad_overlap and _direct_grads
+
+
+def wgrad_stream(device):
+    key = (device.type, device.index)
+    st = _wgrad_streams.get(key)
+    if st is None:
+        st = _wgrad_streams[key] = torch.cuda.Stream(device=device)
+    _wgrad_pending[key] = True
+    return st
+
+
+def join_wgrad_stream(waiter=None, clear: bool = True):
+    """``waiter`` (default: the current stream) waits for every weight gradient launched on the side stream so far."""
+    for key, pending in list(_wgrad_pending.items()):
+        if pending:
+            (waiter or torch.cuda.current_stream()).wait_stream(_wgrad_streams[key])
+            if clear:
+                _wgrad_pending[key] = False
+
+
 _direct_grads = False
 
 
