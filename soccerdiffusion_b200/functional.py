@@ -512,7 +512,8 @@ class DenoiserFn(torch.autograd.Function):
         fused = L > 0 and _fused_enc_ok(cfg, d, layer_params[8].shape[0], T, H)
         wp = _pack_dec_weights(layer_params, L, d) if fused else None
         mem_bf = kv_all = None
-        if fused and L <= ops.KV_MAX_LAYERS and ops.ca_block_supported(d, H, T, Mm):
+        # training (saves for the backward kernel): T <= 16; inference: T <= 64 through query-row groups
+        if fused and L <= ops.KV_MAX_LAYERS and (ops.ca_block_supported(d, H, T, Mm) if save else ops.ca_block_fwd_supported(d, H, T, Mm)):
             # the memory is not layer-normed and every layer reads it: ONE bf16 copy, ONE GEMM for the K | V of all layers
             mem_bf = _bf16((B * Mm, d), mem2)
             ops.cast_bf16(mem2, mem_bf)
