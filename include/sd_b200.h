@@ -359,7 +359,7 @@ int sd_wgrad_bf16(const sd_wgrad_job* jobs, int n_jobs, long long rows, void* st
 
 /* ---------------------------------------------------------------------------------------------
  * The decoder layer's cross-attention block, layer-fused on tcgen05 + TMA (bf16 mode; d_model = 128, 4 heads,
- * T <= 16 query tokens, memory length M <= 384).  Replaces, per decoder layer, LN2 -> q projection -> k/v projection
+ * T <= 64 query tokens in groups of <= 16, memory length M <= 384).  Replaces, per decoder layer, LN2 -> q projection -> k/v projection
  * of the memory -> nn.MultiheadAttention core -> out-projection + dropout + residual
  * (torch/nn/modules/transformer.py:1137-1139; ml/model/decoder.py:25-54) and its autograd.
  *
@@ -432,8 +432,8 @@ typedef struct sd_ca_block_desc {
     void* xn_save; void* q_save; void* attn_save; float* stats_save; float* lse_save;
     float dropout_p; unsigned long long dropout_seed; unsigned int dropout_stream;
 } sd_ca_block_desc;
-int sd_ca_block_supported(int d, int H, int T, int M);     /* forward with saves + backward: T <= 16 */
-int sd_ca_block_fwd_supported(int d, int H, int T, int M); /* forward without saves (inference): T <= 64, rows in groups of <= 16 */
+int sd_ca_block_supported(int d, int H, int T, int M);     /* forward + backward: d = 128, 4 heads, T <= 64 (query rows in groups of <= 16), M <= 384 */
+int sd_ca_block_fwd_supported(int d, int H, int T, int M); /* the same set (kept for callers that only run the forward) */
 int sd_ca_block_fwd(const sd_ca_block_desc* desc, void* stream);
 
 /* Backward of the block (data path): dy -> dx (fp32 [B*T][128], may alias), g1 = dy*mask and dq (bf16 [B*T][128], the G

@@ -706,6 +706,7 @@ struct CaBwdParams {
     const __nv_bfloat16 *q, *attn;
     const float *stats, *lse;
     int B, T, M;
+    int t0, Tg, dkv_accumulate;   // this launch's query-row group
     int w_row_q, w_row_o, kv_col0;
     const float* n_w;
     __nv_bfloat16 *g1, *dq, *dkv;   // g1, dq: [B*T][128]; dkv: the all-layer dK | dV matrix (row stride lddkv), same columns as kv
@@ -729,7 +730,10 @@ __global__ void __launch_bounds__(CNT, 1) ca_bwd_kernel(const __grid_constant__ 
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.x, T = p.T, M = p.M;
+    // one launch per query-row group (p.t0 .. p.t0 + T): groups of one sample add into the same dK | dV rows, so they run as
+    // consecutive launches, the later ones with p.dkv_accumulate
+    const int b = blockIdx.x, Tf = p.T, t0 = p.t0, T = min(p.Tg, Tf - t0), M = p.M;
+    const long long rowb = (long long)b * Tf + t0;
     const int nch = (M + 127) >> 7;
     const long long krow0 = (long long)b * M;
 
@@ -777,7 +781,7 @@ __global__ void __launch_bounds__(CNT, 1) ca_bwd_kernel(const __grid_constant__ 
     float dyr[TP];
 #pragma unroll
     for (int t = 0; t < TP; ++t) {
-        const long long e = ((long long)b * T + t) * 128 + tid;
+        const long long e = (rowb + t) * 128 + tid;
         dyr[t] = t < T ? p.dy[e] : 0.f;
         float g = dyr[t];
         if (DROP && t < T) g *= dropout_scale(dseed, p.drop.stream + 1, (uint64_t)e, p.drop.thresh, p.drop.inv_keep);
@@ -787,7 +791,7 @@ __global__ void __launch_bounds__(CNT, 1) ca_bwd_kernel(const __grid_constant__ 
     }
     if (tid < NQ) {
         const int h = tid >> 4, t = tid & 15;
-        s_lse[tid] = t < T ? p.lse[((long long)b * CA_H + h) * T + t] : 0.f;
+        s_lse[tid] = t < T ? p.lse[((long long)b * CA_H + h) * Tf + t0 + t] : 0.f;
     }
     fence_proxy_async_smem();
     tc_fence_before_sync();
@@ -810,7 +814,7 @@ __global__ void __launch_bounds__(CNT, 1) ca_bwd_kernel(const __grid_constant__ 
         unsigned short at[TP], qv[TP];
 #pragma unroll
         for (int t = 0; t < TP; ++t) {
-            const long long e = ((long long)b * T + t) * 128 + tid;
+            const long long e = (rowb + t) * 128 + tid;
             at[t] = t < T ? reinterpret_cast<const unsigned short*>(p.attn)[e] : (unsigned short)0;
             qv[t] = t < T ? reinterpret_cast<const unsigned short*>(p.q)[e] : (unsigned short)0;
         }
@@ -861,7 +865,7 @@ __global__ void __launch_bounds__(CNT, 1) ca_bwd_kernel(const __grid_constant__ 
                     const float pr = ex2_approx(fmaf(s[i], sc, -s_lse[c]));
                     float dm = 1.0f;
                     if (DROP)
-                        dm = dropout_scale(dseed, p.drop.stream, (((uint64_t)b * CA_H + h) * T + t) * (uint64_t)M + m, p.drop.thresh,
+                        dm = dropout_scale(dseed, p.drop.stream, (((uint64_t)b * CA_H + h) * Tf + t0 + t) * (uint64_t)M + m, p.drop.thresh,
                                            p.drop.inv_keep);
                     pd = pr * dm;
                     ds = pr * (dp[i] * dm - s_delta[c]) * scale;
@@ -909,6 +913,15 @@ __global__ void __launch_bounds__(CNT, 1) ca_bwd_kernel(const __grid_constant__ 
                 ld_lane32(tmem, warp, (c0 < 128 ? DKC + c0 : DVC + c0 - 128), v);
                 if (kvld) {
                     uint4* gp = reinterpret_cast<uint4*>(drow + c0);
+                    if (p.dkv_accumulate) {   // a later query-row group of the same sample: add to what the earlier ones stored
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float o[8];
+                            unpack8_bf16(gp[i], o);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[8 * i + e] += o[e];
+                        }
+                    }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) gp[i] = pack8_bf16(v + 8 * i);
                 }
@@ -927,7 +940,7 @@ __global__ void __launch_bounds__(CNT, 1) ca_bwd_kernel(const __grid_constant__ 
         for (int t = 0; t < TP; ++t) {
             const unsigned short u = t < T ? bf16_bits(dq[t]) : (unsigned short)0;
             *reinterpret_cast<unsigned short*>(smem + B_OFF_XB + elem_off(t, tid, XB_TILE)) = u;
-            if (t < T && p.dq) reinterpret_cast<unsigned short*>(p.dq)[((long long)b * T + t) * 128 + tid] = u;
+            if (t < T && p.dq) reinterpret_cast<unsigned short*>(p.dq)[(rowb + t) * 128 + tid] = u;
         }
     }
     fence_proxy_async_smem();
@@ -950,7 +963,7 @@ __global__ void __launch_bounds__(CNT, 1) ca_bwd_kernel(const __grid_constant__ 
         const float ga = __ldg(p.n_w + tid);
 #pragma unroll
         for (int t = 0; t < TP; ++t) {
-            const long long grow = (long long)b * T + t;
+            const long long grow = rowb + t;
             xh[t] = t < T ? (p.x[grow * 128 + tid] - p.stats[2 * grow]) * p.stats[2 * grow + 1] : 0.f;
         }
         float dxn[16];
@@ -976,7 +989,7 @@ __global__ void __launch_bounds__(CNT, 1) ca_bwd_kernel(const __grid_constant__ 
 #pragma unroll
         for (int t = 0; t < TP; ++t) {
             if (t < T) {
-                const long long grow = (long long)b * T + t;
+                const long long grow = rowb + t;
                 const float rstd = p.stats[2 * grow + 1];
                 p.dx[grow * 128 + tid] = dyr[t] + rstd * (dxn[t] - fin[t] - xh[t] * fin[16 + t]);
             }
@@ -1034,8 +1047,9 @@ extern "C" int sd_ddim_glue(const float* h, const float* fc_w, const float* fc_b
     return SD_OK;
 }
 
+// forward with saves + backward: as the forward, T <= 64 in query-row groups of <= 16 (the backward runs one launch per group)
 extern "C" int sd_ca_block_supported(int d, int H, int T, int M) {
-    if (d != 128 || H != CA_H || T < 1 || T > TP || M < 1 || M > 128 * MAXCH) return 0;
+    if (d != 128 || H != CA_H || T < 1 || T > 4 * TP || M < 1 || M > 128 * MAXCH) return 0;
     return tensor_map_encoder() != nullptr ? 1 : 0;
 }
 
@@ -1157,9 +1171,6 @@ extern "C" int sd_ca_block_fwd(const sd_ca_block_desc* d, void* stream) {
     if (!d || !d->x || !d->y || !d->w_packed || !d->kv || !d->q_b || !d->out_b || !d->n_w || !d->n_b) return SD_ERR_BAD_ARG;
     if (d->B <= 0) return SD_OK;
     if (!sd_ca_block_fwd_supported(128, 4, d->T, d->M)) return SD_ERR_UNSUPPORTED;
-    // the backward kernel works on whole samples: saves are only produced for T <= 16
-    const bool saves = d->xn_save || d->q_save || d->attn_save || d->stats_save || d->lse_save;
-    if (saves && !sd_ca_block_supported(128, 4, d->T, d->M)) return SD_ERR_UNSUPPORTED;
     if (d->w_row_q < 0 || d->w_row_q + 128 > d->w_rows_total || d->w_row_o < 0 || d->w_row_o + 128 > d->w_rows_total) return SD_ERR_BAD_ARG;
     if (d->kv_col0 < 0 || d->kv_col0 + 256 > d->ldkv || d->kv_col0 % 8 != 0) return SD_ERR_BAD_ARG;
     if (!al16(d->x) || !al16(d->y) || !al16(d->xn_save) || !al16(d->q_save) || !al16(d->attn_save)) return SD_ERR_BAD_ARG;
@@ -1199,6 +1210,14 @@ extern "C" int sd_ca_block_bwd(const sd_ca_block_bwd_desc* d, void* stream) {
     p.g1 = (__nv_bfloat16*)d->g1; p.dq = (__nv_bfloat16*)d->dq; p.dkv = (__nv_bfloat16*)d->dkv; p.lddkv = d->lddkv;
     p.g_n_w = d->g_n_w; p.g_n_b = d->g_n_b;
     p.drop = make_dropout(d->dropout_p, d->dropout_seed, d->dropout_stream);
-    return p.drop.thresh != 0 ? launch_ca_bwd<true>(tmW, tmKV, p, (cudaStream_t)stream)
-                              : launch_ca_bwd<false>(tmW, tmKV, p, (cudaStream_t)stream);
+    const int groups = (d->T + TP - 1) / TP;
+    p.Tg = (d->T + groups - 1) / groups;
+    for (int g = 0; g < groups; ++g) {
+        p.t0 = g * p.Tg;
+        p.dkv_accumulate = g > 0;
+        const int rc = p.drop.thresh != 0 ? launch_ca_bwd<true>(tmW, tmKV, p, (cudaStream_t)stream)
+                                          : launch_ca_bwd<false>(tmW, tmKV, p, (cudaStream_t)stream);
+        if (rc != SD_OK) return rc;
+    }
+    return SD_OK;
 }

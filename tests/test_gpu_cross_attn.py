@@ -153,7 +153,7 @@ def test_ca_block_fwd_dropout_masks(ops, p):
 
 
 @pytest.mark.parametrize("B,T,M,p", [(3, 10, 312, 0.0), (2, 16, 384, 0.0), (4, 7, 128, 0.0), (2, 10, 129, 0.1), (5, 10, 312, 0.1),
-                                     (3, 3, 20, 0.0)])
+                                     (3, 3, 20, 0.0), (3, 20, 322, 0.0), (2, 33, 200, 0.1), (2, 64, 384, 0.0)])
 def test_ca_block_bwd_matches_autograd_of_restatement(ops, B, T, M, p):
     gen = torch.Generator().manual_seed(B * 100 + T + M)
     P = {k: v.cuda() for k, v in make_block(gen).items()}
@@ -284,8 +284,8 @@ def test_tc_sampler_batch_70_matches_fp32_kernels():
 
 @pytest.mark.parametrize("B,T,M,p", [(3, 20, 322, 0.0), (2, 33, 384, 0.0), (2, 64, 100, 0.0), (3, 17, 312, 0.1)])
 def test_ca_block_fwd_inference_row_groups(ops, B, T, M, p):
-    """T > 16 without saves (the scaled-up config's sampler, T = 20): the query rows run in groups of <= 16, one CTA each."""
-    assert ops.ca_block_fwd_supported(D, H, T, M) and not ops.ca_block_supported(D, H, T, M)
+    """T > 16 (the scaled-up config, T = 20): the query rows run in groups of <= 16, one CTA each."""
+    assert ops.ca_block_fwd_supported(D, H, T, M) and ops.ca_block_supported(D, H, T, M)
     gen = torch.Generator().manual_seed(B * 1000 + T * 10 + M)
     P = {k: v.cuda() for k, v in make_block(gen).items()}
     x = torch.randn(B * T, D, generator=gen).cuda()
@@ -297,8 +297,8 @@ def test_ca_block_fwd_inference_row_groups(ops, B, T, M, p):
     want, _ = ca_ref(x, kv.float(), P, B, T, M, m_attn, m_out)
     y, _ = run_fwd(ops, x, kv, 0, P, wp, 0, B, T, M, drop=(p, seed, sid) if p > 0 else None, save=False)
     assert rel(y, want) < 6e-3, rel(y, want)
-    with pytest.raises(Exception):   # saves (training) need whole samples per CTA
-        run_fwd(ops, x, kv, 0, P, wp, 0, B, T, M, save=True)
+    y2, _ = run_fwd(ops, x, kv, 0, P, wp, 0, B, T, M, drop=(p, seed, sid) if p > 0 else None, save=True)
+    assert torch.equal(y2, y)
 
 
 def test_tc_sampler_scaled_config_matches_fp32_kernels():
