@@ -380,6 +380,10 @@ int sd_set_pdl(int on);
  * `reps` repetitions of the MMA sequence (or NULL). */
 int sd_debug_shifted_mma(const void* X, const void* Y, int rows, int shift_a, int lbo_a, int shift_b, int lbo_b, int nblk_b,
                          int ksteps, int use_base_offset, int reps, float* D, long long* cycles, void* stream);
+/* Hardware probe used by tools only: per-warp clock64 ticks (cycles[nwarps]) of `count` TMEM loads run by nwarps <= 16 warps of
+ * one CTA at once (warp w reads lane quadrant w % 4); mode 0: tcgen05.ld.32x32b.x32 + wait each, 1: two such loads in flight,
+ * 2: .x16 loads + wait each.  (use_base_offset bit 2 of sd_debug_shifted_mma runs shift_a loads per warp beside the MMA chain.) */
+int sd_debug_ldtm(int nwarps, int count, int mode, long long* cycles, float* sink, void* stream);
 /* One launch between two denoiser evaluations of the batched DDIM loop (ros.py:301-310; decoder.py:48,54): output
  * projection eps = h fc_w^T + fc_b (h fp32 [rows][128], fc_w [J][128]), the eta=0 update x_next = sap*(x - sb*eps)/sa + sbp*eps
  * (optionally eps_out), the next step's embedding h_next = x_next emb_w^T + emb_b + pe[row % T] (emb_w [128][J]; NULL on

@@ -186,6 +186,7 @@ SIGNATURES = {
     "sd_conv3x3_wgrad_c64_scratch_bytes": [],
     "sd_conv3x3_wgrad_c64_bf16": [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_i, c_f],
     "sd_debug_shifted_mma": [c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_f],
+    "sd_debug_ldtm": [c_i, c_i, c_i, c_f, c_f, c_f],
     "sd_conv1x1s2_dgrad_supported": [c_i, c_i, c_i, c_i],
     "sd_conv1x1s2_dgrad_bf16": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f],
     "sd_ddim_glue": [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_fl, c_fl, c_fl, c_fl, c_f, c_f, c_f, c_i, c_f, c_f, c_ll, c_ll, c_ll,

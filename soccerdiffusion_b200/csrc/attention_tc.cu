@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(NT) attn_tc_fwd_kernel(const AttnTcParams p) {
     const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
     const int T = p.T, M = p.M, dh = p.dh;
     const int Mp = (M + 15) & ~15;
-    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+    if (warp == 0 && elect_one()) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
     if (warp == 0) tmem_alloc(&tmem_slot, 256);
     {   // Qs, Ks, Vs are consecutive tiles
         const StageSrc ops[3] = {{p.Q + (long long)b * T * p.ldq + h * dh, p.ldq, T},
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(NT) attn_tc_fwd_kernel(const AttnTcParams p) {
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = tmem_slot;
-    if (tid == 0) {   // S[t][m] = sum_c Q[t][c] K[m][c]   (both K-major, k = dh)
+    if (warp == 0 && elect_one()) {   // S[t][m] = sum_c Q[t][c] K[m][c]   (both K-major, k = dh)
         const uint32_t idesc = instr_desc_bf16(128, Mp, 0, 0);
         const uint64_t da = smem_desc_k_sw128(smem_u32(Qs)), db = smem_desc_k_sw128(smem_u32(Ks));
         for (int j = 0; j < dh / 16; ++j) mma_bf16_ss(tmem, da + 2 * j, db + 2 * j, idesc, j > 0);
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(NT) attn_tc_fwd_kernel(const AttnTcParams p) {
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    if (tid == 0) {   // O[t][c] = sum_m P[t][m] V[m][c] : A = P K-major (k = m), B = V MN-major (k rows = m)
+    if (warp == 0 && elect_one()) {   // O[t][c] = sum_m P[t][m] V[m][c] : A = P K-major (k = m), B = V MN-major (k rows = m)
         const uint32_t idesc = instr_desc_bf16(128, dh, 0, 1);
         for (int j = 0; j < Mp / 16; ++j) {
             const uint64_t da = smem_desc_k_sw128(smem_u32(Ps + (j >> 2) * TILE)) + 2 * (j & 3);
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(NT) attn_tc_bwd_kernel(const AttnTcParams p) {
     const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
     const int T = p.T, M = p.M, dh = p.dh;
     const int Mp = (M + 15) & ~15, Tp = (T + 15) & ~15;
-    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+    if (warp == 0 && elect_one()) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
     if (warp == 0) tmem_alloc(&tmem_slot, 256);
     const float* Og = p.O + (long long)b * T * p.ldo + h * dh;
     const float* dOg = p.dO + (long long)b * T * p.lddo + h * dh;
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(NT) attn_tc_bwd_kernel(const AttnTcParams p) {
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = tmem_slot;
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
         const uint32_t idesc = instr_desc_bf16(128, Mp, 0, 0);
         const uint64_t dq = smem_desc_k_sw128(smem_u32(Qs)), dk = smem_desc_k_sw128(smem_u32(Ks));
         const uint64_t dg = smem_desc_k_sw128(smem_u32(dOs)), dv = smem_desc_k_sw128(smem_u32(Vs));
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(NT) attn_tc_bwd_kernel(const AttnTcParams p) {
     tc_fence_before_sync();
     __syncthreads();   // every thread has consumed S / dP: their TMEM columns are reused below
     tc_fence_after_sync();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
         const uint32_t id_mn = instr_desc_bf16(128, dh, 1, 1);   // A MN-major (k rows = t), B MN-major
         const uint32_t id_kn = instr_desc_bf16(128, dh, 0, 1);   // A K-major (k = m),     B MN-major
         // dV[m][c] = sum_t P'[t][m] dO[t][c]   -> columns [0, dh)

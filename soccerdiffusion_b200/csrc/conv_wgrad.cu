@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(WG_NT, 1) conv3x3_wgrad_c64_kernel(const __gri
     const int nb = (int)(b1 - b0);
     const int ksteps = WG_BH * Wp / 16;
 
-    if (warp == 0 && lane == 0) {          // ---- TMA producer -------------------------------------------------------------
+    if (warp == 0 && elect_one()) {          // ---- TMA producer -------------------------------------------------------------
         for (int i = 0; i < nb; ++i) {
             const int s = i % WG_STAGES;
             mbar_wait(&bar_empty[s], (uint32_t)(((i / WG_STAGES) & 1) ^ 1));
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(WG_NT, 1) conv3x3_wgrad_c64_kernel(const __gri
             tma_tile_4d(dst, &tmX, 0, -1, h0, n, &bar_full[s]);                 // x rows h0 .. h0+3
             tma_tile_4d(dst + x_bytes, &tmDY, 0, -1, h0 - 1, n, &bar_full[s]);  // dy rows h0-1 .. h0+4
         }
-    } else if (warp == 1 && lane == 0) {   // ---- MMA issuer ---------------------------------------------------------------
+    } else if (warp == 1 && elect_one()) {   // ---- MMA issuer ---------------------------------------------------------------
         const uint32_t idesc = instr_desc_bf16(128, 192, 1, 1);
         for (int i = 0; i < nb; ++i) {
             const int s = i % WG_STAGES;

@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(KP_NT, 1) kv_proj_kernel(const __grid_constant
     const int j = blockIdx.x % p.nblk, g = blockIdx.x / p.nblk, G = gridDim.x / p.nblk;
     const int ntiles_all = (int)((p.rows + 127) / 128);
     const int nt = g < ntiles_all ? (ntiles_all - g + G - 1) / G : 0;   // tiles g, g + G, ...
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
         mbar_init(&bar_w, 1);
         for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 1); }
         mbar_fence_init();
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(KP_NT, 1) kv_proj_kernel(const __grid_constant
     const uint32_t tmem = tmem_slot;
     const uint32_t OFF_A = 4 * LTILE, OFF_C = 8 * LTILE;
 
-    if (warp == 0 && lane == 0) {          // ---- TMA producer: the weight block once, then the A tiles ------------------
+    if (warp == 0 && elect_one()) {          // ---- TMA producer: the weight block once, then the A tiles ------------------
         const int wr = p.w_row0 + j * p.w_stride;
         mbar_arrive_expect_tx(&bar_w, 4 * LTILE);
         tma_tile_2d(sbase, &tmW, 0, wr, &bar_w);                    // tiles [k half][row half]: 256 rows x 64 k contiguous
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(KP_NT, 1) kv_proj_kernel(const __grid_constant
             tma_tile_2d(sbase + OFF_A + s * 2 * LTILE, &tmA, 0, row0, &a_full[s]);
             tma_tile_2d(sbase + OFF_A + s * 2 * LTILE + LTILE, &tmA, 64, row0, &a_full[s]);
         }
-    } else if (warp == 1 && lane == 0) {   // ---- MMA issuer ---------------------------------------------------------------
+    } else if (warp == 1 && elect_one()) {   // ---- MMA issuer ---------------------------------------------------------------
         const uint32_t id256 = instr_desc_bf16(128, 256);
         mbar_wait(&bar_w, 0);
         for (int i = 0; i < nt; ++i) {
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(CNT, 1) mn_gemm_kernel(const __grid_constant__
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long row0 = (long long)blockIdx.x * 128;
     const int N = p.N, stage = LTILE + N * 128;
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
         for (int s = 0; s < KD_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
         mbar_init(&bar_done, 1);
         mbar_fence_init();
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(CNT, 1) mn_gemm_kernel(const __grid_constant__
     tc_fence_after_sync();
     const uint32_t tmem = tmem_slot;
     const int nk = p.ktiles;
-    if (warp == 0 && lane == 0) {          // TMA producer
+    if (warp == 0 && elect_one()) {          // TMA producer
         for (int i = 0; i < nk; ++i) {
             const int s = i % KD_STAGES;
             mbar_wait(&bar_empty[s], (uint32_t)(((i / KD_STAGES) & 1) ^ 1));
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(CNT, 1) mn_gemm_kernel(const __grid_constant__
             tma_tile_2d(dst, &tmA, 64 * i, (int)row0, &bar_full[s]);
             for (int nb = 0; nb < N / 64; ++nb) tma_tile_2d(dst + LTILE + nb * (LTILE / 2), &tmW, 64 * nb, wrow, &bar_full[s]);
         }
-    } else if (warp == 1 && lane == 0) {   // MMA issuer: A K-major, B MN-major ([64 k rows][64 n] blocks 8 KB apart)
+    } else if (warp == 1 && elect_one()) {   // MMA issuer: A K-major, B MN-major ([64 k rows][64 n] blocks 8 KB apart)
         const uint32_t idesc = instr_desc_bf16(128, N, 0, 1);
         for (int i = 0; i < nk; ++i) {
             const int s = i % KD_STAGES;
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(F_NT, 2) ca_fwd_kernel(const __grid_constant__
     const int nch = (M + 127) >> 7;
     const long long krow0 = (long long)b * M;
 
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
         for (int i = 0; i < FB_N; ++i) mbar_init(&bar[i], 1);
         mbar_fence_init();
         tma_prefetch_desc(&tmW);
@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(F_NT, 2) ca_fwd_kernel(const __grid_constant__
     pdl_trigger();
     if (warp == 4) {
         // ---- TMA producer ---------------------------------------------------------------------------------------------------
-        if (lane == 0) {
+        if (elect_one()) {
             for (int item = 0; item <= IT_WO; ++item) {
                 const int s = item & 1;
                 if (item >= 2) mbar_wait(&bar[FB_EMPTY0 + s], (uint32_t)(((item >> 1) & 1) ^ 1));
@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(F_NT, 2) ca_fwd_kernel(const __grid_constant__
     asm volatile("bar.sync 1, 128;" ::: "memory");
     // ---- Q^T[n][t] = Wq[n][:] . xn[t][:] ---------------------------------------------------------------------------------
     const uint32_t id16 = instr_desc_bf16(128, 16);
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
         tc_fence_after_sync();
         wait_item(0);
         mma_k_tiles(tmem + QT, slot_addr(0), LTILE, sbase + F_OFF_XB, XB_TILE, id16, 2, false);
@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(F_NT, 2) ca_fwd_kernel(const __grid_constant__
     asm volatile("bar.sync 1, 128;" ::: "memory");   // Qblk complete; Q^T columns consumed
     // ---- S^T chunks ------------------------------------------------------------------------------------------------------
     const uint32_t id64 = instr_desc_bf16(128, NQ);
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
         tc_fence_after_sync();
         for (int j = 0; j < nch; ++j) {
             wait_item(IT_K + j);
@@ -618,7 +618,7 @@ __global__ void __launch_bounds__(F_NT, 2) ca_fwd_kernel(const __grid_constant__
         fence_proxy_async_smem();
         tc_fence_before_sync();
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tc_fence_after_sync();
             wait_item(IT_V + j);
             const int ks = min(8, (M - 128 * j + 15) >> 4);   // keys beyond M carry zero probabilities
@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(F_NT, 2) ca_fwd_kernel(const __grid_constant__
     tc_fence_before_sync();
     asm volatile("bar.sync 1, 128;" ::: "memory");
     // ---- Y^T[n][t] = Wout[n][:] . attn[t][:] ; y = x + Drop(Y + b) ----------------------------------------------------------
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
         tc_fence_after_sync();
         wait_item(IT_WO);
         mma_k_tiles(tmem + YT, slot_addr(IT_WO), LTILE, sbase + F_OFF_XB, XB_TILE, id16, 2, false);
@@ -737,7 +737,7 @@ __global__ void __launch_bounds__(CNT, 1) ca_bwd_kernel(const __grid_constant__ 
     const int nch = (M + 127) >> 7;
     const long long krow0 = (long long)b * M;
 
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
         for (int i = 0; i < BB_N; ++i) mbar_init(&bar[i], 1);
         mbar_fence_init();
         tma_prefetch_desc(&tmW);
@@ -766,7 +766,7 @@ __global__ void __launch_bounds__(CNT, 1) ca_bwd_kernel(const __grid_constant__ 
         tma_tile_2d(wq_addr, &tmW, 0, p.w_row_q, &bar[BB_WQ]);
         tma_tile_2d(wq_addr + LTILE, &tmW, 64, p.w_row_q, &bar[BB_WQ]);
     };
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
         mbar_arrive_expect_tx(&bar[BB_WO], 2 * LTILE);
         tma_tile_2d(sbase + B_OFF_PD, &tmW, 0, p.w_row_o, &bar[BB_WO]);
         tma_tile_2d(sbase + B_OFF_DS, &tmW, 64, p.w_row_o, &bar[BB_WO]);
@@ -797,7 +797,7 @@ __global__ void __launch_bounds__(CNT, 1) ca_bwd_kernel(const __grid_constant__ 
     tc_fence_before_sync();
     __syncthreads();
     // ---- dattn^T[c][t] = sum_n Wout[n][c] g1[t][n] : A = Wout used MN-major ------------------------------------------------
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
         tc_fence_after_sync();
         mbar_wait(&bar[BB_WO], 0);
         const uint32_t idesc = instr_desc_bf16(128, 16, 1, 0);
@@ -840,7 +840,7 @@ __global__ void __launch_bounds__(CNT, 1) ca_bwd_kernel(const __grid_constant__ 
 #pragma unroll 1
     for (int j = 0; j < nch; ++j) {
         const uint32_t kv = sbase + B_OFF_KV + (j & 1) * 4 * LTILE;
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tc_fence_after_sync();
             mbar_wait(&bar[BB_KV0 + (j & 1)], (uint32_t)((j >> 1) & 1));
             mma_k_tiles(tmem + SC, kv, LTILE, sbase + B_OFF_QB, QB_TILE, id64, 2, false);                  // S^T
@@ -882,7 +882,7 @@ __global__ void __launch_bounds__(CNT, 1) ca_bwd_kernel(const __grid_constant__ 
         fence_proxy_async_smem();
         tc_fence_before_sync();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tc_fence_after_sync();
             const uint32_t id_kn = instr_desc_bf16(128, 128, 0, 1);
             // dV[m][c] = sum_(h,t) Pd^T[m][(h,t)] dOblk[(h,t)][c] ; dK[m][c] = sum dS^T[m][(h,t)] Qblk[(h,t)][c]
@@ -899,7 +899,7 @@ __global__ void __launch_bounds__(CNT, 1) ca_bwd_kernel(const __grid_constant__ 
         __syncwarp();
         mbar_wait(&bar[BB_G], (uint32_t)(j & 1));
         tc_fence_after_sync();
-        if (tid == 0) {   // stage j & 1 is free: it takes the next-but-one chunk, or Wq once no chunk needs it any more
+        if (warp == 0 && elect_one()) {   // stage j & 1 is free: it takes the next-but-one chunk, or Wq once no chunk needs it any more
             if (j + 2 < nch) load_chunk(j + 2);
             else if (j == nch - 2) load_wq();
         }
@@ -947,7 +947,7 @@ __global__ void __launch_bounds__(CNT, 1) ca_bwd_kernel(const __grid_constant__ 
     tc_fence_before_sync();
     __syncthreads();
     // ---- dxn^T[k][t] = sum_c Wq[c][k] dq[t][c] : A = Wq used MN-major ---------------------------------------------------------
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
         tc_fence_after_sync();
         mbar_wait(&bar[BB_WQ], 0);
         const uint32_t idesc = instr_desc_bf16(128, 16, 1, 0);

@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(NT) gemm_tc_kernel(const TcParams p) {
     const int stage_bytes = A_STAGE_BYTES + ((BN + 63) & ~63) * TK * 2;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) mbar_init(&bar_stage[s], 1);
         mbar_init(&bar_done, 1);
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(NT) gemm_tc_kernel(const TcParams p) {
         }
         fence_proxy_async_smem();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tc_fence_after_sync();
             // K-major: +32 bytes of K per step inside the swizzle atom; MN-major: +2 atoms of 8 k-rows (2048 bytes)
             const uint64_t da = A_MN ? smem_desc_mn_sw128(smem_u32(As), TK * 128, 1024) : smem_desc_k_sw128(smem_u32(As));

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(WNT, 2) wgrad_tma_kernel(const __grid_constant
     tc_fence_after_sync();
     const uint32_t tmem = tmem_slot;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0 && elect_one()) {
         for (int i = 0; i < nb; ++i) {
             const int s = i % WSTAGES;
             mbar_wait(&bar_empty[s], (uint32_t)(((i / WSTAGES) & 1) ^ 1));
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(WNT, 2) wgrad_tma_kernel(const __grid_constant
             tma_tile_2d(dst + 2 * BOX, &maps.x[job], p.x_col0[job], row, &bar_full[s]);
             tma_tile_2d(dst + 3 * BOX, &maps.x[job], p.x_col0[job] + 64, row, &bar_full[s]);
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1 && elect_one()) {
         const uint32_t id_w = instr_desc_bf16(128, 128, 1, 1);
         const uint32_t id_b = instr_desc_bf16(128, 16, 1, 1);
         const uint64_t d1 = smem_desc_mn_sw128(smem_u32(ones), BOX, 1024);

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_bwd_kernel(const __grid_cons
     const Lane L;
     const int tid = L.tid, r = L.row, c0 = L.col0;
 
-    if (tid == 0) {
+    if ((L.warp == 0 && elect_one())) {
         for (int i = 0; i < NBAR; ++i) mbar_init(&bar[i], 1);
         mbar_fence_init();
         tma_prefetch_desc(&tmW);
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_bwd_kernel(const __grid_cons
         load_w(1, P3, BW_K);
         load_w(2, P4, BW_V);
     };
-    if (tid == 0) {
+    if ((L.warp == 0 && elect_one())) {
         if (FFN) { load_w(4, P4, BW_W1); load_w(5, P5, BW_W2); } else load_attn_w();
     }
 
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_bwd_kernel(const __grid_cons
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if ((L.warp == 0 && elect_one())) {
         tc_fence_after_sync();
         mbar_wait(&bar[BW_W1], 0);
         mma_k_tiles(tmem + ACC0, sbase + P1, LTILE, sbase + P4, LTILE, id_kk, 2, false);       // hpre = LN2(x1) W1^T
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_bwd_kernel(const __grid_cons
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if ((L.warp == 0 && elect_one())) {
         tc_fence_after_sync();
         mma_a_k_b_mn(tmem + ACC2, sbase + P2, LTILE, sbase + P4, LTILE, id_km, 8, false);      // d(LN2 out) = dhpre W1
         mma_commit(&bar[B_F4]);
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_bwd_kernel(const __grid_cons
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if ((L.warp == 0 && elect_one())) {
         tc_fence_after_sync();
         mbar_wait(&bar[BW_OUT], 0);
         mma_a_k_b_mn(tmem + ACC0, sbase + P0, LTILE, sbase + P5, LTILE, id_km, 8, false);      // dO = g1 Wout
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_bwd_kernel(const __grid_cons
         for (int j = 0; j < dh / 16; ++j) mma_bf16_ss(tmem + ACC1, dg + 2 * j, dv + 2 * j, id_kk, j > 0);   // dP = dO V^T
         mma_commit(&bar[B_SP0 + h]);
     };
-    if (tid == 0) {
+    if ((L.warp == 0 && elect_one())) {
         tc_fence_after_sync();
         issue_SP(0);
     }
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_bwd_kernel(const __grid_cons
         fence_proxy_async_smem();
         tc_fence_before_sync();
         __syncthreads();
-        if (tid == 0) {
+        if ((L.warp == 0 && elect_one())) {
             tc_fence_after_sync();
             // One accumulation chain per loop.  (Interleaving the dV and dK chains instruction by instruction — two
             // accumulators, four descriptors per iteration — produced a wrong result in whichever chain's descriptor
@@ -437,14 +437,14 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_bwd_kernel(const __grid_cons
         fence_proxy_async_smem();
         tc_fence_before_sync();
         __syncthreads();
-        if (tid == 0 && h + 1 < H) {
+        if ((L.warp == 0 && elect_one()) && h + 1 < H) {
             tc_fence_after_sync();
             issue_SP(h + 1);
         }
         __syncwarp();
     }
     // ---- d(LN1 out) = dQ Wq + dK Wk + dV Wv ; LayerNorm-1 backward ------------------------------------------------------------
-    if (tid == 0) {
+    if ((L.warp == 0 && elect_one())) {
         tc_fence_after_sync();
         load_w(0, P0, BW_Q2);   // P' / dS / dO are dead
         load_w(1, P1, BW_K2);

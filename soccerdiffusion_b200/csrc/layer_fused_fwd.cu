@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
     const Lane L;
     const int tid = L.tid, r = L.row, c0 = L.col0;
 
-    if (tid == 0) {
+    if ((L.warp == 0 && elect_one())) {
         for (int i = 0; i < NBAR; ++i) mbar_init(&bar[i], 1);
         mbar_fence_init();
         tma_prefetch_desc(&tmW);
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
         tma_tile_2d(dst, &tmW, 0, row, &bar[BW0 + mi]);
         tma_tile_2d(dst + LTILE, &tmW, 64, row, &bar[BW0 + mi]);
     };
-    if (tid == 0) {
+    if ((L.warp == 0 && elect_one())) {
         if (SA && !FFN_FIRST) { load_w(0); load_w(1); } else { load_w(4); load_w(5); }   // packed weights: written by a non-triggering kernel
     }
     pdl_trigger();
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
     tc_fence_before_sync();
     __syncthreads();
 
-    if (tid == 0) {
+    if ((L.warp == 0 && elect_one())) {
         tc_fence_after_sync();
         mbar_wait(&bar[BW0 + 0], 0);
         mma_k_tiles(tmem + ACC0, sbase + OFF_XN, LTILE, sbase + OFF_W, LTILE, id128, 2, false);   // Q = LN1(x) Wq^T
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
         const float bv = __ldg(p.in_b + 256 + r);
         mbar_wait(&bar[BV], 0);
         tc_fence_after_sync();
-        if (FFN && !FFN_FIRST && tid == 0) load_w(4);   // slot A drained by the V^T MMAs
+        if (FFN && !FFN_FIRST && (L.warp == 0 && elect_one())) load_w(4);   // slot A drained by the V^T MMAs
         __syncwarp();
         ld_acc32(tmem, L, ACC2, v);   // row = feature r, columns = tokens
 #pragma unroll
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
         mma_bf16_ss(tmem + ((h & 1) ? ACC1 : ACC0), du, du, idS, 1u);   // + 1024 on same-sample pairs
         mma_commit(&bar[BS0 + h]);
     };
-    if (tid == 0) {
+    if ((L.warp == 0 && elect_one())) {
         tc_fence_after_sync();
         issue_S(0);
         if (H > 1) issue_S(1);
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
         fence_proxy_async_smem();
         tc_fence_before_sync();
         __syncthreads();
-        if (tid == 0) {
+        if ((L.warp == 0 && elect_one())) {
             tc_fence_after_sync();
             const int hoff = h * dh;
             for (int j = 0; j < Kp16; ++j) {   // O[:, hoff:hoff+dh] = P V_h : A = P (k = key), B = rows hoff.. of V^T
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if ((L.warp == 0 && elect_one())) {
         tc_fence_after_sync();
         mbar_wait(&bar[BW0 + 3], 0);
         mma_k_tiles(tmem + ACC0, sbase + OFF_XN, LTILE, sbase + OFF_W + 2 * LTILE, LTILE, id128, 2, false);
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
         ldg32(p.out_b + c0, b);
         mbar_wait(&bar[BOUT], 0);
         tc_fence_after_sync();
-        if (FFN && !FFN_FIRST && tid == 0) load_w(5);   // slot B drained by the out-projection
+        if (FFN && !FFN_FIRST && (L.warp == 0 && elect_one())) load_w(5);   // slot B drained by the out-projection
         __syncwarp();
         ld_acc32(tmem, L, ACC0, v);
 #pragma unroll
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if ((L.warp == 0 && elect_one())) {
         tc_fence_after_sync();
         mbar_wait(&bar[BW0 + 4], 0);
         mma_k_tiles(tmem + ACC1, sbase + OFF_XN, LTILE, sbase + OFF_W, LTILE, id128, 2, false);   // FC1
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
         ldg32(p.l1_b + c0, b);
         mbar_wait(&bar[BF1], 0);
         tc_fence_after_sync();
-        if (FFN_FIRST && tid == 0) load_w(0);   // slot A drained by FC1: the attention block's Wq
+        if (FFN_FIRST && (L.warp == 0 && elect_one())) load_w(0);   // slot A drained by FC1: the attention block's Wq
         __syncwarp();
         ld_acc32(tmem, L, ACC1, v);
 #pragma unroll
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if ((L.warp == 0 && elect_one())) {
         tc_fence_after_sync();
         mbar_wait(&bar[BW0 + 5], 0);
         mma_k_tiles(tmem + ACC0, sbase + OFF_QS, LTILE, sbase + OFF_W + 2 * LTILE, LTILE, id128, 2, false);   // FC2
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(LNT, 1) enc_layer_fwd_kernel(const __grid_cons
         ldg32(p.l2_b + c0, b);
         mbar_wait(&bar[BF2], 0);
         tc_fence_after_sync();
-        if (FFN_FIRST && tid == 0) load_w(1);   // slot B drained by FC2: the attention block's Wk
+        if (FFN_FIRST && (L.warp == 0 && elect_one())) load_w(1);   // slot B drained by FC2: the attention block's Wk
         __syncwarp();
         ld_acc32(tmem, L, ACC0, v);
         if (FFN_FIRST) {   // the attention block follows: the residual stream stays in registers

@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(NT, 1) stem_wgrad_tma_kernel(const __grid_cons
     const long long r_end = min(rows_total, r_begin + rows_per_cta);
     const int nrows = (int)max(0LL, r_end - r_begin);
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0 && elect_one()) {
         for (int ci = 0; ci < nrows; ++ci) {
             const int s = ci % TMA_STAGES;
             mbar_wait(&bar_empty[s], (uint32_t)(((ci / TMA_STAGES) & 1) ^ 1));
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(NT, 1) stem_wgrad_tma_kernel(const __grid_cons
                 tma_load_2d(base + kh * blk, &tmA, 0, (n * Hp + ho + kh) * Wp, &bar_full[s]);
             tma_load_2d(base + 4 * blk, &tmB, 0, (int)(r * WO), &bar_full[s]);
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1 && elect_one()) {
         // D[64 output channels][256 = (kh, kw, ci)] += dy^T (M = 64, MN-major A) x patches (N = 256: the four filter-row
         // tiles are the four 64-wide MN blocks of ONE MN-major B operand, LBO = blk).  One 64 x 256 x 16 instruction per 16
         // pixels instead of two 128 x 64 x 16: with N = 64 the tensor pipe ran at ~110 clk per instruction (25 % active).
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(NT, 1) stem_wgrad_pair_kernel(const __grid_con
     const int nst = HO + 2;            // stages per image
     const int ntl = HO + 3, ndl = HO + 4;   // patch tiles / dy tiles per image
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0 && elect_one()) {
         // ---- producer: tiles in the order the stages first need them; a slot is refilled once the last stage that read its
         //      previous tile has completed (stages complete in order: one running maximum of waited stages suffices)
         int last_t[RT], last_d[RD];   // global stage of the last read of each slot's tile
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(NT, 1) stem_wgrad_pair_kernel(const __grid_con
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1 && elect_one()) {
         const uint32_t idesc = instr_desc_bf16(128, 128, 1, 1);
         const int ksteps = WO / 16;
         int wt = 0, wdd = 0;           // tiles whose full barrier has been waited for
@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(FNT, 1) stem_fprop_tma_kernel(const __grid_con
     const long long r_end = min(rows_total, r_begin + rows_per_cta);
     const int nrows = (int)max(0LL, r_end - r_begin);
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0 && elect_one()) {
         int g = 0;   // tile sequence number
         long long r = r_begin;
         RowWindow w;
@@ -456,39 +456,54 @@ __global__ void __launch_bounds__(FNT, 1) stem_fprop_tma_kernel(const __grid_con
                 mbar_arrive_expect_tx(&bar_full[s], (uint32_t)blk);
                 tma_load_2d(smem_u32(smem + s * blk), &tmA, 0, (w.n * Hp + t) * Wp, &bar_full[s]);
             }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1 && elect_one()) {
         const uint32_t idesc = instr_desc_bf16(128, 128, 0, 0);
         const uint64_t db01 = smem_desc_k_sw128(smem_u32(Ws)), db23 = smem_desc_k_sw128(smem_u32(Ws) + 2 * 8192);
-        int g = 0, u = 0, v = 0;   // tile / accumulator-slot / output-row sequence numbers
+        int gbase = 0, gready = -1, u = 0, v = 0;   // first tile of the window / last tile waited for / accumulator-slot / output-row sequence numbers
         long long r = r_begin;
         RowWindow w;
+        // This thread issues in program order, so a wait for a free accumulator slot also delays everything behind it.  G1(t)
+        // (which overwrites slot S(t) = S(t-4)) waits for the epilogue of output row t-4, i.e. for G2(t-1) to complete plus the
+        // hand-off latency E ~ 800 clk (commit -> epilogue wake-up -> tcgen05.ld -> barrier -> arrive -> this thread's wake-up).
+        // Issued as G2(t), G1(t) per tile, G2(t+1) sits behind that wait and the loop runs at 628 + E clk per row.  Issued as
+        // G2(t+1), G1(t), the MMA whose completion a wait depends on was issued two iterations earlier: (628 + E) / 3 < 628.
         while (next_window(r, r_end, HO, w)) {
             const int u0 = u;      // S(ho_a)
-            for (int t = w.ho_a; t <= w.ho_b + 3; ++t, ++g) {
-                const int s = g % RING;
-                mbar_wait(&bar_full[s], (uint32_t)((g / RING) & 1));
-                tc_fence_after_sync();
-                const uint64_t da = smem_desc_k_sw128(smem_u32(smem + s * blk));
-                // G2 first: it completes output row t-3 and needs no free slot, so the epilogue of that row (and its release
-                // of a slot) overlaps G1 below instead of sitting between two tiles' MMAs
-                if (t - 2 >= w.ho_a) {            // G2: S(t-2) += P_t [W2;W3]^T
-                    const int us = u0 + (t - 2 - w.ho_a);
+            for (int t = w.ho_a - 1; t <= w.ho_b + 3; ++t) {
+                const int t2 = t + 1;                                  // tile of this iteration's G2
+                if (t2 - 2 >= w.ho_a && t2 <= w.ho_b + 3) {            // G2: S(t2-2) += P_t2 [W2;W3]^T
+                    const int g = gbase + (t2 - w.ho_a);
+                    while (gready < g) {
+                        ++gready;
+                        mbar_wait(&bar_full[gready % RING], (uint32_t)((gready / RING) & 1));
+                    }
+                    tc_fence_after_sync();
+                    const uint64_t da = smem_desc_k_sw128(smem_u32(smem + (g % RING) * blk));
+                    const int us = u0 + (t2 - 2 - w.ho_a);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) mma_bf16_ss(tmem + (us % NACC) * 128, da + 2 * ks, db23 + 2 * ks, idesc, 1u);
+                    if (t2 - 3 >= w.ho_a) {        // output row t2-3 = S(t2-3).lo + S(t2-2).hi is complete
+                        mma_commit(&row_full[v % NACC]);
+                        ++v;
+                    }
                 }
-                if (t - 3 >= w.ho_a) {            // output row t-3 = S(t-3).lo + S(t-2).hi is complete
-                    mma_commit(&row_full[v % NACC]);
-                    ++v;
-                }
+                if (t < w.ho_a) continue;
+                const int g = gbase + (t - w.ho_a);
                 if (t <= w.ho_b + 1) {            // G1: S(t) = P_t [W0;W1]^T
+                    while (gready < g) {
+                        ++gready;
+                        mbar_wait(&bar_full[gready % RING], (uint32_t)((gready / RING) & 1));
+                    }
+                    const uint64_t da = smem_desc_k_sw128(smem_u32(smem + (g % RING) * blk));
                     const int us = u0 + (t - w.ho_a);
                     mbar_wait(&acc_empty[us % NACC], (uint32_t)(((us / NACC) & 1) ^ 1));
                     tc_fence_after_sync();
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) mma_bf16_ss(tmem + (us % NACC) * 128, da + 2 * ks, db01 + 2 * ks, idesc, ks ? 1u : 0u);
                 }
-                mma_commit(&bar_empty[s]);        // the tile is read during this step only
+                mma_commit(&bar_empty[g % RING]);        // both uses of tile t have been issued
             }
+            gbase += w.ho_b - w.ho_a + 4;
             u = u0 + (w.ho_b - w.ho_a + 2);
         }
     } else if (warp >= 4) {
