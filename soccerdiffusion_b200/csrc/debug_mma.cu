@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(128, 1) dbg_shifted_mma_kernel(const __grid_co
                 for (int k = 0; k < p.ksteps; ++k) {
                     mma_bf16_ss(tmem, smem_desc_k_sw128(sbase) + 2 * (k & 3), smem_desc_k_sw128(sbase + LTILE) + 2 * (k & 3), idesc,
                                 (k > 0 || r > 0) ? 1u : 0u);
-                    if (p.shift_b > 0 && ++n % p.shift_b == 0) mma_commit(&bar_x);
+                    if (p.shift_b > 0 && (++n & (p.shift_b - 1)) == 0) mma_commit(&bar_x);   // shift_b: a power of two
                 }
         } else
         for (int r = 0; r < p.reps; ++r)

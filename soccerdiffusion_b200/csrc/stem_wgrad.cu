@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(NT, 1) stem_wgrad_pair_kernel(const __grid_con
 // ---- conv1 forward (space-to-depth form) on the same TMA tensor map: y[p][c] = sum_j patch[p][j] * W[c][j] ------------
 // The patch tile of packed-image row t ([WO pixels][64], the very boxes the weight-gradient kernel loads, read here with
 // K-major descriptors) is the operand of output row t - kh for every filter row kh.  A tcgen05.mma of 128 x 64 x 16 costs
-// no less than one of 128 x 128 x 16 (~94 clk either way, tools/probe_shifted_mma.py), so TWO filter rows share each
+// almost as much as one of 128 x 128 x 16 (55-68 vs 64-67 clk, tools/probe_shifted_mma.py), so TWO filter rows share each
 // instruction: N = 128 = [W_kh ; W_kh+1] (the weight tiles are adjacent in shared memory).  Per input tile t:
 //     G1:  S(t)   = P_t [W0;W1]^T     columns 0..63 -> output row t (kh = 0), columns 64..127 -> output row t-1 (kh = 1)
 //     G2:  S(t-2) += P_t [W2;W3]^T    columns 0..63 -> output row t-2 (kh = 2), columns 64..127 -> output row t-3 (kh = 3)
@@ -462,11 +462,10 @@ __global__ void __launch_bounds__(FNT, 1) stem_fprop_tma_kernel(const __grid_con
         int gbase = 0, gready = -1, u = 0, v = 0;   // first tile of the window / last tile waited for / accumulator-slot / output-row sequence numbers
         long long r = r_begin;
         RowWindow w;
-        // This thread issues in program order, so a wait for a free accumulator slot also delays everything behind it.  G1(t)
+        // This thread issues in program order, so a wait for a free accumulator slot also delays everything behind it: G1(t)
         // (which overwrites slot S(t) = S(t-4)) waits for the epilogue of output row t-4, i.e. for G2(t-1) to complete plus the
-        // hand-off latency E ~ 800 clk (commit -> epilogue wake-up -> tcgen05.ld -> barrier -> arrive -> this thread's wake-up).
-        // Issued as G2(t), G1(t) per tile, G2(t+1) sits behind that wait and the loop runs at 628 + E clk per row.  Issued as
-        // G2(t+1), G1(t), the MMA whose completion a wait depends on was issued two iterations earlier: (628 + E) / 3 < 628.
+        // hand-off (commit -> epilogue wake-up -> tcgen05.ld -> barrier -> arrive -> wake-up here, ~450 + 300 clk).  G2 of the
+        // NEXT tile is therefore issued before that wait: the MMA a wait depends on was issued two iterations earlier.
         while (next_window(r, r_end, HO, w)) {
             const int u0 = u;      // S(ho_a)
             for (int t = w.ho_a - 1; t <= w.ho_b + 3; ++t) {
